@@ -1,0 +1,178 @@
+/*
+ * fs2_b200.h -- C ABI of the B200-native FastSpeech2-align inference forward.
+ *
+ * This is the drop-in boundary for ONE hot path of SMART-TTS/SMART-NAR_Fast_TTS:
+ * `FastSpeech2Align.forward` with `mel_lens=None`
+ * (reference: model/fastspeech2_align.py:30-100).  The reference has no FFI of its
+ * own (it is pure PyTorch), so the entry points below are what a ctypes binding in
+ * the reference's `model/fastspeech2_align.py` would call.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; no torch types.  All tensor pointers are DEVICE
+ *    pointers on the handle's device unless a parameter says "host".
+ *  - tensors are dense row-major fp32 unless stated; ids / lengths are int64 like the
+ *    reference's `texts` / `src_lens` (utils/tools.py:56-63); masks are uint8 (1 = padded),
+ *    the layout of a torch.bool tensor.
+ *  - every function returns FS2_OK (0) or a negative error code, never throws, never
+ *    exits.  `fs2_last_error` gives the message for the last failure on that handle.
+ *  - all work is enqueued on the `stream` argument (a cudaStream_t / CUstream passed as
+ *    void*; NULL = legacy default stream).  The only blocking call is the 4-byte D2H of
+ *    T_max at the end of `fs2_forward_stage1`.
+ *  - a handle is bound to one device and is not thread-safe; separate handles are
+ *    independent.  The library owns packed weights and workspace; the caller owns every
+ *    tensor it passes in or receives results in.
+ */
+#ifndef FS2_B200_H
+#define FS2_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default) /* the only exported symbols of libfs2_b200.so */
+#endif
+
+#define FS2_OK 0
+#define FS2_ERR_INVALID (-1)      /* bad argument */
+#define FS2_ERR_CUDA (-2)         /* CUDA runtime / driver error */
+#define FS2_ERR_STATE (-3)        /* call order violated (weights not loaded, stage2 before stage1) */
+#define FS2_ERR_UNSUPPORTED (-4)  /* dims outside what the kernels are built for */
+#define FS2_ERR_MISSING_WEIGHT (-5)
+#define FS2_ERR_NO_DEVICE (-6)    /* no CUDA device: there is NO CPU fallback */
+
+/* arithmetic used by a segment of the path */
+#define FS2_PREC_FP32 0 /* fp32 FFMA kernels (fp32-faithful; decides durations and pitch/energy buckets) */
+#define FS2_PREC_BF16 1 /* tcgen05 tensor-core kernels: bf16 operands, fp32 accumulate in TMEM */
+
+typedef struct fs2_handle fs2_handle;
+
+/* Model hyper-parameters: config/LJSpeech/model.yaml:1-25, preprocess.yaml:24-32,
+ * PostNet() defaults transformer/Layers.py:112-118, vocab = len(symbols)+1 (Models.py:40). */
+typedef struct fs2_dims {
+  int32_t vocab;         /* 361 */
+  int32_t d_model;       /* 256 (encoder_hidden == decoder_hidden) */
+  int32_t n_enc_layers;  /* 4 */
+  int32_t n_dec_layers;  /* 4 */
+  int32_t n_heads;       /* 2 */
+  int32_t d_ffn;         /* 1024 */
+  int32_t ffn_k1;        /* 9 */
+  int32_t ffn_k2;        /* 1 */
+  int32_t vp_filter;     /* 256 */
+  int32_t vp_kernel;     /* 3 */
+  int32_t n_bins;        /* 256 */
+  int32_t n_mel;         /* 80 */
+  int32_t pn_dim;        /* 512 */
+  int32_t pn_kernel;     /* 5 */
+  int32_t pn_layers;     /* 5 */
+  int32_t max_seq_len;   /* 1000 */
+  int32_t pitch_phoneme_level;  /* 0 = frame_level (LJSpeech), 1 = phoneme_level (modules.py:117-121) */
+  int32_t energy_phoneme_level; /* 0 = frame_level, 1 = phoneme_level (modules.py:122-126) */
+} fs2_dims;
+
+/* One entry of the reference `state_dict` (key list: SURVEY.md section 8(b)). fp32 data. */
+typedef struct fs2_weight_desc {
+  const char* name;   /* e.g. "mel_decoder.layer_stack.0.pos_ffn.w_1.weight" */
+  const void* data;   /* fp32, contiguous */
+  int32_t ndim;
+  int64_t shape[4];
+  int32_t on_device;  /* 1 = device pointer on the handle's device, 0 = host pointer */
+} fs2_weight_desc;
+
+/* ---- lifetime ---------------------------------------------------------------------- */
+/* replaces: FastSpeech2Align.__init__ (model/fastspeech2_align.py:16-28) */
+int fs2_create(fs2_handle** out, const fs2_dims* dims, int device);
+void fs2_destroy(fs2_handle* h);
+const char* fs2_last_error(const fs2_handle* h); /* h may be NULL: last creation error */
+const char* fs2_version(void);
+
+/* replaces: load_state_dict in utils/model.py:16-22.  Copies + repacks (QKV concat,
+ * BatchNorm fold, conv weight -> per-tap K-major bf16 tiles).  `mel_encoder.*`,
+ * `*.num_batches_tracked` are accepted and ignored.  Missing inference keys -> error. */
+int fs2_load_weights(fs2_handle* h, const fs2_weight_desc* descs, int32_t n);
+
+/* encoder_prec covers txt_encoder + all three variance predictors (the discrete
+ * decisions: durations, pitch/energy buckets); decoder_prec covers mel_decoder,
+ * mel_linear and PostNet.  Defaults: FP32 / BF16. */
+int fs2_set_precision(fs2_handle* h, int32_t encoder_prec, int32_t decoder_prec);
+
+/* ---- the forward, in two stages because T = max(sum(durations)) is data dependent --- */
+/* replaces: fastspeech2_align.py:46-53 (src mask, TxtEncoder) + modules.py:116-135
+ * (duration predictor, rounding) + the length bookkeeping of LengthRegulator.LR
+ * (modules.py:201-218).
+ *   texts[B,L] int64 (0 = PAD), src_lens[B] int64
+ *   out: log_d[B,L], d_rounded[B,L] (fp32 integers, bit-exact gate), mel_lens[B] int64,
+ *        src_mask[B,L] uint8, *T_max_out (host int) = max_b mel_lens[b]
+ *   pitch_ph / energy_ph [B,L]: only written when the corresponding *_phoneme_level dim
+ *   is 1 (may be NULL otherwise). */
+int fs2_forward_stage1(fs2_handle* h, const int64_t* texts, const int64_t* src_lens, int32_t B, int32_t L,
+                       float p_control, float e_control, float d_control, float* log_d, float* d_rounded,
+                       int64_t* mel_lens, uint8_t* src_mask, float* pitch_ph, float* energy_ph,
+                       int32_t* T_max_out, void* stream);
+
+/* replaces: LengthRegulator expand/pad (modules.py:220-226, utils/tools.py:288-306),
+ * frame-level pitch/energy (modules.py:137-149), MelDecoder (Models.py:212-244),
+ * mel_linear + PostNet + residual (fastspeech2_align.py:82-85).
+ *   T >= the T_max of stage 1 (a larger T = the batch-global maximum when the batch is
+ *   sharded across GPUs; outputs are then padded exactly like the unsharded reference).
+ *   out: mel[B,T,n_mel], mel_post[B,T,n_mel], pitch[B,T], energy[B,T] (NULL allowed when
+ *   phoneme-level), mel_mask[B,T] uint8. */
+int fs2_forward_stage2(fs2_handle* h, int32_t T, float p_control, float e_control, float* mel, float* mel_post,
+                       float* pitch, float* energy, uint8_t* mel_mask, void* stream);
+
+/* ---- stand-alone operators (no weights) -------------------------------------------- */
+/* modules.py:132-135: out = clamp(round(exp(log_d) - 1) * d_control, min=0); n elements */
+int fs2_round_durations(const float* log_d, int64_t n, float d_control, float* out, void* stream);
+/* modules.py:206-218 bookkeeping: cum[B,L] = inclusive cumsum of max(int(d),0); mel_lens[B];
+ * *T_max_out (host) = max mel_lens.  Blocks on a 4-byte D2H. */
+int fs2_duration_scan(const float* d, int32_t B, int32_t L, int32_t* cum, int64_t* mel_lens, int32_t* T_max_out,
+                      void* stream);
+/* modules.py:220-226 + tools.py:288-306: out[b,t,:] = x[b,i,:] for cum[b,i-1] <= t < cum[b,i], 0 for t >= mel_len */
+int fs2_length_regulate(const float* x, const int32_t* cum, int32_t B, int32_t L, int32_t D, int32_t T, float* out,
+                        void* stream);
+/* modules.py:166-192 GaussianUpsampling (sigma fixed to 10.0 as in :175).  d[B,L] fp32 durations,
+ * T = number of output frames (>= max sum d; frames beyond max-sum are zero like `pad`),
+ * T_w = int(max_b sum d) = extent of the weight tensor.  out[B,T,D]; s[B]; w[B,L,T_w] or NULL. */
+int fs2_gaussian_upsample(const float* x, const float* d, int32_t B, int32_t L, int32_t D, int32_t T, int32_t T_w,
+                          float* out, float* s, float* w, void* stream);
+/* utils/tools.py:89-97: mask[b,i] = i >= lens[b] */
+int fs2_mask_from_lengths(const int64_t* lens, int32_t B, int32_t max_len, uint8_t* mask, void* stream);
+
+/* ---- per-operator entry points on a loaded handle (unit parity tests) --------------- */
+/* Models.py:10-30: table[n_pos, d_model] as the reference builds it (float64 -> float32) */
+int fs2_op_sinusoid_table(fs2_handle* h, int32_t n_pos, float* out, void* stream);
+/* Models.py:82-91: out[B,L,D] = src_word_emb[texts] + PE[:L] */
+int fs2_op_embed_pe(fs2_handle* h, const int64_t* texts, int32_t B, int32_t L, float* out, void* stream);
+/* Layers.py:39-48 x (layer_end-layer_begin): stack 0 = txt_encoder, 1 = mel_decoder. x,out [B,S,D] */
+int fs2_op_fft_stack(fs2_handle* h, int32_t stack, int32_t layer_begin, int32_t layer_end, int32_t prec,
+                     const float* x, const int64_t* lens, int32_t B, int32_t S, float* out, void* stream);
+/* modules.py:278-286: which 0 = duration, 1 = pitch, 2 = energy. x[B,S,D] -> out[B,S] */
+int fs2_op_variance_predictor(fs2_handle* h, int32_t which, const float* x, const int64_t* lens, int32_t B,
+                              int32_t S, float* out, void* stream);
+/* modules.py:80-100 inference branch: pred <- pred*control (in place); idx = bucketize(pred, bins);
+ * x[B,S,D] += embedding[idx]; idx_out[B,S] int32 optional. which 1 = pitch, 2 = energy */
+int fs2_op_variance_embed(fs2_handle* h, int32_t which, float* pred, float control, float* x, int32_t B, int32_t S,
+                          int32_t* idx_out, void* stream);
+/* fastspeech2_align.py:83-85: mel = mel_linear(dec); mel_post = PostNet(mel) + mel. dec[B,T,D] */
+int fs2_op_mel_postnet(fs2_handle* h, int32_t prec, const float* dec, int32_t B, int32_t T, float* mel,
+                       float* mel_post, void* stream);
+/* Raw conv-as-GEMM check: out[R,N] = act(sum_t A[r+t-pad,:] . W[:, :, t]^T + bias), rows laid out as
+ * B utterances of S rows (zero padded outside [0,S)).  W is torch Conv1d layout [N,K,taps].
+ * act: 0 none, 1 relu, 2 tanh.  prec selects the SIMT fp32 or the tcgen05 bf16 kernel. */
+int fs2_op_conv_gemm(int32_t prec, const float* A, const float* W, const float* bias, int32_t B, int32_t S,
+                     int32_t K, int32_t N, int32_t taps, int32_t act, float* out, void* stream);
+/* Modules.py:14-25 on packed heads: q,k,v,out [B,S,H*dk]; keys >= lens[b] masked; rows >= lens[b] zero */
+int fs2_op_attention(int32_t prec, const float* q, const float* k, const float* v, const int64_t* lens, int32_t B,
+                     int32_t S, int32_t H, int32_t dk, float* out, void* stream);
+
+/* number of kernels launched by this handle since creation (bench.py's gpu_launches) */
+int64_t fs2_launch_count(const fs2_handle* h);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+#ifdef __cplusplus
+}
+#endif
+#endif /* FS2_B200_H */

@@ -1,0 +1,440 @@
+"""CPU oracle for the FastSpeech2-align inference forward.  TEST INFRASTRUCTURE ONLY.
+
+This file restates, function by function, the algorithm of the reference's
+inference path (`FastSpeech2Align.forward` with `mel_lens=None`) as plain
+functional torch-CPU fp32 code driven by a `state_dict`.  It exists so that the
+CUDA path can be checked on a machine where `/root/reference` is absent (the
+GPU box).  Only `tests/`, `__graft_entry__.smoke()` and `bench.py`'s
+`cpu_baseline` / `--impl reference` legs may import it; the product package
+never does.
+
+Pinning: the reference ships no tests, golden vectors or checkpoints for this
+path, so the oracle is pinned against outputs of the
+reference module itself: `oracle/gen_golden.py` imports `/root/reference`,
+loads the weights produced by `make_state_dict` below into the reference's own
+`FastSpeech2Align`, runs it, asserts this restatement is bit-identical on the
+same machine, and commits the reference outputs under `tests/golden/`.
+`tests/test_oracle_golden.py` re-checks the restatement against those files.
+
+Every function cites the reference lines it follows (paths relative to
+/root/reference).
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Tuple
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+
+# ----------------------------------------------------------------------------
+# dims / config  (config/LJSpeech/model.yaml:1-25, preprocess.yaml:24-32)
+# ----------------------------------------------------------------------------
+@dataclass
+class Dims:
+    vocab: int = 361            # len(text.symbols) + 1, transformer/Models.py:40
+    d_model: int = 256          # transformer.encoder_hidden == decoder_hidden
+    n_enc_layers: int = 4
+    n_dec_layers: int = 4
+    n_heads: int = 2
+    d_ffn: int = 1024           # transformer.conv_filter_size
+    ffn_k1: int = 9             # transformer.conv_kernel_size[0]
+    ffn_k2: int = 1
+    vp_filter: int = 256        # variance_predictor.filter_size
+    vp_kernel: int = 3
+    n_bins: int = 256
+    n_mel: int = 80
+    pn_dim: int = 512           # PostNet() defaults, transformer/Layers.py:112-118
+    pn_kernel: int = 5
+    pn_layers: int = 5
+    max_seq_len: int = 1000
+    pitch_quantization: str = "log"
+    energy_quantization: str = "linear"
+    pitch_feature: str = "frame_level"
+    energy_feature: str = "frame_level"
+
+
+# stats.json contents used by SURVEY section 8(d): [min, max, mean, std]
+STATS_NAN_BINS = {"pitch": [-2.9, 11.4, 127.0, 110.0], "energy": [-1.4, 8.0, 37.0, 26.0]}
+STATS_FINITE_BINS = {"pitch": [0.5, 11.4, 127.0, 110.0], "energy": [-1.4, 8.0, 37.0, 26.0]}
+
+
+# ----------------------------------------------------------------------------
+# transformer/Models.py:10-30  get_sinusoid_encoding_table
+# ----------------------------------------------------------------------------
+def sinusoid_table(n_position: int, d_hid: int) -> torch.Tensor:
+    """float64 numpy table, even columns sin / odd columns cos, cast to float32.
+
+    The reference builds it with Python list comprehensions; the arithmetic per
+    element is `position / np.power(10000, 2 * (j // 2) / d_hid)` in float64,
+    reproduced here vectorised (gen_golden.py asserts bit equality).
+    """
+    j = np.arange(d_hid)
+    denom = np.power(10000, 2 * (j // 2) / d_hid)            # float64
+    pos = np.arange(n_position, dtype=np.float64)[:, None]
+    tab = pos / denom[None, :]
+    tab[:, 0::2] = np.sin(tab[:, 0::2])
+    tab[:, 1::2] = np.cos(tab[:, 1::2])
+    return torch.from_numpy(tab.astype(np.float32))
+
+
+# ----------------------------------------------------------------------------
+# utils/tools.py:89-97  get_mask_from_lengths  (True = padded)
+# ----------------------------------------------------------------------------
+def get_mask_from_lengths(lengths: torch.Tensor, max_len: Optional[int] = None) -> torch.Tensor:
+    if max_len is None:
+        max_len = int(torch.max(lengths).item())
+    ids = torch.arange(0, max_len).unsqueeze(0).expand(lengths.shape[0], -1)
+    return ids >= lengths.unsqueeze(1).expand(-1, max_len)
+
+
+# ----------------------------------------------------------------------------
+# model/modules.py:41-71  pitch / energy bin boundaries
+# ----------------------------------------------------------------------------
+def make_bins(vmin: float, vmax: float, n_bins: int, quantization: str) -> torch.Tensor:
+    if quantization == "log":
+        with np.errstate(invalid="ignore"):
+            lo, hi = np.log(vmin), np.log(vmax)               # NaN for a negative minimum
+        return torch.exp(torch.linspace(lo, hi, n_bins - 1))
+    return torch.linspace(vmin, vmax, n_bins - 1)
+
+
+# ----------------------------------------------------------------------------
+# weight factory (new; no counterpart in the reference, which ships no checkpoint)
+# ----------------------------------------------------------------------------
+def make_state_dict(seed: int = 0, dims: Optional[Dims] = None, stats: Optional[dict] = None,
+                    frames_per_phoneme: float = 7.67, include_mel_encoder: bool = False
+                    ) -> Dict[str, torch.Tensor]:
+    """Deterministic weights with the reference's `state_dict` key layout
+    (SURVEY.md section 8(b)).  numpy PCG64 so that the values do not depend on the
+    torch version.  Non-trivial LayerNorm / BatchNorm parameters so that folding
+    or affine bugs are visible; duration head biased to ~`frames_per_phoneme`
+    frames per phoneme (SURVEY.md section 8(c) weight recipe)."""
+    d = dims or Dims()
+    stats = stats or STATS_NAN_BINS
+    rng = np.random.Generator(np.random.PCG64(seed))
+    sd: Dict[str, torch.Tensor] = {}
+
+    def uni(shape, fan_in, scale=1.0):
+        b = scale / math.sqrt(fan_in)
+        return torch.from_numpy(rng.uniform(-b, b, size=shape).astype(np.float32))
+
+    def nrm(shape, std=1.0, mean=0.0):
+        return torch.from_numpy((mean + std * rng.standard_normal(size=shape)).astype(np.float32))
+
+    D, F_, H = d.d_model, d.d_ffn, d.n_heads
+
+    def fft_stack(prefix: str, n_layers: int):
+        for i in range(n_layers):
+            p = f"{prefix}.layer_stack.{i}"
+            for nm in ("w_qs", "w_ks", "w_vs", "fc"):
+                sd[f"{p}.slf_attn.{nm}.weight"] = uni((D, D), D)
+                sd[f"{p}.slf_attn.{nm}.bias"] = uni((D,), D)
+            sd[f"{p}.slf_attn.layer_norm.weight"] = nrm((D,), 0.1, 1.0)
+            sd[f"{p}.slf_attn.layer_norm.bias"] = nrm((D,), 0.1)
+            sd[f"{p}.pos_ffn.w_1.weight"] = uni((F_, D, d.ffn_k1), D * d.ffn_k1)
+            sd[f"{p}.pos_ffn.w_1.bias"] = uni((F_,), D * d.ffn_k1)
+            sd[f"{p}.pos_ffn.w_2.weight"] = uni((D, F_, d.ffn_k2), F_ * d.ffn_k2)
+            sd[f"{p}.pos_ffn.w_2.bias"] = uni((D,), F_ * d.ffn_k2)
+            sd[f"{p}.pos_ffn.layer_norm.weight"] = nrm((D,), 0.1, 1.0)
+            sd[f"{p}.pos_ffn.layer_norm.bias"] = nrm((D,), 0.1)
+
+    pe = sinusoid_table(d.max_seq_len + 1, D).unsqueeze(0)
+    sd["txt_encoder.position_enc"] = pe.clone()
+    emb = nrm((d.vocab, D), 1.0)
+    emb[0] = 0.0                                              # padding_idx=0, Models.py:59-61
+    sd["txt_encoder.src_word_emb.weight"] = emb
+    fft_stack("txt_encoder", d.n_enc_layers)
+
+    sd["variance_adaptor.pitch_bins"] = make_bins(stats["pitch"][0], stats["pitch"][1], d.n_bins, d.pitch_quantization)
+    sd["variance_adaptor.energy_bins"] = make_bins(stats["energy"][0], stats["energy"][1], d.n_bins, d.energy_quantization)
+    for which in ("duration", "pitch", "energy"):
+        p = f"variance_adaptor.{which}_predictor"
+        sd[f"{p}.conv_layer.conv1d_1.conv.weight"] = uni((d.vp_filter, D, d.vp_kernel), D * d.vp_kernel)
+        sd[f"{p}.conv_layer.conv1d_1.conv.bias"] = uni((d.vp_filter,), D * d.vp_kernel)
+        sd[f"{p}.conv_layer.layer_norm_1.weight"] = nrm((d.vp_filter,), 0.1, 1.0)
+        sd[f"{p}.conv_layer.layer_norm_1.bias"] = nrm((d.vp_filter,), 0.1)
+        sd[f"{p}.conv_layer.conv1d_2.conv.weight"] = uni((d.vp_filter, d.vp_filter, d.vp_kernel), d.vp_filter * d.vp_kernel)
+        sd[f"{p}.conv_layer.conv1d_2.conv.bias"] = uni((d.vp_filter,), d.vp_filter * d.vp_kernel)
+        sd[f"{p}.conv_layer.layer_norm_2.weight"] = nrm((d.vp_filter,), 0.1, 1.0)
+        sd[f"{p}.conv_layer.layer_norm_2.bias"] = nrm((d.vp_filter,), 0.1)
+        if which == "duration":
+            sd[f"{p}.linear_layer.weight"] = uni((1, d.vp_filter), d.vp_filter, 0.5)
+            sd[f"{p}.linear_layer.bias"] = torch.tensor([math.log(frames_per_phoneme)], dtype=torch.float32)
+        else:
+            # spread predictions over several bins so bucketize is exercised
+            sd[f"{p}.linear_layer.weight"] = uni((1, d.vp_filter), d.vp_filter, 5.0)
+            sd[f"{p}.linear_layer.bias"] = torch.tensor([3.0], dtype=torch.float32)
+    sd["variance_adaptor.pitch_embedding.weight"] = nrm((d.n_bins, D), 1.0)
+    sd["variance_adaptor.energy_embedding.weight"] = nrm((d.n_bins, D), 1.0)
+
+    sd["mel_decoder.position_enc"] = pe.clone()
+    fft_stack("mel_decoder", d.n_dec_layers)
+    sd["mel_linear.weight"] = uni((d.n_mel, D), D)
+    sd["mel_linear.bias"] = uni((d.n_mel,), D)
+
+    chans = [d.n_mel] + [d.pn_dim] * (d.pn_layers - 1) + [d.n_mel]
+    for i in range(d.pn_layers):
+        cin, cout = chans[i], chans[i + 1]
+        p = f"postnet.convolutions.{i}"
+        sd[f"{p}.0.conv.weight"] = uni((cout, cin, d.pn_kernel), cin * d.pn_kernel)
+        sd[f"{p}.0.conv.bias"] = uni((cout,), cin * d.pn_kernel)
+        sd[f"{p}.1.weight"] = nrm((cout,), 0.1, 1.0)
+        sd[f"{p}.1.bias"] = nrm((cout,), 0.1)
+        sd[f"{p}.1.running_mean"] = nrm((cout,), 0.1)
+        sd[f"{p}.1.running_var"] = torch.from_numpy(rng.uniform(0.5, 1.5, size=(cout,)).astype(np.float32))
+        sd[f"{p}.1.num_batches_tracked"] = torch.tensor(0, dtype=torch.long)
+
+    if include_mel_encoder:
+        # training-only aligner (transformer/Models.py:103-173): present in real
+        # checkpoints, must be accepted and ignored by the drop-in.
+        sd["mel_encoder.position_enc"] = pe.clone()
+        sd["mel_encoder.prenet.w_1.weight"] = uni((256, 80), 80)
+        sd["mel_encoder.prenet.w_1.bias"] = uni((256,), 80)
+        sd["mel_encoder.prenet.w_2.weight"] = uni((256, 256), 256)
+        sd["mel_encoder.prenet.w_2.bias"] = uni((256,), 256)
+        for i in range(d.n_dec_layers):
+            p = f"mel_encoder.layer_stack.{i}"
+            for nm in ("w_qs", "w_ks", "w_vs", "fc"):
+                sd[f"{p}.crs_attn.{nm}.weight"] = uni((D, D), D)
+                sd[f"{p}.crs_attn.{nm}.bias"] = uni((D,), D)
+            sd[f"{p}.crs_attn.layer_norm.weight"] = nrm((D,), 0.1, 1.0)
+            sd[f"{p}.crs_attn.layer_norm.bias"] = nrm((D,), 0.1)
+            sd[f"{p}.pos_ffn.w_1.weight"] = uni((F_, D, d.ffn_k1), D * d.ffn_k1)
+            sd[f"{p}.pos_ffn.w_1.bias"] = uni((F_,), D * d.ffn_k1)
+            sd[f"{p}.pos_ffn.w_2.weight"] = uni((D, F_, d.ffn_k2), F_ * d.ffn_k2)
+            sd[f"{p}.pos_ffn.w_2.bias"] = uni((D,), F_ * d.ffn_k2)
+            sd[f"{p}.pos_ffn.layer_norm.weight"] = nrm((D,), 0.1, 1.0)
+            sd[f"{p}.pos_ffn.layer_norm.bias"] = nrm((D,), 0.1)
+    return sd
+
+
+# ----------------------------------------------------------------------------
+# synthetic inputs
+# ----------------------------------------------------------------------------
+def make_inputs(batch: int, len_lo: int, len_hi: int, seed: int = 1, vocab: int = 361
+                ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor, int]:
+    """(speakers[B], texts[B,L] int64 0-padded, src_lens[B] int64, max_src_len)."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    lens = rng.integers(len_lo, len_hi + 1, size=batch).astype(np.int64)
+    L = int(lens.max())
+    texts = np.zeros((batch, L), dtype=np.int64)
+    for b in range(batch):
+        texts[b, : lens[b]] = rng.integers(1, vocab, size=int(lens[b]))
+    return (torch.zeros(batch, dtype=torch.long), torch.from_numpy(texts),
+            torch.from_numpy(lens), L)
+
+
+# ----------------------------------------------------------------------------
+# transformer/Modules.py:14-25 + SubLayers.py:29-59  MultiHeadAttention (eval)
+# ----------------------------------------------------------------------------
+def multi_head_attention(sd, p: str, x: torch.Tensor, key_pad: torch.Tensor, n_head: int) -> torch.Tensor:
+    B, S, D = x.shape
+    dk = D // n_head
+    residual = x
+    q = F.linear(x, sd[f"{p}.w_qs.weight"], sd[f"{p}.w_qs.bias"]).view(B, S, n_head, dk)
+    k = F.linear(x, sd[f"{p}.w_ks.weight"], sd[f"{p}.w_ks.bias"]).view(B, S, n_head, dk)
+    v = F.linear(x, sd[f"{p}.w_vs.weight"], sd[f"{p}.w_vs.bias"]).view(B, S, n_head, dk)
+    q = q.permute(2, 0, 1, 3).contiguous().view(-1, S, dk)
+    k = k.permute(2, 0, 1, 3).contiguous().view(-1, S, dk)
+    v = v.permute(2, 0, 1, 3).contiguous().view(-1, S, dk)
+    mask = key_pad.unsqueeze(1).expand(-1, S, -1).repeat(n_head, 1, 1)
+    attn = torch.bmm(q, k.transpose(1, 2))
+    attn = attn / np.power(dk, 0.5)
+    attn = attn.masked_fill(mask, -np.inf)
+    attn = torch.softmax(attn, dim=2)
+    out = torch.bmm(attn, v)
+    out = out.view(n_head, B, S, dk).permute(1, 2, 0, 3).contiguous().view(B, S, -1)
+    out = F.linear(out, sd[f"{p}.fc.weight"], sd[f"{p}.fc.bias"])
+    return F.layer_norm(out + residual, (D,), sd[f"{p}.layer_norm.weight"], sd[f"{p}.layer_norm.bias"], 1e-5)
+
+
+# transformer/SubLayers.py:87-95  PositionwiseFeedForward (eval)
+def positionwise_ffn(sd, p: str, x: torch.Tensor) -> torch.Tensor:
+    D = x.shape[-1]
+    w1, w2 = sd[f"{p}.w_1.weight"], sd[f"{p}.w_2.weight"]
+    out = x.transpose(1, 2)
+    out = F.conv1d(out, w1, sd[f"{p}.w_1.bias"], padding=(w1.shape[2] - 1) // 2)
+    out = F.conv1d(F.relu(out), w2, sd[f"{p}.w_2.bias"], padding=(w2.shape[2] - 1) // 2)
+    out = out.transpose(1, 2)
+    return F.layer_norm(out + x, (D,), sd[f"{p}.layer_norm.weight"], sd[f"{p}.layer_norm.bias"], 1e-5)
+
+
+# transformer/Layers.py:39-48  FFTBlock
+def fft_block(sd, p: str, x: torch.Tensor, pad_mask: torch.Tensor, n_head: int) -> torch.Tensor:
+    x = multi_head_attention(sd, f"{p}.slf_attn", x, pad_mask, n_head)
+    x = x.masked_fill(pad_mask.unsqueeze(-1), 0)
+    x = positionwise_ffn(sd, f"{p}.pos_ffn", x)
+    return x.masked_fill(pad_mask.unsqueeze(-1), 0)
+
+
+# transformer/Models.py:73-100  TxtEncoder.forward (eval)
+def txt_encoder(sd, d: Dims, texts: torch.Tensor, pad_mask: torch.Tensor) -> torch.Tensor:
+    B, L = texts.shape
+    emb = F.embedding(texts, sd["txt_encoder.src_word_emb.weight"])
+    if L > d.max_seq_len:
+        x = emb + sinusoid_table(L, d.d_model)[:L, :].unsqueeze(0).expand(B, -1, -1)
+    else:
+        x = emb + sd["txt_encoder.position_enc"][:, :L, :].expand(B, -1, -1)
+    for i in range(d.n_enc_layers):
+        x = fft_block(sd, f"txt_encoder.layer_stack.{i}", x, pad_mask, d.n_heads)
+    return x
+
+
+# transformer/Models.py:212-244  MelDecoder.forward (eval)
+def mel_decoder(sd, d: Dims, x: torch.Tensor, pad_mask: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    B, T, _ = x.shape
+    if T > d.max_seq_len:
+        x = x + sinusoid_table(T, d.d_model)[:T, :].unsqueeze(0).expand(B, -1, -1)
+    else:
+        x = x + sd["mel_decoder.position_enc"][:, :T, :].expand(B, -1, -1)
+    for i in range(d.n_dec_layers):
+        x = fft_block(sd, f"mel_decoder.layer_stack.{i}", x, pad_mask, d.n_heads)
+    return x, pad_mask
+
+
+# model/modules.py:278-286 (+ Conv :327-332)  VariancePredictor.forward (eval)
+def variance_predictor(sd, p: str, x: torch.Tensor, pad_mask: Optional[torch.Tensor]) -> torch.Tensor:
+    w1, w2 = sd[f"{p}.conv_layer.conv1d_1.conv.weight"], sd[f"{p}.conv_layer.conv1d_2.conv.weight"]
+    C = w1.shape[0]
+    h = F.conv1d(x.transpose(1, 2), w1, sd[f"{p}.conv_layer.conv1d_1.conv.bias"], padding=(w1.shape[2] - 1) // 2).transpose(1, 2)
+    h = F.layer_norm(F.relu(h), (C,), sd[f"{p}.conv_layer.layer_norm_1.weight"], sd[f"{p}.conv_layer.layer_norm_1.bias"], 1e-5)
+    h = F.conv1d(h.transpose(1, 2), w2, sd[f"{p}.conv_layer.conv1d_2.conv.bias"], padding=1).transpose(1, 2)
+    h = F.layer_norm(F.relu(h), (C,), sd[f"{p}.conv_layer.layer_norm_2.weight"], sd[f"{p}.conv_layer.layer_norm_2.bias"], 1e-5)
+    out = F.linear(h, sd[f"{p}.linear_layer.weight"], sd[f"{p}.linear_layer.bias"]).squeeze(-1)
+    if pad_mask is not None:
+        out = out.masked_fill(pad_mask, 0.0)
+    return out
+
+
+# model/modules.py:132-135  duration rounding
+def round_durations(log_d: torch.Tensor, d_control: float = 1.0) -> torch.Tensor:
+    return torch.clamp(torch.round(torch.exp(log_d) - 1) * d_control, min=0)
+
+
+# model/modules.py:201-230 + utils/tools.py:288-306  LengthRegulator
+def length_regulate(x: torch.Tensor, duration: torch.Tensor, max_len: Optional[int] = None
+                    ) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Row i of utterance b repeated max(int(d[b,i]), 0) times; utterances
+    zero-padded to `max_len` or the batch maximum.  Vectorised with
+    repeat_interleave (same result as the reference's per-phoneme expand/cat)."""
+    B, L, D = x.shape
+    reps = torch.clamp(duration.to(torch.int64), min=0)       # int() truncates toward zero
+    mel_len = reps.sum(dim=1)
+    T = int(max_len) if max_len else int(mel_len.max().item()) if B > 0 else 0
+    out = x.new_zeros(B, T, D)
+    for b in range(B):
+        e = torch.repeat_interleave(x[b], reps[b], dim=0)
+        out[b, : e.shape[0]] = e
+    return out, mel_len
+
+
+# model/modules.py:166-192  GaussianUpsampling.forward (dead code in the reference; required by north_star)
+def gaussian_upsample(x: torch.Tensor, durations: torch.Tensor, max_len: Optional[int] = None
+                      ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """The `range_outputs` argument of the reference is overwritten by 10.0 (:175)
+    so it is not an input here.  Returns (out[B,T,D], s[B,1], w[B,L,T])."""
+    s = torch.sum(durations, dim=-1, keepdim=True)
+    e = torch.cumsum(durations, dim=-1).float()
+    c = (e - 0.5 * durations).unsqueeze(-1)
+    t = torch.arange(0, torch.max(s)).unsqueeze(0).unsqueeze(1)
+    r = 10.0
+    w_1 = torch.exp(-(r ** -2) * ((t - c) ** 2))
+    w_2 = torch.sum(torch.exp(-(r ** -2) * ((t - c) ** 2)), dim=1, keepdim=True) + 1e-20
+    w = w_1 / w_2
+    out = torch.matmul(w.transpose(1, 2), x)
+    T = out.shape[1]
+    if max_len:
+        out = F.pad(out, (0, 0, 0, max_len - T), "constant", 0.0)
+    return out, s, w
+
+
+# transformer/Layers.py:169-177  PostNet.forward (eval; BatchNorm1d with running stats)
+def postnet(sd, d: Dims, mel: torch.Tensor) -> torch.Tensor:
+    x = mel.contiguous().transpose(1, 2)
+    for i in range(d.pn_layers):
+        p = f"postnet.convolutions.{i}"
+        w = sd[f"{p}.0.conv.weight"]
+        x = F.conv1d(x, w, sd[f"{p}.0.conv.bias"], padding=int((w.shape[2] - 1) / 2))
+        x = F.batch_norm(x, sd[f"{p}.1.running_mean"], sd[f"{p}.1.running_var"],
+                         sd[f"{p}.1.weight"], sd[f"{p}.1.bias"], False, 0.1, 1e-5)
+        if i < d.pn_layers - 1:
+            x = torch.tanh(x)
+    return x.contiguous().transpose(1, 2)
+
+
+# model/modules.py:80-100  get_pitch_embedding / get_energy_embedding (inference branch)
+def variance_embedding(sd, which: str, x: torch.Tensor, pad_mask, control: float):
+    pred = variance_predictor(sd, f"variance_adaptor.{which}_predictor", x, pad_mask)
+    pred = pred * control
+    idx = torch.bucketize(pred, sd[f"variance_adaptor.{which}_bins"])
+    return pred, F.embedding(idx, sd[f"variance_adaptor.{which}_embedding.weight"]), idx
+
+
+@dataclass
+class Trace:
+    """Intermediates for per-op parity tests."""
+    enc_out: Optional[torch.Tensor] = None
+    lr_out: Optional[torch.Tensor] = None
+    pitch_idx: Optional[torch.Tensor] = None
+    energy_idx: Optional[torch.Tensor] = None
+    adaptor_out: Optional[torch.Tensor] = None
+    dec_out: Optional[torch.Tensor] = None
+
+
+# model/modules.py:102-159  VarianceAdaptor.forward (inference: all targets None)
+def variance_adaptor(sd, d: Dims, x, src_mask, p_control=1.0, e_control=1.0, d_control=1.0,
+                     trace: Optional[Trace] = None, force_durations: Optional[torch.Tensor] = None):
+    log_d = variance_predictor(sd, "variance_adaptor.duration_predictor", x, src_mask)
+    if d.pitch_feature == "phoneme_level":
+        p_pred, p_emb, p_idx = variance_embedding(sd, "pitch", x, src_mask, p_control)
+        x = x + p_emb
+    if d.energy_feature == "phoneme_level":
+        e_pred, e_emb, e_idx = variance_embedding(sd, "energy", x, src_mask, e_control)
+        x = x + e_emb
+    d_rounded = round_durations(log_d, d_control) if force_durations is None else force_durations
+    x, mel_len = length_regulate(x, d_rounded, None)
+    mel_mask = get_mask_from_lengths(mel_len)
+    if trace is not None:
+        trace.lr_out = x
+    if d.pitch_feature == "frame_level":
+        p_pred, p_emb, p_idx = variance_embedding(sd, "pitch", x, mel_mask, p_control)
+        x = x + p_emb
+    if d.energy_feature == "frame_level":
+        e_pred, e_emb, e_idx = variance_embedding(sd, "energy", x, mel_mask, e_control)
+        x = x + e_emb
+    if trace is not None:
+        trace.pitch_idx, trace.energy_idx, trace.adaptor_out = p_idx, e_idx, x
+    return x, p_pred, e_pred, log_d, d_rounded, mel_len, mel_mask
+
+
+# model/fastspeech2_align.py:30-100  FastSpeech2Align.forward (mel_lens=None)
+@torch.no_grad()
+def forward(sd, d: Dims, speakers, texts, src_lens, max_src_len, p_control=1.0, e_control=1.0,
+            trace: Optional[Trace] = None, force_durations: Optional[torch.Tensor] = None):
+    """Returns the reference's 12-tuple.  `speakers` is ignored (no speaker
+    embedding exists in the reference).  `force_durations` (test hook, not in the
+    reference) replaces d_rounded so downstream stages can be compared on
+    identical shapes."""
+    src_masks = get_mask_from_lengths(src_lens, int(max_src_len))
+    enc = txt_encoder(sd, d, texts, src_masks)
+    if trace is not None:
+        trace.enc_out = enc
+    (x, p_pred, e_pred, log_d, d_rounded, mel_lens, mel_masks) = variance_adaptor(
+        sd, d, enc, src_masks, p_control, e_control, 1.0, trace, force_durations)
+    dec, mel_masks = mel_decoder(sd, d, x, mel_masks)
+    if trace is not None:
+        trace.dec_out = dec
+    mel = F.linear(dec, sd["mel_linear.weight"], sd["mel_linear.bias"])
+    post = postnet(sd, d, mel) + mel
+    return (mel, post, p_pred, e_pred, log_d, d_rounded, src_masks, mel_masks, src_lens, mel_lens, None, None)
+
+
+def duration_margin(log_d: torch.Tensor) -> torch.Tensor:
+    """|frac(exp(log_d) - 1) - 0.5|: distance of each duration from a rounding
+    boundary (SURVEY.md section 8(d) parity gates)."""
+    v = torch.exp(log_d.double()) - 1.0
+    return (v - torch.floor(v) - 0.5).abs()

@@ -1,0 +1,77 @@
+"""Build the C-ABI shared library in-tree with nvcc for sm_100a (no torch headers involved).
+
+    python smart-nar_fast_tts_b200/build.py [--force]
+
+Output: smart-nar_fast_tts_b200/libfs2_b200.so  (git-ignored; travels to the GPU box with the snapshot).
+"""
+from __future__ import annotations
+
+import hashlib
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB = os.path.join(HERE, "libfs2_b200.so")
+STAMP = os.path.join(HERE, "build", "stamp.txt")
+SOURCES = ["fs2_api.cu", "fs2_rowops.cu", "fs2_simt_gemm.cu", "fs2_simt_attn.cu", "fs2_tc_gemm.cu", "fs2_tc_attn.cu"]
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
+    "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr",
+    "-Xptxas", "-v",
+]
+
+
+def _nvcc() -> str:
+    for cand in (os.environ.get("NVCC"), "/usr/local/cuda/bin/nvcc", "nvcc"):
+        if cand and (os.path.isabs(cand) and os.path.exists(cand) or not os.path.isabs(cand)):
+            return cand
+    raise RuntimeError("nvcc not found")
+
+
+def _digest() -> str:
+    h = hashlib.sha256()
+    for root in (CSRC, os.path.join(HERE, "..", "include")):
+        for fn in sorted(os.listdir(root)):
+            if fn.endswith((".cu", ".cuh", ".h")):
+                h.update(fn.encode())
+                h.update(open(os.path.join(root, fn), "rb").read())
+    h.update(" ".join(NVCC_FLAGS).encode())
+    return h.hexdigest()
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile every .cu for sm_100a and link libfs2_b200.so.  Returns the library path."""
+    dig = _digest()
+    if not force and os.path.exists(LIB) and os.path.exists(STAMP) and open(STAMP).read().strip() == dig:
+        return LIB
+    os.makedirs(os.path.join(HERE, "build"), exist_ok=True)
+    nvcc = _nvcc()
+    objs = []
+    procs = []
+    for src in SOURCES:
+        obj = os.path.join(HERE, "build", src.replace(".cu", ".o"))
+        objs.append(obj)
+        cmd = [nvcc, *NVCC_FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
+        procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    log = []
+    failed = False
+    for src, p in procs:
+        out, _ = p.communicate()
+        log.append(f"==== {src}\n{out}")
+        if p.returncode != 0:
+            failed = True
+    open(os.path.join(HERE, "build", "nvcc.log"), "w").write("\n".join(log))
+    if failed or verbose:
+        sys.stderr.write("\n".join(log))
+    if failed:
+        raise RuntimeError("nvcc failed; see smart-nar_fast_tts_b200/build/nvcc.log")
+    link = [nvcc, "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static"]
+    subprocess.run(link, check=True)
+    open(STAMP, "w").write(dig)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -1,0 +1,847 @@
+// fs2_api.cu -- C ABI (include/fs2_b200.h): handle, weight repacking, workspace and the
+// two-stage orchestration of FastSpeech2Align.forward (inference branch,
+// reference model/fastspeech2_align.py:30-100).  No torch types, no CPU compute path:
+// every function needs a CUDA device and fails with FS2_ERR_NO_DEVICE / FS2_ERR_CUDA otherwise.
+#include "fs2_common.cuh"
+#include "../../include/fs2_b200.h"
+
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+#include <map>
+#include <string>
+#include <vector>
+
+static thread_local std::string g_last_error;  // creation-time / handle-less errors
+
+int fs2_fail_cuda(cudaError_t e, const char* what) {
+  char buf[512];
+  snprintf(buf, sizeof buf, "CUDA error %d (%s) at %s", (int)e, cudaGetErrorString(e), what);
+  g_last_error = buf;
+  return FS2_ERR_CUDA;
+}
+
+namespace {
+
+struct RawT {
+  float* d = nullptr;
+  std::vector<int64_t> shape;
+  int64_t numel = 0;
+};
+
+struct GemmW {
+  float* wf = nullptr;  // [taps][K][N]
+  bf16* wb = nullptr;   // [taps][N][K]
+  float* bias = nullptr;
+  int N = 0, K = 0, taps = 1;
+};
+struct FftW {
+  GemmW qkv, fc, w1, w2;
+  float *ln1_g = nullptr, *ln1_b = nullptr, *ln2_g = nullptr, *ln2_b = nullptr;
+};
+struct PredW {
+  GemmW c1, c2;
+  float *ln1_g = nullptr, *ln1_b = nullptr, *ln2_g = nullptr, *ln2_b = nullptr, *lin_w = nullptr;
+  float lin_b = 0.f;
+};
+
+}  // namespace
+
+struct fs2_handle {
+  fs2_dims dims{};
+  int device = 0;
+  int prec_enc = FS2_PREC_FP32, prec_dec = FS2_PREC_BF16;
+  bool loaded = false;
+  std::string err;
+  std::map<std::string, RawT> raw;
+  std::vector<void*> owned;  // packed weight allocations
+  std::vector<FftW> enc, dec;
+  PredW pred[3];
+  GemmW mel_linear;
+  std::vector<GemmW> postnet;
+  float* pe_ext[2] = {nullptr, nullptr};  // on-the-fly tables for S > max_seq_len (encoder / decoder)
+  int pe_ext_n[2] = {0, 0};
+  std::map<std::string, std::pair<void*, size_t>> ws;  // growable workspace
+  int* host_tmax = nullptr;                            // pinned
+  // stage-1 -> stage-2 state
+  bool have_stage1 = false;
+  int st_B = 0, st_L = 0, st_LA = 0, st_Tmax = 0;
+  float* st_enc_out = nullptr;  // grid [B*LA, D]
+
+  int fail(int code, const std::string& m) {
+    err = m;
+    g_last_error = m;
+    return code;
+  }
+  int cuda_fail(cudaError_t e, const char* what) {
+    int rc = fs2_fail_cuda(e, what);
+    err = g_last_error;
+    return rc;
+  }
+  void* ensure(const std::string& name, size_t bytes) {
+    auto it = ws.find(name);
+    if (it != ws.end() && it->second.second >= bytes) return it->second.first;
+    if (it != ws.end()) {
+      cudaFree(it->second.first);
+      ws.erase(it);
+    }
+    size_t cap = bytes + bytes / 4 + 256;
+    void* p = nullptr;
+    if (cudaMalloc(&p, cap) != cudaSuccess) return nullptr;
+    // fresh workspace is zeroed once so that no kernel can ever multiply a masked 0 with a NaN bit pattern
+    if (cudaMemset(p, 0, cap) != cudaSuccess) { cudaFree(p); return nullptr; }
+    ws[name] = {p, cap};
+    return p;
+  }
+};
+
+#define HCHECK(expr)                                         \
+  do {                                                       \
+    cudaError_t _e = (expr);                                 \
+    if (_e != cudaSuccess) return h->cuda_fail(_e, #expr);   \
+  } while (0)
+#define RCHECK(expr)          \
+  do {                        \
+    int _rc = (expr);         \
+    if (_rc != FS2_OK) return _rc; \
+  } while (0)
+#define WS(T, var, name, count)                                                   \
+  T* var = reinterpret_cast<T*>(h->ensure(name, sizeof(T) * (size_t)(count)));    \
+  if (!var) return h->fail(FS2_ERR_CUDA, std::string("workspace allocation failed: ") + name)
+
+namespace {
+
+const float* raw_ptr(fs2_handle* h, const std::string& k) {
+  auto it = h->raw.find(k);
+  return it == h->raw.end() ? nullptr : it->second.d;
+}
+
+int need(fs2_handle* h, const std::string& k, std::initializer_list<int64_t> shape, const float** out) {
+  auto it = h->raw.find(k);
+  if (it == h->raw.end()) return h->fail(FS2_ERR_MISSING_WEIGHT, "missing state_dict key: " + k);
+  std::vector<int64_t> want(shape);
+  if (it->second.shape != want) {
+    std::string m = "bad shape for " + k + ": got [";
+    for (auto v : it->second.shape) m += std::to_string(v) + ",";
+    m += "] want [";
+    for (auto v : want) m += std::to_string(v) + ",";
+    return h->fail(FS2_ERR_INVALID, m + "]");
+  }
+  *out = it->second.d;
+  return FS2_OK;
+}
+
+template <typename T>
+int dev_alloc(fs2_handle* h, T** p, size_t count) {
+  void* q = nullptr;
+  cudaError_t e = cudaMalloc(&q, sizeof(T) * (count ? count : 1));
+  if (e != cudaSuccess) return h->cuda_fail(e, "cudaMalloc(packed weight)");
+  h->owned.push_back(q);
+  *p = reinterpret_cast<T*>(q);
+  return FS2_OK;
+}
+
+// Build one GEMM weight from `parts` torch tensors [N_i, K, taps] stacked along N (QKV concat).
+int build_gemm(fs2_handle* h, GemmW& g, const std::vector<std::string>& wkeys, const std::vector<std::string>& bkeys,
+               int N_each, int K, int taps, const float* scale, const float* bias_override, cudaStream_t st) {
+  const int parts = (int)wkeys.size();
+  g.N = N_each * parts;
+  g.K = K;
+  g.taps = taps;
+  RCHECK(dev_alloc(h, &g.wf, (size_t)taps * K * g.N));
+  RCHECK(dev_alloc(h, &g.wb, (size_t)taps * K * g.N));
+  RCHECK(dev_alloc(h, &g.bias, (size_t)g.N));
+  for (int i = 0; i < parts; ++i) {
+    const float* w = nullptr;
+    if (taps == 1 && h->raw.count(wkeys[i]) && h->raw[wkeys[i]].shape.size() == 2)
+      RCHECK(need(h, wkeys[i], {N_each, K}, &w));
+    else
+      RCHECK(need(h, wkeys[i], {N_each, K, taps}, &w));
+    HCHECK(rowops_pack_weight(w, N_each, K, taps, scale, g.wf, g.wb, g.N, i * N_each, st));
+    if (bias_override) {
+      HCHECK(cudaMemcpyAsync(g.bias + i * N_each, bias_override, sizeof(float) * N_each, cudaMemcpyDeviceToDevice, st));
+    } else {
+      const float* b = nullptr;
+      RCHECK(need(h, bkeys[i], {N_each}, &b));
+      HCHECK(cudaMemcpyAsync(g.bias + i * N_each, b, sizeof(float) * N_each, cudaMemcpyDeviceToDevice, st));
+    }
+  }
+  return FS2_OK;
+}
+
+int build_fft(fs2_handle* h, FftW& L, const std::string& p, cudaStream_t st) {
+  const int D = h->dims.d_model, F = h->dims.d_ffn;
+  const std::string a = p + ".slf_attn.", f = p + ".pos_ffn.";
+  RCHECK(build_gemm(h, L.qkv, {a + "w_qs.weight", a + "w_ks.weight", a + "w_vs.weight"},
+                    {a + "w_qs.bias", a + "w_ks.bias", a + "w_vs.bias"}, D, D, 1, nullptr, nullptr, st));
+  RCHECK(build_gemm(h, L.fc, {a + "fc.weight"}, {a + "fc.bias"}, D, D, 1, nullptr, nullptr, st));
+  RCHECK(build_gemm(h, L.w1, {f + "w_1.weight"}, {f + "w_1.bias"}, F, D, h->dims.ffn_k1, nullptr, nullptr, st));
+  RCHECK(build_gemm(h, L.w2, {f + "w_2.weight"}, {f + "w_2.bias"}, D, F, h->dims.ffn_k2, nullptr, nullptr, st));
+  const float* t = nullptr;
+  RCHECK(need(h, a + "layer_norm.weight", {D}, &t)); L.ln1_g = const_cast<float*>(t);
+  RCHECK(need(h, a + "layer_norm.bias", {D}, &t));   L.ln1_b = const_cast<float*>(t);
+  RCHECK(need(h, f + "layer_norm.weight", {D}, &t)); L.ln2_g = const_cast<float*>(t);
+  RCHECK(need(h, f + "layer_norm.bias", {D}, &t));   L.ln2_b = const_cast<float*>(t);
+  return FS2_OK;
+}
+
+int build_pred(fs2_handle* h, PredW& P, const std::string& p, cudaStream_t st) {
+  const int D = h->dims.d_model, C = h->dims.vp_filter, k = h->dims.vp_kernel;
+  const std::string c = p + ".conv_layer.";
+  RCHECK(build_gemm(h, P.c1, {c + "conv1d_1.conv.weight"}, {c + "conv1d_1.conv.bias"}, C, D, k, nullptr, nullptr, st));
+  RCHECK(build_gemm(h, P.c2, {c + "conv1d_2.conv.weight"}, {c + "conv1d_2.conv.bias"}, C, C, k, nullptr, nullptr, st));
+  const float* t = nullptr;
+  RCHECK(need(h, c + "layer_norm_1.weight", {C}, &t)); P.ln1_g = const_cast<float*>(t);
+  RCHECK(need(h, c + "layer_norm_1.bias", {C}, &t));   P.ln1_b = const_cast<float*>(t);
+  RCHECK(need(h, c + "layer_norm_2.weight", {C}, &t)); P.ln2_g = const_cast<float*>(t);
+  RCHECK(need(h, c + "layer_norm_2.bias", {C}, &t));   P.ln2_b = const_cast<float*>(t);
+  RCHECK(need(h, p + ".linear_layer.weight", {1, C}, &t)); P.lin_w = const_cast<float*>(t);
+  RCHECK(need(h, p + ".linear_layer.bias", {1}, &t));
+  HCHECK(cudaMemcpyAsync(&P.lin_b, t, sizeof(float), cudaMemcpyDeviceToHost, st));
+  HCHECK(cudaStreamSynchronize(st));
+  return FS2_OK;
+}
+
+// transformer/Models.py:10-30 in float64 on the host (libm), cast to fp32, uploaded.
+int sinusoid_table_host(fs2_handle* h, int n_pos, int D, float* dev_out, cudaStream_t st) {
+  std::vector<float> tab((size_t)n_pos * D);
+  std::vector<double> denom(D);
+  for (int j = 0; j < D; ++j) denom[j] = pow(10000.0, 2.0 * (double)(j / 2) / (double)D);
+  for (int p = 0; p < n_pos; ++p)
+    for (int j = 0; j < D; ++j) {
+      const double ang = (double)p / denom[j];
+      tab[(size_t)p * D + j] = (float)((j & 1) ? cos(ang) : sin(ang));
+    }
+  HCHECK(cudaMemcpyAsync(dev_out, tab.data(), sizeof(float) * tab.size(), cudaMemcpyHostToDevice, st));
+  HCHECK(cudaStreamSynchronize(st));  // `tab` is pageable and dies at return
+  return FS2_OK;
+}
+
+// position table for a stack (0 = encoder, 1 = decoder) covering S positions (Models.py:82-91, 218-233)
+int position_table(fs2_handle* h, int stack, int S, const float** out, cudaStream_t st) {
+  const int D = h->dims.d_model;
+  if (S <= h->dims.max_seq_len) {
+    *out = raw_ptr(h, stack == 0 ? "txt_encoder.position_enc" : "mel_decoder.position_enc");
+    return FS2_OK;
+  }
+  if (h->pe_ext_n[stack] < S) {
+    if (h->pe_ext[stack]) cudaFree(h->pe_ext[stack]);
+    h->pe_ext[stack] = nullptr;
+    const int n = S + S / 4;
+    HCHECK(cudaMalloc(reinterpret_cast<void**>(&h->pe_ext[stack]), sizeof(float) * (size_t)n * D));
+    RCHECK(sinusoid_table_host(h, n, D, h->pe_ext[stack], st));
+    h->pe_ext_n[stack] = n;
+  }
+  *out = h->pe_ext[stack];
+  return FS2_OK;
+}
+
+ConvGemmArgs base_args(const GemmW& w, int B, int S, int SA, const int* lens) {
+  ConvGemmArgs a;
+  memset(&a, 0, sizeof a);
+  a.K = w.K; a.N = w.N; a.taps = w.taps;
+  a.Wf = w.wf; a.Wb = w.wb; a.bias = w.bias;
+  a.B = B; a.S = S; a.SA = SA; a.lens = lens;
+  return a;
+}
+
+int run_gemm(fs2_handle* h, int prec, const ConvGemmArgs& a, cudaStream_t st) {
+  if (prec == FS2_PREC_FP32) {
+    cudaError_t e = simt_conv_gemm_launch(a, st);
+    if (e != cudaSuccess) return h ? h->cuda_fail(e, "simt_conv_gemm_launch") : fs2_fail_cuda(e, "simt_conv_gemm_launch");
+    return FS2_OK;
+  }
+  int rc = tc_conv_gemm_launch(a, st);
+  if (rc != FS2_OK && h) h->err = g_last_error;
+  return rc;
+}
+
+// Layers.py:39-48 x n layers on grid-layout activations.  x (fp32) and, in bf16 mode, xb (its bf16 shadow) are
+// updated in place.  Returns through x/xb.
+int run_fft_stack(fs2_handle* h, std::vector<FftW>& Ls, int l0, int l1, int prec, float* x, bf16* xb, const int* lens,
+                  int B, int S, int SA, cudaStream_t st) {
+  const int D = h->dims.d_model, F = h->dims.d_ffn, H = h->dims.n_heads, dk = D / H;
+  const size_t R = (size_t)B * SA;
+  WS(float, y, "fft.y", R * D);
+  if (prec == FS2_PREC_FP32) {
+    WS(float, qkv, "fft.qkv", R * 3 * D);
+    WS(float, att, "fft.att", R * D);
+    WS(float, hid, "fft.hid", R * F);
+    for (int l = l0; l < l1; ++l) {
+      FftW& L = Ls[l];
+      ConvGemmArgs a = base_args(L.qkv, B, S, SA, lens);
+      a.A = x; a.epi = EPI_BIAS; a.mask_mode = MASK_GRID; a.out = qkv; a.ldo = 3 * D;
+      RCHECK(run_gemm(h, prec, a, st));
+      HCHECK(simt_attention_launch(qkv, 3 * D, 0, D, 2 * D, lens, B, S, SA, H, dk, att, D, st));
+      a = base_args(L.fc, B, S, SA, lens);
+      a.A = att; a.epi = EPI_RES_LN; a.mask_mode = MASK_LEN; a.residual = x; a.ln_g = L.ln1_g; a.ln_b = L.ln1_b;
+      a.out = y; a.ldo = D;
+      RCHECK(run_gemm(h, prec, a, st));
+      a = base_args(L.w1, B, S, SA, lens);
+      a.A = y; a.epi = EPI_RELU; a.mask_mode = MASK_GRID; a.out = hid; a.ldo = F;
+      RCHECK(run_gemm(h, prec, a, st));
+      a = base_args(L.w2, B, S, SA, lens);
+      a.A = hid; a.epi = EPI_RES_LN; a.mask_mode = MASK_LEN; a.residual = y; a.ln_g = L.ln2_g; a.ln_b = L.ln2_b;
+      a.out = x; a.ldo = D;
+      RCHECK(run_gemm(h, prec, a, st));
+    }
+    return FS2_OK;
+  }
+  // tcgen05 bf16 path
+  const int SAv = (SA + 7) & ~7;
+  WS(bf16, yb, "fft.yb", R * D);
+  WS(bf16, qb, "fft.qb", R * D);
+  WS(bf16, kb, "fft.kb", R * D);
+  WS(bf16, vtb, "fft.vtb", (size_t)B * D * SAv);
+  WS(bf16, attb, "fft.attb", R * D);
+  WS(bf16, hidb, "fft.hidb", R * F);
+  for (int l = l0; l < l1; ++l) {
+    FftW& L = Ls[l];
+    ConvGemmArgs a = base_args(L.qkv, B, S, SA, lens);
+    a.Ab = xb; a.epi = EPI_QKV; a.mask_mode = MASK_GRID; a.q_b = qb; a.k_b = kb; a.vt_b = vtb; a.SAv = SAv;
+    RCHECK(run_gemm(h, prec, a, st));
+    int rc = tc_attention_launch(qb, kb, vtb, lens, B, S, SA, SAv, H, attb, st);
+    if (rc != FS2_OK) { h->err = g_last_error; return rc; }
+    a = base_args(L.fc, B, S, SA, lens);
+    a.Ab = attb; a.epi = EPI_RES_LN; a.mask_mode = MASK_LEN; a.residual = x; a.ln_g = L.ln1_g; a.ln_b = L.ln1_b;
+    a.out = y; a.ldo = D; a.out_b = yb; a.ldob = D;
+    RCHECK(run_gemm(h, prec, a, st));
+    a = base_args(L.w1, B, S, SA, lens);
+    a.Ab = yb; a.epi = EPI_RELU; a.mask_mode = MASK_GRID; a.out_b = hidb; a.ldob = F;
+    RCHECK(run_gemm(h, prec, a, st));
+    a = base_args(L.w2, B, S, SA, lens);
+    a.Ab = hidb; a.epi = EPI_RES_LN; a.mask_mode = MASK_LEN; a.residual = y; a.ln_g = L.ln2_g; a.ln_b = L.ln2_b;
+    a.out = x; a.ldo = D; a.out_b = xb; a.ldob = D;
+    RCHECK(run_gemm(h, prec, a, st));
+  }
+  return FS2_OK;
+}
+
+// modules.py:278-286 on the padded grid (halo-leak semantics, SURVEY.md section 8(a) note 1): out_user[B,S]
+int run_predictor(fs2_handle* h, PredW& P, int prec, const float* x, const bf16* xb, const int* lens, int B, int S,
+                  int SA, float* out_user, cudaStream_t st) {
+  const int C = h->dims.vp_filter;
+  const size_t R = (size_t)B * SA;
+  WS(float, p1, "pred.h1", R * C);
+  bf16* p1b = nullptr;
+  if (prec == FS2_PREC_BF16) {
+    WS(bf16, t, "pred.h1b", R * C);
+    p1b = t;
+  }
+  ConvGemmArgs a = base_args(P.c1, B, S, SA, lens);
+  a.A = x; a.Ab = xb; a.epi = EPI_RELU_LN; a.mask_mode = MASK_GRID; a.ln_g = P.ln1_g; a.ln_b = P.ln1_b;
+  a.out = p1; a.ldo = C; a.out_b = p1b; a.ldob = C;
+  RCHECK(run_gemm(h, prec, a, st));
+  a = base_args(P.c2, B, S, SA, lens);
+  a.A = p1; a.Ab = p1b; a.epi = EPI_RELU_LN_DOT; a.mask_mode = MASK_LEN; a.ln_g = P.ln2_g; a.ln_b = P.ln2_b;
+  a.dot_w = P.lin_w; a.dot_b = P.lin_b; a.out_user = out_user; a.ldu = 1;
+  RCHECK(run_gemm(h, prec, a, st));
+  return FS2_OK;
+}
+
+// fastspeech2_align.py:83-85: mel_linear, PostNet (BatchNorm folded), residual.  dec in grid layout.
+int run_mel_postnet(fs2_handle* h, int prec, const float* dec, const bf16* decb, int B, int T, int TA, float* mel,
+                    float* mel_post, cudaStream_t st) {
+  const int M = h->dims.n_mel, P = h->dims.pn_dim, NL = h->dims.pn_layers;
+  const size_t R = (size_t)B * TA;
+  const bool tc = prec == FS2_PREC_BF16;
+  WS(float, melg, "pn.mel", R * M);
+  bf16 *melb = nullptr, *pa_b = nullptr, *pb_b = nullptr;
+  float *pa = nullptr, *pb = nullptr;
+  if (tc) {
+    WS(bf16, t0, "pn.melb", R * M); melb = t0;
+    WS(bf16, t1, "pn.a_b", R * P);  pa_b = t1;
+    WS(bf16, t2, "pn.b_b", R * P);  pb_b = t2;
+  } else {
+    WS(float, t1, "pn.a", R * P); pa = t1;
+    WS(float, t2, "pn.b", R * P); pb = t2;
+  }
+  ConvGemmArgs a = base_args(h->mel_linear, B, T, TA, nullptr);
+  a.A = dec; a.Ab = decb; a.epi = EPI_BIAS; a.mask_mode = MASK_GRID;
+  a.out = melg; a.ldo = M; a.out_b = melb; a.ldob = M; a.out_user = mel; a.ldu = M;
+  RCHECK(run_gemm(h, prec, a, st));
+  const float* in_f = melg; const bf16* in_b = melb;
+  for (int i = 0; i < NL; ++i) {
+    a = base_args(h->postnet[i], B, T, TA, nullptr);
+    a.A = in_f; a.Ab = in_b; a.mask_mode = MASK_GRID;
+    if (i < NL - 1) {
+      a.epi = EPI_TANH;
+      float* of = (i & 1) ? pb : pa; bf16* ob = (i & 1) ? pb_b : pa_b;
+      a.out = of; a.ldo = P; a.out_b = ob; a.ldob = P;
+      in_f = of; in_b = ob;
+    } else {
+      a.epi = EPI_RES; a.residual = melg; a.out_user = mel_post; a.ldu = M;
+    }
+    RCHECK(run_gemm(h, prec, a, st));
+  }
+  return FS2_OK;
+}
+
+int check_device(int device) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) {
+    g_last_error = std::string("no CUDA device available (") + cudaGetErrorString(e) +
+                   "); this library has no CPU fallback";
+    (void)cudaGetLastError();
+    return FS2_ERR_NO_DEVICE;
+  }
+  if (device < 0 || device >= n) {
+    g_last_error = "device index out of range";
+    return FS2_ERR_INVALID;
+  }
+  return FS2_OK;
+}
+
+}  // namespace
+
+// =============================================================================================
+extern "C" {
+
+const char* fs2_version(void) { return "fs2_b200 0.1 (sm_100a)"; }
+
+const char* fs2_last_error(const fs2_handle* h) { return h ? h->err.c_str() : g_last_error.c_str(); }
+
+int64_t fs2_launch_count(const fs2_handle*) { return (int64_t)g_fs2_launches; }
+
+int fs2_create(fs2_handle** out, const fs2_dims* d, int device) {
+  if (!out || !d) { g_last_error = "null argument"; return FS2_ERR_INVALID; }
+  *out = nullptr;
+  RCHECK(check_device(device));
+  // what the kernels are built for (config/LJSpeech/model.yaml is the only shipped config)
+  if (d->d_model != 256 || d->vp_filter != 256) { g_last_error = "d_model and vp_filter must be 256"; return FS2_ERR_UNSUPPORTED; }
+  if (d->n_heads <= 0 || d->d_model % d->n_heads || (d->d_model / d->n_heads != 128 && d->d_model / d->n_heads != 64)) {
+    g_last_error = "head dim must be 64 or 128"; return FS2_ERR_UNSUPPORTED; }
+  if (d->ffn_k1 % 2 == 0 || d->ffn_k2 % 2 == 0 || d->ffn_k1 > 2 * FS2_HALO + 1 || d->ffn_k2 > 2 * FS2_HALO + 1 ||
+      d->vp_kernel != 3 || d->pn_kernel % 2 == 0 || d->pn_kernel > 2 * FS2_HALO + 1) {
+    g_last_error = "conv kernels must be odd and <= 9; variance predictor kernel must be 3"; return FS2_ERR_UNSUPPORTED; }
+  if (d->d_ffn % 256 || d->pn_dim % 256 || d->n_mel % 16 || d->n_mel > 128 || d->pn_layers < 2 || d->n_bins < 2 ||
+      d->vocab < 1 || d->n_enc_layers < 1 || d->n_dec_layers < 1 || d->max_seq_len < 1) {
+    g_last_error = "unsupported dims (d_ffn, pn_dim multiples of 256; n_mel multiple of 16 and <= 128)"; return FS2_ERR_UNSUPPORTED; }
+  cudaError_t e = cudaSetDevice(device);
+  if (e != cudaSuccess) return fs2_fail_cuda(e, "cudaSetDevice");
+  fs2_handle* h = new fs2_handle();
+  h->dims = *d;
+  h->device = device;
+  e = cudaMallocHost(reinterpret_cast<void**>(&h->host_tmax), sizeof(int));
+  if (e != cudaSuccess) { delete h; return fs2_fail_cuda(e, "cudaMallocHost"); }
+  *out = h;
+  return FS2_OK;
+}
+
+void fs2_destroy(fs2_handle* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  cudaDeviceSynchronize();
+  for (auto& kv : h->raw) cudaFree(kv.second.d);
+  for (void* p : h->owned) cudaFree(p);
+  for (auto& kv : h->ws) cudaFree(kv.second.first);
+  for (int i = 0; i < 2; ++i) if (h->pe_ext[i]) cudaFree(h->pe_ext[i]);
+  if (h->host_tmax) cudaFreeHost(h->host_tmax);
+  delete h;
+}
+
+int fs2_set_precision(fs2_handle* h, int32_t enc, int32_t dec) {
+  if (!h) return FS2_ERR_INVALID;
+  if ((enc != FS2_PREC_FP32 && enc != FS2_PREC_BF16) || (dec != FS2_PREC_FP32 && dec != FS2_PREC_BF16))
+    return h->fail(FS2_ERR_INVALID, "precision must be FS2_PREC_FP32 or FS2_PREC_BF16");
+  h->prec_enc = enc;
+  h->prec_dec = dec;
+  return FS2_OK;
+}
+
+int fs2_load_weights(fs2_handle* h, const fs2_weight_desc* descs, int32_t n) {
+  if (!h || !descs || n <= 0) return h ? h->fail(FS2_ERR_INVALID, "null/empty weight list") : FS2_ERR_INVALID;
+  HCHECK(cudaSetDevice(h->device));
+  cudaStream_t st = 0;
+  // drop anything loaded before
+  for (auto& kv : h->raw) cudaFree(kv.second.d);
+  h->raw.clear();
+  for (void* p : h->owned) cudaFree(p);
+  h->owned.clear();
+  h->loaded = false;
+  h->have_stage1 = false;
+
+  for (int i = 0; i < n; ++i) {
+    const fs2_weight_desc& w = descs[i];
+    if (!w.name || !w.data || w.ndim < 0 || w.ndim > 4) return h->fail(FS2_ERR_INVALID, "malformed weight descriptor");
+    const std::string name(w.name);
+    if (name.rfind("mel_encoder.", 0) == 0) continue;  // training-only aligner (Models.py:103-173)
+    if (name.size() > 19 && name.compare(name.size() - 19, 19, "num_batches_tracked") == 0) continue;
+    RawT t;
+    t.numel = 1;
+    for (int k = 0; k < w.ndim; ++k) { t.shape.push_back(w.shape[k]); t.numel *= w.shape[k]; }
+    if (t.numel <= 0) return h->fail(FS2_ERR_INVALID, "empty tensor: " + name);
+    HCHECK(cudaMalloc(reinterpret_cast<void**>(&t.d), sizeof(float) * (size_t)t.numel));
+    cudaError_t e = cudaMemcpyAsync(t.d, w.data, sizeof(float) * (size_t)t.numel,
+                                    w.on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st);
+    if (e != cudaSuccess) { cudaFree(t.d); return h->cuda_fail(e, "cudaMemcpyAsync(weight)"); }
+    if (h->raw.count(name)) cudaFree(h->raw[name].d);
+    h->raw[name] = t;
+  }
+  HCHECK(cudaStreamSynchronize(st));
+
+  const fs2_dims& d = h->dims;
+  const int D = d.d_model;
+  const float* t = nullptr;
+  RCHECK(need(h, "txt_encoder.src_word_emb.weight", {d.vocab, D}, &t));
+  RCHECK(need(h, "txt_encoder.position_enc", {1, d.max_seq_len + 1, D}, &t));
+  RCHECK(need(h, "mel_decoder.position_enc", {1, d.max_seq_len + 1, D}, &t));
+  RCHECK(need(h, "variance_adaptor.pitch_bins", {d.n_bins - 1}, &t));
+  RCHECK(need(h, "variance_adaptor.energy_bins", {d.n_bins - 1}, &t));
+  RCHECK(need(h, "variance_adaptor.pitch_embedding.weight", {d.n_bins, D}, &t));
+  RCHECK(need(h, "variance_adaptor.energy_embedding.weight", {d.n_bins, D}, &t));
+  h->enc.assign(d.n_enc_layers, FftW());
+  h->dec.assign(d.n_dec_layers, FftW());
+  for (int l = 0; l < d.n_enc_layers; ++l) RCHECK(build_fft(h, h->enc[l], "txt_encoder.layer_stack." + std::to_string(l), st));
+  for (int l = 0; l < d.n_dec_layers; ++l) RCHECK(build_fft(h, h->dec[l], "mel_decoder.layer_stack." + std::to_string(l), st));
+  const char* which[3] = {"duration", "pitch", "energy"};
+  for (int i = 0; i < 3; ++i) RCHECK(build_pred(h, h->pred[i], std::string("variance_adaptor.") + which[i] + "_predictor", st));
+  RCHECK(build_gemm(h, h->mel_linear, {"mel_linear.weight"}, {"mel_linear.bias"}, d.n_mel, D, 1, nullptr, nullptr, st));
+  h->postnet.assign(d.pn_layers, GemmW());
+  for (int i = 0; i < d.pn_layers; ++i) {
+    const int cin = i == 0 ? d.n_mel : d.pn_dim, cout = i == d.pn_layers - 1 ? d.n_mel : d.pn_dim;
+    const std::string p = "postnet.convolutions." + std::to_string(i);
+    const float *cb, *g, *b, *mean, *var;
+    RCHECK(need(h, p + ".0.conv.bias", {cout}, &cb));
+    RCHECK(need(h, p + ".1.weight", {cout}, &g));
+    RCHECK(need(h, p + ".1.bias", {cout}, &b));
+    RCHECK(need(h, p + ".1.running_mean", {cout}, &mean));
+    RCHECK(need(h, p + ".1.running_var", {cout}, &var));
+    float *scale = nullptr, *fb = nullptr;
+    RCHECK(dev_alloc(h, &scale, (size_t)cout));
+    RCHECK(dev_alloc(h, &fb, (size_t)cout));
+    HCHECK(rowops_bn_fold(cb, g, b, mean, var, cout, 1e-5f, scale, fb, st));
+    RCHECK(build_gemm(h, h->postnet[i], {p + ".0.conv.weight"}, {}, cout, cin, d.pn_kernel, scale, fb, st));
+  }
+  HCHECK(cudaStreamSynchronize(st));
+  h->loaded = true;
+  return FS2_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+int fs2_forward_stage1(fs2_handle* h, const int64_t* texts, const int64_t* src_lens, int32_t B, int32_t L,
+                       float p_control, float e_control, float d_control, float* log_d, float* d_rounded,
+                       int64_t* mel_lens, uint8_t* src_mask, float* pitch_ph, float* energy_ph, int32_t* T_max_out,
+                       void* stream) {
+  if (!h) return FS2_ERR_INVALID;
+  if (!h->loaded) return h->fail(FS2_ERR_STATE, "fs2_load_weights has not succeeded on this handle");
+  if (!texts || !src_lens || !log_d || !d_rounded || !mel_lens || !T_max_out || B <= 0 || L <= 0)
+    return h->fail(FS2_ERR_INVALID, "stage1: null pointer or empty batch");
+  if (L > 8192) return h->fail(FS2_ERR_UNSUPPORTED, "stage1: L > 8192");
+  const fs2_dims& d = h->dims;
+  if ((d.pitch_phoneme_level && !pitch_ph) || (d.energy_phoneme_level && !energy_ph))
+    return h->fail(FS2_ERR_INVALID, "stage1: phoneme-level pitch/energy output pointer missing");
+  HCHECK(cudaSetDevice(h->device));
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int D = d.d_model, LA = L + FS2_HALO;
+  const size_t R = (size_t)B * LA;
+  h->have_stage1 = false;
+
+  WS(int, lens32, "s1.lens32", B);
+  WS(float, x, "s1.x", R * D);
+  WS(int, cum, "s1.cum", (size_t)B * L);
+  WS(int, mlens32, "s1.mel_lens32", B);
+  WS(int, tmax_dev, "s1.tmax", 1);
+  bf16* xb = nullptr;
+  if (h->prec_enc == FS2_PREC_BF16) {
+    WS(bf16, t, "s1.xb", R * D);
+    xb = t;
+  }
+  HCHECK(rowops_lens_to_i32(src_lens, B, L, lens32, st));
+  if (src_mask) HCHECK(rowops_mask(src_lens, nullptr, B, L, src_mask, st));
+  const float* pe = nullptr;
+  RCHECK(position_table(h, 0, L, &pe, st));
+  HCHECK(rowops_embed_pe(texts, raw_ptr(h, "txt_encoder.src_word_emb.weight"), pe, d.vocab, B, L, LA, D, x, nullptr, st));
+  if (xb) HCHECK(rowops_f32_to_bf16(x, (int64_t)(R * D), xb, st));
+  RCHECK(run_fft_stack(h, h->enc, 0, d.n_enc_layers, h->prec_enc, x, xb, lens32, B, L, LA, st));
+  // modules.py:116 duration predictor on the encoder output
+  RCHECK(run_predictor(h, h->pred[0], h->prec_enc, x, xb, lens32, B, L, LA, log_d, st));
+  // modules.py:117-126 phoneme-level variants
+  if (d.pitch_phoneme_level) {
+    RCHECK(run_predictor(h, h->pred[1], h->prec_enc, x, xb, lens32, B, L, LA, pitch_ph, st));
+    HCHECK(rowops_variance_embed(pitch_ph, p_control, raw_ptr(h, "variance_adaptor.pitch_bins"), d.n_bins,
+                                 raw_ptr(h, "variance_adaptor.pitch_embedding.weight"), nullptr, x, xb, B, L, LA, D,
+                                 nullptr, st));
+  }
+  if (d.energy_phoneme_level) {
+    RCHECK(run_predictor(h, h->pred[2], h->prec_enc, x, xb, lens32, B, L, LA, energy_ph, st));
+    HCHECK(rowops_variance_embed(energy_ph, e_control, raw_ptr(h, "variance_adaptor.energy_bins"), d.n_bins,
+                                 raw_ptr(h, "variance_adaptor.energy_embedding.weight"), nullptr, x, xb, B, L, LA, D,
+                                 nullptr, st));
+  }
+  // modules.py:132-135 + LengthRegulator bookkeeping
+  HCHECK(rowops_round_durations(log_d, (int64_t)B * L, d_control, d_rounded, st));
+  HCHECK(cudaMemsetAsync(tmax_dev, 0, sizeof(int), st));
+  HCHECK(rowops_duration_scan(d_rounded, B, L, cum, mel_lens, mlens32, tmax_dev, st));
+  HCHECK(cudaMemcpyAsync(h->host_tmax, tmax_dev, sizeof(int), cudaMemcpyDeviceToHost, st));
+  HCHECK(cudaStreamSynchronize(st));  // the one data-dependent size of the path
+  *T_max_out = *h->host_tmax;
+  h->have_stage1 = true;
+  h->st_B = B; h->st_L = L; h->st_LA = LA; h->st_Tmax = *h->host_tmax;
+  h->st_enc_out = x;
+  return FS2_OK;
+}
+
+int fs2_forward_stage2(fs2_handle* h, int32_t T, float p_control, float e_control, float* mel, float* mel_post,
+                       float* pitch, float* energy, uint8_t* mel_mask, void* stream) {
+  if (!h) return FS2_ERR_INVALID;
+  if (!h->loaded || !h->have_stage1) return h->fail(FS2_ERR_STATE, "stage2 called before a successful stage1");
+  if (T < h->st_Tmax) return h->fail(FS2_ERR_INVALID, "stage2: T smaller than the stage-1 maximum mel length");
+  const fs2_dims& d = h->dims;
+  if (T == 0) return FS2_OK;  // degenerate batch (all durations zero): nothing to write
+  if (!mel || !mel_post || (!d.pitch_phoneme_level && !pitch) || (!d.energy_phoneme_level && !energy))
+    return h->fail(FS2_ERR_INVALID, "stage2: null output pointer");
+  HCHECK(cudaSetDevice(h->device));
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int B = h->st_B, L = h->st_L, LA = h->st_LA, D = d.d_model, TA = T + FS2_HALO;
+  const size_t R = (size_t)B * TA;
+  const int* cum = reinterpret_cast<int*>(h->ws["s1.cum"].first);
+  const int* mlens32 = reinterpret_cast<int*>(h->ws["s1.mel_lens32"].first);
+
+  WS(float, x, "s2.x", R * D);
+  bf16* xb = nullptr;
+  if (h->prec_dec == FS2_PREC_BF16 || h->prec_enc == FS2_PREC_BF16) {
+    WS(bf16, t, "s2.xb", R * D);
+    xb = t;
+  }
+  if (mel_mask) HCHECK(rowops_mask(nullptr, mlens32, B, T, mel_mask, st));
+  // modules.py:136 length regulator (hard), straight into the halo'ed grid
+  HCHECK(rowops_length_regulate(h->st_enc_out, LA * D, cum, B, L, D, T, TA, x, st));
+  const float* pe = nullptr;
+  RCHECK(position_table(h, 1, T, &pe, st));
+  const bool pitch_fl = !d.pitch_phoneme_level, energy_fl = !d.energy_phoneme_level;
+  if (h->prec_enc == FS2_PREC_BF16 && (pitch_fl || energy_fl)) HCHECK(rowops_f32_to_bf16(x, (int64_t)(R * D), xb, st));
+  // modules.py:139-149 frame-level pitch then energy (energy sees x + pitch embedding)
+  if (pitch_fl) {
+    RCHECK(run_predictor(h, h->pred[1], h->prec_enc, x, xb, mlens32, B, T, TA, pitch, st));
+    HCHECK(rowops_variance_embed(pitch, p_control, raw_ptr(h, "variance_adaptor.pitch_bins"), d.n_bins,
+                                 raw_ptr(h, "variance_adaptor.pitch_embedding.weight"), energy_fl ? nullptr : pe, x, xb,
+                                 B, T, TA, D, nullptr, st));
+  }
+  if (energy_fl) {
+    RCHECK(run_predictor(h, h->pred[2], h->prec_enc, x, xb, mlens32, B, T, TA, energy, st));
+    // fused: + energy embedding, + decoder positional encoding (Models.py:231-233), bf16 shadow for the decoder
+    HCHECK(rowops_variance_embed(energy, e_control, raw_ptr(h, "variance_adaptor.energy_bins"), d.n_bins,
+                                 raw_ptr(h, "variance_adaptor.energy_embedding.weight"), pe, x, xb, B, T, TA, D,
+                                 nullptr, st));
+  }
+  if (!pitch_fl && !energy_fl)  // both phoneme-level: only the decoder's positional add remains
+    HCHECK(rowops_add_pe(x, xb, pe, B, T, TA, D, st));
+  RCHECK(run_fft_stack(h, h->dec, 0, d.n_dec_layers, h->prec_dec, x, xb, mlens32, B, T, TA, st));
+  RCHECK(run_mel_postnet(h, h->prec_dec, x, xb, B, T, TA, mel, mel_post, st));
+  return FS2_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// stand-alone operators
+int fs2_round_durations(const float* log_d, int64_t n, float d_control, float* out, void* stream) {
+  if (!log_d || !out || n < 0) { g_last_error = "null argument"; return FS2_ERR_INVALID; }
+  FS2_CUDA_CHECK(rowops_round_durations(log_d, n, d_control, out, reinterpret_cast<cudaStream_t>(stream)));
+  return FS2_OK;
+}
+
+int fs2_duration_scan(const float* dd, int32_t B, int32_t L, int32_t* cum, int64_t* mel_lens, int32_t* T_max_out,
+                      void* stream) {
+  if (!dd || !cum || !mel_lens || !T_max_out || B <= 0 || L <= 0) { g_last_error = "bad argument"; return FS2_ERR_INVALID; }
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  int* tmax = nullptr;
+  FS2_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&tmax), sizeof(int)));
+  cudaError_t e = cudaMemsetAsync(tmax, 0, sizeof(int), st);
+  if (e == cudaSuccess) e = rowops_duration_scan(dd, B, L, cum, mel_lens, nullptr, tmax, st);
+  int host = 0;
+  if (e == cudaSuccess) e = cudaMemcpyAsync(&host, tmax, sizeof(int), cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  cudaFree(tmax);
+  if (e != cudaSuccess) return fs2_fail_cuda(e, "fs2_duration_scan");
+  *T_max_out = host;
+  return FS2_OK;
+}
+
+int fs2_length_regulate(const float* x, const int32_t* cum, int32_t B, int32_t L, int32_t D, int32_t T, float* out,
+                        void* stream) {
+  if (!x || !cum || !out || B <= 0 || L <= 0 || D <= 0 || D % 4 || T < 0) { g_last_error = "bad argument"; return FS2_ERR_INVALID; }
+  FS2_CUDA_CHECK(rowops_length_regulate(x, L * D, cum, B, L, D, T, T, out, reinterpret_cast<cudaStream_t>(stream)));
+  return FS2_OK;
+}
+
+int fs2_gaussian_upsample(const float* x, const float* dd, int32_t B, int32_t L, int32_t D, int32_t T, int32_t T_w,
+                          float* out, float* s, float* w, void* stream) {
+  if (!x || !dd || !out || B <= 0 || L <= 0 || D <= 0 || D % 4 || T < 0 || T_w < 0 || T_w > T) {
+    g_last_error = "bad argument"; return FS2_ERR_INVALID; }
+  FS2_CUDA_CHECK(rowops_gaussian_upsample(x, dd, B, L, D, T, T_w, out, s, w, reinterpret_cast<cudaStream_t>(stream)));
+  return FS2_OK;
+}
+
+int fs2_mask_from_lengths(const int64_t* lens, int32_t B, int32_t max_len, uint8_t* mask, void* stream) {
+  if (!lens || !mask || B <= 0 || max_len < 0) { g_last_error = "bad argument"; return FS2_ERR_INVALID; }
+  FS2_CUDA_CHECK(rowops_mask(lens, nullptr, B, max_len, mask, reinterpret_cast<cudaStream_t>(stream)));
+  return FS2_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// per-operator entry points (unit parity)
+int fs2_op_sinusoid_table(fs2_handle* h, int32_t n_pos, float* out, void* stream) {
+  if (!h || !out || n_pos <= 0) return FS2_ERR_INVALID;
+  HCHECK(cudaSetDevice(h->device));
+  return sinusoid_table_host(h, n_pos, h->dims.d_model, out, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int fs2_op_embed_pe(fs2_handle* h, const int64_t* texts, int32_t B, int32_t L, float* out, void* stream) {
+  if (!h || !h->loaded) return FS2_ERR_STATE;
+  if (!texts || !out || B <= 0 || L <= 0) return h->fail(FS2_ERR_INVALID, "bad argument");
+  HCHECK(cudaSetDevice(h->device));
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const float* pe = nullptr;
+  RCHECK(position_table(h, 0, L, &pe, st));
+  HCHECK(rowops_embed_pe(texts, raw_ptr(h, "txt_encoder.src_word_emb.weight"), pe, h->dims.vocab, B, L, L, h->dims.d_model,
+                         nullptr, out, st));
+  return FS2_OK;
+}
+
+int fs2_op_fft_stack(fs2_handle* h, int32_t stack, int32_t l0, int32_t l1, int32_t prec, const float* x,
+                     const int64_t* lens, int32_t B, int32_t S, float* out, void* stream) {
+  if (!h || !h->loaded) return FS2_ERR_STATE;
+  std::vector<FftW>& Ls = stack == 0 ? h->enc : h->dec;
+  if (!x || !lens || !out || B <= 0 || S <= 0 || l0 < 0 || l1 > (int)Ls.size() || l0 > l1 ||
+      (prec != FS2_PREC_FP32 && prec != FS2_PREC_BF16))
+    return h->fail(FS2_ERR_INVALID, "bad argument");
+  HCHECK(cudaSetDevice(h->device));
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int D = h->dims.d_model, SA = S + FS2_HALO;
+  const size_t R = (size_t)B * SA;
+  WS(int, lens32, "op.lens32", B);
+  WS(float, xg, "op.x", R * D);
+  bf16* xb = nullptr;
+  if (prec == FS2_PREC_BF16) { WS(bf16, t, "op.xb", R * D); xb = t; }
+  HCHECK(rowops_lens_to_i32(lens, B, S, lens32, st));
+  HCHECK(rowops_to_grid(x, B, S, SA, D, xg, D, 0, xb, st));
+  RCHECK(run_fft_stack(h, Ls, l0, l1, prec, xg, xb, lens32, B, S, SA, st));
+  HCHECK(rowops_from_grid(xg, B, S, SA, D, out, st));
+  return FS2_OK;
+}
+
+int fs2_op_variance_predictor(fs2_handle* h, int32_t which, const float* x, const int64_t* lens, int32_t B, int32_t S,
+                              float* out, void* stream) {
+  if (!h || !h->loaded) return FS2_ERR_STATE;
+  if (!x || !lens || !out || B <= 0 || S <= 0 || which < 0 || which > 2) return h->fail(FS2_ERR_INVALID, "bad argument");
+  HCHECK(cudaSetDevice(h->device));
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int D = h->dims.d_model, SA = S + FS2_HALO;
+  const size_t R = (size_t)B * SA;
+  WS(int, lens32, "op.lens32", B);
+  WS(float, xg, "op.x", R * D);
+  bf16* xb = nullptr;
+  if (h->prec_enc == FS2_PREC_BF16) { WS(bf16, t, "op.xb", R * D); xb = t; }
+  HCHECK(rowops_lens_to_i32(lens, B, S, lens32, st));
+  HCHECK(rowops_to_grid(x, B, S, SA, D, xg, D, 0, xb, st));
+  return run_predictor(h, h->pred[which], h->prec_enc, xg, xb, lens32, B, S, SA, out, st);
+}
+
+int fs2_op_variance_embed(fs2_handle* h, int32_t which, float* pred, float control, float* x, int32_t B, int32_t S,
+                          int32_t* idx_out, void* stream) {
+  if (!h || !h->loaded) return FS2_ERR_STATE;
+  if (!pred || !x || B <= 0 || S <= 0 || (which != 1 && which != 2)) return h->fail(FS2_ERR_INVALID, "bad argument");
+  HCHECK(cudaSetDevice(h->device));
+  const char* nm = which == 1 ? "pitch" : "energy";
+  HCHECK(rowops_variance_embed(pred, control, raw_ptr(h, std::string("variance_adaptor.") + nm + "_bins"), h->dims.n_bins,
+                               raw_ptr(h, std::string("variance_adaptor.") + nm + "_embedding.weight"), nullptr, x, nullptr,
+                               B, S, S, h->dims.d_model, idx_out, reinterpret_cast<cudaStream_t>(stream)));
+  return FS2_OK;
+}
+
+int fs2_op_mel_postnet(fs2_handle* h, int32_t prec, const float* dec, int32_t B, int32_t T, float* mel, float* mel_post,
+                       void* stream) {
+  if (!h || !h->loaded) return FS2_ERR_STATE;
+  if (!dec || !mel || !mel_post || B <= 0 || T <= 0 || (prec != FS2_PREC_FP32 && prec != FS2_PREC_BF16))
+    return h->fail(FS2_ERR_INVALID, "bad argument");
+  HCHECK(cudaSetDevice(h->device));
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int D = h->dims.d_model, TA = T + FS2_HALO;
+  const size_t R = (size_t)B * TA;
+  WS(float, xg, "op.x", R * D);
+  bf16* xb = nullptr;
+  if (prec == FS2_PREC_BF16) { WS(bf16, t, "op.xb", R * D); xb = t; }
+  HCHECK(rowops_to_grid(dec, B, T, TA, D, xg, D, 0, xb, st));
+  return run_mel_postnet(h, prec, xg, xb, B, T, TA, mel, mel_post, st);
+}
+
+int fs2_op_conv_gemm(int32_t prec, const float* A, const float* W, const float* bias, int32_t B, int32_t S, int32_t K,
+                     int32_t N, int32_t taps, int32_t act, float* out, void* stream) {
+  if (!A || !W || !bias || !out || B <= 0 || S <= 0 || K <= 0 || N <= 0 || taps < 1 || taps > 2 * FS2_HALO + 1 ||
+      taps % 2 == 0 || K % 16 || N % 4 || act < 0 || act > 2) { g_last_error = "bad argument"; return FS2_ERR_INVALID; }
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int SA = S + FS2_HALO;
+  const size_t R = (size_t)B * SA;
+  float *Ag = nullptr, *Wf = nullptr, *Og = nullptr;
+  bf16 *Ab = nullptr, *Wb = nullptr;
+  int rc = FS2_OK;
+  cudaError_t e = cudaSuccess;
+  do {
+    if ((e = cudaMalloc(reinterpret_cast<void**>(&Ag), sizeof(float) * R * K)) != cudaSuccess) break;
+    if ((e = cudaMalloc(reinterpret_cast<void**>(&Ab), sizeof(bf16) * R * K)) != cudaSuccess) break;
+    if ((e = cudaMalloc(reinterpret_cast<void**>(&Wf), sizeof(float) * (size_t)N * K * taps)) != cudaSuccess) break;
+    if ((e = cudaMalloc(reinterpret_cast<void**>(&Wb), sizeof(bf16) * (size_t)N * K * taps)) != cudaSuccess) break;
+    if ((e = cudaMalloc(reinterpret_cast<void**>(&Og), sizeof(float) * R * N)) != cudaSuccess) break;
+    if ((e = rowops_to_grid(A, B, S, SA, K, Ag, K, 0, Ab, st)) != cudaSuccess) break;
+    if ((e = rowops_pack_weight(W, N, K, taps, nullptr, Wf, Wb, N, 0, st)) != cudaSuccess) break;
+    ConvGemmArgs a;
+    memset(&a, 0, sizeof a);
+    a.A = Ag; a.Ab = Ab; a.K = K; a.Wf = Wf; a.Wb = Wb; a.bias = bias; a.N = N; a.taps = taps;
+    a.B = B; a.S = S; a.SA = SA; a.epi = act == 0 ? EPI_BIAS : act == 1 ? EPI_RELU : EPI_TANH; a.mask_mode = MASK_GRID;
+    a.out = Og; a.ldo = N; a.out_user = out; a.ldu = N;
+    rc = run_gemm(nullptr, prec, a, st);
+    if (rc != FS2_OK) break;
+    e = cudaStreamSynchronize(st);
+  } while (0);
+  cudaFree(Ag); cudaFree(Ab); cudaFree(Wf); cudaFree(Wb); cudaFree(Og);
+  if (e != cudaSuccess) return fs2_fail_cuda(e, "fs2_op_conv_gemm");
+  return rc;
+}
+
+int fs2_op_attention(int32_t prec, const float* q, const float* k, const float* v, const int64_t* lens, int32_t B,
+                     int32_t S, int32_t H, int32_t dk, float* out, void* stream) {
+  if (!q || !k || !v || !lens || !out || B <= 0 || S <= 0 || H <= 0 || (dk != 64 && dk != 128)) {
+    g_last_error = "bad argument"; return FS2_ERR_INVALID; }
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int D = H * dk, SA = S + FS2_HALO, SAv = (SA + 7) & ~7;
+  const size_t R = (size_t)B * SA;
+  float *qkv = nullptr, *og = nullptr;
+  bf16 *qb = nullptr, *kb = nullptr, *vb = nullptr, *vtb = nullptr, *ob = nullptr;
+  int* lens32 = nullptr;
+  int rc = FS2_OK;
+  cudaError_t e = cudaSuccess;
+  do {
+    if ((e = cudaMalloc(reinterpret_cast<void**>(&lens32), sizeof(int) * B)) != cudaSuccess) break;
+    if ((e = cudaMalloc(reinterpret_cast<void**>(&og), sizeof(float) * R * D)) != cudaSuccess) break;
+    if ((e = rowops_lens_to_i32(lens, B, S, lens32, st)) != cudaSuccess) break;
+    if (prec == FS2_PREC_FP32) {
+      if ((e = cudaMalloc(reinterpret_cast<void**>(&qkv), sizeof(float) * R * 3 * D)) != cudaSuccess) break;
+      if ((e = rowops_to_grid(q, B, S, SA, D, qkv, 3 * D, 0, nullptr, st)) != cudaSuccess) break;
+      if ((e = rowops_to_grid(k, B, S, SA, D, qkv, 3 * D, D, nullptr, st)) != cudaSuccess) break;
+      if ((e = rowops_to_grid(v, B, S, SA, D, qkv, 3 * D, 2 * D, nullptr, st)) != cudaSuccess) break;
+      if ((e = simt_attention_launch(qkv, 3 * D, 0, D, 2 * D, lens32, B, S, SA, H, dk, og, D, st)) != cudaSuccess) break;
+    } else {
+      if (D != 256 || dk != 128) { g_last_error = "tcgen05 attention is built for H*dk = 256, dk = 128"; rc = FS2_ERR_UNSUPPORTED; break; }
+      if ((e = cudaMalloc(reinterpret_cast<void**>(&qb), sizeof(bf16) * R * D)) != cudaSuccess) break;
+      if ((e = cudaMalloc(reinterpret_cast<void**>(&kb), sizeof(bf16) * R * D)) != cudaSuccess) break;
+      if ((e = cudaMalloc(reinterpret_cast<void**>(&vb), sizeof(bf16) * R * D)) != cudaSuccess) break;
+      if ((e = cudaMalloc(reinterpret_cast<void**>(&vtb), sizeof(bf16) * (size_t)B * D * SAv)) != cudaSuccess) break;
+      if ((e = cudaMalloc(reinterpret_cast<void**>(&ob), sizeof(bf16) * R * D)) != cudaSuccess) break;
+      if ((e = rowops_to_grid(q, B, S, SA, D, nullptr, 0, 0, qb, st)) != cudaSuccess) break;
+      if ((e = rowops_to_grid(k, B, S, SA, D, nullptr, 0, 0, kb, st)) != cudaSuccess) break;
+      if ((e = rowops_to_grid(v, B, S, SA, D, nullptr, 0, 0, vb, st)) != cudaSuccess) break;
+      if ((e = rowops_transpose_v(vb, B, SA, SAv, D, vtb, st)) != cudaSuccess) break;
+      rc = tc_attention_launch(qb, kb, vtb, lens32, B, S, SA, SAv, H, ob, st);
+      if (rc != FS2_OK) break;
+      if ((e = rowops_bf16_to_f32(ob, (int64_t)(R * D), og, st)) != cudaSuccess) break;
+    }
+    if ((e = rowops_from_grid(og, B, S, SA, D, out, st)) != cudaSuccess) break;
+    e = cudaStreamSynchronize(st);
+  } while (0);
+  cudaFree(qkv); cudaFree(og); cudaFree(qb); cudaFree(kb); cudaFree(vb); cudaFree(vtb); cudaFree(ob); cudaFree(lens32);
+  if (e != cudaSuccess) return fs2_fail_cuda(e, "fs2_op_attention");
+  return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,483 @@
+// fs2_rowops.cu -- the HBM-bound row operators of the path (sm_100a): gathers, scans, the
+// length regulator, the Gaussian upsampler, bucketize+embedding, masks and weight repacking.
+// All of them move 16-byte vectors per lane with coalesced row accesses; none has reuse
+// worth staging beyond a per-CTA copy of the small per-utterance tables (cumulative
+// durations / centres), so there is no shared-memory tiling of the payload.
+#include "fs2_common.cuh"
+#include <math.h>
+
+long long g_fs2_launches = 0;
+
+namespace {
+
+__device__ __forceinline__ float4 ld4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+
+// ---------------------------------------------------------------------------------------------
+// transformer/Models.py:82-91  out[b,p,:] = src_word_emb[texts[b,p]] + PE[p]   (all p < L, incl. PAD ids)
+// one warp per row; D/4 float4 per row
+__global__ void embed_pe_kernel(const int64_t* __restrict__ texts, const float* __restrict__ emb,
+                                const float* __restrict__ pe, int vocab, int B, int L, int SA, int D,
+                                float* __restrict__ out_grid, float* __restrict__ out_user) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= B * SA) return;
+  const int b = warp / SA, p = warp - b * SA;
+  const int nv = D >> 2;
+  if (p >= L) {  // halo rows stay zero
+    if (out_grid)
+      for (int c = lane; c < nv; c += 32) st4(out_grid + (size_t)warp * D + c * 4, make_float4(0.f, 0.f, 0.f, 0.f));
+    return;
+  }
+  long long id = texts[(size_t)b * L + p];
+  id = id < 0 ? 0 : (id >= vocab ? vocab - 1 : id);  // the reference would raise; clamp instead of faulting
+  for (int c = lane; c < nv; c += 32) {
+    const float4 e = ld4(emb + (size_t)id * D + c * 4), q = ld4(pe + (size_t)p * D + c * 4);
+    const float4 v = make_float4(e.x + q.x, e.y + q.y, e.z + q.z, e.w + q.w);
+    if (out_grid) st4(out_grid + (size_t)warp * D + c * 4, v);
+    if (out_user) st4(out_user + ((size_t)b * L + p) * D + c * 4, v);
+  }
+}
+
+__global__ void lens_to_i32_kernel(const int64_t* __restrict__ lens, int B, int cap, int* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < B) {
+    long long v = lens[i];
+    out[i] = (int)(v < 0 ? 0 : (v > cap ? cap : v));
+  }
+}
+
+// utils/tools.py:89-97  mask[b,i] = i >= lens[b]
+__global__ void mask_kernel(const int64_t* __restrict__ lens64, const int* __restrict__ lens32, int B, int max_len,
+                            uint8_t* __restrict__ mask) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)B * max_len) return;
+  const int b = (int)(i / max_len), p = (int)(i - (size_t)b * max_len);
+  const long long len = lens64 ? lens64[b] : (long long)lens32[b];
+  mask[i] = (uint8_t)(p >= len);
+}
+
+// model/modules.py:132-135  clamp(round(exp(log_d) - 1) * d_control, min=0); torch.round = half-to-even = rintf
+__device__ __forceinline__ float round_duration(float log_d, float d_control) {
+  return fmaxf(rintf(expf(log_d) - 1.0f) * d_control, 0.0f);
+}
+__global__ void round_durations_kernel(const float* __restrict__ log_d, int64_t n, float d_control,
+                                       float* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = round_duration(log_d[i], d_control);
+}
+
+// model/modules.py:206-222 bookkeeping: expand_size = max(int(d), 0); mel_len = sum.  One CTA per utterance,
+// block-wide inclusive scan (warp shuffles + one smem hop), chunks of 1024 phonemes.
+__global__ void __launch_bounds__(1024) duration_scan_kernel(const float* __restrict__ d, int L, int* __restrict__ cum,
+                                                             int64_t* __restrict__ mel_lens,
+                                                             int* __restrict__ mel_lens32, int* __restrict__ tmax) {
+  __shared__ int warp_tot[32];
+  __shared__ int carry_s;
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  if (tid == 0) carry_s = 0;
+  __syncthreads();
+  for (int base = 0; base < L; base += 1024) {
+    const int i = base + tid;
+    int v = 0;
+    if (i < L) {
+      const float f = d[(size_t)b * L + i];
+      // int() truncates toward zero; guard the conversion against inf/NaN/huge values
+      v = (f > 0.f) ? (f < 1.0e6f ? (int)f : 1000000) : 0;
+    }
+    int x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int y = __shfl_up_sync(0xffffffffu, x, o);
+      if (lane >= o) x += y;
+    }
+    if (lane == 31) warp_tot[w] = x;
+    __syncthreads();
+    if (w == 0) {
+      int t = warp_tot[lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int y = __shfl_up_sync(0xffffffffu, t, o);
+        if (lane >= o) t += y;
+      }
+      warp_tot[lane] = t;  // inclusive totals
+    }
+    __syncthreads();
+    const int carry = carry_s;
+    const int incl = carry + x + (w > 0 ? warp_tot[w - 1] : 0);
+    if (i < L) cum[(size_t)b * L + i] = incl;
+    __syncthreads();
+    if (tid == 1023) carry_s = incl;
+    __syncthreads();
+  }
+  if (tid == 0) {
+    const int total = carry_s;
+    if (mel_lens) mel_lens[b] = total;
+    if (mel_lens32) mel_lens32[b] = total;
+    if (tmax) atomicMax(tmax, total);
+  }
+}
+
+// model/modules.py:220-226 + utils/tools.py:288-306: frame t of utterance b copies phoneme row i with
+// cum[i-1] <= t < cum[i]; frames >= mel_len and halo rows are zero.  One warp per output row, the
+// utterance's cumulative table staged in shared memory, binary search per row, 16-byte row copy.
+__global__ void __launch_bounds__(256) length_regulate_kernel(const float* __restrict__ x, int x_utt_stride,
+                                                              const int* __restrict__ cum, int L, int D, int T,
+                                                              int out_SA, float* __restrict__ out) {
+  extern __shared__ int cum_s[];
+  const int b = blockIdx.y;
+  for (int i = threadIdx.x; i < L; i += blockDim.x) cum_s[i] = cum[(size_t)b * L + i];
+  __syncthreads();
+  const int total = L > 0 ? cum_s[L - 1] : 0;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int rows_per_cta = (blockDim.x >> 5) * 8;
+  const int nv = D >> 2;
+  for (int k = 0; k < 8; ++k) {
+    const int t = blockIdx.x * rows_per_cta + k * (blockDim.x >> 5) + w;
+    if (t >= out_SA) continue;
+    float* dst = out + ((size_t)b * out_SA + t) * D;
+    if (t >= total || t >= T) {
+      for (int c = lane; c < nv; c += 32) st4(dst + c * 4, make_float4(0.f, 0.f, 0.f, 0.f));
+      continue;
+    }
+    int lo = 0, hi = L - 1;  // first i with cum[i] > t
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (cum_s[mid] > t) hi = mid; else lo = mid + 1;
+    }
+    const float* src = x + (size_t)b * x_utt_stride + (size_t)lo * D;
+    for (int c = lane; c < nv; c += 32) st4(dst + c * 4, ld4(src + c * 4));
+  }
+}
+
+// model/modules.py:80-100 (inference branch) fused with the decoder's positional add (Models.py:231-233):
+//   pred <- pred * control ; idx = bucketize(pred, bins) ; x[row] += emb[idx] (+ pe[p])
+// torch.bucketize(right=False) lower bound, incl. its behaviour on NaN boundaries (every compare false -> n_bins-1).
+__global__ void variance_embed_kernel(float* __restrict__ pred, float control, const float* __restrict__ bins,
+                                      int n_bins, const float* __restrict__ emb, const float* __restrict__ pe,
+                                      float* __restrict__ x, bf16* __restrict__ xb, int B, int S, int SA, int D,
+                                      int* __restrict__ idx_out) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= B * S) return;
+  const int b = warp / S, p = warp - b * S;
+  const float v = pred[warp] * control;
+  int start = 0, end = n_bins - 1;  // boundaries array has n_bins-1 entries
+  while (start < end) {
+    const int mid = start + ((end - start) >> 1);
+    const float mv = __ldg(bins + mid);
+    if (!(mv >= v)) start = mid + 1; else end = mid;
+  }
+  if (lane == 0) {
+    pred[warp] = v;
+    if (idx_out) idx_out[warp] = start;
+  }
+  const size_t row = (size_t)b * SA + p;
+  const int nv = D >> 2;
+  for (int c = lane; c < nv; c += 32) {
+    float4 a = *reinterpret_cast<const float4*>(x + row * D + c * 4);
+    const float4 e = ld4(emb + (size_t)start * D + c * 4);
+    a.x += e.x; a.y += e.y; a.z += e.z; a.w += e.w;
+    if (pe) {
+      const float4 q = ld4(pe + (size_t)p * D + c * 4);
+      a.x += q.x; a.y += q.y; a.z += q.z; a.w += q.w;
+    }
+    st4(x + row * D + c * 4, a);
+    if (xb) {
+      __nv_bfloat162 lo = __floats2bfloat162_rn(a.x, a.y), hi = __floats2bfloat162_rn(a.z, a.w);
+      uint2 pk;
+      pk.x = *reinterpret_cast<uint32_t*>(&lo);
+      pk.y = *reinterpret_cast<uint32_t*>(&hi);
+      *reinterpret_cast<uint2*>(xb + row * D + c * 4) = pk;
+    }
+  }
+}
+
+// model/modules.py:166-192 GaussianUpsampling.  Per utterance: e = cumsum(d), c = e - d/2 (monotone non-decreasing
+// because d >= 0 on this path; negative durations fall back to the full range), w[i,t] = exp(-0.01 (t-c_i)^2) /
+// (sum_i exp(..) + 1e-20), out[t,:] = sum_i w[i,t] x[i,:].  exp(-0.01*D^2) is exactly 0 in fp32 for |D| >= 103
+// (denormal limit: 0.01*D^2 > 103.97), so each frame only visits the phonemes with |t - c_i| < 104 found by binary
+// search: O(band) instead of O(L) work per frame, identical sums.  One warp per frame; lanes split the band for the
+// weights (warp-shuffle normalisation), then split the D channels for the accumulation.
+__global__ void __launch_bounds__(256) gaussian_upsample_kernel(const float* __restrict__ x, const float* __restrict__ d,
+                                                                int L, int D, int T, int T_w, float* __restrict__ out,
+                                                                float* __restrict__ s_out, float* __restrict__ w_out) {
+  extern __shared__ float c_s[];  // [L] centres
+  __shared__ int mono_s;
+  const int b = blockIdx.y;
+  if (threadIdx.x == 0) {  // sequential fp32 cumsum: same association order as torch.cumsum on CPU
+    float e = 0.f;
+    int mono = 1;
+    float prev = -INFINITY;
+    for (int i = 0; i < L; ++i) {
+      const float di = d[(size_t)b * L + i];
+      e += di;
+      const float c = e - 0.5f * di;
+      c_s[i] = c;
+      if (!(c >= prev)) mono = 0;
+      prev = c;
+    }
+    mono_s = mono;
+    if (s_out && blockIdx.x == 0) s_out[b] = e;
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const int nv = D >> 2;
+  for (int t = blockIdx.x * nwarps + wp; t < T; t += gridDim.x * nwarps) {
+    float* dst = out + ((size_t)b * T + t) * D;
+    if (t >= T_w) {  // `pad(output, max_len)` rows
+      for (int c = lane; c < nv; c += 32) st4(dst + c * 4, make_float4(0.f, 0.f, 0.f, 0.f));
+      continue;
+    }
+    const float tf = (float)t;
+    int i_lo = 0, i_hi = L;
+    if (mono_s) {
+      int lo = 0, hi = L;  // first i with c_i > t - 104
+      while (lo < hi) { const int mid = (lo + hi) >> 1; if (c_s[mid] > tf - 104.f) hi = mid; else lo = mid + 1; }
+      i_lo = lo;
+      hi = L;              // first i with c_i >= t + 104
+      while (lo < hi) { const int mid = (lo + hi) >> 1; if (c_s[mid] >= tf + 104.f) hi = mid; else lo = mid + 1; }
+      i_hi = lo;
+    }
+    float part = 0.f;
+    for (int i = i_lo + lane; i < i_hi; i += 32) {
+      const float dl = tf - c_s[i];
+      part += expf(-0.01f * (dl * dl));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+    const float denom = part + 1e-20f;
+    if (w_out) {
+      for (int i = lane; i < L; i += 32) {
+        float wv = 0.f;
+        if (i >= i_lo && i < i_hi) { const float dl = tf - c_s[i]; wv = expf(-0.01f * (dl * dl)) / denom; }
+        w_out[((size_t)b * L + i) * T_w + t] = wv;
+      }
+    }
+    for (int c = lane; c < nv; c += 32) {
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int i = i_lo; i < i_hi; ++i) {
+        const float dl = tf - c_s[i];
+        const float wv = expf(-0.01f * (dl * dl)) / denom;
+        const float4 xv = ld4(x + ((size_t)b * L + i) * D + c * 4);
+        acc.x = fmaf(wv, xv.x, acc.x); acc.y = fmaf(wv, xv.y, acc.y);
+        acc.z = fmaf(wv, xv.z, acc.z); acc.w = fmaf(wv, xv.w, acc.w);
+      }
+      st4(dst + c * 4, acc);
+    }
+  }
+}
+
+// dense user layout [B,S,C] <-> halo'ed grid layout [B*SA, C]
+__global__ void to_grid_kernel(const float* __restrict__ xu, int B, int S, int SA, int C, float* __restrict__ out,
+                               int ldo, int col_off, bf16* __restrict__ out_b) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;  // one float4 per thread
+  const int nv = C >> 2;
+  if (i >= (size_t)B * SA * nv) return;
+  const size_t row = i / nv;
+  const int c = (int)(i - row * nv);
+  const int b = (int)(row / SA), p = (int)(row - (size_t)b * SA);
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (p < S) v = ld4(xu + ((size_t)b * S + p) * C + c * 4);
+  if (out) st4(out + row * ldo + col_off + c * 4, v);
+  if (out_b) {
+    __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+    uint2 pk;
+    pk.x = *reinterpret_cast<uint32_t*>(&lo);
+    pk.y = *reinterpret_cast<uint32_t*>(&hi);
+    *reinterpret_cast<uint2*>(out_b + row * C + c * 4) = pk;
+  }
+}
+__global__ void from_grid_kernel(const float* __restrict__ xg, int B, int S, int SA, int C, float* __restrict__ out) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int nv = C >> 2;
+  if (i >= (size_t)B * S * nv) return;
+  const size_t row = i / nv;
+  const int c = (int)(i - row * nv);
+  const int b = (int)(row / S), p = (int)(row - (size_t)b * S);
+  st4(out + row * C + c * 4, ld4(xg + ((size_t)b * SA + p) * C + c * 4));
+}
+
+// torch Conv1d / Linear weight [N][K][taps] -> fp32 [taps][K][n_total] (columns n_off..) and/or
+// bf16 [taps][n_total][K] (rows n_off..), optionally scaled per output channel (BatchNorm fold).
+__global__ void pack_weight_kernel(const float* __restrict__ src, int N, int K, int taps, const float* __restrict__ scale,
+                                   float* __restrict__ dst_f, bf16* __restrict__ dst_b, int n_total, int n_off) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)N * K * taps) return;
+  const int t = (int)(i % taps);
+  const int k = (int)((i / taps) % K);
+  const int n = (int)(i / ((size_t)taps * K));
+  float v = src[i];
+  if (scale) v *= scale[n];
+  if (dst_f) dst_f[((size_t)t * K + k) * n_total + n_off + n] = v;
+  if (dst_b) dst_b[((size_t)t * n_total + n_off + n) * K + k] = __float2bfloat16_rn(v);
+}
+
+// BatchNorm1d(eval) folded into the preceding conv (transformer/Layers.py:120-167, eps 1e-5):
+//   scale = g / sqrt(var + eps) ; bias' = (conv_bias - mean) * scale + b
+__global__ void bn_fold_kernel(const float* __restrict__ conv_bias, const float* __restrict__ g,
+                               const float* __restrict__ b, const float* __restrict__ mean,
+                               const float* __restrict__ var, int n, float eps, float* __restrict__ scale_out,
+                               float* __restrict__ bias_out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float s = g[i] / sqrtf(var[i] + eps);
+  scale_out[i] = s;
+  bias_out[i] = (conv_bias[i] - mean[i]) * s + b[i];
+}
+
+__global__ void f32_to_bf16_kernel(const float* __restrict__ src, int64_t n, bf16* __restrict__ dst) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = __float2bfloat16_rn(src[i]);
+}
+__global__ void bf16_to_f32_kernel(const bf16* __restrict__ src, int64_t n, float* __restrict__ dst) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = __bfloat162float(src[i]);
+}
+
+// V [B*SA, D] bf16 (grid layout) -> V^T [B*D, SAv]: row b*D + c, column p (columns >= SA zero).  Test helper for the
+// tcgen05 attention entry point; on the product path the QKV GEMM epilogue writes V^T directly.
+__global__ void transpose_v_kernel(const bf16* __restrict__ v, int B, int SA, int SAv, int D, bf16* __restrict__ vt) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)B * D * SAv) return;
+  const int p = (int)(i % SAv);
+  const size_t row = i / SAv;
+  const int c = (int)(row % D), b = (int)(row / D);
+  vt[i] = p < SA ? v[((size_t)b * SA + p) * D + c] : __float2bfloat16_rn(0.f);
+}
+
+// Models.py:231-233 alone: x[b,p,:] += pe[p,:] for p < S (+ bf16 shadow); used when no variance embedding is frame-level
+__global__ void add_pe_kernel(float* __restrict__ x, bf16* __restrict__ xb, const float* __restrict__ pe, int B, int S,
+                              int SA, int D) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int nv = D >> 2;
+  if (i >= (size_t)B * S * nv) return;
+  const size_t rowu = i / nv;
+  const int c = (int)(i - rowu * nv);
+  const int b = (int)(rowu / S), p = (int)(rowu - (size_t)b * S);
+  const size_t row = (size_t)b * SA + p;
+  float4 a = *reinterpret_cast<const float4*>(x + row * D + c * 4);
+  const float4 q = ld4(pe + (size_t)p * D + c * 4);
+  a.x += q.x; a.y += q.y; a.z += q.z; a.w += q.w;
+  st4(x + row * D + c * 4, a);
+  if (xb) {
+    __nv_bfloat162 lo = __floats2bfloat162_rn(a.x, a.y), hi = __floats2bfloat162_rn(a.z, a.w);
+    uint2 pk;
+    pk.x = *reinterpret_cast<uint32_t*>(&lo);
+    pk.y = *reinterpret_cast<uint32_t*>(&hi);
+    *reinterpret_cast<uint2*>(xb + row * D + c * 4) = pk;
+  }
+}
+
+inline unsigned blocks_for(size_t n, int per) { return (unsigned)((n + per - 1) / per); }
+
+}  // namespace
+
+#define LAUNCHED() (++g_fs2_launches, cudaGetLastError())
+
+cudaError_t rowops_embed_pe(const int64_t* texts, const float* emb, const float* pe, int vocab, int B, int L, int SA,
+                            int D, float* out_grid, float* out_user, cudaStream_t st) {
+  if (B * SA <= 0) return cudaSuccess;
+  embed_pe_kernel<<<blocks_for((size_t)B * SA, 8), 256, 0, st>>>(texts, emb, pe, vocab, B, L, SA, D, out_grid, out_user);
+  return LAUNCHED();
+}
+cudaError_t rowops_lens_to_i32(const int64_t* lens, int B, int cap, int* out, cudaStream_t st) {
+  if (B <= 0) return cudaSuccess;
+  lens_to_i32_kernel<<<blocks_for(B, 256), 256, 0, st>>>(lens, B, cap, out);
+  return LAUNCHED();
+}
+cudaError_t rowops_mask(const int64_t* lens64, const int* lens32, int B, int max_len, uint8_t* mask, cudaStream_t st) {
+  if ((size_t)B * max_len == 0) return cudaSuccess;
+  mask_kernel<<<blocks_for((size_t)B * max_len, 256), 256, 0, st>>>(lens64, lens32, B, max_len, mask);
+  return LAUNCHED();
+}
+cudaError_t rowops_round_durations(const float* log_d, int64_t n, float d_control, float* out, cudaStream_t st) {
+  if (n <= 0) return cudaSuccess;
+  round_durations_kernel<<<blocks_for((size_t)n, 256), 256, 0, st>>>(log_d, n, d_control, out);
+  return LAUNCHED();
+}
+cudaError_t rowops_duration_scan(const float* d, int B, int L, int* cum, int64_t* mel_lens, int* mel_lens32,
+                                 int* tmax_dev, cudaStream_t st) {
+  if (B <= 0) return cudaSuccess;
+  duration_scan_kernel<<<B, 1024, 0, st>>>(d, L, cum, mel_lens, mel_lens32, tmax_dev);
+  return LAUNCHED();
+}
+cudaError_t rowops_length_regulate(const float* x, int x_row_stride_utt, const int* cum, int B, int L, int D, int T,
+                                   int out_SA, float* out, cudaStream_t st) {
+  if (B <= 0 || out_SA <= 0) return cudaSuccess;
+  const size_t smem = sizeof(int) * (size_t)(L > 0 ? L : 1);
+  if (smem > 48 * 1024) return cudaErrorInvalidValue;
+  dim3 grid((out_SA + 63) / 64, B);
+  length_regulate_kernel<<<grid, 256, smem, st>>>(x, x_row_stride_utt, cum, L, D, T, out_SA, out);
+  return LAUNCHED();
+}
+cudaError_t rowops_variance_embed(float* pred, float control, const float* bins, int n_bins, const float* emb,
+                                  const float* pe, float* x, bf16* xb, int B, int S, int SA, int D, int* idx_out,
+                                  cudaStream_t st) {
+  if (B * S <= 0) return cudaSuccess;
+  variance_embed_kernel<<<blocks_for((size_t)B * S, 8), 256, 0, st>>>(pred, control, bins, n_bins, emb, pe, x, xb, B, S,
+                                                                     SA, D, idx_out);
+  return LAUNCHED();
+}
+cudaError_t rowops_gaussian_upsample(const float* x, const float* d, int B, int L, int D, int T, int T_w, float* out,
+                                     float* s, float* w, cudaStream_t st) {
+  if (B <= 0) return cudaSuccess;
+  const size_t smem = sizeof(float) * (size_t)(L > 0 ? L : 1);
+  if (smem > 48 * 1024) return cudaErrorInvalidValue;
+  int gx = (T + 7) / 8;
+  if (gx < 1) gx = 1;
+  if (gx > 1024) gx = 1024;
+  dim3 grid(gx, B);
+  gaussian_upsample_kernel<<<grid, 256, smem, st>>>(x, d, L, D, T, T_w, out, s, w);
+  return LAUNCHED();
+}
+cudaError_t rowops_to_grid(const float* x_user, int B, int S, int SA, int C, float* out, int ldo, int col_off,
+                           bf16* out_b, cudaStream_t st) {
+  const size_t n = (size_t)B * SA * (C / 4);
+  if (n == 0) return cudaSuccess;
+  to_grid_kernel<<<blocks_for(n, 256), 256, 0, st>>>(x_user, B, S, SA, C, out, ldo, col_off, out_b);
+  return LAUNCHED();
+}
+cudaError_t rowops_from_grid(const float* x_grid, int B, int S, int SA, int C, float* out_user, cudaStream_t st) {
+  const size_t n = (size_t)B * S * (C / 4);
+  if (n == 0) return cudaSuccess;
+  from_grid_kernel<<<blocks_for(n, 256), 256, 0, st>>>(x_grid, B, S, SA, C, out_user);
+  return LAUNCHED();
+}
+cudaError_t rowops_pack_weight(const float* src, int N, int K, int taps, const float* scale, float* dst_f,
+                               bf16* dst_b, int n_total, int n_off, cudaStream_t st) {
+  const size_t n = (size_t)N * K * taps;
+  if (n == 0) return cudaSuccess;
+  pack_weight_kernel<<<blocks_for(n, 256), 256, 0, st>>>(src, N, K, taps, scale, dst_f, dst_b, n_total, n_off);
+  return LAUNCHED();
+}
+cudaError_t rowops_bn_fold(const float* conv_bias, const float* g, const float* b, const float* mean,
+                           const float* var, int n, float eps, float* scale_out, float* bias_out, cudaStream_t st) {
+  if (n <= 0) return cudaSuccess;
+  bn_fold_kernel<<<blocks_for(n, 256), 256, 0, st>>>(conv_bias, g, b, mean, var, n, eps, scale_out, bias_out);
+  return LAUNCHED();
+}
+cudaError_t rowops_f32_to_bf16(const float* src, int64_t n, bf16* dst, cudaStream_t st) {
+  if (n <= 0) return cudaSuccess;
+  f32_to_bf16_kernel<<<blocks_for((size_t)n, 256), 256, 0, st>>>(src, n, dst);
+  return LAUNCHED();
+}
+cudaError_t rowops_bf16_to_f32(const bf16* src, int64_t n, float* dst, cudaStream_t st) {
+  if (n <= 0) return cudaSuccess;
+  bf16_to_f32_kernel<<<blocks_for((size_t)n, 256), 256, 0, st>>>(src, n, dst);
+  return LAUNCHED();
+}
+cudaError_t rowops_transpose_v(const bf16* v, int B, int SA, int SAv, int D, bf16* vt, cudaStream_t st) {
+  const size_t n = (size_t)B * D * SAv;
+  if (n == 0) return cudaSuccess;
+  transpose_v_kernel<<<blocks_for(n, 256), 256, 0, st>>>(v, B, SA, SAv, D, vt);
+  return LAUNCHED();
+}
+cudaError_t rowops_add_pe(float* x, bf16* xb, const float* pe, int B, int S, int SA, int D, cudaStream_t st) {
+  const size_t n = (size_t)B * S * (D / 4);
+  if (n == 0) return cudaSuccess;
+  add_pe_kernel<<<blocks_for(n, 256), 256, 0, st>>>(x, xb, pe, B, S, SA, D);
+  return LAUNCHED();
+}
+cudaError_t rowops_fill_zero(void* p, size_t bytes, cudaStream_t st) {
+  if (bytes == 0) return cudaSuccess;
+  return cudaMemsetAsync(p, 0, bytes, st);
+}

@@ -1,0 +1,195 @@
+// fs2_simt_attn.cu -- fp32 flash-style scaled-dot-product attention (sm_100a, FFMA path).
+//
+// Restates transformer/Modules.py:14-25 + the head split/merge of SubLayers.py:39-55:
+//   out[b, q, h*dk:(h+1)*dk] = softmax_k( Q_h[b,q,:] . K_h[b,k,:] / sqrt(dk)  masked(k >= len_b -> -inf) ) @ V_h[b]
+// without materialising the [H*B, S, S] matrix the reference builds (its callers discard it:
+// Models.py:97,241 return_attns=False).  Online softmax over 64-key tiles; one CTA = 32
+// queries of one (utterance, head).  Query rows >= len_b are written as zeros (the caller
+// masks them anyway, Layers.py:43).  Used for the fp32-faithful encoder and for fp32 mode.
+#include "fs2_common.cuh"
+#include <math.h>
+
+namespace {
+
+constexpr int BQ = 32;
+constexpr int BKV = 64;
+
+template <int DK>
+__global__ void __launch_bounds__(128) simt_attention_kernel(const float* __restrict__ qkv, int ldqkv, int q_off,
+                                                             int k_off, int v_off, const int* __restrict__ lens, int S,
+                                                             int SA, float* __restrict__ out, int ldo, float temperature) {
+  constexpr int QS = DK + 4;     // padded row stride (floats) of Q/K tiles: conflict-free float4 column walks
+  constexpr int PS = BKV + 4;
+  constexpr int DC = DK / 64;    // float4 output column groups per thread
+  extern __shared__ __align__(16) float smem[];
+  float* Qs = smem;                 // [BQ][QS]
+  float* Ks = Qs + BQ * QS;         // [BKV][QS]
+  float* Vs = Ks + BKV * QS;        // [BKV][DK]
+  float* Ps = Vs + BKV * DK;        // [BQ][PS]
+
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;  // ty in [0,8)
+  const int b = blockIdx.z, h = blockIdx.y;
+  const int p0 = blockIdx.x * BQ;
+  const int len = min(__ldg(lens + b), S);
+  const size_t row0 = (size_t)b * SA;
+
+  if (p0 >= len) {  // whole tile is padding: zeros
+    for (int idx = tid; idx < BQ * (DK / 4); idx += 128) {
+      const int q = idx / (DK / 4), c = idx % (DK / 4);
+      if (p0 + q < SA)
+        *reinterpret_cast<float4*>(out + (row0 + p0 + q) * ldo + h * DK + c * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    return;
+  }
+
+  // Q tile
+  for (int idx = tid; idx < BQ * (DK / 4); idx += 128) {
+    const int q = idx / (DK / 4), c = idx % (DK / 4);
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (p0 + q < len) v = __ldg(reinterpret_cast<const float4*>(qkv + (row0 + p0 + q) * ldqkv + q_off + h * DK + c * 4));
+    *reinterpret_cast<float4*>(Qs + q * QS + c * 4) = v;
+  }
+
+  float m[4], l[4], o[4][DC * 4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    m[i] = -INFINITY;
+    l[i] = 0.f;
+#pragma unroll
+    for (int c = 0; c < DC * 4; ++c) o[i][c] = 0.f;
+  }
+
+  for (int k0 = 0; k0 < len; k0 += BKV) {
+    __syncthreads();  // previous tile fully consumed (and Q tile visible on first pass)
+    for (int idx = tid; idx < BKV * (DK / 4); idx += 128) {
+      const int kr = idx / (DK / 4), c = idx % (DK / 4);
+      float4 kv = make_float4(0.f, 0.f, 0.f, 0.f), vv = kv;
+      if (k0 + kr < len) {
+        const float* base = qkv + (row0 + k0 + kr) * ldqkv + h * DK + c * 4;
+        kv = __ldg(reinterpret_cast<const float4*>(base + k_off));
+        vv = __ldg(reinterpret_cast<const float4*>(base + v_off));
+      }
+      *reinterpret_cast<float4*>(Ks + kr * QS + c * 4) = kv;
+      *reinterpret_cast<float4*>(Vs + kr * DK + c * 4) = vv;
+    }
+    __syncthreads();
+
+    // scores: queries ty + 8*i, keys tx + 16*j
+    float s[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) s[i][j] = 0.f;
+#pragma unroll 4
+    for (int d = 0; d < DK; d += 4) {
+      float4 qv[4], kv[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) qv[i] = *reinterpret_cast<const float4*>(Qs + (ty + 8 * i) * QS + d);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) kv[j] = *reinterpret_cast<const float4*>(Ks + (tx + 16 * j) * QS + d);
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          s[i][j] = fmaf(qv[i].x, kv[j].x, s[i][j]);
+          s[i][j] = fmaf(qv[i].y, kv[j].y, s[i][j]);
+          s[i][j] = fmaf(qv[i].z, kv[j].z, s[i][j]);
+          s[i][j] = fmaf(qv[i].w, kv[j].w, s[i][j]);
+        }
+    }
+    // scale, key mask, online softmax (row statistics shared by the 16 tx lanes of a half-warp)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float tmax = -INFINITY;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int key = k0 + tx + 16 * j;
+        s[i][j] = (key < len) ? s[i][j] / temperature : -INFINITY;
+        tmax = fmaxf(tmax, s[i][j]);
+      }
+#pragma unroll
+      for (int off = 8; off > 0; off >>= 1) tmax = fmaxf(tmax, __shfl_xor_sync(0xffffffffu, tmax, off));
+      const float m_new = fmaxf(m[i], tmax);  // finite: every processed tile holds >= 1 valid key
+      const float alpha = expf(m[i] - m_new);
+      float psum = 0.f;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float pv = expf(s[i][j] - m_new);
+        psum += pv;
+        Ps[(ty + 8 * i) * PS + tx + 16 * j] = pv;
+      }
+#pragma unroll
+      for (int off = 8; off > 0; off >>= 1) psum += __shfl_xor_sync(0xffffffffu, psum, off);
+      l[i] = l[i] * alpha + psum;
+      m[i] = m_new;
+#pragma unroll
+      for (int c = 0; c < DC * 4; ++c) o[i][c] *= alpha;
+    }
+    __syncthreads();
+
+    // O += P @ V : queries ty + 8*i, output columns tx*4 + 64*c .. +3
+#pragma unroll 2
+    for (int j = 0; j < BKV; j += 4) {
+      float4 pv[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) pv[i] = *reinterpret_cast<const float4*>(Ps + (ty + 8 * i) * PS + j);
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) {
+#pragma unroll
+        for (int c = 0; c < DC; ++c) {
+          const float4 vv = *reinterpret_cast<const float4*>(Vs + (j + jj) * DK + c * 64 + tx * 4);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float pw = jj == 0 ? pv[i].x : jj == 1 ? pv[i].y : jj == 2 ? pv[i].z : pv[i].w;
+            o[i][c * 4 + 0] = fmaf(pw, vv.x, o[i][c * 4 + 0]);
+            o[i][c * 4 + 1] = fmaf(pw, vv.y, o[i][c * 4 + 1]);
+            o[i][c * 4 + 2] = fmaf(pw, vv.z, o[i][c * 4 + 2]);
+            o[i][c * 4 + 3] = fmaf(pw, vv.w, o[i][c * 4 + 3]);
+          }
+        }
+      }
+    }
+  }
+
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int p = p0 + ty + 8 * i;
+    if (p >= SA) continue;
+    const bool valid = p < len;
+    const float inv = valid ? 1.0f / l[i] : 0.f;
+#pragma unroll
+    for (int c = 0; c < DC; ++c) {
+      float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (valid) r = make_float4(o[i][c * 4] * inv, o[i][c * 4 + 1] * inv, o[i][c * 4 + 2] * inv, o[i][c * 4 + 3] * inv);
+      *reinterpret_cast<float4*>(out + (row0 + p) * ldo + h * DK + c * 64 + tx * 4) = r;
+    }
+  }
+}
+
+template <int DK>
+cudaError_t launch(const float* qkv, int ldqkv, int q_off, int k_off, int v_off, const int* lens, int B, int S, int SA,
+                   int H, float* out, int ldo, cudaStream_t st) {
+  const size_t smem = sizeof(float) * (BQ * (DK + 4) + BKV * (DK + 4) + BKV * DK + BQ * (BKV + 4));
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(simt_attention_kernel<DK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  dim3 grid((SA + BQ - 1) / BQ, H, B);
+  simt_attention_kernel<DK><<<grid, 128, smem, st>>>(qkv, ldqkv, q_off, k_off, v_off, lens, S, SA, out, ldo,
+                                                      (float)sqrt((double)DK));
+  ++g_fs2_launches;
+  return cudaGetLastError();
+}
+
+}  // namespace
+
+cudaError_t simt_attention_launch(const float* qkv, int ldqkv, int q_off, int k_off, int v_off, const int* lens, int B,
+                                  int S, int SA, int H, int dk, float* out, int ldo, cudaStream_t st) {
+  if (B <= 0 || S <= 0) return cudaSuccess;
+  if (dk == 128) return launch<128>(qkv, ldqkv, q_off, k_off, v_off, lens, B, S, SA, H, out, ldo, st);
+  if (dk == 64) return launch<64>(qkv, ldqkv, q_off, k_off, v_off, lens, B, S, SA, H, out, ldo, st);
+  return cudaErrorInvalidValue;
+}

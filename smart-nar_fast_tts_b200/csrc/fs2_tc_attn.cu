@@ -1,0 +1,270 @@
+// fs2_tc_attn.cu -- tcgen05 flash attention for the decoder FFT blocks (sm_100a).
+//
+// Restates transformer/Modules.py:14-25 with the head split of SubLayers.py:39-55 (H = 2, d_k = 128):
+//   out[b, q, h*128:(h+1)*128] = softmax_k( Q_h[b,q,:] . K_h[b,k,:] / sqrt(128), keys >= len_b masked ) @ V_h[b]
+// One CTA = one (128-query tile, head, utterance).  The [S,S] score matrix never leaves the SM:
+//   warp 0   : TMA.  Q tile once, then a 2-stage ring of (K block [128 keys x 128], V^T block [128 d x 128 keys]).
+//   warp 1   : tcgen05.mma.  S = Q K^T (M=128,N=128,K=128) into TMEM columns [0,128); O += P V (M=128,N=128,K=128 keys)
+//              into TMEM columns [128,256).  S(j+1) is issued before P(j)V(j) so the softmax of block j+1 overlaps the
+//              PV MMA of block j.
+//   warps 2-5: online softmax, one thread per query row (= TMEM lane): tcgen05.ld S, scale + key mask, running max /
+//              sum in the exp2 domain, P written as bf16 into a 128B-swizzled K-major shared tile (A operand of the PV
+//              MMA), O rescaled in TMEM by exp2(m_old - m_new).
+// V is consumed K-major as V^T ([d, key]); the QKV GEMM epilogue (fs2_tc_gemm.cu, EPI_QKV) writes it in that layout.
+// Query rows >= len_b are written as zeros (masked by the caller anyway, Layers.py:43).
+#include "fs2_tc_common.cuh"
+#include "../../include/fs2_b200.h"
+
+namespace {
+
+using namespace tc;
+
+constexpr int BQ = 128, BKV = 128, DK = 128;
+constexpr int ATOM_BYTES = 128 * 128;            // 128 rows x 64 bf16
+constexpr int TILE_BYTES = 2 * ATOM_BYTES;       // 128 x 128 bf16 = 32 KB
+constexpr int Q_OFF = 0;
+constexpr int K_OFF = TILE_BYTES;                // 2 stages
+constexpr int V_OFF = K_OFF + 2 * TILE_BYTES;    // 2 stages
+constexpr int P_OFF = V_OFF + 2 * TILE_BYTES;
+constexpr int BAR_OFF = P_OFF + TILE_BYTES;      // 192 KB
+constexpr int NUM_BARS = 8;
+constexpr int SMEM_TOTAL = BAR_OFF + NUM_BARS * 8 + 16;
+constexpr int ATT_THREADS = 192;
+constexpr uint32_t TMEM_COLS = 256;
+
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+__global__ void __launch_bounds__(ATT_THREADS, 1)
+tc_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                    const __grid_constant__ CUtensorMap tmV, const int* __restrict__ lens, int S, int SA,
+                    bf16* __restrict__ out_b, float scale_log2) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  const uint32_t base = (raw_addr + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - raw_addr);
+  const uint32_t bars = base + BAR_OFF;
+  const uint32_t q_full = bars, kv_full0 = bars + 8, kv_empty0 = bars + 24, s_full = bars + 40, p_ready = bars + 48,
+                 o_ready = bars + 56;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + BAR_OFF + NUM_BARS * 8);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.z, h = blockIdx.y, p0 = blockIdx.x * BQ;
+  const int len = min(__ldg(lens + b), S);
+  const size_t row0 = (size_t)b * SA;
+
+  if (p0 >= len) {  // tile is all padding: zeros, no tensor work (uniform over the CTA)
+    for (int idx = threadIdx.x; idx < BQ * (DK / 8); idx += ATT_THREADS) {
+      const int q = idx / (DK / 8), c = idx % (DK / 8);
+      if (p0 + q < SA) *reinterpret_cast<uint4*>(out_b + (row0 + p0 + q) * 256 + h * DK + c * 8) = make_uint4(0, 0, 0, 0);
+    }
+    return;
+  }
+  const int nb = (len + BKV - 1) / BKV;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+    mbar_init(q_full, 1);
+    for (int s = 0; s < 2; ++s) { mbar_init(kv_full0 + 8 * s, 1); mbar_init(kv_empty0 + 8 * s, 1); }
+    mbar_init(s_full, 1);
+    mbar_init(p_ready, 128);
+    mbar_init(o_ready, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(smem_u32(tmem_slot), TMEM_COLS);
+    tmem_relinquish();
+  }
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_S = tmem_base, tmem_O = tmem_base + 128;
+
+  if (warp == 0) {
+    // ===================================================== TMA producer
+    if (lane == 0) {
+      mbar_expect_tx(q_full, TILE_BYTES);
+      tma_load_2d(base + Q_OFF, &tmQ, q_full, h * DK, (int)row0 + p0);
+      tma_load_2d(base + Q_OFF + ATOM_BYTES, &tmQ, q_full, h * DK + 64, (int)row0 + p0);
+      for (int j = 0; j < nb; ++j) {
+        const int s = j & 1;
+        mbar_wait(kv_empty0 + 8 * s, ((j >> 1) & 1) ^ 1u);
+        mbar_expect_tx(kv_full0 + 8 * s, 2 * TILE_BYTES);
+        const uint32_t ks = base + K_OFF + s * TILE_BYTES, vs = base + V_OFF + s * TILE_BYTES;
+        tma_load_2d(ks, &tmK, kv_full0 + 8 * s, h * DK, (int)row0 + j * BKV);
+        tma_load_2d(ks + ATOM_BYTES, &tmK, kv_full0 + 8 * s, h * DK + 64, (int)row0 + j * BKV);
+        tma_load_2d(vs, &tmV, kv_full0 + 8 * s, j * BKV, (b * 2 + h) * DK);
+        tma_load_2d(vs + ATOM_BYTES, &tmV, kv_full0 + 8 * s, j * BKV + 64, (b * 2 + h) * DK);
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================== MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(128, 128);
+      auto issue_S = [&](int j) {
+        const int s = j & 1;
+        mbar_wait(kv_full0 + 8 * s, (j >> 1) & 1);
+        fence_after_sync();
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) {
+          const uint32_t off = (kk >> 2) * ATOM_BYTES;
+          const uint64_t ad = make_smem_desc_sw128(base + Q_OFF + off) + (uint64_t)(2 * (kk & 3));
+          const uint64_t bd = make_smem_desc_sw128(base + K_OFF + s * TILE_BYTES + off) + (uint64_t)(2 * (kk & 3));
+          umma_bf16(tmem_S, ad, bd, idesc, kk ? 1u : 0u);
+        }
+        umma_commit(s_full);
+      };
+      mbar_wait(q_full, 0);
+      issue_S(0);
+      for (int j = 0; j < nb; ++j) {
+        const int s = j & 1;
+        mbar_wait(p_ready, j & 1);     // P(j) in smem, O rescaled, S(j) fully consumed
+        fence_after_sync();
+        if (j + 1 < nb) issue_S(j + 1);
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) {
+          const uint32_t off = (kk >> 2) * ATOM_BYTES;
+          const uint64_t ad = make_smem_desc_sw128(base + P_OFF + off) + (uint64_t)(2 * (kk & 3));
+          const uint64_t bd = make_smem_desc_sw128(base + V_OFF + s * TILE_BYTES + off) + (uint64_t)(2 * (kk & 3));
+          umma_bf16(tmem_O, ad, bd, idesc, (j | kk) ? 1u : 0u);
+        }
+        umma_commit(kv_empty0 + 8 * s);
+        umma_commit(o_ready);
+      }
+    }
+  } else {
+    // ===================================================== softmax warps (one thread = one query row)
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+    uint8_t* p_row = smem + P_OFF + row * 128;  // + atom*ATOM_BYTES + swizzled 16-byte chunk
+    const int sw = row & 7;
+    float m = -INFINITY, l = 0.f;
+    uint32_t v[32];
+    for (int j = 0; j < nb; ++j) {
+      mbar_wait(s_full, j & 1);
+      fence_after_sync();
+      // pass A: block maximum of the scaled, masked scores
+      float bm = -INFINITY;
+      for (int c = 0; c < 4; ++c) {
+        __syncwarp();
+        tmem_ld32(tmem_S + lane_off + c * 32, v);
+        tmem_wait_ld();
+        const int kbase = j * BKV + c * 32;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const float t = (kbase + i < len) ? __uint_as_float(v[i]) * scale_log2 : -INFINITY;
+          bm = fmaxf(bm, t);
+        }
+      }
+      const float m_new = fmaxf(m, bm);          // finite: every processed block holds >= 1 valid key
+      const float alpha = fast_exp2(m - m_new);  // 0 on the first block (m = -inf)
+      if (j > 0) {                               // P buffer and O are free once P(j-1)V(j-1) has completed
+        mbar_wait(o_ready, (j - 1) & 1);
+        fence_after_sync();
+      }
+      // pass B: P = exp2(t - m_new) -> bf16 swizzled smem tile; row sum
+      float bsum = 0.f;
+      for (int c = 0; c < 4; ++c) {
+        __syncwarp();
+        tmem_ld32(tmem_S + lane_off + c * 32, v);
+        tmem_wait_ld();
+        const int kbase = j * BKV + c * 32;
+        float pv[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const float t = (kbase + i < len) ? __uint_as_float(v[i]) * scale_log2 : -INFINITY;
+          pv[i] = fast_exp2(t - m_new);
+          bsum += pv[i];
+        }
+        uint8_t* atom = p_row + (c >> 1) * ATOM_BYTES;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int ch = ((c & 1) * 4 + u) ^ sw;
+          *reinterpret_cast<uint4*>(atom + ch * 16) =
+              make_uint4(pack_bf16x2(pv[u * 8], pv[u * 8 + 1]), pack_bf16x2(pv[u * 8 + 2], pv[u * 8 + 3]),
+                         pack_bf16x2(pv[u * 8 + 4], pv[u * 8 + 5]), pack_bf16x2(pv[u * 8 + 6], pv[u * 8 + 7]));
+        }
+      }
+      l = l * alpha + bsum;
+      m = m_new;
+      if (j > 0) {  // rescale the running output
+        for (int c = 0; c < 4; ++c) {
+          __syncwarp();
+          tmem_ld32(tmem_O + lane_off + c * 32, v);
+          tmem_wait_ld();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
+          tmem_st32(tmem_O + lane_off + c * 32, v);
+        }
+        tmem_wait_st();
+      }
+      fence_proxy_async();   // P tile (generic-proxy stores) -> visible to the tensor core's async proxy
+      fence_before_sync();
+      mbar_arrive(p_ready);
+    }
+    // final: O / l -> bf16
+    mbar_wait(o_ready, (nb - 1) & 1);
+    fence_after_sync();
+    const int p = p0 + row;
+    const bool writable = p < SA;
+    const bool valid = p < len;
+    const float inv = valid ? 1.0f / l : 0.f;
+    bf16* o = out_b + (row0 + (writable ? p : 0)) * 256 + h * DK;
+    for (int c = 0; c < 4; ++c) {
+      __syncwarp();
+      tmem_ld32(tmem_O + lane_off + c * 32, v);
+      tmem_wait_ld();
+      if (writable) {
+#pragma unroll
+        for (int i = 0; i < 32; i += 8) {
+          float y[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) y[u] = valid ? __uint_as_float(v[i + u]) * inv : 0.f;
+          *reinterpret_cast<uint4*>(o + c * 32 + i) =
+              make_uint4(pack_bf16x2(y[0], y[1]), pack_bf16x2(y[2], y[3]), pack_bf16x2(y[4], y[5]), pack_bf16x2(y[6], y[7]));
+        }
+      }
+    }
+  }
+
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 1) {
+    fence_after_sync();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+}  // namespace
+
+int tc_attention_launch(const bf16* q, const bf16* k, const bf16* vt, const int* lens, int B, int S, int SA, int SAv,
+                        int H, bf16* out_b, cudaStream_t st) {
+  if (B <= 0 || S <= 0) return FS2_OK;
+  if (H != 2) return fs2_fail_cuda(cudaErrorInvalidValue, "tc_attention: built for H = 2, d_k = 128");
+  const uint64_t R = (uint64_t)B * SA;
+  CUtensorMap tmQ, tmK, tmV;
+  if (!tc::make_tmap_bf16(&tmQ, q, R, 256, 256, BQ) || !tc::make_tmap_bf16(&tmK, k, R, 256, 256, BKV) ||
+      !tc::make_tmap_bf16(&tmV, vt, (uint64_t)B * 256, (uint64_t)SAv, (uint64_t)SAv, DK))
+    return fs2_fail_cuda(cudaErrorInvalidValue, "cuTensorMapEncodeTiled(attention)");
+  static bool configured = false;
+  const int smem = SMEM_TOTAL + 1024;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(tc_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return fs2_fail_cuda(e, "cudaFuncSetAttribute(tc_attention)");
+    configured = true;
+  }
+  dim3 grid((SA + BQ - 1) / BQ, H, B);
+  const float scale_log2 = (float)(1.4426950408889634 / sqrt((double)DK));
+  tc_attention_kernel<<<grid, ATT_THREADS, smem, st>>>(tmQ, tmK, tmV, lens, S, SA, out_b, scale_log2);
+  ++g_fs2_launches;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fs2_fail_cuda(e, "tc_attention_kernel launch");
+  return FS2_OK;
+}

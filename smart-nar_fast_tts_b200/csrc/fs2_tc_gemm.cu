@@ -1,0 +1,367 @@
+// fs2_tc_gemm.cu -- tcgen05 / TMEM / TMA implicit-GEMM Conv1d + Linear for sm_100a with fused epilogues.
+//
+// Computes, for the decoder FFT blocks (transformer/SubLayers.py:39-41,56,89-93), mel_linear
+// (model/fastspeech2_align.py:83) and PostNet (transformer/Layers.py:169-177):
+//     out[r, n] = epi( sum_t sum_k A[r + t - pad, k] * W[t][n][k] + bias[n] )
+// over the flat halo'ed row grid (fs2_common.cuh), bf16 operands, fp32 accumulation in TMEM.
+//
+// Structure (persistent, warp specialised, one CTA per SM):
+//   warp 0   : TMA producer.  Per k-step one 128x64 bf16 box of A at row coordinate r0 + t - pad (the conv tap is a
+//              row shift of the SAME activation tensor; rows outside the buffer are zero-filled by TMA = Conv1d zero
+//              padding) and one BNx64 box of W_t, into a 4-stage 128B-swizzled shared-memory ring (mbarrier tx-count).
+//   warp 1   : allocates TMEM (2 accumulator stages of BN fp32 columns) and issues tcgen05.mma (M=128, N=BN, K=16)
+//              from one elected lane; tcgen05.commit releases ring slots and publishes finished accumulators.
+//   warps 2-5: epilogue.  Thread = one output row (TMEM lane); tcgen05.ld 32 columns at a time; bias / ReLU / tanh /
+//              residual / LayerNorm(256) / row mask / final dot fused; the LayerNorm row statistics need no shuffles
+//              because a thread owns its whole row; the pre-norm row is parked back in TMEM (tcgen05.st) between the
+//              statistics pass and the normalise pass.  Overlaps with the next tile's mainloop (accumulator double buffer).
+#include "fs2_tc_common.cuh"
+#include "../../include/fs2_b200.h"
+
+namespace {
+
+using namespace tc;
+
+constexpr int BM = 128;
+constexpr int BKE = 64;        // bf16 elements per k-block = 128 bytes = one swizzle row
+constexpr int STAGES = 4;
+constexpr int NUM_THREADS = 192;
+
+template <int BN>
+struct SmemLayout {
+  static constexpr int A_BYTES = BM * BKE * 2;   // 16 KB
+  static constexpr int B_BYTES = BN * BKE * 2;   // 32 KB (BN=256) / 16 KB (BN=128)
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int RING_BYTES = STAGES * STAGE_BYTES;
+  static constexpr int PARAM_FLOATS = BN + 3 * 256;  // bias tile, ln_g, ln_b, dot_w
+  static constexpr int BAR_OFF = RING_BYTES + PARAM_FLOATS * 4;
+  static constexpr int NUM_BARS = 2 * STAGES + 4;
+  static constexpr int TOTAL = BAR_OFF + NUM_BARS * 8 + 16;
+};
+
+struct RowInfo {
+  int r, b, p;
+  bool in_buf, in_grid, keep_len, keep;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+tc_conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                    const ConvGemmArgs a, const int num_m_blocks, const int num_n_blocks) {
+  using L = SmemLayout<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  // 1024-byte alignment for the 128B-swizzled tiles
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  const uint32_t base = (raw_addr + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - raw_addr);
+  float* s_bias = reinterpret_cast<float*>(smem + L::RING_BYTES);
+  float* s_g = s_bias + BN;
+  float* s_b = s_g + 256;
+  float* s_dw = s_b + 256;
+  const uint32_t bars = base + L::BAR_OFF;
+  auto full_bar = [&](int s) { return bars + 8u * s; };
+  auto empty_bar = [&](int s) { return bars + 8u * (STAGES + s); };
+  auto tfull_bar = [&](int s) { return bars + 8u * (2 * STAGES + s); };
+  auto tempty_bar = [&](int s) { return bars + 8u * (2 * STAGES + 2 + s); };
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L::BAR_OFF + L::NUM_BARS * 8);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int pad = (a.taps - 1) / 2;
+  const int KB = (a.K + BKE - 1) / BKE;
+  const int iters = a.taps * KB;
+  const int num_tiles = num_m_blocks * num_n_blocks;
+  constexpr uint32_t TMEM_COLS = 2 * BN;  // 512 or 256: power of two
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 4); }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(smem_u32(tmem_slot), TMEM_COLS);
+    tmem_relinquish();
+  }
+  if (warp >= 2) {  // LayerNorm / dot parameters are tile independent
+    const int t = threadIdx.x - 64;
+    const bool ln = (a.epi == EPI_RES_LN || a.epi == EPI_RELU_LN || a.epi == EPI_RELU_LN_DOT);
+    for (int i = t; i < 256; i += 128) {
+      s_g[i] = ln ? __ldg(a.ln_g + i) : 1.f;
+      s_b[i] = ln ? __ldg(a.ln_b + i) : 0.f;
+      s_dw[i] = (a.epi == EPI_RELU_LN_DOT) ? __ldg(a.dot_w + i) : 0.f;
+    }
+  }
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================================================== TMA producer
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_blk = tile / num_n_blocks, n_blk = tile - m_blk * num_n_blocks;
+        const int r0 = m_blk * BM, n0 = n_blk * BN;
+        for (int it = 0; it < iters; ++it) {
+          const int t = it / KB, k0 = (it - t * KB) * BKE;
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          mbar_expect_tx(full_bar(stage), L::STAGE_BYTES);
+          const uint32_t sa = base + stage * L::STAGE_BYTES;
+          tma_load_2d(sa, &tmA, full_bar(stage), k0, r0 + t - pad);
+          tma_load_2d(sa + L::A_BYTES, &tmB, full_bar(stage), k0, t * a.N + n0);
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================== MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(BM, BN);
+      int stage = 0; uint32_t phase = 0;
+      int as = 0; uint32_t aphase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(tempty_bar(as), aphase ^ 1u);  // epilogue has drained this accumulator stage
+        fence_after_sync();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(as * BN);
+        for (int it = 0; it < iters; ++it) {
+          mbar_wait(full_bar(stage), phase);
+          fence_after_sync();
+          const uint32_t sa = base + stage * L::STAGE_BYTES;
+          const uint64_t adesc = make_smem_desc_sw128(sa);
+          const uint64_t bdesc = make_smem_desc_sw128(sa + L::A_BYTES);
+#pragma unroll
+          for (int k = 0; k < BKE / 16; ++k)  // 16 bf16 = 32 bytes = +2 in the (addr >> 4) field
+            umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (it | k) ? 1u : 0u);
+          umma_commit(empty_bar(stage));   // ring slot reusable once these MMAs have read it
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit(tfull_bar(as));        // accumulator complete
+        if (++as == 2) { as = 0; aphase ^= 1u; }
+      }
+    }
+  } else {
+    // ===================================================== epilogue (warps 2..5, 128 threads)
+    const int q = warp & 3;                 // TMEM lane quarter this warp may access
+    const int row_in_tile = q * 32 + lane;
+    const int R = a.B * a.SA;
+    int as = 0; uint32_t aphase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m_blk = tile / num_n_blocks, n_blk = tile - m_blk * num_n_blocks;
+      const int n0 = n_blk * BN;
+      // bias slice of this tile (guarded by a named barrier over the 128 epilogue threads)
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      for (int i = threadIdx.x - 64; i < BN; i += 128) s_bias[i] = (n0 + i < a.N) ? __ldg(a.bias + n0 + i) : 0.f;
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+
+      RowInfo ri;
+      ri.r = m_blk * BM + row_in_tile;
+      ri.in_buf = ri.r < R;
+      ri.b = ri.in_buf ? ri.r / a.SA : 0;
+      ri.p = ri.in_buf ? ri.r - ri.b * a.SA : 0;
+      ri.in_grid = ri.in_buf && ri.p < a.S;
+      ri.keep_len = ri.in_grid && (a.lens == nullptr || ri.p < __ldg(a.lens + ri.b));
+      ri.keep = (a.mask_mode == MASK_LEN) ? ri.keep_len : ri.in_grid;
+
+      mbar_wait(tfull_bar(as), aphase);
+      fence_after_sync();
+      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN);
+      const int ncols = min(BN, a.N - n0);          // valid columns in this tile (multiple of 8)
+      const int nchunks = (ncols + 31) / 32;
+      uint32_t v[32];
+
+      if (a.epi == EPI_RES_LN || a.epi == EPI_RELU_LN || a.epi == EPI_RELU_LN_DOT) {
+        // ---- pass 1: pre-norm value, row statistics, park the row back in TMEM
+        float sum = 0.f, sq = 0.f;
+        for (int c = 0; c < BN / 32; ++c) {
+          __syncwarp();
+          tmem_ld32(t_row + c * 32, v);
+          tmem_wait_ld();
+          const float* res = (a.epi == EPI_RES_LN && ri.in_buf) ? a.residual + (size_t)ri.r * a.N + c * 32 : nullptr;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            float4 rv = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (res) rv = __ldg(reinterpret_cast<const float4*>(res + j));
+            const float rr[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              float x = __uint_as_float(v[j + u]) + s_bias[c * 32 + j + u] + rr[u];
+              if (a.epi != EPI_RES_LN) x = fmaxf(x, 0.f);
+              sum += x;
+              sq = fmaf(x, x, sq);
+              v[j + u] = __float_as_uint(x);
+            }
+          }
+          tmem_st32(t_row + c * 32, v);
+        }
+        tmem_wait_st();
+        const float mean = sum * (1.0f / 256.0f);
+        const float var = fmaxf(sq * (1.0f / 256.0f) - mean * mean, 0.f);
+        const float rstd = rsqrtf(var + 1e-5f);
+        // ---- pass 2: normalise, affine, mask, store
+        float dot = 0.f;
+        for (int c = 0; c < BN / 32; ++c) {
+          __syncwarp();
+          tmem_ld32(t_row + c * 32, v);
+          tmem_wait_ld();
+          float y[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float x = (__uint_as_float(v[j]) - mean) * rstd * s_g[c * 32 + j] + s_b[c * 32 + j];
+            y[j] = ri.keep ? x : 0.f;
+            dot = fmaf(x, s_dw[c * 32 + j], dot);
+          }
+          if (a.epi != EPI_RELU_LN_DOT && ri.in_buf) {
+            if (a.out) {
+              float* o = a.out + (size_t)ri.r * a.ldo + c * 32;
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(y[j], y[j + 1], y[j + 2], y[j + 3]);
+            }
+            if (a.out_b) {
+              bf16* o = a.out_b + (size_t)ri.r * a.ldob + c * 32;
+#pragma unroll
+              for (int j = 0; j < 32; j += 8)
+                *reinterpret_cast<uint4*>(o + j) = make_uint4(pack_bf16x2(y[j], y[j + 1]), pack_bf16x2(y[j + 2], y[j + 3]),
+                                                              pack_bf16x2(y[j + 4], y[j + 5]), pack_bf16x2(y[j + 6], y[j + 7]));
+            }
+          }
+        }
+        if (a.epi == EPI_RELU_LN_DOT && ri.in_grid && a.out_user)
+          a.out_user[(size_t)ri.b * a.S + ri.p] = ri.keep_len ? dot + a.dot_b : 0.f;
+      } else if (a.epi == EPI_QKV) {
+        // n_blk 0 -> Q, 1 -> K (bf16 row-major [R,256]); 2 -> V transposed per utterance: vt[(b*256 + c), p]
+        for (int c = 0; c < BN / 32; ++c) {
+          __syncwarp();
+          tmem_ld32(t_row + c * 32, v);
+          tmem_wait_ld();
+          float y[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) y[j] = ri.in_grid ? __uint_as_float(v[j]) + s_bias[c * 32 + j] : 0.f;
+          if (ri.in_buf && n_blk < 2) {
+            bf16* o = (n_blk == 0 ? a.q_b : a.k_b) + (size_t)ri.r * 256 + c * 32;
+#pragma unroll
+            for (int j = 0; j < 32; j += 8)
+              *reinterpret_cast<uint4*>(o + j) = make_uint4(pack_bf16x2(y[j], y[j + 1]), pack_bf16x2(y[j + 2], y[j + 3]),
+                                                            pack_bf16x2(y[j + 4], y[j + 5]), pack_bf16x2(y[j + 6], y[j + 7]));
+          } else if (ri.in_buf) {
+            bf16* o = a.vt_b + ((size_t)ri.b * 256 + c * 32) * a.SAv + ri.p;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) o[(size_t)j * a.SAv] = __float2bfloat16_rn(y[j]);
+          }
+        }
+      } else {
+        // ---- EPI_BIAS / EPI_RELU / EPI_TANH / EPI_RES
+        for (int c = 0; c < nchunks; ++c) {
+          __syncwarp();
+          tmem_ld32(t_row + c * 32, v);
+          tmem_wait_ld();
+          const int nb = n0 + c * 32;
+          float y[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            float x = __uint_as_float(v[j]) + s_bias[c * 32 + j];
+            if (a.epi == EPI_RELU) x = fmaxf(x, 0.f);
+            if (a.epi == EPI_TANH) x = tanhf(x);
+            y[j] = x;
+          }
+          if (a.epi == EPI_RES && ri.in_buf) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              if (nb + j < a.N) {
+                const float4 rv = __ldg(reinterpret_cast<const float4*>(a.residual + (size_t)ri.r * a.N + nb + j));
+                y[j] += rv.x; y[j + 1] += rv.y; y[j + 2] += rv.z; y[j + 3] += rv.w;
+              }
+            }
+          }
+          if (!ri.keep) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) y[j] = 0.f;
+          }
+          if (a.out && ri.in_buf) {
+            float* o = a.out + (size_t)ri.r * a.ldo + nb;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+              if (nb + j < a.N) *reinterpret_cast<float4*>(o + j) = make_float4(y[j], y[j + 1], y[j + 2], y[j + 3]);
+          }
+          if (a.out_b && ri.in_buf) {
+            bf16* o = a.out_b + (size_t)ri.r * a.ldob + nb;
+#pragma unroll
+            for (int j = 0; j < 32; j += 8)
+              if (nb + j < a.N)
+                *reinterpret_cast<uint4*>(o + j) = make_uint4(pack_bf16x2(y[j], y[j + 1]), pack_bf16x2(y[j + 2], y[j + 3]),
+                                                              pack_bf16x2(y[j + 4], y[j + 5]), pack_bf16x2(y[j + 6], y[j + 7]));
+          }
+          if (a.out_user && ri.in_grid) {
+            float* o = a.out_user + ((size_t)ri.b * a.S + ri.p) * a.ldu + nb;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+              if (nb + j < a.N) *reinterpret_cast<float4*>(o + j) = make_float4(y[j], y[j + 1], y[j + 2], y[j + 3]);
+          }
+        }
+      }
+      // release the accumulator stage to the MMA warp
+      fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(as));
+      if (++as == 2) { as = 0; aphase ^= 1u; }
+    }
+  }
+
+  // teardown: everyone done with TMEM before the allocating warp frees it
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 1) {
+    fence_after_sync();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+int g_num_sms = 0;
+
+template <int BN>
+int launch(const ConvGemmArgs& a, cudaStream_t st) {
+  using L = SmemLayout<BN>;
+  const int R = a.B * a.SA;
+  const int num_m_blocks = (R + BM - 1) / BM;
+  const int num_n_blocks = (a.N + BN - 1) / BN;
+  CUtensorMap tmA, tmB;
+  if (!make_tmap_bf16(&tmA, a.Ab, (uint64_t)R, (uint64_t)a.K, (uint64_t)a.K, BM))
+    return fs2_fail_cuda(cudaErrorInvalidValue, "cuTensorMapEncodeTiled(A)");
+  if (!make_tmap_bf16(&tmB, a.Wb, (uint64_t)a.taps * a.N, (uint64_t)a.K, (uint64_t)a.K, BN))
+    return fs2_fail_cuda(cudaErrorInvalidValue, "cuTensorMapEncodeTiled(W)");
+  static bool configured = false;
+  const int smem = L::TOTAL + 1024;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(tc_conv_gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return fs2_fail_cuda(e, "cudaFuncSetAttribute(tc_conv_gemm)");
+    configured = true;
+  }
+  if (g_num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g_num_sms <= 0) g_num_sms = 148;
+  }
+  const int tiles = num_m_blocks * num_n_blocks;
+  const int grid = tiles < g_num_sms ? tiles : g_num_sms;
+  tc_conv_gemm_kernel<BN><<<grid, NUM_THREADS, smem, st>>>(tmA, tmB, a, num_m_blocks, num_n_blocks);
+  ++g_fs2_launches;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fs2_fail_cuda(e, "tc_conv_gemm_kernel launch");
+  return FS2_OK;
+}
+
+}  // namespace
+
+int tc_conv_gemm_launch(const ConvGemmArgs& a, cudaStream_t st) {
+  const int R = a.B * a.SA;
+  if (R <= 0) return FS2_OK;
+  if (!a.Ab || !a.Wb || a.K % 8 != 0 || a.N % 8 != 0) return fs2_fail_cuda(cudaErrorInvalidValue, "tc_conv_gemm: operands");
+  const bool ln = (a.epi == EPI_RES_LN || a.epi == EPI_RELU_LN || a.epi == EPI_RELU_LN_DOT);
+  if (ln && a.N != 256) return fs2_fail_cuda(cudaErrorInvalidValue, "tc_conv_gemm: LayerNorm epilogue needs N == 256");
+  if (a.epi == EPI_QKV && a.N != 768) return fs2_fail_cuda(cudaErrorInvalidValue, "tc_conv_gemm: QKV epilogue needs N == 768");
+  if (a.N % 256 == 0) return launch<256>(a, st);
+  if (a.N <= 128) return launch<128>(a, st);
+  return fs2_fail_cuda(cudaErrorInvalidValue, "tc_conv_gemm: N must be a multiple of 256 or <= 128");
+}

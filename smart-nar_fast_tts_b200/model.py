@@ -1,0 +1,296 @@
+"""Host-side mirror of the reference's `model.FastSpeech2Align` (model/fastspeech2_align.py:13-100).
+
+Same constructor, same `forward(speakers, texts, src_lens, max_src_len, ...)` signature, same 12-tuple
+of outputs (shapes / dtypes / devices), same `state_dict` key layout (so `utils/model.py:16-22`'s
+`load_state_dict(ckpt["model"])` works unchanged, `mel_encoder.*` included) -- but the nn.Modules
+below are parameter CONTAINERS only.  All arithmetic happens in libfs2_b200.so (hand-written sm_100a
+kernels) through the C ABI in include/fs2_b200.h; PyTorch provides device memory and the stream.
+There is no CPU or eager-PyTorch fallback: without the library or without a CUDA device `forward` raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import json
+import os
+from collections import OrderedDict
+from typing import Callable, Optional
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from .capi import Dims, Fs2Error, PREC_BF16, PREC_FP32, WeightDesc, load_library
+
+N_SRC_VOCAB_LJSPEECH = 361  # len(text.symbols) + 1 (transformer/Models.py:40)
+
+
+# --------------------------------------------------------------------------- parameter containers
+def _sinusoid_table(n_position: int, d_hid: int) -> torch.Tensor:
+    """transformer/Models.py:10-30 (float64 -> float32)."""
+    j = np.arange(d_hid)
+    tab = np.arange(n_position, dtype=np.float64)[:, None] / np.power(10000, 2 * (j // 2) / d_hid)[None, :]
+    tab[:, 0::2] = np.sin(tab[:, 0::2])
+    tab[:, 1::2] = np.cos(tab[:, 1::2])
+    return torch.from_numpy(tab.astype(np.float32))
+
+
+class _Attn(nn.Module):  # SubLayers.py:11-27
+    def __init__(self, n_head, d_model, d_k, d_v):
+        super().__init__()
+        self.w_qs = nn.Linear(d_model, n_head * d_k)
+        self.w_ks = nn.Linear(d_model, n_head * d_k)
+        self.w_vs = nn.Linear(d_model, n_head * d_v)
+        self.layer_norm = nn.LayerNorm(d_model)
+        self.fc = nn.Linear(n_head * d_v, d_model)
+
+
+class _FFN(nn.Module):  # SubLayers.py:65-85
+    def __init__(self, d_in, d_hid, kernel_size):
+        super().__init__()
+        self.w_1 = nn.Conv1d(d_in, d_hid, kernel_size=kernel_size[0], padding=(kernel_size[0] - 1) // 2)
+        self.w_2 = nn.Conv1d(d_hid, d_in, kernel_size=kernel_size[1], padding=(kernel_size[1] - 1) // 2)
+        self.layer_norm = nn.LayerNorm(d_in)
+
+
+class _FFTBlock(nn.Module):  # Layers.py:32-37 (attn_name = "crs_attn" for the training-only FFTBlock2, :54-59)
+    def __init__(self, d_model, n_head, d_inner, kernel_size, attn_name="slf_attn"):
+        super().__init__()
+        setattr(self, attn_name, _Attn(n_head, d_model, d_model // n_head, d_model // n_head))
+        self.pos_ffn = _FFN(d_model, d_inner, kernel_size)
+
+
+class _Stack(nn.Module):  # Models.py:36-71 / 179-210 / 106-138
+    def __init__(self, cfg, which: str, n_src_vocab: Optional[int] = None):
+        super().__init__()
+        t = cfg["transformer"]
+        side = "encoder" if which == "txt_encoder" else "decoder"
+        d_model, n_layers, n_head = t[f"{side}_hidden"], t[f"{side}_layer"], t[f"{side}_head"]
+        if which == "txt_encoder":
+            self.src_word_emb = nn.Embedding(n_src_vocab, d_model, padding_idx=0)
+        if which == "mel_encoder":
+            self.prenet = _Prenet()
+        self.position_enc = nn.Parameter(_sinusoid_table(cfg["max_seq_len"] + 1, d_model).unsqueeze(0), requires_grad=False)
+        attn = "crs_attn" if which == "mel_encoder" else "slf_attn"
+        self.layer_stack = nn.ModuleList(
+            [_FFTBlock(d_model, n_head, t["conv_filter_size"], t["conv_kernel_size"], attn) for _ in range(n_layers)])
+
+
+class _Prenet(nn.Module):  # Layers.py:15-21 (training-only; kept so checkpoints load strictly)
+    def __init__(self):
+        super().__init__()
+        self.w_1 = nn.Linear(80, 256)
+        self.w_2 = nn.Linear(256, 256)
+
+
+class _Conv(nn.Module):  # modules.py:289-325
+    def __init__(self, cin, cout, k, padding):
+        super().__init__()
+        self.conv = nn.Conv1d(cin, cout, kernel_size=k, padding=padding)
+
+
+class _VariancePredictor(nn.Module):  # modules.py:236-276
+    def __init__(self, cfg):
+        super().__init__()
+        d_in = cfg["transformer"]["encoder_hidden"]
+        filt, k = cfg["variance_predictor"]["filter_size"], cfg["variance_predictor"]["kernel_size"]
+        self.conv_layer = nn.Sequential(OrderedDict([
+            ("conv1d_1", _Conv(d_in, filt, k, (k - 1) // 2)), ("layer_norm_1", nn.LayerNorm(filt)),
+            ("conv1d_2", _Conv(filt, filt, k, 1)), ("layer_norm_2", nn.LayerNorm(filt))]))
+        self.linear_layer = nn.Linear(filt, 1)
+
+
+class _VarianceAdaptor(nn.Module):  # modules.py:20-78
+    def __init__(self, preprocess_config, model_config):
+        super().__init__()
+        self.duration_predictor = _VariancePredictor(model_config)
+        self.pitch_predictor = _VariancePredictor(model_config)
+        self.energy_predictor = _VariancePredictor(model_config)
+        ve = model_config["variance_embedding"]
+        n_bins = ve["n_bins"]
+        with open(os.path.join(preprocess_config["path"]["preprocessed_path"], "stats.json")) as f:
+            stats = json.load(f)
+        for name in ("pitch", "energy"):
+            lo, hi = stats[name][:2]
+            if ve[f"{name}_quantization"] == "log":
+                with np.errstate(invalid="ignore"):
+                    bins = torch.exp(torch.linspace(np.log(lo), np.log(hi), n_bins - 1))
+            else:
+                bins = torch.linspace(lo, hi, n_bins - 1)
+            setattr(self, f"{name}_bins", nn.Parameter(bins, requires_grad=False))
+        self.pitch_embedding = nn.Embedding(n_bins, model_config["transformer"]["encoder_hidden"])
+        self.energy_embedding = nn.Embedding(n_bins, model_config["transformer"]["encoder_hidden"])
+
+
+class _ConvNorm(nn.Module):  # Layers.py:73-104
+    def __init__(self, cin, cout, k):
+        super().__init__()
+        self.conv = nn.Conv1d(cin, cout, kernel_size=k, padding=(k - 1) // 2)
+
+
+class _PostNet(nn.Module):  # Layers.py:112-167
+    def __init__(self, n_mel=80, dim=512, k=5, n=5):
+        super().__init__()
+        chans = [n_mel] + [dim] * (n - 1) + [n_mel]
+        self.convolutions = nn.ModuleList(
+            [nn.Sequential(_ConvNorm(chans[i], chans[i + 1], k), nn.BatchNorm1d(chans[i + 1])) for i in range(n)])
+
+
+def dims_from_configs(preprocess_config, model_config, n_src_vocab: int = N_SRC_VOCAB_LJSPEECH) -> Dims:
+    t = model_config["transformer"]
+    if t["encoder_hidden"] != t["decoder_hidden"] or t["encoder_head"] != t["decoder_head"]:
+        raise ValueError("encoder and decoder hidden size / head count must match")
+    return Dims(
+        vocab=n_src_vocab, d_model=t["encoder_hidden"], n_enc_layers=t["encoder_layer"], n_dec_layers=t["decoder_layer"],
+        n_heads=t["encoder_head"], d_ffn=t["conv_filter_size"], ffn_k1=t["conv_kernel_size"][0],
+        ffn_k2=t["conv_kernel_size"][1], vp_filter=model_config["variance_predictor"]["filter_size"],
+        vp_kernel=model_config["variance_predictor"]["kernel_size"], n_bins=model_config["variance_embedding"]["n_bins"],
+        n_mel=preprocess_config["preprocessing"]["mel"]["n_mel_channels"], pn_dim=512, pn_kernel=5, pn_layers=5,
+        max_seq_len=model_config["max_seq_len"],
+        pitch_phoneme_level=int(preprocess_config["preprocessing"]["pitch"]["feature"] == "phoneme_level"),
+        energy_phoneme_level=int(preprocess_config["preprocessing"]["energy"]["feature"] == "phoneme_level"))
+
+
+# --------------------------------------------------------------------------- the drop-in module
+class FastSpeech2Align(nn.Module):
+    """Drop-in for the reference class of the same name; inference (`mel_lens is None`) only."""
+
+    def __init__(self, preprocess_config, model_config, n_src_vocab: int = N_SRC_VOCAB_LJSPEECH):
+        super().__init__()
+        self.model_config = model_config
+        # construction order mirrors fastspeech2_align.py:20-28 so that default initialisation consumes the
+        # torch RNG in the same order as the reference
+        self.txt_encoder = _Stack(model_config, "txt_encoder", n_src_vocab)
+        self.variance_adaptor = _VarianceAdaptor(preprocess_config, model_config)
+        self.mel_encoder = _Stack(model_config, "mel_encoder")  # training-only aligner: parameters kept, never used
+        self.mel_decoder = _Stack(model_config, "mel_decoder")
+        self.mel_linear = nn.Linear(model_config["transformer"]["decoder_hidden"],
+                                    preprocess_config["preprocessing"]["mel"]["n_mel_channels"])
+        self.postnet = _PostNet()
+        self._dims = dims_from_configs(preprocess_config, model_config, n_src_vocab)
+        self._handle: Optional[int] = None
+        self._handle_device: Optional[torch.device] = None
+        self._stamp = None
+        self._cached_ws = None
+        self._precision = (PREC_FP32, PREC_BF16)
+        # multi-GPU hook (sharding.py): maps the local T_max to the batch-global one between the two stages
+        self.t_max_hook: Optional[Callable[[int, torch.device], int]] = None
+
+    # ------------------------------------------------------------------ engine plumbing
+    def set_precision(self, encoder: str = "fp32", decoder: str = "bf16") -> "FastSpeech2Align":
+        """encoder: txt_encoder + variance predictors; decoder: mel_decoder + mel_linear + PostNet."""
+        m = {"fp32": PREC_FP32, "bf16": PREC_BF16}
+        self._precision = (m[encoder], m[decoder])
+        if self._handle is not None:
+            lib = load_library()
+            lib.check(lib.fs2_set_precision(self._handle, *self._precision), self._handle)
+        return self
+
+    def _weights(self):
+        if self._cached_ws is None:
+            self._cached_ws = [(k, v) for k, v in self.state_dict(keep_vars=True).items()
+                               if not k.startswith("mel_encoder.") and not k.endswith("num_batches_tracked")]
+        return self._cached_ws
+
+    def _apply(self, fn, *a, **k):  # .to() / .cuda() / .float(): parameter storage changes
+        self._cached_ws, self._stamp = None, None
+        return super()._apply(fn, *a, **k)
+
+    def load_state_dict(self, *a, **k):
+        self._cached_ws, self._stamp = None, None
+        return super().load_state_dict(*a, **k)
+
+    def _ensure_engine(self, device: torch.device):
+        lib = load_library()
+        if device.type != "cuda":
+            raise RuntimeError("FastSpeech2Align (B200) runs on CUDA only; there is no CPU fallback. "
+                               "Move the module and its inputs to a cuda device.")
+        if self._handle is not None and self._handle_device != device:
+            lib.fs2_destroy(self._handle)
+            self._handle, self._stamp = None, None
+        if self._handle is None:
+            hp = C.c_void_p()
+            rc = lib.fs2_create(C.byref(hp), C.byref(self._dims), device.index if device.index is not None else torch.cuda.current_device())
+            lib.check(rc, None)
+            self._handle, self._handle_device = hp.value, device
+            lib.check(lib.fs2_set_precision(self._handle, *self._precision), self._handle)
+        ws = self._weights()
+        stamp = (ws[0][1].data_ptr(), ws[-1][1].data_ptr(), sum(t._version for _, t in ws))
+        if stamp != self._stamp:
+            descs = (WeightDesc * len(ws))()
+            keep = []
+            for i, (k, t) in enumerate(ws):
+                if t.device != device:
+                    raise RuntimeError(f"parameter {k} lives on {t.device}, inputs on {device}")
+                tt = t.detach()
+                if tt.dtype != torch.float32 or not tt.is_contiguous():
+                    tt = tt.float().contiguous()
+                keep.append(tt)
+                descs[i].name = k.encode()
+                descs[i].data = tt.data_ptr()
+                descs[i].ndim = tt.dim()
+                for j, s in enumerate(tt.shape):
+                    descs[i].shape[j] = s
+                descs[i].on_device = 1
+            torch.cuda.current_stream(device).synchronize()
+            lib.check(lib.fs2_load_weights(self._handle, descs, len(ws)), self._handle)
+            self._stamp = stamp
+        return lib
+
+    def __del__(self):
+        try:
+            if getattr(self, "_handle", None) is not None:
+                load_library().fs2_destroy(self._handle)
+                self._handle = None
+        except Exception:
+            pass
+
+    @property
+    def launch_count(self) -> int:
+        return int(load_library().fs2_launch_count(self._handle)) if self._handle is not None else 0
+
+    # ------------------------------------------------------------------ forward (fastspeech2_align.py:30-100)
+    @torch.no_grad()
+    def forward(self, speakers, texts, src_lens, max_src_len, mels=None, mel_lens=None, max_mel_len=None,
+                p_targets=None, e_targets=None, p_control=1.0, e_control=1.0):
+        if any(a is not None for a in (mels, mel_lens, max_mel_len, p_targets, e_targets)):
+            raise NotImplementedError("only the inference branch (mel_lens=None) is implemented; the reference's "
+                                      "training branch calls an undefined _calculate_duration")
+        if texts.dim() != 2 or src_lens.dim() != 1 or texts.shape[0] != src_lens.shape[0]:
+            raise ValueError("texts must be [B, L] and src_lens [B]")
+        B, L = texts.shape
+        if int(max_src_len) != L:
+            raise ValueError(f"max_src_len ({int(max_src_len)}) must equal texts.shape[1] ({L})")
+        dev = texts.device
+        lib = self._ensure_engine(dev)
+        h = self._handle
+        texts = texts.long().contiguous()
+        src_lens_in = src_lens.to(device=dev, dtype=torch.long).contiguous()
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        f32 = dict(device=dev, dtype=torch.float32)
+        log_d = torch.empty(B, L, **f32)
+        d_rounded = torch.empty(B, L, **f32)
+        out_mel_lens = torch.empty(B, device=dev, dtype=torch.long)
+        src_masks = torch.empty(B, L, device=dev, dtype=torch.bool)
+        ph_p = torch.empty(B, L, **f32) if self._dims.pitch_phoneme_level else None
+        ph_e = torch.empty(B, L, **f32) if self._dims.energy_phoneme_level else None
+        t_max = C.c_int32(0)
+        with torch.cuda.device(dev):
+            lib.check(lib.fs2_forward_stage1(
+                h, texts.data_ptr(), src_lens_in.data_ptr(), B, L, float(p_control), float(e_control), 1.0,
+                log_d.data_ptr(), d_rounded.data_ptr(), out_mel_lens.data_ptr(), src_masks.data_ptr(),
+                ph_p.data_ptr() if ph_p is not None else None, ph_e.data_ptr() if ph_e is not None else None,
+                C.byref(t_max), stream), h)
+            T = int(t_max.value)
+            if self.t_max_hook is not None:
+                T = int(self.t_max_hook(T, dev))
+            n_mel = self._dims.n_mel
+            mel = torch.empty(B, T, n_mel, **f32)
+            mel_post = torch.empty(B, T, n_mel, **f32)
+            pitch = ph_p if ph_p is not None else torch.empty(B, T, **f32)
+            energy = ph_e if ph_e is not None else torch.empty(B, T, **f32)
+            mel_masks = torch.empty(B, T, device=dev, dtype=torch.bool)
+            lib.check(lib.fs2_forward_stage2(
+                h, T, float(p_control), float(e_control), mel.data_ptr(), mel_post.data_ptr(),
+                None if ph_p is not None else pitch.data_ptr(), None if ph_e is not None else energy.data_ptr(),
+                mel_masks.data_ptr(), stream), h)
+        return (mel, mel_post, pitch, energy, log_d, d_rounded, src_masks, mel_masks, src_lens, out_mel_lens, None, None)

@@ -1,0 +1,108 @@
+"""Shared test plumbing: LJSpeech config dicts (the reference's yaml files do not exist on the GPU box),
+a raw C-ABI handle wrapper for per-operator tests, and comparison helpers."""
+from __future__ import annotations
+
+import ctypes as C
+import json
+import os
+import tempfile
+
+import numpy as np
+import torch
+
+import fs2_oracle as O
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def ljspeech_configs(stats: dict, pitch_q: str = "log", energy_q: str = "linear", pitch_feature="frame_level",
+                     energy_feature="frame_level"):
+    """config/LJSpeech/{preprocess,model}.yaml as dicts (only the keys the model reads)."""
+    tmp = tempfile.mkdtemp(prefix="fs2_stats_")
+    with open(os.path.join(tmp, "stats.json"), "w") as f:
+        json.dump(stats, f)
+    pc = {"path": {"preprocessed_path": tmp},
+          "preprocessing": {"mel": {"n_mel_channels": 80}, "pitch": {"feature": pitch_feature, "normalization": True},
+                            "energy": {"feature": energy_feature, "normalization": True}}}
+    mc = {"transformer": {"encoder_layer": 4, "encoder_head": 2, "encoder_hidden": 256, "decoder_layer": 4,
+                          "decoder_head": 2, "decoder_hidden": 256, "conv_filter_size": 1024,
+                          "conv_kernel_size": [9, 1], "encoder_dropout": 0.2, "decoder_dropout": 0.2},
+          "variance_predictor": {"filter_size": 256, "kernel_size": 3, "dropout": 0.5},
+          "variance_embedding": {"pitch_quantization": pitch_q, "energy_quantization": energy_q, "n_bins": 256},
+          "multi_speaker": False, "max_seq_len": 1000}
+    return pc, mc
+
+
+def build_model(sd, stats, pitch_q="log", device="cuda", pitch_feature="frame_level", energy_feature="frame_level"):
+    from smart_nar_fast_tts_b200 import FastSpeech2Align
+    pc, mc = ljspeech_configs(stats, pitch_q, pitch_feature=pitch_feature, energy_feature=energy_feature)
+    with np.errstate(invalid="ignore"):
+        m = FastSpeech2Align(pc, mc)
+    full = m.state_dict()
+    merged = {k: (sd[k] if k in sd else v) for k, v in full.items()}
+    m.load_state_dict(merged, strict=True)
+    return m.to(device).eval()
+
+
+def load_golden(name):
+    z = np.load(os.path.join(GOLDEN, f"{name}.npz"), allow_pickle=False)
+    return {k: z[k] for k in z.files}
+
+
+def golden_state_dict(g):
+    stats = json.loads(str(g["stats"]))
+    pq = str(g["pitch_quantization"])
+    d = O.Dims(pitch_quantization=pq)
+    return O.make_state_dict(int(g["seed"]), d, stats, frames_per_phoneme=float(g["frames_per_phoneme"])), d, stats, pq
+
+
+class OpHandle:
+    """fs2_handle created straight through ctypes (no nn.Module), weights loaded from a host state_dict."""
+
+    def __init__(self, lib, sd, dims: O.Dims = None, device=0):
+        from smart_nar_fast_tts_b200.capi import Dims, WeightDesc
+        d = dims or O.Dims()
+        self.lib = lib
+        cd = Dims(d.vocab, d.d_model, d.n_enc_layers, d.n_dec_layers, d.n_heads, d.d_ffn, d.ffn_k1, d.ffn_k2, d.vp_filter,
+                  d.vp_kernel, d.n_bins, d.n_mel, d.pn_dim, d.pn_kernel, d.pn_layers, d.max_seq_len,
+                  int(d.pitch_feature == "phoneme_level"), int(d.energy_feature == "phoneme_level"))
+        hp = C.c_void_p()
+        lib.check(lib.fs2_create(C.byref(hp), C.byref(cd), device), None)
+        self.h = hp.value
+        items = [(k, v.contiguous().float()) for k, v in sd.items() if v.dtype.is_floating_point]
+        descs = (WeightDesc * len(items))()
+        for i, (k, t) in enumerate(items):
+            descs[i].name = k.encode()
+            descs[i].data = t.data_ptr()
+            descs[i].ndim = t.dim()
+            for j, s in enumerate(t.shape):
+                descs[i].shape[j] = s
+            descs[i].on_device = 0
+        lib.check(lib.fs2_load_weights(self.h, descs, len(items)), self.h)
+
+    def check(self, rc):
+        self.lib.check(rc, self.h)
+
+    def close(self):
+        if self.h:
+            self.lib.fs2_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def rel_rms(a: torch.Tensor, b: torch.Tensor) -> float:
+    a, b = a.double().flatten(), b.double().flatten()
+    return float(torch.sqrt(((a - b) ** 2).mean() / (b ** 2).mean().clamp_min(1e-30)))
+
+
+def max_abs(a: torch.Tensor, b: torch.Tensor) -> float:
+    return float((a.double() - b.double()).abs().max()) if a.numel() else 0.0
