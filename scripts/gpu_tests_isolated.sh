@@ -1,10 +1,17 @@
 #!/bin/bash
-# Run the GPU test files in separate processes (a trapped tcgen05 kernel poisons its CUDA context; isolating the
-# files keeps the other results readable).  Logs under gpurun_out/.
+# Run the GPU tests in separate processes (a trapped tcgen05 kernel poisons its CUDA context; isolating the
+# groups keeps the other results readable).  Logs under gpurun_out/.
 mkdir -p gpurun_out
+: > gpurun_out/summary.txt
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/gpu.txt 2>&1
-for f in test_gpu_ops test_gpu_tc test_gpu_forward; do
-  timeout 900 python -m pytest tests/$f.py -m gpu -q -x --timeout 300 -p no:cacheprovider "$@" > gpurun_out/$f.log 2>&1
-  echo "$f exit=$?" | tee -a gpurun_out/summary.txt
-  tail -n 25 gpurun_out/$f.log
-done
+run() {  # name, file, -k expr
+  timeout 600 python -m pytest "tests/$2.py" -m gpu -q --timeout 240 -p no:cacheprovider -k "$3" > "gpurun_out/$1.log" 2>&1
+  echo "$1 exit=$? $(tail -n 1 gpurun_out/$1.log)" | tee -a gpurun_out/summary.txt
+}
+run ops test_gpu_ops ""
+run tc_gemm test_gpu_tc "conv_gemm"
+run tc_attn test_gpu_tc "attention"
+run tc_stack test_gpu_tc "fft_stack or mel_postnet"
+run fwd_fp32 test_gpu_forward "fp32 or determinism or rejects or phoneme"
+run fwd_bf16 test_gpu_forward "bf16"
+for f in ops tc_gemm tc_attn tc_stack fwd_fp32 fwd_bf16; do echo "=== $f"; grep -E "^(FAILED|ERROR)|Error|error|assert" gpurun_out/$f.log | head -n 12; done
