@@ -166,6 +166,20 @@ int fs2_op_conv_gemm(int32_t prec, const float* A, const float* W, const float* 
 int fs2_op_attention(int32_t prec, const float* q, const float* k, const float* v, const int64_t* lens, int32_t B,
                      int32_t S, int32_t H, int32_t dk, float* out, void* stream);
 
+/* ---- tracing (new; the reference has none) ------------------------ */
+/* When enabled every kernel class of the forward ("dec.ffn_w1", "enc.attn", "postnet.2", ...) is
+ * bracketed by CUDA events on the launching stream.  fs2_profile_read synchronises the device and
+ * returns accumulated device milliseconds and launch counts per class since the last reset.
+ * Events perturb back-to-back launches slightly: time whole steps with tracing OFF. */
+typedef struct fs2_profile_entry {
+  char name[48];
+  int64_t launches;
+  double ms;
+} fs2_profile_entry;
+int fs2_profile_enable(fs2_handle* h, int32_t on);
+int fs2_profile_reset(fs2_handle* h);
+int fs2_profile_read(fs2_handle* h, fs2_profile_entry* out, int32_t max_entries, int32_t* n_out);
+
 /* number of kernels launched by this handle since creation (bench.py's gpu_launches) */
 int64_t fs2_launch_count(const fs2_handle* h);
 

@@ -25,9 +25,20 @@ import math
 from dataclasses import dataclass, field
 from typing import Dict, List, Optional, Tuple
 
+import os
+import sys
+
 import numpy as np
 import torch
 import torch.nn.functional as F
+
+# weights / inputs / stats come from the package's data factory (pure data generation, no compute of the path) so the
+# reference, this oracle and the CUDA path are driven by the same tensors
+_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if _ROOT not in sys.path:
+    sys.path.insert(0, _ROOT)
+from smart_nar_fast_tts_b200.synthetic import (STATS_FINITE_BINS, STATS_NAN_BINS, make_inputs,  # noqa: E402,F401
+                                               make_state_dict as _make_state_dict)
 
 
 # ----------------------------------------------------------------------------
@@ -55,11 +66,6 @@ class Dims:
     energy_quantization: str = "linear"
     pitch_feature: str = "frame_level"
     energy_feature: str = "frame_level"
-
-
-# stats.json contents used by SURVEY section 8(d): [min, max, mean, std]
-STATS_NAN_BINS = {"pitch": [-2.9, 11.4, 127.0, 110.0], "energy": [-1.4, 8.0, 37.0, 26.0]}
-STATS_FINITE_BINS = {"pitch": [0.5, 11.4, 127.0, 110.0], "energy": [-1.4, 8.0, 37.0, 26.0]}
 
 
 # ----------------------------------------------------------------------------
@@ -102,130 +108,10 @@ def make_bins(vmin: float, vmax: float, n_bins: int, quantization: str) -> torch
     return torch.linspace(vmin, vmax, n_bins - 1)
 
 
-# ----------------------------------------------------------------------------
-# weight factory (new; no counterpart in the reference, which ships no checkpoint)
-# ----------------------------------------------------------------------------
 def make_state_dict(seed: int = 0, dims: Optional[Dims] = None, stats: Optional[dict] = None,
-                    frames_per_phoneme: float = 7.67, include_mel_encoder: bool = False
-                    ) -> Dict[str, torch.Tensor]:
-    """Deterministic weights with the reference's `state_dict` key layout
-    (SURVEY.md section 8(b)).  numpy PCG64 so that the values do not depend on the
-    torch version.  Non-trivial LayerNorm / BatchNorm parameters so that folding
-    or affine bugs are visible; duration head biased to ~`frames_per_phoneme`
-    frames per phoneme (SURVEY.md section 8(c) weight recipe)."""
-    d = dims or Dims()
-    stats = stats or STATS_NAN_BINS
-    rng = np.random.Generator(np.random.PCG64(seed))
-    sd: Dict[str, torch.Tensor] = {}
-
-    def uni(shape, fan_in, scale=1.0):
-        b = scale / math.sqrt(fan_in)
-        return torch.from_numpy(rng.uniform(-b, b, size=shape).astype(np.float32))
-
-    def nrm(shape, std=1.0, mean=0.0):
-        return torch.from_numpy((mean + std * rng.standard_normal(size=shape)).astype(np.float32))
-
-    D, F_, H = d.d_model, d.d_ffn, d.n_heads
-
-    def fft_stack(prefix: str, n_layers: int):
-        for i in range(n_layers):
-            p = f"{prefix}.layer_stack.{i}"
-            for nm in ("w_qs", "w_ks", "w_vs", "fc"):
-                sd[f"{p}.slf_attn.{nm}.weight"] = uni((D, D), D)
-                sd[f"{p}.slf_attn.{nm}.bias"] = uni((D,), D)
-            sd[f"{p}.slf_attn.layer_norm.weight"] = nrm((D,), 0.1, 1.0)
-            sd[f"{p}.slf_attn.layer_norm.bias"] = nrm((D,), 0.1)
-            sd[f"{p}.pos_ffn.w_1.weight"] = uni((F_, D, d.ffn_k1), D * d.ffn_k1)
-            sd[f"{p}.pos_ffn.w_1.bias"] = uni((F_,), D * d.ffn_k1)
-            sd[f"{p}.pos_ffn.w_2.weight"] = uni((D, F_, d.ffn_k2), F_ * d.ffn_k2)
-            sd[f"{p}.pos_ffn.w_2.bias"] = uni((D,), F_ * d.ffn_k2)
-            sd[f"{p}.pos_ffn.layer_norm.weight"] = nrm((D,), 0.1, 1.0)
-            sd[f"{p}.pos_ffn.layer_norm.bias"] = nrm((D,), 0.1)
-
-    pe = sinusoid_table(d.max_seq_len + 1, D).unsqueeze(0)
-    sd["txt_encoder.position_enc"] = pe.clone()
-    emb = nrm((d.vocab, D), 1.0)
-    emb[0] = 0.0                                              # padding_idx=0, Models.py:59-61
-    sd["txt_encoder.src_word_emb.weight"] = emb
-    fft_stack("txt_encoder", d.n_enc_layers)
-
-    sd["variance_adaptor.pitch_bins"] = make_bins(stats["pitch"][0], stats["pitch"][1], d.n_bins, d.pitch_quantization)
-    sd["variance_adaptor.energy_bins"] = make_bins(stats["energy"][0], stats["energy"][1], d.n_bins, d.energy_quantization)
-    for which in ("duration", "pitch", "energy"):
-        p = f"variance_adaptor.{which}_predictor"
-        sd[f"{p}.conv_layer.conv1d_1.conv.weight"] = uni((d.vp_filter, D, d.vp_kernel), D * d.vp_kernel)
-        sd[f"{p}.conv_layer.conv1d_1.conv.bias"] = uni((d.vp_filter,), D * d.vp_kernel)
-        sd[f"{p}.conv_layer.layer_norm_1.weight"] = nrm((d.vp_filter,), 0.1, 1.0)
-        sd[f"{p}.conv_layer.layer_norm_1.bias"] = nrm((d.vp_filter,), 0.1)
-        sd[f"{p}.conv_layer.conv1d_2.conv.weight"] = uni((d.vp_filter, d.vp_filter, d.vp_kernel), d.vp_filter * d.vp_kernel)
-        sd[f"{p}.conv_layer.conv1d_2.conv.bias"] = uni((d.vp_filter,), d.vp_filter * d.vp_kernel)
-        sd[f"{p}.conv_layer.layer_norm_2.weight"] = nrm((d.vp_filter,), 0.1, 1.0)
-        sd[f"{p}.conv_layer.layer_norm_2.bias"] = nrm((d.vp_filter,), 0.1)
-        if which == "duration":
-            sd[f"{p}.linear_layer.weight"] = uni((1, d.vp_filter), d.vp_filter, 0.5)
-            sd[f"{p}.linear_layer.bias"] = torch.tensor([math.log(frames_per_phoneme)], dtype=torch.float32)
-        else:
-            # spread predictions over several bins so bucketize is exercised
-            sd[f"{p}.linear_layer.weight"] = uni((1, d.vp_filter), d.vp_filter, 5.0)
-            sd[f"{p}.linear_layer.bias"] = torch.tensor([3.0], dtype=torch.float32)
-    sd["variance_adaptor.pitch_embedding.weight"] = nrm((d.n_bins, D), 1.0)
-    sd["variance_adaptor.energy_embedding.weight"] = nrm((d.n_bins, D), 1.0)
-
-    sd["mel_decoder.position_enc"] = pe.clone()
-    fft_stack("mel_decoder", d.n_dec_layers)
-    sd["mel_linear.weight"] = uni((d.n_mel, D), D)
-    sd["mel_linear.bias"] = uni((d.n_mel,), D)
-
-    chans = [d.n_mel] + [d.pn_dim] * (d.pn_layers - 1) + [d.n_mel]
-    for i in range(d.pn_layers):
-        cin, cout = chans[i], chans[i + 1]
-        p = f"postnet.convolutions.{i}"
-        sd[f"{p}.0.conv.weight"] = uni((cout, cin, d.pn_kernel), cin * d.pn_kernel)
-        sd[f"{p}.0.conv.bias"] = uni((cout,), cin * d.pn_kernel)
-        sd[f"{p}.1.weight"] = nrm((cout,), 0.1, 1.0)
-        sd[f"{p}.1.bias"] = nrm((cout,), 0.1)
-        sd[f"{p}.1.running_mean"] = nrm((cout,), 0.1)
-        sd[f"{p}.1.running_var"] = torch.from_numpy(rng.uniform(0.5, 1.5, size=(cout,)).astype(np.float32))
-        sd[f"{p}.1.num_batches_tracked"] = torch.tensor(0, dtype=torch.long)
-
-    if include_mel_encoder:
-        # training-only aligner (transformer/Models.py:103-173): present in real
-        # checkpoints, must be accepted and ignored by the drop-in.
-        sd["mel_encoder.position_enc"] = pe.clone()
-        sd["mel_encoder.prenet.w_1.weight"] = uni((256, 80), 80)
-        sd["mel_encoder.prenet.w_1.bias"] = uni((256,), 80)
-        sd["mel_encoder.prenet.w_2.weight"] = uni((256, 256), 256)
-        sd["mel_encoder.prenet.w_2.bias"] = uni((256,), 256)
-        for i in range(d.n_dec_layers):
-            p = f"mel_encoder.layer_stack.{i}"
-            for nm in ("w_qs", "w_ks", "w_vs", "fc"):
-                sd[f"{p}.crs_attn.{nm}.weight"] = uni((D, D), D)
-                sd[f"{p}.crs_attn.{nm}.bias"] = uni((D,), D)
-            sd[f"{p}.crs_attn.layer_norm.weight"] = nrm((D,), 0.1, 1.0)
-            sd[f"{p}.crs_attn.layer_norm.bias"] = nrm((D,), 0.1)
-            sd[f"{p}.pos_ffn.w_1.weight"] = uni((F_, D, d.ffn_k1), D * d.ffn_k1)
-            sd[f"{p}.pos_ffn.w_1.bias"] = uni((F_,), D * d.ffn_k1)
-            sd[f"{p}.pos_ffn.w_2.weight"] = uni((D, F_, d.ffn_k2), F_ * d.ffn_k2)
-            sd[f"{p}.pos_ffn.w_2.bias"] = uni((D,), F_ * d.ffn_k2)
-            sd[f"{p}.pos_ffn.layer_norm.weight"] = nrm((D,), 0.1, 1.0)
-            sd[f"{p}.pos_ffn.layer_norm.bias"] = nrm((D,), 0.1)
-    return sd
-
-
-# ----------------------------------------------------------------------------
-# synthetic inputs (SURVEY.md section 8(d))
-# ----------------------------------------------------------------------------
-def make_inputs(batch: int, len_lo: int, len_hi: int, seed: int = 1, vocab: int = 361
-                ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor, int]:
-    """(speakers[B], texts[B,L] int64 0-padded, src_lens[B] int64, max_src_len)."""
-    rng = np.random.Generator(np.random.PCG64(seed))
-    lens = rng.integers(len_lo, len_hi + 1, size=batch).astype(np.int64)
-    L = int(lens.max())
-    texts = np.zeros((batch, L), dtype=np.int64)
-    for b in range(batch):
-        texts[b, : lens[b]] = rng.integers(1, vocab, size=int(lens[b]))
-    return (torch.zeros(batch, dtype=torch.long), torch.from_numpy(texts),
-            torch.from_numpy(lens), L)
+                    frames_per_phoneme: float = 7.67, include_mel_encoder: bool = False) -> Dict[str, torch.Tensor]:
+    """Deterministic weights with the reference's `state_dict` key layout (see synthetic.make_state_dict)."""
+    return _make_state_dict(seed, dims or Dims(), stats, frames_per_phoneme, include_mel_encoder)
 
 
 # ----------------------------------------------------------------------------

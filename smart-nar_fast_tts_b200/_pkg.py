@@ -2,6 +2,7 @@
 from .capi import Fs2Error, Fs2Library, PREC_BF16, PREC_FP32, load_library  # noqa: F401
 from .model import FastSpeech2Align, dims_from_configs  # noqa: F401
 from .sharding import ShardedSynthesizer, shard_bounds  # noqa: F401
+from . import synthetic  # noqa: F401
 
 __all__ = ["FastSpeech2Align", "dims_from_configs", "Fs2Error", "Fs2Library", "load_library", "PREC_FP32", "PREC_BF16",
-           "ShardedSynthesizer", "shard_bounds"]
+           "ShardedSynthesizer", "shard_bounds", "synthetic"]

@@ -38,6 +38,10 @@ class WeightDesc(C.Structure):
                 ("on_device", C.c_int32)]
 
 
+class ProfileEntry(C.Structure):
+    _fields_ = [("name", C.c_char * 48), ("launches", C.c_int64), ("ms", C.c_double)]
+
+
 _P = C.c_void_p
 _I = C.c_int32
 _F = C.c_float
@@ -65,6 +69,9 @@ SIGNATURES = {
     "fs2_op_mel_postnet": (C.c_int, [_P, _I, _P, _I, _I, _P, _P, _P]),
     "fs2_op_conv_gemm": (C.c_int, [_I, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P]),
     "fs2_op_attention": (C.c_int, [_I, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P]),
+    "fs2_profile_enable": (C.c_int, [_P, _I]),
+    "fs2_profile_reset": (C.c_int, [_P]),
+    "fs2_profile_read": (C.c_int, [_P, C.POINTER(ProfileEntry), _I, C.POINTER(_I)]),
     "fs2_launch_count": (C.c_int64, [_P]),
 }
 

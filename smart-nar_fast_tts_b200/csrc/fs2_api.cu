@@ -63,6 +63,25 @@ struct fs2_handle {
   int pe_ext_n[2] = {0, 0};
   std::map<std::string, std::pair<void*, size_t>> ws;  // growable workspace
   int* host_tmax = nullptr;                            // pinned
+  // tracing: per-kernel-class device time from CUDA events on the launching stream (fs2_profile_*)
+  bool prof_on = false;
+  struct ProfPending { int slot; cudaEvent_t a, b; };
+  std::vector<ProfPending> prof_pending;
+  std::vector<cudaEvent_t> prof_pool;
+  std::vector<std::string> prof_names;
+  std::vector<double> prof_ms;
+  std::vector<long long> prof_launches;
+  int prof_slot(const std::string& name) {
+    for (size_t i = 0; i < prof_names.size(); ++i) if (prof_names[i] == name) return (int)i;
+    prof_names.push_back(name); prof_ms.push_back(0.0); prof_launches.push_back(0);
+    return (int)prof_names.size() - 1;
+  }
+  cudaEvent_t prof_event() {
+    if (!prof_pool.empty()) { cudaEvent_t e = prof_pool.back(); prof_pool.pop_back(); return e; }
+    cudaEvent_t e = nullptr;
+    cudaEventCreate(&e);
+    return e;
+  }
   // stage-1 -> stage-2 state
   bool have_stage1 = false;
   int st_B = 0, st_L = 0, st_LA = 0, st_Tmax = 0;
@@ -110,6 +129,26 @@ struct fs2_handle {
   if (!var) return h->fail(FS2_ERR_CUDA, std::string("workspace allocation failed: ") + name)
 
 namespace {
+
+// Times everything enqueued on `st` during its lifetime under `name` when tracing is enabled (otherwise free).
+struct ProfScope {
+  fs2_handle* h; cudaStream_t st; int slot = -1; cudaEvent_t a = nullptr; long long l0 = 0;
+  ProfScope(fs2_handle* h_, const std::string& name, cudaStream_t st_) : h(h_), st(st_) {
+    if (!h || !h->prof_on) return;
+    slot = h->prof_slot(name);
+    a = h->prof_event();
+    l0 = g_fs2_launches;
+    cudaEventRecord(a, st);
+  }
+  ~ProfScope() {
+    if (slot < 0) return;
+    cudaEvent_t b = h->prof_event();
+    cudaEventRecord(b, st);
+    h->prof_pending.push_back({slot, a, b});
+    h->prof_launches[slot] += g_fs2_launches - l0;
+  }
+};
+#define PROF(name) ProfScope _prof_scope(h, name, st)
 
 const float* raw_ptr(fs2_handle* h, const std::string& k) {
   auto it = h->raw.find(k);
@@ -245,7 +284,8 @@ ConvGemmArgs base_args(const GemmW& w, int B, int S, int SA, const int* lens) {
   return a;
 }
 
-int run_gemm(fs2_handle* h, int prec, const ConvGemmArgs& a, cudaStream_t st) {
+int run_gemm(fs2_handle* h, int prec, const ConvGemmArgs& a, cudaStream_t st, const std::string& tag = std::string()) {
+  ProfScope _ps(tag.empty() ? nullptr : h, tag, st);
   if (prec == FS2_PREC_FP32) {
     cudaError_t e = simt_conv_gemm_launch(a, st);
     if (e != cudaSuccess) return h ? h->cuda_fail(e, "simt_conv_gemm_launch") : fs2_fail_cuda(e, "simt_conv_gemm_launch");
@@ -262,6 +302,7 @@ int run_fft_stack(fs2_handle* h, std::vector<FftW>& Ls, int l0, int l1, int prec
                   int B, int S, int SA, cudaStream_t st) {
   const int D = h->dims.d_model, F = h->dims.d_ffn, H = h->dims.n_heads, dk = D / H;
   const size_t R = (size_t)B * SA;
+  const std::string tg = (&Ls == &h->enc) ? "enc." : "dec.";
   WS(float, y, "fft.y", R * D);
   if (prec == FS2_PREC_FP32) {
     WS(float, qkv, "fft.qkv", R * 3 * D);
@@ -271,19 +312,22 @@ int run_fft_stack(fs2_handle* h, std::vector<FftW>& Ls, int l0, int l1, int prec
       FftW& L = Ls[l];
       ConvGemmArgs a = base_args(L.qkv, B, S, SA, lens);
       a.A = x; a.epi = EPI_BIAS; a.mask_mode = MASK_GRID; a.out = qkv; a.ldo = 3 * D;
-      RCHECK(run_gemm(h, prec, a, st));
-      HCHECK(simt_attention_launch(qkv, 3 * D, 0, D, 2 * D, lens, B, S, SA, H, dk, att, D, st));
+      RCHECK(run_gemm(h, prec, a, st, tg + "qkv"));
+      {
+        PROF(tg + "attn");
+        HCHECK(simt_attention_launch(qkv, 3 * D, 0, D, 2 * D, lens, B, S, SA, H, dk, att, D, st));
+      }
       a = base_args(L.fc, B, S, SA, lens);
       a.A = att; a.epi = EPI_RES_LN; a.mask_mode = MASK_LEN; a.residual = x; a.ln_g = L.ln1_g; a.ln_b = L.ln1_b;
       a.out = y; a.ldo = D;
-      RCHECK(run_gemm(h, prec, a, st));
+      RCHECK(run_gemm(h, prec, a, st, tg + "fc_ln"));
       a = base_args(L.w1, B, S, SA, lens);
       a.A = y; a.epi = EPI_RELU; a.mask_mode = MASK_GRID; a.out = hid; a.ldo = F;
-      RCHECK(run_gemm(h, prec, a, st));
+      RCHECK(run_gemm(h, prec, a, st, tg + "ffn_w1"));
       a = base_args(L.w2, B, S, SA, lens);
       a.A = hid; a.epi = EPI_RES_LN; a.mask_mode = MASK_LEN; a.residual = y; a.ln_g = L.ln2_g; a.ln_b = L.ln2_b;
       a.out = x; a.ldo = D;
-      RCHECK(run_gemm(h, prec, a, st));
+      RCHECK(run_gemm(h, prec, a, st, tg + "ffn_w2_ln"));
     }
     return FS2_OK;
   }
@@ -299,20 +343,23 @@ int run_fft_stack(fs2_handle* h, std::vector<FftW>& Ls, int l0, int l1, int prec
     FftW& L = Ls[l];
     ConvGemmArgs a = base_args(L.qkv, B, S, SA, lens);
     a.Ab = xb; a.epi = EPI_QKV; a.mask_mode = MASK_GRID; a.q_b = qb; a.k_b = kb; a.vt_b = vtb; a.SAv = SAv;
-    RCHECK(run_gemm(h, prec, a, st));
-    int rc = tc_attention_launch(qb, kb, vtb, lens, B, S, SA, SAv, H, attb, st);
-    if (rc != FS2_OK) { h->err = g_last_error; return rc; }
+    RCHECK(run_gemm(h, prec, a, st, tg + "qkv"));
+    {
+      PROF(tg + "attn");
+      int rc = tc_attention_launch(qb, kb, vtb, lens, B, S, SA, SAv, H, attb, st);
+      if (rc != FS2_OK) { h->err = g_last_error; return rc; }
+    }
     a = base_args(L.fc, B, S, SA, lens);
     a.Ab = attb; a.epi = EPI_RES_LN; a.mask_mode = MASK_LEN; a.residual = x; a.ln_g = L.ln1_g; a.ln_b = L.ln1_b;
     a.out = y; a.ldo = D; a.out_b = yb; a.ldob = D;
-    RCHECK(run_gemm(h, prec, a, st));
+    RCHECK(run_gemm(h, prec, a, st, tg + "fc_ln"));
     a = base_args(L.w1, B, S, SA, lens);
     a.Ab = yb; a.epi = EPI_RELU; a.mask_mode = MASK_GRID; a.out_b = hidb; a.ldob = F;
-    RCHECK(run_gemm(h, prec, a, st));
+    RCHECK(run_gemm(h, prec, a, st, tg + "ffn_w1"));
     a = base_args(L.w2, B, S, SA, lens);
     a.Ab = hidb; a.epi = EPI_RES_LN; a.mask_mode = MASK_LEN; a.residual = y; a.ln_g = L.ln2_g; a.ln_b = L.ln2_b;
     a.out = x; a.ldo = D; a.out_b = xb; a.ldob = D;
-    RCHECK(run_gemm(h, prec, a, st));
+    RCHECK(run_gemm(h, prec, a, st, tg + "ffn_w2_ln"));
   }
   return FS2_OK;
 }
@@ -321,6 +368,7 @@ int run_fft_stack(fs2_handle* h, std::vector<FftW>& Ls, int l0, int l1, int prec
 int run_predictor(fs2_handle* h, PredW& P, int prec, const float* x, const bf16* xb, const int* lens, int B, int S,
                   int SA, float* out_user, cudaStream_t st) {
   const int C = h->dims.vp_filter;
+  const std::string tg = &P == &h->pred[0] ? "dur." : &P == &h->pred[1] ? "pitch." : "energy.";
   const size_t R = (size_t)B * SA;
   WS(float, p1, "pred.h1", R * C);
   bf16* p1b = nullptr;
@@ -331,11 +379,11 @@ int run_predictor(fs2_handle* h, PredW& P, int prec, const float* x, const bf16*
   ConvGemmArgs a = base_args(P.c1, B, S, SA, lens);
   a.A = x; a.Ab = xb; a.epi = EPI_RELU_LN; a.mask_mode = MASK_GRID; a.ln_g = P.ln1_g; a.ln_b = P.ln1_b;
   a.out = p1; a.ldo = C; a.out_b = p1b; a.ldob = C;
-  RCHECK(run_gemm(h, prec, a, st));
+  RCHECK(run_gemm(h, prec, a, st, tg + "conv1"));
   a = base_args(P.c2, B, S, SA, lens);
   a.A = p1; a.Ab = p1b; a.epi = EPI_RELU_LN_DOT; a.mask_mode = MASK_LEN; a.ln_g = P.ln2_g; a.ln_b = P.ln2_b;
   a.dot_w = P.lin_w; a.dot_b = P.lin_b; a.out_user = out_user; a.ldu = 1;
-  RCHECK(run_gemm(h, prec, a, st));
+  RCHECK(run_gemm(h, prec, a, st, tg + "conv2_dot"));
   return FS2_OK;
 }
 
@@ -359,7 +407,7 @@ int run_mel_postnet(fs2_handle* h, int prec, const float* dec, const bf16* decb,
   ConvGemmArgs a = base_args(h->mel_linear, B, T, TA, nullptr);
   a.A = dec; a.Ab = decb; a.epi = EPI_BIAS; a.mask_mode = MASK_GRID;
   a.out = melg; a.ldo = M; a.out_b = melb; a.ldob = M; a.out_user = mel; a.ldu = M;
-  RCHECK(run_gemm(h, prec, a, st));
+  RCHECK(run_gemm(h, prec, a, st, "mel_linear"));
   const float* in_f = melg; const bf16* in_b = melb;
   for (int i = 0; i < NL; ++i) {
     a = base_args(h->postnet[i], B, T, TA, nullptr);
@@ -372,7 +420,7 @@ int run_mel_postnet(fs2_handle* h, int prec, const float* dec, const bf16* decb,
     } else {
       a.epi = EPI_RES; a.residual = melg; a.out_user = mel_post; a.ldu = M;
     }
-    RCHECK(run_gemm(h, prec, a, st));
+    RCHECK(run_gemm(h, prec, a, st, "postnet." + std::to_string(i)));
   }
   return FS2_OK;
 }
@@ -437,6 +485,8 @@ void fs2_destroy(fs2_handle* h) {
   for (void* p : h->owned) cudaFree(p);
   for (auto& kv : h->ws) cudaFree(kv.second.first);
   for (int i = 0; i < 2; ++i) if (h->pe_ext[i]) cudaFree(h->pe_ext[i]);
+  for (auto& p : h->prof_pending) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
+  for (cudaEvent_t e : h->prof_pool) cudaEventDestroy(e);
   if (h->host_tmax) cudaFreeHost(h->host_tmax);
   delete h;
 }
@@ -548,12 +598,15 @@ int fs2_forward_stage1(fs2_handle* h, const int64_t* texts, const int64_t* src_l
     WS(bf16, t, "s1.xb", R * D);
     xb = t;
   }
-  HCHECK(rowops_lens_to_i32(src_lens, B, L, lens32, st));
-  if (src_mask) HCHECK(rowops_mask(src_lens, nullptr, B, L, src_mask, st));
   const float* pe = nullptr;
   RCHECK(position_table(h, 0, L, &pe, st));
-  HCHECK(rowops_embed_pe(texts, raw_ptr(h, "txt_encoder.src_word_emb.weight"), pe, d.vocab, B, L, LA, D, x, nullptr, st));
-  if (xb) HCHECK(rowops_f32_to_bf16(x, (int64_t)(R * D), xb, st));
+  {
+    PROF("rows.embed_pe");
+    HCHECK(rowops_lens_to_i32(src_lens, B, L, lens32, st));
+    if (src_mask) HCHECK(rowops_mask(src_lens, nullptr, B, L, src_mask, st));
+    HCHECK(rowops_embed_pe(texts, raw_ptr(h, "txt_encoder.src_word_emb.weight"), pe, d.vocab, B, L, LA, D, x, nullptr, st));
+    if (xb) HCHECK(rowops_f32_to_bf16(x, (int64_t)(R * D), xb, st));
+  }
   RCHECK(run_fft_stack(h, h->enc, 0, d.n_enc_layers, h->prec_enc, x, xb, lens32, B, L, LA, st));
   // modules.py:116 duration predictor on the encoder output
   RCHECK(run_predictor(h, h->pred[0], h->prec_enc, x, xb, lens32, B, L, LA, log_d, st));
@@ -571,9 +624,12 @@ int fs2_forward_stage1(fs2_handle* h, const int64_t* texts, const int64_t* src_l
                                  nullptr, st));
   }
   // modules.py:132-135 + LengthRegulator bookkeeping
-  HCHECK(rowops_round_durations(log_d, (int64_t)B * L, d_control, d_rounded, st));
-  HCHECK(cudaMemsetAsync(tmax_dev, 0, sizeof(int), st));
-  HCHECK(rowops_duration_scan(d_rounded, B, L, cum, mel_lens, mlens32, tmax_dev, st));
+  {
+    PROF("rows.round_scan");
+    HCHECK(rowops_round_durations(log_d, (int64_t)B * L, d_control, d_rounded, st));
+    HCHECK(cudaMemsetAsync(tmax_dev, 0, sizeof(int), st));
+    HCHECK(rowops_duration_scan(d_rounded, B, L, cum, mel_lens, mlens32, tmax_dev, st));
+  }
   HCHECK(cudaMemcpyAsync(h->host_tmax, tmax_dev, sizeof(int), cudaMemcpyDeviceToHost, st));
   HCHECK(cudaStreamSynchronize(st));  // the one data-dependent size of the path
   *T_max_out = *h->host_tmax;
@@ -605,9 +661,12 @@ int fs2_forward_stage2(fs2_handle* h, int32_t T, float p_control, float e_contro
     WS(bf16, t, "s2.xb", R * D);
     xb = t;
   }
-  if (mel_mask) HCHECK(rowops_mask(nullptr, mlens32, B, T, mel_mask, st));
-  // modules.py:136 length regulator (hard), straight into the halo'ed grid
-  HCHECK(rowops_length_regulate(h->st_enc_out, LA * D, cum, B, L, D, T, TA, x, st));
+  {
+    PROF("rows.length_regulate");
+    if (mel_mask) HCHECK(rowops_mask(nullptr, mlens32, B, T, mel_mask, st));
+    // modules.py:136 length regulator (hard), straight into the halo'ed grid
+    HCHECK(rowops_length_regulate(h->st_enc_out, LA * D, cum, B, L, D, T, TA, x, st));
+  }
   const float* pe = nullptr;
   RCHECK(position_table(h, 1, T, &pe, st));
   const bool pitch_fl = !d.pitch_phoneme_level, energy_fl = !d.energy_phoneme_level;
@@ -615,6 +674,7 @@ int fs2_forward_stage2(fs2_handle* h, int32_t T, float p_control, float e_contro
   // modules.py:139-149 frame-level pitch then energy (energy sees x + pitch embedding)
   if (pitch_fl) {
     RCHECK(run_predictor(h, h->pred[1], h->prec_enc, x, xb, mlens32, B, T, TA, pitch, st));
+    PROF("rows.variance_embed");
     HCHECK(rowops_variance_embed(pitch, p_control, raw_ptr(h, "variance_adaptor.pitch_bins"), d.n_bins,
                                  raw_ptr(h, "variance_adaptor.pitch_embedding.weight"), energy_fl ? nullptr : pe, x, xb,
                                  B, T, TA, D, nullptr, st));
@@ -622,6 +682,7 @@ int fs2_forward_stage2(fs2_handle* h, int32_t T, float p_control, float e_contro
   if (energy_fl) {
     RCHECK(run_predictor(h, h->pred[2], h->prec_enc, x, xb, mlens32, B, T, TA, energy, st));
     // fused: + energy embedding, + decoder positional encoding (Models.py:231-233), bf16 shadow for the decoder
+    PROF("rows.variance_embed");
     HCHECK(rowops_variance_embed(energy, e_control, raw_ptr(h, "variance_adaptor.energy_bins"), d.n_bins,
                                  raw_ptr(h, "variance_adaptor.energy_embedding.weight"), pe, x, xb, B, T, TA, D,
                                  nullptr, st));
@@ -630,6 +691,46 @@ int fs2_forward_stage2(fs2_handle* h, int32_t T, float p_control, float e_contro
     HCHECK(rowops_add_pe(x, xb, pe, B, T, TA, D, st));
   RCHECK(run_fft_stack(h, h->dec, 0, d.n_dec_layers, h->prec_dec, x, xb, mlens32, B, T, TA, st));
   RCHECK(run_mel_postnet(h, h->prec_dec, x, xb, B, T, TA, mel, mel_post, st));
+  return FS2_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// tracing
+int fs2_profile_enable(fs2_handle* h, int32_t on) {
+  if (!h) return FS2_ERR_INVALID;
+  h->prof_on = on != 0;
+  return FS2_OK;
+}
+
+int fs2_profile_reset(fs2_handle* h) {
+  if (!h) return FS2_ERR_INVALID;
+  HCHECK(cudaSetDevice(h->device));
+  HCHECK(cudaDeviceSynchronize());
+  for (auto& p : h->prof_pending) { h->prof_pool.push_back(p.a); h->prof_pool.push_back(p.b); }
+  h->prof_pending.clear();
+  h->prof_names.clear(); h->prof_ms.clear(); h->prof_launches.clear();
+  return FS2_OK;
+}
+
+int fs2_profile_read(fs2_handle* h, fs2_profile_entry* out, int32_t max_entries, int32_t* n_out) {
+  if (!h || !n_out || (max_entries > 0 && !out)) return h ? h->fail(FS2_ERR_INVALID, "profile_read: null argument") : FS2_ERR_INVALID;
+  HCHECK(cudaSetDevice(h->device));
+  HCHECK(cudaDeviceSynchronize());
+  for (auto& p : h->prof_pending) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess) h->prof_ms[p.slot] += (double)ms;
+    h->prof_pool.push_back(p.a);
+    h->prof_pool.push_back(p.b);
+  }
+  h->prof_pending.clear();
+  const int n = (int)h->prof_names.size();
+  *n_out = n;
+  for (int i = 0; i < n && i < max_entries; ++i) {
+    memset(&out[i], 0, sizeof out[i]);
+    strncpy(out[i].name, h->prof_names[i].c_str(), sizeof(out[i].name) - 1);
+    out[i].launches = h->prof_launches[i];
+    out[i].ms = h->prof_ms[i];
+  }
   return FS2_OK;
 }
 

@@ -244,6 +244,24 @@ class FastSpeech2Align(nn.Module):
         except Exception:
             pass
 
+    # tracing (fs2_profile_*): per-kernel-class device time, CUDA events on the launching stream
+    def profile_enable(self, on: bool = True, reset: bool = True) -> None:
+        if self._handle is None:
+            raise RuntimeError("profile_enable needs an engine: run one forward first")
+        lib = load_library()
+        if reset:
+            lib.check(lib.fs2_profile_reset(self._handle), self._handle)
+        lib.check(lib.fs2_profile_enable(self._handle, int(on)), self._handle)
+
+    def profile_read(self) -> dict:
+        """{kernel class: {"ms": accumulated device ms, "launches": n}} since the last reset (synchronises)."""
+        from .capi import ProfileEntry
+        lib = load_library()
+        buf = (ProfileEntry * 128)()
+        n = C.c_int32(0)
+        lib.check(lib.fs2_profile_read(self._handle, buf, 128, C.byref(n)), self._handle)
+        return {buf[i].name.decode(): {"ms": buf[i].ms, "launches": int(buf[i].launches)} for i in range(min(n.value, 128))}
+
     @property
     def launch_count(self) -> int:
         return int(load_library().fs2_launch_count(self._handle)) if self._handle is not None else 0
