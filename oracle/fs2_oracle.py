@@ -273,7 +273,8 @@ class Trace:
 
 # model/modules.py:102-159  VarianceAdaptor.forward (inference: all targets None)
 def variance_adaptor(sd, d: Dims, x, src_mask, p_control=1.0, e_control=1.0, d_control=1.0,
-                     trace: Optional[Trace] = None, force_durations: Optional[torch.Tensor] = None):
+                     trace: Optional[Trace] = None, force_durations: Optional[torch.Tensor] = None,
+                     t_pad: Optional[int] = None):
     log_d = variance_predictor(sd, "variance_adaptor.duration_predictor", x, src_mask)
     if d.pitch_feature == "phoneme_level":
         p_pred, p_emb, p_idx = variance_embedding(sd, "pitch", x, src_mask, p_control)
@@ -282,8 +283,8 @@ def variance_adaptor(sd, d: Dims, x, src_mask, p_control=1.0, e_control=1.0, d_c
         e_pred, e_emb, e_idx = variance_embedding(sd, "energy", x, src_mask, e_control)
         x = x + e_emb
     d_rounded = round_durations(log_d, d_control) if force_durations is None else force_durations
-    x, mel_len = length_regulate(x, d_rounded, None)
-    mel_mask = get_mask_from_lengths(mel_len)
+    x, mel_len = length_regulate(x, d_rounded, t_pad)
+    mel_mask = get_mask_from_lengths(mel_len, t_pad)
     if trace is not None:
         trace.lr_out = x
     if d.pitch_feature == "frame_level":
@@ -300,17 +301,20 @@ def variance_adaptor(sd, d: Dims, x, src_mask, p_control=1.0, e_control=1.0, d_c
 # model/fastspeech2_align.py:30-100  FastSpeech2Align.forward (mel_lens=None)
 @torch.no_grad()
 def forward(sd, d: Dims, speakers, texts, src_lens, max_src_len, p_control=1.0, e_control=1.0,
-            trace: Optional[Trace] = None, force_durations: Optional[torch.Tensor] = None):
+            trace: Optional[Trace] = None, force_durations: Optional[torch.Tensor] = None,
+            t_pad: Optional[int] = None):
     """Returns the reference's 12-tuple.  `speakers` is ignored (no speaker
     embedding exists in the reference).  `force_durations` (test hook, not in the
     reference) replaces d_rounded so downstream stages can be compared on
-    identical shapes."""
+    identical shapes.  `t_pad` (test hook) pads the frame grid to a T larger than
+    this batch's own maximum: what a shard of a bigger batch must compute so that
+    the padded-grid convolutions see the batch-global T."""
     src_masks = get_mask_from_lengths(src_lens, int(max_src_len))
     enc = txt_encoder(sd, d, texts, src_masks)
     if trace is not None:
         trace.enc_out = enc
     (x, p_pred, e_pred, log_d, d_rounded, mel_lens, mel_masks) = variance_adaptor(
-        sd, d, enc, src_masks, p_control, e_control, 1.0, trace, force_durations)
+        sd, d, enc, src_masks, p_control, e_control, 1.0, trace, force_durations, t_pad)
     dec, mel_masks = mel_decoder(sd, d, x, mel_masks)
     if trace is not None:
         trace.dec_out = dec

@@ -1,0 +1,75 @@
+#!/usr/bin/env python
+"""Turn gpurun_out/ ncu artefacts into the tracked summaries under profiles/.
+
+    python scripts/summarize_profiles.py <tag>      # e.g. r1a
+
+Reads gpurun_out/launches_*_<tag>.csv (ncu --metrics gpu__time_duration.sum launch lists),
+gpurun_out/prof_*_<tag>.ncu-rep (ncu --set full captures) and gpurun_out/bench_*_<tag>.json."""
+import collections
+import csv
+import glob
+import io
+import json
+import os
+import re
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GO, PR = os.path.join(ROOT, "gpurun_out"), os.path.join(ROOT, "profiles")
+tag = sys.argv[1]
+os.makedirs(PR, exist_ok=True)
+KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+        "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+        "lts__throughput.avg.pct_of_peak_sustained_elapsed", "l1tex__m_xbar2l1tex_read_bytes.sum", "sm__warps_active.avg.pct_of_peak_sustained_active",
+        "launch__registers_per_thread", "launch__grid_size", "launch__block_size", "launch__shared_mem_per_block_dynamic",
+        "sm__cycles_elapsed.max", "sm__cycles_elapsed.max.per_second", "smsp__cycles_active.avg",
+        "sm__inst_executed_pipe_tensor_subpipe_hmma.avg.pct_of_peak_sustained_active", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum",
+        "smsp__inst_executed.sum", "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active", "smsp__warp_issue_stalled_long_scoreboard_per_warp_active.pct",
+        "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active"]
+
+out = [f"# ncu summaries, tag {tag}\n"]
+for path in sorted(glob.glob(os.path.join(GO, f"launches_*_{tag}.csv"))):
+    rows = [r for r in csv.reader(open(path)) if len(r) > 10]
+    if not rows:
+        continue
+    hdr = rows[0]
+    ki, vi, mi = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index("Metric Name")
+    agg, tot = collections.OrderedDict(), 0.0
+    for r in rows[1:]:
+        if r[mi] != "gpu__time_duration.sum":
+            continue
+        name = re.sub(r"\(.*", "", r[ki]).replace("void ", "").replace("<unnamed>::", "")
+        v = float(r[vi].replace(",", ""))
+        a = agg.setdefault(name, [0, 0.0]); a[0] += 1; a[1] += v; tot += v
+    out.append(f"\n## launch list {os.path.basename(path)} (cold-cache, serialised; compare shares)\n")
+    out.append("| kernel | launches | total us | share |\n|---|---|---|---|")
+    for k, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+        out.append(f"| `{k}` | {n} | {t / 1e3:.1f} | {100 * t / tot:.1f} % |")
+for path in sorted(glob.glob(os.path.join(GO, f"prof_*_{tag}.ncu-rep"))):
+    txt = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(txt)))
+    if len(rows) < 3:
+        continue
+    hdr, units = rows[0], rows[1]
+    for vals in rows[2:]:
+        d = dict(zip(hdr, zip(vals, units)))
+        out.append(f"\n## full capture {os.path.basename(path)}: `{d['Kernel Name'][0][:120]}`\n")
+        out.append("| metric | value | unit |\n|---|---|---|")
+        for k in KEYS:
+            if k in d:
+                out.append(f"| {k} | {d[k][0]} | {d[k][1]} |")
+        if "dram__bytes_read.sum" in d:
+            def tobytes(v, u):
+                m = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+                return float(v.replace(",", "")) * m.get(u, 1)
+            tr = tobytes(*d["dram__bytes_read.sum"]) + tobytes(*d["dram__bytes_write.sum"])
+            out.append(f"| dram traffic (read+write) | {tr / 1e6:.1f} | MB per launch |")
+for path in sorted(glob.glob(os.path.join(GO, f"bench_*_{tag}.json"))):
+    try:
+        d = json.loads(open(path).read().strip().splitlines()[-1])
+    except Exception:
+        continue
+    out.append(f"\n## bench line {os.path.basename(path)}\n\n```json\n{json.dumps(d, indent=1)}\n```")
+open(os.path.join(PR, f"{tag}_summary.md"), "w").write("\n".join(out) + "\n")
+print("wrote", os.path.join(PR, f"{tag}_summary.md"))
