@@ -45,6 +45,8 @@ extern "C" {
 /* arithmetic used by a segment of the path */
 #define FS2_PREC_FP32 0 /* fp32 FFMA kernels (fp32-faithful; decides durations and pitch/energy buckets) */
 #define FS2_PREC_BF16 1 /* tcgen05 tensor-core kernels: bf16 operands, fp32 accumulate in TMEM */
+#define FS2_PREC_BF16X3 2 /* tcgen05, fp32-faithful: operands split into 3 bf16 terms, 6 cross products per MAC block
+                             accumulated in fp32 (error ~2^-23 per product); attention stays fp32 FFMA */
 
 typedef struct fs2_handle fs2_handle;
 
@@ -94,7 +96,7 @@ int fs2_load_weights(fs2_handle* h, const fs2_weight_desc* descs, int32_t n);
 
 /* encoder_prec covers txt_encoder + all three variance predictors (the discrete
  * decisions: durations, pitch/energy buckets); decoder_prec covers mel_decoder,
- * mel_linear and PostNet.  Defaults: FP32 / BF16. */
+ * mel_linear and PostNet.  Defaults: BF16X3 / BF16. */
 int fs2_set_precision(fs2_handle* h, int32_t encoder_prec, int32_t decoder_prec);
 
 /* ---- the forward, in two stages because T = max(sum(durations)) is data dependent --- */

@@ -31,7 +31,7 @@ struct RawT {
 
 struct GemmW {
   float* wf = nullptr;  // [taps][K][N]
-  bf16* wb = nullptr;   // [taps][N][K]
+  bf16* wb = nullptr;   // [3][taps][N][K]: plane 0 = bf16(w), planes 1-2 = split residuals (bf16x3 mode)
   float* bias = nullptr;
   int N = 0, K = 0, taps = 1;
 };
@@ -50,7 +50,7 @@ struct PredW {
 struct fs2_handle {
   fs2_dims dims{};
   int device = 0;
-  int prec_enc = FS2_PREC_FP32, prec_dec = FS2_PREC_BF16;
+  int prec_enc = FS2_PREC_BF16X3, prec_dec = FS2_PREC_BF16;
   bool loaded = false;
   std::string err;
   std::map<std::string, RawT> raw;
@@ -188,7 +188,7 @@ int build_gemm(fs2_handle* h, GemmW& g, const std::vector<std::string>& wkeys, c
   g.K = K;
   g.taps = taps;
   RCHECK(dev_alloc(h, &g.wf, (size_t)taps * K * g.N));
-  RCHECK(dev_alloc(h, &g.wb, (size_t)taps * K * g.N));
+  RCHECK(dev_alloc(h, &g.wb, (size_t)3 * taps * K * g.N));
   RCHECK(dev_alloc(h, &g.bias, (size_t)g.N));
   for (int i = 0; i < parts; ++i) {
     const float* w = nullptr;
@@ -275,6 +275,15 @@ int position_table(fs2_handle* h, int stack, int S, const float** out, cudaStrea
   return FS2_OK;
 }
 
+inline int planes_of(int prec) { return prec == FS2_PREC_BF16X3 ? 3 : prec == FS2_PREC_BF16 ? 1 : 0; }
+
+// bf16 shadow of an fp32 activation tensor for a tensor-core consumer of precision `prec` (no-op for fp32 consumers)
+cudaError_t make_shadow(const float* x, size_t n, int prec, bf16* xb, cudaStream_t st) {
+  if (prec == FS2_PREC_BF16) return rowops_f32_to_bf16(x, (int64_t)n, xb, st);
+  if (prec == FS2_PREC_BF16X3) return rowops_split3(x, (int64_t)n, xb, (int64_t)n, st);
+  return cudaSuccess;
+}
+
 ConvGemmArgs base_args(const GemmW& w, int B, int S, int SA, const int* lens) {
   ConvGemmArgs a;
   memset(&a, 0, sizeof a);
@@ -291,7 +300,10 @@ int run_gemm(fs2_handle* h, int prec, const ConvGemmArgs& a, cudaStream_t st, co
     if (e != cudaSuccess) return h ? h->cuda_fail(e, "simt_conv_gemm_launch") : fs2_fail_cuda(e, "simt_conv_gemm_launch");
     return FS2_OK;
   }
-  int rc = tc_conv_gemm_launch(a, st);
+  ConvGemmArgs b = a;
+  b.planes = prec == FS2_PREC_BF16X3 ? 3 : 1;
+  if (b.out_planes == 0) b.out_planes = b.planes;
+  int rc = tc_conv_gemm_launch(b, st);
   if (rc != FS2_OK && h) h->err = g_last_error;
   return rc;
 }
@@ -327,6 +339,37 @@ int run_fft_stack(fs2_handle* h, std::vector<FftW>& Ls, int l0, int l1, int prec
       a = base_args(L.w2, B, S, SA, lens);
       a.A = hid; a.epi = EPI_RES_LN; a.mask_mode = MASK_LEN; a.residual = y; a.ln_g = L.ln2_g; a.ln_b = L.ln2_b;
       a.out = x; a.ldo = D;
+      RCHECK(run_gemm(h, prec, a, st, tg + "ffn_w2_ln"));
+    }
+    return FS2_OK;
+  }
+  if (prec == FS2_PREC_BF16X3) {
+    // fp32-faithful tensor-core path: bf16x3 GEMMs (xb, yb, attb, hidb hold 3 planes), fp32 FFMA attention
+    WS(float, qkv, "fft.qkv", R * 3 * D);
+    WS(float, att, "fft.att", R * D);
+    WS(bf16, yb3, "fft.yb3", 3 * R * D);
+    WS(bf16, attb3, "fft.attb3", 3 * R * D);
+    WS(bf16, hidb3, "fft.hidb3", 3 * R * F);
+    for (int l = l0; l < l1; ++l) {
+      FftW& L = Ls[l];
+      ConvGemmArgs a = base_args(L.qkv, B, S, SA, lens);
+      a.Ab = xb; a.epi = EPI_BIAS; a.mask_mode = MASK_GRID; a.out = qkv; a.ldo = 3 * D;
+      RCHECK(run_gemm(h, prec, a, st, tg + "qkv"));
+      {
+        PROF(tg + "attn");
+        HCHECK(simt_attention_launch(qkv, 3 * D, 0, D, 2 * D, lens, B, S, SA, H, dk, att, D, st));
+        HCHECK(rowops_split3(att, (int64_t)(R * D), attb3, (int64_t)(R * D), st));
+      }
+      a = base_args(L.fc, B, S, SA, lens);
+      a.Ab = attb3; a.epi = EPI_RES_LN; a.mask_mode = MASK_LEN; a.residual = x; a.ln_g = L.ln1_g; a.ln_b = L.ln1_b;
+      a.out = y; a.ldo = D; a.out_b = yb3; a.ldob = D;
+      RCHECK(run_gemm(h, prec, a, st, tg + "fc_ln"));
+      a = base_args(L.w1, B, S, SA, lens);
+      a.Ab = yb3; a.epi = EPI_RELU; a.mask_mode = MASK_GRID; a.out_b = hidb3; a.ldob = F;
+      RCHECK(run_gemm(h, prec, a, st, tg + "ffn_w1"));
+      a = base_args(L.w2, B, S, SA, lens);
+      a.Ab = hidb3; a.epi = EPI_RES_LN; a.mask_mode = MASK_LEN; a.residual = y; a.ln_g = L.ln2_g; a.ln_b = L.ln2_b;
+      a.out = x; a.ldo = D; a.out_b = xb; a.ldob = D;
       RCHECK(run_gemm(h, prec, a, st, tg + "ffn_w2_ln"));
     }
     return FS2_OK;
@@ -372,13 +415,13 @@ int run_predictor(fs2_handle* h, PredW& P, int prec, const float* x, const bf16*
   const size_t R = (size_t)B * SA;
   WS(float, p1, "pred.h1", R * C);
   bf16* p1b = nullptr;
-  if (prec == FS2_PREC_BF16) {
-    WS(bf16, t, "pred.h1b", R * C);
+  if (prec != FS2_PREC_FP32) {
+    WS(bf16, t, "pred.h1b", (prec == FS2_PREC_BF16X3 ? 3 : 1) * R * C);
     p1b = t;
   }
   ConvGemmArgs a = base_args(P.c1, B, S, SA, lens);
   a.A = x; a.Ab = xb; a.epi = EPI_RELU_LN; a.mask_mode = MASK_GRID; a.ln_g = P.ln1_g; a.ln_b = P.ln1_b;
-  a.out = p1; a.ldo = C; a.out_b = p1b; a.ldob = C;
+  a.out = prec == FS2_PREC_FP32 ? p1 : nullptr; a.ldo = C; a.out_b = p1b; a.ldob = C;
   RCHECK(run_gemm(h, prec, a, st, tg + "conv1"));
   a = base_args(P.c2, B, S, SA, lens);
   a.A = p1; a.Ab = p1b; a.epi = EPI_RELU_LN_DOT; a.mask_mode = MASK_LEN; a.ln_g = P.ln2_g; a.ln_b = P.ln2_b;
@@ -392,14 +435,15 @@ int run_mel_postnet(fs2_handle* h, int prec, const float* dec, const bf16* decb,
                     float* mel_post, cudaStream_t st) {
   const int M = h->dims.n_mel, P = h->dims.pn_dim, NL = h->dims.pn_layers;
   const size_t R = (size_t)B * TA;
-  const bool tc = prec == FS2_PREC_BF16;
+  const bool tc = prec != FS2_PREC_FP32;
+  const size_t np = (size_t)planes_of(prec);
   WS(float, melg, "pn.mel", R * M);
   bf16 *melb = nullptr, *pa_b = nullptr, *pb_b = nullptr;
   float *pa = nullptr, *pb = nullptr;
   if (tc) {
-    WS(bf16, t0, "pn.melb", R * M); melb = t0;
-    WS(bf16, t1, "pn.a_b", R * P);  pa_b = t1;
-    WS(bf16, t2, "pn.b_b", R * P);  pb_b = t2;
+    WS(bf16, t0, "pn.melb", np * R * M); melb = t0;
+    WS(bf16, t1, "pn.a_b", np * R * P);  pa_b = t1;
+    WS(bf16, t2, "pn.b_b", np * R * P);  pb_b = t2;
   } else {
     WS(float, t1, "pn.a", R * P); pa = t1;
     WS(float, t2, "pn.b", R * P); pb = t2;
@@ -493,8 +537,8 @@ void fs2_destroy(fs2_handle* h) {
 
 int fs2_set_precision(fs2_handle* h, int32_t enc, int32_t dec) {
   if (!h) return FS2_ERR_INVALID;
-  if ((enc != FS2_PREC_FP32 && enc != FS2_PREC_BF16) || (dec != FS2_PREC_FP32 && dec != FS2_PREC_BF16))
-    return h->fail(FS2_ERR_INVALID, "precision must be FS2_PREC_FP32 or FS2_PREC_BF16");
+  if (enc < FS2_PREC_FP32 || enc > FS2_PREC_BF16X3 || dec < FS2_PREC_FP32 || dec > FS2_PREC_BF16X3)
+    return h->fail(FS2_ERR_INVALID, "precision must be FS2_PREC_FP32, FS2_PREC_BF16 or FS2_PREC_BF16X3");
   h->prec_enc = enc;
   h->prec_dec = dec;
   return FS2_OK;
@@ -594,8 +638,8 @@ int fs2_forward_stage1(fs2_handle* h, const int64_t* texts, const int64_t* src_l
   WS(int, mlens32, "s1.mel_lens32", B);
   WS(int, tmax_dev, "s1.tmax", 1);
   bf16* xb = nullptr;
-  if (h->prec_enc == FS2_PREC_BF16) {
-    WS(bf16, t, "s1.xb", R * D);
+  if (h->prec_enc != FS2_PREC_FP32) {
+    WS(bf16, t, "s1.xb", (size_t)planes_of(h->prec_enc) * R * D);
     xb = t;
   }
   const float* pe = nullptr;
@@ -605,7 +649,7 @@ int fs2_forward_stage1(fs2_handle* h, const int64_t* texts, const int64_t* src_l
     HCHECK(rowops_lens_to_i32(src_lens, B, L, lens32, st));
     if (src_mask) HCHECK(rowops_mask(src_lens, nullptr, B, L, src_mask, st));
     HCHECK(rowops_embed_pe(texts, raw_ptr(h, "txt_encoder.src_word_emb.weight"), pe, d.vocab, B, L, LA, D, x, nullptr, st));
-    if (xb) HCHECK(rowops_f32_to_bf16(x, (int64_t)(R * D), xb, st));
+    HCHECK(make_shadow(x, R * D, h->prec_enc, xb, st));
   }
   RCHECK(run_fft_stack(h, h->enc, 0, d.n_enc_layers, h->prec_enc, x, xb, lens32, B, L, LA, st));
   // modules.py:116 duration predictor on the encoder output
@@ -614,14 +658,14 @@ int fs2_forward_stage1(fs2_handle* h, const int64_t* texts, const int64_t* src_l
   if (d.pitch_phoneme_level) {
     RCHECK(run_predictor(h, h->pred[1], h->prec_enc, x, xb, lens32, B, L, LA, pitch_ph, st));
     HCHECK(rowops_variance_embed(pitch_ph, p_control, raw_ptr(h, "variance_adaptor.pitch_bins"), d.n_bins,
-                                 raw_ptr(h, "variance_adaptor.pitch_embedding.weight"), nullptr, x, xb, B, L, LA, D,
-                                 nullptr, st));
+                                 raw_ptr(h, "variance_adaptor.pitch_embedding.weight"), nullptr, x, xb,
+                                 planes_of(h->prec_enc), B, L, LA, D, nullptr, st));
   }
   if (d.energy_phoneme_level) {
     RCHECK(run_predictor(h, h->pred[2], h->prec_enc, x, xb, lens32, B, L, LA, energy_ph, st));
     HCHECK(rowops_variance_embed(energy_ph, e_control, raw_ptr(h, "variance_adaptor.energy_bins"), d.n_bins,
-                                 raw_ptr(h, "variance_adaptor.energy_embedding.weight"), nullptr, x, xb, B, L, LA, D,
-                                 nullptr, st));
+                                 raw_ptr(h, "variance_adaptor.energy_embedding.weight"), nullptr, x, xb,
+                                 planes_of(h->prec_enc), B, L, LA, D, nullptr, st));
   }
   // modules.py:132-135 + LengthRegulator bookkeeping
   {
@@ -657,9 +701,12 @@ int fs2_forward_stage2(fs2_handle* h, int32_t T, float p_control, float e_contro
 
   WS(float, x, "s2.x", R * D);
   bf16* xb = nullptr;
-  if (h->prec_dec == FS2_PREC_BF16 || h->prec_enc == FS2_PREC_BF16) {
-    WS(bf16, t, "s2.xb", R * D);
-    xb = t;
+  {
+    const int np = planes_of(h->prec_dec) > planes_of(h->prec_enc) ? planes_of(h->prec_dec) : planes_of(h->prec_enc);
+    if (np > 0) {
+      WS(bf16, t, "s2.xb", (size_t)np * R * D);
+      xb = t;
+    }
   }
   {
     PROF("rows.length_regulate");
@@ -670,25 +717,31 @@ int fs2_forward_stage2(fs2_handle* h, int32_t T, float p_control, float e_contro
   const float* pe = nullptr;
   RCHECK(position_table(h, 1, T, &pe, st));
   const bool pitch_fl = !d.pitch_phoneme_level, energy_fl = !d.energy_phoneme_level;
-  if (h->prec_enc == FS2_PREC_BF16 && (pitch_fl || energy_fl)) HCHECK(rowops_f32_to_bf16(x, (int64_t)(R * D), xb, st));
+  // every producer of x writes the bf16 shadow in the precision of its NEXT consumer
+  if (pitch_fl || energy_fl) {
+    PROF("rows.length_regulate");
+    HCHECK(make_shadow(x, R * D, h->prec_enc, xb, st));
+  }
   // modules.py:139-149 frame-level pitch then energy (energy sees x + pitch embedding)
   if (pitch_fl) {
     RCHECK(run_predictor(h, h->pred[1], h->prec_enc, x, xb, mlens32, B, T, TA, pitch, st));
     PROF("rows.variance_embed");
     HCHECK(rowops_variance_embed(pitch, p_control, raw_ptr(h, "variance_adaptor.pitch_bins"), d.n_bins,
                                  raw_ptr(h, "variance_adaptor.pitch_embedding.weight"), energy_fl ? nullptr : pe, x, xb,
-                                 B, T, TA, D, nullptr, st));
+                                 planes_of(energy_fl ? h->prec_enc : h->prec_dec), B, T, TA, D, nullptr, st));
   }
   if (energy_fl) {
     RCHECK(run_predictor(h, h->pred[2], h->prec_enc, x, xb, mlens32, B, T, TA, energy, st));
     // fused: + energy embedding, + decoder positional encoding (Models.py:231-233), bf16 shadow for the decoder
     PROF("rows.variance_embed");
     HCHECK(rowops_variance_embed(energy, e_control, raw_ptr(h, "variance_adaptor.energy_bins"), d.n_bins,
-                                 raw_ptr(h, "variance_adaptor.energy_embedding.weight"), pe, x, xb, B, T, TA, D,
-                                 nullptr, st));
+                                 raw_ptr(h, "variance_adaptor.energy_embedding.weight"), pe, x, xb,
+                                 planes_of(h->prec_dec), B, T, TA, D, nullptr, st));
   }
-  if (!pitch_fl && !energy_fl)  // both phoneme-level: only the decoder's positional add remains
-    HCHECK(rowops_add_pe(x, xb, pe, B, T, TA, D, st));
+  if (!pitch_fl && !energy_fl) {  // both phoneme-level: only the decoder's positional add remains
+    HCHECK(rowops_add_pe(x, nullptr, pe, B, T, TA, D, st));
+    HCHECK(make_shadow(x, R * D, h->prec_dec, xb, st));
+  }
   RCHECK(run_fft_stack(h, h->dec, 0, d.n_dec_layers, h->prec_dec, x, xb, mlens32, B, T, TA, st));
   RCHECK(run_mel_postnet(h, h->prec_dec, x, xb, B, T, TA, mel, mel_post, st));
   return FS2_OK;
@@ -805,7 +858,7 @@ int fs2_op_fft_stack(fs2_handle* h, int32_t stack, int32_t l0, int32_t l1, int32
   if (!h || !h->loaded) return FS2_ERR_STATE;
   std::vector<FftW>& Ls = stack == 0 ? h->enc : h->dec;
   if (!x || !lens || !out || B <= 0 || S <= 0 || l0 < 0 || l1 > (int)Ls.size() || l0 > l1 ||
-      (prec != FS2_PREC_FP32 && prec != FS2_PREC_BF16))
+      prec < FS2_PREC_FP32 || prec > FS2_PREC_BF16X3)
     return h->fail(FS2_ERR_INVALID, "bad argument");
   HCHECK(cudaSetDevice(h->device));
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
@@ -814,9 +867,10 @@ int fs2_op_fft_stack(fs2_handle* h, int32_t stack, int32_t l0, int32_t l1, int32
   WS(int, lens32, "op.lens32", B);
   WS(float, xg, "op.x", R * D);
   bf16* xb = nullptr;
-  if (prec == FS2_PREC_BF16) { WS(bf16, t, "op.xb", R * D); xb = t; }
+  if (prec != FS2_PREC_FP32) { WS(bf16, t, "op.xb", (size_t)planes_of(prec) * R * D); xb = t; }
   HCHECK(rowops_lens_to_i32(lens, B, S, lens32, st));
-  HCHECK(rowops_to_grid(x, B, S, SA, D, xg, D, 0, xb, st));
+  HCHECK(rowops_to_grid(x, B, S, SA, D, xg, D, 0, nullptr, st));
+  HCHECK(make_shadow(xg, R * D, prec, xb, st));
   RCHECK(run_fft_stack(h, Ls, l0, l1, prec, xg, xb, lens32, B, S, SA, st));
   HCHECK(rowops_from_grid(xg, B, S, SA, D, out, st));
   return FS2_OK;
@@ -833,9 +887,10 @@ int fs2_op_variance_predictor(fs2_handle* h, int32_t which, const float* x, cons
   WS(int, lens32, "op.lens32", B);
   WS(float, xg, "op.x", R * D);
   bf16* xb = nullptr;
-  if (h->prec_enc == FS2_PREC_BF16) { WS(bf16, t, "op.xb", R * D); xb = t; }
+  if (h->prec_enc != FS2_PREC_FP32) { WS(bf16, t, "op.xb", (size_t)planes_of(h->prec_enc) * R * D); xb = t; }
   HCHECK(rowops_lens_to_i32(lens, B, S, lens32, st));
-  HCHECK(rowops_to_grid(x, B, S, SA, D, xg, D, 0, xb, st));
+  HCHECK(rowops_to_grid(x, B, S, SA, D, xg, D, 0, nullptr, st));
+  HCHECK(make_shadow(xg, R * D, h->prec_enc, xb, st));
   return run_predictor(h, h->pred[which], h->prec_enc, xg, xb, lens32, B, S, SA, out, st);
 }
 
@@ -847,14 +902,14 @@ int fs2_op_variance_embed(fs2_handle* h, int32_t which, float* pred, float contr
   const char* nm = which == 1 ? "pitch" : "energy";
   HCHECK(rowops_variance_embed(pred, control, raw_ptr(h, std::string("variance_adaptor.") + nm + "_bins"), h->dims.n_bins,
                                raw_ptr(h, std::string("variance_adaptor.") + nm + "_embedding.weight"), nullptr, x, nullptr,
-                               B, S, S, h->dims.d_model, idx_out, reinterpret_cast<cudaStream_t>(stream)));
+                               0, B, S, S, h->dims.d_model, idx_out, reinterpret_cast<cudaStream_t>(stream)));
   return FS2_OK;
 }
 
 int fs2_op_mel_postnet(fs2_handle* h, int32_t prec, const float* dec, int32_t B, int32_t T, float* mel, float* mel_post,
                        void* stream) {
   if (!h || !h->loaded) return FS2_ERR_STATE;
-  if (!dec || !mel || !mel_post || B <= 0 || T <= 0 || (prec != FS2_PREC_FP32 && prec != FS2_PREC_BF16))
+  if (!dec || !mel || !mel_post || B <= 0 || T <= 0 || prec < FS2_PREC_FP32 || prec > FS2_PREC_BF16X3)
     return h->fail(FS2_ERR_INVALID, "bad argument");
   HCHECK(cudaSetDevice(h->device));
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
@@ -862,15 +917,17 @@ int fs2_op_mel_postnet(fs2_handle* h, int32_t prec, const float* dec, int32_t B,
   const size_t R = (size_t)B * TA;
   WS(float, xg, "op.x", R * D);
   bf16* xb = nullptr;
-  if (prec == FS2_PREC_BF16) { WS(bf16, t, "op.xb", R * D); xb = t; }
-  HCHECK(rowops_to_grid(dec, B, T, TA, D, xg, D, 0, xb, st));
+  if (prec != FS2_PREC_FP32) { WS(bf16, t, "op.xb", (size_t)planes_of(prec) * R * D); xb = t; }
+  HCHECK(rowops_to_grid(dec, B, T, TA, D, xg, D, 0, nullptr, st));
+  HCHECK(make_shadow(xg, R * D, prec, xb, st));
   return run_mel_postnet(h, prec, xg, xb, B, T, TA, mel, mel_post, st);
 }
 
 int fs2_op_conv_gemm(int32_t prec, const float* A, const float* W, const float* bias, int32_t B, int32_t S, int32_t K,
                      int32_t N, int32_t taps, int32_t act, float* out, void* stream) {
   if (!A || !W || !bias || !out || B <= 0 || S <= 0 || K <= 0 || N <= 0 || taps < 1 || taps > 2 * FS2_HALO + 1 ||
-      taps % 2 == 0 || K % 16 || N % 4 || act < 0 || act > 2) { g_last_error = "bad argument"; return FS2_ERR_INVALID; }
+      taps % 2 == 0 || K % 16 || N % 4 || act < 0 || act > 2 || prec < FS2_PREC_FP32 || prec > FS2_PREC_BF16X3) {
+    g_last_error = "bad argument"; return FS2_ERR_INVALID; }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int SA = S + FS2_HALO;
   const size_t R = (size_t)B * SA;
@@ -880,11 +937,12 @@ int fs2_op_conv_gemm(int32_t prec, const float* A, const float* W, const float* 
   cudaError_t e = cudaSuccess;
   do {
     if ((e = cudaMalloc(reinterpret_cast<void**>(&Ag), sizeof(float) * R * K)) != cudaSuccess) break;
-    if ((e = cudaMalloc(reinterpret_cast<void**>(&Ab), sizeof(bf16) * R * K)) != cudaSuccess) break;
+    if ((e = cudaMalloc(reinterpret_cast<void**>(&Ab), sizeof(bf16) * 3 * R * K)) != cudaSuccess) break;
     if ((e = cudaMalloc(reinterpret_cast<void**>(&Wf), sizeof(float) * (size_t)N * K * taps)) != cudaSuccess) break;
-    if ((e = cudaMalloc(reinterpret_cast<void**>(&Wb), sizeof(bf16) * (size_t)N * K * taps)) != cudaSuccess) break;
+    if ((e = cudaMalloc(reinterpret_cast<void**>(&Wb), sizeof(bf16) * 3 * (size_t)N * K * taps)) != cudaSuccess) break;
     if ((e = cudaMalloc(reinterpret_cast<void**>(&Og), sizeof(float) * R * N)) != cudaSuccess) break;
-    if ((e = rowops_to_grid(A, B, S, SA, K, Ag, K, 0, Ab, st)) != cudaSuccess) break;
+    if ((e = rowops_to_grid(A, B, S, SA, K, Ag, K, 0, nullptr, st)) != cudaSuccess) break;
+    if ((e = make_shadow(Ag, R * K, prec, Ab, st)) != cudaSuccess) break;
     if ((e = rowops_pack_weight(W, N, K, taps, nullptr, Wf, Wb, N, 0, st)) != cudaSuccess) break;
     ConvGemmArgs a;
     memset(&a, 0, sizeof a);

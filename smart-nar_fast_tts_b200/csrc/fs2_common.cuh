@@ -38,11 +38,15 @@ enum Fs2Mask : int {
 struct ConvGemmArgs {
   // A operand: activations in grid layout, lda == K
   const float* A;
-  const bf16* Ab;
+  const bf16* Ab;   // tcgen05 path: [planes][R][K]
   int K;
+  // tcgen05 path: 1 = plain bf16 operands; 3 = bf16x3 split operands (hi, mid, lo planes of A and W): the six
+  // significant cross products are accumulated in fp32, which reproduces an fp32 GEMM to ~2^-23 per product
+  int planes;
+  int out_planes;   // planes written to out_b (1, or 3 = split the fp32 result for a following bf16x3 GEMM)
   // W operand, per tap
   const float* Wf;  // [taps][K][N]   (SIMT fp32 kernel; n contiguous)
-  const bf16* Wb;   // [taps][N][K]   (tcgen05 kernel; K-major B operand)
+  const bf16* Wb;   // [planes][taps][N][K]   (tcgen05 kernel; K-major B operand)
   const float* bias;
   int N, taps;
   // grid
@@ -57,7 +61,7 @@ struct ConvGemmArgs {
   // outputs (any may be null)
   float* out;      // grid layout [R, ldo]
   int ldo;
-  bf16* out_b;     // grid layout [R, ldob] bf16 shadow (tcgen05 path)
+  bf16* out_b;     // grid layout [out_planes][R, ldob] bf16 shadow (tcgen05 path)
   int ldob;
   float* out_user; // dense user layout: row (b,p), p < S, at (b*S + p)*ldu
   int ldu;
@@ -97,15 +101,18 @@ cudaError_t rowops_duration_scan(const float* d, int B, int L, int* cum, int64_t
 cudaError_t rowops_length_regulate(const float* x, int x_row_stride_utt, const int* cum, int B, int L, int D, int T,
                                    int out_SA, float* out, cudaStream_t st);
 cudaError_t rowops_variance_embed(float* pred, float control, const float* bins, int n_bins, const float* emb,
-                                  const float* pe, float* x, bf16* xb, int B, int S, int SA, int D, int* idx_out,
-                                  cudaStream_t st);
+                                  const float* pe, float* x, bf16* xb, int xb_planes, int B, int S, int SA, int D,
+                                  int* idx_out, cudaStream_t st);
 cudaError_t rowops_gaussian_upsample(const float* x, const float* d, int B, int L, int D, int T, int T_w, float* out,
                                      float* s, float* w, cudaStream_t st);
 cudaError_t rowops_to_grid(const float* x_user, int B, int S, int SA, int C, float* out, int ldo, int col_off,
                            bf16* out_b, cudaStream_t st);
 cudaError_t rowops_from_grid(const float* x_grid, int B, int S, int SA, int C, float* out_user, cudaStream_t st);
+// dst_b: [3][taps][n_total][K] -- plane 0 doubles as the plain bf16 weight, planes 1..2 are the split residuals
 cudaError_t rowops_pack_weight(const float* src, int N, int K, int taps, const float* scale, float* dst_f,
                                bf16* dst_b, int n_total, int n_off, cudaStream_t st);
+// fp32 -> bf16x3 planes: dst[p][i], plane stride = plane_elems
+cudaError_t rowops_split3(const float* src, int64_t n, bf16* dst, int64_t plane_elems, cudaStream_t st);
 cudaError_t rowops_bn_fold(const float* conv_bias, const float* g, const float* b, const float* mean,
                            const float* var, int n, float eps, float* scale_out, float* bias_out, cudaStream_t st);
 cudaError_t rowops_f32_to_bf16(const float* src, int64_t n, bf16* dst, cudaStream_t st);

@@ -12,6 +12,31 @@ namespace {
 
 __device__ __forceinline__ float4 ld4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 __device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+__device__ __forceinline__ uint32_t pack2(float a, float b) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+// y -> (hi, mid, lo) bf16 terms, residuals exact in fp32
+__device__ __forceinline__ void split3f(float y, float& hi, float& mid, float& lo) {
+  hi = __bfloat162float(__float2bfloat16_rn(y));
+  const float r1 = y - hi;
+  mid = __bfloat162float(__float2bfloat16_rn(r1));
+  lo = r1 - mid;
+}
+// write 4 consecutive values as bf16 into `planes` planes (1: rounded; 3: hi/mid/lo split)
+__device__ __forceinline__ void store_planes4(bf16* dst, size_t plane_elems, int planes, float4 a) {
+  if (planes == 1) {
+    *reinterpret_cast<uint2*>(dst) = make_uint2(pack2(a.x, a.y), pack2(a.z, a.w));
+    return;
+  }
+  float h[4], m[4], l[4];
+  split3f(a.x, h[0], m[0], l[0]); split3f(a.y, h[1], m[1], l[1]);
+  split3f(a.z, h[2], m[2], l[2]); split3f(a.w, h[3], m[3], l[3]);
+  *reinterpret_cast<uint2*>(dst) = make_uint2(pack2(h[0], h[1]), pack2(h[2], h[3]));
+  *reinterpret_cast<uint2*>(dst + plane_elems) = make_uint2(pack2(m[0], m[1]), pack2(m[2], m[3]));
+  *reinterpret_cast<uint2*>(dst + 2 * plane_elems) = make_uint2(pack2(l[0], l[1]), pack2(l[2], l[3]));
+}
+
 
 // ---------------------------------------------------------------------------------------------
 // transformer/Models.py:82-91  out[b,p,:] = src_word_emb[texts[b,p]] + PE[p]   (all p < L, incl. PAD ids)
@@ -154,8 +179,8 @@ __global__ void __launch_bounds__(256) length_regulate_kernel(const float* __res
 // torch.bucketize(right=False) lower bound, incl. its behaviour on NaN boundaries (every compare false -> n_bins-1).
 __global__ void variance_embed_kernel(float* __restrict__ pred, float control, const float* __restrict__ bins,
                                       int n_bins, const float* __restrict__ emb, const float* __restrict__ pe,
-                                      float* __restrict__ x, bf16* __restrict__ xb, int B, int S, int SA, int D,
-                                      int* __restrict__ idx_out) {
+                                      float* __restrict__ x, bf16* __restrict__ xb, int xb_planes, int B, int S, int SA,
+                                      int D, int* __restrict__ idx_out) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (warp >= B * S) return;
   const int b = warp / S, p = warp - b * S;
@@ -181,13 +206,7 @@ __global__ void variance_embed_kernel(float* __restrict__ pred, float control, c
       a.x += q.x; a.y += q.y; a.z += q.z; a.w += q.w;
     }
     st4(x + row * D + c * 4, a);
-    if (xb) {
-      __nv_bfloat162 lo = __floats2bfloat162_rn(a.x, a.y), hi = __floats2bfloat162_rn(a.z, a.w);
-      uint2 pk;
-      pk.x = *reinterpret_cast<uint32_t*>(&lo);
-      pk.y = *reinterpret_cast<uint32_t*>(&hi);
-      *reinterpret_cast<uint2*>(xb + row * D + c * 4) = pk;
-    }
+    if (xb && xb_planes > 0) store_planes4(xb + row * D + c * 4, (size_t)B * SA * D, xb_planes, a);
   }
 }
 
@@ -308,7 +327,15 @@ __global__ void pack_weight_kernel(const float* __restrict__ src, int N, int K, 
   float v = src[i];
   if (scale) v *= scale[n];
   if (dst_f) dst_f[((size_t)t * K + k) * n_total + n_off + n] = v;
-  if (dst_b) dst_b[((size_t)t * n_total + n_off + n) * K + k] = __float2bfloat16_rn(v);
+  if (dst_b) {
+    const size_t plane = (size_t)taps * n_total * K, idx = ((size_t)t * n_total + n_off + n) * K + k;
+    const bf16 hi = __float2bfloat16_rn(v);
+    const float r1 = v - __bfloat162float(hi);
+    const bf16 mid = __float2bfloat16_rn(r1);
+    dst_b[idx] = hi;
+    dst_b[plane + idx] = mid;
+    dst_b[2 * plane + idx] = __float2bfloat16_rn(r1 - __bfloat162float(mid));
+  }
 }
 
 // BatchNorm1d(eval) folded into the preceding conv (transformer/Layers.py:120-167, eps 1e-5):
@@ -322,6 +349,11 @@ __global__ void bn_fold_kernel(const float* __restrict__ conv_bias, const float*
   const float s = g[i] / sqrtf(var[i] + eps);
   scale_out[i] = s;
   bias_out[i] = (conv_bias[i] - mean[i]) * s + b[i];
+}
+
+__global__ void split3_kernel(const float* __restrict__ src, int64_t n4, bf16* __restrict__ dst, int64_t plane_elems) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n4) store_planes4(dst + i * 4, (size_t)plane_elems, 3, ld4(src + i * 4));
 }
 
 __global__ void f32_to_bf16_kernel(const float* __restrict__ src, int64_t n, bf16* __restrict__ dst) {
@@ -410,11 +442,17 @@ cudaError_t rowops_length_regulate(const float* x, int x_row_stride_utt, const i
   return LAUNCHED();
 }
 cudaError_t rowops_variance_embed(float* pred, float control, const float* bins, int n_bins, const float* emb,
-                                  const float* pe, float* x, bf16* xb, int B, int S, int SA, int D, int* idx_out,
-                                  cudaStream_t st) {
+                                  const float* pe, float* x, bf16* xb, int xb_planes, int B, int S, int SA, int D,
+                                  int* idx_out, cudaStream_t st) {
   if (B * S <= 0) return cudaSuccess;
-  variance_embed_kernel<<<blocks_for((size_t)B * S, 8), 256, 0, st>>>(pred, control, bins, n_bins, emb, pe, x, xb, B, S,
-                                                                     SA, D, idx_out);
+  variance_embed_kernel<<<blocks_for((size_t)B * S, 8), 256, 0, st>>>(pred, control, bins, n_bins, emb, pe, x, xb,
+                                                                     xb_planes, B, S, SA, D, idx_out);
+  return LAUNCHED();
+}
+cudaError_t rowops_split3(const float* src, int64_t n, bf16* dst, int64_t plane_elems, cudaStream_t st) {
+  if (n <= 0) return cudaSuccess;
+  if (n % 4) return cudaErrorInvalidValue;
+  split3_kernel<<<blocks_for((size_t)(n / 4), 256), 256, 0, st>>>(src, n / 4, dst, plane_elems);
   return LAUNCHED();
 }
 cudaError_t rowops_gaussian_upsample(const float* x, const float* d, int B, int L, int D, int T, int T_w, float* out,

@@ -61,6 +61,14 @@ __device__ __forceinline__ void tma_load_2d(uint32_t smem_dst, const CUtensorMap
       : "memory");
 }
 
+// 3D tiled load (c0 = innermost element, c1 = row, c2 = plane); same OOB rule per dimension
+__device__ __forceinline__ void tma_load_3d(uint32_t smem_dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+
 // ------------------------------------------------------------------ tcgen05
 __device__ __forceinline__ void tmem_alloc(uint32_t smem_result, uint32_t ncols) {  // whole warp
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_result), "r"(ncols) : "memory");
@@ -173,6 +181,30 @@ inline bool make_tmap_bf16(CUtensorMap* m, const void* base, uint64_t rows, uint
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS;
+}
+
+// bf16 [planes][rows][cols] (row pitch = ld elements, plane pitch = plane_elems), box = [1, box_rows, 64 cols]:
+// a row coordinate outside [0, rows) is zero-filled WITHIN its plane (conv zero padding for every split plane)
+inline bool make_tmap_bf16_3d(CUtensorMap* m, const void* base, uint64_t planes, uint64_t rows, uint64_t cols, uint64_t ld,
+                              uint64_t plane_elems, uint32_t box_rows) {
+  PFN_encodeTiled fn = get_encode_fn();
+  if (!fn) return false;
+  cuuint64_t gdim[3] = {cols, rows, planes};
+  cuuint64_t gstride[2] = {ld * sizeof(bf16), plane_elems * sizeof(bf16)};
+  cuuint32_t box[3] = {64, box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), gdim, gstride, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+// fp32 -> three bf16 terms with hi + mid + lo == y to 2^-24 relative (each residual is exact in fp32)
+__device__ __forceinline__ void split3(float y, float& hi, float& mid, float& lo) {
+  hi = __bfloat162float(__float2bfloat16_rn(y));
+  const float r1 = y - hi;
+  mid = __bfloat162float(__float2bfloat16_rn(r1));
+  lo = r1 - mid;   // rounded to bf16 when packed
 }
 
 }  // namespace tc

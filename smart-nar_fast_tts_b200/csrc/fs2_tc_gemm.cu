@@ -5,6 +5,12 @@
 //     out[r, n] = epi( sum_t sum_k A[r + t - pad, k] * W[t][n][k] + bias[n] )
 // over the flat halo'ed row grid (fs2_common.cuh), bf16 operands, fp32 accumulation in TMEM.
 //
+// bf16x3 mode (a.planes == 3): A and W are given as three bf16 planes (hi, mid, lo; x = hi + mid + lo to 2^-24).  Per
+// (tap, k-block) the six significant cross products hi*hi, hi*mid, mid*hi, mid*mid, hi*lo, lo*hi are issued as six
+// ordinary bf16 MMAs into the same fp32 TMEM accumulator: an fp32-faithful GEMM on the tensor cores at 1/6 of the bf16
+// rate (~4-5x the FFMA path).  It carries the encoder and the variance predictors, whose outputs are rounded to
+// integer durations / bucket indices and therefore must track the fp32 reference to round-off.
+//
 // Structure (persistent, warp specialised, one CTA per SM):
 //   warp 0   : TMA producer.  Per k-step one 128x64 bf16 box of A at row coordinate r0 + t - pad (the conv tap is a
 //              row shift of the SAME activation tensor; rows outside the buffer are zero-filled by TMA = Conv1d zero
@@ -44,6 +50,35 @@ struct RowInfo {
   bool in_buf, in_grid, keep_len, keep;
 };
 
+// cross products of the bf16x3 split as (A plane, W plane), SMALLEST FIRST.  The tensor core truncates (round toward
+// zero) at every accumulation, an error proportional to the running sum: the five correction products are ~2^-8 of the
+// result, so while they are accumulated the truncation error is ~2^-8 ulp per step; only the final hi*hi pass
+// (K/16 steps) truncates at full magnitude.  Measured: with hi*hi first the error was 6x larger (profiles/r1b notes).
+__constant__ int c_combo_a[6] = {0, 2, 1, 0, 1, 0};
+__constant__ int c_combo_b[6] = {2, 0, 1, 1, 0, 0};
+
+// 32 consecutive outputs of one row -> bf16 (1 plane: rounded; 3 planes: hi/mid/lo split), 16-byte stores
+__device__ __forceinline__ void store_bf16_chunk(bf16* o, size_t plane_elems, int planes, const float (&y)[32], int nb, int N) {
+  if (planes != 3) {
+#pragma unroll
+    for (int j = 0; j < 32; j += 8)
+      if (nb + j < N)
+        *reinterpret_cast<uint4*>(o + j) = make_uint4(pack_bf16x2(y[j], y[j + 1]), pack_bf16x2(y[j + 2], y[j + 3]),
+                                                      pack_bf16x2(y[j + 4], y[j + 5]), pack_bf16x2(y[j + 6], y[j + 7]));
+    return;
+  }
+#pragma unroll
+  for (int j = 0; j < 32; j += 8) {
+    if (nb + j >= N) continue;
+    float h[8], m[8], l[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) split3(y[j + u], h[u], m[u], l[u]);
+    *reinterpret_cast<uint4*>(o + j) = make_uint4(pack_bf16x2(h[0], h[1]), pack_bf16x2(h[2], h[3]), pack_bf16x2(h[4], h[5]), pack_bf16x2(h[6], h[7]));
+    *reinterpret_cast<uint4*>(o + plane_elems + j) = make_uint4(pack_bf16x2(m[0], m[1]), pack_bf16x2(m[2], m[3]), pack_bf16x2(m[4], m[5]), pack_bf16x2(m[6], m[7]));
+    *reinterpret_cast<uint4*>(o + 2 * plane_elems + j) = make_uint4(pack_bf16x2(l[0], l[1]), pack_bf16x2(l[2], l[3]), pack_bf16x2(l[4], l[5]), pack_bf16x2(l[6], l[7]));
+  }
+}
+
 template <int BN>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 tc_conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -68,6 +103,7 @@ tc_conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int pad = (a.taps - 1) / 2;
   const int KB = (a.K + BKE - 1) / BKE;
+  const int ncombo = a.planes == 3 ? 6 : 1;
   const int iters = a.taps * KB;
   const int num_tiles = num_m_blocks * num_n_blocks;
   constexpr uint32_t TMEM_COLS = 2 * BN;  // 512 or 256: power of two
@@ -104,14 +140,17 @@ tc_conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int m_blk = tile / num_n_blocks, n_blk = tile - m_blk * num_n_blocks;
         const int r0 = m_blk * BM, n0 = n_blk * BN;
-        for (int it = 0; it < iters; ++it) {
-          const int t = it / KB, k0 = (it - t * KB) * BKE;
-          mbar_wait(empty_bar(stage), phase ^ 1u);
-          mbar_expect_tx(full_bar(stage), L::STAGE_BYTES);
-          const uint32_t sa = base + stage * L::STAGE_BYTES;
-          tma_load_2d(sa, &tmA, full_bar(stage), k0, r0 + t - pad);
-          tma_load_2d(sa + L::A_BYTES, &tmB, full_bar(stage), k0, t * a.N + n0);
-          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        for (int c = 0; c < ncombo; ++c) {
+          const int pa = ncombo == 1 ? 0 : c_combo_a[c], pb = ncombo == 1 ? 0 : c_combo_b[c];
+          for (int it = 0; it < iters; ++it) {
+            const int t = it / KB, k0 = (it - t * KB) * BKE;
+            mbar_wait(empty_bar(stage), phase ^ 1u);
+            mbar_expect_tx(full_bar(stage), L::STAGE_BYTES);
+            const uint32_t sa = base + stage * L::STAGE_BYTES;
+            tma_load_3d(sa, &tmA, full_bar(stage), k0, r0 + t - pad, pa);
+            tma_load_2d(sa + L::A_BYTES, &tmB, full_bar(stage), k0, (pb * a.taps + t) * a.N + n0);
+            if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+          }
         }
       }
     }
@@ -125,7 +164,8 @@ tc_conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         mbar_wait(tempty_bar(as), aphase ^ 1u);  // epilogue has drained this accumulator stage
         fence_after_sync();
         const uint32_t d_tmem = tmem_base + (uint32_t)(as * BN);
-        for (int it = 0; it < iters; ++it) {
+        const int steps = iters * ncombo;
+        for (int it = 0; it < steps; ++it) {
           mbar_wait(full_bar(stage), phase);
           fence_after_sync();
           const uint32_t sa = base + stage * L::STAGE_BYTES;
@@ -218,13 +258,8 @@ tc_conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
               for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(y[j], y[j + 1], y[j + 2], y[j + 3]);
             }
-            if (a.out_b) {
-              bf16* o = a.out_b + (size_t)ri.r * a.ldob + c * 32;
-#pragma unroll
-              for (int j = 0; j < 32; j += 8)
-                *reinterpret_cast<uint4*>(o + j) = make_uint4(pack_bf16x2(y[j], y[j + 1]), pack_bf16x2(y[j + 2], y[j + 3]),
-                                                              pack_bf16x2(y[j + 4], y[j + 5]), pack_bf16x2(y[j + 6], y[j + 7]));
-            }
+            if (a.out_b)
+              store_bf16_chunk(a.out_b + (size_t)ri.r * a.ldob + c * 32, (size_t)R * a.ldob, a.out_planes, y, c * 32, 256);
           }
         }
         if (a.epi == EPI_RELU_LN_DOT && ri.in_grid && a.out_user)
@@ -284,14 +319,8 @@ tc_conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             for (int j = 0; j < 32; j += 4)
               if (nb + j < a.N) *reinterpret_cast<float4*>(o + j) = make_float4(y[j], y[j + 1], y[j + 2], y[j + 3]);
           }
-          if (a.out_b && ri.in_buf) {
-            bf16* o = a.out_b + (size_t)ri.r * a.ldob + nb;
-#pragma unroll
-            for (int j = 0; j < 32; j += 8)
-              if (nb + j < a.N)
-                *reinterpret_cast<uint4*>(o + j) = make_uint4(pack_bf16x2(y[j], y[j + 1]), pack_bf16x2(y[j + 2], y[j + 3]),
-                                                              pack_bf16x2(y[j + 4], y[j + 5]), pack_bf16x2(y[j + 6], y[j + 7]));
-          }
+          if (a.out_b && ri.in_buf)
+            store_bf16_chunk(a.out_b + (size_t)ri.r * a.ldob + nb, (size_t)R * a.ldob, a.out_planes, y, nb, a.N);
           if (a.out_user && ri.in_grid) {
             float* o = a.out_user + ((size_t)ri.b * a.S + ri.p) * a.ldu + nb;
 #pragma unroll
@@ -326,9 +355,10 @@ int launch(const ConvGemmArgs& a, cudaStream_t st) {
   const int num_m_blocks = (R + BM - 1) / BM;
   const int num_n_blocks = (a.N + BN - 1) / BN;
   CUtensorMap tmA, tmB;
-  if (!make_tmap_bf16(&tmA, a.Ab, (uint64_t)R, (uint64_t)a.K, (uint64_t)a.K, BM))
+  const int planes = a.planes == 3 ? 3 : 1;
+  if (!make_tmap_bf16_3d(&tmA, a.Ab, (uint64_t)planes, (uint64_t)R, (uint64_t)a.K, (uint64_t)a.K, (uint64_t)R * a.K, BM))
     return fs2_fail_cuda(cudaErrorInvalidValue, "cuTensorMapEncodeTiled(A)");
-  if (!make_tmap_bf16(&tmB, a.Wb, (uint64_t)a.taps * a.N, (uint64_t)a.K, (uint64_t)a.K, BN))
+  if (!make_tmap_bf16(&tmB, a.Wb, (uint64_t)planes * a.taps * a.N, (uint64_t)a.K, (uint64_t)a.K, BN))
     return fs2_fail_cuda(cudaErrorInvalidValue, "cuTensorMapEncodeTiled(W)");
   static bool configured = false;
   const int smem = L::TOTAL + 1024;
@@ -358,6 +388,8 @@ int tc_conv_gemm_launch(const ConvGemmArgs& a, cudaStream_t st) {
   const int R = a.B * a.SA;
   if (R <= 0) return FS2_OK;
   if (!a.Ab || !a.Wb || a.K % 8 != 0 || a.N % 8 != 0) return fs2_fail_cuda(cudaErrorInvalidValue, "tc_conv_gemm: operands");
+  if ((a.planes != 0 && a.planes != 1 && a.planes != 3) || (a.out_planes != 0 && a.out_planes != 1 && a.out_planes != 3))
+    return fs2_fail_cuda(cudaErrorInvalidValue, "tc_conv_gemm: planes must be 1 or 3");
   const bool ln = (a.epi == EPI_RES_LN || a.epi == EPI_RELU_LN || a.epi == EPI_RELU_LN_DOT);
   if (ln && a.N != 256) return fs2_fail_cuda(cudaErrorInvalidValue, "tc_conv_gemm: LayerNorm epilogue needs N == 256");
   if (a.epi == EPI_QKV && a.N != 768) return fs2_fail_cuda(cudaErrorInvalidValue, "tc_conv_gemm: QKV epilogue needs N == 768");
