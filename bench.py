@@ -194,7 +194,9 @@ def run_b200_arm(args):
     steps, warmup = max(1, args.steps), max(3, args.warmup)
     sd = synthetic.make_state_dict(0)
     model = synthetic.build_module(sd, synthetic.STATS_NAN_BINS, device=dev)
-    model.set_precision("fp32", "bf16")   # fp32 encoder/predictors (bit-exact durations), bf16 tcgen05 decoder
+    # tcgen05 everywhere: bf16x3 (3-term split operands, fp32-faithful) for the encoder + variance predictors, whose
+    # outputs are rounded to integer durations / bucket indices; plain bf16 for the decoder, mel linear and PostNet
+    model.set_precision(args.enc, args.dec)
     synth = pkg.ShardedSynthesizer(model) if world > 1 else None
 
     speakers, texts, src_lens, L = make_batch(args.workload, world)
@@ -306,7 +308,8 @@ def run_b200_arm(args):
         line = {
             "metric": METRIC, "value": frames / (ms_res * 1e-3), "unit": UNIT, "n_gpus": world, "steps": steps,
             "warmup": warmup, "ms_per_step": ms_res, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "bf16 (decoder, tcgen05, fp32 accumulate) + f32 (encoder, variance predictors)", "data": "synthetic",
+            "dtype": f"{args.dec} (decoder, mel linear, PostNet) + {args.enc} (encoder, variance predictors); tcgen05, "
+                     "fp32 accumulation in TMEM", "data": "synthetic",
             "config": {"workload": args.workload, "description": WORKLOADS[args.workload][3], "batch_per_gpu": per,
                        "global_batch": per * world, "max_src_len": L, "T_max": T, "frames_per_step": frames,
                        "weights": "random init (numpy PCG64 seed 0), duration head biased to ~7.67 frames/phoneme",
@@ -350,6 +353,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--enc", default="bf16x3", choices=["fp32", "bf16x3", "bf16"], help="encoder + predictor arithmetic")
+    ap.add_argument("--dec", default="bf16", choices=["fp32", "bf16x3", "bf16"], help="decoder + PostNet arithmetic")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

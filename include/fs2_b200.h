@@ -99,6 +99,12 @@ int fs2_load_weights(fs2_handle* h, const fs2_weight_desc* descs, int32_t n);
  * mel_linear and PostNet.  Defaults: BF16X3 / BF16. */
 int fs2_set_precision(fs2_handle* h, int32_t encoder_prec, int32_t decoder_prec);
 
+/* Row packing of the internal activation layout.  keep_rows = padded rows kept after each utterance's valid rows:
+ * 2 (default) is the minimum that reproduces the reference's padded-grid convolutions exactly (SURVEY.md section 8(a)
+ * note 1); any value >= the longest utterance stores the reference's full padded [B, S_max] grid.  Results are
+ * identical for every legal value; only the amount of padded work changes. */
+int fs2_set_row_packing(fs2_handle* h, int32_t keep_rows);
+
 /* ---- the forward, in two stages because T = max(sum(durations)) is data dependent --- */
 /* replaces: fastspeech2_align.py:46-53 (src mask, TxtEncoder) + modules.py:116-135
  * (duration predictor, rounding) + the length bookkeeping of LengthRegulator.LR

@@ -51,6 +51,7 @@ struct fs2_handle {
   fs2_dims dims{};
   int device = 0;
   int prec_enc = FS2_PREC_BF16X3, prec_dec = FS2_PREC_BF16;
+  int halo_keep = 2;  // padded rows kept per utterance (2 = packed; >= max length = the reference's padded grid)
   bool loaded = false;
   std::string err;
   std::map<std::string, RawT> raw;
@@ -84,8 +85,9 @@ struct fs2_handle {
   }
   // stage-1 -> stage-2 state
   bool have_stage1 = false;
-  int st_B = 0, st_L = 0, st_LA = 0, st_Tmax = 0;
-  float* st_enc_out = nullptr;  // grid [B*LA, D]
+  int st_B = 0, st_L = 0, st_Tmax = 0;
+  float* st_enc_out = nullptr;  // encoder output, rows in the stage-1 layout
+  RowLayout st_lay1{};          // stage-1 (phoneme) row layout; its buffers live in the workspace
 
   int fail(int code, const std::string& m) {
     err = m;
@@ -284,12 +286,44 @@ cudaError_t make_shadow(const float* x, size_t n, int prec, bf16* xb, cudaStream
   return cudaSuccess;
 }
 
-ConvGemmArgs base_args(const GemmW& w, int B, int S, int SA, const int* lens) {
+// Device-resident ragged row layout (fs2_common.cuh) in workspace buffers named `name`.* ; lens32 = null -> every
+// utterance has S grid rows.  halo_keep: padded rows kept after the valid ones (>= S: the reference's padded grid).
+int make_layout(fs2_handle* h, const std::string& name, const int* lens32, int B, int S, int halo_keep, int halo_rows,
+                RowLayout* out, cudaStream_t st) {
+  if (B > 65535) return h->fail(FS2_ERR_UNSUPPORTED, "more than 65535 utterances in one call");
+  if (S > FS2_MAX_ROWS_PER_UTT) return h->fail(FS2_ERR_UNSUPPORTED, "more than 65535 rows per utterance");
+  const int R_cap = B * (S + halo_rows);
+  WS(int, off, name + ".off", (size_t)B + 1);
+  WS(int, ext, name + ".ext", (size_t)B);
+  WS(unsigned, rowmap, name + ".map", (size_t)R_cap);
+  HCHECK(rowops_build_layout(lens32, B, S, halo_keep, halo_rows, off, ext, rowmap, R_cap, st));
+  out->B = B; out->S = S; out->R_cap = R_cap; out->off = off; out->ext = ext; out->lens = lens32; out->rowmap = rowmap;
+  return FS2_OK;
+}
+
+// handle-less variant for the stand-alone operator entry points
+struct TmpLayout {
+  RowLayout lay{};
+  int *off = nullptr, *ext = nullptr;
+  unsigned* map = nullptr;
+  cudaError_t build(const int* lens32, int B, int S, int halo_keep, int halo_rows, cudaStream_t st) {
+    const int R_cap = B * (S + halo_rows);
+    cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&off), sizeof(int) * ((size_t)B + 1));
+    if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&ext), sizeof(int) * (size_t)B);
+    if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&map), sizeof(unsigned) * (size_t)(R_cap > 0 ? R_cap : 1));
+    if (e == cudaSuccess) e = rowops_build_layout(lens32, B, S, halo_keep, halo_rows, off, ext, map, R_cap, st);
+    lay = RowLayout{B, S, R_cap, off, ext, lens32, map};
+    return e;
+  }
+  ~TmpLayout() { cudaFree(off); cudaFree(ext); cudaFree(map); }
+};
+
+ConvGemmArgs base_args(const GemmW& w, const RowLayout& lay) {
   ConvGemmArgs a;
   memset(&a, 0, sizeof a);
   a.K = w.K; a.N = w.N; a.taps = w.taps;
   a.Wf = w.wf; a.Wb = w.wb; a.bias = w.bias;
-  a.B = B; a.S = S; a.SA = SA; a.lens = lens;
+  a.lay = lay;
   return a;
 }
 
@@ -308,12 +342,12 @@ int run_gemm(fs2_handle* h, int prec, const ConvGemmArgs& a, cudaStream_t st, co
   return rc;
 }
 
-// Layers.py:39-48 x n layers on grid-layout activations.  x (fp32) and, in bf16 mode, xb (its bf16 shadow) are
-// updated in place.  Returns through x/xb.
-int run_fft_stack(fs2_handle* h, std::vector<FftW>& Ls, int l0, int l1, int prec, float* x, bf16* xb, const int* lens,
-                  int B, int S, int SA, cudaStream_t st) {
+// Layers.py:39-48 x n layers on ragged-grid activations.  x (fp32) and, in tensor-core modes, xb (its bf16 / bf16x3
+// shadow) are updated in place.  Returns through x/xb.
+int run_fft_stack(fs2_handle* h, std::vector<FftW>& Ls, int l0, int l1, int prec, float* x, bf16* xb, const RowLayout& lay,
+                  cudaStream_t st) {
   const int D = h->dims.d_model, F = h->dims.d_ffn, H = h->dims.n_heads, dk = D / H;
-  const size_t R = (size_t)B * SA;
+  const size_t R = (size_t)lay.R_cap;
   const std::string tg = (&Ls == &h->enc) ? "enc." : "dec.";
   WS(float, y, "fft.y", R * D);
   if (prec == FS2_PREC_FP32) {
@@ -322,21 +356,21 @@ int run_fft_stack(fs2_handle* h, std::vector<FftW>& Ls, int l0, int l1, int prec
     WS(float, hid, "fft.hid", R * F);
     for (int l = l0; l < l1; ++l) {
       FftW& L = Ls[l];
-      ConvGemmArgs a = base_args(L.qkv, B, S, SA, lens);
+      ConvGemmArgs a = base_args(L.qkv, lay);
       a.A = x; a.epi = EPI_BIAS; a.mask_mode = MASK_GRID; a.out = qkv; a.ldo = 3 * D;
       RCHECK(run_gemm(h, prec, a, st, tg + "qkv"));
       {
         PROF(tg + "attn");
-        HCHECK(simt_attention_launch(qkv, 3 * D, 0, D, 2 * D, lens, B, S, SA, H, dk, att, D, st));
+        HCHECK(simt_attention_launch(qkv, 3 * D, 0, D, 2 * D, lay, H, dk, att, D, st));
       }
-      a = base_args(L.fc, B, S, SA, lens);
+      a = base_args(L.fc, lay);
       a.A = att; a.epi = EPI_RES_LN; a.mask_mode = MASK_LEN; a.residual = x; a.ln_g = L.ln1_g; a.ln_b = L.ln1_b;
       a.out = y; a.ldo = D;
       RCHECK(run_gemm(h, prec, a, st, tg + "fc_ln"));
-      a = base_args(L.w1, B, S, SA, lens);
+      a = base_args(L.w1, lay);
       a.A = y; a.epi = EPI_RELU; a.mask_mode = MASK_GRID; a.out = hid; a.ldo = F;
       RCHECK(run_gemm(h, prec, a, st, tg + "ffn_w1"));
-      a = base_args(L.w2, B, S, SA, lens);
+      a = base_args(L.w2, lay);
       a.A = hid; a.epi = EPI_RES_LN; a.mask_mode = MASK_LEN; a.residual = y; a.ln_g = L.ln2_g; a.ln_b = L.ln2_b;
       a.out = x; a.ldo = D;
       RCHECK(run_gemm(h, prec, a, st, tg + "ffn_w2_ln"));
@@ -352,22 +386,22 @@ int run_fft_stack(fs2_handle* h, std::vector<FftW>& Ls, int l0, int l1, int prec
     WS(bf16, hidb3, "fft.hidb3", 3 * R * F);
     for (int l = l0; l < l1; ++l) {
       FftW& L = Ls[l];
-      ConvGemmArgs a = base_args(L.qkv, B, S, SA, lens);
+      ConvGemmArgs a = base_args(L.qkv, lay);
       a.Ab = xb; a.epi = EPI_BIAS; a.mask_mode = MASK_GRID; a.out = qkv; a.ldo = 3 * D;
       RCHECK(run_gemm(h, prec, a, st, tg + "qkv"));
       {
         PROF(tg + "attn");
-        HCHECK(simt_attention_launch(qkv, 3 * D, 0, D, 2 * D, lens, B, S, SA, H, dk, att, D, st));
+        HCHECK(simt_attention_launch(qkv, 3 * D, 0, D, 2 * D, lay, H, dk, att, D, st));
         HCHECK(rowops_split3(att, (int64_t)(R * D), attb3, (int64_t)(R * D), st));
       }
-      a = base_args(L.fc, B, S, SA, lens);
+      a = base_args(L.fc, lay);
       a.Ab = attb3; a.epi = EPI_RES_LN; a.mask_mode = MASK_LEN; a.residual = x; a.ln_g = L.ln1_g; a.ln_b = L.ln1_b;
       a.out = y; a.ldo = D; a.out_b = yb3; a.ldob = D;
       RCHECK(run_gemm(h, prec, a, st, tg + "fc_ln"));
-      a = base_args(L.w1, B, S, SA, lens);
+      a = base_args(L.w1, lay);
       a.Ab = yb3; a.epi = EPI_RELU; a.mask_mode = MASK_GRID; a.out_b = hidb3; a.ldob = F;
       RCHECK(run_gemm(h, prec, a, st, tg + "ffn_w1"));
-      a = base_args(L.w2, B, S, SA, lens);
+      a = base_args(L.w2, lay);
       a.Ab = hidb3; a.epi = EPI_RES_LN; a.mask_mode = MASK_LEN; a.residual = y; a.ln_g = L.ln2_g; a.ln_b = L.ln2_b;
       a.out = x; a.ldo = D; a.out_b = xb; a.ldob = D;
       RCHECK(run_gemm(h, prec, a, st, tg + "ffn_w2_ln"));
@@ -375,31 +409,31 @@ int run_fft_stack(fs2_handle* h, std::vector<FftW>& Ls, int l0, int l1, int prec
     return FS2_OK;
   }
   // tcgen05 bf16 path
-  const int SAv = (SA + 7) & ~7;
+  const int Rv = (lay.R_cap + 7) & ~7;
   WS(bf16, yb, "fft.yb", R * D);
   WS(bf16, qb, "fft.qb", R * D);
   WS(bf16, kb, "fft.kb", R * D);
-  WS(bf16, vtb, "fft.vtb", (size_t)B * D * SAv);
+  WS(bf16, vtb, "fft.vtb", (size_t)D * Rv);
   WS(bf16, attb, "fft.attb", R * D);
   WS(bf16, hidb, "fft.hidb", R * F);
   for (int l = l0; l < l1; ++l) {
     FftW& L = Ls[l];
-    ConvGemmArgs a = base_args(L.qkv, B, S, SA, lens);
-    a.Ab = xb; a.epi = EPI_QKV; a.mask_mode = MASK_GRID; a.q_b = qb; a.k_b = kb; a.vt_b = vtb; a.SAv = SAv;
+    ConvGemmArgs a = base_args(L.qkv, lay);
+    a.Ab = xb; a.epi = EPI_QKV; a.mask_mode = MASK_GRID; a.q_b = qb; a.k_b = kb; a.vt_b = vtb; a.Rv = Rv;
     RCHECK(run_gemm(h, prec, a, st, tg + "qkv"));
     {
       PROF(tg + "attn");
-      int rc = tc_attention_launch(qb, kb, vtb, lens, B, S, SA, SAv, H, attb, st);
+      int rc = tc_attention_launch(qb, kb, vtb, lay, Rv, H, attb, st);
       if (rc != FS2_OK) { h->err = g_last_error; return rc; }
     }
-    a = base_args(L.fc, B, S, SA, lens);
+    a = base_args(L.fc, lay);
     a.Ab = attb; a.epi = EPI_RES_LN; a.mask_mode = MASK_LEN; a.residual = x; a.ln_g = L.ln1_g; a.ln_b = L.ln1_b;
     a.out = y; a.ldo = D; a.out_b = yb; a.ldob = D;
     RCHECK(run_gemm(h, prec, a, st, tg + "fc_ln"));
-    a = base_args(L.w1, B, S, SA, lens);
+    a = base_args(L.w1, lay);
     a.Ab = yb; a.epi = EPI_RELU; a.mask_mode = MASK_GRID; a.out_b = hidb; a.ldob = F;
     RCHECK(run_gemm(h, prec, a, st, tg + "ffn_w1"));
-    a = base_args(L.w2, B, S, SA, lens);
+    a = base_args(L.w2, lay);
     a.Ab = hidb; a.epi = EPI_RES_LN; a.mask_mode = MASK_LEN; a.residual = y; a.ln_g = L.ln2_g; a.ln_b = L.ln2_b;
     a.out = x; a.ldo = D; a.out_b = xb; a.ldob = D;
     RCHECK(run_gemm(h, prec, a, st, tg + "ffn_w2_ln"));
@@ -407,36 +441,44 @@ int run_fft_stack(fs2_handle* h, std::vector<FftW>& Ls, int l0, int l1, int prec
   return FS2_OK;
 }
 
-// modules.py:278-286 on the padded grid (halo-leak semantics, SURVEY.md section 8(a) note 1): out_user[B,S]
-int run_predictor(fs2_handle* h, PredW& P, int prec, const float* x, const bf16* xb, const int* lens, int B, int S,
-                  int SA, float* out_user, cudaStream_t st) {
+// modules.py:278-286 with the reference's padded-grid semantics (halo leak, SURVEY.md section 8(a) note 1): the layout
+// keeps the 2 padded rows that can reach a valid output.  out_user[B,S]; rows the layout does not carry are 0 (masked).
+int run_predictor(fs2_handle* h, PredW& P, int prec, const float* x, const bf16* xb, const RowLayout& lay,
+                  float* out_user, cudaStream_t st) {
   const int C = h->dims.vp_filter;
   const std::string tg = &P == &h->pred[0] ? "dur." : &P == &h->pred[1] ? "pitch." : "energy.";
-  const size_t R = (size_t)B * SA;
+  const size_t R = (size_t)lay.R_cap;
   WS(float, p1, "pred.h1", R * C);
   bf16* p1b = nullptr;
   if (prec != FS2_PREC_FP32) {
     WS(bf16, t, "pred.h1b", (prec == FS2_PREC_BF16X3 ? 3 : 1) * R * C);
     p1b = t;
   }
-  ConvGemmArgs a = base_args(P.c1, B, S, SA, lens);
+  HCHECK(cudaMemsetAsync(out_user, 0, sizeof(float) * (size_t)lay.B * lay.S, st));
+  ConvGemmArgs a = base_args(P.c1, lay);
   a.A = x; a.Ab = xb; a.epi = EPI_RELU_LN; a.mask_mode = MASK_GRID; a.ln_g = P.ln1_g; a.ln_b = P.ln1_b;
   a.out = prec == FS2_PREC_FP32 ? p1 : nullptr; a.ldo = C; a.out_b = p1b; a.ldob = C;
   RCHECK(run_gemm(h, prec, a, st, tg + "conv1"));
-  a = base_args(P.c2, B, S, SA, lens);
+  a = base_args(P.c2, lay);
   a.A = p1; a.Ab = p1b; a.epi = EPI_RELU_LN_DOT; a.mask_mode = MASK_LEN; a.ln_g = P.ln2_g; a.ln_b = P.ln2_b;
   a.dot_w = P.lin_w; a.dot_b = P.lin_b; a.out_user = out_user; a.ldu = 1;
   RCHECK(run_gemm(h, prec, a, st, tg + "conv2_dot"));
   return FS2_OK;
 }
 
-// fastspeech2_align.py:83-85: mel_linear, PostNet (BatchNorm folded), residual.  dec in grid layout.
-int run_mel_postnet(fs2_handle* h, int prec, const float* dec, const bf16* decb, int B, int T, int TA, float* mel,
+// fastspeech2_align.py:83-85: mel_linear, PostNet (BatchNorm folded), residual.  dec follows `lay` (possibly packed);
+// PostNet runs on the reference's full padded grid [B, T] because its padded rows are returned to the caller
+// (SURVEY.md a15): mel_linear scatters into that uniform grid and the rows the packed layout does not carry -- whose
+// decoder output is exactly zero -- are filled with the bias row.
+int run_mel_postnet(fs2_handle* h, int prec, const float* dec, const bf16* decb, const RowLayout& lay, float* mel,
                     float* mel_post, cudaStream_t st) {
   const int M = h->dims.n_mel, P = h->dims.pn_dim, NL = h->dims.pn_layers;
+  const int B = lay.B, T = lay.S, TA = T + FS2_HALO;
   const size_t R = (size_t)B * TA;
   const bool tc = prec != FS2_PREC_FP32;
   const size_t np = (size_t)planes_of(prec);
+  RowLayout pn;
+  RCHECK(make_layout(h, "pn.lay", nullptr, B, T, T, FS2_HALO, &pn, st));
   WS(float, melg, "pn.mel", R * M);
   bf16 *melb = nullptr, *pa_b = nullptr, *pb_b = nullptr;
   float *pa = nullptr, *pb = nullptr;
@@ -448,13 +490,17 @@ int run_mel_postnet(fs2_handle* h, int prec, const float* dec, const bf16* decb,
     WS(float, t1, "pn.a", R * P); pa = t1;
     WS(float, t2, "pn.b", R * P); pb = t2;
   }
-  ConvGemmArgs a = base_args(h->mel_linear, B, T, TA, nullptr);
-  a.A = dec; a.Ab = decb; a.epi = EPI_BIAS; a.mask_mode = MASK_GRID;
+  ConvGemmArgs a = base_args(h->mel_linear, lay);
+  a.A = dec; a.Ab = decb; a.epi = EPI_BIAS; a.mask_mode = MASK_GRID; a.dst_SA = TA;
   a.out = melg; a.ldo = M; a.out_b = melb; a.ldob = M; a.out_user = mel; a.ldu = M;
   RCHECK(run_gemm(h, prec, a, st, "mel_linear"));
+  {
+    PROF("rows.fill_padded");
+    HCHECK(rowops_fill_padded_rows(h->mel_linear.bias, M, lay, TA, melg, melb, (int)np, mel, st));
+  }
   const float* in_f = melg; const bf16* in_b = melb;
   for (int i = 0; i < NL; ++i) {
-    a = base_args(h->postnet[i], B, T, TA, nullptr);
+    a = base_args(h->postnet[i], pn);
     a.A = in_f; a.Ab = in_b; a.mask_mode = MASK_GRID;
     if (i < NL - 1) {
       a.epi = EPI_TANH;
@@ -544,6 +590,14 @@ int fs2_set_precision(fs2_handle* h, int32_t enc, int32_t dec) {
   return FS2_OK;
 }
 
+int fs2_set_row_packing(fs2_handle* h, int32_t keep_rows) {
+  if (!h) return FS2_ERR_INVALID;
+  if (keep_rows < 2) return h->fail(FS2_ERR_INVALID, "keep_rows must be >= 2 (the variance predictors' halo)");
+  h->halo_keep = keep_rows;
+  h->have_stage1 = false;
+  return FS2_OK;
+}
+
 int fs2_load_weights(fs2_handle* h, const fs2_weight_desc* descs, int32_t n) {
   if (!h || !descs || n <= 0) return h ? h->fail(FS2_ERR_INVALID, "null/empty weight list") : FS2_ERR_INVALID;
   HCHECK(cudaSetDevice(h->device));
@@ -628,15 +682,19 @@ int fs2_forward_stage1(fs2_handle* h, const int64_t* texts, const int64_t* src_l
     return h->fail(FS2_ERR_INVALID, "stage1: phoneme-level pitch/energy output pointer missing");
   HCHECK(cudaSetDevice(h->device));
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  const int D = d.d_model, LA = L + FS2_HALO;
-  const size_t R = (size_t)B * LA;
+  const int D = d.d_model;
   h->have_stage1 = false;
 
   WS(int, lens32, "s1.lens32", B);
-  WS(float, x, "s1.x", R * D);
   WS(int, cum, "s1.cum", (size_t)B * L);
   WS(int, mlens32, "s1.mel_lens32", B);
   WS(int, tmax_dev, "s1.tmax", 1);
+  HCHECK(rowops_lens_to_i32(src_lens, B, L, lens32, st));
+  // packed phoneme rows: valid rows + the 2 padded rows the duration predictor's convolutions can see (+ zero halo)
+  RowLayout lay;
+  RCHECK(make_layout(h, "s1.lay", lens32, B, L, h->halo_keep, FS2_HALO, &lay, st));
+  const size_t R = (size_t)lay.R_cap;
+  WS(float, x, "s1.x", R * D);
   bf16* xb = nullptr;
   if (h->prec_enc != FS2_PREC_FP32) {
     WS(bf16, t, "s1.xb", (size_t)planes_of(h->prec_enc) * R * D);
@@ -646,26 +704,25 @@ int fs2_forward_stage1(fs2_handle* h, const int64_t* texts, const int64_t* src_l
   RCHECK(position_table(h, 0, L, &pe, st));
   {
     PROF("rows.embed_pe");
-    HCHECK(rowops_lens_to_i32(src_lens, B, L, lens32, st));
     if (src_mask) HCHECK(rowops_mask(src_lens, nullptr, B, L, src_mask, st));
-    HCHECK(rowops_embed_pe(texts, raw_ptr(h, "txt_encoder.src_word_emb.weight"), pe, d.vocab, B, L, LA, D, x, nullptr, st));
-    HCHECK(make_shadow(x, R * D, h->prec_enc, xb, st));
+    HCHECK(rowops_embed_pe(texts, raw_ptr(h, "txt_encoder.src_word_emb.weight"), pe, d.vocab, lay, D, x, xb,
+                           planes_of(h->prec_enc), nullptr, st));
   }
-  RCHECK(run_fft_stack(h, h->enc, 0, d.n_enc_layers, h->prec_enc, x, xb, lens32, B, L, LA, st));
+  RCHECK(run_fft_stack(h, h->enc, 0, d.n_enc_layers, h->prec_enc, x, xb, lay, st));
   // modules.py:116 duration predictor on the encoder output
-  RCHECK(run_predictor(h, h->pred[0], h->prec_enc, x, xb, lens32, B, L, LA, log_d, st));
+  RCHECK(run_predictor(h, h->pred[0], h->prec_enc, x, xb, lay, log_d, st));
   // modules.py:117-126 phoneme-level variants
   if (d.pitch_phoneme_level) {
-    RCHECK(run_predictor(h, h->pred[1], h->prec_enc, x, xb, lens32, B, L, LA, pitch_ph, st));
+    RCHECK(run_predictor(h, h->pred[1], h->prec_enc, x, xb, lay, pitch_ph, st));
     HCHECK(rowops_variance_embed(pitch_ph, p_control, raw_ptr(h, "variance_adaptor.pitch_bins"), d.n_bins,
                                  raw_ptr(h, "variance_adaptor.pitch_embedding.weight"), nullptr, x, xb,
-                                 planes_of(h->prec_enc), B, L, LA, D, nullptr, st));
+                                 planes_of(h->prec_enc), lay, D, nullptr, st));
   }
   if (d.energy_phoneme_level) {
-    RCHECK(run_predictor(h, h->pred[2], h->prec_enc, x, xb, lens32, B, L, LA, energy_ph, st));
+    RCHECK(run_predictor(h, h->pred[2], h->prec_enc, x, xb, lay, energy_ph, st));
     HCHECK(rowops_variance_embed(energy_ph, e_control, raw_ptr(h, "variance_adaptor.energy_bins"), d.n_bins,
                                  raw_ptr(h, "variance_adaptor.energy_embedding.weight"), nullptr, x, xb,
-                                 planes_of(h->prec_enc), B, L, LA, D, nullptr, st));
+                                 planes_of(h->prec_enc), lay, D, nullptr, st));
   }
   // modules.py:132-135 + LengthRegulator bookkeeping
   {
@@ -678,8 +735,9 @@ int fs2_forward_stage1(fs2_handle* h, const int64_t* texts, const int64_t* src_l
   HCHECK(cudaStreamSynchronize(st));  // the one data-dependent size of the path
   *T_max_out = *h->host_tmax;
   h->have_stage1 = true;
-  h->st_B = B; h->st_L = L; h->st_LA = LA; h->st_Tmax = *h->host_tmax;
+  h->st_B = B; h->st_L = L; h->st_Tmax = *h->host_tmax;
   h->st_enc_out = x;
+  h->st_lay1 = lay;
   return FS2_OK;
 }
 
@@ -690,15 +748,20 @@ int fs2_forward_stage2(fs2_handle* h, int32_t T, float p_control, float e_contro
   if (T < h->st_Tmax) return h->fail(FS2_ERR_INVALID, "stage2: T smaller than the stage-1 maximum mel length");
   const fs2_dims& d = h->dims;
   if (T == 0) return FS2_OK;  // degenerate batch (all durations zero): nothing to write
+  if (T > FS2_MAX_ROWS_PER_UTT) return h->fail(FS2_ERR_UNSUPPORTED, "stage2: more than 65535 mel frames per utterance");
   if (!mel || !mel_post || (!d.pitch_phoneme_level && !pitch) || (!d.energy_phoneme_level && !energy))
     return h->fail(FS2_ERR_INVALID, "stage2: null output pointer");
   HCHECK(cudaSetDevice(h->device));
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  const int B = h->st_B, L = h->st_L, LA = h->st_LA, D = d.d_model, TA = T + FS2_HALO;
-  const size_t R = (size_t)B * TA;
+  const int B = h->st_B, L = h->st_L, D = d.d_model;
   const int* cum = reinterpret_cast<int*>(h->ws["s1.cum"].first);
   const int* mlens32 = reinterpret_cast<int*>(h->ws["s1.mel_lens32"].first);
+  const bool pitch_fl = !d.pitch_phoneme_level, energy_fl = !d.energy_phoneme_level;
 
+  // packed frame rows: valid frames + the 2 padded rows the pitch / energy predictors can see (+ zero halo)
+  RowLayout lay;
+  RCHECK(make_layout(h, "s2.lay", mlens32, B, T, h->halo_keep, FS2_HALO, &lay, st));
+  const size_t R = (size_t)lay.R_cap;
   WS(float, x, "s2.x", R * D);
   bf16* xb = nullptr;
   {
@@ -708,42 +771,38 @@ int fs2_forward_stage2(fs2_handle* h, int32_t T, float p_control, float e_contro
       xb = t;
     }
   }
+  // every producer of x writes the bf16 shadow in the precision of its NEXT consumer
+  const int first_prec = (pitch_fl || energy_fl) ? h->prec_enc : FS2_PREC_FP32;
   {
     PROF("rows.length_regulate");
     if (mel_mask) HCHECK(rowops_mask(nullptr, mlens32, B, T, mel_mask, st));
-    // modules.py:136 length regulator (hard), straight into the halo'ed grid
-    HCHECK(rowops_length_regulate(h->st_enc_out, LA * D, cum, B, L, D, T, TA, x, st));
+    // modules.py:136 length regulator (hard): gathers encoder rows (stage-1 layout) into frame rows (stage-2 layout)
+    HCHECK(rowops_length_regulate(h->st_enc_out, h->st_lay1.off, 0, cum, L, D, lay, x, xb, planes_of(first_prec), st));
   }
   const float* pe = nullptr;
   RCHECK(position_table(h, 1, T, &pe, st));
-  const bool pitch_fl = !d.pitch_phoneme_level, energy_fl = !d.energy_phoneme_level;
-  // every producer of x writes the bf16 shadow in the precision of its NEXT consumer
-  if (pitch_fl || energy_fl) {
-    PROF("rows.length_regulate");
-    HCHECK(make_shadow(x, R * D, h->prec_enc, xb, st));
-  }
   // modules.py:139-149 frame-level pitch then energy (energy sees x + pitch embedding)
   if (pitch_fl) {
-    RCHECK(run_predictor(h, h->pred[1], h->prec_enc, x, xb, mlens32, B, T, TA, pitch, st));
+    RCHECK(run_predictor(h, h->pred[1], h->prec_enc, x, xb, lay, pitch, st));
     PROF("rows.variance_embed");
     HCHECK(rowops_variance_embed(pitch, p_control, raw_ptr(h, "variance_adaptor.pitch_bins"), d.n_bins,
                                  raw_ptr(h, "variance_adaptor.pitch_embedding.weight"), energy_fl ? nullptr : pe, x, xb,
-                                 planes_of(energy_fl ? h->prec_enc : h->prec_dec), B, T, TA, D, nullptr, st));
+                                 planes_of(energy_fl ? h->prec_enc : h->prec_dec), lay, D, nullptr, st));
   }
   if (energy_fl) {
-    RCHECK(run_predictor(h, h->pred[2], h->prec_enc, x, xb, mlens32, B, T, TA, energy, st));
-    // fused: + energy embedding, + decoder positional encoding (Models.py:231-233), bf16 shadow for the decoder
+    RCHECK(run_predictor(h, h->pred[2], h->prec_enc, x, xb, lay, energy, st));
+    // fused: + energy embedding, + decoder positional encoding (Models.py:231-233), shadow for the decoder
     PROF("rows.variance_embed");
     HCHECK(rowops_variance_embed(energy, e_control, raw_ptr(h, "variance_adaptor.energy_bins"), d.n_bins,
                                  raw_ptr(h, "variance_adaptor.energy_embedding.weight"), pe, x, xb,
-                                 planes_of(h->prec_dec), B, T, TA, D, nullptr, st));
+                                 planes_of(h->prec_dec), lay, D, nullptr, st));
   }
   if (!pitch_fl && !energy_fl) {  // both phoneme-level: only the decoder's positional add remains
-    HCHECK(rowops_add_pe(x, nullptr, pe, B, T, TA, D, st));
+    HCHECK(rowops_add_pe(x, pe, lay, D, st));
     HCHECK(make_shadow(x, R * D, h->prec_dec, xb, st));
   }
-  RCHECK(run_fft_stack(h, h->dec, 0, d.n_dec_layers, h->prec_dec, x, xb, mlens32, B, T, TA, st));
-  RCHECK(run_mel_postnet(h, h->prec_dec, x, xb, B, T, TA, mel, mel_post, st));
+  RCHECK(run_fft_stack(h, h->dec, 0, d.n_dec_layers, h->prec_dec, x, xb, lay, st));
+  RCHECK(run_mel_postnet(h, h->prec_dec, x, xb, lay, mel, mel_post, st));
   return FS2_OK;
 }
 
@@ -814,8 +873,16 @@ int fs2_duration_scan(const float* dd, int32_t B, int32_t L, int32_t* cum, int64
 
 int fs2_length_regulate(const float* x, const int32_t* cum, int32_t B, int32_t L, int32_t D, int32_t T, float* out,
                         void* stream) {
-  if (!x || !cum || !out || B <= 0 || L <= 0 || D <= 0 || D % 4 || T < 0) { g_last_error = "bad argument"; return FS2_ERR_INVALID; }
-  FS2_CUDA_CHECK(rowops_length_regulate(x, L * D, cum, B, L, D, T, T, out, reinterpret_cast<cudaStream_t>(stream)));
+  if (!x || !cum || !out || B <= 0 || L <= 0 || D <= 0 || D % 4 || T < 0 || B > 65535 || T > FS2_MAX_ROWS_PER_UTT) {
+    g_last_error = "bad argument"; return FS2_ERR_INVALID; }
+  if (T == 0) return FS2_OK;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  // dense layouts on both sides: x [B,L,D] -> out [B,T,D], no halo rows
+  TmpLayout tl;
+  cudaError_t e = tl.build(nullptr, B, T, T, 0, st);
+  if (e == cudaSuccess) e = rowops_length_regulate(x, nullptr, L, cum, L, D, tl.lay, out, nullptr, 0, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  if (e != cudaSuccess) return fs2_fail_cuda(e, "fs2_length_regulate");
   return FS2_OK;
 }
 
@@ -848,8 +915,10 @@ int fs2_op_embed_pe(fs2_handle* h, const int64_t* texts, int32_t B, int32_t L, f
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const float* pe = nullptr;
   RCHECK(position_table(h, 0, L, &pe, st));
-  HCHECK(rowops_embed_pe(texts, raw_ptr(h, "txt_encoder.src_word_emb.weight"), pe, h->dims.vocab, B, L, L, h->dims.d_model,
-                         nullptr, out, st));
+  RowLayout lay;
+  RCHECK(make_layout(h, "op.lay", nullptr, B, L, L, 0, &lay, st));
+  HCHECK(rowops_embed_pe(texts, raw_ptr(h, "txt_encoder.src_word_emb.weight"), pe, h->dims.vocab, lay, h->dims.d_model,
+                         nullptr, nullptr, 0, out, st));
   return FS2_OK;
 }
 
@@ -862,17 +931,19 @@ int fs2_op_fft_stack(fs2_handle* h, int32_t stack, int32_t l0, int32_t l1, int32
     return h->fail(FS2_ERR_INVALID, "bad argument");
   HCHECK(cudaSetDevice(h->device));
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  const int D = h->dims.d_model, SA = S + FS2_HALO;
-  const size_t R = (size_t)B * SA;
+  const int D = h->dims.d_model;
   WS(int, lens32, "op.lens32", B);
+  HCHECK(rowops_lens_to_i32(lens, B, S, lens32, st));
+  RowLayout lay;
+  RCHECK(make_layout(h, "op.lay", lens32, B, S, h->halo_keep, FS2_HALO, &lay, st));
+  const size_t R = (size_t)lay.R_cap;
   WS(float, xg, "op.x", R * D);
   bf16* xb = nullptr;
   if (prec != FS2_PREC_FP32) { WS(bf16, t, "op.xb", (size_t)planes_of(prec) * R * D); xb = t; }
-  HCHECK(rowops_lens_to_i32(lens, B, S, lens32, st));
-  HCHECK(rowops_to_grid(x, B, S, SA, D, xg, D, 0, nullptr, st));
+  HCHECK(rowops_to_grid(x, lay, D, xg, D, 0, nullptr, st));
   HCHECK(make_shadow(xg, R * D, prec, xb, st));
-  RCHECK(run_fft_stack(h, Ls, l0, l1, prec, xg, xb, lens32, B, S, SA, st));
-  HCHECK(rowops_from_grid(xg, B, S, SA, D, out, st));
+  RCHECK(run_fft_stack(h, Ls, l0, l1, prec, xg, xb, lay, st));
+  HCHECK(rowops_from_grid(xg, lay, D, out, st));
   return FS2_OK;
 }
 
@@ -882,16 +953,18 @@ int fs2_op_variance_predictor(fs2_handle* h, int32_t which, const float* x, cons
   if (!x || !lens || !out || B <= 0 || S <= 0 || which < 0 || which > 2) return h->fail(FS2_ERR_INVALID, "bad argument");
   HCHECK(cudaSetDevice(h->device));
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  const int D = h->dims.d_model, SA = S + FS2_HALO;
-  const size_t R = (size_t)B * SA;
+  const int D = h->dims.d_model;
   WS(int, lens32, "op.lens32", B);
+  HCHECK(rowops_lens_to_i32(lens, B, S, lens32, st));
+  RowLayout lay;
+  RCHECK(make_layout(h, "op.lay", lens32, B, S, h->halo_keep, FS2_HALO, &lay, st));
+  const size_t R = (size_t)lay.R_cap;
   WS(float, xg, "op.x", R * D);
   bf16* xb = nullptr;
   if (h->prec_enc != FS2_PREC_FP32) { WS(bf16, t, "op.xb", (size_t)planes_of(h->prec_enc) * R * D); xb = t; }
-  HCHECK(rowops_lens_to_i32(lens, B, S, lens32, st));
-  HCHECK(rowops_to_grid(x, B, S, SA, D, xg, D, 0, nullptr, st));
+  HCHECK(rowops_to_grid(x, lay, D, xg, D, 0, nullptr, st));
   HCHECK(make_shadow(xg, R * D, h->prec_enc, xb, st));
-  return run_predictor(h, h->pred[which], h->prec_enc, xg, xb, lens32, B, S, SA, out, st);
+  return run_predictor(h, h->pred[which], h->prec_enc, xg, xb, lay, out, st);
 }
 
 int fs2_op_variance_embed(fs2_handle* h, int32_t which, float* pred, float control, float* x, int32_t B, int32_t S,
@@ -899,10 +972,13 @@ int fs2_op_variance_embed(fs2_handle* h, int32_t which, float* pred, float contr
   if (!h || !h->loaded) return FS2_ERR_STATE;
   if (!pred || !x || B <= 0 || S <= 0 || (which != 1 && which != 2)) return h->fail(FS2_ERR_INVALID, "bad argument");
   HCHECK(cudaSetDevice(h->device));
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const char* nm = which == 1 ? "pitch" : "energy";
+  RowLayout lay;   // dense user tensor: every row is a grid row, no halo
+  RCHECK(make_layout(h, "op.lay", nullptr, B, S, S, 0, &lay, st));
   HCHECK(rowops_variance_embed(pred, control, raw_ptr(h, std::string("variance_adaptor.") + nm + "_bins"), h->dims.n_bins,
                                raw_ptr(h, std::string("variance_adaptor.") + nm + "_embedding.weight"), nullptr, x, nullptr,
-                               0, B, S, S, h->dims.d_model, idx_out, reinterpret_cast<cudaStream_t>(stream)));
+                               0, lay, h->dims.d_model, idx_out, st));
   return FS2_OK;
 }
 
@@ -913,41 +989,45 @@ int fs2_op_mel_postnet(fs2_handle* h, int32_t prec, const float* dec, int32_t B,
     return h->fail(FS2_ERR_INVALID, "bad argument");
   HCHECK(cudaSetDevice(h->device));
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  const int D = h->dims.d_model, TA = T + FS2_HALO;
-  const size_t R = (size_t)B * TA;
+  const int D = h->dims.d_model;
+  RowLayout lay;   // all T rows of every utterance are given: the reference's padded grid
+  RCHECK(make_layout(h, "op.lay", nullptr, B, T, T, FS2_HALO, &lay, st));
+  const size_t R = (size_t)lay.R_cap;
   WS(float, xg, "op.x", R * D);
   bf16* xb = nullptr;
   if (prec != FS2_PREC_FP32) { WS(bf16, t, "op.xb", (size_t)planes_of(prec) * R * D); xb = t; }
-  HCHECK(rowops_to_grid(dec, B, T, TA, D, xg, D, 0, nullptr, st));
+  HCHECK(rowops_to_grid(dec, lay, D, xg, D, 0, nullptr, st));
   HCHECK(make_shadow(xg, R * D, prec, xb, st));
-  return run_mel_postnet(h, prec, xg, xb, B, T, TA, mel, mel_post, st);
+  return run_mel_postnet(h, prec, xg, xb, lay, mel, mel_post, st);
 }
 
 int fs2_op_conv_gemm(int32_t prec, const float* A, const float* W, const float* bias, int32_t B, int32_t S, int32_t K,
                      int32_t N, int32_t taps, int32_t act, float* out, void* stream) {
   if (!A || !W || !bias || !out || B <= 0 || S <= 0 || K <= 0 || N <= 0 || taps < 1 || taps > 2 * FS2_HALO + 1 ||
-      taps % 2 == 0 || K % 16 || N % 4 || act < 0 || act > 2 || prec < FS2_PREC_FP32 || prec > FS2_PREC_BF16X3) {
+      taps % 2 == 0 || K % 16 || N % 4 || act < 0 || act > 2 || prec < FS2_PREC_FP32 || prec > FS2_PREC_BF16X3 ||
+      B > 65535 || S > FS2_MAX_ROWS_PER_UTT) {
     g_last_error = "bad argument"; return FS2_ERR_INVALID; }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  const int SA = S + FS2_HALO;
-  const size_t R = (size_t)B * SA;
   float *Ag = nullptr, *Wf = nullptr, *Og = nullptr;
   bf16 *Ab = nullptr, *Wb = nullptr;
   int rc = FS2_OK;
   cudaError_t e = cudaSuccess;
+  TmpLayout tl;
   do {
+    if ((e = tl.build(nullptr, B, S, S, FS2_HALO, st)) != cudaSuccess) break;   // the padded grid itself
+    const size_t R = (size_t)tl.lay.R_cap;
     if ((e = cudaMalloc(reinterpret_cast<void**>(&Ag), sizeof(float) * R * K)) != cudaSuccess) break;
     if ((e = cudaMalloc(reinterpret_cast<void**>(&Ab), sizeof(bf16) * 3 * R * K)) != cudaSuccess) break;
     if ((e = cudaMalloc(reinterpret_cast<void**>(&Wf), sizeof(float) * (size_t)N * K * taps)) != cudaSuccess) break;
     if ((e = cudaMalloc(reinterpret_cast<void**>(&Wb), sizeof(bf16) * 3 * (size_t)N * K * taps)) != cudaSuccess) break;
     if ((e = cudaMalloc(reinterpret_cast<void**>(&Og), sizeof(float) * R * N)) != cudaSuccess) break;
-    if ((e = rowops_to_grid(A, B, S, SA, K, Ag, K, 0, nullptr, st)) != cudaSuccess) break;
+    if ((e = rowops_to_grid(A, tl.lay, K, Ag, K, 0, nullptr, st)) != cudaSuccess) break;
     if ((e = make_shadow(Ag, R * K, prec, Ab, st)) != cudaSuccess) break;
     if ((e = rowops_pack_weight(W, N, K, taps, nullptr, Wf, Wb, N, 0, st)) != cudaSuccess) break;
     ConvGemmArgs a;
     memset(&a, 0, sizeof a);
     a.A = Ag; a.Ab = Ab; a.K = K; a.Wf = Wf; a.Wb = Wb; a.bias = bias; a.N = N; a.taps = taps;
-    a.B = B; a.S = S; a.SA = SA; a.epi = act == 0 ? EPI_BIAS : act == 1 ? EPI_RELU : EPI_TANH; a.mask_mode = MASK_GRID;
+    a.lay = tl.lay; a.epi = act == 0 ? EPI_BIAS : act == 1 ? EPI_RELU : EPI_TANH; a.mask_mode = MASK_GRID;
     a.out = Og; a.ldo = N; a.out_user = out; a.ldu = N;
     rc = run_gemm(nullptr, prec, a, st);
     if (rc != FS2_OK) break;
@@ -960,42 +1040,48 @@ int fs2_op_conv_gemm(int32_t prec, const float* A, const float* W, const float* 
 
 int fs2_op_attention(int32_t prec, const float* q, const float* k, const float* v, const int64_t* lens, int32_t B,
                      int32_t S, int32_t H, int32_t dk, float* out, void* stream) {
-  if (!q || !k || !v || !lens || !out || B <= 0 || S <= 0 || H <= 0 || (dk != 64 && dk != 128)) {
+  if (!q || !k || !v || !lens || !out || B <= 0 || S <= 0 || H <= 0 || (dk != 64 && dk != 128) || B > 65535 ||
+      S > FS2_MAX_ROWS_PER_UTT) {
     g_last_error = "bad argument"; return FS2_ERR_INVALID; }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  const int D = H * dk, SA = S + FS2_HALO, SAv = (SA + 7) & ~7;
-  const size_t R = (size_t)B * SA;
+  const int D = H * dk;
   float *qkv = nullptr, *og = nullptr;
   bf16 *qb = nullptr, *kb = nullptr, *vb = nullptr, *vtb = nullptr, *ob = nullptr;
   int* lens32 = nullptr;
   int rc = FS2_OK;
   cudaError_t e = cudaSuccess;
+  TmpLayout tl;
   do {
     if ((e = cudaMalloc(reinterpret_cast<void**>(&lens32), sizeof(int) * B)) != cudaSuccess) break;
-    if ((e = cudaMalloc(reinterpret_cast<void**>(&og), sizeof(float) * R * D)) != cudaSuccess) break;
     if ((e = rowops_lens_to_i32(lens, B, S, lens32, st)) != cudaSuccess) break;
+    if ((e = tl.build(lens32, B, S, 2, FS2_HALO, st)) != cudaSuccess) break;   // packed rows, as on the product path
+    const size_t R = (size_t)tl.lay.R_cap;
+    const int Rv = (tl.lay.R_cap + 7) & ~7;
+    if ((e = cudaMalloc(reinterpret_cast<void**>(&og), sizeof(float) * R * D)) != cudaSuccess) break;
+    if ((e = cudaMemsetAsync(og, 0, sizeof(float) * R * D, st)) != cudaSuccess) break;
     if (prec == FS2_PREC_FP32) {
       if ((e = cudaMalloc(reinterpret_cast<void**>(&qkv), sizeof(float) * R * 3 * D)) != cudaSuccess) break;
-      if ((e = rowops_to_grid(q, B, S, SA, D, qkv, 3 * D, 0, nullptr, st)) != cudaSuccess) break;
-      if ((e = rowops_to_grid(k, B, S, SA, D, qkv, 3 * D, D, nullptr, st)) != cudaSuccess) break;
-      if ((e = rowops_to_grid(v, B, S, SA, D, qkv, 3 * D, 2 * D, nullptr, st)) != cudaSuccess) break;
-      if ((e = simt_attention_launch(qkv, 3 * D, 0, D, 2 * D, lens32, B, S, SA, H, dk, og, D, st)) != cudaSuccess) break;
+      if ((e = rowops_to_grid(q, tl.lay, D, qkv, 3 * D, 0, nullptr, st)) != cudaSuccess) break;
+      if ((e = rowops_to_grid(k, tl.lay, D, qkv, 3 * D, D, nullptr, st)) != cudaSuccess) break;
+      if ((e = rowops_to_grid(v, tl.lay, D, qkv, 3 * D, 2 * D, nullptr, st)) != cudaSuccess) break;
+      if ((e = simt_attention_launch(qkv, 3 * D, 0, D, 2 * D, tl.lay, H, dk, og, D, st)) != cudaSuccess) break;
     } else {
       if (D != 256 || dk != 128) { g_last_error = "tcgen05 attention is built for H*dk = 256, dk = 128"; rc = FS2_ERR_UNSUPPORTED; break; }
       if ((e = cudaMalloc(reinterpret_cast<void**>(&qb), sizeof(bf16) * R * D)) != cudaSuccess) break;
       if ((e = cudaMalloc(reinterpret_cast<void**>(&kb), sizeof(bf16) * R * D)) != cudaSuccess) break;
       if ((e = cudaMalloc(reinterpret_cast<void**>(&vb), sizeof(bf16) * R * D)) != cudaSuccess) break;
-      if ((e = cudaMalloc(reinterpret_cast<void**>(&vtb), sizeof(bf16) * (size_t)B * D * SAv)) != cudaSuccess) break;
+      if ((e = cudaMalloc(reinterpret_cast<void**>(&vtb), sizeof(bf16) * (size_t)D * Rv)) != cudaSuccess) break;
       if ((e = cudaMalloc(reinterpret_cast<void**>(&ob), sizeof(bf16) * R * D)) != cudaSuccess) break;
-      if ((e = rowops_to_grid(q, B, S, SA, D, nullptr, 0, 0, qb, st)) != cudaSuccess) break;
-      if ((e = rowops_to_grid(k, B, S, SA, D, nullptr, 0, 0, kb, st)) != cudaSuccess) break;
-      if ((e = rowops_to_grid(v, B, S, SA, D, nullptr, 0, 0, vb, st)) != cudaSuccess) break;
-      if ((e = rowops_transpose_v(vb, B, SA, SAv, D, vtb, st)) != cudaSuccess) break;
-      rc = tc_attention_launch(qb, kb, vtb, lens32, B, S, SA, SAv, H, ob, st);
+      if ((e = cudaMemsetAsync(ob, 0, sizeof(bf16) * R * D, st)) != cudaSuccess) break;
+      if ((e = rowops_to_grid(q, tl.lay, D, nullptr, 0, 0, qb, st)) != cudaSuccess) break;
+      if ((e = rowops_to_grid(k, tl.lay, D, nullptr, 0, 0, kb, st)) != cudaSuccess) break;
+      if ((e = rowops_to_grid(v, tl.lay, D, nullptr, 0, 0, vb, st)) != cudaSuccess) break;
+      if ((e = rowops_transpose_v(vb, tl.lay.R_cap, Rv, D, vtb, st)) != cudaSuccess) break;
+      rc = tc_attention_launch(qb, kb, vtb, tl.lay, Rv, H, ob, st);
       if (rc != FS2_OK) break;
       if ((e = rowops_bf16_to_f32(ob, (int64_t)(R * D), og, st)) != cudaSuccess) break;
     }
-    if ((e = rowops_from_grid(og, B, S, SA, D, out, st)) != cudaSuccess) break;
+    if ((e = rowops_from_grid(og, tl.lay, D, out, st)) != cudaSuccess) break;
     e = cudaStreamSynchronize(st);
   } while (0);
   cudaFree(qkv); cudaFree(og); cudaFree(qb); cudaFree(kb); cudaFree(vb); cudaFree(vtb); cudaFree(ob); cudaFree(lens32);

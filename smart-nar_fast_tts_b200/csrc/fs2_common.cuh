@@ -1,15 +1,26 @@
 // fs2_common.cuh -- shared definitions for the sm_100a FastSpeech2-align forward kernels.
 //
-// Row layout ("grid") used by every internal activation tensor
-// ------------------------------------------------------------
-// A reference tensor [B, S, C] is stored as R = B*SA rows of C channels, SA = S + FS2_HALO.
-// Row r = b*SA + p.  Rows with p >= S (the halo) are always ZERO.  Because every Conv1d on
-// the path has padding <= 4 (FFN k=9), a row-shifted read A[r + t - pad] that leaves
-// [0,S) of its utterance lands in a halo row (or outside the buffer, which loaders treat
-// as zero), which is exactly the zero padding Conv1d applies at the edge of the padded
-// [B,S] grid in the reference (SubLayers.py:73-85, modules.py:254-272, Layers.py:120-167).
-// So a convolution over the whole batch is ONE implicit GEMM over flat rows, tiles may
-// straddle utterances, and no per-utterance tile quantisation is paid.
+// Row layout ("ragged grid") used by every internal activation tensor
+// ------------------------------------------------------------------
+// A reference tensor [B, S, C] is stored as flat rows of C channels.  Utterance b owns rows
+// [off[b], off[b+1]): first ext[b] "grid" rows (position p = 0..ext[b]-1), then FS2_HALO rows that
+// are always ZERO.  Because every Conv1d on the path has padding <= 4 (FFN k=9), a row-shifted
+// read A[r + t - pad] that leaves the utterance's grid rows lands in a zero halo row (or outside
+// the buffer, which TMA / the loaders treat as zero) -- exactly the zero padding Conv1d applies
+// at the edge of the reference's padded [B,S] grid (SubLayers.py:73-85, modules.py:254-272,
+// Layers.py:120-167).  So a convolution over the whole batch is ONE implicit GEMM over flat rows,
+// tiles straddle utterances, and no per-utterance tile quantisation is paid.
+//
+// ext[b] = min(lens[b] + halo_keep, S):
+//   * halo_keep >= S ("uniform"): ext = S, the reference's padded grid itself (PostNet, whose
+//     padded rows are returned to the caller, and the raw conv test entry point);
+//   * halo_keep = 2 ("packed"): only the rows that can influence a valid output are stored.
+//     FFT blocks are exact on valid rows alone (keys masked, rows zeroed after each sub-layer);
+//     the two-layer k=3 variance predictors leak 2 padded rows into the last valid outputs
+//     (SURVEY.md section 8(a) note 1), hence the 2 kept rows; everything past them is masked in
+//     the reference as well.  Padding of a batch then costs 6 rows per utterance instead of
+//     (S_max - len) rows.
+// The layout lives in device memory (lens are device data; nothing is copied back to size it).
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
@@ -35,6 +46,18 @@ enum Fs2Mask : int {
   MASK_LEN = 1,   // rows p >= lens[b] -> 0 (FFT blocks: masked_fill after each sub-layer, Layers.py:43-46)
 };
 
+struct RowLayout {
+  int B;                   // utterances
+  int S;                   // rows per utterance of the user tensor [B,S,*]: user row = b*S + p
+  int R_cap;               // rows allocated = B*(S + FS2_HALO) (host-known upper bound of off[B])
+  const int* off;          // [B+1] device: first row of utterance b; off[B] = rows in use
+  const int* ext;          // [B] device: grid rows of utterance b
+  const int* lens;         // [B] device: valid rows (p < lens[b]); may be null where no length mask applies
+  const unsigned* rowmap;  // [R_cap] device: (b << 16) | p for grid rows, FS2_ROW_NONE for halo / unused rows
+};
+#define FS2_ROW_NONE 0xFFFFFFFFu
+#define FS2_MAX_ROWS_PER_UTT 65535
+
 struct ConvGemmArgs {
   // A operand: activations in grid layout, lda == K
   const float* A;
@@ -49,9 +72,9 @@ struct ConvGemmArgs {
   const bf16* Wb;   // [planes][taps][N][K]   (tcgen05 kernel; K-major B operand)
   const float* bias;
   int N, taps;
-  // grid
-  int B, S, SA;
-  const int* lens;  // [B] int32 (MASK_LEN, EPI_RELU_LN_DOT)
+  // rows
+  RowLayout lay;    // layout of A (and of out / out_b / residual unless dst_SA > 0)
+  int dst_SA;       // > 0: out / out_b rows are addressed b*dst_SA + p (uniform destination grid), grid rows only
   int epi, mask_mode;
   const float* residual;  // grid layout, ld == N
   const float* ln_g;
@@ -68,9 +91,23 @@ struct ConvGemmArgs {
   // EPI_QKV extras (tcgen05 path)
   bf16* q_b;   // [R, 256]
   bf16* k_b;   // [R, 256]
-  bf16* vt_b;  // [B*H*dk, SAv]  V transposed: row (b*H + h)*dk + d, column p
-  int SAv;
+  bf16* vt_b;  // [H*dk, Rv]  V transposed: row h*dk + d, column = flat row index r
+  int Rv;      // R_cap rounded up to 8 (16-byte row pitch for TMA)
 };
+
+// (b, p) of a flat row
+struct RowPos {
+  int b, p;
+  bool in_grid;
+};
+__device__ __forceinline__ RowPos row_pos(const RowLayout& lay, int r, int R) {
+  RowPos rp;
+  const unsigned code = (r < R) ? __ldg(lay.rowmap + r) : FS2_ROW_NONE;
+  rp.in_grid = code != FS2_ROW_NONE;
+  rp.b = rp.in_grid ? (int)(code >> 16) : 0;
+  rp.p = rp.in_grid ? (int)(code & 0xFFFFu) : 0;
+  return rp;
+}
 
 #define FS2_CUDA_CHECK(expr)                                  \
   do {                                                        \
@@ -82,32 +119,41 @@ struct ConvGemmArgs {
 int fs2_fail_cuda(cudaError_t e, const char* what);  // records message, returns FS2_ERR_CUDA
 
 cudaError_t simt_conv_gemm_launch(const ConvGemmArgs& a, cudaStream_t st);
-cudaError_t simt_attention_launch(const float* qkv, int ldqkv, int q_off, int k_off, int v_off, const int* lens, int B,
-                                  int S, int SA, int H, int dk, float* out, int ldo, cudaStream_t st);
+cudaError_t simt_attention_launch(const float* qkv, int ldqkv, int q_off, int k_off, int v_off, const RowLayout& lay,
+                                  int H, int dk, float* out, int ldo, cudaStream_t st);
 
 // tcgen05 path
 int tc_conv_gemm_launch(const ConvGemmArgs& a, cudaStream_t st);  // returns FS2_* code
-int tc_attention_launch(const bf16* q, const bf16* k, const bf16* vt, const int* lens, int B, int S, int SA, int SAv,
-                        int H, bf16* out_b, cudaStream_t st);
+int tc_attention_launch(const bf16* q, const bf16* k, const bf16* vt, const RowLayout& lay, int Rv, int H, bf16* out_b,
+                        cudaStream_t st);
 
 // row operators (fs2_rowops.cu)
-cudaError_t rowops_embed_pe(const int64_t* texts, const float* emb, const float* pe, int vocab, int B, int L, int SA,
-                            int D, float* out_grid, float* out_user, cudaStream_t st);
+// off/ext/rowmap of `lay` from lens32 (device; null = every utterance has S rows): ext = min(lens + halo_keep, S),
+// each utterance followed by halo_rows zero rows (FS2_HALO for GEMM operands, 0 for dense user tensors).
+cudaError_t rowops_build_layout(const int* lens32, int B, int S, int halo_keep, int halo_rows, int* off, int* ext,
+                                unsigned* rowmap, int R_cap, cudaStream_t st);
+cudaError_t rowops_embed_pe(const int64_t* texts, const float* emb, const float* pe, int vocab, const RowLayout& lay,
+                            int D, float* out_grid, bf16* out_b, int out_planes, float* out_user, cudaStream_t st);
 cudaError_t rowops_lens_to_i32(const int64_t* lens, int B, int cap, int* out, cudaStream_t st);
 cudaError_t rowops_mask(const int64_t* lens64, const int* lens32, int B, int max_len, uint8_t* mask, cudaStream_t st);
 cudaError_t rowops_round_durations(const float* log_d, int64_t n, float d_control, float* out, cudaStream_t st);
 cudaError_t rowops_duration_scan(const float* d, int B, int L, int* cum, int64_t* mel_lens, int* mel_lens32,
                                  int* tmax_dev, cudaStream_t st);
-cudaError_t rowops_length_regulate(const float* x, int x_row_stride_utt, const int* cum, int B, int L, int D, int T,
-                                   int out_SA, float* out, cudaStream_t st);
+// x rows of utterance b start at src_off[b] (device) or b*src_stride when src_off is null; out rows follow `lay`
+cudaError_t rowops_length_regulate(const float* x, const int* src_off, int src_stride, const int* cum, int L, int D,
+                                   const RowLayout& lay, float* out, bf16* out_b, int out_planes, cudaStream_t st);
 cudaError_t rowops_variance_embed(float* pred, float control, const float* bins, int n_bins, const float* emb,
-                                  const float* pe, float* x, bf16* xb, int xb_planes, int B, int S, int SA, int D,
+                                  const float* pe, float* x, bf16* xb, int xb_planes, const RowLayout& lay, int D,
                                   int* idx_out, cudaStream_t st);
+// rows p in [ext[b], S) of a uniform destination grid (dst_SA rows per utterance) <- bias row (mel_linear of a zero
+// decoder row), halo rows p in [S, dst_SA) <- 0; also the user tensor [B,S,N]
+cudaError_t rowops_fill_padded_rows(const float* bias, int N, const RowLayout& lay, int dst_SA, float* out_grid,
+                                    bf16* out_b, int out_planes, float* out_user, cudaStream_t st);
 cudaError_t rowops_gaussian_upsample(const float* x, const float* d, int B, int L, int D, int T, int T_w, float* out,
                                      float* s, float* w, cudaStream_t st);
-cudaError_t rowops_to_grid(const float* x_user, int B, int S, int SA, int C, float* out, int ldo, int col_off,
+cudaError_t rowops_to_grid(const float* x_user, const RowLayout& lay, int C, float* out, int ldo, int col_off,
                            bf16* out_b, cudaStream_t st);
-cudaError_t rowops_from_grid(const float* x_grid, int B, int S, int SA, int C, float* out_user, cudaStream_t st);
+cudaError_t rowops_from_grid(const float* x_grid, const RowLayout& lay, int C, float* out_user, cudaStream_t st);
 // dst_b: [3][taps][n_total][K] -- plane 0 doubles as the plain bf16 weight, planes 1..2 are the split residuals
 cudaError_t rowops_pack_weight(const float* src, int N, int K, int taps, const float* scale, float* dst_f,
                                bf16* dst_b, int n_total, int n_off, cudaStream_t st);
@@ -117,8 +163,8 @@ cudaError_t rowops_bn_fold(const float* conv_bias, const float* g, const float* 
                            const float* var, int n, float eps, float* scale_out, float* bias_out, cudaStream_t st);
 cudaError_t rowops_f32_to_bf16(const float* src, int64_t n, bf16* dst, cudaStream_t st);
 cudaError_t rowops_bf16_to_f32(const bf16* src, int64_t n, float* dst, cudaStream_t st);
-cudaError_t rowops_transpose_v(const bf16* v, int B, int SA, int SAv, int D, bf16* vt, cudaStream_t st);
-cudaError_t rowops_add_pe(float* x, bf16* xb, const float* pe, int B, int S, int SA, int D, cudaStream_t st);
+cudaError_t rowops_transpose_v(const bf16* v, int R, int Rv, int D, bf16* vt, cudaStream_t st);
+cudaError_t rowops_add_pe(float* x, const float* pe, const RowLayout& lay, int D, cudaStream_t st);
 cudaError_t rowops_fill_zero(void* p, size_t bytes, cudaStream_t st);
 
 extern long long g_fs2_launches;  // kernels launched (incremented by every launcher)

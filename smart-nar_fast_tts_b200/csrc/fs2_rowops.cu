@@ -39,27 +39,95 @@ __device__ __forceinline__ void store_planes4(bf16* dst, size_t plane_elems, int
 
 
 // ---------------------------------------------------------------------------------------------
-// transformer/Models.py:82-91  out[b,p,:] = src_word_emb[texts[b,p]] + PE[p]   (all p < L, incl. PAD ids)
-// one warp per row; D/4 float4 per row
+// Ragged-grid layout (fs2_common.cuh): ext[b] = min(lens[b] + halo_keep, S); off = exclusive scan of ext + FS2_HALO.
+// One CTA, chunks of 1024 utterances, block-wide scan by warp shuffles.
+__global__ void __launch_bounds__(1024) build_layout_kernel(const int* __restrict__ lens, int B, int S, int halo_keep,
+                                                            int halo_rows, int* __restrict__ off, int* __restrict__ ext) {
+  __shared__ int warp_tot[32];
+  __shared__ int carry_s;
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  if (tid == 0) carry_s = 0;
+  __syncthreads();
+  for (int base = 0; base < B; base += 1024) {
+    const int b = base + tid;
+    int e = 0, v = 0;
+    if (b < B) {
+      const long long want = lens ? (long long)lens[b] + halo_keep : (long long)S;
+      e = (int)(want < S ? want : S);
+      if (e < 0) e = 0;
+      ext[b] = e;
+      v = e + halo_rows;
+    }
+    int x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int y = __shfl_up_sync(0xffffffffu, x, o);
+      if (lane >= o) x += y;
+    }
+    if (lane == 31) warp_tot[w] = x;
+    __syncthreads();
+    if (w == 0) {
+      int t = warp_tot[lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int y = __shfl_up_sync(0xffffffffu, t, o);
+        if (lane >= o) t += y;
+      }
+      warp_tot[lane] = t;
+    }
+    __syncthreads();
+    const int incl = carry_s + x + (w > 0 ? warp_tot[w - 1] : 0);
+    if (b < B) off[b] = incl - v;
+    __syncthreads();
+    if (tid == 1023) carry_s = incl;
+    __syncthreads();
+  }
+  if (tid == 0) off[B] = carry_s;
+}
+__global__ void fill_rowmap_kernel(const int* __restrict__ off, const int* __restrict__ ext, int B, int R_cap,
+                                   unsigned* __restrict__ rowmap) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= R_cap) return;
+  unsigned code = FS2_ROW_NONE;
+  if (r < off[B]) {
+    int lo = 0, hi = B - 1;  // last b with off[b] <= r
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (off[mid] <= r) lo = mid; else hi = mid - 1;
+    }
+    const int p = r - off[lo];
+    if (p < ext[lo]) code = ((unsigned)lo << 16) | (unsigned)p;
+  }
+  rowmap[r] = code;
+}
+
+// transformer/Models.py:82-91  out[b,p,:] = src_word_emb[texts[b,p]] + PE[p]   (all grid rows, incl. PAD ids)
+// one warp per flat row; D/4 float4 per row; optional bf16 / bf16x3 shadow for the first GEMM
 __global__ void embed_pe_kernel(const int64_t* __restrict__ texts, const float* __restrict__ emb,
-                                const float* __restrict__ pe, int vocab, int B, int L, int SA, int D,
-                                float* __restrict__ out_grid, float* __restrict__ out_user) {
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (warp >= B * SA) return;
-  const int b = warp / SA, p = warp - b * SA;
+                                const float* __restrict__ pe, int vocab, const RowLayout lay, int D,
+                                float* __restrict__ out_grid, bf16* __restrict__ out_b, int out_planes,
+                                float* __restrict__ out_user) {
+  const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  const int R = __ldg(lay.off + lay.B);
+  if (r >= R) return;
+  const RowPos rp = row_pos(lay, r, R);
   const int nv = D >> 2;
-  if (p >= L) {  // halo rows stay zero
-    if (out_grid)
-      for (int c = lane; c < nv; c += 32) st4(out_grid + (size_t)warp * D + c * 4, make_float4(0.f, 0.f, 0.f, 0.f));
+  const size_t plane = (size_t)lay.R_cap * D;
+  if (!rp.in_grid) {  // halo rows stay zero
+    for (int c = lane; c < nv; c += 32) {
+      if (out_grid) st4(out_grid + (size_t)r * D + c * 4, make_float4(0.f, 0.f, 0.f, 0.f));
+      if (out_b && out_planes > 0) store_planes4(out_b + (size_t)r * D + c * 4, plane, out_planes, make_float4(0.f, 0.f, 0.f, 0.f));
+    }
     return;
   }
-  long long id = texts[(size_t)b * L + p];
+  long long id = texts[(size_t)rp.b * lay.S + rp.p];
   id = id < 0 ? 0 : (id >= vocab ? vocab - 1 : id);  // the reference would raise; clamp instead of faulting
   for (int c = lane; c < nv; c += 32) {
-    const float4 e = ld4(emb + (size_t)id * D + c * 4), q = ld4(pe + (size_t)p * D + c * 4);
+    const float4 e = ld4(emb + (size_t)id * D + c * 4), q = ld4(pe + (size_t)rp.p * D + c * 4);
     const float4 v = make_float4(e.x + q.x, e.y + q.y, e.z + q.z, e.w + q.w);
-    if (out_grid) st4(out_grid + (size_t)warp * D + c * 4, v);
-    if (out_user) st4(out_user + ((size_t)b * L + p) * D + c * 4, v);
+    if (out_grid) st4(out_grid + (size_t)r * D + c * 4, v);
+    if (out_b && out_planes > 0) store_planes4(out_b + (size_t)r * D + c * 4, plane, out_planes, v);
+    if (out_user) st4(out_user + ((size_t)rp.b * lay.S + rp.p) * D + c * 4, v);
   }
 }
 
@@ -143,34 +211,44 @@ __global__ void __launch_bounds__(1024) duration_scan_kernel(const float* __rest
 }
 
 // model/modules.py:220-226 + utils/tools.py:288-306: frame t of utterance b copies phoneme row i with
-// cum[i-1] <= t < cum[i]; frames >= mel_len and halo rows are zero.  One warp per output row, the
-// utterance's cumulative table staged in shared memory, binary search per row, 16-byte row copy.
-__global__ void __launch_bounds__(256) length_regulate_kernel(const float* __restrict__ x, int x_utt_stride,
-                                                              const int* __restrict__ cum, int L, int D, int T,
-                                                              int out_SA, float* __restrict__ out) {
+// cum[i-1] <= t < cum[i]; frames >= mel_len (kept padded rows and halo) are zero.  One warp per output row, the
+// utterance's cumulative table staged in shared memory, binary search per row, 16-byte row copy (+ bf16 shadow).
+__global__ void __launch_bounds__(256) length_regulate_kernel(const float* __restrict__ x, const int* __restrict__ src_off,
+                                                              int src_stride, const int* __restrict__ cum, int L, int D,
+                                                              const RowLayout lay, float* __restrict__ out,
+                                                              bf16* __restrict__ out_b, int out_planes) {
   extern __shared__ int cum_s[];
   const int b = blockIdx.y;
+  const int rows_b = __ldg(lay.off + b + 1) - __ldg(lay.off + b);   // ext + halo
+  const int rows_per_cta = (blockDim.x >> 5) * 8;
+  if ((int)blockIdx.x * rows_per_cta >= rows_b) return;
   for (int i = threadIdx.x; i < L; i += blockDim.x) cum_s[i] = cum[(size_t)b * L + i];
   __syncthreads();
   const int total = L > 0 ? cum_s[L - 1] : 0;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const int rows_per_cta = (blockDim.x >> 5) * 8;
   const int nv = D >> 2;
+  const size_t plane = (size_t)lay.R_cap * D;
+  const size_t row0 = (size_t)__ldg(lay.off + b);
+  const size_t src0 = src_off ? (size_t)__ldg(src_off + b) : (size_t)b * src_stride;
   for (int k = 0; k < 8; ++k) {
     const int t = blockIdx.x * rows_per_cta + k * (blockDim.x >> 5) + w;
-    if (t >= out_SA) continue;
-    float* dst = out + ((size_t)b * out_SA + t) * D;
-    if (t >= total || t >= T) {
-      for (int c = lane; c < nv; c += 32) st4(dst + c * 4, make_float4(0.f, 0.f, 0.f, 0.f));
-      continue;
+    if (t >= rows_b) continue;
+    float* dst = out + (row0 + t) * D;
+    bf16* dstb = out_b ? out_b + (row0 + t) * D : nullptr;
+    const float* src = nullptr;
+    if (t < total && t < lay.S) {
+      int lo = 0, hi = L - 1;  // first i with cum[i] > t
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (cum_s[mid] > t) hi = mid; else lo = mid + 1;
+      }
+      src = x + (src0 + lo) * D;
     }
-    int lo = 0, hi = L - 1;  // first i with cum[i] > t
-    while (lo < hi) {
-      const int mid = (lo + hi) >> 1;
-      if (cum_s[mid] > t) hi = mid; else lo = mid + 1;
+    for (int c = lane; c < nv; c += 32) {
+      const float4 v = src ? ld4(src + c * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      st4(dst + c * 4, v);
+      if (dstb && out_planes > 0) store_planes4(dstb + c * 4, plane, out_planes, v);
     }
-    const float* src = x + (size_t)b * x_utt_stride + (size_t)lo * D;
-    for (int c = lane; c < nv; c += 32) st4(dst + c * 4, ld4(src + c * 4));
   }
 }
 
@@ -179,12 +257,15 @@ __global__ void __launch_bounds__(256) length_regulate_kernel(const float* __res
 // torch.bucketize(right=False) lower bound, incl. its behaviour on NaN boundaries (every compare false -> n_bins-1).
 __global__ void variance_embed_kernel(float* __restrict__ pred, float control, const float* __restrict__ bins,
                                       int n_bins, const float* __restrict__ emb, const float* __restrict__ pe,
-                                      float* __restrict__ x, bf16* __restrict__ xb, int xb_planes, int B, int S, int SA,
+                                      float* __restrict__ x, bf16* __restrict__ xb, int xb_planes, const RowLayout lay,
                                       int D, int* __restrict__ idx_out) {
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (warp >= B * S) return;
-  const int b = warp / S, p = warp - b * S;
-  const float v = pred[warp] * control;
+  const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  const int R = __ldg(lay.off + lay.B);
+  if (r >= R) return;
+  const RowPos rp = row_pos(lay, r, R);
+  if (!rp.in_grid) return;   // halo rows stay zero
+  const size_t u = (size_t)rp.b * lay.S + rp.p;
+  const float v = pred[u] * control;
   int start = 0, end = n_bins - 1;  // boundaries array has n_bins-1 entries
   while (start < end) {
     const int mid = start + ((end - start) >> 1);
@@ -192,21 +273,42 @@ __global__ void variance_embed_kernel(float* __restrict__ pred, float control, c
     if (!(mv >= v)) start = mid + 1; else end = mid;
   }
   if (lane == 0) {
-    pred[warp] = v;
-    if (idx_out) idx_out[warp] = start;
+    pred[u] = v;
+    if (idx_out) idx_out[u] = start;
   }
-  const size_t row = (size_t)b * SA + p;
+  const size_t row = (size_t)r;
   const int nv = D >> 2;
   for (int c = lane; c < nv; c += 32) {
     float4 a = *reinterpret_cast<const float4*>(x + row * D + c * 4);
     const float4 e = ld4(emb + (size_t)start * D + c * 4);
     a.x += e.x; a.y += e.y; a.z += e.z; a.w += e.w;
     if (pe) {
-      const float4 q = ld4(pe + (size_t)p * D + c * 4);
+      const float4 q = ld4(pe + (size_t)rp.p * D + c * 4);
       a.x += q.x; a.y += q.y; a.z += q.z; a.w += q.w;
     }
     st4(x + row * D + c * 4, a);
-    if (xb && xb_planes > 0) store_planes4(xb + row * D + c * 4, (size_t)B * SA * D, xb_planes, a);
+    if (xb && xb_planes > 0) store_planes4(xb + row * D + c * 4, (size_t)lay.R_cap * D, xb_planes, a);
+  }
+}
+
+// Rows of a uniform destination grid that the packed source layout does not carry: padded rows p in [ext[b], S) get
+// the bias row (what mel_linear makes of a zero decoder row, fastspeech2_align.py:83), halo rows [S, dst_SA) get zero.
+__global__ void __launch_bounds__(256) fill_padded_rows_kernel(const float* __restrict__ bias, int N, const RowLayout lay,
+                                                               int dst_SA, float* __restrict__ out_grid,
+                                                               bf16* __restrict__ out_b, int out_planes,
+                                                               float* __restrict__ out_user) {
+  const int b = blockIdx.y;
+  const int e = __ldg(lay.ext + b);
+  const int p = e + blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (p >= dst_SA) return;
+  const int lane = threadIdx.x & 31, nv = N >> 2;
+  const size_t g = (size_t)b * dst_SA + p;
+  const size_t plane = (size_t)lay.B * dst_SA * N;
+  for (int c = lane; c < nv; c += 32) {
+    const float4 v = p < lay.S ? ld4(bias + c * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    if (out_grid) st4(out_grid + g * N + c * 4, v);
+    if (out_b && out_planes > 0) store_planes4(out_b + g * N + c * 4, plane, out_planes, v);
+    if (out_user && p < lay.S) st4(out_user + ((size_t)b * lay.S + p) * N + c * 4, v);
   }
 }
 
@@ -285,34 +387,30 @@ __global__ void __launch_bounds__(256) gaussian_upsample_kernel(const float* __r
   }
 }
 
-// dense user layout [B,S,C] <-> halo'ed grid layout [B*SA, C]
-__global__ void to_grid_kernel(const float* __restrict__ xu, int B, int S, int SA, int C, float* __restrict__ out,
+// dense user layout [B,S,C] <-> ragged grid layout (test / per-operator entry points)
+__global__ void to_grid_kernel(const float* __restrict__ xu, const RowLayout lay, int C, float* __restrict__ out,
                                int ldo, int col_off, bf16* __restrict__ out_b) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;  // one float4 per thread
   const int nv = C >> 2;
-  if (i >= (size_t)B * SA * nv) return;
+  if (i >= (size_t)lay.R_cap * nv) return;
   const size_t row = i / nv;
   const int c = (int)(i - row * nv);
-  const int b = (int)(row / SA), p = (int)(row - (size_t)b * SA);
+  const RowPos rp = row_pos(lay, (int)row, __ldg(lay.off + lay.B));
   float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (p < S) v = ld4(xu + ((size_t)b * S + p) * C + c * 4);
+  if (rp.in_grid) v = ld4(xu + ((size_t)rp.b * lay.S + rp.p) * C + c * 4);
   if (out) st4(out + row * ldo + col_off + c * 4, v);
-  if (out_b) {
-    __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
-    uint2 pk;
-    pk.x = *reinterpret_cast<uint32_t*>(&lo);
-    pk.y = *reinterpret_cast<uint32_t*>(&hi);
-    *reinterpret_cast<uint2*>(out_b + row * C + c * 4) = pk;
-  }
+  if (out_b) *reinterpret_cast<uint2*>(out_b + row * C + c * 4) = make_uint2(pack2(v.x, v.y), pack2(v.z, v.w));
 }
-__global__ void from_grid_kernel(const float* __restrict__ xg, int B, int S, int SA, int C, float* __restrict__ out) {
+__global__ void from_grid_kernel(const float* __restrict__ xg, const RowLayout lay, int C, float* __restrict__ out) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int nv = C >> 2;
-  if (i >= (size_t)B * S * nv) return;
+  if (i >= (size_t)lay.B * lay.S * nv) return;
   const size_t row = i / nv;
   const int c = (int)(i - row * nv);
-  const int b = (int)(row / S), p = (int)(row - (size_t)b * S);
-  st4(out + row * C + c * 4, ld4(xg + ((size_t)b * SA + p) * C + c * 4));
+  const int b = (int)(row / lay.S), p = (int)(row - (size_t)b * lay.S);
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (p < __ldg(lay.ext + b)) v = ld4(xg + ((size_t)__ldg(lay.off + b) + p) * C + c * 4);
+  st4(out + row * C + c * 4, v);
 }
 
 // torch Conv1d / Linear weight [N][K][taps] -> fp32 [taps][K][n_total] (columns n_off..) and/or
@@ -365,38 +463,28 @@ __global__ void bf16_to_f32_kernel(const bf16* __restrict__ src, int64_t n, floa
   if (i < n) dst[i] = __bfloat162float(src[i]);
 }
 
-// V [B*SA, D] bf16 (grid layout) -> V^T [B*D, SAv]: row b*D + c, column p (columns >= SA zero).  Test helper for the
-// tcgen05 attention entry point; on the product path the QKV GEMM epilogue writes V^T directly.
-__global__ void transpose_v_kernel(const bf16* __restrict__ v, int B, int SA, int SAv, int D, bf16* __restrict__ vt) {
+// V [R, D] bf16 (flat rows) -> V^T [D, Rv]: row c, column r (columns >= R zero).  Test helper for the tcgen05
+// attention entry point; on the product path the QKV GEMM epilogue writes V^T directly.
+__global__ void transpose_v_kernel(const bf16* __restrict__ v, int R, int Rv, int D, bf16* __restrict__ vt) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= (size_t)B * D * SAv) return;
-  const int p = (int)(i % SAv);
-  const size_t row = i / SAv;
-  const int c = (int)(row % D), b = (int)(row / D);
-  vt[i] = p < SA ? v[((size_t)b * SA + p) * D + c] : __float2bfloat16_rn(0.f);
+  if (i >= (size_t)D * Rv) return;
+  const int r = (int)(i % Rv), c = (int)(i / Rv);
+  vt[i] = r < R ? v[(size_t)r * D + c] : __float2bfloat16_rn(0.f);
 }
 
-// Models.py:231-233 alone: x[b,p,:] += pe[p,:] for p < S (+ bf16 shadow); used when no variance embedding is frame-level
-__global__ void add_pe_kernel(float* __restrict__ x, bf16* __restrict__ xb, const float* __restrict__ pe, int B, int S,
-                              int SA, int D) {
+// Models.py:231-233 alone: x[b,p,:] += pe[p,:] on grid rows; used when no variance embedding is frame-level
+__global__ void add_pe_kernel(float* __restrict__ x, const float* __restrict__ pe, const RowLayout lay, int D) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int nv = D >> 2;
-  if (i >= (size_t)B * S * nv) return;
-  const size_t rowu = i / nv;
-  const int c = (int)(i - rowu * nv);
-  const int b = (int)(rowu / S), p = (int)(rowu - (size_t)b * S);
-  const size_t row = (size_t)b * SA + p;
+  if (i >= (size_t)lay.R_cap * nv) return;
+  const size_t row = i / nv;
+  const int c = (int)(i - row * nv);
+  const RowPos rp = row_pos(lay, (int)row, __ldg(lay.off + lay.B));
+  if (!rp.in_grid) return;
   float4 a = *reinterpret_cast<const float4*>(x + row * D + c * 4);
-  const float4 q = ld4(pe + (size_t)p * D + c * 4);
+  const float4 q = ld4(pe + (size_t)rp.p * D + c * 4);
   a.x += q.x; a.y += q.y; a.z += q.z; a.w += q.w;
   st4(x + row * D + c * 4, a);
-  if (xb) {
-    __nv_bfloat162 lo = __floats2bfloat162_rn(a.x, a.y), hi = __floats2bfloat162_rn(a.z, a.w);
-    uint2 pk;
-    pk.x = *reinterpret_cast<uint32_t*>(&lo);
-    pk.y = *reinterpret_cast<uint32_t*>(&hi);
-    *reinterpret_cast<uint2*>(xb + row * D + c * 4) = pk;
-  }
 }
 
 inline unsigned blocks_for(size_t n, int per) { return (unsigned)((n + per - 1) / per); }
@@ -405,10 +493,20 @@ inline unsigned blocks_for(size_t n, int per) { return (unsigned)((n + per - 1) 
 
 #define LAUNCHED() (++g_fs2_launches, cudaGetLastError())
 
-cudaError_t rowops_embed_pe(const int64_t* texts, const float* emb, const float* pe, int vocab, int B, int L, int SA,
-                            int D, float* out_grid, float* out_user, cudaStream_t st) {
-  if (B * SA <= 0) return cudaSuccess;
-  embed_pe_kernel<<<blocks_for((size_t)B * SA, 8), 256, 0, st>>>(texts, emb, pe, vocab, B, L, SA, D, out_grid, out_user);
+cudaError_t rowops_build_layout(const int* lens32, int B, int S, int halo_keep, int halo_rows, int* off, int* ext,
+                                unsigned* rowmap, int R_cap, cudaStream_t st) {
+  if (B <= 0 || R_cap <= 0) return cudaSuccess;
+  if (B > 65535 || S > FS2_MAX_ROWS_PER_UTT) return cudaErrorInvalidValue;
+  build_layout_kernel<<<1, 1024, 0, st>>>(lens32, B, S, halo_keep, halo_rows, off, ext);
+  ++g_fs2_launches;
+  fill_rowmap_kernel<<<blocks_for((size_t)R_cap, 256), 256, 0, st>>>(off, ext, B, R_cap, rowmap);
+  return LAUNCHED();
+}
+cudaError_t rowops_embed_pe(const int64_t* texts, const float* emb, const float* pe, int vocab, const RowLayout& lay,
+                            int D, float* out_grid, bf16* out_b, int out_planes, float* out_user, cudaStream_t st) {
+  if (lay.R_cap <= 0) return cudaSuccess;
+  embed_pe_kernel<<<blocks_for((size_t)lay.R_cap, 8), 256, 0, st>>>(texts, emb, pe, vocab, lay, D, out_grid, out_b,
+                                                                   out_planes, out_user);
   return LAUNCHED();
 }
 cudaError_t rowops_lens_to_i32(const int64_t* lens, int B, int cap, int* out, cudaStream_t st) {
@@ -432,21 +530,28 @@ cudaError_t rowops_duration_scan(const float* d, int B, int L, int* cum, int64_t
   duration_scan_kernel<<<B, 1024, 0, st>>>(d, L, cum, mel_lens, mel_lens32, tmax_dev);
   return LAUNCHED();
 }
-cudaError_t rowops_length_regulate(const float* x, int x_row_stride_utt, const int* cum, int B, int L, int D, int T,
-                                   int out_SA, float* out, cudaStream_t st) {
-  if (B <= 0 || out_SA <= 0) return cudaSuccess;
+cudaError_t rowops_length_regulate(const float* x, const int* src_off, int src_stride, const int* cum, int L, int D,
+                                   const RowLayout& lay, float* out, bf16* out_b, int out_planes, cudaStream_t st) {
+  if (lay.B <= 0 || lay.R_cap <= 0) return cudaSuccess;
   const size_t smem = sizeof(int) * (size_t)(L > 0 ? L : 1);
   if (smem > 48 * 1024) return cudaErrorInvalidValue;
-  dim3 grid((out_SA + 63) / 64, B);
-  length_regulate_kernel<<<grid, 256, smem, st>>>(x, x_row_stride_utt, cum, L, D, T, out_SA, out);
+  dim3 grid((lay.S + FS2_HALO + 63) / 64, lay.B);   // covers ext + halo rows of the longest utterance
+  length_regulate_kernel<<<grid, 256, smem, st>>>(x, src_off, src_stride, cum, L, D, lay, out, out_b, out_planes);
   return LAUNCHED();
 }
 cudaError_t rowops_variance_embed(float* pred, float control, const float* bins, int n_bins, const float* emb,
-                                  const float* pe, float* x, bf16* xb, int xb_planes, int B, int S, int SA, int D,
+                                  const float* pe, float* x, bf16* xb, int xb_planes, const RowLayout& lay, int D,
                                   int* idx_out, cudaStream_t st) {
-  if (B * S <= 0) return cudaSuccess;
-  variance_embed_kernel<<<blocks_for((size_t)B * S, 8), 256, 0, st>>>(pred, control, bins, n_bins, emb, pe, x, xb,
-                                                                     xb_planes, B, S, SA, D, idx_out);
+  if (lay.R_cap <= 0) return cudaSuccess;
+  variance_embed_kernel<<<blocks_for((size_t)lay.R_cap, 8), 256, 0, st>>>(pred, control, bins, n_bins, emb, pe, x, xb,
+                                                                         xb_planes, lay, D, idx_out);
+  return LAUNCHED();
+}
+cudaError_t rowops_fill_padded_rows(const float* bias, int N, const RowLayout& lay, int dst_SA, float* out_grid,
+                                    bf16* out_b, int out_planes, float* out_user, cudaStream_t st) {
+  if (lay.B <= 0 || dst_SA <= 0) return cudaSuccess;
+  dim3 grid((dst_SA + 7) / 8, lay.B);
+  fill_padded_rows_kernel<<<grid, 256, 0, st>>>(bias, N, lay, dst_SA, out_grid, out_b, out_planes, out_user);
   return LAUNCHED();
 }
 cudaError_t rowops_split3(const float* src, int64_t n, bf16* dst, int64_t plane_elems, cudaStream_t st) {
@@ -467,17 +572,17 @@ cudaError_t rowops_gaussian_upsample(const float* x, const float* d, int B, int 
   gaussian_upsample_kernel<<<grid, 256, smem, st>>>(x, d, L, D, T, T_w, out, s, w);
   return LAUNCHED();
 }
-cudaError_t rowops_to_grid(const float* x_user, int B, int S, int SA, int C, float* out, int ldo, int col_off,
+cudaError_t rowops_to_grid(const float* x_user, const RowLayout& lay, int C, float* out, int ldo, int col_off,
                            bf16* out_b, cudaStream_t st) {
-  const size_t n = (size_t)B * SA * (C / 4);
+  const size_t n = (size_t)lay.R_cap * (C / 4);
   if (n == 0) return cudaSuccess;
-  to_grid_kernel<<<blocks_for(n, 256), 256, 0, st>>>(x_user, B, S, SA, C, out, ldo, col_off, out_b);
+  to_grid_kernel<<<blocks_for(n, 256), 256, 0, st>>>(x_user, lay, C, out, ldo, col_off, out_b);
   return LAUNCHED();
 }
-cudaError_t rowops_from_grid(const float* x_grid, int B, int S, int SA, int C, float* out_user, cudaStream_t st) {
-  const size_t n = (size_t)B * S * (C / 4);
+cudaError_t rowops_from_grid(const float* x_grid, const RowLayout& lay, int C, float* out_user, cudaStream_t st) {
+  const size_t n = (size_t)lay.B * lay.S * (C / 4);
   if (n == 0) return cudaSuccess;
-  from_grid_kernel<<<blocks_for(n, 256), 256, 0, st>>>(x_grid, B, S, SA, C, out_user);
+  from_grid_kernel<<<blocks_for(n, 256), 256, 0, st>>>(x_grid, lay, C, out_user);
   return LAUNCHED();
 }
 cudaError_t rowops_pack_weight(const float* src, int N, int K, int taps, const float* scale, float* dst_f,
@@ -503,16 +608,16 @@ cudaError_t rowops_bf16_to_f32(const bf16* src, int64_t n, float* dst, cudaStrea
   bf16_to_f32_kernel<<<blocks_for((size_t)n, 256), 256, 0, st>>>(src, n, dst);
   return LAUNCHED();
 }
-cudaError_t rowops_transpose_v(const bf16* v, int B, int SA, int SAv, int D, bf16* vt, cudaStream_t st) {
-  const size_t n = (size_t)B * D * SAv;
+cudaError_t rowops_transpose_v(const bf16* v, int R, int Rv, int D, bf16* vt, cudaStream_t st) {
+  const size_t n = (size_t)D * Rv;
   if (n == 0) return cudaSuccess;
-  transpose_v_kernel<<<blocks_for(n, 256), 256, 0, st>>>(v, B, SA, SAv, D, vt);
+  transpose_v_kernel<<<blocks_for(n, 256), 256, 0, st>>>(v, R, Rv, D, vt);
   return LAUNCHED();
 }
-cudaError_t rowops_add_pe(float* x, bf16* xb, const float* pe, int B, int S, int SA, int D, cudaStream_t st) {
-  const size_t n = (size_t)B * S * (D / 4);
+cudaError_t rowops_add_pe(float* x, const float* pe, const RowLayout& lay, int D, cudaStream_t st) {
+  const size_t n = (size_t)lay.R_cap * (D / 4);
   if (n == 0) return cudaSuccess;
-  add_pe_kernel<<<blocks_for(n, 256), 256, 0, st>>>(x, xb, pe, B, S, SA, D);
+  add_pe_kernel<<<blocks_for(n, 256), 256, 0, st>>>(x, pe, lay, D);
   return LAUNCHED();
 }
 cudaError_t rowops_fill_zero(void* p, size_t bytes, cudaStream_t st) {

@@ -16,8 +16,8 @@ constexpr int BKV = 64;
 
 template <int DK>
 __global__ void __launch_bounds__(128) simt_attention_kernel(const float* __restrict__ qkv, int ldqkv, int q_off,
-                                                             int k_off, int v_off, const int* __restrict__ lens, int S,
-                                                             int SA, float* __restrict__ out, int ldo, float temperature) {
+                                                             int k_off, int v_off, const RowLayout lay,
+                                                             float* __restrict__ out, int ldo, float temperature) {
   constexpr int QS = DK + 4;     // padded row stride (floats) of Q/K tiles: conflict-free float4 column walks
   constexpr int PS = BKV + 4;
   constexpr int DC = DK / 64;    // float4 output column groups per thread
@@ -31,8 +31,10 @@ __global__ void __launch_bounds__(128) simt_attention_kernel(const float* __rest
   const int tx = tid & 15, ty = tid >> 4;  // ty in [0,8)
   const int b = blockIdx.z, h = blockIdx.y;
   const int p0 = blockIdx.x * BQ;
-  const int len = min(__ldg(lens + b), S);
-  const size_t row0 = (size_t)b * SA;
+  const size_t row0 = (size_t)__ldg(lay.off + b);
+  const int SA = __ldg(lay.off + b + 1) - (int)row0;   // this utterance's rows (grid + halo)
+  const int len = min(__ldg(lay.lens + b), __ldg(lay.ext + b));
+  if (p0 >= SA) return;
 
   if (p0 >= len) {  // whole tile is padding: zeros
     for (int idx = tid; idx < BQ * (DK / 4); idx += 128) {
@@ -168,8 +170,8 @@ __global__ void __launch_bounds__(128) simt_attention_kernel(const float* __rest
 }
 
 template <int DK>
-cudaError_t launch(const float* qkv, int ldqkv, int q_off, int k_off, int v_off, const int* lens, int B, int S, int SA,
-                   int H, float* out, int ldo, cudaStream_t st) {
+cudaError_t launch(const float* qkv, int ldqkv, int q_off, int k_off, int v_off, const RowLayout& lay, int H, float* out,
+                   int ldo, cudaStream_t st) {
   const size_t smem = sizeof(float) * (BQ * (DK + 4) + BKV * (DK + 4) + BKV * DK + BQ * (BKV + 4));
   static bool configured = false;
   if (!configured) {
@@ -177,8 +179,8 @@ cudaError_t launch(const float* qkv, int ldqkv, int q_off, int k_off, int v_off,
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  dim3 grid((SA + BQ - 1) / BQ, H, B);
-  simt_attention_kernel<DK><<<grid, 128, smem, st>>>(qkv, ldqkv, q_off, k_off, v_off, lens, S, SA, out, ldo,
+  dim3 grid((lay.S + FS2_HALO + BQ - 1) / BQ, H, lay.B);
+  simt_attention_kernel<DK><<<grid, 128, smem, st>>>(qkv, ldqkv, q_off, k_off, v_off, lay, out, ldo,
                                                       (float)sqrt((double)DK));
   ++g_fs2_launches;
   return cudaGetLastError();
@@ -186,10 +188,11 @@ cudaError_t launch(const float* qkv, int ldqkv, int q_off, int k_off, int v_off,
 
 }  // namespace
 
-cudaError_t simt_attention_launch(const float* qkv, int ldqkv, int q_off, int k_off, int v_off, const int* lens, int B,
-                                  int S, int SA, int H, int dk, float* out, int ldo, cudaStream_t st) {
-  if (B <= 0 || S <= 0) return cudaSuccess;
-  if (dk == 128) return launch<128>(qkv, ldqkv, q_off, k_off, v_off, lens, B, S, SA, H, out, ldo, st);
-  if (dk == 64) return launch<64>(qkv, ldqkv, q_off, k_off, v_off, lens, B, S, SA, H, out, ldo, st);
+cudaError_t simt_attention_launch(const float* qkv, int ldqkv, int q_off, int k_off, int v_off, const RowLayout& lay,
+                                  int H, int dk, float* out, int ldo, cudaStream_t st) {
+  if (lay.B <= 0 || lay.S <= 0) return cudaSuccess;
+  if (!lay.off || !lay.ext || !lay.lens) return cudaErrorInvalidValue;
+  if (dk == 128) return launch<128>(qkv, ldqkv, q_off, k_off, v_off, lay, H, out, ldo, st);
+  if (dk == 64) return launch<64>(qkv, ldqkv, q_off, k_off, v_off, lay, H, out, ldo, st);
   return cudaErrorInvalidValue;
 }

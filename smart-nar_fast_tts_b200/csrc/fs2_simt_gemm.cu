@@ -37,8 +37,9 @@ __global__ void __launch_bounds__(256) simt_conv_gemm_kernel(const ConvGemmArgs 
 
   const int tid = threadIdx.x;
   const int tx = tid % TX, ty = tid / TX;
-  const int R = a.B * a.SA;
+  const int R = __ldg(a.lay.off + a.lay.B);   // rows in use (device data); rows beyond are never read as non-zero
   const int r0 = blockIdx.x * BM;
+  if (r0 >= R) return;
   const int n0 = blockIdx.y * BN;
   const int pad = (a.taps - 1) / 2;
   const int KB = a.K / BK;
@@ -149,11 +150,13 @@ __global__ void __launch_bounds__(256) simt_conv_gemm_kernel(const ConvGemmArgs 
   for (int i = 0; i < 8; ++i) {
     const int r = r0 + ty * 8 + i;
     const bool in_buf = r < R;   // warp-uniform (a warp owns consecutive rows of one ty)
-    const int b = in_buf ? r / a.SA : 0;
-    const int p = in_buf ? r - b * a.SA : 0;
-    const bool in_grid = in_buf && p < a.S;
-    const bool keep_len = in_grid && (a.lens == nullptr || p < __ldg(a.lens + b));
+    const RowPos rp = row_pos(a.lay, r, R);
+    const int b = rp.b, p = rp.p;
+    const bool in_grid = rp.in_grid;
+    const bool keep_len = in_grid && (a.lay.lens == nullptr || p < __ldg(a.lay.lens + b));
     const bool keep = (a.mask_mode == MASK_LEN) ? keep_len : in_grid;
+    const bool dst_ok = a.dst_SA > 0 ? in_grid : in_buf;
+    const size_t dst_r = a.dst_SA > 0 ? (size_t)b * a.dst_SA + p : (size_t)r;
 
     float v[8];
 #pragma unroll
@@ -198,7 +201,7 @@ __global__ void __launch_bounds__(256) simt_conv_gemm_kernel(const ConvGemmArgs 
 #pragma unroll
         for (int j = 0; j < 8; ++j) d = fmaf(v[j], dw[j], d);
         d = warp_sum(d) + a.dot_b;
-        if (tx == 0 && in_grid && a.out_user) a.out_user[(size_t)b * a.S + p] = keep_len ? d : 0.0f;
+        if (tx == 0 && in_grid && a.out_user) a.out_user[(size_t)b * a.lay.S + p] = keep_len ? d : 0.0f;
         continue;
       }
     }
@@ -206,12 +209,12 @@ __global__ void __launch_bounds__(256) simt_conv_gemm_kernel(const ConvGemmArgs 
 #pragma unroll
       for (int j = 0; j < 8; ++j) v[j] = 0.f;
     }
-    if (a.out && in_buf) {
-      if (nA < a.N) *reinterpret_cast<float4*>(a.out + (size_t)r * a.ldo + nA) = make_float4(v[0], v[1], v[2], v[3]);
-      if (nB < a.N) *reinterpret_cast<float4*>(a.out + (size_t)r * a.ldo + nB) = make_float4(v[4], v[5], v[6], v[7]);
+    if (a.out && dst_ok) {
+      if (nA < a.N) *reinterpret_cast<float4*>(a.out + dst_r * a.ldo + nA) = make_float4(v[0], v[1], v[2], v[3]);
+      if (nB < a.N) *reinterpret_cast<float4*>(a.out + dst_r * a.ldo + nB) = make_float4(v[4], v[5], v[6], v[7]);
     }
     if (a.out_user && in_grid) {
-      float* o = a.out_user + ((size_t)b * a.S + p) * a.ldu;
+      float* o = a.out_user + ((size_t)b * a.lay.S + p) * a.ldu;
       if (nA < a.N) *reinterpret_cast<float4*>(o + nA) = make_float4(v[0], v[1], v[2], v[3]);
       if (nB < a.N) *reinterpret_cast<float4*>(o + nB) = make_float4(v[4], v[5], v[6], v[7]);
     }
@@ -221,8 +224,9 @@ __global__ void __launch_bounds__(256) simt_conv_gemm_kernel(const ConvGemmArgs 
 }  // namespace
 
 cudaError_t simt_conv_gemm_launch(const ConvGemmArgs& a, cudaStream_t st) {
-  const int R = a.B * a.SA;
+  const int R = a.lay.R_cap;
   if (R <= 0) return cudaSuccess;
+  if (!a.lay.off || !a.lay.rowmap) return cudaErrorInvalidValue;
   if (a.K % BK != 0 || a.N % 4 != 0) return cudaErrorInvalidValue;
   const bool ln = (a.epi == EPI_RES_LN || a.epi == EPI_RELU_LN || a.epi == EPI_RELU_LN_DOT);
   if (ln && a.N != 256) return cudaErrorInvalidValue;

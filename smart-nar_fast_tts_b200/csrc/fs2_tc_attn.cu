@@ -10,7 +10,8 @@
 //   warps 2-5: online softmax, one thread per query row (= TMEM lane): tcgen05.ld S, scale + key mask, running max /
 //              sum in the exp2 domain, P written as bf16 into a 128B-swizzled K-major shared tile (A operand of the PV
 //              MMA), O rescaled in TMEM by exp2(m_old - m_new).
-// V is consumed K-major as V^T ([d, key]); the QKV GEMM epilogue (fs2_tc_gemm.cu, EPI_QKV) writes it in that layout.
+// V is consumed K-major as V^T ([d, flat row]); the QKV GEMM epilogue (fs2_tc_gemm.cu, EPI_QKV) writes it in that layout.
+// Rows follow the ragged layout of fs2_common.cuh: utterance b owns flat rows [off[b], off[b+1]).
 // Query rows >= len_b are written as zeros (masked by the caller anyway, Layers.py:43).
 #include "fs2_tc_common.cuh"
 #include "../../include/fs2_b200.h"
@@ -40,8 +41,8 @@ __device__ __forceinline__ float fast_exp2(float x) {
 
 __global__ void __launch_bounds__(ATT_THREADS, 1)
 tc_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-                    const __grid_constant__ CUtensorMap tmV, const int* __restrict__ lens, int S, int SA,
-                    bf16* __restrict__ out_b, float scale_log2) {
+                    const __grid_constant__ CUtensorMap tmV, const RowLayout lay, bf16* __restrict__ out_b,
+                    float scale_log2) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   const uint32_t base = (raw_addr + 1023u) & ~1023u;
@@ -53,8 +54,10 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.z, h = blockIdx.y, p0 = blockIdx.x * BQ;
-  const int len = min(__ldg(lens + b), S);
-  const size_t row0 = (size_t)b * SA;
+  const size_t row0 = (size_t)__ldg(lay.off + b);
+  const int SA = __ldg(lay.off + b + 1) - (int)row0;   // this utterance's rows (grid + halo)
+  const int len = min(__ldg(lay.lens + b), __ldg(lay.ext + b));
+  if (p0 >= SA) return;   // uniform over the CTA, before any barrier / TMEM use
 
   if (p0 >= len) {  // tile is all padding: zeros, no tensor work (uniform over the CTA)
     for (int idx = threadIdx.x; idx < BQ * (DK / 8); idx += ATT_THREADS) {
@@ -99,8 +102,8 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         const uint32_t ks = base + K_OFF + s * TILE_BYTES, vs = base + V_OFF + s * TILE_BYTES;
         tma_load_2d(ks, &tmK, kv_full0 + 8 * s, h * DK, (int)row0 + j * BKV);
         tma_load_2d(ks + ATOM_BYTES, &tmK, kv_full0 + 8 * s, h * DK + 64, (int)row0 + j * BKV);
-        tma_load_2d(vs, &tmV, kv_full0 + 8 * s, j * BKV, (b * 2 + h) * DK);
-        tma_load_2d(vs + ATOM_BYTES, &tmV, kv_full0 + 8 * s, j * BKV + 64, (b * 2 + h) * DK);
+        tma_load_2d(vs, &tmV, kv_full0 + 8 * s, (int)row0 + j * BKV, h * DK);
+        tma_load_2d(vs + ATOM_BYTES, &tmV, kv_full0 + 8 * s, (int)row0 + j * BKV + 64, h * DK);
       }
     }
   } else if (warp == 1) {
@@ -244,14 +247,15 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 
 }  // namespace
 
-int tc_attention_launch(const bf16* q, const bf16* k, const bf16* vt, const int* lens, int B, int S, int SA, int SAv,
-                        int H, bf16* out_b, cudaStream_t st) {
-  if (B <= 0 || S <= 0) return FS2_OK;
+int tc_attention_launch(const bf16* q, const bf16* k, const bf16* vt, const RowLayout& lay, int Rv, int H, bf16* out_b,
+                        cudaStream_t st) {
+  if (lay.B <= 0 || lay.S <= 0) return FS2_OK;
   if (H != 2) return fs2_fail_cuda(cudaErrorInvalidValue, "tc_attention: built for H = 2, d_k = 128");
-  const uint64_t R = (uint64_t)B * SA;
+  if (!lay.off || !lay.ext || !lay.lens) return fs2_fail_cuda(cudaErrorInvalidValue, "tc_attention: row layout missing");
+  const uint64_t R = (uint64_t)lay.R_cap;
   CUtensorMap tmQ, tmK, tmV;
   if (!tc::make_tmap_bf16(&tmQ, q, R, 256, 256, BQ) || !tc::make_tmap_bf16(&tmK, k, R, 256, 256, BKV) ||
-      !tc::make_tmap_bf16(&tmV, vt, (uint64_t)B * 256, (uint64_t)SAv, (uint64_t)SAv, DK))
+      !tc::make_tmap_bf16(&tmV, vt, 256, (uint64_t)Rv, (uint64_t)Rv, DK))
     return fs2_fail_cuda(cudaErrorInvalidValue, "cuTensorMapEncodeTiled(attention)");
   static bool configured = false;
   const int smem = SMEM_TOTAL + 1024;
@@ -260,9 +264,9 @@ int tc_attention_launch(const bf16* q, const bf16* k, const bf16* vt, const int*
     if (e != cudaSuccess) return fs2_fail_cuda(e, "cudaFuncSetAttribute(tc_attention)");
     configured = true;
   }
-  dim3 grid((SA + BQ - 1) / BQ, H, B);
+  dim3 grid((lay.S + FS2_HALO + BQ - 1) / BQ, H, lay.B);
   const float scale_log2 = (float)(1.4426950408889634 / sqrt((double)DK));
-  tc_attention_kernel<<<grid, ATT_THREADS, smem, st>>>(tmQ, tmK, tmV, lens, S, SA, out_b, scale_log2);
+  tc_attention_kernel<<<grid, ATT_THREADS, smem, st>>>(tmQ, tmK, tmV, lay, out_b, scale_log2);
   ++g_fs2_launches;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fs2_fail_cuda(e, "tc_attention_kernel launch");

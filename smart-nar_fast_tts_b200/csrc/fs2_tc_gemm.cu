@@ -82,7 +82,7 @@ __device__ __forceinline__ void store_bf16_chunk(bf16* o, size_t plane_elems, in
 template <int BN>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 tc_conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                    const ConvGemmArgs a, const int num_m_blocks, const int num_n_blocks) {
+                    const ConvGemmArgs a, const int num_n_blocks) {
   using L = SmemLayout<BN>;
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment for the 128B-swizzled tiles
@@ -105,7 +105,8 @@ tc_conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const int KB = (a.K + BKE - 1) / BKE;
   const int ncombo = a.planes == 3 ? 6 : 1;
   const int iters = a.taps * KB;
-  const int num_tiles = num_m_blocks * num_n_blocks;
+  const int R = __ldg(a.lay.off + a.lay.B);          // rows in use: device data (ragged layout)
+  const int num_tiles = ((R + BM - 1) / BM) * num_n_blocks;
   constexpr uint32_t TMEM_COLS = 2 * BN;  // 512 or 256: power of two
 
   if (warp == 0 && lane == 0) {
@@ -185,7 +186,6 @@ tc_conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     // ===================================================== epilogue (warps 2..5, 128 threads)
     const int q = warp & 3;                 // TMEM lane quarter this warp may access
     const int row_in_tile = q * 32 + lane;
-    const int R = a.B * a.SA;
     int as = 0; uint32_t aphase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m_blk = tile / num_n_blocks, n_blk = tile - m_blk * num_n_blocks;
@@ -198,11 +198,14 @@ tc_conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       RowInfo ri;
       ri.r = m_blk * BM + row_in_tile;
       ri.in_buf = ri.r < R;
-      ri.b = ri.in_buf ? ri.r / a.SA : 0;
-      ri.p = ri.in_buf ? ri.r - ri.b * a.SA : 0;
-      ri.in_grid = ri.in_buf && ri.p < a.S;
-      ri.keep_len = ri.in_grid && (a.lens == nullptr || ri.p < __ldg(a.lens + ri.b));
+      const RowPos rp = row_pos(a.lay, ri.r, R);
+      ri.b = rp.b; ri.p = rp.p; ri.in_grid = rp.in_grid;
+      ri.keep_len = ri.in_grid && (a.lay.lens == nullptr || ri.p < __ldg(a.lay.lens + ri.b));
       ri.keep = (a.mask_mode == MASK_LEN) ? ri.keep_len : ri.in_grid;
+      // destination row of out / out_b: same flat row, or a uniform grid of dst_SA rows per utterance (grid rows only)
+      const bool dst_ok = a.dst_SA > 0 ? ri.in_grid : ri.in_buf;
+      const size_t dst_r = a.dst_SA > 0 ? (size_t)ri.b * a.dst_SA + ri.p : (size_t)ri.r;
+      const size_t dst_plane = a.dst_SA > 0 ? (size_t)a.lay.B * a.dst_SA : (size_t)a.lay.R_cap;
 
       mbar_wait(tfull_bar(as), aphase);
       fence_after_sync();
@@ -252,20 +255,20 @@ tc_conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             y[j] = ri.keep ? x : 0.f;
             dot = fmaf(x, s_dw[c * 32 + j], dot);
           }
-          if (a.epi != EPI_RELU_LN_DOT && ri.in_buf) {
+          if (a.epi != EPI_RELU_LN_DOT && dst_ok) {
             if (a.out) {
-              float* o = a.out + (size_t)ri.r * a.ldo + c * 32;
+              float* o = a.out + dst_r * a.ldo + c * 32;
 #pragma unroll
               for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(y[j], y[j + 1], y[j + 2], y[j + 3]);
             }
             if (a.out_b)
-              store_bf16_chunk(a.out_b + (size_t)ri.r * a.ldob + c * 32, (size_t)R * a.ldob, a.out_planes, y, c * 32, 256);
+              store_bf16_chunk(a.out_b + dst_r * a.ldob + c * 32, dst_plane * a.ldob, a.out_planes, y, c * 32, 256);
           }
         }
         if (a.epi == EPI_RELU_LN_DOT && ri.in_grid && a.out_user)
-          a.out_user[(size_t)ri.b * a.S + ri.p] = ri.keep_len ? dot + a.dot_b : 0.f;
+          a.out_user[(size_t)ri.b * a.lay.S + ri.p] = ri.keep_len ? dot + a.dot_b : 0.f;
       } else if (a.epi == EPI_QKV) {
-        // n_blk 0 -> Q, 1 -> K (bf16 row-major [R,256]); 2 -> V transposed per utterance: vt[(b*256 + c), p]
+        // n_blk 0 -> Q, 1 -> K (bf16 row-major [R,256]); 2 -> V transposed: vt[c, r] (column = flat row)
         for (int c = 0; c < BN / 32; ++c) {
           __syncwarp();
           tmem_ld32(t_row + c * 32, v);
@@ -280,9 +283,9 @@ tc_conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               *reinterpret_cast<uint4*>(o + j) = make_uint4(pack_bf16x2(y[j], y[j + 1]), pack_bf16x2(y[j + 2], y[j + 3]),
                                                             pack_bf16x2(y[j + 4], y[j + 5]), pack_bf16x2(y[j + 6], y[j + 7]));
           } else if (ri.in_buf) {
-            bf16* o = a.vt_b + ((size_t)ri.b * 256 + c * 32) * a.SAv + ri.p;
+            bf16* o = a.vt_b + (size_t)(c * 32) * a.Rv + ri.r;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) o[(size_t)j * a.SAv] = __float2bfloat16_rn(y[j]);
+            for (int j = 0; j < 32; ++j) o[(size_t)j * a.Rv] = __float2bfloat16_rn(y[j]);
           }
         }
       } else {
@@ -313,16 +316,16 @@ tc_conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
             for (int j = 0; j < 32; ++j) y[j] = 0.f;
           }
-          if (a.out && ri.in_buf) {
-            float* o = a.out + (size_t)ri.r * a.ldo + nb;
+          if (a.out && dst_ok) {
+            float* o = a.out + dst_r * a.ldo + nb;
 #pragma unroll
             for (int j = 0; j < 32; j += 4)
               if (nb + j < a.N) *reinterpret_cast<float4*>(o + j) = make_float4(y[j], y[j + 1], y[j + 2], y[j + 3]);
           }
-          if (a.out_b && ri.in_buf)
-            store_bf16_chunk(a.out_b + (size_t)ri.r * a.ldob + nb, (size_t)R * a.ldob, a.out_planes, y, nb, a.N);
+          if (a.out_b && dst_ok)
+            store_bf16_chunk(a.out_b + dst_r * a.ldob + nb, dst_plane * a.ldob, a.out_planes, y, nb, a.N);
           if (a.out_user && ri.in_grid) {
-            float* o = a.out_user + ((size_t)ri.b * a.S + ri.p) * a.ldu + nb;
+            float* o = a.out_user + ((size_t)ri.b * a.lay.S + ri.p) * a.ldu + nb;
 #pragma unroll
             for (int j = 0; j < 32; j += 4)
               if (nb + j < a.N) *reinterpret_cast<float4*>(o + j) = make_float4(y[j], y[j + 1], y[j + 2], y[j + 3]);
@@ -351,7 +354,7 @@ int g_num_sms = 0;
 template <int BN>
 int launch(const ConvGemmArgs& a, cudaStream_t st) {
   using L = SmemLayout<BN>;
-  const int R = a.B * a.SA;
+  const int R = a.lay.R_cap;                       // allocated rows; the rows in use (off[B]) are device data
   const int num_m_blocks = (R + BM - 1) / BM;
   const int num_n_blocks = (a.N + BN - 1) / BN;
   CUtensorMap tmA, tmB;
@@ -375,7 +378,7 @@ int launch(const ConvGemmArgs& a, cudaStream_t st) {
   }
   const int tiles = num_m_blocks * num_n_blocks;
   const int grid = tiles < g_num_sms ? tiles : g_num_sms;
-  tc_conv_gemm_kernel<BN><<<grid, NUM_THREADS, smem, st>>>(tmA, tmB, a, num_m_blocks, num_n_blocks);
+  tc_conv_gemm_kernel<BN><<<grid, NUM_THREADS, smem, st>>>(tmA, tmB, a, num_n_blocks);
   ++g_fs2_launches;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fs2_fail_cuda(e, "tc_conv_gemm_kernel launch");
@@ -385,8 +388,9 @@ int launch(const ConvGemmArgs& a, cudaStream_t st) {
 }  // namespace
 
 int tc_conv_gemm_launch(const ConvGemmArgs& a, cudaStream_t st) {
-  const int R = a.B * a.SA;
+  const int R = a.lay.R_cap;
   if (R <= 0) return FS2_OK;
+  if (!a.lay.off || !a.lay.rowmap) return fs2_fail_cuda(cudaErrorInvalidValue, "tc_conv_gemm: row layout missing");
   if (!a.Ab || !a.Wb || a.K % 8 != 0 || a.N % 8 != 0) return fs2_fail_cuda(cudaErrorInvalidValue, "tc_conv_gemm: operands");
   if ((a.planes != 0 && a.planes != 1 && a.planes != 3) || (a.out_planes != 0 && a.out_planes != 1 && a.out_planes != 3))
     return fs2_fail_cuda(cudaErrorInvalidValue, "tc_conv_gemm: planes must be 1 or 3");

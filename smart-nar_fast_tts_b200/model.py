@@ -172,6 +172,7 @@ class FastSpeech2Align(nn.Module):
         self._stamp = None
         self._cached_ws = None
         self._precision = (PREC_BF16X3, PREC_BF16)
+        self._keep_rows = 2
         # multi-GPU hook (sharding.py): maps the local T_max to the batch-global one between the two stages
         self.t_max_hook: Optional[Callable[[int, torch.device], int]] = None
 
@@ -184,6 +185,15 @@ class FastSpeech2Align(nn.Module):
         if self._handle is not None:
             lib = load_library()
             lib.check(lib.fs2_set_precision(self._handle, *self._precision), self._handle)
+        return self
+
+    def set_row_packing(self, keep_rows: int = 2) -> "FastSpeech2Align":
+        """Padded rows kept per utterance in the internal layout: 2 = packed (default); a value >= the longest
+        utterance = the reference's full padded grid.  Results are identical; only padded work changes."""
+        self._keep_rows = int(keep_rows)
+        if self._handle is not None:
+            lib = load_library()
+            lib.check(lib.fs2_set_row_packing(self._handle, self._keep_rows), self._handle)
         return self
 
     def _weights(self):
@@ -214,6 +224,7 @@ class FastSpeech2Align(nn.Module):
             lib.check(rc, None)
             self._handle, self._handle_device = hp.value, device
             lib.check(lib.fs2_set_precision(self._handle, *self._precision), self._handle)
+            lib.check(lib.fs2_set_row_packing(self._handle, self._keep_rows), self._handle)
         ws = self._weights()
         stamp = (ws[0][1].data_ptr(), ws[-1][1].data_ptr(), sum(t._version for _, t in ws))
         if stamp != self._stamp:

@@ -103,6 +103,19 @@ def test_forward_oracle_batch32(lib, enc_prec, dec_prec):
     check_against(ref2, out2[:10], sd, dec_prec)
 
 
+@pytest.mark.parametrize("enc_prec,dec_prec", [("fp32", "fp32"), ("bf16x3", "bf16")])
+def test_forward_packed_equals_padded_grid(lib, enc_prec, dec_prec):
+    """The packed row layout (valid rows + 2 padded rows per utterance) must give the same numbers as storing the
+    reference's whole padded [B, S_max] grid -- on every row of every output, padded ones included."""
+    sd = O.make_state_dict(0)
+    inputs = O.make_inputs(6, 3, 40, seed=11)           # ragged: lengths 3..40 -> very different mel lengths
+    m = build_model(sd, O.STATS_NAN_BINS).set_precision(enc_prec, dec_prec)
+    packed = run_model(m.set_row_packing(2), *inputs)
+    padded = run_model(m.set_row_packing(1 << 20), *inputs)
+    for i, (a, b) in enumerate(zip(packed[:10], padded[:10])):
+        assert a.shape == b.shape and torch.equal(a, b), f"output {i} differs between packed and padded layouts"
+
+
 def test_forward_determinism_and_reuse(lib):
     sd = O.make_state_dict(0)
     m = build_model(sd, O.STATS_NAN_BINS)
