@@ -292,7 +292,7 @@ int make_layout(fs2_handle* h, const std::string& name, const int* lens32, int B
                 RowLayout* out, cudaStream_t st) {
   if (B > 65535) return h->fail(FS2_ERR_UNSUPPORTED, "more than 65535 utterances in one call");
   if (S > FS2_MAX_ROWS_PER_UTT) return h->fail(FS2_ERR_UNSUPPORTED, "more than 65535 rows per utterance");
-  const int R_cap = B * (S + halo_rows);
+  const int R_cap = B * FS2_ROWS_PER_UTT(S, halo_rows);
   WS(int, off, name + ".off", (size_t)B + 1);
   WS(int, ext, name + ".ext", (size_t)B);
   WS(unsigned, rowmap, name + ".map", (size_t)R_cap);
@@ -307,7 +307,7 @@ struct TmpLayout {
   int *off = nullptr, *ext = nullptr;
   unsigned* map = nullptr;
   cudaError_t build(const int* lens32, int B, int S, int halo_keep, int halo_rows, cudaStream_t st) {
-    const int R_cap = B * (S + halo_rows);
+    const int R_cap = B * FS2_ROWS_PER_UTT(S, halo_rows);
     cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&off), sizeof(int) * ((size_t)B + 1));
     if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&ext), sizeof(int) * (size_t)B);
     if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&map), sizeof(unsigned) * (size_t)(R_cap > 0 ? R_cap : 1));
@@ -473,7 +473,7 @@ int run_predictor(fs2_handle* h, PredW& P, int prec, const float* x, const bf16*
 int run_mel_postnet(fs2_handle* h, int prec, const float* dec, const bf16* decb, const RowLayout& lay, float* mel,
                     float* mel_post, cudaStream_t st) {
   const int M = h->dims.n_mel, P = h->dims.pn_dim, NL = h->dims.pn_layers;
-  const int B = lay.B, T = lay.S, TA = T + FS2_HALO;
+  const int B = lay.B, T = lay.S, TA = FS2_ROWS_PER_UTT(T, FS2_HALO);   // rows per utterance of the PostNet grid
   const size_t R = (size_t)B * TA;
   const bool tc = prec != FS2_PREC_FP32;
   const size_t np = (size_t)planes_of(prec);

@@ -3,8 +3,8 @@
 // Row layout ("ragged grid") used by every internal activation tensor
 // ------------------------------------------------------------------
 // A reference tensor [B, S, C] is stored as flat rows of C channels.  Utterance b owns rows
-// [off[b], off[b+1]): first ext[b] "grid" rows (position p = 0..ext[b]-1), then FS2_HALO rows that
-// are always ZERO.  Because every Conv1d on the path has padding <= 4 (FFN k=9), a row-shifted
+// [off[b], off[b+1]): first ext[b] "grid" rows (position p = 0..ext[b]-1), then >= FS2_HALO rows that
+// are always ZERO (off[b] is a multiple of FS2_ROW_ALIGN).  Because every Conv1d on the path has padding <= 4 (FFN k=9), a row-shifted
 // read A[r + t - pad] that leaves the utterance's grid rows lands in a zero halo row (or outside
 // the buffer, which TMA / the loaders treat as zero) -- exactly the zero padding Conv1d applies
 // at the edge of the reference's padded [B,S] grid (SubLayers.py:73-85, modules.py:254-272,
@@ -27,6 +27,10 @@
 #include <stdint.h>
 
 #define FS2_HALO 4
+#define FS2_ROW_ALIGN 8   // utterances start at flat rows that are multiples of 8: V^T (bf16, row index innermost) is
+                          // loaded by TMA at column off[b] + j*128, and TMA needs 16-byte aligned global addresses
+// rows reserved per utterance of a layout with S grid rows (upper bound of ext + halo, aligned)
+#define FS2_ROWS_PER_UTT(S, halo_rows) ((halo_rows) > 0 ? (((S) + (halo_rows) + FS2_ROW_ALIGN - 1) / FS2_ROW_ALIGN) * FS2_ROW_ALIGN : (S))
 
 typedef __nv_bfloat16 bf16;
 
@@ -49,7 +53,7 @@ enum Fs2Mask : int {
 struct RowLayout {
   int B;                   // utterances
   int S;                   // rows per utterance of the user tensor [B,S,*]: user row = b*S + p
-  int R_cap;               // rows allocated = B*(S + FS2_HALO) (host-known upper bound of off[B])
+  int R_cap;               // rows allocated = B * FS2_ROWS_PER_UTT(S, halo) (host-known upper bound of off[B])
   const int* off;          // [B+1] device: first row of utterance b; off[B] = rows in use
   const int* ext;          // [B] device: grid rows of utterance b
   const int* lens;         // [B] device: valid rows (p < lens[b]); may be null where no length mask applies

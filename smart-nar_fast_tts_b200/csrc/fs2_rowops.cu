@@ -39,7 +39,8 @@ __device__ __forceinline__ void store_planes4(bf16* dst, size_t plane_elems, int
 
 
 // ---------------------------------------------------------------------------------------------
-// Ragged-grid layout (fs2_common.cuh): ext[b] = min(lens[b] + halo_keep, S); off = exclusive scan of ext + FS2_HALO.
+// Ragged-grid layout (fs2_common.cuh): ext[b] = min(lens[b] + halo_keep, S); off = exclusive scan of ext + halo_rows
+// rounded up to FS2_ROW_ALIGN rows (utterances start on 16-byte boundaries of the transposed-V operand).
 // One CTA, chunks of 1024 utterances, block-wide scan by warp shuffles.
 __global__ void __launch_bounds__(1024) build_layout_kernel(const int* __restrict__ lens, int B, int S, int halo_keep,
                                                             int halo_rows, int* __restrict__ off, int* __restrict__ ext) {
@@ -56,7 +57,7 @@ __global__ void __launch_bounds__(1024) build_layout_kernel(const int* __restric
       e = (int)(want < S ? want : S);
       if (e < 0) e = 0;
       ext[b] = e;
-      v = e + halo_rows;
+      v = halo_rows > 0 ? ((e + halo_rows + FS2_ROW_ALIGN - 1) / FS2_ROW_ALIGN) * FS2_ROW_ALIGN : e;
     }
     int x = v;
 #pragma unroll
@@ -535,7 +536,7 @@ cudaError_t rowops_length_regulate(const float* x, const int* src_off, int src_s
   if (lay.B <= 0 || lay.R_cap <= 0) return cudaSuccess;
   const size_t smem = sizeof(int) * (size_t)(L > 0 ? L : 1);
   if (smem > 48 * 1024) return cudaErrorInvalidValue;
-  dim3 grid((lay.S + FS2_HALO + 63) / 64, lay.B);   // covers ext + halo rows of the longest utterance
+  dim3 grid((FS2_ROWS_PER_UTT(lay.S, FS2_HALO) + 63) / 64, lay.B);   // covers ext + halo rows of the longest utterance
   length_regulate_kernel<<<grid, 256, smem, st>>>(x, src_off, src_stride, cum, L, D, lay, out, out_b, out_planes);
   return LAUNCHED();
 }

@@ -179,7 +179,7 @@ cudaError_t launch(const float* qkv, int ldqkv, int q_off, int k_off, int v_off,
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  dim3 grid((lay.S + FS2_HALO + BQ - 1) / BQ, H, lay.B);
+  dim3 grid((FS2_ROWS_PER_UTT(lay.S, FS2_HALO) + BQ - 1) / BQ, H, lay.B);
   simt_attention_kernel<DK><<<grid, 128, smem, st>>>(qkv, ldqkv, q_off, k_off, v_off, lay, out, ldo,
                                                       (float)sqrt((double)DK));
   ++g_fs2_launches;

@@ -264,7 +264,7 @@ int tc_attention_launch(const bf16* q, const bf16* k, const bf16* vt, const RowL
     if (e != cudaSuccess) return fs2_fail_cuda(e, "cudaFuncSetAttribute(tc_attention)");
     configured = true;
   }
-  dim3 grid((lay.S + FS2_HALO + BQ - 1) / BQ, H, lay.B);
+  dim3 grid((FS2_ROWS_PER_UTT(lay.S, FS2_HALO) + BQ - 1) / BQ, H, lay.B);
   const float scale_log2 = (float)(1.4426950408889634 / sqrt((double)DK));
   tc_attention_kernel<<<grid, ATT_THREADS, smem, st>>>(tmQ, tmK, tmV, lay, out_b, scale_log2);
   ++g_fs2_launches;
