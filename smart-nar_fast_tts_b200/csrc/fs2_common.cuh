@@ -128,6 +128,8 @@ cudaError_t simt_attention_launch(const float* qkv, int ldqkv, int q_off, int k_
 
 // tcgen05 path
 int tc_conv_gemm_launch(const ConvGemmArgs& a, cudaStream_t st);  // returns FS2_* code
+bool tc_conv_gemm_staged_supported(const ConvGemmArgs& a);        // fs2_tc_gemm_staged.cu: TMA-staged epilogue variant
+int tc_conv_gemm_staged_launch(const ConvGemmArgs& a, cudaStream_t st);
 int tc_attention_launch(const bf16* q, const bf16* k, const bf16* vt, const RowLayout& lay, int Rv, int H, bf16* out_b,
                         cudaStream_t st);
 

@@ -23,6 +23,7 @@
 //              statistics pass and the normalise pass.  Overlaps with the next tile's mainloop (accumulator double buffer).
 #include "fs2_tc_common.cuh"
 #include "../../include/fs2_b200.h"
+#include <stdlib.h>
 
 namespace {
 
@@ -397,6 +398,8 @@ int tc_conv_gemm_launch(const ConvGemmArgs& a, cudaStream_t st) {
   const bool ln = (a.epi == EPI_RES_LN || a.epi == EPI_RELU_LN || a.epi == EPI_RELU_LN_DOT);
   if (ln && a.N != 256) return fs2_fail_cuda(cudaErrorInvalidValue, "tc_conv_gemm: LayerNorm epilogue needs N == 256");
   if (a.epi == EPI_QKV && a.N != 768) return fs2_fail_cuda(cudaErrorInvalidValue, "tc_conv_gemm: QKV epilogue needs N == 768");
+  static const bool direct_only = getenv("FS2_DIRECT_EPILOGUE") != nullptr;   // A/B switch for profiling
+  if (!direct_only && tc_conv_gemm_staged_supported(a)) return tc_conv_gemm_staged_launch(a, st);
   if (a.N % 256 == 0) return launch<256>(a, st);
   if (a.N <= 128) return launch<128>(a, st);
   return fs2_fail_cuda(cudaErrorInvalidValue, "tc_conv_gemm: N must be a multiple of 256 or <= 128");
