@@ -15,7 +15,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--workload", default="c2")
 ap.add_argument("--warmup", type=int, default=2)
 ap.add_argument("--steps", type=int, default=1)
-ap.add_argument("--enc", default="fp32")
+ap.add_argument("--enc", default="bf16x3")
 ap.add_argument("--dec", default="bf16")
 a = ap.parse_args()
 dev = torch.device("cuda", 0)

@@ -2,14 +2,17 @@
 //
 // Restates transformer/Modules.py:14-25 with the head split of SubLayers.py:39-55 (H = 2, d_k = 128):
 //   out[b, q, h*128:(h+1)*128] = softmax_k( Q_h[b,q,:] . K_h[b,k,:] / sqrt(128), keys >= len_b masked ) @ V_h[b]
-// One CTA = one (128-query tile, head, utterance).  The [S,S] score matrix never leaves the SM:
-//   warp 0   : TMA.  Q tile once, then a 2-stage ring of (K block [128 keys x 128], V^T block [128 d x 128 keys]).
-//   warp 1   : tcgen05.mma.  S = Q K^T (M=128,N=128,K=128) into TMEM columns [0,128); O += P V (M=128,N=128,K=128 keys)
-//              into TMEM columns [128,256).  S(j+1) is issued before P(j)V(j) so the softmax of block j+1 overlaps the
+// One CTA = one (128-query tile, head, utterance); 112 KB of shared memory and 256 TMEM columns so that TWO CTAs share an
+// SM (one's softmax overlaps the other's MMAs and loads).  The [S,S] score matrix never leaves the SM:
+//   warp 0   : TMA.  Q tile once, then a 2-stage ring of (K block [64 keys x 128], V^T block [128 d x 64 keys]).
+//   warp 1   : tcgen05.mma.  S = Q K^T (M=128,N=64,K=128) into TMEM columns [0,64); O += P V (M=128,N=128,K=64 keys)
+//              into TMEM columns [64,192).  S(j+1) is issued before P(j)V(j) so the softmax of block j+1 overlaps the
 //              PV MMA of block j.
-//   warps 2-5: online softmax, one thread per query row (= TMEM lane): tcgen05.ld S, scale + key mask, running max /
-//              sum in the exp2 domain, P written as bf16 into a 128B-swizzled K-major shared tile (A operand of the PV
-//              MMA), O rescaled in TMEM by exp2(m_old - m_new).
+//   warps 2-5: online softmax, one thread per query row (= TMEM lane): one tcgen05.ld pass brings the row's 64 scores
+//              into registers; scale + key mask, running max / sum in the exp2 domain, P written as bf16 into a
+//              128B-swizzled K-major shared tile (A operand of the PV MMA); O is rescaled in TMEM by exp2(m_old - m_new)
+//              only when a row of the warp actually raised its maximum.  The normalised output tile leaves through a
+//              swizzled staging tile + TMA store when the whole tile lies inside the utterance.
 // V is consumed K-major as V^T ([d, flat row]); the QKV GEMM epilogue (fs2_tc_gemm.cu, EPI_QKV) writes it in that layout.
 // Rows follow the ragged layout of fs2_common.cuh: utterance b owns flat rows [off[b], off[b+1]).
 // Query rows >= len_b are written as zeros (masked by the caller anyway, Layers.py:43).
@@ -20,18 +23,19 @@ namespace {
 
 using namespace tc;
 
-constexpr int BQ = 128, BKV = 128, DK = 128;
-constexpr int ATOM_BYTES = 128 * 128;            // 128 rows x 64 bf16
-constexpr int TILE_BYTES = 2 * ATOM_BYTES;       // 128 x 128 bf16 = 32 KB
-constexpr int Q_OFF = 0;
-constexpr int K_OFF = TILE_BYTES;                // 2 stages
-constexpr int V_OFF = K_OFF + 2 * TILE_BYTES;    // 2 stages
-constexpr int P_OFF = V_OFF + 2 * TILE_BYTES;
-constexpr int BAR_OFF = P_OFF + TILE_BYTES;      // 192 KB
+constexpr int BQ = 128, BKV = 64, DK = 128;
+constexpr int Q_ATOM = BQ * 128;                 // 128 query rows x 64 bf16 (128-byte swizzled rows)
+constexpr int K_ATOM = BKV * 128;                // 64 key rows x 64 bf16
+constexpr int Q_OFF = 0;                         // 2 atoms (d 0..63, 64..127)
+constexpr int K_OFF = Q_OFF + 2 * Q_ATOM;        // 2 stages x 2 atoms
+constexpr int V_OFF = K_OFF + 2 * 2 * K_ATOM;    // 2 stages x [128 d rows x 64 keys]
+constexpr int V_TILE = DK * 128;
+constexpr int P_OFF = V_OFF + 2 * V_TILE;        // [128 query rows x 64 keys]
+constexpr int BAR_OFF = P_OFF + BQ * 128;        // 112 KB
 constexpr int NUM_BARS = 8;
-constexpr int SMEM_TOTAL = BAR_OFF + NUM_BARS * 8 + 16;
+constexpr int SMEM_TOTAL = BAR_OFF + NUM_BARS * 8 + 16;   // 114,768 B: two CTAs per SM
 constexpr int ATT_THREADS = 192;
-constexpr uint32_t TMEM_COLS = 256;
+constexpr uint32_t TMEM_COLS = 256;              // S: columns [0,64); O: columns [64,192); 2 CTAs/SM -> 512
 
 __device__ __forceinline__ float fast_exp2(float x) {
   float y;
@@ -39,14 +43,12 @@ __device__ __forceinline__ float fast_exp2(float x) {
   return y;
 }
 
-__global__ void __launch_bounds__(ATT_THREADS, 1)
+__global__ void __launch_bounds__(ATT_THREADS, 2)
 tc_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-                    const __grid_constant__ CUtensorMap tmV, const RowLayout lay, bf16* __restrict__ out_b,
-                    float scale_log2) {
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t raw_addr = smem_u32(smem_raw);
-  const uint32_t base = (raw_addr + 1023u) & ~1023u;
-  uint8_t* smem = smem_raw + (base - raw_addr);
+                    const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmO,
+                    const RowLayout lay, bf16* __restrict__ out_b, float scale_log2) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const uint32_t base = smem_u32(smem);
   const uint32_t bars = base + BAR_OFF;
   const uint32_t q_full = bars, kv_full0 = bars + 8, kv_empty0 = bars + 24, s_full = bars + 40, p_ready = bars + 48,
                  o_ready = bars + 56;
@@ -58,6 +60,7 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   const int SA = __ldg(lay.off + b + 1) - (int)row0;   // this utterance's rows (grid + halo)
   const int len = min(__ldg(lay.lens + b), __ldg(lay.ext + b));
   if (p0 >= SA) return;   // uniform over the CTA, before any barrier / TMEM use
+  if (base & 1023u) __trap();   // the swizzled tiles assume a 1024-byte aligned dynamic shared memory window
 
   if (p0 >= len) {  // tile is all padding: zeros, no tensor work (uniform over the CTA)
     for (int idx = threadIdx.x; idx < BQ * (DK / 8); idx += ATT_THREADS) {
@@ -87,39 +90,37 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   __syncthreads();
   fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_S = tmem_base, tmem_O = tmem_base + 128;
+  const uint32_t tmem_S = tmem_base, tmem_O = tmem_base + 64;
 
   if (warp == 0) {
     // ===================================================== TMA producer
     if (lane == 0) {
-      mbar_expect_tx(q_full, TILE_BYTES);
+      mbar_expect_tx(q_full, 2 * Q_ATOM);
       tma_load_2d(base + Q_OFF, &tmQ, q_full, h * DK, (int)row0 + p0);
-      tma_load_2d(base + Q_OFF + ATOM_BYTES, &tmQ, q_full, h * DK + 64, (int)row0 + p0);
+      tma_load_2d(base + Q_OFF + Q_ATOM, &tmQ, q_full, h * DK + 64, (int)row0 + p0);
       for (int j = 0; j < nb; ++j) {
         const int s = j & 1;
         mbar_wait(kv_empty0 + 8 * s, ((j >> 1) & 1) ^ 1u);
-        mbar_expect_tx(kv_full0 + 8 * s, 2 * TILE_BYTES);
-        const uint32_t ks = base + K_OFF + s * TILE_BYTES, vs = base + V_OFF + s * TILE_BYTES;
+        mbar_expect_tx(kv_full0 + 8 * s, 2 * K_ATOM + V_TILE);
+        const uint32_t ks = base + K_OFF + s * 2 * K_ATOM, vs = base + V_OFF + s * V_TILE;
         tma_load_2d(ks, &tmK, kv_full0 + 8 * s, h * DK, (int)row0 + j * BKV);
-        tma_load_2d(ks + ATOM_BYTES, &tmK, kv_full0 + 8 * s, h * DK + 64, (int)row0 + j * BKV);
+        tma_load_2d(ks + K_ATOM, &tmK, kv_full0 + 8 * s, h * DK + 64, (int)row0 + j * BKV);
         tma_load_2d(vs, &tmV, kv_full0 + 8 * s, (int)row0 + j * BKV, h * DK);
-        tma_load_2d(vs + ATOM_BYTES, &tmV, kv_full0 + 8 * s, (int)row0 + j * BKV + 64, h * DK);
       }
     }
   } else if (warp == 1) {
     // ===================================================== MMA issuer
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(128, 128);
+      constexpr uint32_t idesc_s = make_idesc_bf16(BQ, BKV), idesc_o = make_idesc_bf16(BQ, DK);
       auto issue_S = [&](int j) {
         const int s = j & 1;
         mbar_wait(kv_full0 + 8 * s, (j >> 1) & 1);
         fence_after_sync();
 #pragma unroll
-        for (int kk = 0; kk < 8; ++kk) {
-          const uint32_t off = (kk >> 2) * ATOM_BYTES;
-          const uint64_t ad = make_smem_desc_sw128(base + Q_OFF + off) + (uint64_t)(2 * (kk & 3));
-          const uint64_t bd = make_smem_desc_sw128(base + K_OFF + s * TILE_BYTES + off) + (uint64_t)(2 * (kk & 3));
-          umma_bf16(tmem_S, ad, bd, idesc, kk ? 1u : 0u);
+        for (int kk = 0; kk < DK / 16; ++kk) {
+          const uint64_t ad = make_smem_desc_sw128(base + Q_OFF + (kk >> 2) * Q_ATOM) + (uint64_t)(2 * (kk & 3));
+          const uint64_t bd = make_smem_desc_sw128(base + K_OFF + s * 2 * K_ATOM + (kk >> 2) * K_ATOM) + (uint64_t)(2 * (kk & 3));
+          umma_bf16(tmem_S, ad, bd, idesc_s, kk ? 1u : 0u);
         }
         umma_commit(s_full);
       };
@@ -131,11 +132,10 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         fence_after_sync();
         if (j + 1 < nb) issue_S(j + 1);
 #pragma unroll
-        for (int kk = 0; kk < 8; ++kk) {
-          const uint32_t off = (kk >> 2) * ATOM_BYTES;
-          const uint64_t ad = make_smem_desc_sw128(base + P_OFF + off) + (uint64_t)(2 * (kk & 3));
-          const uint64_t bd = make_smem_desc_sw128(base + V_OFF + s * TILE_BYTES + off) + (uint64_t)(2 * (kk & 3));
-          umma_bf16(tmem_O, ad, bd, idesc, (j | kk) ? 1u : 0u);
+        for (int kk = 0; kk < BKV / 16; ++kk) {
+          const uint64_t ad = make_smem_desc_sw128(base + P_OFF) + (uint64_t)(2 * kk);
+          const uint64_t bd = make_smem_desc_sw128(base + V_OFF + s * V_TILE) + (uint64_t)(2 * kk);
+          umma_bf16(tmem_O, ad, bd, idesc_o, (j | kk) ? 1u : 0u);
         }
         umma_commit(kv_empty0 + 8 * s);
         umma_commit(o_ready);
@@ -146,65 +146,57 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     const int q = warp & 3;
     const int row = q * 32 + lane;
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
-    uint8_t* p_row = smem + P_OFF + row * 128;  // + atom*ATOM_BYTES + swizzled 16-byte chunk
+    uint8_t* p_row = smem + P_OFF + row * 128;
     const int sw = row & 7;
     float m = -INFINITY, l = 0.f;
-    uint32_t v[32];
+    uint32_t v0[32], v1[32];
     for (int j = 0; j < nb; ++j) {
       mbar_wait(s_full, j & 1);
       fence_after_sync();
-      // pass A: block maximum of the scaled, masked scores
+      // the whole 64-key block of this row in registers: one TMEM pass
+      tmem_ld32(tmem_S + lane_off, v0);
+      tmem_ld32(tmem_S + lane_off + 32, v1);
+      tmem_wait_ld();
+      const int kbase = j * BKV;
       float bm = -INFINITY;
-      for (int c = 0; c < 4; ++c) {
-        __syncwarp();
-        tmem_ld32(tmem_S + lane_off + c * 32, v);
-        tmem_wait_ld();
-        const int kbase = j * BKV + c * 32;
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const float t = (kbase + i < len) ? __uint_as_float(v[i]) * scale_log2 : -INFINITY;
-          bm = fmaxf(bm, t);
-        }
+      for (int i = 0; i < 32; ++i) {
+        const float t0 = (kbase + i < len) ? __uint_as_float(v0[i]) * scale_log2 : -INFINITY;
+        const float t1 = (kbase + 32 + i < len) ? __uint_as_float(v1[i]) * scale_log2 : -INFINITY;
+        v0[i] = __float_as_uint(t0);
+        v1[i] = __float_as_uint(t1);
+        bm = fmaxf(bm, fmaxf(t0, t1));
       }
       const float m_new = fmaxf(m, bm);          // finite: every processed block holds >= 1 valid key
-      const float alpha = fast_exp2(m - m_new);  // 0 on the first block (m = -inf)
+      const float alpha = fast_exp2(m - m_new);  // 0 on the first block (m = -inf); exactly 1 when the max is unchanged
       if (j > 0) {                               // P buffer and O are free once P(j-1)V(j-1) has completed
         mbar_wait(o_ready, (j - 1) & 1);
         fence_after_sync();
       }
-      // pass B: P = exp2(t - m_new) -> bf16 swizzled smem tile; row sum
       float bsum = 0.f;
-      for (int c = 0; c < 4; ++c) {
-        __syncwarp();
-        tmem_ld32(tmem_S + lane_off + c * 32, v);
-        tmem_wait_ld();
-        const int kbase = j * BKV + c * 32;
-        float pv[32];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const float t = (kbase + i < len) ? __uint_as_float(v[i]) * scale_log2 : -INFINITY;
+      for (int u = 0; u < 8; ++u) {              // 8 x 16-byte chunks = 64 bf16 probabilities
+        float pv[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int k = u * 8 + i;
+          const float t = __uint_as_float(k < 32 ? v0[k] : v1[k - 32]);
           pv[i] = fast_exp2(t - m_new);
           bsum += pv[i];
         }
-        uint8_t* atom = p_row + (c >> 1) * ATOM_BYTES;
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int ch = ((c & 1) * 4 + u) ^ sw;
-          *reinterpret_cast<uint4*>(atom + ch * 16) =
-              make_uint4(pack_bf16x2(pv[u * 8], pv[u * 8 + 1]), pack_bf16x2(pv[u * 8 + 2], pv[u * 8 + 3]),
-                         pack_bf16x2(pv[u * 8 + 4], pv[u * 8 + 5]), pack_bf16x2(pv[u * 8 + 6], pv[u * 8 + 7]));
-        }
+        *reinterpret_cast<uint4*>(p_row + ((u ^ sw) << 4)) =
+            make_uint4(pack_bf16x2(pv[0], pv[1]), pack_bf16x2(pv[2], pv[3]), pack_bf16x2(pv[4], pv[5]), pack_bf16x2(pv[6], pv[7]));
       }
       l = l * alpha + bsum;
       m = m_new;
-      if (j > 0) {  // rescale the running output
+      // rescale the running output only when some row of the warp raised its maximum (warp-uniform branch)
+      if (j > 0 && __any_sync(0xffffffffu, alpha != 1.0f)) {
         for (int c = 0; c < 4; ++c) {
-          __syncwarp();
-          tmem_ld32(tmem_O + lane_off + c * 32, v);
+          tmem_ld32(tmem_O + lane_off + c * 32, v0);
           tmem_wait_ld();
 #pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
-          tmem_st32(tmem_O + lane_off + c * 32, v);
+          for (int i = 0; i < 32; ++i) v0[i] = __float_as_uint(__uint_as_float(v0[i]) * alpha);
+          tmem_st32(tmem_O + lane_off + c * 32, v0);
         }
         tmem_wait_st();
       }
@@ -216,22 +208,48 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     mbar_wait(o_ready, (nb - 1) & 1);
     fence_after_sync();
     const int p = p0 + row;
-    const bool writable = p < SA;
     const bool valid = p < len;
     const float inv = valid ? 1.0f / l : 0.f;
-    bf16* o = out_b + (row0 + (writable ? p : 0)) * 256 + h * DK;
-    for (int c = 0; c < 4; ++c) {
-      __syncwarp();
-      tmem_ld32(tmem_O + lane_off + c * 32, v);
-      tmem_wait_ld();
-      if (writable) {
+    const bool interior = p0 + BQ <= SA;       // the whole 128-row tile belongs to this utterance: TMA store
+    if (interior) {
+      // stage the [128 x 128] bf16 tile in the (now idle) Q buffers: two 128B-swizzled [128 x 64] atoms
+      for (int c = 0; c < 4; ++c) {
+        tmem_ld32(tmem_O + lane_off + c * 32, v0);
+        tmem_wait_ld();
+        uint8_t* o_row = smem + Q_OFF + (c >> 1) * Q_ATOM + row * 128;
 #pragma unroll
-        for (int i = 0; i < 32; i += 8) {
+        for (int u = 0; u < 4; ++u) {
           float y[8];
 #pragma unroll
-          for (int u = 0; u < 8; ++u) y[u] = valid ? __uint_as_float(v[i + u]) * inv : 0.f;
-          *reinterpret_cast<uint4*>(o + c * 32 + i) =
+          for (int i = 0; i < 8; ++i) y[i] = __uint_as_float(v0[u * 8 + i]) * inv;
+          *reinterpret_cast<uint4*>(o_row + ((((c & 1) * 4 + u) ^ sw) << 4)) =
               make_uint4(pack_bf16x2(y[0], y[1]), pack_bf16x2(y[2], y[3]), pack_bf16x2(y[4], y[5]), pack_bf16x2(y[6], y[7]));
+        }
+      }
+      fence_proxy_async();
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (threadIdx.x == 64) {
+        tma_store_2d(&tmO, base + Q_OFF, h * DK, (int)row0 + p0);
+        tma_store_2d(&tmO, base + Q_OFF + Q_ATOM, h * DK + 64, (int)row0 + p0);
+        tma_store_commit();
+        tma_store_wait_all();
+      }
+    } else {
+      const bool writable = p < SA;              // rows past SA belong to the next utterance
+      bf16* o = out_b + (row0 + (writable ? p : 0)) * 256 + h * DK;
+      for (int c = 0; c < 4; ++c) {
+        __syncwarp();
+        tmem_ld32(tmem_O + lane_off + c * 32, v0);
+        tmem_wait_ld();
+        if (writable) {
+#pragma unroll
+          for (int i = 0; i < 32; i += 8) {
+            float y[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) y[u] = __uint_as_float(v0[i + u]) * inv;
+            *reinterpret_cast<uint4*>(o + c * 32 + i) =
+                make_uint4(pack_bf16x2(y[0], y[1]), pack_bf16x2(y[2], y[3]), pack_bf16x2(y[4], y[5]), pack_bf16x2(y[6], y[7]));
+          }
         }
       }
     }
@@ -253,12 +271,12 @@ int tc_attention_launch(const bf16* q, const bf16* k, const bf16* vt, const RowL
   if (H != 2) return fs2_fail_cuda(cudaErrorInvalidValue, "tc_attention: built for H = 2, d_k = 128");
   if (!lay.off || !lay.ext || !lay.lens) return fs2_fail_cuda(cudaErrorInvalidValue, "tc_attention: row layout missing");
   const uint64_t R = (uint64_t)lay.R_cap;
-  CUtensorMap tmQ, tmK, tmV;
+  CUtensorMap tmQ, tmK, tmV, tmO;
   if (!tc::make_tmap_bf16(&tmQ, q, R, 256, 256, BQ) || !tc::make_tmap_bf16(&tmK, k, R, 256, 256, BKV) ||
-      !tc::make_tmap_bf16(&tmV, vt, 256, (uint64_t)Rv, (uint64_t)Rv, DK))
+      !tc::make_tmap_bf16(&tmV, vt, 256, (uint64_t)Rv, (uint64_t)Rv, DK) || !tc::make_tmap_bf16(&tmO, out_b, R, 256, 256, BQ))
     return fs2_fail_cuda(cudaErrorInvalidValue, "cuTensorMapEncodeTiled(attention)");
   static bool configured = false;
-  const int smem = SMEM_TOTAL + 1024;
+  const int smem = SMEM_TOTAL;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(tc_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return fs2_fail_cuda(e, "cudaFuncSetAttribute(tc_attention)");
@@ -266,7 +284,7 @@ int tc_attention_launch(const bf16* q, const bf16* k, const bf16* vt, const RowL
   }
   dim3 grid((FS2_ROWS_PER_UTT(lay.S, FS2_HALO) + BQ - 1) / BQ, H, lay.B);
   const float scale_log2 = (float)(1.4426950408889634 / sqrt((double)DK));
-  tc_attention_kernel<<<grid, ATT_THREADS, smem, st>>>(tmQ, tmK, tmV, lay, out_b, scale_log2);
+  tc_attention_kernel<<<grid, ATT_THREADS, smem, st>>>(tmQ, tmK, tmV, tmO, lay, out_b, scale_log2);
   ++g_fs2_launches;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fs2_fail_cuda(e, "tc_attention_kernel launch");
