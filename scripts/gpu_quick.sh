@@ -1,5 +1,6 @@
 #!/bin/bash
-# Short GPU visit: parity tests + bench lines (no ncu).  Usage: bash scripts/gpu_quick.sh <tag> [workloads...]
+# Short GPU visit: parity tests + bench lines + ncu launch lists (no full captures).
+# Usage: bash scripts/gpu_quick.sh <tag> [workloads...]
 TAG=${1:-q}; shift
 WLS=${@:-c2 c3}
 mkdir -p gpurun_out
@@ -16,4 +17,8 @@ try:
 except Exception as e:
     print("no bench line", e)
 PY
+  # launch list of the LAST forward only is selected afterwards by scripts/summarize_profiles.py (cold-cache, serialised)
+  timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv \
+    --log-file gpurun_out/launches_${wl}_${TAG}.csv python scripts/prof_step.py --workload $wl --warmup 1 --steps 1 > gpurun_out/ncu_list_${wl}.log 2>&1
+  echo "ncu list $wl exit=$?"; tail -n 2 gpurun_out/ncu_list_${wl}.log
 done

@@ -36,9 +36,14 @@ for path in sorted(glob.glob(os.path.join(GO, f"launches_*_{tag}.csv"))):
     hdr = rows[0]
     ki, vi, mi = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index("Metric Name")
     agg, tot = collections.OrderedDict(), 0.0
-    for r in rows[1:]:
-        if r[mi] != "gpu__time_duration.sum":
-            continue
+    body = [r for r in rows[1:] if r[mi] == "gpu__time_duration.sum"]
+    # keep the LAST forward only (the list also holds the weight-repacking launches and the warm-up forward)
+    wl = os.path.basename(path).split("_")[1]
+    logp = os.path.join(GO, f"ncu_list_{wl}.log")
+    m = re.search(r"launches/forward (\d+)", open(logp).read()) if os.path.exists(logp) else None
+    if m:
+        body = body[-int(m.group(1)):]
+    for r in body:
         name = re.sub(r"\(.*", "", r[ki]).replace("void ", "").replace("<unnamed>::", "")
         v = float(r[vi].replace(",", ""))
         a = agg.setdefault(name, [0, 0.0]); a[0] += 1; a[1] += v; tot += v
