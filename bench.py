@@ -194,7 +194,7 @@ def run_b200_arm(args):
     steps, warmup = max(1, args.steps), max(3, args.warmup)
     sd = synthetic.make_state_dict(0)
     model = synthetic.build_module(sd, synthetic.STATS_NAN_BINS, device=dev)
-    # tcgen05 everywhere: bf16x3 (3-term split operands, fp32-faithful) for the encoder + variance predictors, whose
+    # tcgen05 everywhere: f16x2 (2-term scaled fp16 split operands, fp32-faithful) for the encoder + variance predictors, whose
     # outputs are rounded to integer durations / bucket indices; plain bf16 for the decoder, mel linear and PostNet
     model.set_precision(args.enc, args.dec)
     synth = pkg.ShardedSynthesizer(model) if world > 1 else None
@@ -353,8 +353,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--enc", default="bf16x3", choices=["fp32", "bf16x3", "bf16"], help="encoder + predictor arithmetic")
-    ap.add_argument("--dec", default="bf16", choices=["fp32", "bf16x3", "bf16"], help="decoder + PostNet arithmetic")
+    ap.add_argument("--enc", default="f16x2", choices=["fp32", "bf16x3", "f16x2", "bf16"], help="encoder + predictor arithmetic")
+    ap.add_argument("--dec", default="bf16", choices=["fp32", "bf16x3", "f16x2", "bf16"], help="decoder + PostNet arithmetic")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

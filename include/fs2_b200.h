@@ -47,6 +47,9 @@ extern "C" {
 #define FS2_PREC_BF16 1 /* tcgen05 tensor-core kernels: bf16 operands, fp32 accumulate in TMEM */
 #define FS2_PREC_BF16X3 2 /* tcgen05, fp32-faithful: operands split into 3 bf16 terms, 6 cross products per MAC block
                              accumulated in fp32 (error ~2^-23 per product); attention stays fp32 FFMA */
+#define FS2_PREC_F16X2 3  /* tcgen05, fp32-faithful: operands carried as 2 power-of-two-scaled fp16 terms (22 significant
+                             bits), 3 cross products per MAC block -- half the tensor work of BF16X3 at the same error
+                             level as an fp32 FFMA GEMM; activations saturate at |x| = 4094; attention stays fp32 FFMA */
 
 typedef struct fs2_handle fs2_handle;
 
@@ -96,7 +99,7 @@ int fs2_load_weights(fs2_handle* h, const fs2_weight_desc* descs, int32_t n);
 
 /* encoder_prec covers txt_encoder + all three variance predictors (the discrete
  * decisions: durations, pitch/energy buckets); decoder_prec covers mel_decoder,
- * mel_linear and PostNet.  Defaults: BF16X3 / BF16. */
+ * mel_linear and PostNet.  Defaults: F16X2 / BF16. */
 int fs2_set_precision(fs2_handle* h, int32_t encoder_prec, int32_t decoder_prec);
 
 /* Row packing of the internal activation layout.  keep_rows = padded rows kept after each utterance's valid rows:

@@ -15,6 +15,7 @@ LIB_PATH = os.path.join(HERE, "libfs2_b200.so")
 PREC_FP32 = 0
 PREC_BF16 = 1
 PREC_BF16X3 = 2
+PREC_F16X2 = 3
 
 FS2_OK = 0
 ERR_NAMES = {-1: "FS2_ERR_INVALID", -2: "FS2_ERR_CUDA", -3: "FS2_ERR_STATE", -4: "FS2_ERR_UNSUPPORTED",

@@ -32,6 +32,8 @@ struct RawT {
 struct GemmW {
   float* wf = nullptr;  // [taps][K][N]
   bf16* wb = nullptr;   // [3][taps][N][K]: plane 0 = bf16(w), planes 1-2 = split residuals (bf16x3 mode)
+  bf16* wh = nullptr;   // [2][taps][N][K]: fp16 hi / lo terms of w * w_scale (f16x2 mode)
+  float w_scale = 1.f;  // power of two
   float* bias = nullptr;
   int N = 0, K = 0, taps = 1;
 };
@@ -207,6 +209,8 @@ int build_gemm(fs2_handle* h, GemmW& g, const std::vector<std::string>& wkeys, c
       HCHECK(cudaMemcpyAsync(g.bias + i * N_each, b, sizeof(float) * N_each, cudaMemcpyDeviceToDevice, st));
     }
   }
+  RCHECK(dev_alloc(h, &g.wh, (size_t)2 * taps * K * g.N));
+  HCHECK(rowops_pack_weight_f16x2(g.wf, g.N, K, taps, g.wh, &g.w_scale, st));
   return FS2_OK;
 }
 
@@ -277,12 +281,15 @@ int position_table(fs2_handle* h, int stack, int S, const float** out, cudaStrea
   return FS2_OK;
 }
 
-inline int planes_of(int prec) { return prec == FS2_PREC_BF16X3 ? 3 : prec == FS2_PREC_BF16 ? 1 : 0; }
+inline int planes_of(int prec) {
+  return prec == FS2_PREC_BF16X3 ? 3 : prec == FS2_PREC_F16X2 ? 2 : prec == FS2_PREC_BF16 ? 1 : 0;
+}
+inline bool is_split(int prec) { return prec == FS2_PREC_BF16X3 || prec == FS2_PREC_F16X2; }
 
 // bf16 shadow of an fp32 activation tensor for a tensor-core consumer of precision `prec` (no-op for fp32 consumers)
 cudaError_t make_shadow(const float* x, size_t n, int prec, bf16* xb, cudaStream_t st) {
   if (prec == FS2_PREC_BF16) return rowops_f32_to_bf16(x, (int64_t)n, xb, st);
-  if (prec == FS2_PREC_BF16X3) return rowops_split3(x, (int64_t)n, xb, (int64_t)n, st);
+  if (is_split(prec)) return rowops_split(x, (int64_t)n, planes_of(prec), xb, (int64_t)n, st);
   return cudaSuccess;
 }
 
@@ -322,7 +329,9 @@ ConvGemmArgs base_args(const GemmW& w, const RowLayout& lay) {
   ConvGemmArgs a;
   memset(&a, 0, sizeof a);
   a.K = w.K; a.N = w.N; a.taps = w.taps;
-  a.Wf = w.wf; a.Wb = w.wb; a.bias = w.bias;
+  a.Wf = w.wf; a.Wb = w.wb; a.Wh = w.wh; a.bias = w.bias;
+  a.acc_scale = 1.f;
+  a.acc_scale_f16x2 = 1.f / (FS2_F16X2_ACT_SCALE * w.w_scale);
   a.lay = lay;
   return a;
 }
@@ -335,7 +344,9 @@ int run_gemm(fs2_handle* h, int prec, const ConvGemmArgs& a, cudaStream_t st, co
     return FS2_OK;
   }
   ConvGemmArgs b = a;
-  b.planes = prec == FS2_PREC_BF16X3 ? 3 : 1;
+  b.planes = planes_of(prec);
+  b.acc_scale = 1.f;
+  if (prec == FS2_PREC_F16X2) { b.Wb = a.Wh; b.acc_scale = a.acc_scale_f16x2; }
   if (b.out_planes == 0) b.out_planes = b.planes;
   int rc = tc_conv_gemm_launch(b, st);
   if (rc != FS2_OK && h) h->err = g_last_error;
@@ -377,13 +388,15 @@ int run_fft_stack(fs2_handle* h, std::vector<FftW>& Ls, int l0, int l1, int prec
     }
     return FS2_OK;
   }
-  if (prec == FS2_PREC_BF16X3) {
-    // fp32-faithful tensor-core path: bf16x3 GEMMs (xb, yb, attb, hidb hold 3 planes), fp32 FFMA attention
+  if (is_split(prec)) {
+    // fp32-faithful tensor-core path: split-operand GEMMs (xb, yb, attb, hidb hold 3 bf16 or 2 fp16 planes), fp32 FFMA
+    // attention
+    const size_t np = (size_t)planes_of(prec);
     WS(float, qkv, "fft.qkv", R * 3 * D);
     WS(float, att, "fft.att", R * D);
-    WS(bf16, yb3, "fft.yb3", 3 * R * D);
-    WS(bf16, attb3, "fft.attb3", 3 * R * D);
-    WS(bf16, hidb3, "fft.hidb3", 3 * R * F);
+    WS(bf16, yb3, "fft.yb3", np * R * D);
+    WS(bf16, attb3, "fft.attb3", np * R * D);
+    WS(bf16, hidb3, "fft.hidb3", np * R * F);
     for (int l = l0; l < l1; ++l) {
       FftW& L = Ls[l];
       ConvGemmArgs a = base_args(L.qkv, lay);
@@ -392,7 +405,7 @@ int run_fft_stack(fs2_handle* h, std::vector<FftW>& Ls, int l0, int l1, int prec
       {
         PROF(tg + "attn");
         HCHECK(simt_attention_launch(qkv, 3 * D, 0, D, 2 * D, lay, H, dk, att, D, st));
-        HCHECK(rowops_split3(att, (int64_t)(R * D), attb3, (int64_t)(R * D), st));
+        HCHECK(rowops_split(att, (int64_t)(R * D), (int)np, attb3, (int64_t)(R * D), st));
       }
       a = base_args(L.fc, lay);
       a.Ab = attb3; a.epi = EPI_RES_LN; a.mask_mode = MASK_LEN; a.residual = x; a.ln_g = L.ln1_g; a.ln_b = L.ln1_b;
@@ -451,7 +464,7 @@ int run_predictor(fs2_handle* h, PredW& P, int prec, const float* x, const bf16*
   WS(float, p1, "pred.h1", R * C);
   bf16* p1b = nullptr;
   if (prec != FS2_PREC_FP32) {
-    WS(bf16, t, "pred.h1b", (prec == FS2_PREC_BF16X3 ? 3 : 1) * R * C);
+    WS(bf16, t, "pred.h1b", (size_t)planes_of(prec) * R * C);
     p1b = t;
   }
   HCHECK(cudaMemsetAsync(out_user, 0, sizeof(float) * (size_t)lay.B * lay.S, st));
@@ -583,8 +596,8 @@ void fs2_destroy(fs2_handle* h) {
 
 int fs2_set_precision(fs2_handle* h, int32_t enc, int32_t dec) {
   if (!h) return FS2_ERR_INVALID;
-  if (enc < FS2_PREC_FP32 || enc > FS2_PREC_BF16X3 || dec < FS2_PREC_FP32 || dec > FS2_PREC_BF16X3)
-    return h->fail(FS2_ERR_INVALID, "precision must be FS2_PREC_FP32, FS2_PREC_BF16 or FS2_PREC_BF16X3");
+  if (enc < FS2_PREC_FP32 || enc > FS2_PREC_F16X2 || dec < FS2_PREC_FP32 || dec > FS2_PREC_F16X2)
+    return h->fail(FS2_ERR_INVALID, "precision must be FS2_PREC_FP32, FS2_PREC_BF16, FS2_PREC_BF16X3 or FS2_PREC_F16X2");
   h->prec_enc = enc;
   h->prec_dec = dec;
   return FS2_OK;
@@ -927,7 +940,7 @@ int fs2_op_fft_stack(fs2_handle* h, int32_t stack, int32_t l0, int32_t l1, int32
   if (!h || !h->loaded) return FS2_ERR_STATE;
   std::vector<FftW>& Ls = stack == 0 ? h->enc : h->dec;
   if (!x || !lens || !out || B <= 0 || S <= 0 || l0 < 0 || l1 > (int)Ls.size() || l0 > l1 ||
-      prec < FS2_PREC_FP32 || prec > FS2_PREC_BF16X3)
+      prec < FS2_PREC_FP32 || prec > FS2_PREC_F16X2)
     return h->fail(FS2_ERR_INVALID, "bad argument");
   HCHECK(cudaSetDevice(h->device));
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
@@ -985,7 +998,7 @@ int fs2_op_variance_embed(fs2_handle* h, int32_t which, float* pred, float contr
 int fs2_op_mel_postnet(fs2_handle* h, int32_t prec, const float* dec, int32_t B, int32_t T, float* mel, float* mel_post,
                        void* stream) {
   if (!h || !h->loaded) return FS2_ERR_STATE;
-  if (!dec || !mel || !mel_post || B <= 0 || T <= 0 || prec < FS2_PREC_FP32 || prec > FS2_PREC_BF16X3)
+  if (!dec || !mel || !mel_post || B <= 0 || T <= 0 || prec < FS2_PREC_FP32 || prec > FS2_PREC_F16X2)
     return h->fail(FS2_ERR_INVALID, "bad argument");
   HCHECK(cudaSetDevice(h->device));
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
@@ -1004,12 +1017,12 @@ int fs2_op_mel_postnet(fs2_handle* h, int32_t prec, const float* dec, int32_t B,
 int fs2_op_conv_gemm(int32_t prec, const float* A, const float* W, const float* bias, int32_t B, int32_t S, int32_t K,
                      int32_t N, int32_t taps, int32_t act, float* out, void* stream) {
   if (!A || !W || !bias || !out || B <= 0 || S <= 0 || K <= 0 || N <= 0 || taps < 1 || taps > 2 * FS2_HALO + 1 ||
-      taps % 2 == 0 || K % 16 || N % 4 || act < 0 || act > 2 || prec < FS2_PREC_FP32 || prec > FS2_PREC_BF16X3 ||
+      taps % 2 == 0 || K % 16 || N % 4 || act < 0 || act > 2 || prec < FS2_PREC_FP32 || prec > FS2_PREC_F16X2 ||
       B > 65535 || S > FS2_MAX_ROWS_PER_UTT) {
     g_last_error = "bad argument"; return FS2_ERR_INVALID; }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   float *Ag = nullptr, *Wf = nullptr, *Og = nullptr;
-  bf16 *Ab = nullptr, *Wb = nullptr;
+  bf16 *Ab = nullptr, *Wb = nullptr, *Wh = nullptr;
   int rc = FS2_OK;
   cudaError_t e = cudaSuccess;
   TmpLayout tl;
@@ -1024,16 +1037,20 @@ int fs2_op_conv_gemm(int32_t prec, const float* A, const float* W, const float* 
     if ((e = rowops_to_grid(A, tl.lay, K, Ag, K, 0, nullptr, st)) != cudaSuccess) break;
     if ((e = make_shadow(Ag, R * K, prec, Ab, st)) != cudaSuccess) break;
     if ((e = rowops_pack_weight(W, N, K, taps, nullptr, Wf, Wb, N, 0, st)) != cudaSuccess) break;
+    float w_scale = 1.f;
+    if ((e = cudaMalloc(reinterpret_cast<void**>(&Wh), sizeof(bf16) * 2 * (size_t)N * K * taps)) != cudaSuccess) break;
+    if ((e = rowops_pack_weight_f16x2(Wf, N, K, taps, Wh, &w_scale, st)) != cudaSuccess) break;
     ConvGemmArgs a;
     memset(&a, 0, sizeof a);
-    a.A = Ag; a.Ab = Ab; a.K = K; a.Wf = Wf; a.Wb = Wb; a.bias = bias; a.N = N; a.taps = taps;
+    a.A = Ag; a.Ab = Ab; a.K = K; a.Wf = Wf; a.Wb = Wb; a.Wh = Wh; a.bias = bias; a.N = N; a.taps = taps;
+    a.acc_scale = 1.f; a.acc_scale_f16x2 = 1.f / (FS2_F16X2_ACT_SCALE * w_scale);
     a.lay = tl.lay; a.epi = act == 0 ? EPI_BIAS : act == 1 ? EPI_RELU : EPI_TANH; a.mask_mode = MASK_GRID;
     a.out = Og; a.ldo = N; a.out_user = out; a.ldu = N;
     rc = run_gemm(nullptr, prec, a, st);
     if (rc != FS2_OK) break;
     e = cudaStreamSynchronize(st);
   } while (0);
-  cudaFree(Ag); cudaFree(Ab); cudaFree(Wf); cudaFree(Wb); cudaFree(Og);
+  cudaFree(Ag); cudaFree(Ab); cudaFree(Wf); cudaFree(Wb); cudaFree(Wh); cudaFree(Og);
   if (e != cudaSuccess) return fs2_fail_cuda(e, "fs2_op_conv_gemm");
   return rc;
 }

@@ -24,6 +24,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 
 #define FS2_HALO 4
@@ -33,6 +34,14 @@
 #define FS2_ROWS_PER_UTT(S, halo_rows) ((halo_rows) > 0 ? (((S) + (halo_rows) + FS2_ROW_ALIGN - 1) / FS2_ROW_ALIGN) * FS2_ROW_ALIGN : (S))
 
 typedef __nv_bfloat16 bf16;
+
+// f16x2 operand mode (planes == 2): an fp32 value x is carried as two fp16 terms of x * 2^k, hi = fp16(x 2^k) and
+// lo = fp16(x 2^k - hi): 22 significant bits, 3 cross products (hi*hi, hi*lo, lo*hi) per MAC block instead of the six
+// of the bf16x3 split.  The power-of-two pre-scale keeps the lo term in fp16's NORMAL range for every value that
+// matters (|x 2^k| >= 2^-3); it is undone exactly in the GEMM epilogue (ConvGemmArgs::acc_scale).  Activations use
+// the fixed k = 4 (|x| up to 4094 before saturation); each weight tensor picks its own k at load time.
+// The 16-bit patterns live in the same bf16-typed plane buffers as the other modes.
+#define FS2_F16X2_ACT_SCALE 16.0f
 
 enum Fs2Epi : int {
   EPI_BIAS = 0,         // out = acc + bias
@@ -68,12 +77,16 @@ struct ConvGemmArgs {
   const bf16* Ab;   // tcgen05 path: [planes][R][K]
   int K;
   // tcgen05 path: 1 = plain bf16 operands; 3 = bf16x3 split operands (hi, mid, lo planes of A and W): the six
-  // significant cross products are accumulated in fp32, which reproduces an fp32 GEMM to ~2^-23 per product
+  // significant cross products are accumulated in fp32, which reproduces an fp32 GEMM to ~2^-23 per product;
+  // 2 = f16x2 split operands (scaled fp16 hi / lo planes, 3 cross products, see FS2_F16X2_ACT_SCALE)
   int planes;
-  int out_planes;   // planes written to out_b (1, or 3 = split the fp32 result for a following bf16x3 GEMM)
+  int out_planes;   // planes written to out_b (1; 3 / 2 = split the fp32 result for a following bf16x3 / f16x2 GEMM)
   // W operand, per tap
   const float* Wf;  // [taps][K][N]   (SIMT fp32 kernel; n contiguous)
   const bf16* Wb;   // [planes][taps][N][K]   (tcgen05 kernel; K-major B operand)
+  const bf16* Wh;   // [2][taps][N][K] fp16 bit patterns of W * w_scale, hi / lo terms (f16x2 mode)
+  float acc_scale;  // multiplies the accumulator before the bias: 1, or 1 / (FS2_F16X2_ACT_SCALE * w_scale) in f16x2 mode
+  float acc_scale_f16x2;  // the f16x2 value for this weight (run_gemm copies it into acc_scale when that mode is used)
   const float* bias;
   int N, taps;
   // rows
@@ -111,6 +124,25 @@ __device__ __forceinline__ RowPos row_pos(const RowLayout& lay, int r, int R) {
   rp.b = rp.in_grid ? (int)(code >> 16) : 0;
   rp.p = rp.in_grid ? (int)(code & 0xFFFFu) : 0;
   return rp;
+}
+
+// fp32 -> (hi, lo) fp16 bit patterns of y * FS2_F16X2_ACT_SCALE, saturating (never inf)
+__device__ __forceinline__ uint16_t f32_to_f16_sat_bits(float v) {
+  uint16_t h;
+  asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(h) : "f"(v));
+  return h;
+}
+__device__ __forceinline__ void split2h_scaled(float ys, uint16_t& hi, uint16_t& lo) {   // ys already scaled
+  hi = f32_to_f16_sat_bits(ys);
+  lo = f32_to_f16_sat_bits(ys - __half2float(__ushort_as_half(hi)));
+}
+// two values -> packed hi word and packed lo word
+__device__ __forceinline__ void split2h_pair(float a, float b, uint32_t& hi2, uint32_t& lo2) {
+  uint16_t ha, la, hb, lb;
+  split2h_scaled(a * FS2_F16X2_ACT_SCALE, ha, la);
+  split2h_scaled(b * FS2_F16X2_ACT_SCALE, hb, lb);
+  hi2 = (uint32_t)ha | ((uint32_t)hb << 16);
+  lo2 = (uint32_t)la | ((uint32_t)lb << 16);
 }
 
 #define FS2_CUDA_CHECK(expr)                                  \
@@ -163,8 +195,11 @@ cudaError_t rowops_from_grid(const float* x_grid, const RowLayout& lay, int C, f
 // dst_b: [3][taps][n_total][K] -- plane 0 doubles as the plain bf16 weight, planes 1..2 are the split residuals
 cudaError_t rowops_pack_weight(const float* src, int N, int K, int taps, const float* scale, float* dst_f,
                                bf16* dst_b, int n_total, int n_off, cudaStream_t st);
-// fp32 -> bf16x3 planes: dst[p][i], plane stride = plane_elems
-cudaError_t rowops_split3(const float* src, int64_t n, bf16* dst, int64_t plane_elems, cudaStream_t st);
+// fp32 -> operand planes (3: bf16x3, 2: f16x2, 1: bf16): dst[p][i], plane stride = plane_elems
+cudaError_t rowops_split(const float* src, int64_t n, int planes, bf16* dst, int64_t plane_elems, cudaStream_t st);
+// f16x2 weight planes from the packed fp32 weight wf [taps][K][N]: returns the power-of-two scale chosen for the
+// tensor (max |w| * scale in [8192, 16384)) through *w_scale_out (host); dst [2][taps][N][K]
+cudaError_t rowops_pack_weight_f16x2(const float* wf, int N, int K, int taps, bf16* dst, float* w_scale_out, cudaStream_t st);
 cudaError_t rowops_bn_fold(const float* conv_bias, const float* g, const float* b, const float* mean,
                            const float* var, int n, float eps, float* scale_out, float* bias_out, cudaStream_t st);
 cudaError_t rowops_f32_to_bf16(const float* src, int64_t n, bf16* dst, cudaStream_t st);

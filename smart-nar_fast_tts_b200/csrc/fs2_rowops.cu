@@ -5,6 +5,7 @@
 // durations / centres), so there is no shared-memory tiling of the payload.
 #include "fs2_common.cuh"
 #include <math.h>
+#include <string.h>
 
 long long g_fs2_launches = 0;
 
@@ -23,10 +24,18 @@ __device__ __forceinline__ void split3f(float y, float& hi, float& mid, float& l
   mid = __bfloat162float(__float2bfloat16_rn(r1));
   lo = r1 - mid;
 }
-// write 4 consecutive values as bf16 into `planes` planes (1: rounded; 3: hi/mid/lo split)
+// write 4 consecutive values into `planes` operand planes (1: bf16 rounded; 3: bf16 hi/mid/lo split; 2: scaled fp16 hi/lo)
 __device__ __forceinline__ void store_planes4(bf16* dst, size_t plane_elems, int planes, float4 a) {
   if (planes == 1) {
     *reinterpret_cast<uint2*>(dst) = make_uint2(pack2(a.x, a.y), pack2(a.z, a.w));
+    return;
+  }
+  if (planes == 2) {
+    uint32_t h0, l0, h1, l1;
+    split2h_pair(a.x, a.y, h0, l0);
+    split2h_pair(a.z, a.w, h1, l1);
+    *reinterpret_cast<uint2*>(dst) = make_uint2(h0, h1);
+    *reinterpret_cast<uint2*>(dst + plane_elems) = make_uint2(l0, l1);
     return;
   }
   float h[4], m[4], l[4];
@@ -450,9 +459,34 @@ __global__ void bn_fold_kernel(const float* __restrict__ conv_bias, const float*
   bias_out[i] = (conv_bias[i] - mean[i]) * s + b[i];
 }
 
-__global__ void split3_kernel(const float* __restrict__ src, int64_t n4, bf16* __restrict__ dst, int64_t plane_elems) {
+__global__ void split_kernel(const float* __restrict__ src, int64_t n4, int planes, bf16* __restrict__ dst, int64_t plane_elems) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n4) store_planes4(dst + i * 4, (size_t)plane_elems, 3, ld4(src + i * 4));
+  if (i < n4) store_planes4(dst + i * 4, (size_t)plane_elems, planes, ld4(src + i * 4));
+}
+
+// max |w| of a tensor as the bit pattern of a non-negative float (monotonic as unsigned)
+__global__ void absmax_kernel(const float* __restrict__ w, size_t n, unsigned* __restrict__ out) {
+  float m = 0.f;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const float v = fabsf(w[i]);
+    if (v == v && v <= 3.0e38f) m = fmaxf(m, v);
+  }
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) atomicMax(out, __float_as_uint(m));
+}
+
+// wf [taps][K][N] fp32 -> dst [2][taps][N][K] fp16 bit patterns of (w * scale): hi, lo
+__global__ void pack_weight_f16x2_kernel(const float* __restrict__ wf, int N, int K, int taps, float scale, bf16* __restrict__ dst) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;   // index into dst plane: ((t*N + n)*K + k)
+  const size_t plane = (size_t)taps * N * K;
+  if (i >= plane) return;
+  const int k = (int)(i % K);
+  const int n = (int)((i / K) % N);
+  const int t = (int)(i / ((size_t)K * N));
+  uint16_t hi, lo;
+  split2h_scaled(wf[((size_t)t * K + k) * N + n] * scale, hi, lo);
+  reinterpret_cast<uint16_t*>(dst)[i] = hi;
+  reinterpret_cast<uint16_t*>(dst)[plane + i] = lo;
 }
 
 __global__ void f32_to_bf16_kernel(const float* __restrict__ src, int64_t n, bf16* __restrict__ dst) {
@@ -555,10 +589,43 @@ cudaError_t rowops_fill_padded_rows(const float* bias, int N, const RowLayout& l
   fill_padded_rows_kernel<<<grid, 256, 0, st>>>(bias, N, lay, dst_SA, out_grid, out_b, out_planes, out_user);
   return LAUNCHED();
 }
-cudaError_t rowops_split3(const float* src, int64_t n, bf16* dst, int64_t plane_elems, cudaStream_t st) {
+cudaError_t rowops_pack_weight_f16x2(const float* wf, int N, int K, int taps, bf16* dst, float* w_scale_out, cudaStream_t st) {
+  const size_t n = (size_t)N * K * taps;
+  if (n == 0) return cudaSuccess;
+  unsigned* d_max = nullptr;
+  cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&d_max), sizeof(unsigned));
+  if (e != cudaSuccess) return e;
+  unsigned bits = 0;
+  e = cudaMemsetAsync(d_max, 0, sizeof(unsigned), st);
+  if (e == cudaSuccess) {
+    const int blocks = (int)(blocks_for(n, 256) < 1024 ? blocks_for(n, 256) : 1024);
+    absmax_kernel<<<blocks, 256, 0, st>>>(wf, n, d_max);
+    ++g_fs2_launches;
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaMemcpyAsync(&bits, d_max, sizeof(unsigned), cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  cudaFree(d_max);
+  if (e != cudaSuccess) return e;
+  float mx;
+  memcpy(&mx, &bits, sizeof mx);
+  // largest power of two with max|w| * scale < 16384 (fp16 max is 65504: 4x head-room), clamped to a sane range
+  int ex = 0;
+  if (mx > 0.f) {
+    (void)frexpf(mx, &ex);          // mx = m * 2^ex, m in [0.5, 1)
+    ex = 14 - ex;
+  }
+  if (ex > 24) ex = 24;
+  if (ex < -24) ex = -24;
+  const float scale = ldexpf(1.0f, ex);
+  *w_scale_out = scale;
+  pack_weight_f16x2_kernel<<<blocks_for(n, 256), 256, 0, st>>>(wf, N, K, taps, scale, dst);
+  return LAUNCHED();
+}
+cudaError_t rowops_split(const float* src, int64_t n, int planes, bf16* dst, int64_t plane_elems, cudaStream_t st) {
   if (n <= 0) return cudaSuccess;
   if (n % 4) return cudaErrorInvalidValue;
-  split3_kernel<<<blocks_for((size_t)(n / 4), 256), 256, 0, st>>>(src, n / 4, dst, plane_elems);
+  split_kernel<<<blocks_for((size_t)(n / 4), 256), 256, 0, st>>>(src, n / 4, planes, dst, plane_elems);
   return LAUNCHED();
 }
 cudaError_t rowops_gaussian_upsample(const float* x, const float* d, int B, int L, int D, int T, int T_w, float* out,

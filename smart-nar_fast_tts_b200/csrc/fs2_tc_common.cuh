@@ -152,14 +152,15 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t smem_addr) {
   d |= (uint64_t)2 << 61;                            // [61,64) SWIZZLE_128B
   return d;
 }
-// Instruction descriptor, kind::f16: D fp32, A/B bf16, both K-major, M x N tile.
-__host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
+// Instruction descriptor, kind::f16: D fp32, A/B bf16 (format 1) or fp16 (format 0), both K-major, M x N tile.
+__host__ __device__ constexpr uint32_t make_idesc_f16kind(int M, int N, uint32_t ab_format) {
   return (1u << 4)                    // [4,6)   D format: 1 = F32
-         | (1u << 7)                  // [7,10)  A format: 1 = BF16
-         | (1u << 10)                 // [10,13) B format: 1 = BF16
+         | (ab_format << 7)           // [7,10)  A format: 0 = F16, 1 = BF16
+         | (ab_format << 10)          // [10,13) B format
          | ((uint32_t)(N >> 3) << 17) // [17,23) N >> 3
          | ((uint32_t)(M >> 4) << 24);// [24,29) M >> 4
 }
+__host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) { return make_idesc_f16kind(M, N, 1u); }
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
   __nv_bfloat162 v = __floats2bfloat162_rn(a, b);

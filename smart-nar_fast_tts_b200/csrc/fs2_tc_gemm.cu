@@ -57,9 +57,24 @@ struct RowInfo {
 // (K/16 steps) truncates at full magnitude.  Measured: with hi*hi first the error was 6x larger (profiles/r1b notes).
 __constant__ int c_combo_a[6] = {0, 2, 1, 0, 1, 0};
 __constant__ int c_combo_b[6] = {2, 0, 1, 1, 0, 0};
+// f16x2 split (planes == 2): hi*lo, lo*hi, then hi*hi -- same smallest-first rule
+__constant__ int c_combo2_a[3] = {0, 1, 0};
+__constant__ int c_combo2_b[3] = {1, 0, 0};
 
 // 32 consecutive outputs of one row -> bf16 (1 plane: rounded; 3 planes: hi/mid/lo split), 16-byte stores
 __device__ __forceinline__ void store_bf16_chunk(bf16* o, size_t plane_elems, int planes, const float (&y)[32], int nb, int N) {
+  if (planes == 2) {
+#pragma unroll
+    for (int j = 0; j < 32; j += 8) {
+      if (nb + j >= N) continue;
+      uint32_t h[4], l[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) split2h_pair(y[j + 2 * u], y[j + 2 * u + 1], h[u], l[u]);
+      *reinterpret_cast<uint4*>(o + j) = make_uint4(h[0], h[1], h[2], h[3]);
+      *reinterpret_cast<uint4*>(o + plane_elems + j) = make_uint4(l[0], l[1], l[2], l[3]);
+    }
+    return;
+  }
   if (planes != 3) {
 #pragma unroll
     for (int j = 0; j < 32; j += 8)
@@ -104,8 +119,9 @@ tc_conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int pad = (a.taps - 1) / 2;
   const int KB = (a.K + BKE - 1) / BKE;
-  const int ncombo = a.planes == 3 ? 6 : 1;
+  const int ncombo = a.planes == 3 ? 6 : a.planes == 2 ? 3 : 1;
   const int iters = a.taps * KB;
+  const float asc = a.acc_scale;
   const int R = __ldg(a.lay.off + a.lay.B);          // rows in use: device data (ragged layout)
   const int num_tiles = ((R + BM - 1) / BM) * num_n_blocks;
   constexpr uint32_t TMEM_COLS = 2 * BN;  // 512 or 256: power of two
@@ -143,7 +159,8 @@ tc_conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const int m_blk = tile / num_n_blocks, n_blk = tile - m_blk * num_n_blocks;
         const int r0 = m_blk * BM, n0 = n_blk * BN;
         for (int c = 0; c < ncombo; ++c) {
-          const int pa = ncombo == 1 ? 0 : c_combo_a[c], pb = ncombo == 1 ? 0 : c_combo_b[c];
+          const int pa = ncombo == 1 ? 0 : ncombo == 3 ? c_combo2_a[c] : c_combo_a[c];
+          const int pb = ncombo == 1 ? 0 : ncombo == 3 ? c_combo2_b[c] : c_combo_b[c];
           for (int it = 0; it < iters; ++it) {
             const int t = it / KB, k0 = (it - t * KB) * BKE;
             mbar_wait(empty_bar(stage), phase ^ 1u);
@@ -159,7 +176,7 @@ tc_conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   } else if (warp == 1) {
     // ===================================================== MMA issuer
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(BM, BN);
+      const uint32_t idesc = make_idesc_f16kind(BM, BN, a.planes == 2 ? 0u : 1u);
       int stage = 0; uint32_t phase = 0;
       int as = 0; uint32_t aphase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -230,7 +247,7 @@ tc_conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             const float rr[4] = {rv.x, rv.y, rv.z, rv.w};
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-              float x = __uint_as_float(v[j + u]) + s_bias[c * 32 + j + u] + rr[u];
+              float x = fmaf(__uint_as_float(v[j + u]), asc, s_bias[c * 32 + j + u]) + rr[u];
               if (a.epi != EPI_RES_LN) x = fmaxf(x, 0.f);
               sum += x;
               sq = fmaf(x, x, sq);
@@ -276,7 +293,7 @@ tc_conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           tmem_wait_ld();
           float y[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) y[j] = ri.in_grid ? __uint_as_float(v[j]) + s_bias[c * 32 + j] : 0.f;
+          for (int j = 0; j < 32; ++j) y[j] = ri.in_grid ? fmaf(__uint_as_float(v[j]), asc, s_bias[c * 32 + j]) : 0.f;
           if (ri.in_buf && n_blk < 2) {
             bf16* o = (n_blk == 0 ? a.q_b : a.k_b) + (size_t)ri.r * 256 + c * 32;
 #pragma unroll
@@ -299,7 +316,7 @@ tc_conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           float y[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
-            float x = __uint_as_float(v[j]) + s_bias[c * 32 + j];
+            float x = fmaf(__uint_as_float(v[j]), asc, s_bias[c * 32 + j]);
             if (a.epi == EPI_RELU) x = fmaxf(x, 0.f);
             if (a.epi == EPI_TANH) x = tanhf(x);
             y[j] = x;
@@ -359,7 +376,7 @@ int launch(const ConvGemmArgs& a, cudaStream_t st) {
   const int num_m_blocks = (R + BM - 1) / BM;
   const int num_n_blocks = (a.N + BN - 1) / BN;
   CUtensorMap tmA, tmB;
-  const int planes = a.planes == 3 ? 3 : 1;
+  const int planes = a.planes == 3 ? 3 : a.planes == 2 ? 2 : 1;
   if (!make_tmap_bf16_3d(&tmA, a.Ab, (uint64_t)planes, (uint64_t)R, (uint64_t)a.K, (uint64_t)a.K, (uint64_t)R * a.K, BM))
     return fs2_fail_cuda(cudaErrorInvalidValue, "cuTensorMapEncodeTiled(A)");
   if (!make_tmap_bf16(&tmB, a.Wb, (uint64_t)planes * a.taps * a.N, (uint64_t)a.K, (uint64_t)a.K, BN))
@@ -393,8 +410,8 @@ int tc_conv_gemm_launch(const ConvGemmArgs& a, cudaStream_t st) {
   if (R <= 0) return FS2_OK;
   if (!a.lay.off || !a.lay.rowmap) return fs2_fail_cuda(cudaErrorInvalidValue, "tc_conv_gemm: row layout missing");
   if (!a.Ab || !a.Wb || a.K % 8 != 0 || a.N % 8 != 0) return fs2_fail_cuda(cudaErrorInvalidValue, "tc_conv_gemm: operands");
-  if ((a.planes != 0 && a.planes != 1 && a.planes != 3) || (a.out_planes != 0 && a.out_planes != 1 && a.out_planes != 3))
-    return fs2_fail_cuda(cudaErrorInvalidValue, "tc_conv_gemm: planes must be 1 or 3");
+  if (a.planes < 0 || a.planes > 3 || a.out_planes < 0 || a.out_planes > 3)
+    return fs2_fail_cuda(cudaErrorInvalidValue, "tc_conv_gemm: planes must be 1, 2 or 3");
   const bool ln = (a.epi == EPI_RES_LN || a.epi == EPI_RELU_LN || a.epi == EPI_RELU_LN_DOT);
   if (ln && a.N != 256) return fs2_fail_cuda(cudaErrorInvalidValue, "tc_conv_gemm: LayerNorm epilogue needs N == 256");
   if (a.epi == EPI_QKV && a.N != 768) return fs2_fail_cuda(cudaErrorInvalidValue, "tc_conv_gemm: QKV epilogue needs N == 768");

@@ -35,6 +35,8 @@ constexpr uint32_t TMEM_COLS = 2 * BN;
 
 __constant__ int s_combo_a[6] = {0, 2, 1, 0, 1, 0};       // bf16x3 cross products, smallest first (see fs2_tc_gemm.cu)
 __constant__ int s_combo_b[6] = {2, 0, 1, 1, 0, 0};
+__constant__ int s_combo2_a[3] = {0, 1, 0};               // f16x2 cross products (hi*lo, lo*hi, hi*hi)
+__constant__ int s_combo2_b[3] = {1, 0, 0};
 
 __device__ __forceinline__ void bar_epi() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
@@ -61,8 +63,9 @@ tc_conv_gemm_staged_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int pad = (a.taps - 1) / 2;
   const int KB = (a.K + BKE - 1) / BKE;
-  const int ncombo = a.planes == 3 ? 6 : 1;
+  const int ncombo = a.planes == 3 ? 6 : a.planes == 2 ? 3 : 1;
   const int iters = a.taps * KB;
+  const float asc = a.acc_scale;
   const int R = __ldg(a.lay.off + a.lay.B);
   const int num_tiles = ((R + BM - 1) / BM) * num_n_blocks;
   const bool ln = (a.epi == EPI_RES_LN || a.epi == EPI_RELU_LN);
@@ -98,7 +101,8 @@ tc_conv_gemm_staged_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
         const int m_blk = tile / num_n_blocks, n_blk = tile - m_blk * num_n_blocks;
         const int r0 = m_blk * BM, n0 = n_blk * BN;
         for (int c = 0; c < ncombo; ++c) {
-          const int pa = ncombo == 1 ? 0 : s_combo_a[c], pb = ncombo == 1 ? 0 : s_combo_b[c];
+          const int pa = ncombo == 1 ? 0 : ncombo == 3 ? s_combo2_a[c] : s_combo_a[c];
+          const int pb = ncombo == 1 ? 0 : ncombo == 3 ? s_combo2_b[c] : s_combo_b[c];
           for (int it = 0; it < iters; ++it) {
             const int t = it / KB, k0 = (it - t * KB) * BKE;
             mbar_wait(empty_bar(stage), phase ^ 1u);
@@ -114,7 +118,7 @@ tc_conv_gemm_staged_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
   } else if (warp == 1) {
     // ===================================================== MMA issuer
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(BM, BN);
+      const uint32_t idesc = make_idesc_f16kind(BM, BN, a.planes == 2 ? 0u : 1u);
       int stage = 0; uint32_t phase = 0;
       int as = 0; uint32_t aphase = 0;
       const int steps = iters * ncombo;
@@ -148,7 +152,7 @@ tc_conv_gemm_staged_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
     uint8_t* outf_row = smem + OUTF_OFF + row * 128;
     uint8_t* outb_row = smem + OUTB_OFF + row * 64;
     const bool has_res = a.epi == EPI_RES_LN;
-    const int out_planes = a.out_planes == 3 ? 3 : 1;
+    const int out_planes = a.out_planes == 3 ? 3 : a.out_planes == 2 ? 2 : 1;
     int res_cnt = 0;                                // residual chunks consumed so far by this thread (buffer / parity)
     int as = 0; uint32_t aphase = 0;
 
@@ -170,6 +174,16 @@ tc_conv_gemm_staged_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
             *reinterpret_cast<uint4*>(outb_row + ((j ^ sw64) << 4)) =
                 make_uint4(pack_bf16x2(y[8 * j], y[8 * j + 1]), pack_bf16x2(y[8 * j + 2], y[8 * j + 3]),
                            pack_bf16x2(y[8 * j + 4], y[8 * j + 5]), pack_bf16x2(y[8 * j + 6], y[8 * j + 7]));
+        } else if (out_planes == 2) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            uint32_t h[4], l[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) split2h_pair(y[8 * j + 2 * u], y[8 * j + 2 * u + 1], h[u], l[u]);
+            uint8_t* o = outb_row + ((j ^ sw64) << 4);
+            *reinterpret_cast<uint4*>(o) = make_uint4(h[0], h[1], h[2], h[3]);
+            *reinterpret_cast<uint4*>(o + CH_B16) = make_uint4(l[0], l[1], l[2], l[3]);
+          }
         } else {
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
@@ -242,7 +256,7 @@ tc_conv_gemm_staged_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
           }
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
-            float x = __uint_as_float(v[j]) + s_bias[c * 32 + j] + rr[j];
+            float x = fmaf(__uint_as_float(v[j]), asc, s_bias[c * 32 + j]) + rr[j];
             if (!has_res) x = fmaxf(x, 0.f);
             sum += x;
             sq = fmaf(x, x, sq);
@@ -284,7 +298,7 @@ tc_conv_gemm_staged_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
           tmem_wait_ld();
           float y[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) y[j] = rp.in_grid ? __uint_as_float(v[j]) + s_bias[c * 32 + j] : 0.f;
+          for (int j = 0; j < 32; ++j) y[j] = rp.in_grid ? fmaf(__uint_as_float(v[j]), asc, s_bias[c * 32 + j]) : 0.f;
           if (n_blk < 2) {
             stage_out(y, c * 32, r0, false, true, n_blk == 0 ? &tmOutB0 : &tmOutB1);
           } else {
@@ -310,7 +324,7 @@ tc_conv_gemm_staged_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
           float y[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
-            float x = __uint_as_float(v[j]) + s_bias[c * 32 + j];
+            float x = fmaf(__uint_as_float(v[j]), asc, s_bias[c * 32 + j]);
             if (a.epi == EPI_RELU) x = fmaxf(x, 0.f);
             if (a.epi == EPI_TANH) x = tanhf(x);
             y[j] = keep ? x : 0.f;
@@ -348,8 +362,8 @@ bool tc_conv_gemm_staged_supported(const ConvGemmArgs& a) {
 
 int tc_conv_gemm_staged_launch(const ConvGemmArgs& a, cudaStream_t st) {
   const uint64_t R = (uint64_t)a.lay.R_cap;
-  const int planes = a.planes == 3 ? 3 : 1;
-  const int out_planes = a.out_planes == 3 ? 3 : 1;
+  const int planes = a.planes == 3 ? 3 : a.planes == 2 ? 2 : 1;
+  const int out_planes = a.out_planes == 3 ? 3 : a.out_planes == 2 ? 2 : 1;
   CUtensorMap tmA, tmB, tmRes, tmOutF, tmOutB0, tmOutB1, tmVt;
   if (!make_tmap_bf16_3d(&tmA, a.Ab, (uint64_t)planes, R, (uint64_t)a.K, (uint64_t)a.K, R * a.K, BM) ||
       !make_tmap_bf16(&tmB, a.Wb, (uint64_t)planes * a.taps * a.N, (uint64_t)a.K, (uint64_t)a.K, BN))

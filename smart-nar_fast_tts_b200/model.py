@@ -19,7 +19,7 @@ import numpy as np
 import torch
 import torch.nn as nn
 
-from .capi import Dims, Fs2Error, PREC_BF16, PREC_BF16X3, PREC_FP32, WeightDesc, load_library
+from .capi import Dims, Fs2Error, PREC_BF16, PREC_BF16X3, PREC_F16X2, PREC_FP32, WeightDesc, load_library
 
 N_SRC_VOCAB_LJSPEECH = 361  # len(text.symbols) + 1 (transformer/Models.py:40)
 
@@ -171,16 +171,17 @@ class FastSpeech2Align(nn.Module):
         self._handle_device: Optional[torch.device] = None
         self._stamp = None
         self._cached_ws = None
-        self._precision = (PREC_BF16X3, PREC_BF16)
+        self._precision = (PREC_F16X2, PREC_BF16)
         self._keep_rows = 2
         # multi-GPU hook (sharding.py): maps the local T_max to the batch-global one between the two stages
         self.t_max_hook: Optional[Callable[[int, torch.device], int]] = None
 
     # ------------------------------------------------------------------ engine plumbing
-    def set_precision(self, encoder: str = "bf16x3", decoder: str = "bf16") -> "FastSpeech2Align":
+    def set_precision(self, encoder: str = "f16x2", decoder: str = "bf16") -> "FastSpeech2Align":
         """encoder: txt_encoder + variance predictors; decoder: mel_decoder + mel_linear + PostNet.
-        "fp32" = FFMA kernels; "bf16x3" = tcgen05 with 3-term split operands (fp32-faithful); "bf16" = tcgen05 bf16."""
-        m = {"fp32": PREC_FP32, "bf16": PREC_BF16, "bf16x3": PREC_BF16X3}
+        "fp32" = FFMA kernels; "bf16x3" / "f16x2" = tcgen05 with split operands (fp32-faithful: 3 bf16 terms and 6 cross
+        products, or 2 scaled fp16 terms and 3 cross products); "bf16" = tcgen05 bf16."""
+        m = {"fp32": PREC_FP32, "bf16": PREC_BF16, "bf16x3": PREC_BF16X3, "f16x2": PREC_F16X2}
         self._precision = (m[encoder], m[decoder])
         if self._handle is not None:
             lib = load_library()

@@ -64,7 +64,7 @@ def check_against(ref, out, sd, dec_prec):
     assert keep.any()
     for k in ("mel", "postnet_mel"):
         a, b = o[k][keep], r[k][keep]
-        if dec_prec in ("fp32", "bf16x3"):
+        if dec_prec in ("fp32", "bf16x3", "f16x2"):
             assert max_abs(a, b) < 2e-3, (k, max_abs(a, b))
         else:
             assert rel_rms(a, b) < 3e-2, (k, rel_rms(a, b))
@@ -73,7 +73,8 @@ def check_against(ref, out, sd, dec_prec):
 
 
 @pytest.mark.parametrize("case", ["small_nanbins", "small_finitebins", "ragged_linearbins", "longform"])
-@pytest.mark.parametrize("enc_prec,dec_prec", [("fp32", "fp32"), ("fp32", "bf16"), ("bf16x3", "bf16"), ("bf16x3", "bf16x3")])
+@pytest.mark.parametrize("enc_prec,dec_prec", [("fp32", "fp32"), ("fp32", "bf16"), ("bf16x3", "bf16"), ("bf16x3", "bf16x3"),
+                                               ("f16x2", "bf16"), ("f16x2", "f16x2")])
 def test_forward_golden(lib, case, enc_prec, dec_prec):
     g = load_golden(case)
     sd, d, stats, pq = golden_state_dict(g)
@@ -85,7 +86,7 @@ def test_forward_golden(lib, case, enc_prec, dec_prec):
     check_against(ref, out[:10], sd, dec_prec)
 
 
-@pytest.mark.parametrize("enc_prec,dec_prec", [("fp32", "fp32"), ("fp32", "bf16"), ("bf16x3", "bf16")])
+@pytest.mark.parametrize("enc_prec,dec_prec", [("fp32", "fp32"), ("fp32", "bf16"), ("bf16x3", "bf16"), ("f16x2", "bf16")])
 def test_forward_oracle_batch32(lib, enc_prec, dec_prec):
     """BASELINE.json configs[1]: batch 32, lengths 40..120, LJSpeech dims."""
     sd = O.make_state_dict(0)
@@ -103,7 +104,7 @@ def test_forward_oracle_batch32(lib, enc_prec, dec_prec):
     check_against(ref2, out2[:10], sd, dec_prec)
 
 
-@pytest.mark.parametrize("enc_prec,dec_prec", [("fp32", "fp32"), ("bf16x3", "bf16")])
+@pytest.mark.parametrize("enc_prec,dec_prec", [("fp32", "fp32"), ("bf16x3", "bf16"), ("f16x2", "bf16")])
 def test_forward_packed_equals_padded_grid(lib, enc_prec, dec_prec):
     """The packed row layout (valid rows + 2 padded rows per utterance) must give the same numbers as storing the
     reference's whole padded [B, S_max] grid -- on every row of every output, padded ones included."""

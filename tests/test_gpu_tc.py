@@ -120,15 +120,16 @@ def test_tc_mel_postnet(lib, oph, sd):
     assert torch.equal(mel.cpu()[1, 40:], sd["mel_linear.bias"].expand(T - 40, -1))
 
 
-# ------------------------------------------------------------------------------------------------ bf16x3 (fp32-faithful)
+# ------------------------------------------------------------------------------ bf16x3 / f16x2 (fp32-faithful split modes)
 X3_CONV_CASES = [(2, 37, 256, 768, 1, 0), (3, 150, 256, 1024, 9, 1), (2, 200, 1024, 256, 1, 0), (2, 133, 256, 256, 3, 1),
                  (2, 300, 512, 512, 5, 2), (1, 700, 256, 80, 1, 0)]
 
 
 @pytest.mark.parametrize("B,S,K,N,taps,act", X3_CONV_CASES)
 def test_x3_conv_gemm_matches_fp32(lib, B, S, K, N, taps, act):
-    """bf16x3 tcgen05 GEMM on UNROUNDED fp32 inputs against a float64 reference; it must be as close to the exact
-    result as the fp32 FFMA kernel is (same order of magnitude: both are fp32-accumulation round-off)."""
+    """Split-operand tcgen05 GEMMs (bf16x3 = prec 2, f16x2 = prec 3) on UNROUNDED fp32 inputs against a float64
+    reference; they must be as close to the exact result as the fp32 FFMA kernel is (same order of magnitude: all are
+    fp32-accumulation round-off)."""
     rng = np.random.Generator(np.random.PCG64(B * 7 + S + K + N + taps))
     A = torch.from_numpy(rng.standard_normal((B, S, K)).astype(np.float32))
     W = torch.from_numpy((rng.standard_normal((N, K, taps)) / np.sqrt(K * taps)).astype(np.float32))
@@ -137,17 +138,18 @@ def test_x3_conv_gemm_matches_fp32(lib, B, S, K, N, taps, act):
     ref = [ref, F.relu(ref), torch.tanh(ref)][act]
     a, w, b = A.to(DEV), W.to(DEV), bias.to(DEV)
     errs = {}
-    for prec in (0, 2):
+    for prec in (0, 2, 3):
         out = torch.empty(B, S, N, device=DEV)
         lib.check(lib.fs2_op_conv_gemm(prec, a.data_ptr(), w.data_ptr(), b.data_ptr(), B, S, K, N, taps, act,
                                        out.data_ptr(), stream()))
         torch.cuda.synchronize()
         errs[prec] = max_abs(out.cpu(), ref)
-    print(f"K={K * taps} max|err| fp32-FFMA {errs[0]:.2e}  bf16x3 {errs[2]:.2e}")
+    print(f"K={K * taps} max|err| fp32-FFMA {errs[0]:.2e}  bf16x3 {errs[2]:.2e}  f16x2 {errs[3]:.2e}")
     # outputs are O(1); the tensor core truncates once per 16-deep accumulation step of the hi*hi pass, so the error
     # grows ~ K/16 * 2^-24 * |out| (measured 1.3e-5 at K = 2304, vs 8.8e-6 for the FFMA kernel)
-    assert errs[2] < 2e-6 + 8e-9 * K * taps, errs
-    assert errs[2] < 4 * errs[0] + 1e-6, errs
+    for prec in (2, 3):
+        assert errs[prec] < 2e-6 + 8e-9 * K * taps, errs
+        assert errs[prec] < 4 * errs[0] + 1e-6, errs
 
 
 @pytest.mark.parametrize("stack,S,n_layers", [(0, 60, 4), (1, 333, 2)])
@@ -163,19 +165,22 @@ def test_x3_fft_stack(lib, oph, sd, stack, S, n_layers):
         ref = O.fft_block(sd, f"{prefix}.layer_stack.{i}", ref, mask, 2)
     xd, ld = x.to(DEV), lens.to(DEV)
     errs = {}
-    for prec in (0, 2):
+    for prec in (0, 2, 3):
         out = torch.empty(B, S, 256, device=DEV)
         oph.check(lib.fs2_op_fft_stack(oph.h, stack, 0, n_layers, prec, xd.data_ptr(), ld.data_ptr(), B, S,
                                        out.data_ptr(), stream()))
         torch.cuda.synchronize()
         errs[prec] = max_abs(out.cpu(), ref)
         assert bool((out.cpu()[mask] == 0).all())
-    print(f"fft stack {prefix} x{n_layers}: max|err| vs CPU oracle: fp32-FFMA {errs[0]:.2e}  bf16x3 {errs[2]:.2e}")
-    assert errs[2] < 2e-4, errs            # same gate as the fp32 path (test_gpu_ops.py)
-    assert errs[2] < 4 * errs[0] + 2e-5, errs
+    print(f"fft stack {prefix} x{n_layers}: max|err| vs CPU oracle: fp32-FFMA {errs[0]:.2e}  bf16x3 {errs[2]:.2e}  "
+          f"f16x2 {errs[3]:.2e}")
+    for prec in (2, 3):
+        assert errs[prec] < 2e-4, errs            # same gate as the fp32 path (test_gpu_ops.py)
+        assert errs[prec] < 4 * errs[0] + 2e-5, errs
 
 
-def test_x3_mel_postnet(lib, oph, sd):
+@pytest.mark.parametrize("prec", [2, 3])
+def test_x3_mel_postnet(lib, oph, sd, prec):
     rng = np.random.Generator(np.random.PCG64(9))
     B, T = 2, 131
     dec = torch.from_numpy(rng.standard_normal((B, T, 256)).astype(np.float32))
@@ -184,7 +189,7 @@ def test_x3_mel_postnet(lib, oph, sd):
     mel = torch.empty(B, T, 80, device=DEV)
     post = torch.empty(B, T, 80, device=DEV)
     d = dec.to(DEV)
-    oph.check(lib.fs2_op_mel_postnet(oph.h, 2, d.data_ptr(), B, T, mel.data_ptr(), post.data_ptr(), stream()))
+    oph.check(lib.fs2_op_mel_postnet(oph.h, prec, d.data_ptr(), B, T, mel.data_ptr(), post.data_ptr(), stream()))
     torch.cuda.synchronize()
     assert max_abs(mel.cpu(), ref_mel) < 1e-5 and max_abs(post.cpu(), ref_post) < 1e-4, (
         max_abs(mel.cpu(), ref_mel), max_abs(post.cpu(), ref_post))
