@@ -26,6 +26,7 @@
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 #include <stdint.h>
+#include <string.h>
 
 #define FS2_HALO 4
 #define FS2_ROW_ALIGN 8   // utterances start at flat rows that are multiples of 8: V^T (bf16, row index innermost) is
@@ -209,3 +210,30 @@ cudaError_t rowops_add_pe(float* x, const float* pe, const RowLayout& lay, int D
 cudaError_t rowops_fill_zero(void* p, size_t bytes, cudaStream_t st);
 
 extern long long g_fs2_launches;  // kernels launched (incremented by every launcher)
+
+// ---------------------------------------------------------------------------------------------
+// Programmatic dependent launch.  Every kernel of the library is launched with the programmatic-stream-serialization
+// attribute: kernel N+1 may be scheduled (and run its private prologue: barrier init, TMEM allocation, tensor-map
+// prefetch, parameter staging) while kernel N drains.  Rule that makes this safe without per-buffer reasoning:
+// EVERY CTA of EVERY kernel executes griddep_wait() before its first access to global memory that any other kernel
+// writes (and before it exits), so a kernel's completion implies the completion of all its predecessors and all
+// read-after-write / write-after-read hazards are ordered exactly as with plain stream order.
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#define FS2_PDL_PROLOGUE() do { griddep_launch_dependents(); griddep_wait(); } while (0)
+
+extern int g_fs2_pdl;  // 1: launch with the programmatic-stream-serialization attribute (default; FS2_NO_PDL=1 clears it)
+template <typename F>
+inline cudaError_t fs2_launch_cfg(dim3 grid, dim3 block, size_t smem, cudaStream_t st, F&& f) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof cfg);
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = g_fs2_pdl;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  return f(&cfg);
+}
+// FS2_LAUNCH(kernel, grid, block, smem_bytes, stream, args...) -> cudaError_t
+#define FS2_LAUNCH(kernel, grid, block, smem, st, ...) \
+  fs2_launch_cfg(grid, block, smem, st, [&](const cudaLaunchConfig_t* _c) { return cudaLaunchKernelEx(_c, kernel, __VA_ARGS__); })

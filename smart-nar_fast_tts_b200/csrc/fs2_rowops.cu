@@ -5,9 +5,11 @@
 // durations / centres), so there is no shared-memory tiling of the payload.
 #include "fs2_common.cuh"
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 long long g_fs2_launches = 0;
+int g_fs2_pdl = getenv("FS2_NO_PDL") ? 0 : 1;
 
 namespace {
 
@@ -53,6 +55,7 @@ __device__ __forceinline__ void store_planes4(bf16* dst, size_t plane_elems, int
 // One CTA, chunks of 1024 utterances, block-wide scan by warp shuffles.
 __global__ void __launch_bounds__(1024) build_layout_kernel(const int* __restrict__ lens, int B, int S, int halo_keep,
                                                             int halo_rows, int* __restrict__ off, int* __restrict__ ext) {
+  FS2_PDL_PROLOGUE();
   __shared__ int warp_tot[32];
   __shared__ int carry_s;
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
@@ -96,6 +99,7 @@ __global__ void __launch_bounds__(1024) build_layout_kernel(const int* __restric
 }
 __global__ void fill_rowmap_kernel(const int* __restrict__ off, const int* __restrict__ ext, int B, int R_cap,
                                    unsigned* __restrict__ rowmap) {
+  FS2_PDL_PROLOGUE();
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= R_cap) return;
   unsigned code = FS2_ROW_NONE;
@@ -117,6 +121,7 @@ __global__ void embed_pe_kernel(const int64_t* __restrict__ texts, const float* 
                                 const float* __restrict__ pe, int vocab, const RowLayout lay, int D,
                                 float* __restrict__ out_grid, bf16* __restrict__ out_b, int out_planes,
                                 float* __restrict__ out_user) {
+  FS2_PDL_PROLOGUE();
   const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   const int R = __ldg(lay.off + lay.B);
   if (r >= R) return;
@@ -142,6 +147,7 @@ __global__ void embed_pe_kernel(const int64_t* __restrict__ texts, const float* 
 }
 
 __global__ void lens_to_i32_kernel(const int64_t* __restrict__ lens, int B, int cap, int* __restrict__ out) {
+  FS2_PDL_PROLOGUE();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < B) {
     long long v = lens[i];
@@ -152,6 +158,7 @@ __global__ void lens_to_i32_kernel(const int64_t* __restrict__ lens, int B, int 
 // utils/tools.py:89-97  mask[b,i] = i >= lens[b]
 __global__ void mask_kernel(const int64_t* __restrict__ lens64, const int* __restrict__ lens32, int B, int max_len,
                             uint8_t* __restrict__ mask) {
+  FS2_PDL_PROLOGUE();
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (size_t)B * max_len) return;
   const int b = (int)(i / max_len), p = (int)(i - (size_t)b * max_len);
@@ -165,6 +172,7 @@ __device__ __forceinline__ float round_duration(float log_d, float d_control) {
 }
 __global__ void round_durations_kernel(const float* __restrict__ log_d, int64_t n, float d_control,
                                        float* __restrict__ out) {
+  FS2_PDL_PROLOGUE();
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) out[i] = round_duration(log_d[i], d_control);
 }
@@ -174,6 +182,7 @@ __global__ void round_durations_kernel(const float* __restrict__ log_d, int64_t 
 __global__ void __launch_bounds__(1024) duration_scan_kernel(const float* __restrict__ d, int L, int* __restrict__ cum,
                                                              int64_t* __restrict__ mel_lens,
                                                              int* __restrict__ mel_lens32, int* __restrict__ tmax) {
+  FS2_PDL_PROLOGUE();
   __shared__ int warp_tot[32];
   __shared__ int carry_s;
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
@@ -227,6 +236,7 @@ __global__ void __launch_bounds__(256) length_regulate_kernel(const float* __res
                                                               int src_stride, const int* __restrict__ cum, int L, int D,
                                                               const RowLayout lay, float* __restrict__ out,
                                                               bf16* __restrict__ out_b, int out_planes) {
+  FS2_PDL_PROLOGUE();
   extern __shared__ int cum_s[];
   const int b = blockIdx.y;
   const int rows_b = __ldg(lay.off + b + 1) - __ldg(lay.off + b);   // ext + halo
@@ -269,6 +279,7 @@ __global__ void variance_embed_kernel(float* __restrict__ pred, float control, c
                                       int n_bins, const float* __restrict__ emb, const float* __restrict__ pe,
                                       float* __restrict__ x, bf16* __restrict__ xb, int xb_planes, const RowLayout lay,
                                       int D, int* __restrict__ idx_out) {
+  FS2_PDL_PROLOGUE();
   const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   const int R = __ldg(lay.off + lay.B);
   if (r >= R) return;
@@ -307,6 +318,7 @@ __global__ void __launch_bounds__(256) fill_padded_rows_kernel(const float* __re
                                                                int dst_SA, float* __restrict__ out_grid,
                                                                bf16* __restrict__ out_b, int out_planes,
                                                                float* __restrict__ out_user) {
+  FS2_PDL_PROLOGUE();
   const int b = blockIdx.y;
   const int e = __ldg(lay.ext + b);
   const int p = e + blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -331,6 +343,7 @@ __global__ void __launch_bounds__(256) fill_padded_rows_kernel(const float* __re
 __global__ void __launch_bounds__(256) gaussian_upsample_kernel(const float* __restrict__ x, const float* __restrict__ d,
                                                                 int L, int D, int T, int T_w, float* __restrict__ out,
                                                                 float* __restrict__ s_out, float* __restrict__ w_out) {
+  FS2_PDL_PROLOGUE();
   extern __shared__ float c_s[];  // [L] centres
   __shared__ int mono_s;
   const int b = blockIdx.y;
@@ -400,6 +413,7 @@ __global__ void __launch_bounds__(256) gaussian_upsample_kernel(const float* __r
 // dense user layout [B,S,C] <-> ragged grid layout (test / per-operator entry points)
 __global__ void to_grid_kernel(const float* __restrict__ xu, const RowLayout lay, int C, float* __restrict__ out,
                                int ldo, int col_off, bf16* __restrict__ out_b) {
+  FS2_PDL_PROLOGUE();
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;  // one float4 per thread
   const int nv = C >> 2;
   if (i >= (size_t)lay.R_cap * nv) return;
@@ -412,6 +426,7 @@ __global__ void to_grid_kernel(const float* __restrict__ xu, const RowLayout lay
   if (out_b) *reinterpret_cast<uint2*>(out_b + row * C + c * 4) = make_uint2(pack2(v.x, v.y), pack2(v.z, v.w));
 }
 __global__ void from_grid_kernel(const float* __restrict__ xg, const RowLayout lay, int C, float* __restrict__ out) {
+  FS2_PDL_PROLOGUE();
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int nv = C >> 2;
   if (i >= (size_t)lay.B * lay.S * nv) return;
@@ -427,6 +442,7 @@ __global__ void from_grid_kernel(const float* __restrict__ xg, const RowLayout l
 // bf16 [taps][n_total][K] (rows n_off..), optionally scaled per output channel (BatchNorm fold).
 __global__ void pack_weight_kernel(const float* __restrict__ src, int N, int K, int taps, const float* __restrict__ scale,
                                    float* __restrict__ dst_f, bf16* __restrict__ dst_b, int n_total, int n_off) {
+  FS2_PDL_PROLOGUE();
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (size_t)N * K * taps) return;
   const int t = (int)(i % taps);
@@ -452,6 +468,7 @@ __global__ void bn_fold_kernel(const float* __restrict__ conv_bias, const float*
                                const float* __restrict__ b, const float* __restrict__ mean,
                                const float* __restrict__ var, int n, float eps, float* __restrict__ scale_out,
                                float* __restrict__ bias_out) {
+  FS2_PDL_PROLOGUE();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const float s = g[i] / sqrtf(var[i] + eps);
@@ -460,12 +477,14 @@ __global__ void bn_fold_kernel(const float* __restrict__ conv_bias, const float*
 }
 
 __global__ void split_kernel(const float* __restrict__ src, int64_t n4, int planes, bf16* __restrict__ dst, int64_t plane_elems) {
+  FS2_PDL_PROLOGUE();
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n4) store_planes4(dst + i * 4, (size_t)plane_elems, planes, ld4(src + i * 4));
 }
 
 // max |w| of a tensor as the bit pattern of a non-negative float (monotonic as unsigned)
 __global__ void absmax_kernel(const float* __restrict__ w, size_t n, unsigned* __restrict__ out) {
+  FS2_PDL_PROLOGUE();
   float m = 0.f;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     const float v = fabsf(w[i]);
@@ -477,6 +496,7 @@ __global__ void absmax_kernel(const float* __restrict__ w, size_t n, unsigned* _
 
 // wf [taps][K][N] fp32 -> dst [2][taps][N][K] fp16 bit patterns of (w * scale): hi, lo
 __global__ void pack_weight_f16x2_kernel(const float* __restrict__ wf, int N, int K, int taps, float scale, bf16* __restrict__ dst) {
+  FS2_PDL_PROLOGUE();
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;   // index into dst plane: ((t*N + n)*K + k)
   const size_t plane = (size_t)taps * N * K;
   if (i >= plane) return;
@@ -490,10 +510,12 @@ __global__ void pack_weight_f16x2_kernel(const float* __restrict__ wf, int N, in
 }
 
 __global__ void f32_to_bf16_kernel(const float* __restrict__ src, int64_t n, bf16* __restrict__ dst) {
+  FS2_PDL_PROLOGUE();
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) dst[i] = __float2bfloat16_rn(src[i]);
 }
 __global__ void bf16_to_f32_kernel(const bf16* __restrict__ src, int64_t n, float* __restrict__ dst) {
+  FS2_PDL_PROLOGUE();
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) dst[i] = __bfloat162float(src[i]);
 }
@@ -501,6 +523,7 @@ __global__ void bf16_to_f32_kernel(const bf16* __restrict__ src, int64_t n, floa
 // V [R, D] bf16 (flat rows) -> V^T [D, Rv]: row c, column r (columns >= R zero).  Test helper for the tcgen05
 // attention entry point; on the product path the QKV GEMM epilogue writes V^T directly.
 __global__ void transpose_v_kernel(const bf16* __restrict__ v, int R, int Rv, int D, bf16* __restrict__ vt) {
+  FS2_PDL_PROLOGUE();
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (size_t)D * Rv) return;
   const int r = (int)(i % Rv), c = (int)(i / Rv);
@@ -509,6 +532,7 @@ __global__ void transpose_v_kernel(const bf16* __restrict__ v, int R, int Rv, in
 
 // Models.py:231-233 alone: x[b,p,:] += pe[p,:] on grid rows; used when no variance embedding is frame-level
 __global__ void add_pe_kernel(float* __restrict__ x, const float* __restrict__ pe, const RowLayout lay, int D) {
+  FS2_PDL_PROLOGUE();
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int nv = D >> 2;
   if (i >= (size_t)lay.R_cap * nv) return;
@@ -532,37 +556,37 @@ cudaError_t rowops_build_layout(const int* lens32, int B, int S, int halo_keep, 
                                 unsigned* rowmap, int R_cap, cudaStream_t st) {
   if (B <= 0 || R_cap <= 0) return cudaSuccess;
   if (B > 65535 || S > FS2_MAX_ROWS_PER_UTT) return cudaErrorInvalidValue;
-  build_layout_kernel<<<1, 1024, 0, st>>>(lens32, B, S, halo_keep, halo_rows, off, ext);
+  (void)FS2_LAUNCH(build_layout_kernel, 1, 1024, 0, st, lens32, B, S, halo_keep, halo_rows, off, ext);
   ++g_fs2_launches;
-  fill_rowmap_kernel<<<blocks_for((size_t)R_cap, 256), 256, 0, st>>>(off, ext, B, R_cap, rowmap);
+  (void)FS2_LAUNCH(fill_rowmap_kernel, blocks_for((size_t)R_cap, 256), 256, 0, st, off, ext, B, R_cap, rowmap);
   return LAUNCHED();
 }
 cudaError_t rowops_embed_pe(const int64_t* texts, const float* emb, const float* pe, int vocab, const RowLayout& lay,
                             int D, float* out_grid, bf16* out_b, int out_planes, float* out_user, cudaStream_t st) {
   if (lay.R_cap <= 0) return cudaSuccess;
-  embed_pe_kernel<<<blocks_for((size_t)lay.R_cap, 8), 256, 0, st>>>(texts, emb, pe, vocab, lay, D, out_grid, out_b,
+  (void)FS2_LAUNCH(embed_pe_kernel, blocks_for((size_t)lay.R_cap, 8), 256, 0, st, texts, emb, pe, vocab, lay, D, out_grid, out_b,
                                                                    out_planes, out_user);
   return LAUNCHED();
 }
 cudaError_t rowops_lens_to_i32(const int64_t* lens, int B, int cap, int* out, cudaStream_t st) {
   if (B <= 0) return cudaSuccess;
-  lens_to_i32_kernel<<<blocks_for(B, 256), 256, 0, st>>>(lens, B, cap, out);
+  (void)FS2_LAUNCH(lens_to_i32_kernel, blocks_for(B, 256), 256, 0, st, lens, B, cap, out);
   return LAUNCHED();
 }
 cudaError_t rowops_mask(const int64_t* lens64, const int* lens32, int B, int max_len, uint8_t* mask, cudaStream_t st) {
   if ((size_t)B * max_len == 0) return cudaSuccess;
-  mask_kernel<<<blocks_for((size_t)B * max_len, 256), 256, 0, st>>>(lens64, lens32, B, max_len, mask);
+  (void)FS2_LAUNCH(mask_kernel, blocks_for((size_t)B * max_len, 256), 256, 0, st, lens64, lens32, B, max_len, mask);
   return LAUNCHED();
 }
 cudaError_t rowops_round_durations(const float* log_d, int64_t n, float d_control, float* out, cudaStream_t st) {
   if (n <= 0) return cudaSuccess;
-  round_durations_kernel<<<blocks_for((size_t)n, 256), 256, 0, st>>>(log_d, n, d_control, out);
+  (void)FS2_LAUNCH(round_durations_kernel, blocks_for((size_t)n, 256), 256, 0, st, log_d, n, d_control, out);
   return LAUNCHED();
 }
 cudaError_t rowops_duration_scan(const float* d, int B, int L, int* cum, int64_t* mel_lens, int* mel_lens32,
                                  int* tmax_dev, cudaStream_t st) {
   if (B <= 0) return cudaSuccess;
-  duration_scan_kernel<<<B, 1024, 0, st>>>(d, L, cum, mel_lens, mel_lens32, tmax_dev);
+  (void)FS2_LAUNCH(duration_scan_kernel, B, 1024, 0, st, d, L, cum, mel_lens, mel_lens32, tmax_dev);
   return LAUNCHED();
 }
 cudaError_t rowops_length_regulate(const float* x, const int* src_off, int src_stride, const int* cum, int L, int D,
@@ -571,14 +595,14 @@ cudaError_t rowops_length_regulate(const float* x, const int* src_off, int src_s
   const size_t smem = sizeof(int) * (size_t)(L > 0 ? L : 1);
   if (smem > 48 * 1024) return cudaErrorInvalidValue;
   dim3 grid((FS2_ROWS_PER_UTT(lay.S, FS2_HALO) + 63) / 64, lay.B);   // covers ext + halo rows of the longest utterance
-  length_regulate_kernel<<<grid, 256, smem, st>>>(x, src_off, src_stride, cum, L, D, lay, out, out_b, out_planes);
+  (void)FS2_LAUNCH(length_regulate_kernel, grid, 256, smem, st, x, src_off, src_stride, cum, L, D, lay, out, out_b, out_planes);
   return LAUNCHED();
 }
 cudaError_t rowops_variance_embed(float* pred, float control, const float* bins, int n_bins, const float* emb,
                                   const float* pe, float* x, bf16* xb, int xb_planes, const RowLayout& lay, int D,
                                   int* idx_out, cudaStream_t st) {
   if (lay.R_cap <= 0) return cudaSuccess;
-  variance_embed_kernel<<<blocks_for((size_t)lay.R_cap, 8), 256, 0, st>>>(pred, control, bins, n_bins, emb, pe, x, xb,
+  (void)FS2_LAUNCH(variance_embed_kernel, blocks_for((size_t)lay.R_cap, 8), 256, 0, st, pred, control, bins, n_bins, emb, pe, x, xb,
                                                                          xb_planes, lay, D, idx_out);
   return LAUNCHED();
 }
@@ -586,7 +610,7 @@ cudaError_t rowops_fill_padded_rows(const float* bias, int N, const RowLayout& l
                                     bf16* out_b, int out_planes, float* out_user, cudaStream_t st) {
   if (lay.B <= 0 || dst_SA <= 0) return cudaSuccess;
   dim3 grid((dst_SA + 7) / 8, lay.B);
-  fill_padded_rows_kernel<<<grid, 256, 0, st>>>(bias, N, lay, dst_SA, out_grid, out_b, out_planes, out_user);
+  (void)FS2_LAUNCH(fill_padded_rows_kernel, grid, 256, 0, st, bias, N, lay, dst_SA, out_grid, out_b, out_planes, out_user);
   return LAUNCHED();
 }
 cudaError_t rowops_pack_weight_f16x2(const float* wf, int N, int K, int taps, bf16* dst, float* w_scale_out, cudaStream_t st) {
@@ -599,7 +623,7 @@ cudaError_t rowops_pack_weight_f16x2(const float* wf, int N, int K, int taps, bf
   e = cudaMemsetAsync(d_max, 0, sizeof(unsigned), st);
   if (e == cudaSuccess) {
     const int blocks = (int)(blocks_for(n, 256) < 1024 ? blocks_for(n, 256) : 1024);
-    absmax_kernel<<<blocks, 256, 0, st>>>(wf, n, d_max);
+    (void)FS2_LAUNCH(absmax_kernel, blocks, 256, 0, st, wf, n, d_max);
     ++g_fs2_launches;
     e = cudaGetLastError();
   }
@@ -619,13 +643,13 @@ cudaError_t rowops_pack_weight_f16x2(const float* wf, int N, int K, int taps, bf
   if (ex < -24) ex = -24;
   const float scale = ldexpf(1.0f, ex);
   *w_scale_out = scale;
-  pack_weight_f16x2_kernel<<<blocks_for(n, 256), 256, 0, st>>>(wf, N, K, taps, scale, dst);
+  (void)FS2_LAUNCH(pack_weight_f16x2_kernel, blocks_for(n, 256), 256, 0, st, wf, N, K, taps, scale, dst);
   return LAUNCHED();
 }
 cudaError_t rowops_split(const float* src, int64_t n, int planes, bf16* dst, int64_t plane_elems, cudaStream_t st) {
   if (n <= 0) return cudaSuccess;
   if (n % 4) return cudaErrorInvalidValue;
-  split_kernel<<<blocks_for((size_t)(n / 4), 256), 256, 0, st>>>(src, n / 4, planes, dst, plane_elems);
+  (void)FS2_LAUNCH(split_kernel, blocks_for((size_t)(n / 4), 256), 256, 0, st, src, n / 4, planes, dst, plane_elems);
   return LAUNCHED();
 }
 cudaError_t rowops_gaussian_upsample(const float* x, const float* d, int B, int L, int D, int T, int T_w, float* out,
@@ -637,55 +661,55 @@ cudaError_t rowops_gaussian_upsample(const float* x, const float* d, int B, int 
   if (gx < 1) gx = 1;
   if (gx > 1024) gx = 1024;
   dim3 grid(gx, B);
-  gaussian_upsample_kernel<<<grid, 256, smem, st>>>(x, d, L, D, T, T_w, out, s, w);
+  (void)FS2_LAUNCH(gaussian_upsample_kernel, grid, 256, smem, st, x, d, L, D, T, T_w, out, s, w);
   return LAUNCHED();
 }
 cudaError_t rowops_to_grid(const float* x_user, const RowLayout& lay, int C, float* out, int ldo, int col_off,
                            bf16* out_b, cudaStream_t st) {
   const size_t n = (size_t)lay.R_cap * (C / 4);
   if (n == 0) return cudaSuccess;
-  to_grid_kernel<<<blocks_for(n, 256), 256, 0, st>>>(x_user, lay, C, out, ldo, col_off, out_b);
+  (void)FS2_LAUNCH(to_grid_kernel, blocks_for(n, 256), 256, 0, st, x_user, lay, C, out, ldo, col_off, out_b);
   return LAUNCHED();
 }
 cudaError_t rowops_from_grid(const float* x_grid, const RowLayout& lay, int C, float* out_user, cudaStream_t st) {
   const size_t n = (size_t)lay.B * lay.S * (C / 4);
   if (n == 0) return cudaSuccess;
-  from_grid_kernel<<<blocks_for(n, 256), 256, 0, st>>>(x_grid, lay, C, out_user);
+  (void)FS2_LAUNCH(from_grid_kernel, blocks_for(n, 256), 256, 0, st, x_grid, lay, C, out_user);
   return LAUNCHED();
 }
 cudaError_t rowops_pack_weight(const float* src, int N, int K, int taps, const float* scale, float* dst_f,
                                bf16* dst_b, int n_total, int n_off, cudaStream_t st) {
   const size_t n = (size_t)N * K * taps;
   if (n == 0) return cudaSuccess;
-  pack_weight_kernel<<<blocks_for(n, 256), 256, 0, st>>>(src, N, K, taps, scale, dst_f, dst_b, n_total, n_off);
+  (void)FS2_LAUNCH(pack_weight_kernel, blocks_for(n, 256), 256, 0, st, src, N, K, taps, scale, dst_f, dst_b, n_total, n_off);
   return LAUNCHED();
 }
 cudaError_t rowops_bn_fold(const float* conv_bias, const float* g, const float* b, const float* mean,
                            const float* var, int n, float eps, float* scale_out, float* bias_out, cudaStream_t st) {
   if (n <= 0) return cudaSuccess;
-  bn_fold_kernel<<<blocks_for(n, 256), 256, 0, st>>>(conv_bias, g, b, mean, var, n, eps, scale_out, bias_out);
+  (void)FS2_LAUNCH(bn_fold_kernel, blocks_for(n, 256), 256, 0, st, conv_bias, g, b, mean, var, n, eps, scale_out, bias_out);
   return LAUNCHED();
 }
 cudaError_t rowops_f32_to_bf16(const float* src, int64_t n, bf16* dst, cudaStream_t st) {
   if (n <= 0) return cudaSuccess;
-  f32_to_bf16_kernel<<<blocks_for((size_t)n, 256), 256, 0, st>>>(src, n, dst);
+  (void)FS2_LAUNCH(f32_to_bf16_kernel, blocks_for((size_t)n, 256), 256, 0, st, src, n, dst);
   return LAUNCHED();
 }
 cudaError_t rowops_bf16_to_f32(const bf16* src, int64_t n, float* dst, cudaStream_t st) {
   if (n <= 0) return cudaSuccess;
-  bf16_to_f32_kernel<<<blocks_for((size_t)n, 256), 256, 0, st>>>(src, n, dst);
+  (void)FS2_LAUNCH(bf16_to_f32_kernel, blocks_for((size_t)n, 256), 256, 0, st, src, n, dst);
   return LAUNCHED();
 }
 cudaError_t rowops_transpose_v(const bf16* v, int R, int Rv, int D, bf16* vt, cudaStream_t st) {
   const size_t n = (size_t)D * Rv;
   if (n == 0) return cudaSuccess;
-  transpose_v_kernel<<<blocks_for(n, 256), 256, 0, st>>>(v, R, Rv, D, vt);
+  (void)FS2_LAUNCH(transpose_v_kernel, blocks_for(n, 256), 256, 0, st, v, R, Rv, D, vt);
   return LAUNCHED();
 }
 cudaError_t rowops_add_pe(float* x, const float* pe, const RowLayout& lay, int D, cudaStream_t st) {
   const size_t n = (size_t)lay.R_cap * (D / 4);
   if (n == 0) return cudaSuccess;
-  add_pe_kernel<<<blocks_for(n, 256), 256, 0, st>>>(x, pe, lay, D);
+  (void)FS2_LAUNCH(add_pe_kernel, blocks_for(n, 256), 256, 0, st, x, pe, lay, D);
   return LAUNCHED();
 }
 cudaError_t rowops_fill_zero(void* p, size_t bytes, cudaStream_t st) {

@@ -18,6 +18,7 @@ template <int DK>
 __global__ void __launch_bounds__(128) simt_attention_kernel(const float* __restrict__ qkv, int ldqkv, int q_off,
                                                              int k_off, int v_off, const RowLayout lay,
                                                              float* __restrict__ out, int ldo, float temperature) {
+  FS2_PDL_PROLOGUE();
   constexpr int QS = DK + 4;     // padded row stride (floats) of Q/K tiles: conflict-free float4 column walks
   constexpr int PS = BKV + 4;
   constexpr int DC = DK / 64;    // float4 output column groups per thread
@@ -180,7 +181,7 @@ cudaError_t launch(const float* qkv, int ldqkv, int q_off, int k_off, int v_off,
     configured = true;
   }
   dim3 grid((FS2_ROWS_PER_UTT(lay.S, FS2_HALO) + BQ - 1) / BQ, H, lay.B);
-  simt_attention_kernel<DK><<<grid, 128, smem, st>>>(qkv, ldqkv, q_off, k_off, v_off, lay, out, ldo,
+  (void)FS2_LAUNCH((simt_attention_kernel<DK>), grid, 128, smem, st, qkv, ldqkv, q_off, k_off, v_off, lay, out, ldo,
                                                       (float)sqrt((double)DK));
   ++g_fs2_launches;
   return cudaGetLastError();

@@ -26,6 +26,7 @@ __device__ __forceinline__ float warp_sum(float v) {
 
 template <int BM, int BN>
 __global__ void __launch_bounds__(256) simt_conv_gemm_kernel(const ConvGemmArgs a) {
+  FS2_PDL_PROLOGUE();
   constexpr int TX = BN / 8;   // threads along N (each owns 2 x 4 columns)
   constexpr int TY = 256 / TX; // threads along M (each owns 8 rows)
   static_assert(TY * 8 == BM, "tile/thread mismatch");
@@ -232,10 +233,10 @@ cudaError_t simt_conv_gemm_launch(const ConvGemmArgs& a, cudaStream_t st) {
   if (ln && a.N != 256) return cudaErrorInvalidValue;
   if (ln || a.N % 256 == 0) {
     dim3 grid((R + 63) / 64, (a.N + 255) / 256);
-    simt_conv_gemm_kernel<64, 256><<<grid, 256, 0, st>>>(a);
+    (void)FS2_LAUNCH((simt_conv_gemm_kernel<64, 256>), grid, 256, 0, st, a);
   } else {
     dim3 grid((R + 127) / 128, (a.N + 127) / 128);
-    simt_conv_gemm_kernel<128, 128><<<grid, 256, 0, st>>>(a);
+    (void)FS2_LAUNCH((simt_conv_gemm_kernel<128, 128>), grid, 256, 0, st, a);
   }
   ++g_fs2_launches;
   return cudaGetLastError();

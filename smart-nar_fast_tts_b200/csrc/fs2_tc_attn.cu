@@ -56,6 +56,7 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.z, h = blockIdx.y, p0 = blockIdx.x * BQ;
+  FS2_PDL_PROLOGUE();   // the layout tables read next are written by a predecessor; every CTA waits before it may exit
   const size_t row0 = (size_t)__ldg(lay.off + b);
   const int SA = __ldg(lay.off + b + 1) - (int)row0;   // this utterance's rows (grid + halo)
   const int len = min(__ldg(lay.lens + b), __ldg(lay.ext + b));
@@ -284,7 +285,7 @@ int tc_attention_launch(const bf16* q, const bf16* k, const bf16* vt, const RowL
   }
   dim3 grid((FS2_ROWS_PER_UTT(lay.S, FS2_HALO) + BQ - 1) / BQ, H, lay.B);
   const float scale_log2 = (float)(1.4426950408889634 / sqrt((double)DK));
-  tc_attention_kernel<<<grid, ATT_THREADS, smem, st>>>(tmQ, tmK, tmV, tmO, lay, out_b, scale_log2);
+  (void)FS2_LAUNCH(tc_attention_kernel, grid, ATT_THREADS, smem, st, tmQ, tmK, tmV, tmO, lay, out_b, scale_log2);
   ++g_fs2_launches;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fs2_fail_cuda(e, "tc_attention_kernel launch");

@@ -122,10 +122,9 @@ tc_conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const int ncombo = a.planes == 3 ? 6 : a.planes == 2 ? 3 : 1;
   const int iters = a.taps * KB;
   const float asc = a.acc_scale;
-  const int R = __ldg(a.lay.off + a.lay.B);          // rows in use: device data (ragged layout)
-  const int num_tiles = ((R + BM - 1) / BM) * num_n_blocks;
   constexpr uint32_t TMEM_COLS = 2 * BN;  // 512 or 256: power of two
 
+  griddep_launch_dependents();   // PDL: the next kernel may start its own prologue while this one runs
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
@@ -146,10 +145,15 @@ tc_conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       s_dw[i] = (a.epi == EPI_RELU_LN_DOT) ? __ldg(a.dot_w + i) : 0.f;
     }
   }
+  // everything above touched only kernel parameters, weights and on-chip state; from here on the kernel reads
+  // activations / layout tables written by its predecessors
+  griddep_wait();
   fence_before_sync();
   __syncthreads();
   fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
+  const int R = __ldg(a.lay.off + a.lay.B);          // rows in use: device data (ragged layout)
+  const int num_tiles = ((R + BM - 1) / BM) * num_n_blocks;
 
   if (warp == 0) {
     // ===================================================== TMA producer
@@ -396,7 +400,7 @@ int launch(const ConvGemmArgs& a, cudaStream_t st) {
   }
   const int tiles = num_m_blocks * num_n_blocks;
   const int grid = tiles < g_num_sms ? tiles : g_num_sms;
-  tc_conv_gemm_kernel<BN><<<grid, NUM_THREADS, smem, st>>>(tmA, tmB, a, num_n_blocks);
+  (void)FS2_LAUNCH((tc_conv_gemm_kernel<BN>), grid, NUM_THREADS, smem, st, tmA, tmB, a, num_n_blocks);
   ++g_fs2_launches;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fs2_fail_cuda(e, "tc_conv_gemm_kernel launch");

@@ -66,10 +66,9 @@ tc_conv_gemm_staged_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
   const int ncombo = a.planes == 3 ? 6 : a.planes == 2 ? 3 : 1;
   const int iters = a.taps * KB;
   const float asc = a.acc_scale;
-  const int R = __ldg(a.lay.off + a.lay.B);
-  const int num_tiles = ((R + BM - 1) / BM) * num_n_blocks;
   const bool ln = (a.epi == EPI_RES_LN || a.epi == EPI_RELU_LN);
 
+  griddep_launch_dependents();   // PDL (fs2_common.cuh)
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
@@ -88,10 +87,13 @@ tc_conv_gemm_staged_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
       s_b[i] = ln ? __ldg(a.ln_b + i) : 0.f;
     }
   }
+  griddep_wait();   // first access to predecessor-written global memory is below
   fence_before_sync();
   __syncthreads();
   fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
+  const int R = __ldg(a.lay.off + a.lay.B);
+  const int num_tiles = ((R + BM - 1) / BM) * num_n_blocks;
 
   if (warp == 0) {
     // ===================================================== TMA producer
@@ -413,7 +415,7 @@ int tc_conv_gemm_staged_launch(const ConvGemmArgs& a, cudaStream_t st) {
   const int grid = tiles < num_sms ? tiles : num_sms;
   ConvGemmArgs b = a;
   if (a.epi == EPI_QKV) b.out_planes = 1;
-  tc_conv_gemm_staged_kernel<<<grid, NUM_THREADS, smem, st>>>(tmA, tmB, tmRes, tmOutF, tmOutB0, tmOutB1, tmVt, b, num_n_blocks);
+  (void)FS2_LAUNCH(tc_conv_gemm_staged_kernel, grid, NUM_THREADS, smem, st, tmA, tmB, tmRes, tmOutF, tmOutB0, tmOutB1, tmVt, b, num_n_blocks);
   ++g_fs2_launches;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fs2_fail_cuda(e, "tc_conv_gemm_staged_kernel launch");
