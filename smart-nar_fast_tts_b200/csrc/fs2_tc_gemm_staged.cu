@@ -1,17 +1,22 @@
 // fs2_tc_gemm_staged.cu -- the tcgen05 implicit-GEMM of fs2_tc_gemm.cu with a shared-memory staged epilogue.
 //
-// Same mainloop (TMA producer warp, MMA warp, TMEM double-buffered accumulators, bf16 or bf16x3 operands) for the
-// N % 256 == 0 GEMMs of the path; what changes is how the epilogue touches HBM.  With one thread per output row the
+// Same mainloop (TMA producer warp, MMA warp, TMEM double-buffered accumulators, bf16 / bf16x3 / f16x2 operands) for
+// the N % 256 == 0 GEMMs of the path; what changes is how the epilogue touches HBM.  With one thread per output row the
 // direct version issues 16-byte accesses to 32 different 1-KB rows per warp instruction (32 L1 wavefronts each), which
 // made the small-K GEMMs (attention output projection + LayerNorm, FFN conv k=1 + LayerNorm, QKV) epilogue-bound at
 // 3-5x their HBM time (profiles/r1a).  Here every global access of the epilogue is a TMA transfer:
-//   * the fp32 residual tile is TMA-loaded in [128 rows x 32 col] chunks into a 2-deep, 128B-swizzled staging ring
-//     (prefetched while the mainloop of the tile is still running);
+//   * the fp32 residual tile is TMA-loaded in [128 rows x 32 col] chunks into 128B-swizzled staging buffers;
 //   * results are written by the row-owning threads into swizzled staging tiles (conflict-free 16-byte st.shared) and
-//     leave as TMA stores: fp32 [128 x 32], bf16 [128 x 32] per operand plane (1 or 3), Q / K tiles, and V^T as a
+//     leave as TMA stores: fp32 [128 x 32], bf16 [128 x 32] per operand plane (1..3), Q / K tiles, and V^T as a
 //     [32 d x 128 row] transposed tile.
+// Epilogue v2 (profiles/r1d: the 4-warp epilogue spent ~45 % of its time waiting on the 2-deep residual ring and on the
+// single output staging tile): EIGHT epilogue warps in two independent groups.  Group g owns columns [128 g, 128 g + 128)
+// of the tile (TMEM restricts a warp to the lane quarter warp % 4, so more warps can only split columns); each group
+// has its own residual / staging buffers, its own named barrier and its own elected TMA thread, so the two halves run
+// decoupled and twice as many bytes are in flight.  A group's two fp32 buffers carry the residual chunks in pass 1
+// and double-buffer the fp32 output tiles in pass 2.  LayerNorm needs one exchange per tile: the two threads that
+// share a row swap their partial (sum, sum of squares) through shared memory (64-thread named barrier per lane quarter).
 // Row masking is by value (masked rows store zeros); rows past the end of the buffer are clipped by TMA.
-// LayerNorm keeps the one-thread-per-row two-pass scheme (row parked in TMEM between the passes).
 #include "fs2_tc_common.cuh"
 #include "../../include/fs2_b200.h"
 
@@ -19,18 +24,24 @@ namespace {
 
 using namespace tc;
 
-constexpr int BM = 128, BN = 256, BKE = 64, STAGES = 3, NUM_THREADS = 192;
-constexpr int A_BYTES = BM * BKE * 2, B_BYTES = BN * BKE * 2, STAGE_BYTES = A_BYTES + B_BYTES;
-constexpr int RING_BYTES = STAGES * STAGE_BYTES;          // 144 KB
+constexpr int BM = 128, BN = 256, BKE = 64;
+constexpr int NUM_THREADS = 320;                          // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue
+constexpr int A_BYTES = BM * BKE * 2, B_BYTES = BN * BKE * 2, STAGE_BYTES = A_BYTES + B_BYTES;   // 48 KB
+constexpr int MAX_STAGES = 3;
 constexpr int CH_F32 = BM * 32 * 4;                       // 16 KB: [128 rows][32 fp32], 128-byte rows, SWIZZLE_128B
 constexpr int CH_B16 = BM * 32 * 2;                       //  8 KB: [128 rows][32 bf16],  64-byte rows, SWIZZLE_64B
-constexpr int RES_OFF = RING_BYTES;                       // 2 x CH_F32
-constexpr int OUTF_OFF = RES_OFF + 2 * CH_F32;            // CH_F32 (also the V^T chunk: [32 d][128 rows] bf16, 8 KB)
-constexpr int OUTB_OFF = OUTF_OFF + CH_F32;               // 3 x CH_B16
-constexpr int PARAM_OFF = OUTB_OFF + 3 * CH_B16;          // bias[256], ln_g[256], ln_b[256]
-constexpr int BAR_OFF = PARAM_OFF + 3 * 256 * 4;
-constexpr int NUM_BARS = 2 * STAGES + 4 + 2;
-constexpr int SMEM_TOTAL = BAR_OFF + NUM_BARS * 8 + 16;
+// shared-memory plan (bytes from the 1024-aligned base):
+//   ring            stages x 48 KB
+//   group g region  "wide" plan (2 stages): F0, F1 (2 x 16 KB) + B (3 x 8 KB) = 56 KB ; "deep" plan (3 stages): B only
+//   params          bias[2][128], ln_g[256], ln_b[256], stats[2 parities][2 groups][128] float2
+//   barriers
+constexpr int GRP_WIDE = 2 * CH_F32 + 3 * CH_B16, GRP_DEEP = 3 * CH_B16;
+constexpr int PARAM_BYTES = (2 * 128 + 256 + 256) * 4 + 2 * 2 * 128 * 8;
+constexpr int NUM_BARS = 2 * MAX_STAGES + 4 + 4;
+__host__ __device__ constexpr int grp_bytes(int stages) { return stages == 2 ? GRP_WIDE : GRP_DEEP; }
+__host__ __device__ constexpr int smem_total(int stages) {
+  return stages * STAGE_BYTES + 2 * grp_bytes(stages) + PARAM_BYTES + NUM_BARS * 8 + 16;
+}
 constexpr uint32_t TMEM_COLS = 2 * BN;
 
 __constant__ int s_combo_a[6] = {0, 2, 1, 0, 1, 0};       // bf16x3 cross products, smallest first (see fs2_tc_gemm.cu)
@@ -38,27 +49,32 @@ __constant__ int s_combo_b[6] = {2, 0, 1, 1, 0, 0};
 __constant__ int s_combo2_a[3] = {0, 1, 0};               // f16x2 cross products (hi*lo, lo*hi, hi*hi)
 __constant__ int s_combo2_b[3] = {1, 0, 0};
 
-__device__ __forceinline__ void bar_epi() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read_n() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
 
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 tc_conv_gemm_staged_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                            const __grid_constant__ CUtensorMap tmRes, const __grid_constant__ CUtensorMap tmOutF,
                            const __grid_constant__ CUtensorMap tmOutB0, const __grid_constant__ CUtensorMap tmOutB1,
-                           const __grid_constant__ CUtensorMap tmVt, const ConvGemmArgs a, const int num_n_blocks) {
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t raw_addr = smem_u32(smem_raw);
-  const uint32_t base = (raw_addr + 1023u) & ~1023u;
-  uint8_t* smem = smem_raw + (base - raw_addr);
-  float* s_bias = reinterpret_cast<float*>(smem + PARAM_OFF);
+                           const __grid_constant__ CUtensorMap tmVt, const ConvGemmArgs a, const int num_n_blocks,
+                           const int stages) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const uint32_t base = smem_u32(smem);
+  const int ring_bytes = stages * STAGE_BYTES;
+  const int grp_sz = grp_bytes(stages);
+  const int param_off = ring_bytes + 2 * grp_sz;
+  float* s_bias = reinterpret_cast<float*>(smem + param_off);           // [2 groups][128]
   float* s_g = s_bias + 256;
   float* s_b = s_g + 256;
-  const uint32_t bars = base + BAR_OFF;
+  float2* s_stat = reinterpret_cast<float2*>(s_b + 256);                // [2 parities][2 groups][128]
+  const int bar_off = param_off + PARAM_BYTES;
+  const uint32_t bars = base + bar_off;
   auto full_bar = [&](int s) { return bars + 8u * s; };
-  auto empty_bar = [&](int s) { return bars + 8u * (STAGES + s); };
-  auto tfull_bar = [&](int s) { return bars + 8u * (2 * STAGES + s); };
-  auto tempty_bar = [&](int s) { return bars + 8u * (2 * STAGES + 2 + s); };
-  auto res_bar = [&](int s) { return bars + 8u * (2 * STAGES + 4 + s); };
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + BAR_OFF + NUM_BARS * 8);
+  auto empty_bar = [&](int s) { return bars + 8u * (MAX_STAGES + s); };
+  auto tfull_bar = [&](int s) { return bars + 8u * (2 * MAX_STAGES + s); };
+  auto tempty_bar = [&](int s) { return bars + 8u * (2 * MAX_STAGES + 2 + s); };
+  auto res_bar = [&](int g, int s) { return bars + 8u * (2 * MAX_STAGES + 4 + 2 * g + s); };
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + bar_off + NUM_BARS * 8);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int pad = (a.taps - 1) / 2;
@@ -69,11 +85,13 @@ tc_conv_gemm_staged_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
   const bool ln = (a.epi == EPI_RES_LN || a.epi == EPI_RELU_LN);
 
   griddep_launch_dependents();   // PDL (fs2_common.cuh)
+  if (base & 1023u) __trap();    // the swizzled tiles assume a 1024-byte aligned dynamic shared memory window
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
-    for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 4); mbar_init(res_bar(s), 1); }
+    for (int s = 0; s < MAX_STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 8); }
+    for (int g = 0; g < 2; ++g) for (int s = 0; s < 2; ++s) mbar_init(res_bar(g, s), 1);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -81,11 +99,9 @@ tc_conv_gemm_staged_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
     tmem_relinquish();
   }
   if (warp >= 2) {
-    const int t = threadIdx.x - 64;
-    for (int i = t; i < 256; i += 128) {
-      s_g[i] = ln ? __ldg(a.ln_g + i) : 1.f;
-      s_b[i] = ln ? __ldg(a.ln_b + i) : 0.f;
-    }
+    const int i = threadIdx.x - 64;   // 0..255
+    s_g[i] = ln ? __ldg(a.ln_g + i) : 1.f;
+    s_b[i] = ln ? __ldg(a.ln_b + i) : 0.f;
   }
   griddep_wait();   // first access to predecessor-written global memory is below
   fence_before_sync();
@@ -112,7 +128,7 @@ tc_conv_gemm_staged_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
             const uint32_t sa = base + stage * STAGE_BYTES;
             tma_load_3d(sa, &tmA, full_bar(stage), k0, r0 + t - pad, pa);
             tma_load_2d(sa + A_BYTES, &tmB, full_bar(stage), k0, (pb * a.taps + t) * a.N + n0);
-            if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+            if (++stage == stages) { stage = 0; phase ^= 1u; }
           }
         }
       }
@@ -138,42 +154,57 @@ tc_conv_gemm_staged_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
           for (int k = 0; k < BKE / 16; ++k)
             umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (it | k) ? 1u : 0u);
           umma_commit(empty_bar(stage));
-          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+          if (++stage == stages) { stage = 0; phase ^= 1u; }
         }
         umma_commit(tfull_bar(as));
         if (++as == 2) { as = 0; aphase ^= 1u; }
       }
     }
   } else {
-    // ===================================================== epilogue (warps 2..5, 128 threads, thread = output row)
+    // ===================================================== epilogue: 2 groups x 4 warps, thread = (output row, column half)
+    const int g = (warp - 2) >> 2;                  // group = column half
     const int q = warp & 3;                         // TMEM lane quarter this warp may access
     const int row = q * 32 + lane;                  // row in tile
-    const bool elected = threadIdx.x == 64;
+    const bool elected = threadIdx.x == 64 + g * 128;
+    const int bar_grp_id = 1 + g, bar_pair_id = 3 + q;
+    auto bar_grp = [&]() { asm volatile("bar.sync %0, 128;" ::"r"(bar_grp_id) : "memory"); };
     const int sw128 = row & 7, sw64 = (row >> 1) & 3;
-    uint8_t* resbuf = smem + RES_OFF;
-    uint8_t* outf_row = smem + OUTF_OFF + row * 128;
-    uint8_t* outb_row = smem + OUTB_OFF + row * 64;
+    const int grp_off = ring_bytes + g * grp_sz;
+    const bool wide = stages == 2;                  // F buffers exist
+    uint8_t* Fbuf = smem + grp_off;                 // F0 | F1 (wide plan only)
+    uint8_t* Bbuf = smem + grp_off + (wide ? 2 * CH_F32 : 0);
     const bool has_res = a.epi == EPI_RES_LN;
     const int out_planes = a.out_planes == 3 ? 3 : a.out_planes == 2 ? 2 : 1;
+    float* my_bias = s_bias + g * 128;
+    const float* my_g = s_g + g * 128;
+    const float* my_b = s_b + g * 128;
     int res_cnt = 0;                                // residual chunks consumed so far by this thread (buffer / parity)
     int as = 0; uint32_t aphase = 0;
+    uint32_t tile_par = 0;
 
-    // Stage one 32-column chunk of this thread's row and ship it: fp32 tile via mapF (if wf), bf16 plane tiles via mapB
-    // (if wb).  Two 128-thread barriers: [A] the previous TMA stores have finished reading the staging tiles,
-    // [B] all rows of the new tiles are written and visible to the async proxy.
-    auto stage_out = [&](const float (&y)[32], int col, int r0, bool wf, bool wb, const CUtensorMap* mapB) {
-      if (elected) tma_store_wait_read();
-      bar_epi();
+    // Stage one 32-column chunk (index c within the group's half) of this thread's row and ship it.
+    //   wf: fp32 tile via tmOutF, staged in F[c & 1]; wb: bf16 plane tiles via mapB, staged in B (or, when bF, in F[c & 1]).
+    // Commit order is B group then F group, so that wait_group.read 1 (all but the newest group have been read out) frees
+    // both B and F[c & 1] while the previous chunk's fp32 store may still be in flight.
+    auto stage_out = [&](const float (&y)[32], int c, int gcol, int r0, bool wf, bool wb, bool bF, const CUtensorMap* mapB) {
+      uint8_t* fb = Fbuf + (c & 1) * CH_F32;
+      uint8_t* bb = bF ? fb : Bbuf;
+      if (elected) {
+        if (wf || bF) tma_store_wait_read_n<1>(); else tma_store_wait_read_n<0>();
+      }
+      bar_grp();
       if (wf) {
+        uint8_t* o = fb + row * 128;
 #pragma unroll
         for (int j = 0; j < 8; ++j)
-          *reinterpret_cast<float4*>(outf_row + ((j ^ sw128) << 4)) = make_float4(y[4 * j], y[4 * j + 1], y[4 * j + 2], y[4 * j + 3]);
+          *reinterpret_cast<float4*>(o + ((j ^ sw128) << 4)) = make_float4(y[4 * j], y[4 * j + 1], y[4 * j + 2], y[4 * j + 3]);
       }
       if (wb) {
+        uint8_t* orow = bb + row * 64;
         if (out_planes == 1) {
 #pragma unroll
           for (int j = 0; j < 4; ++j)
-            *reinterpret_cast<uint4*>(outb_row + ((j ^ sw64) << 4)) =
+            *reinterpret_cast<uint4*>(orow + ((j ^ sw64) << 4)) =
                 make_uint4(pack_bf16x2(y[8 * j], y[8 * j + 1]), pack_bf16x2(y[8 * j + 2], y[8 * j + 3]),
                            pack_bf16x2(y[8 * j + 4], y[8 * j + 5]), pack_bf16x2(y[8 * j + 6], y[8 * j + 7]));
         } else if (out_planes == 2) {
@@ -182,7 +213,7 @@ tc_conv_gemm_staged_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
             uint32_t h[4], l[4];
 #pragma unroll
             for (int u = 0; u < 4; ++u) split2h_pair(y[8 * j + 2 * u], y[8 * j + 2 * u + 1], h[u], l[u]);
-            uint8_t* o = outb_row + ((j ^ sw64) << 4);
+            uint8_t* o = orow + ((j ^ sw64) << 4);
             *reinterpret_cast<uint4*>(o) = make_uint4(h[0], h[1], h[2], h[3]);
             *reinterpret_cast<uint4*>(o + CH_B16) = make_uint4(l[0], l[1], l[2], l[3]);
           }
@@ -192,7 +223,7 @@ tc_conv_gemm_staged_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
             float h[8], m[8], l[8];
 #pragma unroll
             for (int u = 0; u < 8; ++u) split3(y[8 * j + u], h[u], m[u], l[u]);
-            uint8_t* o = outb_row + ((j ^ sw64) << 4);
+            uint8_t* o = orow + ((j ^ sw64) << 4);
             *reinterpret_cast<uint4*>(o) = make_uint4(pack_bf16x2(h[0], h[1]), pack_bf16x2(h[2], h[3]), pack_bf16x2(h[4], h[5]), pack_bf16x2(h[6], h[7]));
             *reinterpret_cast<uint4*>(o + CH_B16) = make_uint4(pack_bf16x2(m[0], m[1]), pack_bf16x2(m[2], m[3]), pack_bf16x2(m[4], m[5]), pack_bf16x2(m[6], m[7]));
             *reinterpret_cast<uint4*>(o + 2 * CH_B16) = make_uint4(pack_bf16x2(l[0], l[1]), pack_bf16x2(l[2], l[3]), pack_bf16x2(l[4], l[5]), pack_bf16x2(l[6], l[7]));
@@ -200,53 +231,76 @@ tc_conv_gemm_staged_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
         }
       }
       fence_proxy_async();
-      bar_epi();
+      bar_grp();
       if (elected) {
-        if (wf) tma_store_2d(&tmOutF, base + OUTF_OFF, col, r0);
-        if (wb)
-          for (int p = 0; p < out_planes; ++p) tma_store_3d(mapB, base + OUTB_OFF + p * CH_B16, col, r0, p);
-        tma_store_commit();
+        if (wb) {
+          const uint32_t bsm = base + (uint32_t)(bb - smem);
+          for (int p = 0; p < out_planes; ++p) tma_store_3d(mapB, bsm + p * CH_B16, gcol, r0, p);
+          tma_store_commit();
+        }
+        if (wf) {
+          tma_store_2d(&tmOutF, base + (uint32_t)(fb - smem), gcol, r0);
+          tma_store_commit();
+        }
       }
     };
 
+    unsigned next_code = FS2_ROW_NONE;
+    {
+      const int r_first = ((int)blockIdx.x / num_n_blocks) * BM + row;
+      if ((int)blockIdx.x < num_tiles && r_first < R) next_code = __ldg(a.lay.rowmap + r_first);
+    }
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m_blk = tile / num_n_blocks, n_blk = tile - m_blk * num_n_blocks;
       const int n0 = n_blk * BN, r0 = m_blk * BM;
-      // residual prefetch (overlaps the tile's mainloop): chunks 0 and 1
+      const int gc0 = g * 128;                       // this group's first column within the tile
+      // residual prefetch: chunks 0 and 1 of this group's half (the F buffers double as output staging in pass 2 of the
+      // previous tile: wait until those stores have been read out)
       if (has_res && elected) {
+        tma_store_wait_read_n<0>();
         for (int c = 0; c < 2; ++c) {
           const int buf = (res_cnt + c) & 1;
-          mbar_expect_tx(res_bar(buf), CH_F32);
-          tma_load_2d(base + RES_OFF + buf * CH_F32, &tmRes, res_bar(buf), c * 32, r0);
+          mbar_expect_tx(res_bar(g, buf), CH_F32);
+          tma_load_2d(base + grp_off + buf * CH_F32, &tmRes, res_bar(g, buf), gc0 + c * 32, r0);
         }
       }
-      // bias slice of this tile
-      bar_epi();
-      for (int i = threadIdx.x - 64; i < BN; i += 128) s_bias[i] = (n0 + i < a.N) ? __ldg(a.bias + n0 + i) : 0.f;
-      bar_epi();
+      // bias slice of this group's half of the tile
+      bar_grp();
+      {
+        const int i = threadIdx.x - 64 - g * 128;
+        my_bias[i] = (n0 + gc0 + i < a.N) ? __ldg(a.bias + n0 + gc0 + i) : 0.f;
+      }
+      bar_grp();
 
-      const int r = r0 + row;
-      const RowPos rp = row_pos(a.lay, r, R);
-      const bool keep_len = rp.in_grid && (a.lay.lens == nullptr || rp.p < __ldg(a.lay.lens + rp.b));
-      const bool keep = (a.mask_mode == MASK_LEN) ? keep_len : rp.in_grid;
+      // (b, p) of this thread's row; the code of the next tile's row is fetched now so its latency is off the critical path
+      const unsigned code = next_code;
+      {
+        const int nt = tile + gridDim.x;
+        const int rn = (nt / num_n_blocks) * BM + row;
+        next_code = (nt < num_tiles && rn < R) ? __ldg(a.lay.rowmap + rn) : FS2_ROW_NONE;
+      }
+      const bool in_grid = code != FS2_ROW_NONE;
+      const int rb = in_grid ? (int)(code >> 16) : 0, rpp = in_grid ? (int)(code & 0xFFFFu) : 0;
+      const bool keep_len = in_grid && (a.lay.lens == nullptr || rpp < __ldg(a.lay.lens + rb));
+      const bool keep = (a.mask_mode == MASK_LEN) ? keep_len : in_grid;
 
       mbar_wait(tfull_bar(as), aphase);
       fence_after_sync();
-      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN);
+      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN + gc0);
       uint32_t v[32];
 
       if (ln) {
-        // ---- pass 1: pre-norm value, row statistics, park the row back in TMEM
+        // ---- pass 1: pre-norm value, partial row statistics, park the row back in TMEM
         float sum = 0.f, sq = 0.f;
-        for (int c = 0; c < BN / 32; ++c) {
+        for (int c = 0; c < 4; ++c) {
           __syncwarp();
           tmem_ld32(t_row + c * 32, v);
           tmem_wait_ld();
           float rr[32];
           if (has_res) {
             const int buf = res_cnt & 1;
-            mbar_wait(res_bar(buf), (uint32_t)((res_cnt >> 1) & 1));
-            const uint8_t* rrow = resbuf + buf * CH_F32 + row * 128;
+            mbar_wait(res_bar(g, buf), (uint32_t)((res_cnt >> 1) & 1));
+            const uint8_t* rrow = smem + grp_off + buf * CH_F32 + row * 128;
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
               const float4 t4 = *reinterpret_cast<const float4*>(rrow + ((j ^ sw128) << 4));
@@ -258,7 +312,7 @@ tc_conv_gemm_staged_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
           }
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
-            float x = fmaf(__uint_as_float(v[j]), asc, s_bias[c * 32 + j]) + rr[j];
+            float x = fmaf(__uint_as_float(v[j]), asc, my_bias[c * 32 + j]) + rr[j];
             if (!has_res) x = fmaxf(x, 0.f);
             sum += x;
             sq = fmaf(x, x, sq);
@@ -266,72 +320,80 @@ tc_conv_gemm_staged_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
           }
           tmem_st32(t_row + c * 32, v);
           if (has_res) {
-            bar_epi();                               // every row of this staging buffer has been read
-            if (elected && c + 2 < BN / 32) {
+            bar_grp();                               // every row of this staging buffer has been read
+            if (elected && c + 2 < 4) {
               const int buf = res_cnt & 1;
-              mbar_expect_tx(res_bar(buf), CH_F32);
-              tma_load_2d(base + RES_OFF + buf * CH_F32, &tmRes, res_bar(buf), (c + 2) * 32, r0);
+              mbar_expect_tx(res_bar(g, buf), CH_F32);
+              tma_load_2d(base + grp_off + buf * CH_F32, &tmRes, res_bar(g, buf), gc0 + (c + 2) * 32, r0);
             }
             ++res_cnt;
           }
         }
         tmem_wait_st();
-        const float mean = sum * (1.0f / 256.0f);
-        const float var = fmaxf(sq * (1.0f / 256.0f) - mean * mean, 0.f);
+        // the two threads of a row (one per group) exchange their partial sums
+        s_stat[(tile_par * 2 + g) * 128 + row] = make_float2(sum, sq);
+        asm volatile("bar.sync %0, 64;" ::"r"(bar_pair_id) : "memory");
+        const float2 other = s_stat[(tile_par * 2 + (g ^ 1)) * 128 + row];
+        // add in a fixed order (group 0 first) so that both threads of the row derive bit-identical statistics
+        const float tsum = g == 0 ? sum + other.x : other.x + sum;
+        const float tsq = g == 0 ? sq + other.y : other.y + sq;
+        const float mean = tsum * (1.0f / 256.0f);
+        const float var = fmaxf(tsq * (1.0f / 256.0f) - mean * mean, 0.f);
         const float rstd = rsqrtf(var + 1e-5f);
         // ---- pass 2: normalise, affine, mask, stage + store
-        for (int c = 0; c < BN / 32; ++c) {
+        for (int c = 0; c < 4; ++c) {
           __syncwarp();
           tmem_ld32(t_row + c * 32, v);
           tmem_wait_ld();
           float y[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
-            const float x = (__uint_as_float(v[j]) - mean) * rstd * s_g[c * 32 + j] + s_b[c * 32 + j];
+            const float x = (__uint_as_float(v[j]) - mean) * rstd * my_g[c * 32 + j] + my_b[c * 32 + j];
             y[j] = keep ? x : 0.f;
           }
-          stage_out(y, c * 32, r0, a.out != nullptr, a.out_b != nullptr, &tmOutB0);
+          stage_out(y, c, gc0 + c * 32, r0, a.out != nullptr, a.out_b != nullptr, false, &tmOutB0);
         }
       } else if (a.epi == EPI_QKV) {
         // n_blk 0 -> Q, 1 -> K (bf16 [R,256] tiles); 2 -> V transposed: vt[d, flat row]
-        for (int c = 0; c < BN / 32; ++c) {
+        for (int c = 0; c < 4; ++c) {
           __syncwarp();
           tmem_ld32(t_row + c * 32, v);
           tmem_wait_ld();
           float y[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) y[j] = rp.in_grid ? fmaf(__uint_as_float(v[j]), asc, s_bias[c * 32 + j]) : 0.f;
+          for (int j = 0; j < 32; ++j) y[j] = in_grid ? fmaf(__uint_as_float(v[j]), asc, my_bias[c * 32 + j]) : 0.f;
           if (n_blk < 2) {
-            stage_out(y, c * 32, r0, false, true, n_blk == 0 ? &tmOutB0 : &tmOutB1);
+            stage_out(y, c, gc0 + c * 32, r0, false, true, true, n_blk == 0 ? &tmOutB0 : &tmOutB1);
           } else {
-            if (elected) tma_store_wait_read();
-            bar_epi();
-            bf16* vt_s = reinterpret_cast<bf16*>(smem + OUTF_OFF);       // [32 d][128 rows]
+            uint8_t* fb = Fbuf + (c & 1) * CH_F32;
+            if (elected) tma_store_wait_read_n<1>();
+            bar_grp();
+            bf16* vt_s = reinterpret_cast<bf16*>(fb);                   // [32 d][128 rows]
 #pragma unroll
             for (int j = 0; j < 32; ++j) vt_s[j * BM + row] = __float2bfloat16_rn(y[j]);
             fence_proxy_async();
-            bar_epi();
+            bar_grp();
             if (elected) {
-              tma_store_2d(&tmVt, base + OUTF_OFF, r0, c * 32);
+              tma_store_2d(&tmVt, base + (uint32_t)(fb - smem), r0, gc0 + c * 32);
               tma_store_commit();
             }
           }
         }
       } else {
         // ---- EPI_BIAS / EPI_RELU / EPI_TANH
-        for (int c = 0; c < BN / 32; ++c) {
+        for (int c = 0; c < 4; ++c) {
           __syncwarp();
           tmem_ld32(t_row + c * 32, v);
           tmem_wait_ld();
           float y[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
-            float x = fmaf(__uint_as_float(v[j]), asc, s_bias[c * 32 + j]);
+            float x = fmaf(__uint_as_float(v[j]), asc, my_bias[c * 32 + j]);
             if (a.epi == EPI_RELU) x = fmaxf(x, 0.f);
             if (a.epi == EPI_TANH) x = tanhf(x);
             y[j] = keep ? x : 0.f;
           }
-          stage_out(y, n0 + c * 32, r0, a.out != nullptr, a.out_b != nullptr, &tmOutB0);
+          stage_out(y, c, n0 + gc0 + c * 32, r0, a.out != nullptr, a.out_b != nullptr, false, &tmOutB0);
         }
       }
       // release the accumulator stage to the MMA warp
@@ -339,6 +401,7 @@ tc_conv_gemm_staged_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(as));
       if (++as == 2) { as = 0; aphase ^= 1u; }
+      tile_par ^= 1u;
     }
     if (elected) tma_store_wait_all();   // staging tiles must outlive the last TMA store
   }
@@ -349,6 +412,13 @@ tc_conv_gemm_staged_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
     fence_after_sync();
     tmem_dealloc(tmem_base, TMEM_COLS);
   }
+}
+
+// 2 stages ("wide": fp32 staging buffers) whenever the epilogue moves fp32 tiles or V^T; these are the small-K GEMMs
+// whose mainloop hides behind the epilogue anyway.  3 stages ("deep") for the mainloop-bound bf16-only producers
+// (FFN conv k=9, PostNet k=5, predictor conv1).
+int stages_for(const ConvGemmArgs& a) {
+  return (a.epi == EPI_RES_LN || a.epi == EPI_QKV || a.out != nullptr) ? 2 : 3;
 }
 
 }  // namespace
@@ -397,9 +467,9 @@ int tc_conv_gemm_staged_launch(const ConvGemmArgs& a, cudaStream_t st) {
   }
   if (!ok) return fs2_fail_cuda(cudaErrorInvalidValue, "cuTensorMapEncodeTiled(staged epilogue)");
   static bool configured = false;
-  const int smem = SMEM_TOTAL + 1024;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(tc_conv_gemm_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaError_t e = cudaFuncSetAttribute(tc_conv_gemm_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         smem_total(2) > smem_total(3) ? smem_total(2) : smem_total(3));
     if (e != cudaSuccess) return fs2_fail_cuda(e, "cudaFuncSetAttribute(tc_conv_gemm_staged)");
     configured = true;
   }
@@ -415,7 +485,9 @@ int tc_conv_gemm_staged_launch(const ConvGemmArgs& a, cudaStream_t st) {
   const int grid = tiles < num_sms ? tiles : num_sms;
   ConvGemmArgs b = a;
   if (a.epi == EPI_QKV) b.out_planes = 1;
-  (void)FS2_LAUNCH(tc_conv_gemm_staged_kernel, grid, NUM_THREADS, smem, st, tmA, tmB, tmRes, tmOutF, tmOutB0, tmOutB1, tmVt, b, num_n_blocks);
+  const int stages = stages_for(a);
+  (void)FS2_LAUNCH(tc_conv_gemm_staged_kernel, grid, NUM_THREADS, smem_total(stages), st, tmA, tmB, tmRes, tmOutF, tmOutB0,
+                   tmOutB1, tmVt, b, num_n_blocks, stages);
   ++g_fs2_launches;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fs2_fail_cuda(e, "tc_conv_gemm_staged_kernel launch");
