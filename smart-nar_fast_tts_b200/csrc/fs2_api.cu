@@ -8,6 +8,7 @@
 #include <math.h>
 #include <stdio.h>
 #include <string.h>
+#include <stdlib.h>
 #include <map>
 #include <string>
 #include <vector>
@@ -295,16 +296,21 @@ cudaError_t make_shadow(const float* x, size_t n, int prec, bf16* xb, cudaStream
 
 // Device-resident ragged row layout (fs2_common.cuh) in workspace buffers named `name`.* ; lens32 = null -> every
 // utterance has S grid rows.  halo_keep: padded rows kept after the valid ones (>= S: the reference's padded grid).
+// extra_ext > 0: one pseudo utterance with extra_ext grid rows is appended (index B; the layout then has B + 1
+// utterances and carries no lens pointer: it is used with MASK_GRID only).
 int make_layout(fs2_handle* h, const std::string& name, const int* lens32, int B, int S, int halo_keep, int halo_rows,
-                RowLayout* out, cudaStream_t st) {
-  if (B > 65535) return h->fail(FS2_ERR_UNSUPPORTED, "more than 65535 utterances in one call");
+                RowLayout* out, cudaStream_t st, int extra_ext = 0) {
+  const int Bt = B + (extra_ext > 0 ? 1 : 0);
+  if (Bt > 65535) return h->fail(FS2_ERR_UNSUPPORTED, "more than 65535 utterances in one call");
   if (S > FS2_MAX_ROWS_PER_UTT) return h->fail(FS2_ERR_UNSUPPORTED, "more than 65535 rows per utterance");
-  const int R_cap = B * FS2_ROWS_PER_UTT(S, halo_rows);
-  WS(int, off, name + ".off", (size_t)B + 1);
-  WS(int, ext, name + ".ext", (size_t)B);
+  // host-known upper bound of the rows in use: a real utterance never needs more than lens + halo_keep <= S grid rows
+  const int R_cap = B * FS2_ROWS_PER_UTT(S, halo_rows) + (extra_ext > 0 ? FS2_ROWS_PER_UTT(extra_ext, halo_rows) : 0);
+  WS(int, off, name + ".off", (size_t)Bt + 1);
+  WS(int, ext, name + ".ext", (size_t)Bt);
   WS(unsigned, rowmap, name + ".map", (size_t)R_cap);
-  HCHECK(rowops_build_layout(lens32, B, S, halo_keep, halo_rows, off, ext, rowmap, R_cap, st));
-  out->B = B; out->S = S; out->R_cap = R_cap; out->off = off; out->ext = ext; out->lens = lens32; out->rowmap = rowmap;
+  HCHECK(rowops_build_layout(lens32, B, S, halo_keep, halo_rows, off, ext, rowmap, R_cap, st, extra_ext));
+  out->B = Bt; out->S = S; out->R_cap = R_cap; out->off = off; out->ext = ext; out->lens = extra_ext > 0 ? nullptr : lens32;
+  out->rowmap = rowmap;
   return FS2_OK;
 }
 
@@ -479,20 +485,26 @@ int run_predictor(fs2_handle* h, PredW& P, int prec, const float* x, const bf16*
   return FS2_OK;
 }
 
-// fastspeech2_align.py:83-85: mel_linear, PostNet (BatchNorm folded), residual.  dec follows `lay` (possibly packed);
-// PostNet runs on the reference's full padded grid [B, T] because its padded rows are returned to the caller
-// (SURVEY.md a15): mel_linear scatters into that uniform grid and the rows the packed layout does not carry -- whose
-// decoder output is exactly zero -- are filled with the bias row.
+// fastspeech2_align.py:83-85: mel_linear, PostNet (BatchNorm folded), residual.  dec follows `lay` (possibly packed).
+// The reference runs PostNet over the whole padded grid [B, T] and returns its padded rows, which are not masked
+// (SURVEY.md a15).  A row farther than H = layers * (k-1)/2 from the last valid frame sees only mel_linear's bias row (the
+// decoder output there is exactly zero) and the zero padding past T: its value depends only on its distance to T.  So
+// PostNet runs on a packed grid -- utterance b keeps min(len_b + 2H, T) rows, of which the first len_b + H come out
+// exact -- plus ONE pseudo utterance of min(T, 2H+1) all-bias rows whose outputs are copied into every farther row.
 int run_mel_postnet(fs2_handle* h, int prec, const float* dec, const bf16* decb, const RowLayout& lay, float* mel,
                     float* mel_post, cudaStream_t st) {
   const int M = h->dims.n_mel, P = h->dims.pn_dim, NL = h->dims.pn_layers;
-  const int B = lay.B, T = lay.S, TA = FS2_ROWS_PER_UTT(T, FS2_HALO);   // rows per utterance of the PostNet grid
-  const size_t R = (size_t)B * TA;
+  const int B = lay.B, T = lay.S;
+  const int H = NL * ((h->dims.pn_kernel - 1) / 2);
   const bool tc = prec != FS2_PREC_FP32;
   const size_t np = (size_t)planes_of(prec);
   RowLayout pn;
-  RCHECK(make_layout(h, "pn.lay", nullptr, B, T, T, FS2_HALO, &pn, st));
+  // never fewer rows than the source layout carries (mel_linear scatters every source grid row into this grid)
+  const int keep = !lay.lens ? T : (h->halo_keep > 2 * H ? h->halo_keep : 2 * H);
+  RCHECK(make_layout(h, "pn.lay", lay.lens, B, T, keep, FS2_HALO, &pn, st, T < 2 * H + 1 ? T : 2 * H + 1));
+  const size_t R = (size_t)pn.R_cap;
   WS(float, melg, "pn.mel", R * M);
+  WS(float, postg, "pn.post", R * M);
   bf16 *melb = nullptr, *pa_b = nullptr, *pb_b = nullptr;
   float *pa = nullptr, *pb = nullptr;
   if (tc) {
@@ -504,13 +516,14 @@ int run_mel_postnet(fs2_handle* h, int prec, const float* dec, const bf16* decb,
     WS(float, t2, "pn.b", R * P); pb = t2;
   }
   ConvGemmArgs a = base_args(h->mel_linear, lay);
-  a.A = dec; a.Ab = decb; a.epi = EPI_BIAS; a.mask_mode = MASK_GRID; a.dst_SA = TA;
+  a.A = dec; a.Ab = decb; a.epi = EPI_BIAS; a.mask_mode = MASK_GRID; a.dst_off = pn.off; a.dst_R_cap = pn.R_cap;
   a.out = melg; a.ldo = M; a.out_b = melb; a.ldob = M; a.out_user = mel; a.ldu = M;
   RCHECK(run_gemm(h, prec, a, st, "mel_linear"));
   {
     PROF("rows.fill_padded");
-    HCHECK(rowops_fill_padded_rows(h->mel_linear.bias, M, lay, TA, melg, melb, (int)np, mel, st));
+    HCHECK(rowops_fill_padded_rows(h->mel_linear.bias, M, lay, pn, melg, melb, (int)np, mel, st));
   }
+
   const float* in_f = melg; const bf16* in_b = melb;
   for (int i = 0; i < NL; ++i) {
     a = base_args(h->postnet[i], pn);
@@ -521,9 +534,13 @@ int run_mel_postnet(fs2_handle* h, int prec, const float* dec, const bf16* decb,
       a.out = of; a.ldo = P; a.out_b = ob; a.ldob = P;
       in_f = of; in_b = ob;
     } else {
-      a.epi = EPI_RES; a.residual = melg; a.out_user = mel_post; a.ldu = M;
+      a.epi = EPI_RES; a.residual = melg; a.out = postg; a.ldo = M; a.out_user = mel_post; a.ldu = M; a.out_user_B = B;
     }
     RCHECK(run_gemm(h, prec, a, st, "postnet." + std::to_string(i)));
+  }
+  {
+    PROF("rows.postnet_far");
+    HCHECK(rowops_postnet_far_rows(postg, M, pn, B, H, mel_post, st));
   }
   return FS2_OK;
 }

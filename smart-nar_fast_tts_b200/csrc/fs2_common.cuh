@@ -91,8 +91,10 @@ struct ConvGemmArgs {
   const float* bias;
   int N, taps;
   // rows
-  RowLayout lay;    // layout of A (and of out / out_b / residual unless dst_SA > 0)
-  int dst_SA;       // > 0: out / out_b rows are addressed b*dst_SA + p (uniform destination grid), grid rows only
+  RowLayout lay;    // layout of A (and of out / out_b / residual unless dst_off is set)
+  const int* dst_off;  // non-null: out / out_b live in ANOTHER ragged layout whose utterance b starts at row dst_off[b]
+                       // (device): the row of (b, p) is dst_off[b] + p; only grid rows of `lay` are written
+  int dst_R_cap;       // rows allocated in that layout (plane stride of out_b)
   int epi, mask_mode;
   const float* residual;  // grid layout, ld == N
   const float* ln_g;
@@ -106,12 +108,38 @@ struct ConvGemmArgs {
   int ldob;
   float* out_user; // dense user layout: row (b,p), p < S, at (b*S + p)*ldu
   int ldu;
+  int out_user_B;  // > 0: only utterances b < out_user_B exist in out_user (the layout carries extra pseudo utterances)
   // EPI_QKV extras (tcgen05 path)
   bf16* q_b;   // [R, 256]
   bf16* k_b;   // [R, 256]
   bf16* vt_b;  // [H*dk, Rv]  V transposed: row h*dk + d, column = flat row index r
   int Rv;      // R_cap rounded up to 8 (16-byte row pitch for TMA)
 };
+
+// Loads of data written by OTHER kernels of the forward (activations, layout tables, lengths): plain coherent
+// ld.global issued from volatile asm.  They must NOT be __ldg / ld.global.nc, and must not go through a
+// `const T* __restrict__` kernel parameter (nvcc turns those into ld.global.nc as well): ptxas schedules non-coherent
+// loads ABOVE griddepcontrol.wait (seen in SASS: LDG.E.CONSTANT issued before ACQBULK), i.e. before the producing
+// kernel has finished under programmatic dependent launch -- stale layout tables were read that way (profiles/r1g
+// notes).  Volatile asm keeps program order against the (volatile) griddepcontrol.wait.  Weights / biases, which no
+// kernel of the forward writes, may keep __ldg.
+__device__ __forceinline__ int ld_act(const int* p) {
+  int v; asm volatile("ld.global.b32 %0, [%1];" : "=r"(v) : "l"(p)); return v;
+}
+__device__ __forceinline__ unsigned ld_act(const unsigned* p) {
+  unsigned v; asm volatile("ld.global.b32 %0, [%1];" : "=r"(v) : "l"(p)); return v;
+}
+__device__ __forceinline__ float ld_act(const float* p) {
+  float v; asm volatile("ld.global.f32 %0, [%1];" : "=f"(v) : "l"(p)); return v;
+}
+__device__ __forceinline__ long long ld_act(const long long* p) {
+  long long v; asm volatile("ld.global.b64 %0, [%1];" : "=l"(v) : "l"(p)); return v;
+}
+__device__ __forceinline__ float4 ld_act(const float4* p) {
+  float4 v;
+  asm volatile("ld.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
+}
 
 // (b, p) of a flat row
 struct RowPos {
@@ -120,7 +148,7 @@ struct RowPos {
 };
 __device__ __forceinline__ RowPos row_pos(const RowLayout& lay, int r, int R) {
   RowPos rp;
-  const unsigned code = (r < R) ? __ldg(lay.rowmap + r) : FS2_ROW_NONE;
+  const unsigned code = (r < R) ? ld_act(lay.rowmap + r) : FS2_ROW_NONE;
   rp.in_grid = code != FS2_ROW_NONE;
   rp.b = rp.in_grid ? (int)(code >> 16) : 0;
   rp.p = rp.in_grid ? (int)(code & 0xFFFFu) : 0;
@@ -169,8 +197,9 @@ int tc_attention_launch(const bf16* q, const bf16* k, const bf16* vt, const RowL
 // row operators (fs2_rowops.cu)
 // off/ext/rowmap of `lay` from lens32 (device; null = every utterance has S rows): ext = min(lens + halo_keep, S),
 // each utterance followed by halo_rows zero rows (FS2_HALO for GEMM operands, 0 for dense user tensors).
+// extra_ext > 0 appends one pseudo utterance (index B) with extra_ext grid rows: off has B + 2 entries, ext B + 1.
 cudaError_t rowops_build_layout(const int* lens32, int B, int S, int halo_keep, int halo_rows, int* off, int* ext,
-                                unsigned* rowmap, int R_cap, cudaStream_t st);
+                                unsigned* rowmap, int R_cap, cudaStream_t st, int extra_ext = 0);
 cudaError_t rowops_embed_pe(const int64_t* texts, const float* emb, const float* pe, int vocab, const RowLayout& lay,
                             int D, float* out_grid, bf16* out_b, int out_planes, float* out_user, cudaStream_t st);
 cudaError_t rowops_lens_to_i32(const int64_t* lens, int B, int cap, int* out, cudaStream_t st);
@@ -184,10 +213,16 @@ cudaError_t rowops_length_regulate(const float* x, const int* src_off, int src_s
 cudaError_t rowops_variance_embed(float* pred, float control, const float* bins, int n_bins, const float* emb,
                                   const float* pe, float* x, bf16* xb, int xb_planes, const RowLayout& lay, int D,
                                   int* idx_out, cudaStream_t st);
-// rows p in [ext[b], S) of a uniform destination grid (dst_SA rows per utterance) <- bias row (mel_linear of a zero
-// decoder row), halo rows p in [S, dst_SA) <- 0; also the user tensor [B,S,N]
-cudaError_t rowops_fill_padded_rows(const float* bias, int N, const RowLayout& lay, int dst_SA, float* out_grid,
+// mel_linear rows that the (packed) source layout `src` does not carry, in the destination layout `dst` (PostNet grid,
+// possibly with one pseudo utterance at index src.B): grid rows p in [src.ext[b], dst.ext[b]) <- bias row (mel_linear of
+// a zero decoder row), the rows after them up to the next utterance <- 0, every grid row of the pseudo utterance <- bias;
+// and the user tensor [B,S,N] rows p in [src.ext[b], S) <- bias
+cudaError_t rowops_fill_padded_rows(const float* bias, int N, const RowLayout& src, const RowLayout& dst, float* out_grid,
                                     bf16* out_b, int out_planes, float* out_user, cudaStream_t st);
+// PostNet rows farther than H from the last valid frame depend only on the bias row and on their distance to the end of
+// the grid: copy them from the pseudo utterance (index B of `pn`, min(S, 2H+1) all-bias rows) into out_user [B,S,N]
+cudaError_t rowops_postnet_far_rows(const float* post_grid, int N, const RowLayout& pn, int B, int H, float* out_user,
+                                    cudaStream_t st);
 cudaError_t rowops_gaussian_upsample(const float* x, const float* d, int B, int L, int D, int T, int T_w, float* out,
                                      float* s, float* w, cudaStream_t st);
 cudaError_t rowops_to_grid(const float* x_user, const RowLayout& lay, int C, float* out, int ldo, int col_off,

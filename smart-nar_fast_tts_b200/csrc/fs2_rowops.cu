@@ -13,7 +13,7 @@ int g_fs2_pdl = getenv("FS2_NO_PDL") ? 0 : 1;
 
 namespace {
 
-__device__ __forceinline__ float4 ld4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ float4 ld4(const float* p) { return ld_act(reinterpret_cast<const float4*>(p)); }
 __device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
 __device__ __forceinline__ uint32_t pack2(float a, float b) {
   __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
@@ -53,9 +53,11 @@ __device__ __forceinline__ void store_planes4(bf16* dst, size_t plane_elems, int
 // Ragged-grid layout (fs2_common.cuh): ext[b] = min(lens[b] + halo_keep, S); off = exclusive scan of ext + halo_rows
 // rounded up to FS2_ROW_ALIGN rows (utterances start on 16-byte boundaries of the transposed-V operand).
 // One CTA, chunks of 1024 utterances, block-wide scan by warp shuffles.
-__global__ void __launch_bounds__(1024) build_layout_kernel(const int* __restrict__ lens, int B, int S, int halo_keep,
-                                                            int halo_rows, int* __restrict__ off, int* __restrict__ ext) {
+__global__ void __launch_bounds__(1024) build_layout_kernel(const int* lens, int Breal, int S, int halo_keep,
+                                                            int halo_rows, int* off, int* ext,
+                                                            int extra_ext) {
   FS2_PDL_PROLOGUE();
+  const int B = Breal + (extra_ext > 0 ? 1 : 0);   // the pseudo utterance (index Breal) has extra_ext grid rows
   __shared__ int warp_tot[32];
   __shared__ int carry_s;
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
@@ -65,7 +67,7 @@ __global__ void __launch_bounds__(1024) build_layout_kernel(const int* __restric
     const int b = base + tid;
     int e = 0, v = 0;
     if (b < B) {
-      const long long want = lens ? (long long)lens[b] + halo_keep : (long long)S;
+      const long long want = b >= Breal ? (long long)extra_ext : lens ? (long long)lens[b] + halo_keep : (long long)S;
       e = (int)(want < S ? want : S);
       if (e < 0) e = 0;
       ext[b] = e;
@@ -97,8 +99,8 @@ __global__ void __launch_bounds__(1024) build_layout_kernel(const int* __restric
   }
   if (tid == 0) off[B] = carry_s;
 }
-__global__ void fill_rowmap_kernel(const int* __restrict__ off, const int* __restrict__ ext, int B, int R_cap,
-                                   unsigned* __restrict__ rowmap) {
+__global__ void fill_rowmap_kernel(const int* off, const int* ext, int B, int R_cap,
+                                   unsigned* rowmap) {
   FS2_PDL_PROLOGUE();
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= R_cap) return;
@@ -117,13 +119,13 @@ __global__ void fill_rowmap_kernel(const int* __restrict__ off, const int* __res
 
 // transformer/Models.py:82-91  out[b,p,:] = src_word_emb[texts[b,p]] + PE[p]   (all grid rows, incl. PAD ids)
 // one warp per flat row; D/4 float4 per row; optional bf16 / bf16x3 shadow for the first GEMM
-__global__ void embed_pe_kernel(const int64_t* __restrict__ texts, const float* __restrict__ emb,
-                                const float* __restrict__ pe, int vocab, const RowLayout lay, int D,
-                                float* __restrict__ out_grid, bf16* __restrict__ out_b, int out_planes,
-                                float* __restrict__ out_user) {
+__global__ void embed_pe_kernel(const int64_t* texts, const float* emb,
+                                const float* pe, int vocab, const RowLayout lay, int D,
+                                float* out_grid, bf16* out_b, int out_planes,
+                                float* out_user) {
   FS2_PDL_PROLOGUE();
   const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  const int R = __ldg(lay.off + lay.B);
+  const int R = ld_act(lay.off + lay.B);
   if (r >= R) return;
   const RowPos rp = row_pos(lay, r, R);
   const int nv = D >> 2;
@@ -146,7 +148,7 @@ __global__ void embed_pe_kernel(const int64_t* __restrict__ texts, const float* 
   }
 }
 
-__global__ void lens_to_i32_kernel(const int64_t* __restrict__ lens, int B, int cap, int* __restrict__ out) {
+__global__ void lens_to_i32_kernel(const int64_t* lens, int B, int cap, int* out) {
   FS2_PDL_PROLOGUE();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < B) {
@@ -156,8 +158,8 @@ __global__ void lens_to_i32_kernel(const int64_t* __restrict__ lens, int B, int 
 }
 
 // utils/tools.py:89-97  mask[b,i] = i >= lens[b]
-__global__ void mask_kernel(const int64_t* __restrict__ lens64, const int* __restrict__ lens32, int B, int max_len,
-                            uint8_t* __restrict__ mask) {
+__global__ void mask_kernel(const int64_t* lens64, const int* lens32, int B, int max_len,
+                            uint8_t* mask) {
   FS2_PDL_PROLOGUE();
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (size_t)B * max_len) return;
@@ -170,8 +172,8 @@ __global__ void mask_kernel(const int64_t* __restrict__ lens64, const int* __res
 __device__ __forceinline__ float round_duration(float log_d, float d_control) {
   return fmaxf(rintf(expf(log_d) - 1.0f) * d_control, 0.0f);
 }
-__global__ void round_durations_kernel(const float* __restrict__ log_d, int64_t n, float d_control,
-                                       float* __restrict__ out) {
+__global__ void round_durations_kernel(const float* log_d, int64_t n, float d_control,
+                                       float* out) {
   FS2_PDL_PROLOGUE();
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) out[i] = round_duration(log_d[i], d_control);
@@ -179,9 +181,9 @@ __global__ void round_durations_kernel(const float* __restrict__ log_d, int64_t 
 
 // model/modules.py:206-222 bookkeeping: expand_size = max(int(d), 0); mel_len = sum.  One CTA per utterance,
 // block-wide inclusive scan (warp shuffles + one smem hop), chunks of 1024 phonemes.
-__global__ void __launch_bounds__(1024) duration_scan_kernel(const float* __restrict__ d, int L, int* __restrict__ cum,
-                                                             int64_t* __restrict__ mel_lens,
-                                                             int* __restrict__ mel_lens32, int* __restrict__ tmax) {
+__global__ void __launch_bounds__(1024) duration_scan_kernel(const float* d, int L, int* cum,
+                                                             int64_t* mel_lens,
+                                                             int* mel_lens32, int* tmax) {
   FS2_PDL_PROLOGUE();
   __shared__ int warp_tot[32];
   __shared__ int carry_s;
@@ -232,14 +234,14 @@ __global__ void __launch_bounds__(1024) duration_scan_kernel(const float* __rest
 // model/modules.py:220-226 + utils/tools.py:288-306: frame t of utterance b copies phoneme row i with
 // cum[i-1] <= t < cum[i]; frames >= mel_len (kept padded rows and halo) are zero.  One warp per output row, the
 // utterance's cumulative table staged in shared memory, binary search per row, 16-byte row copy (+ bf16 shadow).
-__global__ void __launch_bounds__(256) length_regulate_kernel(const float* __restrict__ x, const int* __restrict__ src_off,
-                                                              int src_stride, const int* __restrict__ cum, int L, int D,
-                                                              const RowLayout lay, float* __restrict__ out,
-                                                              bf16* __restrict__ out_b, int out_planes) {
+__global__ void __launch_bounds__(256) length_regulate_kernel(const float* x, const int* src_off,
+                                                              int src_stride, const int* cum, int L, int D,
+                                                              const RowLayout lay, float* out,
+                                                              bf16* out_b, int out_planes) {
   FS2_PDL_PROLOGUE();
   extern __shared__ int cum_s[];
   const int b = blockIdx.y;
-  const int rows_b = __ldg(lay.off + b + 1) - __ldg(lay.off + b);   // ext + halo
+  const int rows_b = ld_act(lay.off + b + 1) - ld_act(lay.off + b);   // ext + halo
   const int rows_per_cta = (blockDim.x >> 5) * 8;
   if ((int)blockIdx.x * rows_per_cta >= rows_b) return;
   for (int i = threadIdx.x; i < L; i += blockDim.x) cum_s[i] = cum[(size_t)b * L + i];
@@ -248,8 +250,8 @@ __global__ void __launch_bounds__(256) length_regulate_kernel(const float* __res
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int nv = D >> 2;
   const size_t plane = (size_t)lay.R_cap * D;
-  const size_t row0 = (size_t)__ldg(lay.off + b);
-  const size_t src0 = src_off ? (size_t)__ldg(src_off + b) : (size_t)b * src_stride;
+  const size_t row0 = (size_t)ld_act(lay.off + b);
+  const size_t src0 = src_off ? (size_t)ld_act(src_off + b) : (size_t)b * src_stride;
   for (int k = 0; k < 8; ++k) {
     const int t = blockIdx.x * rows_per_cta + k * (blockDim.x >> 5) + w;
     if (t >= rows_b) continue;
@@ -275,13 +277,13 @@ __global__ void __launch_bounds__(256) length_regulate_kernel(const float* __res
 // model/modules.py:80-100 (inference branch) fused with the decoder's positional add (Models.py:231-233):
 //   pred <- pred * control ; idx = bucketize(pred, bins) ; x[row] += emb[idx] (+ pe[p])
 // torch.bucketize(right=False) lower bound, incl. its behaviour on NaN boundaries (every compare false -> n_bins-1).
-__global__ void variance_embed_kernel(float* __restrict__ pred, float control, const float* __restrict__ bins,
-                                      int n_bins, const float* __restrict__ emb, const float* __restrict__ pe,
-                                      float* __restrict__ x, bf16* __restrict__ xb, int xb_planes, const RowLayout lay,
-                                      int D, int* __restrict__ idx_out) {
+__global__ void variance_embed_kernel(float* pred, float control, const float* bins,
+                                      int n_bins, const float* emb, const float* pe,
+                                      float* x, bf16* xb, int xb_planes, const RowLayout lay,
+                                      int D, int* idx_out) {
   FS2_PDL_PROLOGUE();
   const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  const int R = __ldg(lay.off + lay.B);
+  const int R = ld_act(lay.off + lay.B);
   if (r >= R) return;
   const RowPos rp = row_pos(lay, r, R);
   if (!rp.in_grid) return;   // halo rows stay zero
@@ -290,7 +292,7 @@ __global__ void variance_embed_kernel(float* __restrict__ pred, float control, c
   int start = 0, end = n_bins - 1;  // boundaries array has n_bins-1 entries
   while (start < end) {
     const int mid = start + ((end - start) >> 1);
-    const float mv = __ldg(bins + mid);
+    const float mv = ld_act(bins + mid);
     if (!(mv >= v)) start = mid + 1; else end = mid;
   }
   if (lane == 0) {
@@ -312,26 +314,51 @@ __global__ void variance_embed_kernel(float* __restrict__ pred, float control, c
   }
 }
 
-// Rows of a uniform destination grid that the packed source layout does not carry: padded rows p in [ext[b], S) get
-// the bias row (what mel_linear makes of a zero decoder row, fastspeech2_align.py:83), halo rows [S, dst_SA) get zero.
-__global__ void __launch_bounds__(256) fill_padded_rows_kernel(const float* __restrict__ bias, int N, const RowLayout lay,
-                                                               int dst_SA, float* __restrict__ out_grid,
-                                                               bf16* __restrict__ out_b, int out_planes,
-                                                               float* __restrict__ out_user) {
+// Rows of the destination (PostNet) layout that the packed source layout does not carry (see fs2_common.cuh): padded
+// grid rows get the bias row (what mel_linear makes of a zero decoder row, fastspeech2_align.py:83), the rows between an
+// utterance's grid rows and the next utterance get zero (the convolutions' zero padding).  One warp per row.
+__global__ void __launch_bounds__(256) fill_padded_rows_kernel(const float* bias, int N, const RowLayout src,
+                                                               const RowLayout dst, float* out_grid,
+                                                               bf16* out_b, int out_planes,
+                                                               float* out_user) {
   FS2_PDL_PROLOGUE();
   const int b = blockIdx.y;
-  const int e = __ldg(lay.ext + b);
-  const int p = e + blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (p >= dst_SA) return;
+  const int e_src = b < src.B ? ld_act(src.ext + b) : 0;          // the pseudo utterance has no source rows
+  const int p = e_src + blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int o0 = ld_act(dst.off + b);
+  const int rows_dst = ld_act(dst.off + b + 1) - o0;               // grid rows + zero rows of utterance b
+  const int e_dst = ld_act(dst.ext + b);
+  const bool in_dst = p < rows_dst, in_user = b < src.B && p < src.S;
+  if (!in_dst && !in_user) return;
   const int lane = threadIdx.x & 31, nv = N >> 2;
-  const size_t g = (size_t)b * dst_SA + p;
-  const size_t plane = (size_t)lay.B * dst_SA * N;
+  const size_t g = (size_t)o0 + p;
+  const size_t plane = (size_t)dst.R_cap * N;
   for (int c = lane; c < nv; c += 32) {
-    const float4 v = p < lay.S ? ld4(bias + c * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-    if (out_grid) st4(out_grid + g * N + c * 4, v);
-    if (out_b && out_planes > 0) store_planes4(out_b + g * N + c * 4, plane, out_planes, v);
-    if (out_user && p < lay.S) st4(out_user + ((size_t)b * lay.S + p) * N + c * 4, v);
+    const float4 bv = ld4(bias + c * 4);
+    if (in_dst) {
+      const float4 v = p < e_dst ? bv : make_float4(0.f, 0.f, 0.f, 0.f);
+      if (out_grid) st4(out_grid + g * N + c * 4, v);
+      if (out_b && out_planes > 0) store_planes4(out_b + g * N + c * 4, plane, out_planes, v);
+    }
+    if (out_user && in_user) st4(out_user + ((size_t)b * src.S + p) * N + c * 4, bv);
   }
+}
+
+// PostNet far rows (fs2_common.cuh): utterance b's rows p >= ext[b] - H (when the layout cut the utterance short of S)
+// equal the rows of an all-bias utterance at the same distance from the end of the grid.  One warp per row.
+__global__ void __launch_bounds__(256) postnet_far_rows_kernel(const float* post_grid, int N, const RowLayout pn,
+                                                               int B, int H, float* out_user) {
+  FS2_PDL_PROLOGUE();
+  const int b = blockIdx.y, S = pn.S;
+  const int e = ld_act(pn.ext + b);
+  if (e >= S) return;                                   // the utterance reaches the end of the grid: every row is exact
+  const int p = max(e - H, 0) + blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (p >= S) return;
+  const int Tp = ld_act(pn.ext + B);                     // rows of the pseudo utterance: min(S, 2H+1)
+  const int j = S > Tp ? ((S - p <= H) ? Tp - (S - p) : H) : p;
+  const float* src = post_grid + ((size_t)ld_act(pn.off + B) + j) * N;
+  float* dst = out_user + ((size_t)b * S + p) * N;
+  for (int c = threadIdx.x & 31; c < (N >> 2); c += 32) st4(dst + c * 4, ld4(src + c * 4));
 }
 
 // model/modules.py:166-192 GaussianUpsampling.  Per utterance: e = cumsum(d), c = e - d/2 (monotone non-decreasing
@@ -340,9 +367,9 @@ __global__ void __launch_bounds__(256) fill_padded_rows_kernel(const float* __re
 // (denormal limit: 0.01*D^2 > 103.97), so each frame only visits the phonemes with |t - c_i| < 104 found by binary
 // search: O(band) instead of O(L) work per frame, identical sums.  One warp per frame; lanes split the band for the
 // weights (warp-shuffle normalisation), then split the D channels for the accumulation.
-__global__ void __launch_bounds__(256) gaussian_upsample_kernel(const float* __restrict__ x, const float* __restrict__ d,
-                                                                int L, int D, int T, int T_w, float* __restrict__ out,
-                                                                float* __restrict__ s_out, float* __restrict__ w_out) {
+__global__ void __launch_bounds__(256) gaussian_upsample_kernel(const float* x, const float* d,
+                                                                int L, int D, int T, int T_w, float* out,
+                                                                float* s_out, float* w_out) {
   FS2_PDL_PROLOGUE();
   extern __shared__ float c_s[];  // [L] centres
   __shared__ int mono_s;
@@ -411,21 +438,21 @@ __global__ void __launch_bounds__(256) gaussian_upsample_kernel(const float* __r
 }
 
 // dense user layout [B,S,C] <-> ragged grid layout (test / per-operator entry points)
-__global__ void to_grid_kernel(const float* __restrict__ xu, const RowLayout lay, int C, float* __restrict__ out,
-                               int ldo, int col_off, bf16* __restrict__ out_b) {
+__global__ void to_grid_kernel(const float* xu, const RowLayout lay, int C, float* out,
+                               int ldo, int col_off, bf16* out_b) {
   FS2_PDL_PROLOGUE();
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;  // one float4 per thread
   const int nv = C >> 2;
   if (i >= (size_t)lay.R_cap * nv) return;
   const size_t row = i / nv;
   const int c = (int)(i - row * nv);
-  const RowPos rp = row_pos(lay, (int)row, __ldg(lay.off + lay.B));
+  const RowPos rp = row_pos(lay, (int)row, ld_act(lay.off + lay.B));
   float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
   if (rp.in_grid) v = ld4(xu + ((size_t)rp.b * lay.S + rp.p) * C + c * 4);
   if (out) st4(out + row * ldo + col_off + c * 4, v);
   if (out_b) *reinterpret_cast<uint2*>(out_b + row * C + c * 4) = make_uint2(pack2(v.x, v.y), pack2(v.z, v.w));
 }
-__global__ void from_grid_kernel(const float* __restrict__ xg, const RowLayout lay, int C, float* __restrict__ out) {
+__global__ void from_grid_kernel(const float* xg, const RowLayout lay, int C, float* out) {
   FS2_PDL_PROLOGUE();
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int nv = C >> 2;
@@ -434,14 +461,14 @@ __global__ void from_grid_kernel(const float* __restrict__ xg, const RowLayout l
   const int c = (int)(i - row * nv);
   const int b = (int)(row / lay.S), p = (int)(row - (size_t)b * lay.S);
   float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (p < __ldg(lay.ext + b)) v = ld4(xg + ((size_t)__ldg(lay.off + b) + p) * C + c * 4);
+  if (p < ld_act(lay.ext + b)) v = ld4(xg + ((size_t)ld_act(lay.off + b) + p) * C + c * 4);
   st4(out + row * C + c * 4, v);
 }
 
 // torch Conv1d / Linear weight [N][K][taps] -> fp32 [taps][K][n_total] (columns n_off..) and/or
 // bf16 [taps][n_total][K] (rows n_off..), optionally scaled per output channel (BatchNorm fold).
-__global__ void pack_weight_kernel(const float* __restrict__ src, int N, int K, int taps, const float* __restrict__ scale,
-                                   float* __restrict__ dst_f, bf16* __restrict__ dst_b, int n_total, int n_off) {
+__global__ void pack_weight_kernel(const float* src, int N, int K, int taps, const float* scale,
+                                   float* dst_f, bf16* dst_b, int n_total, int n_off) {
   FS2_PDL_PROLOGUE();
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (size_t)N * K * taps) return;
@@ -464,10 +491,10 @@ __global__ void pack_weight_kernel(const float* __restrict__ src, int N, int K, 
 
 // BatchNorm1d(eval) folded into the preceding conv (transformer/Layers.py:120-167, eps 1e-5):
 //   scale = g / sqrt(var + eps) ; bias' = (conv_bias - mean) * scale + b
-__global__ void bn_fold_kernel(const float* __restrict__ conv_bias, const float* __restrict__ g,
-                               const float* __restrict__ b, const float* __restrict__ mean,
-                               const float* __restrict__ var, int n, float eps, float* __restrict__ scale_out,
-                               float* __restrict__ bias_out) {
+__global__ void bn_fold_kernel(const float* conv_bias, const float* g,
+                               const float* b, const float* mean,
+                               const float* var, int n, float eps, float* scale_out,
+                               float* bias_out) {
   FS2_PDL_PROLOGUE();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -476,14 +503,14 @@ __global__ void bn_fold_kernel(const float* __restrict__ conv_bias, const float*
   bias_out[i] = (conv_bias[i] - mean[i]) * s + b[i];
 }
 
-__global__ void split_kernel(const float* __restrict__ src, int64_t n4, int planes, bf16* __restrict__ dst, int64_t plane_elems) {
+__global__ void split_kernel(const float* src, int64_t n4, int planes, bf16* dst, int64_t plane_elems) {
   FS2_PDL_PROLOGUE();
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n4) store_planes4(dst + i * 4, (size_t)plane_elems, planes, ld4(src + i * 4));
 }
 
 // max |w| of a tensor as the bit pattern of a non-negative float (monotonic as unsigned)
-__global__ void absmax_kernel(const float* __restrict__ w, size_t n, unsigned* __restrict__ out) {
+__global__ void absmax_kernel(const float* w, size_t n, unsigned* out) {
   FS2_PDL_PROLOGUE();
   float m = 0.f;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
@@ -495,7 +522,7 @@ __global__ void absmax_kernel(const float* __restrict__ w, size_t n, unsigned* _
 }
 
 // wf [taps][K][N] fp32 -> dst [2][taps][N][K] fp16 bit patterns of (w * scale): hi, lo
-__global__ void pack_weight_f16x2_kernel(const float* __restrict__ wf, int N, int K, int taps, float scale, bf16* __restrict__ dst) {
+__global__ void pack_weight_f16x2_kernel(const float* wf, int N, int K, int taps, float scale, bf16* dst) {
   FS2_PDL_PROLOGUE();
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;   // index into dst plane: ((t*N + n)*K + k)
   const size_t plane = (size_t)taps * N * K;
@@ -509,12 +536,12 @@ __global__ void pack_weight_f16x2_kernel(const float* __restrict__ wf, int N, in
   reinterpret_cast<uint16_t*>(dst)[plane + i] = lo;
 }
 
-__global__ void f32_to_bf16_kernel(const float* __restrict__ src, int64_t n, bf16* __restrict__ dst) {
+__global__ void f32_to_bf16_kernel(const float* src, int64_t n, bf16* dst) {
   FS2_PDL_PROLOGUE();
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) dst[i] = __float2bfloat16_rn(src[i]);
 }
-__global__ void bf16_to_f32_kernel(const bf16* __restrict__ src, int64_t n, float* __restrict__ dst) {
+__global__ void bf16_to_f32_kernel(const bf16* src, int64_t n, float* dst) {
   FS2_PDL_PROLOGUE();
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) dst[i] = __bfloat162float(src[i]);
@@ -522,7 +549,7 @@ __global__ void bf16_to_f32_kernel(const bf16* __restrict__ src, int64_t n, floa
 
 // V [R, D] bf16 (flat rows) -> V^T [D, Rv]: row c, column r (columns >= R zero).  Test helper for the tcgen05
 // attention entry point; on the product path the QKV GEMM epilogue writes V^T directly.
-__global__ void transpose_v_kernel(const bf16* __restrict__ v, int R, int Rv, int D, bf16* __restrict__ vt) {
+__global__ void transpose_v_kernel(const bf16* v, int R, int Rv, int D, bf16* vt) {
   FS2_PDL_PROLOGUE();
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (size_t)D * Rv) return;
@@ -531,14 +558,14 @@ __global__ void transpose_v_kernel(const bf16* __restrict__ v, int R, int Rv, in
 }
 
 // Models.py:231-233 alone: x[b,p,:] += pe[p,:] on grid rows; used when no variance embedding is frame-level
-__global__ void add_pe_kernel(float* __restrict__ x, const float* __restrict__ pe, const RowLayout lay, int D) {
+__global__ void add_pe_kernel(float* x, const float* pe, const RowLayout lay, int D) {
   FS2_PDL_PROLOGUE();
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int nv = D >> 2;
   if (i >= (size_t)lay.R_cap * nv) return;
   const size_t row = i / nv;
   const int c = (int)(i - row * nv);
-  const RowPos rp = row_pos(lay, (int)row, __ldg(lay.off + lay.B));
+  const RowPos rp = row_pos(lay, (int)row, ld_act(lay.off + lay.B));
   if (!rp.in_grid) return;
   float4 a = *reinterpret_cast<const float4*>(x + row * D + c * 4);
   const float4 q = ld4(pe + (size_t)rp.p * D + c * 4);
@@ -553,12 +580,13 @@ inline unsigned blocks_for(size_t n, int per) { return (unsigned)((n + per - 1) 
 #define LAUNCHED() (++g_fs2_launches, cudaGetLastError())
 
 cudaError_t rowops_build_layout(const int* lens32, int B, int S, int halo_keep, int halo_rows, int* off, int* ext,
-                                unsigned* rowmap, int R_cap, cudaStream_t st) {
+                                unsigned* rowmap, int R_cap, cudaStream_t st, int extra_ext) {
   if (B <= 0 || R_cap <= 0) return cudaSuccess;
-  if (B > 65535 || S > FS2_MAX_ROWS_PER_UTT) return cudaErrorInvalidValue;
-  (void)FS2_LAUNCH(build_layout_kernel, 1, 1024, 0, st, lens32, B, S, halo_keep, halo_rows, off, ext);
+  const int Bt = B + (extra_ext > 0 ? 1 : 0);
+  if (Bt > 65535 || S > FS2_MAX_ROWS_PER_UTT) return cudaErrorInvalidValue;
+  (void)FS2_LAUNCH(build_layout_kernel, 1, 1024, 0, st, lens32, B, S, halo_keep, halo_rows, off, ext, extra_ext);
   ++g_fs2_launches;
-  (void)FS2_LAUNCH(fill_rowmap_kernel, blocks_for((size_t)R_cap, 256), 256, 0, st, off, ext, B, R_cap, rowmap);
+  (void)FS2_LAUNCH(fill_rowmap_kernel, blocks_for((size_t)R_cap, 256), 256, 0, st, off, ext, Bt, R_cap, rowmap);
   return LAUNCHED();
 }
 cudaError_t rowops_embed_pe(const int64_t* texts, const float* emb, const float* pe, int vocab, const RowLayout& lay,
@@ -606,11 +634,18 @@ cudaError_t rowops_variance_embed(float* pred, float control, const float* bins,
                                                                          xb_planes, lay, D, idx_out);
   return LAUNCHED();
 }
-cudaError_t rowops_fill_padded_rows(const float* bias, int N, const RowLayout& lay, int dst_SA, float* out_grid,
+cudaError_t rowops_fill_padded_rows(const float* bias, int N, const RowLayout& src, const RowLayout& dst, float* out_grid,
                                     bf16* out_b, int out_planes, float* out_user, cudaStream_t st) {
-  if (lay.B <= 0 || dst_SA <= 0) return cudaSuccess;
-  dim3 grid((dst_SA + 7) / 8, lay.B);
-  (void)FS2_LAUNCH(fill_padded_rows_kernel, grid, 256, 0, st, bias, N, lay, dst_SA, out_grid, out_b, out_planes, out_user);
+  if (dst.B <= 0 || dst.S <= 0) return cudaSuccess;
+  dim3 grid((FS2_ROWS_PER_UTT(dst.S, FS2_HALO) + 7) / 8, dst.B);
+  (void)FS2_LAUNCH(fill_padded_rows_kernel, grid, 256, 0, st, bias, N, src, dst, out_grid, out_b, out_planes, out_user);
+  return LAUNCHED();
+}
+cudaError_t rowops_postnet_far_rows(const float* post_grid, int N, const RowLayout& pn, int B, int H, float* out_user,
+                                    cudaStream_t st) {
+  if (B <= 0 || pn.S <= 0) return cudaSuccess;
+  dim3 grid((pn.S + 7) / 8, B);
+  (void)FS2_LAUNCH(postnet_far_rows_kernel, grid, 256, 0, st, post_grid, N, pn, B, H, out_user);
   return LAUNCHED();
 }
 cudaError_t rowops_pack_weight_f16x2(const float* wf, int N, int K, int taps, bf16* dst, float* w_scale_out, cudaStream_t st) {

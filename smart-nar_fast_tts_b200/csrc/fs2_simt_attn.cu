@@ -15,9 +15,9 @@ constexpr int BQ = 32;
 constexpr int BKV = 64;
 
 template <int DK>
-__global__ void __launch_bounds__(128) simt_attention_kernel(const float* __restrict__ qkv, int ldqkv, int q_off,
+__global__ void __launch_bounds__(128) simt_attention_kernel(const float* qkv, int ldqkv, int q_off,
                                                              int k_off, int v_off, const RowLayout lay,
-                                                             float* __restrict__ out, int ldo, float temperature) {
+                                                             float* out, int ldo, float temperature) {
   FS2_PDL_PROLOGUE();
   constexpr int QS = DK + 4;     // padded row stride (floats) of Q/K tiles: conflict-free float4 column walks
   constexpr int PS = BKV + 4;
@@ -32,9 +32,9 @@ __global__ void __launch_bounds__(128) simt_attention_kernel(const float* __rest
   const int tx = tid & 15, ty = tid >> 4;  // ty in [0,8)
   const int b = blockIdx.z, h = blockIdx.y;
   const int p0 = blockIdx.x * BQ;
-  const size_t row0 = (size_t)__ldg(lay.off + b);
-  const int SA = __ldg(lay.off + b + 1) - (int)row0;   // this utterance's rows (grid + halo)
-  const int len = min(__ldg(lay.lens + b), __ldg(lay.ext + b));
+  const size_t row0 = (size_t)ld_act(lay.off + b);
+  const int SA = ld_act(lay.off + b + 1) - (int)row0;   // this utterance's rows (grid + halo)
+  const int len = min(ld_act(lay.lens + b), ld_act(lay.ext + b));
   if (p0 >= SA) return;
 
   if (p0 >= len) {  // whole tile is padding: zeros
@@ -50,7 +50,7 @@ __global__ void __launch_bounds__(128) simt_attention_kernel(const float* __rest
   for (int idx = tid; idx < BQ * (DK / 4); idx += 128) {
     const int q = idx / (DK / 4), c = idx % (DK / 4);
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (p0 + q < len) v = __ldg(reinterpret_cast<const float4*>(qkv + (row0 + p0 + q) * ldqkv + q_off + h * DK + c * 4));
+    if (p0 + q < len) v = ld_act(reinterpret_cast<const float4*>(qkv + (row0 + p0 + q) * ldqkv + q_off + h * DK + c * 4));
     *reinterpret_cast<float4*>(Qs + q * QS + c * 4) = v;
   }
 
@@ -70,8 +70,8 @@ __global__ void __launch_bounds__(128) simt_attention_kernel(const float* __rest
       float4 kv = make_float4(0.f, 0.f, 0.f, 0.f), vv = kv;
       if (k0 + kr < len) {
         const float* base = qkv + (row0 + k0 + kr) * ldqkv + h * DK + c * 4;
-        kv = __ldg(reinterpret_cast<const float4*>(base + k_off));
-        vv = __ldg(reinterpret_cast<const float4*>(base + v_off));
+        kv = ld_act(reinterpret_cast<const float4*>(base + k_off));
+        vv = ld_act(reinterpret_cast<const float4*>(base + v_off));
       }
       *reinterpret_cast<float4*>(Ks + kr * QS + c * 4) = kv;
       *reinterpret_cast<float4*>(Vs + kr * DK + c * 4) = vv;

@@ -38,7 +38,7 @@ __global__ void __launch_bounds__(256) simt_conv_gemm_kernel(const ConvGemmArgs 
 
   const int tid = threadIdx.x;
   const int tx = tid % TX, ty = tid / TX;
-  const int R = __ldg(a.lay.off + a.lay.B);   // rows in use (device data); rows beyond are never read as non-zero
+  const int R = ld_act(a.lay.off + a.lay.B);   // rows in use (device data); rows beyond are never read as non-zero
   const int r0 = blockIdx.x * BM;
   if (r0 >= R) return;
   const int n0 = blockIdx.y * BN;
@@ -63,7 +63,7 @@ __global__ void __launch_bounds__(256) simt_conv_gemm_kernel(const ConvGemmArgs 
       const int row = idx >> 2, kq = idx & 3;
       const int rr = r0 + row + t - pad;
       if (rr >= 0 && rr < R)
-        ra[i] = __ldg(reinterpret_cast<const float4*>(a.A + (size_t)rr * a.K + k0 + kq * 4));
+        ra[i] = ld_act(reinterpret_cast<const float4*>(a.A + (size_t)rr * a.K + k0 + kq * 4));
       else
         ra[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
@@ -154,10 +154,10 @@ __global__ void __launch_bounds__(256) simt_conv_gemm_kernel(const ConvGemmArgs 
     const RowPos rp = row_pos(a.lay, r, R);
     const int b = rp.b, p = rp.p;
     const bool in_grid = rp.in_grid;
-    const bool keep_len = in_grid && (a.lay.lens == nullptr || p < __ldg(a.lay.lens + b));
+    const bool keep_len = in_grid && (a.lay.lens == nullptr || p < ld_act(a.lay.lens + b));
     const bool keep = (a.mask_mode == MASK_LEN) ? keep_len : in_grid;
-    const bool dst_ok = a.dst_SA > 0 ? in_grid : in_buf;
-    const size_t dst_r = a.dst_SA > 0 ? (size_t)b * a.dst_SA + p : (size_t)r;
+    const bool dst_ok = a.dst_off ? in_grid : in_buf;
+    const size_t dst_r = a.dst_off ? (size_t)(ld_act(a.dst_off + b) + p) : (size_t)r;
 
     float v[8];
 #pragma unroll
@@ -166,11 +166,11 @@ __global__ void __launch_bounds__(256) simt_conv_gemm_kernel(const ConvGemmArgs 
     if (a.epi == EPI_RES_LN || a.epi == EPI_RES) {
       if (in_buf) {
         if (nA < a.N) {
-          const float4 q = __ldg(reinterpret_cast<const float4*>(a.residual + (size_t)r * a.N + nA));
+          const float4 q = ld_act(reinterpret_cast<const float4*>(a.residual + (size_t)r * a.N + nA));
           v[0] += q.x; v[1] += q.y; v[2] += q.z; v[3] += q.w;
         }
         if (nB < a.N) {
-          const float4 q = __ldg(reinterpret_cast<const float4*>(a.residual + (size_t)r * a.N + nB));
+          const float4 q = ld_act(reinterpret_cast<const float4*>(a.residual + (size_t)r * a.N + nB));
           v[4] += q.x; v[5] += q.y; v[6] += q.z; v[7] += q.w;
         }
       }
@@ -214,7 +214,7 @@ __global__ void __launch_bounds__(256) simt_conv_gemm_kernel(const ConvGemmArgs 
       if (nA < a.N) *reinterpret_cast<float4*>(a.out + dst_r * a.ldo + nA) = make_float4(v[0], v[1], v[2], v[3]);
       if (nB < a.N) *reinterpret_cast<float4*>(a.out + dst_r * a.ldo + nB) = make_float4(v[4], v[5], v[6], v[7]);
     }
-    if (a.out_user && in_grid) {
+    if (a.out_user && in_grid && (a.out_user_B <= 0 || b < a.out_user_B)) {
       float* o = a.out_user + ((size_t)b * a.lay.S + p) * a.ldu;
       if (nA < a.N) *reinterpret_cast<float4*>(o + nA) = make_float4(v[0], v[1], v[2], v[3]);
       if (nB < a.N) *reinterpret_cast<float4*>(o + nB) = make_float4(v[4], v[5], v[6], v[7]);

@@ -57,9 +57,9 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.z, h = blockIdx.y, p0 = blockIdx.x * BQ;
   FS2_PDL_PROLOGUE();   // the layout tables read next are written by a predecessor; every CTA waits before it may exit
-  const size_t row0 = (size_t)__ldg(lay.off + b);
-  const int SA = __ldg(lay.off + b + 1) - (int)row0;   // this utterance's rows (grid + halo)
-  const int len = min(__ldg(lay.lens + b), __ldg(lay.ext + b));
+  const size_t row0 = (size_t)ld_act(lay.off + b);
+  const int SA = ld_act(lay.off + b + 1) - (int)row0;   // this utterance's rows (grid + halo)
+  const int len = min(ld_act(lay.lens + b), ld_act(lay.ext + b));
   if (p0 >= SA) return;   // uniform over the CTA, before any barrier / TMEM use
   if (base & 1023u) __trap();   // the swizzled tiles assume a 1024-byte aligned dynamic shared memory window
 

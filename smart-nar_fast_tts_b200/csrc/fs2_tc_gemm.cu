@@ -152,7 +152,7 @@ tc_conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   __syncthreads();
   fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
-  const int R = __ldg(a.lay.off + a.lay.B);          // rows in use: device data (ragged layout)
+  const int R = ld_act(a.lay.off + a.lay.B);          // rows in use: device data (ragged layout)
   const int num_tiles = ((R + BM - 1) / BM) * num_n_blocks;
 
   if (warp == 0) {
@@ -222,12 +222,13 @@ tc_conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       ri.in_buf = ri.r < R;
       const RowPos rp = row_pos(a.lay, ri.r, R);
       ri.b = rp.b; ri.p = rp.p; ri.in_grid = rp.in_grid;
-      ri.keep_len = ri.in_grid && (a.lay.lens == nullptr || ri.p < __ldg(a.lay.lens + ri.b));
+      ri.keep_len = ri.in_grid && (a.lay.lens == nullptr || ri.p < ld_act(a.lay.lens + ri.b));
       ri.keep = (a.mask_mode == MASK_LEN) ? ri.keep_len : ri.in_grid;
-      // destination row of out / out_b: same flat row, or a uniform grid of dst_SA rows per utterance (grid rows only)
-      const bool dst_ok = a.dst_SA > 0 ? ri.in_grid : ri.in_buf;
-      const size_t dst_r = a.dst_SA > 0 ? (size_t)ri.b * a.dst_SA + ri.p : (size_t)ri.r;
-      const size_t dst_plane = a.dst_SA > 0 ? (size_t)a.lay.B * a.dst_SA : (size_t)a.lay.R_cap;
+      // destination row of out / out_b: same flat row, or row dst_off[b] + p of another ragged layout (grid rows only)
+      const bool dst_ok = a.dst_off ? ri.in_grid : ri.in_buf;
+      const size_t dst_r = a.dst_off ? (size_t)(ld_act(a.dst_off + ri.b) + ri.p) : (size_t)ri.r;
+      const size_t dst_plane = a.dst_off ? (size_t)a.dst_R_cap : (size_t)a.lay.R_cap;
+      const bool user_ok = ri.in_grid && (a.out_user_B <= 0 || ri.b < a.out_user_B);
 
       mbar_wait(tfull_bar(as), aphase);
       fence_after_sync();
@@ -247,7 +248,7 @@ tc_conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
             float4 rv = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (res) rv = __ldg(reinterpret_cast<const float4*>(res + j));
+            if (res) rv = ld_act(reinterpret_cast<const float4*>(res + j));
             const float rr[4] = {rv.x, rv.y, rv.z, rv.w};
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
@@ -329,7 +330,7 @@ tc_conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
               if (nb + j < a.N) {
-                const float4 rv = __ldg(reinterpret_cast<const float4*>(a.residual + (size_t)ri.r * a.N + nb + j));
+                const float4 rv = ld_act(reinterpret_cast<const float4*>(a.residual + (size_t)ri.r * a.N + nb + j));
                 y[j] += rv.x; y[j + 1] += rv.y; y[j + 2] += rv.z; y[j + 3] += rv.w;
               }
             }
@@ -346,7 +347,7 @@ tc_conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           }
           if (a.out_b && dst_ok)
             store_bf16_chunk(a.out_b + dst_r * a.ldob + nb, dst_plane * a.ldob, a.out_planes, y, nb, a.N);
-          if (a.out_user && ri.in_grid) {
+          if (a.out_user && user_ok) {
             float* o = a.out_user + ((size_t)ri.b * a.lay.S + ri.p) * a.ldu + nb;
 #pragma unroll
             for (int j = 0; j < 32; j += 4)

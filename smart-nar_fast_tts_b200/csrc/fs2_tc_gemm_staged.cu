@@ -25,23 +25,26 @@ namespace {
 using namespace tc;
 
 constexpr int BM = 128, BN = 256, BKE = 64;
-constexpr int NUM_THREADS = 320;                          // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue
-constexpr int A_BYTES = BM * BKE * 2, B_BYTES = BN * BKE * 2, STAGE_BYTES = A_BYTES + B_BYTES;   // 48 KB
-constexpr int MAX_STAGES = 3;
+constexpr int NUM_THREADS = 352;                          // warp 0 TMA (A), warp 1 MMA, warp 2 TMA (B), warps 3-10 epilogue
+constexpr int EPI_T0 = 96;                                // first epilogue thread
+constexpr int A_BYTES = BM * BKE * 2, B_BYTES = BN * BKE * 2;   // 16 KB / 32 KB per k-block
+constexpr int MAX_A = 4, MAX_B = 3;                       // ring depths: A streams from HBM (deep), W from L2 (shallow)
 constexpr int CH_F32 = BM * 32 * 4;                       // 16 KB: [128 rows][32 fp32], 128-byte rows, SWIZZLE_128B
 constexpr int CH_B16 = BM * 32 * 2;                       //  8 KB: [128 rows][32 bf16],  64-byte rows, SWIZZLE_64B
-// shared-memory plan (bytes from the 1024-aligned base):
-//   ring            stages x 48 KB
-//   group g region  "wide" plan (2 stages): F0, F1 (2 x 16 KB) + B (3 x 8 KB) = 56 KB ; "deep" plan (3 stages): B only
+// shared-memory plan (bytes from the 1024-aligned base), chosen per launch (struct Plan):
+//   A ring          nA x 16 KB   (activation k-blocks: HBM latency, deep)
+//   B ring          nB x 32 KB   (weight k-blocks: L2 hits, shallow)
+//   group g region  wide plan: F0, F1 (2 x 16 KB fp32 staging / residual) + B staging (out_planes x 8 KB)
+//                   deep plan: B staging only
 //   params          bias[2][128], ln_g[256], ln_b[256], stats[2 parities][2 groups][128] float2
 //   barriers
-constexpr int GRP_WIDE = 2 * CH_F32 + 3 * CH_B16, GRP_DEEP = 3 * CH_B16;
 constexpr int PARAM_BYTES = (2 * 128 + 256 + 256) * 4 + 2 * 2 * 128 * 8;
-constexpr int NUM_BARS = 2 * MAX_STAGES + 4 + 4;
-__host__ __device__ constexpr int grp_bytes(int stages) { return stages == 2 ? GRP_WIDE : GRP_DEEP; }
-__host__ __device__ constexpr int smem_total(int stages) {
-  return stages * STAGE_BYTES + 2 * grp_bytes(stages) + PARAM_BYTES + NUM_BARS * 8 + 16;
-}
+constexpr int NUM_BARS = 2 * MAX_A + 2 * MAX_B + 4 + 4;
+struct Plan {
+  int nA, nB, wide, grp_bytes;
+  __host__ __device__ int ring_bytes() const { return nA * A_BYTES + nB * B_BYTES; }
+  __host__ __device__ int total() const { return ring_bytes() + 2 * grp_bytes + PARAM_BYTES + NUM_BARS * 8 + 16; }
+};
 constexpr uint32_t TMEM_COLS = 2 * BN;
 
 __constant__ int s_combo_a[6] = {0, 2, 1, 0, 1, 0};       // bf16x3 cross products, smallest first (see fs2_tc_gemm.cu)
@@ -57,11 +60,13 @@ tc_conv_gemm_staged_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
                            const __grid_constant__ CUtensorMap tmRes, const __grid_constant__ CUtensorMap tmOutF,
                            const __grid_constant__ CUtensorMap tmOutB0, const __grid_constant__ CUtensorMap tmOutB1,
                            const __grid_constant__ CUtensorMap tmVt, const ConvGemmArgs a, const int num_n_blocks,
-                           const int stages) {
+                           const Plan plan) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t base = smem_u32(smem);
-  const int ring_bytes = stages * STAGE_BYTES;
-  const int grp_sz = grp_bytes(stages);
+  const int nA = plan.nA, nB = plan.nB;
+  const uint32_t ringB = base + nA * A_BYTES;      // B ring follows the A ring
+  const int ring_bytes = plan.ring_bytes();
+  const int grp_sz = plan.grp_bytes;
   const int param_off = ring_bytes + 2 * grp_sz;
   float* s_bias = reinterpret_cast<float*>(smem + param_off);           // [2 groups][128]
   float* s_g = s_bias + 256;
@@ -69,11 +74,14 @@ tc_conv_gemm_staged_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
   float2* s_stat = reinterpret_cast<float2*>(s_b + 256);                // [2 parities][2 groups][128]
   const int bar_off = param_off + PARAM_BYTES;
   const uint32_t bars = base + bar_off;
-  auto full_bar = [&](int s) { return bars + 8u * s; };
-  auto empty_bar = [&](int s) { return bars + 8u * (MAX_STAGES + s); };
-  auto tfull_bar = [&](int s) { return bars + 8u * (2 * MAX_STAGES + s); };
-  auto tempty_bar = [&](int s) { return bars + 8u * (2 * MAX_STAGES + 2 + s); };
-  auto res_bar = [&](int g, int s) { return bars + 8u * (2 * MAX_STAGES + 4 + 2 * g + s); };
+  auto fullA = [&](int s) { return bars + 8u * s; };
+  auto emptyA = [&](int s) { return bars + 8u * (MAX_A + s); };
+  auto fullB = [&](int s) { return bars + 8u * (2 * MAX_A + s); };
+  auto emptyB = [&](int s) { return bars + 8u * (2 * MAX_A + MAX_B + s); };
+  constexpr int TB0 = 2 * MAX_A + 2 * MAX_B;
+  auto tfull_bar = [&](int s) { return bars + 8u * (TB0 + s); };
+  auto tempty_bar = [&](int s) { return bars + 8u * (TB0 + 2 + s); };
+  auto res_bar = [&](int g, int s) { return bars + 8u * (TB0 + 4 + 2 * g + s); };
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + bar_off + NUM_BARS * 8);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -89,7 +97,8 @@ tc_conv_gemm_staged_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
-    for (int s = 0; s < MAX_STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int s = 0; s < MAX_A; ++s) { mbar_init(fullA(s), 1); mbar_init(emptyA(s), 1); }
+    for (int s = 0; s < MAX_B; ++s) { mbar_init(fullB(s), 1); mbar_init(emptyB(s), 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 8); }
     for (int g = 0; g < 2; ++g) for (int s = 0; s < 2; ++s) mbar_init(res_bar(g, s), 1);
     fence_barrier_init();
@@ -98,8 +107,8 @@ tc_conv_gemm_staged_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
     tmem_alloc(smem_u32(tmem_slot), TMEM_COLS);
     tmem_relinquish();
   }
-  if (warp >= 2) {
-    const int i = threadIdx.x - 64;   // 0..255
+  if (warp >= 3) {
+    const int i = threadIdx.x - EPI_T0;   // 0..255
     s_g[i] = ln ? __ldg(a.ln_g + i) : 1.f;
     s_b[i] = ln ? __ldg(a.ln_b + i) : 0.f;
   }
@@ -108,27 +117,41 @@ tc_conv_gemm_staged_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
   __syncthreads();
   fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
-  const int R = __ldg(a.lay.off + a.lay.B);
+  const int R = ld_act(a.lay.off + a.lay.B);
   const int num_tiles = ((R + BM - 1) / BM) * num_n_blocks;
 
   if (warp == 0) {
-    // ===================================================== TMA producer
+    // ===================================================== TMA producer, activations (A ring)
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m_blk = tile / num_n_blocks, n_blk = tile - m_blk * num_n_blocks;
-        const int r0 = m_blk * BM, n0 = n_blk * BN;
+        const int r0 = (tile / num_n_blocks) * BM;
         for (int c = 0; c < ncombo; ++c) {
           const int pa = ncombo == 1 ? 0 : ncombo == 3 ? s_combo2_a[c] : s_combo_a[c];
+          for (int it = 0; it < iters; ++it) {
+            const int t = it / KB, k0 = (it - t * KB) * BKE;
+            mbar_wait(emptyA(stage), phase ^ 1u);
+            mbar_expect_tx(fullA(stage), A_BYTES);
+            tma_load_3d(base + stage * A_BYTES, &tmA, fullA(stage), k0, r0 + t - pad, pa);
+            if (++stage == nA) { stage = 0; phase ^= 1u; }
+          }
+        }
+      }
+    }
+  } else if (warp == 2) {
+    // ===================================================== TMA producer, weights (B ring)
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int n0 = (tile % num_n_blocks) * BN;
+        for (int c = 0; c < ncombo; ++c) {
           const int pb = ncombo == 1 ? 0 : ncombo == 3 ? s_combo2_b[c] : s_combo_b[c];
           for (int it = 0; it < iters; ++it) {
             const int t = it / KB, k0 = (it - t * KB) * BKE;
-            mbar_wait(empty_bar(stage), phase ^ 1u);
-            mbar_expect_tx(full_bar(stage), STAGE_BYTES);
-            const uint32_t sa = base + stage * STAGE_BYTES;
-            tma_load_3d(sa, &tmA, full_bar(stage), k0, r0 + t - pad, pa);
-            tma_load_2d(sa + A_BYTES, &tmB, full_bar(stage), k0, (pb * a.taps + t) * a.N + n0);
-            if (++stage == stages) { stage = 0; phase ^= 1u; }
+            mbar_wait(emptyB(stage), phase ^ 1u);
+            mbar_expect_tx(fullB(stage), B_BYTES);
+            tma_load_2d(ringB + stage * B_BYTES, &tmB, fullB(stage), k0, (pb * a.taps + t) * a.N + n0);
+            if (++stage == nB) { stage = 0; phase ^= 1u; }
           }
         }
       }
@@ -137,7 +160,7 @@ tc_conv_gemm_staged_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
     // ===================================================== MMA issuer
     if (lane == 0) {
       const uint32_t idesc = make_idesc_f16kind(BM, BN, a.planes == 2 ? 0u : 1u);
-      int stage = 0; uint32_t phase = 0;
+      int sa_i = 0, sb_i = 0; uint32_t pha = 0, phb = 0;
       int as = 0; uint32_t aphase = 0;
       const int steps = iters * ncombo;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -145,16 +168,18 @@ tc_conv_gemm_staged_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
         fence_after_sync();
         const uint32_t d_tmem = tmem_base + (uint32_t)(as * BN);
         for (int it = 0; it < steps; ++it) {
-          mbar_wait(full_bar(stage), phase);
+          mbar_wait(fullB(sb_i), phb);
+          mbar_wait(fullA(sa_i), pha);
           fence_after_sync();
-          const uint32_t sa = base + stage * STAGE_BYTES;
-          const uint64_t adesc = make_smem_desc_sw128(sa);
-          const uint64_t bdesc = make_smem_desc_sw128(sa + A_BYTES);
+          const uint64_t adesc = make_smem_desc_sw128(base + sa_i * A_BYTES);
+          const uint64_t bdesc = make_smem_desc_sw128(ringB + sb_i * B_BYTES);
 #pragma unroll
           for (int k = 0; k < BKE / 16; ++k)
             umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (it | k) ? 1u : 0u);
-          umma_commit(empty_bar(stage));
-          if (++stage == stages) { stage = 0; phase ^= 1u; }
+          umma_commit(emptyA(sa_i));
+          umma_commit(emptyB(sb_i));
+          if (++sa_i == nA) { sa_i = 0; pha ^= 1u; }
+          if (++sb_i == nB) { sb_i = 0; phb ^= 1u; }
         }
         umma_commit(tfull_bar(as));
         if (++as == 2) { as = 0; aphase ^= 1u; }
@@ -162,15 +187,15 @@ tc_conv_gemm_staged_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
     }
   } else {
     // ===================================================== epilogue: 2 groups x 4 warps, thread = (output row, column half)
-    const int g = (warp - 2) >> 2;                  // group = column half
+    const int g = (warp - 3) >> 2;                  // group = column half
     const int q = warp & 3;                         // TMEM lane quarter this warp may access
     const int row = q * 32 + lane;                  // row in tile
-    const bool elected = threadIdx.x == 64 + g * 128;
+    const bool elected = threadIdx.x == EPI_T0 + g * 128;
     const int bar_grp_id = 1 + g, bar_pair_id = 3 + q;
     auto bar_grp = [&]() { asm volatile("bar.sync %0, 128;" ::"r"(bar_grp_id) : "memory"); };
     const int sw128 = row & 7, sw64 = (row >> 1) & 3;
     const int grp_off = ring_bytes + g * grp_sz;
-    const bool wide = stages == 2;                  // F buffers exist
+    const bool wide = plan.wide != 0;               // F buffers exist
     uint8_t* Fbuf = smem + grp_off;                 // F0 | F1 (wide plan only)
     uint8_t* Bbuf = smem + grp_off + (wide ? 2 * CH_F32 : 0);
     const bool has_res = a.epi == EPI_RES_LN;
@@ -248,7 +273,7 @@ tc_conv_gemm_staged_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
     unsigned next_code = FS2_ROW_NONE;
     {
       const int r_first = ((int)blockIdx.x / num_n_blocks) * BM + row;
-      if ((int)blockIdx.x < num_tiles && r_first < R) next_code = __ldg(a.lay.rowmap + r_first);
+      if ((int)blockIdx.x < num_tiles && r_first < R) next_code = ld_act(a.lay.rowmap + r_first);
     }
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m_blk = tile / num_n_blocks, n_blk = tile - m_blk * num_n_blocks;
@@ -267,7 +292,7 @@ tc_conv_gemm_staged_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
       // bias slice of this group's half of the tile
       bar_grp();
       {
-        const int i = threadIdx.x - 64 - g * 128;
+        const int i = threadIdx.x - EPI_T0 - g * 128;
         my_bias[i] = (n0 + gc0 + i < a.N) ? __ldg(a.bias + n0 + gc0 + i) : 0.f;
       }
       bar_grp();
@@ -277,11 +302,11 @@ tc_conv_gemm_staged_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
       {
         const int nt = tile + gridDim.x;
         const int rn = (nt / num_n_blocks) * BM + row;
-        next_code = (nt < num_tiles && rn < R) ? __ldg(a.lay.rowmap + rn) : FS2_ROW_NONE;
+        next_code = (nt < num_tiles && rn < R) ? ld_act(a.lay.rowmap + rn) : FS2_ROW_NONE;
       }
       const bool in_grid = code != FS2_ROW_NONE;
       const int rb = in_grid ? (int)(code >> 16) : 0, rpp = in_grid ? (int)(code & 0xFFFFu) : 0;
-      const bool keep_len = in_grid && (a.lay.lens == nullptr || rpp < __ldg(a.lay.lens + rb));
+      const bool keep_len = in_grid && (a.lay.lens == nullptr || rpp < ld_act(a.lay.lens + rb));
       const bool keep = (a.mask_mode == MASK_LEN) ? keep_len : in_grid;
 
       mbar_wait(tfull_bar(as), aphase);
@@ -414,17 +439,22 @@ tc_conv_gemm_staged_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
   }
 }
 
-// 2 stages ("wide": fp32 staging buffers) whenever the epilogue moves fp32 tiles or V^T; these are the small-K GEMMs
-// whose mainloop hides behind the epilogue anyway.  3 stages ("deep") for the mainloop-bound bf16-only producers
-// (FFN conv k=9, PostNet k=5, predictor conv1).
-int stages_for(const ConvGemmArgs& a) {
-  return (a.epi == EPI_RES_LN || a.epi == EPI_QKV || a.out != nullptr) ? 2 : 3;
+// Wide plan (fp32 staging buffers) whenever the epilogue moves fp32 tiles or V^T; deep plan for the bf16-only
+// producers (FFN conv k=9, PostNet k=5, predictor conv1).  Ring depths fill what the staging leaves of the 227 KB.
+Plan plan_for(const ConvGemmArgs& a, int out_planes) {
+  Plan p;
+  p.wide = (a.epi == EPI_RES_LN || a.epi == EPI_QKV || a.out != nullptr) ? 1 : 0;
+  p.grp_bytes = (p.wide ? 2 * CH_F32 : 0) + out_planes * CH_B16;
+  p.nB = p.wide ? 2 : 3;
+  p.nA = MAX_A;
+  while (p.nA > 2 && p.total() > 227 * 1024) --p.nA;
+  return p;
 }
 
 }  // namespace
 
 bool tc_conv_gemm_staged_supported(const ConvGemmArgs& a) {
-  if (a.N % 256 != 0 || a.dst_SA > 0 || a.out_user != nullptr) return false;
+  if (a.N % 256 != 0 || a.dst_off != nullptr || a.out_user != nullptr) return false;
   if (a.epi == EPI_RES_LN || a.epi == EPI_RELU_LN) return a.N == 256 && (a.out == nullptr || a.ldo == 256) && (a.out_b == nullptr || a.ldob == 256);
   if (a.epi == EPI_QKV) return a.N == 768;
   if (a.epi == EPI_BIAS || a.epi == EPI_RELU || a.epi == EPI_TANH)
@@ -468,8 +498,7 @@ int tc_conv_gemm_staged_launch(const ConvGemmArgs& a, cudaStream_t st) {
   if (!ok) return fs2_fail_cuda(cudaErrorInvalidValue, "cuTensorMapEncodeTiled(staged epilogue)");
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(tc_conv_gemm_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         smem_total(2) > smem_total(3) ? smem_total(2) : smem_total(3));
+    cudaError_t e = cudaFuncSetAttribute(tc_conv_gemm_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return fs2_fail_cuda(e, "cudaFuncSetAttribute(tc_conv_gemm_staged)");
     configured = true;
   }
@@ -485,9 +514,10 @@ int tc_conv_gemm_staged_launch(const ConvGemmArgs& a, cudaStream_t st) {
   const int grid = tiles < num_sms ? tiles : num_sms;
   ConvGemmArgs b = a;
   if (a.epi == EPI_QKV) b.out_planes = 1;
-  const int stages = stages_for(a);
-  (void)FS2_LAUNCH(tc_conv_gemm_staged_kernel, grid, NUM_THREADS, smem_total(stages), st, tmA, tmB, tmRes, tmOutF, tmOutB0,
-                   tmOutB1, tmVt, b, num_n_blocks, stages);
+  const Plan plan = plan_for(a, a.epi == EPI_QKV ? 1 : out_planes);
+  if (plan.total() > 227 * 1024) return fs2_fail_cuda(cudaErrorInvalidValue, "tc_conv_gemm_staged: shared-memory plan");
+  (void)FS2_LAUNCH(tc_conv_gemm_staged_kernel, grid, NUM_THREADS, plan.total(), st, tmA, tmB, tmRes, tmOutF, tmOutB0,
+                   tmOutB1, tmVt, b, num_n_blocks, plan);
   ++g_fs2_launches;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fs2_fail_cuda(e, "tc_conv_gemm_staged_kernel launch");

@@ -57,3 +57,19 @@ def test_no_cpu_fallback(lib):
     sp, tx, sl, L = O.make_inputs(2, 4, 6)
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         m(sp, tx, sl, L)
+
+
+def test_no_global_access_before_pdl_wait():
+    """Every kernel is launched with programmatic dependent launch; ptxas may hoist non-coherent loads above
+    griddepcontrol.wait.  scripts/check_pdl_sass.py scans the SASS of the built objects for any global access scheduled
+    before the wait (the bug class behind the stale layout-table reads of profiles/r1g)."""
+    import shutil
+    import subprocess
+    import sys
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("cuobjdump not available")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    if not os.path.isdir(os.path.join(root, "smart-nar_fast_tts_b200", "build")):
+        pytest.skip("objects not built in this checkout")
+    r = subprocess.run([sys.executable, os.path.join(root, "scripts", "check_pdl_sass.py")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout[-2000:]
