@@ -4,15 +4,19 @@
 //   out[b, q, h*128:(h+1)*128] = softmax_k( Q_h[b,q,:] . K_h[b,k,:] / sqrt(128), keys >= len_b masked ) @ V_h[b]
 // One CTA = one (128-query tile, head, utterance); 112 KB of shared memory and 256 TMEM columns so that TWO CTAs share an
 // SM (one's softmax overlaps the other's MMAs and loads).  The [S,S] score matrix never leaves the SM:
-//   warp 0   : TMA.  Q tile once, then a 2-stage ring of (K block [64 keys x 128], V^T block [128 d x 64 keys]).
-//   warp 1   : tcgen05.mma.  S = Q K^T (M=128,N=64,K=128) into TMEM columns [0,64); O += P V (M=128,N=128,K=64 keys)
-//              into TMEM columns [64,192).  S(j+1) is issued before P(j)V(j) so the softmax of block j+1 overlaps the
-//              PV MMA of block j.
+//   warp 0   : TMA.  Q tile once, then two independent 2-stage rings: K blocks [64 keys x 128] and V^T blocks
+//              [128 d x 64 keys].  A K stage is free as soon as its score MMA has completed, long before the V stage of
+//              the same block, which is what lets the score MMAs run two blocks ahead.
+//   warp 1   : tcgen05.mma.  S = Q K^T (M=128,N=64,K=128) into one of TWO score buffers, TMEM columns [0,64) / [64,128);
+//              O += P V (M=128,N=128,K=64 keys) into TMEM columns [128,256).  S(j+2) is issued right after P(j)V(j), i.e.
+//              while the softmax of block j+1 runs, so a finished softmax always finds its next scores waiting
+//              (profiles/r1g: with a single score buffer the softmax warps spent 22 % of their time waiting for S).
 //   warps 2-5: online softmax, one thread per query row (= TMEM lane): one tcgen05.ld pass brings the row's 64 scores
-//              into registers; scale + key mask, running max / sum in the exp2 domain, P written as bf16 into a
-//              128B-swizzled K-major shared tile (A operand of the PV MMA); O is rescaled in TMEM by exp2(m_old - m_new)
-//              only when a row of the warp actually raised its maximum.  The normalised output tile leaves through a
-//              swizzled staging tile + TMA store when the whole tile lies inside the utterance.
+//              into registers; running max on the raw scores, p = exp2(s * scale - m * scale) as one FFMA + one EX2 per
+//              key (the key mask only touches the utterance's last block), P written as bf16 into a 128B-swizzled
+//              K-major shared tile (A operand of the PV MMA); O is rescaled in TMEM by exp2(m_old - m_new) only when a
+//              row of the warp actually raised its maximum.  The normalised output tile leaves through a swizzled
+//              staging tile + TMA store when the whole tile lies inside the utterance.
 // V is consumed K-major as V^T ([d, flat row]); the QKV GEMM epilogue (fs2_tc_gemm.cu, EPI_QKV) writes it in that layout.
 // Rows follow the ragged layout of fs2_common.cuh: utterance b owns flat rows [off[b], off[b+1]).
 // Query rows >= len_b are written as zeros (masked by the caller anyway, Layers.py:43).
@@ -32,10 +36,10 @@ constexpr int V_OFF = K_OFF + 2 * 2 * K_ATOM;    // 2 stages x [128 d rows x 64 
 constexpr int V_TILE = DK * 128;
 constexpr int P_OFF = V_OFF + 2 * V_TILE;        // [128 query rows x 64 keys]
 constexpr int BAR_OFF = P_OFF + BQ * 128;        // 112 KB
-constexpr int NUM_BARS = 8;
+constexpr int NUM_BARS = 12;
 constexpr int SMEM_TOTAL = BAR_OFF + NUM_BARS * 8 + 16;   // 114,768 B: two CTAs per SM
 constexpr int ATT_THREADS = 192;
-constexpr uint32_t TMEM_COLS = 256;              // S: columns [0,64); O: columns [64,192); 2 CTAs/SM -> 512
+constexpr uint32_t TMEM_COLS = 256;              // S0: columns [0,64); S1: [64,128); O: [128,256); 2 CTAs/SM -> 512
 
 __device__ __forceinline__ float fast_exp2(float x) {
   float y;
@@ -50,8 +54,8 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t base = smem_u32(smem);
   const uint32_t bars = base + BAR_OFF;
-  const uint32_t q_full = bars, kv_full0 = bars + 8, kv_empty0 = bars + 24, s_full = bars + 40, p_ready = bars + 48,
-                 o_ready = bars + 56;
+  const uint32_t q_full = bars, k_full0 = bars + 8, k_empty0 = bars + 24, v_full0 = bars + 40, v_empty0 = bars + 56,
+                 s_full0 = bars + 72, p_ready = bars + 88, o_ready = bars + 96;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + BAR_OFF + NUM_BARS * 8);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -77,8 +81,11 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     tma_prefetch_desc(&tmK);
     tma_prefetch_desc(&tmV);
     mbar_init(q_full, 1);
-    for (int s = 0; s < 2; ++s) { mbar_init(kv_full0 + 8 * s, 1); mbar_init(kv_empty0 + 8 * s, 1); }
-    mbar_init(s_full, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(k_full0 + 8 * s, 1); mbar_init(k_empty0 + 8 * s, 1);
+      mbar_init(v_full0 + 8 * s, 1); mbar_init(v_empty0 + 8 * s, 1);
+      mbar_init(s_full0 + 8 * s, 1);
+    }
     mbar_init(p_ready, 128);
     mbar_init(o_ready, 1);
     fence_barrier_init();
@@ -91,7 +98,7 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   __syncthreads();
   fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_S = tmem_base, tmem_O = tmem_base + 64;
+  const uint32_t tmem_S = tmem_base, tmem_O = tmem_base + 128;   // score buffer i at tmem_S + 64 i
 
   if (warp == 0) {
     // ===================================================== TMA producer
@@ -101,45 +108,51 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       tma_load_2d(base + Q_OFF + Q_ATOM, &tmQ, q_full, h * DK + 64, (int)row0 + p0);
       for (int j = 0; j < nb; ++j) {
         const int s = j & 1;
-        mbar_wait(kv_empty0 + 8 * s, ((j >> 1) & 1) ^ 1u);
-        mbar_expect_tx(kv_full0 + 8 * s, 2 * K_ATOM + V_TILE);
+        const uint32_t par = ((j >> 1) & 1) ^ 1u;
         const uint32_t ks = base + K_OFF + s * 2 * K_ATOM, vs = base + V_OFF + s * V_TILE;
-        tma_load_2d(ks, &tmK, kv_full0 + 8 * s, h * DK, (int)row0 + j * BKV);
-        tma_load_2d(ks + K_ATOM, &tmK, kv_full0 + 8 * s, h * DK + 64, (int)row0 + j * BKV);
-        tma_load_2d(vs, &tmV, kv_full0 + 8 * s, (int)row0 + j * BKV, h * DK);
+        mbar_wait(k_empty0 + 8 * s, par);
+        mbar_expect_tx(k_full0 + 8 * s, 2 * K_ATOM);
+        tma_load_2d(ks, &tmK, k_full0 + 8 * s, h * DK, (int)row0 + j * BKV);
+        tma_load_2d(ks + K_ATOM, &tmK, k_full0 + 8 * s, h * DK + 64, (int)row0 + j * BKV);
+        mbar_wait(v_empty0 + 8 * s, par);
+        mbar_expect_tx(v_full0 + 8 * s, V_TILE);
+        tma_load_2d(vs, &tmV, v_full0 + 8 * s, (int)row0 + j * BKV, h * DK);
       }
     }
   } else if (warp == 1) {
     // ===================================================== MMA issuer
     if (lane == 0) {
       constexpr uint32_t idesc_s = make_idesc_bf16(BQ, BKV), idesc_o = make_idesc_bf16(BQ, DK);
-      auto issue_S = [&](int j) {
+      auto issue_S = [&](int j) {    // scores of block j into score buffer j & 1 (K stage j & 1)
         const int s = j & 1;
-        mbar_wait(kv_full0 + 8 * s, (j >> 1) & 1);
+        mbar_wait(k_full0 + 8 * s, (j >> 1) & 1);
         fence_after_sync();
 #pragma unroll
         for (int kk = 0; kk < DK / 16; ++kk) {
           const uint64_t ad = make_smem_desc_sw128(base + Q_OFF + (kk >> 2) * Q_ATOM) + (uint64_t)(2 * (kk & 3));
           const uint64_t bd = make_smem_desc_sw128(base + K_OFF + s * 2 * K_ATOM + (kk >> 2) * K_ATOM) + (uint64_t)(2 * (kk & 3));
-          umma_bf16(tmem_S, ad, bd, idesc_s, kk ? 1u : 0u);
+          umma_bf16(tmem_S + (uint32_t)(s * 64), ad, bd, idesc_s, kk ? 1u : 0u);
         }
-        umma_commit(s_full);
+        umma_commit(k_empty0 + 8 * s);   // the K stage is reusable as soon as these MMAs have read it
+        umma_commit(s_full0 + 8 * s);
       };
       mbar_wait(q_full, 0);
       issue_S(0);
+      if (nb > 1) issue_S(1);
       for (int j = 0; j < nb; ++j) {
         const int s = j & 1;
-        mbar_wait(p_ready, j & 1);     // P(j) in smem, O rescaled, S(j) fully consumed
+        mbar_wait(p_ready, j & 1);     // P(j) in smem, O rescaled, score buffer j & 1 fully consumed
+        mbar_wait(v_full0 + 8 * s, (j >> 1) & 1);
         fence_after_sync();
-        if (j + 1 < nb) issue_S(j + 1);
 #pragma unroll
         for (int kk = 0; kk < BKV / 16; ++kk) {
           const uint64_t ad = make_smem_desc_sw128(base + P_OFF) + (uint64_t)(2 * kk);
           const uint64_t bd = make_smem_desc_sw128(base + V_OFF + s * V_TILE) + (uint64_t)(2 * kk);
           umma_bf16(tmem_O, ad, bd, idesc_o, (j | kk) ? 1u : 0u);
         }
-        umma_commit(kv_empty0 + 8 * s);
+        umma_commit(v_empty0 + 8 * s);
         umma_commit(o_ready);
+        if (j + 2 < nb) issue_S(j + 2);   // runs under the softmax of block j + 1
       }
     }
   } else {
@@ -151,25 +164,29 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     const int sw = row & 7;
     float m = -INFINITY, l = 0.f;
     uint32_t v0[32], v1[32];
+    // m: running maximum of the RAW scores of this row; the softmax runs in the exp2 domain, p = exp2((s - m) * scale)
     for (int j = 0; j < nb; ++j) {
-      mbar_wait(s_full, j & 1);
+      const uint32_t sbuf = tmem_S + lane_off + (uint32_t)((j & 1) * 64);
+      mbar_wait(s_full0 + 8 * (j & 1), (j >> 1) & 1);
       fence_after_sync();
       // the whole 64-key block of this row in registers: one TMEM pass
-      tmem_ld32(tmem_S + lane_off, v0);
-      tmem_ld32(tmem_S + lane_off + 32, v1);
+      tmem_ld32(sbuf, v0);
+      tmem_ld32(sbuf + 32, v1);
       tmem_wait_ld();
       const int kbase = j * BKV;
+      if (kbase + BKV > len) {                   // only the utterance's last block holds masked keys (CTA-uniform branch)
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          if (kbase + i >= len) v0[i] = 0xff800000u;        // -inf
+          if (kbase + 32 + i >= len) v1[i] = 0xff800000u;
+        }
+      }
       float bm = -INFINITY;
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        const float t0 = (kbase + i < len) ? __uint_as_float(v0[i]) * scale_log2 : -INFINITY;
-        const float t1 = (kbase + 32 + i < len) ? __uint_as_float(v1[i]) * scale_log2 : -INFINITY;
-        v0[i] = __float_as_uint(t0);
-        v1[i] = __float_as_uint(t1);
-        bm = fmaxf(bm, fmaxf(t0, t1));
-      }
+      for (int i = 0; i < 32; ++i) bm = fmaxf(bm, fmaxf(__uint_as_float(v0[i]), __uint_as_float(v1[i])));
       const float m_new = fmaxf(m, bm);          // finite: every processed block holds >= 1 valid key
-      const float alpha = fast_exp2(m - m_new);  // 0 on the first block (m = -inf); exactly 1 when the max is unchanged
+      const float alpha = fast_exp2((m - m_new) * scale_log2);  // 0 on the first block (m = -inf); exactly 1 when the max is unchanged
+      const float neg_ms = -m_new * scale_log2;
       if (j > 0) {                               // P buffer and O are free once P(j-1)V(j-1) has completed
         mbar_wait(o_ready, (j - 1) & 1);
         fence_after_sync();
@@ -182,7 +199,7 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         for (int i = 0; i < 8; ++i) {
           const int k = u * 8 + i;
           const float t = __uint_as_float(k < 32 ? v0[k] : v1[k - 32]);
-          pv[i] = fast_exp2(t - m_new);
+          pv[i] = fast_exp2(fmaf(t, scale_log2, neg_ms));   // exp2(-inf) = 0 for masked keys
           bsum += pv[i];
         }
         *reinterpret_cast<uint4*>(p_row + ((u ^ sw) << 4)) =
