@@ -64,7 +64,7 @@ class ClockSampler:
     def __enter__(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms",
-                                          "100", "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "20", "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except OSError:
             self.proc = None
         return self
@@ -320,7 +320,7 @@ def run_b200_arm(args):
                     "d2h_bytes_per_step": int(h_mel.numel() * h_mel.element_size() + h_lens.numel() * h_lens.element_size())},
             "gpu_launches": int(launches),
             "tflops_algorithmic": flops / (ms_res * 1e-3) / 1e12,
-            "roofline": {"kernel": "tc_conv_gemm_kernel<256> as dec.ffn_w1 (Conv1d 256->1024 k=9 + ReLU, tcgen05 bf16)",
+            "roofline": {"kernel": "tc_conv_gemm_staged_kernel as dec.ffn_w1 (Conv1d 256->1024 k=9 + ReLU, tcgen05 bf16)",
                          "bound": "tensor", "achieved": achieved, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
                          "frac": achieved / peaks["bf16_tflops"], "peak_source": peaks["source"] + ", burst",
                          "peak_sustained": peaks["bf16_tflops_sustained"], "traffic": traffic,

@@ -29,6 +29,7 @@ KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active"]
 
 out = [f"# ncu summaries, tag {tag}\n"]
+traffic = {}
 for path in sorted(glob.glob(os.path.join(GO, f"launches_*_{tag}.csv"))):
     rows = [r for r in csv.reader(open(path)) if len(r) > 10]
     if not rows:
@@ -70,11 +71,21 @@ for path in sorted(glob.glob(os.path.join(GO, f"prof_*_{tag}.ncu-rep"))):
                 return float(v.replace(",", "")) * m.get(u, 1)
             tr = tobytes(*d["dram__bytes_read.sum"]) + tobytes(*d["dram__bytes_write.sum"])
             out.append(f"| dram traffic (read+write) | {tr / 1e6:.1f} | MB per launch |")
+            m2 = re.match(r"prof_ffn_w1_(c\d)_", os.path.basename(path))
+            if m2:   # bench.py's roofline.traffic reads this (dominant kernel: decoder FFN conv k=9 GEMM)
+                traffic[m2.group(1)] = {"dec.ffn_w1_bytes_per_launch": int(tr), "source": os.path.basename(path),
+                                        "kernel": d["Kernel Name"][0][:60], "gpu_time_us": d["gpu__time_duration.sum"][0]}
 for path in sorted(glob.glob(os.path.join(GO, f"bench_*_{tag}.json"))):
     try:
         d = json.loads(open(path).read().strip().splitlines()[-1])
     except Exception:
         continue
     out.append(f"\n## bench line {os.path.basename(path)}\n\n```json\n{json.dumps(d, indent=1)}\n```")
+if traffic:
+    tp = os.path.join(PR, "roofline_traffic.json")
+    old = json.load(open(tp)) if os.path.exists(tp) else {}
+    old.update(traffic)
+    json.dump(old, open(tp, "w"), indent=1)
+    print("wrote", tp, traffic)
 open(os.path.join(PR, f"{tag}_summary.md"), "w").write("\n".join(out) + "\n")
 print("wrote", os.path.join(PR, f"{tag}_summary.md"))
