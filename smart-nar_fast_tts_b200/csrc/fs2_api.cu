@@ -394,9 +394,8 @@ int run_fft_stack(fs2_handle* h, std::vector<FftW>& Ls, int l0, int l1, int prec
     }
     return FS2_OK;
   }
-  if (is_split(prec)) {
-    // fp32-faithful tensor-core path: split-operand GEMMs (xb, yb, attb, hidb hold 3 bf16 or 2 fp16 planes), fp32 FFMA
-    // attention
+  if (prec == FS2_PREC_BF16X3) {
+    // fp32-faithful tensor-core path with 3-term bf16 operands: split-operand GEMMs, fp32 FFMA attention
     const size_t np = (size_t)planes_of(prec);
     WS(float, qkv, "fft.qkv", R * 3 * D);
     WS(float, att, "fft.att", R * D);
@@ -427,14 +426,15 @@ int run_fft_stack(fs2_handle* h, std::vector<FftW>& Ls, int l0, int l1, int prec
     }
     return FS2_OK;
   }
-  // tcgen05 bf16 path
+  // tcgen05 path, attention included: bf16 (1 operand plane) or f16x2 (2 scaled fp16 planes, fp32-faithful)
   const int Rv = (lay.R_cap + 7) & ~7;
-  WS(bf16, yb, "fft.yb", R * D);
-  WS(bf16, qb, "fft.qb", R * D);
-  WS(bf16, kb, "fft.kb", R * D);
-  WS(bf16, vtb, "fft.vtb", (size_t)D * Rv);
-  WS(bf16, attb, "fft.attb", R * D);
-  WS(bf16, hidb, "fft.hidb", R * F);
+  const size_t np = (size_t)planes_of(prec);
+  WS(bf16, yb, "fft.yb", np * R * D);
+  WS(bf16, qb, "fft.qb", np * R * D);
+  WS(bf16, kb, "fft.kb", np * R * D);
+  WS(bf16, vtb, "fft.vtb", np * (size_t)D * Rv);
+  WS(bf16, attb, "fft.attb", np * R * D);
+  WS(bf16, hidb, "fft.hidb", np * R * F);
   for (int l = l0; l < l1; ++l) {
     FftW& L = Ls[l];
     ConvGemmArgs a = base_args(L.qkv, lay);
@@ -442,7 +442,7 @@ int run_fft_stack(fs2_handle* h, std::vector<FftW>& Ls, int l0, int l1, int prec
     RCHECK(run_gemm(h, prec, a, st, tg + "qkv"));
     {
       PROF(tg + "attn");
-      int rc = tc_attention_launch(qb, kb, vtb, lay, Rv, H, attb, st);
+      int rc = tc_attention_launch(qb, kb, vtb, lay, Rv, H, (int)np, attb, st);
       if (rc != FS2_OK) { h->err = g_last_error; return rc; }
     }
     a = base_args(L.fc, lay);
@@ -1101,19 +1101,35 @@ int fs2_op_attention(int32_t prec, const float* q, const float* k, const float* 
       if ((e = simt_attention_launch(qkv, 3 * D, 0, D, 2 * D, tl.lay, H, dk, og, D, st)) != cudaSuccess) break;
     } else {
       if (D != 256 || dk != 128) { g_last_error = "tcgen05 attention is built for H*dk = 256, dk = 128"; rc = FS2_ERR_UNSUPPORTED; break; }
-      if ((e = cudaMalloc(reinterpret_cast<void**>(&qb), sizeof(bf16) * R * D)) != cudaSuccess) break;
-      if ((e = cudaMalloc(reinterpret_cast<void**>(&kb), sizeof(bf16) * R * D)) != cudaSuccess) break;
-      if ((e = cudaMalloc(reinterpret_cast<void**>(&vb), sizeof(bf16) * R * D)) != cudaSuccess) break;
-      if ((e = cudaMalloc(reinterpret_cast<void**>(&vtb), sizeof(bf16) * (size_t)D * Rv)) != cudaSuccess) break;
-      if ((e = cudaMalloc(reinterpret_cast<void**>(&ob), sizeof(bf16) * R * D)) != cudaSuccess) break;
-      if ((e = cudaMemsetAsync(ob, 0, sizeof(bf16) * R * D, st)) != cudaSuccess) break;
-      if ((e = rowops_to_grid(q, tl.lay, D, nullptr, 0, 0, qb, st)) != cudaSuccess) break;
-      if ((e = rowops_to_grid(k, tl.lay, D, nullptr, 0, 0, kb, st)) != cudaSuccess) break;
-      if ((e = rowops_to_grid(v, tl.lay, D, nullptr, 0, 0, vb, st)) != cudaSuccess) break;
-      if ((e = rowops_transpose_v(vb, tl.lay.R_cap, Rv, D, vtb, st)) != cudaSuccess) break;
-      rc = tc_attention_launch(qb, kb, vtb, tl.lay, Rv, H, ob, st);
+      const size_t np = prec == FS2_PREC_F16X2 ? 2 : 1;   // bf16x3 has no tensor-core attention: tested as bf16
+      if ((e = cudaMalloc(reinterpret_cast<void**>(&qb), sizeof(bf16) * np * R * D)) != cudaSuccess) break;
+      if ((e = cudaMalloc(reinterpret_cast<void**>(&kb), sizeof(bf16) * np * R * D)) != cudaSuccess) break;
+      if ((e = cudaMalloc(reinterpret_cast<void**>(&vb), sizeof(bf16) * np * R * D)) != cudaSuccess) break;
+      if ((e = cudaMalloc(reinterpret_cast<void**>(&vtb), sizeof(bf16) * np * (size_t)D * Rv)) != cudaSuccess) break;
+      if ((e = cudaMalloc(reinterpret_cast<void**>(&ob), sizeof(bf16) * np * R * D)) != cudaSuccess) break;
+      if ((e = cudaMemsetAsync(ob, 0, sizeof(bf16) * np * R * D, st)) != cudaSuccess) break;
+      if (np == 1) {
+        if ((e = rowops_to_grid(q, tl.lay, D, nullptr, 0, 0, qb, st)) != cudaSuccess) break;
+        if ((e = rowops_to_grid(k, tl.lay, D, nullptr, 0, 0, kb, st)) != cudaSuccess) break;
+        if ((e = rowops_to_grid(v, tl.lay, D, nullptr, 0, 0, vb, st)) != cudaSuccess) break;
+      } else {   // fp32 grid copy (in og) -> two scaled fp16 planes
+        const float* src3[3] = {q, k, v};
+        bf16* dst3[3] = {qb, kb, vb};
+        bool bad = false;
+        for (int i = 0; i < 3 && !bad; ++i) {
+          if ((e = rowops_to_grid(src3[i], tl.lay, D, og, D, 0, nullptr, st)) != cudaSuccess) { bad = true; break; }
+          if ((e = rowops_split(og, (int64_t)(R * D), 2, dst3[i], (int64_t)(R * D), st)) != cudaSuccess) { bad = true; break; }
+        }
+        if (bad) break;
+      }
+      for (size_t pl = 0; pl < np && e == cudaSuccess; ++pl)
+        e = rowops_transpose_v(vb + pl * R * D, tl.lay.R_cap, Rv, D, vtb + pl * (size_t)D * Rv, st);
+      if (e != cudaSuccess) break;
+      rc = tc_attention_launch(qb, kb, vtb, tl.lay, Rv, H, (int)np, ob, st);
       if (rc != FS2_OK) break;
-      if ((e = rowops_bf16_to_f32(ob, (int64_t)(R * D), og, st)) != cudaSuccess) break;
+      if (np == 1) e = rowops_bf16_to_f32(ob, (int64_t)(R * D), og, st);
+      else e = rowops_unsplit2(ob, (int64_t)(R * D), (int64_t)(R * D), og, st);
+      if (e != cudaSuccess) break;
     }
     if ((e = rowops_from_grid(og, tl.lay, D, out, st)) != cudaSuccess) break;
     e = cudaStreamSynchronize(st);

@@ -191,8 +191,8 @@ cudaError_t simt_attention_launch(const float* qkv, int ldqkv, int q_off, int k_
 int tc_conv_gemm_launch(const ConvGemmArgs& a, cudaStream_t st);  // returns FS2_* code
 bool tc_conv_gemm_staged_supported(const ConvGemmArgs& a);        // fs2_tc_gemm_staged.cu: TMA-staged epilogue variant
 int tc_conv_gemm_staged_launch(const ConvGemmArgs& a, cudaStream_t st);
-int tc_attention_launch(const bf16* q, const bf16* k, const bf16* vt, const RowLayout& lay, int Rv, int H, bf16* out_b,
-                        cudaStream_t st);
+int tc_attention_launch(const bf16* q, const bf16* k, const bf16* vt, const RowLayout& lay, int Rv, int H, int planes,
+                        bf16* out_b, cudaStream_t st);
 
 // row operators (fs2_rowops.cu)
 // off/ext/rowmap of `lay` from lens32 (device; null = every utterance has S rows): ext = min(lens + halo_keep, S),
@@ -240,6 +240,7 @@ cudaError_t rowops_bn_fold(const float* conv_bias, const float* g, const float* 
                            const float* var, int n, float eps, float* scale_out, float* bias_out, cudaStream_t st);
 cudaError_t rowops_f32_to_bf16(const float* src, int64_t n, bf16* dst, cudaStream_t st);
 cudaError_t rowops_bf16_to_f32(const bf16* src, int64_t n, float* dst, cudaStream_t st);
+cudaError_t rowops_unsplit2(const bf16* src, int64_t n, int64_t plane_elems, float* dst, cudaStream_t st);  // f16x2 planes -> fp32
 cudaError_t rowops_transpose_v(const bf16* v, int R, int Rv, int D, bf16* vt, cudaStream_t st);
 cudaError_t rowops_add_pe(float* x, const float* pe, const RowLayout& lay, int D, cudaStream_t st);
 cudaError_t rowops_fill_zero(void* p, size_t bytes, cudaStream_t st);

@@ -536,6 +536,16 @@ __global__ void pack_weight_f16x2_kernel(const float* wf, int N, int K, int taps
   reinterpret_cast<uint16_t*>(dst)[plane + i] = lo;
 }
 
+// f16x2 operand planes -> fp32: (hi + lo) / FS2_F16X2_ACT_SCALE
+__global__ void unsplit2_kernel(const bf16* src, int64_t n, int64_t plane_elems, float* dst) {
+  FS2_PDL_PROLOGUE();
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint16_t* s16 = reinterpret_cast<const uint16_t*>(src);
+  const float hi = __half2float(__ushort_as_half(s16[i])), lo = __half2float(__ushort_as_half(s16[plane_elems + i]));
+  dst[i] = (hi + lo) * (1.0f / FS2_F16X2_ACT_SCALE);
+}
+
 __global__ void f32_to_bf16_kernel(const float* src, int64_t n, bf16* dst) {
   FS2_PDL_PROLOGUE();
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -728,6 +738,11 @@ cudaError_t rowops_bn_fold(const float* conv_bias, const float* g, const float* 
 cudaError_t rowops_f32_to_bf16(const float* src, int64_t n, bf16* dst, cudaStream_t st) {
   if (n <= 0) return cudaSuccess;
   (void)FS2_LAUNCH(f32_to_bf16_kernel, blocks_for((size_t)n, 256), 256, 0, st, src, n, dst);
+  return LAUNCHED();
+}
+cudaError_t rowops_unsplit2(const bf16* src, int64_t n, int64_t plane_elems, float* dst, cudaStream_t st) {
+  if (n <= 0) return cudaSuccess;
+  (void)FS2_LAUNCH(unsplit2_kernel, blocks_for((size_t)n, 256), 256, 0, st, src, n, plane_elems, dst);
   return LAUNCHED();
 }
 cudaError_t rowops_bf16_to_f32(const bf16* src, int64_t n, float* dst, cudaStream_t st) {

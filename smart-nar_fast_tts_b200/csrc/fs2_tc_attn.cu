@@ -27,17 +27,25 @@ namespace {
 
 using namespace tc;
 
+// Operand planes NP: 1 = bf16 (decoder); 2 = f16x2 (fs2_common.cuh): Q, K, V^T and P are carried as scaled fp16 hi / lo
+// planes and every MMA becomes three (hi*lo, lo*hi, hi*hi) -- the fp32-faithful attention of the encoder on the tensor
+// cores.  With two planes the tiles double (224 KB) and one CTA owns the SM.
 constexpr int BQ = 128, BKV = 64, DK = 128;
-constexpr int Q_ATOM = BQ * 128;                 // 128 query rows x 64 bf16 (128-byte swizzled rows)
-constexpr int K_ATOM = BKV * 128;                // 64 key rows x 64 bf16
-constexpr int Q_OFF = 0;                         // 2 atoms (d 0..63, 64..127)
-constexpr int K_OFF = Q_OFF + 2 * Q_ATOM;        // 2 stages x 2 atoms
-constexpr int V_OFF = K_OFF + 2 * 2 * K_ATOM;    // 2 stages x [128 d rows x 64 keys]
-constexpr int V_TILE = DK * 128;
-constexpr int P_OFF = V_OFF + 2 * V_TILE;        // [128 query rows x 64 keys]
-constexpr int BAR_OFF = P_OFF + BQ * 128;        // 112 KB
-constexpr int NUM_BARS = 12;
-constexpr int SMEM_TOTAL = BAR_OFF + NUM_BARS * 8 + 16;   // 114,768 B: two CTAs per SM
+constexpr int Q_ATOM = BQ * 128;                 // 128 query rows x 64 elements (128-byte swizzled rows)
+constexpr int K_ATOM = BKV * 128;                // 64 key rows x 64 elements
+constexpr int V_TILE = DK * 128;                 // [128 d rows x 64 keys]
+constexpr int P_TILE = BQ * 128;                 // [128 query rows x 64 keys]
+template <int NP>
+struct AttSmem {
+  static constexpr int Q_OFF = 0;                               // NP planes x 2 atoms (d 0..63, 64..127)
+  static constexpr int K_OFF = Q_OFF + NP * 2 * Q_ATOM;         // 2 stages x NP planes x 2 atoms
+  static constexpr int V_OFF = K_OFF + 2 * NP * 2 * K_ATOM;     // 2 stages x NP planes
+  static constexpr int P_OFF = V_OFF + 2 * NP * V_TILE;         // NP planes
+  static constexpr int BAR_OFF = P_OFF + NP * P_TILE;           // 112 KB (NP = 1) / 224 KB (NP = 2)
+  static constexpr int NUM_BARS = 12;
+  static constexpr int TOTAL = BAR_OFF + NUM_BARS * 8 + 16;
+};
+constexpr float P_SCALE = 2048.0f;               // f16x2: probabilities are split as fp16 terms of p * 2^11
 constexpr int ATT_THREADS = 192;
 constexpr uint32_t TMEM_COLS = 256;              // S0: columns [0,64); S1: [64,128); O: [128,256); 2 CTAs/SM -> 512
 
@@ -47,10 +55,15 @@ __device__ __forceinline__ float fast_exp2(float x) {
   return y;
 }
 
-__global__ void __launch_bounds__(ATT_THREADS, 2)
+template <int NP>
+__global__ void __launch_bounds__(ATT_THREADS, NP == 1 ? 2 : 1)
 tc_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                     const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmO,
-                    const RowLayout lay, bf16* __restrict__ out_b, float scale_log2) {
+                    const RowLayout lay, bf16* out_b, float scale_log2, float out_scale) {
+  using L = AttSmem<NP>;
+  constexpr int Q_OFF = L::Q_OFF, K_OFF = L::K_OFF, V_OFF = L::V_OFF, P_OFF = L::P_OFF, BAR_OFF = L::BAR_OFF,
+                NUM_BARS = L::NUM_BARS;
+  constexpr int NCOMBO = NP == 2 ? 3 : 1;      // (A plane, B plane): hi*lo, lo*hi, hi*hi -- smallest first
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t base = smem_u32(smem);
   const uint32_t bars = base + BAR_OFF;
@@ -70,7 +83,9 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   if (p0 >= len) {  // tile is all padding: zeros, no tensor work (uniform over the CTA)
     for (int idx = threadIdx.x; idx < BQ * (DK / 8); idx += ATT_THREADS) {
       const int q = idx / (DK / 8), c = idx % (DK / 8);
-      if (p0 + q < SA) *reinterpret_cast<uint4*>(out_b + (row0 + p0 + q) * 256 + h * DK + c * 8) = make_uint4(0, 0, 0, 0);
+      if (p0 + q < SA)
+        for (int pl = 0; pl < NP; ++pl)
+          *reinterpret_cast<uint4*>(out_b + ((size_t)pl * lay.R_cap + row0 + p0 + q) * 256 + h * DK + c * 8) = make_uint4(0, 0, 0, 0);
     }
     return;
   }
@@ -103,35 +118,45 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   if (warp == 0) {
     // ===================================================== TMA producer
     if (lane == 0) {
-      mbar_expect_tx(q_full, 2 * Q_ATOM);
-      tma_load_2d(base + Q_OFF, &tmQ, q_full, h * DK, (int)row0 + p0);
-      tma_load_2d(base + Q_OFF + Q_ATOM, &tmQ, q_full, h * DK + 64, (int)row0 + p0);
+      mbar_expect_tx(q_full, NP * 2 * Q_ATOM);
+      for (int pl = 0; pl < NP; ++pl) {
+        tma_load_3d(base + Q_OFF + pl * 2 * Q_ATOM, &tmQ, q_full, h * DK, (int)row0 + p0, pl);
+        tma_load_3d(base + Q_OFF + pl * 2 * Q_ATOM + Q_ATOM, &tmQ, q_full, h * DK + 64, (int)row0 + p0, pl);
+      }
       for (int j = 0; j < nb; ++j) {
         const int s = j & 1;
         const uint32_t par = ((j >> 1) & 1) ^ 1u;
-        const uint32_t ks = base + K_OFF + s * 2 * K_ATOM, vs = base + V_OFF + s * V_TILE;
+        const uint32_t ks = base + K_OFF + s * NP * 2 * K_ATOM, vs = base + V_OFF + s * NP * V_TILE;
         mbar_wait(k_empty0 + 8 * s, par);
-        mbar_expect_tx(k_full0 + 8 * s, 2 * K_ATOM);
-        tma_load_2d(ks, &tmK, k_full0 + 8 * s, h * DK, (int)row0 + j * BKV);
-        tma_load_2d(ks + K_ATOM, &tmK, k_full0 + 8 * s, h * DK + 64, (int)row0 + j * BKV);
+        mbar_expect_tx(k_full0 + 8 * s, NP * 2 * K_ATOM);
+        for (int pl = 0; pl < NP; ++pl) {
+          tma_load_3d(ks + pl * 2 * K_ATOM, &tmK, k_full0 + 8 * s, h * DK, (int)row0 + j * BKV, pl);
+          tma_load_3d(ks + pl * 2 * K_ATOM + K_ATOM, &tmK, k_full0 + 8 * s, h * DK + 64, (int)row0 + j * BKV, pl);
+        }
         mbar_wait(v_empty0 + 8 * s, par);
-        mbar_expect_tx(v_full0 + 8 * s, V_TILE);
-        tma_load_2d(vs, &tmV, v_full0 + 8 * s, (int)row0 + j * BKV, h * DK);
+        mbar_expect_tx(v_full0 + 8 * s, NP * V_TILE);
+        for (int pl = 0; pl < NP; ++pl) tma_load_3d(vs + pl * V_TILE, &tmV, v_full0 + 8 * s, (int)row0 + j * BKV, h * DK, pl);
       }
     }
   } else if (warp == 1) {
     // ===================================================== MMA issuer
     if (lane == 0) {
-      constexpr uint32_t idesc_s = make_idesc_bf16(BQ, BKV), idesc_o = make_idesc_bf16(BQ, DK);
+      constexpr uint32_t FMT = NP == 2 ? 0u : 1u;   // fp16 / bf16 operands
+      constexpr uint32_t idesc_s = make_idesc_f16kind(BQ, BKV, FMT), idesc_o = make_idesc_f16kind(BQ, DK, FMT);
+      constexpr int CA[3] = {0, 1, 0}, CB[3] = {1, 0, 0};
       auto issue_S = [&](int j) {    // scores of block j into score buffer j & 1 (K stage j & 1)
         const int s = j & 1;
         mbar_wait(k_full0 + 8 * s, (j >> 1) & 1);
         fence_after_sync();
 #pragma unroll
-        for (int kk = 0; kk < DK / 16; ++kk) {
-          const uint64_t ad = make_smem_desc_sw128(base + Q_OFF + (kk >> 2) * Q_ATOM) + (uint64_t)(2 * (kk & 3));
-          const uint64_t bd = make_smem_desc_sw128(base + K_OFF + s * 2 * K_ATOM + (kk >> 2) * K_ATOM) + (uint64_t)(2 * (kk & 3));
-          umma_bf16(tmem_S + (uint32_t)(s * 64), ad, bd, idesc_s, kk ? 1u : 0u);
+        for (int c = 0; c < NCOMBO; ++c) {
+          const int pa = NP == 2 ? CA[c] : 0, pb = NP == 2 ? CB[c] : 0;
+#pragma unroll
+          for (int kk = 0; kk < DK / 16; ++kk) {
+            const uint64_t ad = make_smem_desc_sw128(base + Q_OFF + pa * 2 * Q_ATOM + (kk >> 2) * Q_ATOM) + (uint64_t)(2 * (kk & 3));
+            const uint64_t bd = make_smem_desc_sw128(base + K_OFF + (s * NP + pb) * 2 * K_ATOM + (kk >> 2) * K_ATOM) + (uint64_t)(2 * (kk & 3));
+            umma_bf16(tmem_S + (uint32_t)(s * 64), ad, bd, idesc_s, (c | kk) ? 1u : 0u);
+          }
         }
         umma_commit(k_empty0 + 8 * s);   // the K stage is reusable as soon as these MMAs have read it
         umma_commit(s_full0 + 8 * s);
@@ -145,10 +170,14 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         mbar_wait(v_full0 + 8 * s, (j >> 1) & 1);
         fence_after_sync();
 #pragma unroll
-        for (int kk = 0; kk < BKV / 16; ++kk) {
-          const uint64_t ad = make_smem_desc_sw128(base + P_OFF) + (uint64_t)(2 * kk);
-          const uint64_t bd = make_smem_desc_sw128(base + V_OFF + s * V_TILE) + (uint64_t)(2 * kk);
-          umma_bf16(tmem_O, ad, bd, idesc_o, (j | kk) ? 1u : 0u);
+        for (int c = 0; c < NCOMBO; ++c) {
+          const int pa = NP == 2 ? CA[c] : 0, pb = NP == 2 ? CB[c] : 0;
+#pragma unroll
+          for (int kk = 0; kk < BKV / 16; ++kk) {
+            const uint64_t ad = make_smem_desc_sw128(base + P_OFF + pa * P_TILE) + (uint64_t)(2 * kk);
+            const uint64_t bd = make_smem_desc_sw128(base + V_OFF + (s * NP + pb) * V_TILE) + (uint64_t)(2 * kk);
+            umma_bf16(tmem_O, ad, bd, idesc_o, (j | c | kk) ? 1u : 0u);
+          }
         }
         umma_commit(v_empty0 + 8 * s);
         umma_commit(o_ready);
@@ -202,8 +231,22 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           pv[i] = fast_exp2(fmaf(t, scale_log2, neg_ms));   // exp2(-inf) = 0 for masked keys
           bsum += pv[i];
         }
-        *reinterpret_cast<uint4*>(p_row + ((u ^ sw) << 4)) =
-            make_uint4(pack_bf16x2(pv[0], pv[1]), pack_bf16x2(pv[2], pv[3]), pack_bf16x2(pv[4], pv[5]), pack_bf16x2(pv[6], pv[7]));
+        if (NP == 1) {
+          *reinterpret_cast<uint4*>(p_row + ((u ^ sw) << 4)) =
+              make_uint4(pack_bf16x2(pv[0], pv[1]), pack_bf16x2(pv[2], pv[3]), pack_bf16x2(pv[4], pv[5]), pack_bf16x2(pv[6], pv[7]));
+        } else {
+          uint32_t ph[4], pl[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            uint16_t h0, l0, h1, l1;
+            split2h_scaled(pv[2 * i] * P_SCALE, h0, l0);
+            split2h_scaled(pv[2 * i + 1] * P_SCALE, h1, l1);
+            ph[i] = (uint32_t)h0 | ((uint32_t)h1 << 16);
+            pl[i] = (uint32_t)l0 | ((uint32_t)l1 << 16);
+          }
+          *reinterpret_cast<uint4*>(p_row + ((u ^ sw) << 4)) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+          *reinterpret_cast<uint4*>(p_row + P_TILE + ((u ^ sw) << 4)) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+        }
       }
       l = l * alpha + bsum;
       m = m_new;
@@ -227,10 +270,10 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     fence_after_sync();
     const int p = p0 + row;
     const bool valid = p < len;
-    const float inv = valid ? 1.0f / l : 0.f;
+    const float inv = valid ? out_scale / l : 0.f;   // out_scale undoes the operand pre-scales of the f16x2 mode
     const bool interior = p0 + BQ <= SA;       // the whole 128-row tile belongs to this utterance: TMA store
     if (interior) {
-      // stage the [128 x 128] bf16 tile in the (now idle) Q buffers: two 128B-swizzled [128 x 64] atoms
+      // stage the [128 x 128] tile (per plane) in the (now idle) Q buffers: two 128B-swizzled [128 x 64] atoms per plane
       for (int c = 0; c < 4; ++c) {
         tmem_ld32(tmem_O + lane_off + c * 32, v0);
         tmem_wait_ld();
@@ -240,15 +283,26 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           float y[8];
 #pragma unroll
           for (int i = 0; i < 8; ++i) y[i] = __uint_as_float(v0[u * 8 + i]) * inv;
-          *reinterpret_cast<uint4*>(o_row + ((((c & 1) * 4 + u) ^ sw) << 4)) =
-              make_uint4(pack_bf16x2(y[0], y[1]), pack_bf16x2(y[2], y[3]), pack_bf16x2(y[4], y[5]), pack_bf16x2(y[6], y[7]));
+          uint8_t* o16 = o_row + ((((c & 1) * 4 + u) ^ sw) << 4);
+          if (NP == 1) {
+            *reinterpret_cast<uint4*>(o16) =
+                make_uint4(pack_bf16x2(y[0], y[1]), pack_bf16x2(y[2], y[3]), pack_bf16x2(y[4], y[5]), pack_bf16x2(y[6], y[7]));
+          } else {
+            uint32_t hh[4], ll[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) split2h_pair(y[2 * i], y[2 * i + 1], hh[i], ll[i]);
+            *reinterpret_cast<uint4*>(o16) = make_uint4(hh[0], hh[1], hh[2], hh[3]);
+            *reinterpret_cast<uint4*>(o16 + 2 * Q_ATOM) = make_uint4(ll[0], ll[1], ll[2], ll[3]);
+          }
         }
       }
       fence_proxy_async();
       asm volatile("bar.sync 1, 128;" ::: "memory");
       if (threadIdx.x == 64) {
-        tma_store_2d(&tmO, base + Q_OFF, h * DK, (int)row0 + p0);
-        tma_store_2d(&tmO, base + Q_OFF + Q_ATOM, h * DK + 64, (int)row0 + p0);
+        for (int pl = 0; pl < NP; ++pl) {
+          tma_store_3d(&tmO, base + Q_OFF + pl * 2 * Q_ATOM, h * DK, (int)row0 + p0, pl);
+          tma_store_3d(&tmO, base + Q_OFF + pl * 2 * Q_ATOM + Q_ATOM, h * DK + 64, (int)row0 + p0, pl);
+        }
         tma_store_commit();
         tma_store_wait_all();
       }
@@ -265,8 +319,16 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             float y[8];
 #pragma unroll
             for (int u = 0; u < 8; ++u) y[u] = __uint_as_float(v0[i + u]) * inv;
-            *reinterpret_cast<uint4*>(o + c * 32 + i) =
-                make_uint4(pack_bf16x2(y[0], y[1]), pack_bf16x2(y[2], y[3]), pack_bf16x2(y[4], y[5]), pack_bf16x2(y[6], y[7]));
+            if (NP == 1) {
+              *reinterpret_cast<uint4*>(o + c * 32 + i) =
+                  make_uint4(pack_bf16x2(y[0], y[1]), pack_bf16x2(y[2], y[3]), pack_bf16x2(y[4], y[5]), pack_bf16x2(y[6], y[7]));
+            } else {
+              uint32_t hh[4], ll[4];
+#pragma unroll
+              for (int t = 0; t < 4; ++t) split2h_pair(y[2 * t], y[2 * t + 1], hh[t], ll[t]);
+              *reinterpret_cast<uint4*>(o + c * 32 + i) = make_uint4(hh[0], hh[1], hh[2], hh[3]);
+              *reinterpret_cast<uint4*>(o + (size_t)lay.R_cap * 256 + c * 32 + i) = make_uint4(ll[0], ll[1], ll[2], ll[3]);
+            }
           }
         }
       }
@@ -281,30 +343,46 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   }
 }
 
-}  // namespace
 
-int tc_attention_launch(const bf16* q, const bf16* k, const bf16* vt, const RowLayout& lay, int Rv, int H, bf16* out_b,
-                        cudaStream_t st) {
-  if (lay.B <= 0 || lay.S <= 0) return FS2_OK;
-  if (H != 2) return fs2_fail_cuda(cudaErrorInvalidValue, "tc_attention: built for H = 2, d_k = 128");
-  if (!lay.off || !lay.ext || !lay.lens) return fs2_fail_cuda(cudaErrorInvalidValue, "tc_attention: row layout missing");
+
+template <int NP>
+int launch_attention(const bf16* q, const bf16* k, const bf16* vt, const RowLayout& lay, int Rv, int H, bf16* out_b,
+                     cudaStream_t st) {
   const uint64_t R = (uint64_t)lay.R_cap;
   CUtensorMap tmQ, tmK, tmV, tmO;
-  if (!tc::make_tmap_bf16(&tmQ, q, R, 256, 256, BQ) || !tc::make_tmap_bf16(&tmK, k, R, 256, 256, BKV) ||
-      !tc::make_tmap_bf16(&tmV, vt, 256, (uint64_t)Rv, (uint64_t)Rv, DK) || !tc::make_tmap_bf16(&tmO, out_b, R, 256, 256, BQ))
+  // [planes][rows][cols] maps; the V^T planes are [256 d][Rv] each
+  if (!tc::make_tmap_bf16_3d(&tmQ, q, NP, R, 256, 256, R * 256, BQ) || !tc::make_tmap_bf16_3d(&tmK, k, NP, R, 256, 256, R * 256, BKV) ||
+      !tc::make_tmap_bf16_3d(&tmV, vt, NP, 256, (uint64_t)Rv, (uint64_t)Rv, (uint64_t)256 * Rv, DK) ||
+      !tc::make_tmap_bf16_3d(&tmO, out_b, NP, R, 256, 256, R * 256, BQ))
     return fs2_fail_cuda(cudaErrorInvalidValue, "cuTensorMapEncodeTiled(attention)");
   static bool configured = false;
-  const int smem = SMEM_TOTAL;
+  const int smem = AttSmem<NP>::TOTAL;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(tc_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaError_t e = cudaFuncSetAttribute(tc_attention_kernel<NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return fs2_fail_cuda(e, "cudaFuncSetAttribute(tc_attention)");
     configured = true;
   }
   dim3 grid((FS2_ROWS_PER_UTT(lay.S, FS2_HALO) + BQ - 1) / BQ, H, lay.B);
-  const float scale_log2 = (float)(1.4426950408889634 / sqrt((double)DK));
-  (void)FS2_LAUNCH(tc_attention_kernel, grid, ATT_THREADS, smem, st, tmQ, tmK, tmV, tmO, lay, out_b, scale_log2);
+  // softmax(QK^T / sqrt(dk)) in the exp2 domain; f16x2 operands carry 2^4 (Q, K, V) and 2^11 (P) pre-scales
+  const double a = FS2_F16X2_ACT_SCALE;
+  const float scale_log2 = (float)(1.4426950408889634 / sqrt((double)DK) / (NP == 2 ? a * a : 1.0));
+  const float out_scale = NP == 2 ? (float)(1.0 / ((double)P_SCALE * a)) : 1.0f;
+  (void)FS2_LAUNCH((tc_attention_kernel<NP>), grid, ATT_THREADS, smem, st, tmQ, tmK, tmV, tmO, lay, out_b, scale_log2, out_scale);
   ++g_fs2_launches;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fs2_fail_cuda(e, "tc_attention_kernel launch");
   return FS2_OK;
+}
+
+}  // namespace
+
+// planes: 1 = bf16 operands / bf16 output; 2 = f16x2 operand planes in, f16x2 operand planes out (fs2_common.cuh)
+int tc_attention_launch(const bf16* q, const bf16* k, const bf16* vt, const RowLayout& lay, int Rv, int H, int planes,
+                        bf16* out_b, cudaStream_t st) {
+  if (lay.B <= 0 || lay.S <= 0) return FS2_OK;
+  if (H != 2) return fs2_fail_cuda(cudaErrorInvalidValue, "tc_attention: built for H = 2, d_k = 128");
+  if (!lay.off || !lay.ext || !lay.lens) return fs2_fail_cuda(cudaErrorInvalidValue, "tc_attention: row layout missing");
+  if (planes == 2) return launch_attention<2>(q, k, vt, lay, Rv, H, out_b, st);
+  if (planes == 1) return launch_attention<1>(q, k, vt, lay, Rv, H, out_b, st);
+  return fs2_fail_cuda(cudaErrorInvalidValue, "tc_attention: planes must be 1 or 2");
 }

@@ -410,6 +410,11 @@ int launch(const ConvGemmArgs& a, cudaStream_t st) {
 
 }  // namespace
 
+static bool direct_only_env() {   // A/B switch for profiling
+  static const bool v = getenv("FS2_DIRECT_EPILOGUE") != nullptr;
+  return v;
+}
+
 int tc_conv_gemm_launch(const ConvGemmArgs& a, cudaStream_t st) {
   const int R = a.lay.R_cap;
   if (R <= 0) return FS2_OK;
@@ -420,7 +425,9 @@ int tc_conv_gemm_launch(const ConvGemmArgs& a, cudaStream_t st) {
   const bool ln = (a.epi == EPI_RES_LN || a.epi == EPI_RELU_LN || a.epi == EPI_RELU_LN_DOT);
   if (ln && a.N != 256) return fs2_fail_cuda(cudaErrorInvalidValue, "tc_conv_gemm: LayerNorm epilogue needs N == 256");
   if (a.epi == EPI_QKV && a.N != 768) return fs2_fail_cuda(cudaErrorInvalidValue, "tc_conv_gemm: QKV epilogue needs N == 768");
-  static const bool direct_only = getenv("FS2_DIRECT_EPILOGUE") != nullptr;   // A/B switch for profiling
+  if (a.epi == EPI_QKV && a.planes == 2 && (direct_only_env() || !tc_conv_gemm_staged_supported(a)))
+    return fs2_fail_cuda(cudaErrorInvalidValue, "tc_conv_gemm: the f16x2 QKV epilogue exists in the staged kernel only");
+  const bool direct_only = direct_only_env();
   if (!direct_only && tc_conv_gemm_staged_supported(a)) return tc_conv_gemm_staged_launch(a, st);
   if (a.N % 256 == 0) return launch<256>(a, st);
   if (a.N <= 128) return launch<128>(a, st);

@@ -393,13 +393,24 @@ tc_conv_gemm_staged_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
             uint8_t* fb = Fbuf + (c & 1) * CH_F32;
             if (elected) tma_store_wait_read_n<1>();
             bar_grp();
-            bf16* vt_s = reinterpret_cast<bf16*>(fb);                   // [32 d][128 rows]
+            uint16_t* vt_s = reinterpret_cast<uint16_t*>(fb);           // [out_planes][32 d][128 rows]
+            if (out_planes == 1) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) vt_s[j * BM + row] = __float2bfloat16_rn(y[j]);
+              for (int j = 0; j < 32; ++j) vt_s[j * BM + row] = __bfloat16_as_ushort(__float2bfloat16_rn(y[j]));
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                uint16_t hi, lo;
+                split2h_scaled(y[j] * FS2_F16X2_ACT_SCALE, hi, lo);
+                vt_s[j * BM + row] = hi;
+                vt_s[32 * BM + j * BM + row] = lo;
+              }
+            }
             fence_proxy_async();
             bar_grp();
             if (elected) {
-              tma_store_2d(&tmVt, base + (uint32_t)(fb - smem), r0, gc0 + c * 32);
+              for (int pl = 0; pl < out_planes; ++pl)
+                tma_store_3d(&tmVt, base + (uint32_t)(fb - smem) + pl * CH_B16, r0, gc0 + c * 32, pl);
               tma_store_commit();
             }
           }
@@ -485,10 +496,11 @@ int tc_conv_gemm_staged_launch(const ConvGemmArgs& a, cudaStream_t st) {
   ok = ok && f32_map(&tmRes, a.epi == EPI_RES_LN ? a.residual : (a.out ? a.out : reinterpret_cast<const float*>(a.Ab)), 256);
   ok = ok && f32_map(&tmOutF, a.out ? a.out : reinterpret_cast<const float*>(a.Ab), a.out ? a.ldo : 256);
   if (a.epi == EPI_QKV) {
-    ok = ok && b16_map(&tmOutB0, a.q_b, 256, 1) && b16_map(&tmOutB1, a.k_b, 256, 1);
-    const uint64_t dims[2] = {(uint64_t)a.Rv, 256}, strides[1] = {(uint64_t)a.Rv * 2};
-    const uint32_t box[2] = {(uint32_t)BM, 32};
-    ok = ok && make_tmap_generic(&tmVt, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a.vt_b, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE);
+    const int qp = a.planes == 2 ? 2 : 1;           // Q, K, V^T operand planes for the attention kernel
+    ok = ok && b16_map(&tmOutB0, a.q_b, 256, qp) && b16_map(&tmOutB1, a.k_b, 256, qp);
+    const uint64_t dims[3] = {(uint64_t)a.Rv, 256, (uint64_t)qp}, strides[2] = {(uint64_t)a.Rv * 2, (uint64_t)a.Rv * 512};
+    const uint32_t box[3] = {(uint32_t)BM, 32, 1};
+    ok = ok && make_tmap_generic(&tmVt, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, a.vt_b, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE);
   } else {
     const bf16* ob = a.out_b ? a.out_b : a.Ab;
     ok = ok && b16_map(&tmOutB0, ob, a.out_b ? a.ldob : a.K, a.out_b ? out_planes : 1);
@@ -513,8 +525,8 @@ int tc_conv_gemm_staged_launch(const ConvGemmArgs& a, cudaStream_t st) {
   const int tiles = (int)((R + BM - 1) / BM) * num_n_blocks;
   const int grid = tiles < num_sms ? tiles : num_sms;
   ConvGemmArgs b = a;
-  if (a.epi == EPI_QKV) b.out_planes = 1;
-  const Plan plan = plan_for(a, a.epi == EPI_QKV ? 1 : out_planes);
+  if (a.epi == EPI_QKV) b.out_planes = a.planes == 2 ? 2 : 1;
+  const Plan plan = plan_for(a, a.epi == EPI_QKV ? 1 : out_planes);   // Q / K / V^T are staged in the fp32 buffers
   if (plan.total() > 227 * 1024) return fs2_fail_cuda(cudaErrorInvalidValue, "tc_conv_gemm_staged: shared-memory plan");
   (void)FS2_LAUNCH(tc_conv_gemm_staged_kernel, grid, NUM_THREADS, plan.total(), st, tmA, tmB, tmRes, tmOutF, tmOutB0,
                    tmOutB1, tmVt, b, num_n_blocks, plan);

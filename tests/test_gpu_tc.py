@@ -69,6 +69,34 @@ def test_tc_attention(lib, B, S):
     assert bool((out.cpu()[mask] == 0).all())
 
 
+@pytest.mark.parametrize("B,S", [(3, 70), (2, 128), (2, 300), (1, 1), (2, 1100)])
+def test_tc_attention_f16x2_matches_fp32(lib, B, S):
+    """f16x2 tensor-core attention (scaled fp16 hi / lo operand planes, 3 MMAs per product, fp32 softmax) on UNROUNDED
+    fp32 inputs against a float64 reference: it must be as close as the fp32 FFMA attention kernel."""
+    rng = np.random.Generator(np.random.PCG64(S + 17))
+    H, dk, D = 2, 128, 256
+    q, k, v = (torch.from_numpy(rng.standard_normal((B, S, D)).astype(np.float32)) for _ in range(3))
+    lens = torch.from_numpy(rng.integers(1, S + 1, size=B).astype(np.int64))
+    lens[0] = S
+    mask = O.get_mask_from_lengths(lens, S)
+    qh, kh, vh = (t.double().view(B, S, H, dk).permute(0, 2, 1, 3) for t in (q, k, v))
+    att = (qh @ kh.transpose(-1, -2)) / np.power(dk, 0.5)
+    att = att.masked_fill(mask[:, None, None, :], -np.inf).softmax(-1)
+    ref = (att @ vh).permute(0, 2, 1, 3).reshape(B, S, D).masked_fill(mask.unsqueeze(-1), 0)
+    qd, kd, vd, ld = q.to(DEV), k.to(DEV), v.to(DEV), lens.to(DEV)
+    errs = {}
+    for prec in (0, 3):
+        out = torch.empty(B, S, D, device=DEV)
+        lib.check(lib.fs2_op_attention(prec, qd.data_ptr(), kd.data_ptr(), vd.data_ptr(), ld.data_ptr(), B, S, H, dk,
+                                       out.data_ptr(), stream()))
+        torch.cuda.synchronize()
+        errs[prec] = max_abs(out.cpu(), ref)
+        assert bool((out.cpu()[mask] == 0).all())
+    print(f"attention S={S}: max|err| fp32-FFMA {errs[0]:.2e}  f16x2 {errs[3]:.2e}")
+    # the test reads the f16x2 result back from its two fp16 operand planes (22 significant bits): 2^-22 on O(1) values
+    assert errs[3] < 3e-6 and errs[3] < 4 * errs[0] + 1e-6, errs
+
+
 @pytest.fixture(scope="module")
 def sd():
     return O.make_state_dict(0)
