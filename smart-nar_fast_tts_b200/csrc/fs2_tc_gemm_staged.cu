@@ -28,7 +28,7 @@ constexpr int BM = 128, BN = 256, BKE = 64;
 constexpr int NUM_THREADS = 352;                          // warp 0 TMA (A), warp 1 MMA, warp 2 TMA (B), warps 3-10 epilogue
 constexpr int EPI_T0 = 96;                                // first epilogue thread
 constexpr int A_BYTES = BM * BKE * 2, B_BYTES = BN * BKE * 2;   // 16 KB / 32 KB per k-block
-constexpr int MAX_A = 4, MAX_B = 3;                       // ring depths: A streams from HBM (deep), W from L2 (shallow)
+constexpr int MAX_A = 4, MAX_B = 4;                       // ring depths: A streams from HBM (deep), W from L2 (shallow)
 constexpr int CH_F32 = BM * 32 * 4;                       // 16 KB: [128 rows][32 fp32], 128-byte rows, SWIZZLE_128B
 constexpr int CH_B16 = BM * 32 * 2;                       //  8 KB: [128 rows][32 bf16],  64-byte rows, SWIZZLE_64B
 // shared-memory plan (bytes from the 1024-aligned base), chosen per launch (struct Plan):
@@ -42,6 +42,7 @@ constexpr int PARAM_BYTES = (2 * 128 + 256 + 256) * 4 + 2 * 2 * 128 * 8;
 constexpr int NUM_BARS = 2 * MAX_A + 2 * MAX_B + 4 + 4;
 struct Plan {
   int nA, nB, wide, grp_bytes;
+  int serial_planes;   // deep plan with several operand planes out: the planes go through ONE 8 KB staging tile in turn
   __host__ __device__ int ring_bytes() const { return nA * A_BYTES + nB * B_BYTES; }
   __host__ __device__ int total() const { return ring_bytes() + 2 * grp_bytes + PARAM_BYTES + NUM_BARS * 8 + 16; }
 };
@@ -214,6 +215,31 @@ tc_conv_gemm_staged_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
     auto stage_out = [&](const float (&y)[32], int c, int gcol, int r0, bool wf, bool wb, bool bF, const CUtensorMap* mapB) {
       uint8_t* fb = Fbuf + (c & 1) * CH_F32;
       uint8_t* bb = bF ? fb : Bbuf;
+      if (plan.serial_planes && wb && !wf && out_planes == 2) {
+        // mainloop-bound producers with two operand planes out (encoder FFN conv k=9 in f16x2): the staging tile is kept to
+        // 8 KB so that the weight ring gets a fourth stage; hi and lo plane leave one after the other
+        uint32_t hh[16], ll[16];
+#pragma unroll
+        for (int u = 0; u < 16; ++u) split2h_pair(y[2 * u], y[2 * u + 1], hh[u], ll[u]);
+        uint8_t* orow = Bbuf + row * 64;
+#pragma unroll
+        for (int pl = 0; pl < 2; ++pl) {
+          if (elected) tma_store_wait_read_n<0>();
+          bar_grp();
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            *reinterpret_cast<uint4*>(orow + ((j ^ sw64) << 4)) =
+                pl == 0 ? make_uint4(hh[4 * j], hh[4 * j + 1], hh[4 * j + 2], hh[4 * j + 3])
+                        : make_uint4(ll[4 * j], ll[4 * j + 1], ll[4 * j + 2], ll[4 * j + 3]);
+          fence_proxy_async();
+          bar_grp();
+          if (elected) {
+            tma_store_3d(mapB, base + (uint32_t)(Bbuf - smem), gcol, r0, pl);
+            tma_store_commit();
+          }
+        }
+        return;
+      }
       if (elected) {
         if (wf || bF) tma_store_wait_read_n<1>(); else tma_store_wait_read_n<0>();
       }
@@ -455,9 +481,13 @@ tc_conv_gemm_staged_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
 Plan plan_for(const ConvGemmArgs& a, int out_planes) {
   Plan p;
   p.wide = (a.epi == EPI_RES_LN || a.epi == EPI_QKV || a.out != nullptr) ? 1 : 0;
-  p.grp_bytes = (p.wide ? 2 * CH_F32 : 0) + out_planes * CH_B16;
-  p.nB = p.wide ? 2 : 3;
+  p.serial_planes = (!p.wide && out_planes == 2) ? 1 : 0;
+  p.grp_bytes = (p.wide ? 2 * CH_F32 : 0) + (p.serial_planes ? 1 : out_planes) * CH_B16;
+  // a k-step consumes one A and one B stage: the pipeline is as deep as the shallower ring.  Deepest B ring that
+  // fits next to a full A ring, then shrink the A ring if even two B stages do not fit.
   p.nA = MAX_A;
+  p.nB = MAX_B;
+  while (p.nB > 2 && p.total() > 227 * 1024) --p.nB;
   while (p.nA > 2 && p.total() > 227 * 1024) --p.nA;
   return p;
 }
