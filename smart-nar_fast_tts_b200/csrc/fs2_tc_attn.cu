@@ -213,8 +213,14 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       float bm = -INFINITY;
 #pragma unroll
       for (int i = 0; i < 32; ++i) bm = fmaxf(bm, fmaxf(__uint_as_float(v0[i]), __uint_as_float(v1[i])));
-      const float m_new = fmaxf(m, bm);          // finite: every processed block holds >= 1 valid key
-      const float alpha = fast_exp2((m - m_new) * scale_log2);  // 0 on the first block (m = -inf); exactly 1 when the max is unchanged
+      // m is the REFERENCE maximum the running sum and O are expressed against.  It only moves when a block's maximum
+      // exceeds it by more than SLACK in the exp2 domain: probabilities may then reach 2^SLACK (exact in fp32, harmless
+      // in bf16 / scaled fp16), and the O rescale pass -- a full TMEM round trip -- practically never runs after the first
+      // block (with the exact running maximum nearly every block of a short utterance raised some row of the warp).
+      constexpr float SLACK = NP == 1 ? 8.0f : 4.0f;   // f16x2: p * 2^11 must stay below the fp16 maximum
+      const bool raise = (bm - m) * scale_log2 > SLACK;          // first block: m = -inf -> true; bm is finite (>= 1 valid key)
+      const float m_new = raise ? bm : m;
+      const float alpha = raise ? fast_exp2((m - m_new) * scale_log2) : 1.0f;   // 0 on the first block
       const float neg_ms = -m_new * scale_log2;
       if (j > 0) {                               // P buffer and O are free once P(j-1)V(j-1) has completed
         mbar_wait(o_ready, (j - 1) & 1);
