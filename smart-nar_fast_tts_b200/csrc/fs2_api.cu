@@ -89,6 +89,7 @@ struct fs2_handle {
   // stage-1 -> stage-2 state
   bool have_stage1 = false;
   int st_B = 0, st_L = 0, st_Tmax = 0;
+  int st_frames = 0;            // frames of the whole batch (sum of mel_lens): sizes the tile-shape decisions of stage 2
   float* st_enc_out = nullptr;  // encoder output, rows in the stage-1 layout
   RowLayout st_lay1{};          // stage-1 (phoneme) row layout; its buffers live in the workspace
 
@@ -311,6 +312,7 @@ int make_layout(fs2_handle* h, const std::string& name, const int* lens32, int B
   HCHECK(rowops_build_layout(lens32, B, S, halo_keep, halo_rows, off, ext, rowmap, R_cap, st, extra_ext));
   out->B = Bt; out->S = S; out->R_cap = R_cap; out->off = off; out->ext = ext; out->lens = extra_ext > 0 ? nullptr : lens32;
   out->rowmap = rowmap;
+  out->rows_hint = 0;
   return FS2_OK;
 }
 
@@ -502,6 +504,10 @@ int run_mel_postnet(fs2_handle* h, int prec, const float* dec, const bf16* decb,
   // never fewer rows than the source layout carries (mel_linear scatters every source grid row into this grid)
   const int keep = !lay.lens ? T : (h->halo_keep > 2 * H ? h->halo_keep : 2 * H);
   RCHECK(make_layout(h, "pn.lay", lay.lens, B, T, keep, FS2_HALO, &pn, st, T < 2 * H + 1 ? T : 2 * H + 1));
+  if (lay.rows_hint > 0 && keep < T) {
+    const long long est = (long long)lay.rows_hint + (long long)B * (keep - h->halo_keep) + 4 * H;
+    pn.rows_hint = (int)(est < pn.R_cap ? est : pn.R_cap);
+  }
   const size_t R = (size_t)pn.R_cap;
   WS(float, melg, "pn.mel", R * M);
   WS(float, postg, "pn.post", R * M);
@@ -591,7 +597,7 @@ int fs2_create(fs2_handle** out, const fs2_dims* d, int device) {
   fs2_handle* h = new fs2_handle();
   h->dims = *d;
   h->device = device;
-  e = cudaMallocHost(reinterpret_cast<void**>(&h->host_tmax), sizeof(int));
+  e = cudaMallocHost(reinterpret_cast<void**>(&h->host_tmax), 2 * sizeof(int));
   if (e != cudaSuccess) { delete h; return fs2_fail_cuda(e, "cudaMallocHost"); }
   *out = h;
   return FS2_OK;
@@ -718,7 +724,7 @@ int fs2_forward_stage1(fs2_handle* h, const int64_t* texts, const int64_t* src_l
   WS(int, lens32, "s1.lens32", B);
   WS(int, cum, "s1.cum", (size_t)B * L);
   WS(int, mlens32, "s1.mel_lens32", B);
-  WS(int, tmax_dev, "s1.tmax", 1);
+  WS(int, tmax_dev, "s1.tmax", 2);   // [0] max frames of an utterance, [1] frames of the batch
   HCHECK(rowops_lens_to_i32(src_lens, B, L, lens32, st));
   // packed phoneme rows: valid rows + the 2 padded rows the duration predictor's convolutions can see (+ zero halo)
   RowLayout lay;
@@ -758,14 +764,15 @@ int fs2_forward_stage1(fs2_handle* h, const int64_t* texts, const int64_t* src_l
   {
     PROF("rows.round_scan");
     HCHECK(rowops_round_durations(log_d, (int64_t)B * L, d_control, d_rounded, st));
-    HCHECK(cudaMemsetAsync(tmax_dev, 0, sizeof(int), st));
+    HCHECK(cudaMemsetAsync(tmax_dev, 0, 2 * sizeof(int), st));
     HCHECK(rowops_duration_scan(d_rounded, B, L, cum, mel_lens, mlens32, tmax_dev, st));
   }
-  HCHECK(cudaMemcpyAsync(h->host_tmax, tmax_dev, sizeof(int), cudaMemcpyDeviceToHost, st));
+  HCHECK(cudaMemcpyAsync(h->host_tmax, tmax_dev, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
   HCHECK(cudaStreamSynchronize(st));  // the one data-dependent size of the path
   *T_max_out = *h->host_tmax;
   h->have_stage1 = true;
-  h->st_B = B; h->st_L = L; h->st_Tmax = *h->host_tmax;
+  h->st_B = B; h->st_L = L; h->st_Tmax = h->host_tmax[0];
+  h->st_frames = h->host_tmax[1];
   h->st_enc_out = x;
   h->st_lay1 = lay;
   return FS2_OK;
@@ -791,6 +798,11 @@ int fs2_forward_stage2(fs2_handle* h, int32_t T, float p_control, float e_contro
   // packed frame rows: valid frames + the 2 padded rows the pitch / energy predictors can see (+ zero halo)
   RowLayout lay;
   RCHECK(make_layout(h, "s2.lay", mlens32, B, T, h->halo_keep, FS2_HALO, &lay, st));
+  // rows in use, estimated on the host from the batch's frame count (exact up to the 8-row alignment of each utterance)
+  if (h->halo_keep < T) {
+    const long long est = (long long)h->st_frames + (long long)B * (h->halo_keep + FS2_HALO + FS2_ROW_ALIGN / 2);
+    lay.rows_hint = (int)(est < lay.R_cap ? est : lay.R_cap);
+  }
   const size_t R = (size_t)lay.R_cap;
   WS(float, x, "s2.x", R * D);
   bf16* xb = nullptr;
@@ -889,8 +901,8 @@ int fs2_duration_scan(const float* dd, int32_t B, int32_t L, int32_t* cum, int64
   if (!dd || !cum || !mel_lens || !T_max_out || B <= 0 || L <= 0) { g_last_error = "bad argument"; return FS2_ERR_INVALID; }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   int* tmax = nullptr;
-  FS2_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&tmax), sizeof(int)));
-  cudaError_t e = cudaMemsetAsync(tmax, 0, sizeof(int), st);
+  FS2_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&tmax), 2 * sizeof(int)));   // [0] max, [1] batch total
+  cudaError_t e = cudaMemsetAsync(tmax, 0, 2 * sizeof(int), st);
   if (e == cudaSuccess) e = rowops_duration_scan(dd, B, L, cum, mel_lens, nullptr, tmax, st);
   int host = 0;
   if (e == cudaSuccess) e = cudaMemcpyAsync(&host, tmax, sizeof(int), cudaMemcpyDeviceToHost, st);

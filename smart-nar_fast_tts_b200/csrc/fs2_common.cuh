@@ -68,6 +68,7 @@ struct RowLayout {
   const int* ext;          // [B] device: grid rows of utterance b
   const int* lens;         // [B] device: valid rows (p < lens[b]); may be null where no length mask applies
   const unsigned* rowmap;  // [R_cap] device: (b << 16) | p for grid rows, FS2_ROW_NONE for halo / unused rows
+  int rows_hint;           // host-side estimate of off[B] (rows in use) for tile-shape decisions; 0 = unknown (use R_cap)
 };
 #define FS2_ROW_NONE 0xFFFFFFFFu
 #define FS2_MAX_ROWS_PER_UTT 65535
@@ -260,16 +261,23 @@ __device__ __forceinline__ void griddep_launch_dependents() { asm volatile("grid
 
 extern int g_fs2_pdl;  // 1: launch with the programmatic-stream-serialization attribute (default; FS2_NO_PDL=1 clears it)
 template <typename F>
-inline cudaError_t fs2_launch_cfg(dim3 grid, dim3 block, size_t smem, cudaStream_t st, F&& f) {
+inline cudaError_t fs2_launch_cfg(dim3 grid, dim3 block, size_t smem, cudaStream_t st, F&& f, int cluster_x = 1) {
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof cfg);
   cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = g_fs2_pdl;
   cfg.attrs = attr; cfg.numAttrs = 1;
+  if (cluster_x > 1) {   // thread-block cluster along x
+    attr[1].id = cudaLaunchAttributeClusterDimension;
+    attr[1].val.clusterDim.x = (unsigned)cluster_x; attr[1].val.clusterDim.y = 1; attr[1].val.clusterDim.z = 1;
+    cfg.numAttrs = 2;
+  }
   return f(&cfg);
 }
 // FS2_LAUNCH(kernel, grid, block, smem_bytes, stream, args...) -> cudaError_t
 #define FS2_LAUNCH(kernel, grid, block, smem, st, ...) \
   fs2_launch_cfg(grid, block, smem, st, [&](const cudaLaunchConfig_t* _c) { return cudaLaunchKernelEx(_c, kernel, __VA_ARGS__); })
+#define FS2_LAUNCH_CLUSTER(cluster_x, kernel, grid, block, smem, st, ...) \
+  fs2_launch_cfg(grid, block, smem, st, [&](const cudaLaunchConfig_t* _c) { return cudaLaunchKernelEx(_c, kernel, __VA_ARGS__); }, cluster_x)

@@ -227,7 +227,10 @@ __global__ void __launch_bounds__(1024) duration_scan_kernel(const float* d, int
     const int total = carry_s;
     if (mel_lens) mel_lens[b] = total;
     if (mel_lens32) mel_lens32[b] = total;
-    if (tmax) atomicMax(tmax, total);
+    if (tmax) {               // tmax[0] = longest utterance (frames), tmax[1] = frames of the whole batch (saturating)
+      atomicMax(tmax, total);
+      atomicAdd(tmax + 1, total);
+    }
   }
 }
 

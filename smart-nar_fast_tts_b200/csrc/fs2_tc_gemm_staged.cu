@@ -17,17 +17,24 @@
 // and double-buffer the fp32 output tiles in pass 2.  LayerNorm needs one exchange per tile: the two threads that
 // share a row swap their partial (sum, sum of squares) through shared memory (64-thread named barrier per lane quarter).
 // Row masking is by value (masked rows store zeros); rows past the end of the buffer are clipped by TMA.
+//
+// Tile width (Plan::bn): 256 columns, or 128 when that fills the 148 SMs better (the launcher compares the number of
+// rounds: at batch 32 the decoder has 151 row tiles, i.e. TWO rounds of 256-wide tiles for every N = 256 GEMM, and the
+// encoder only 22).  A LayerNorm epilogue needs the whole 256-column row: with 128-wide tiles the two CTAs that share a row
+// tile form a 2-CTA cluster and swap their partial (sum, sum of squares) through distributed shared memory
+// (st.shared::cluster + remote mbarrier arrive with release / acquire at cluster scope), one exchange per tile.
 #include "fs2_tc_common.cuh"
 #include "../../include/fs2_b200.h"
+#include <stdlib.h>
 
 namespace {
 
 using namespace tc;
 
-constexpr int BM = 128, BN = 256, BKE = 64;
+constexpr int BM = 128, BN_MAX = 256, BKE = 64;
 constexpr int NUM_THREADS = 352;                          // warp 0 TMA (A), warp 1 MMA, warp 2 TMA (B), warps 3-10 epilogue
 constexpr int EPI_T0 = 96;                                // first epilogue thread
-constexpr int A_BYTES = BM * BKE * 2, B_BYTES = BN * BKE * 2;   // 16 KB / 32 KB per k-block
+constexpr int A_BYTES = BM * BKE * 2;                     // 16 KB per k-block; the weight k-block is bn x 128 B (32 / 16 KB)
 constexpr int MAX_A = 4, MAX_B = 4;                       // ring depths: A streams from HBM (deep), W from L2 (shallow)
 constexpr int CH_F32 = BM * 32 * 4;                       // 16 KB: [128 rows][32 fp32], 128-byte rows, SWIZZLE_128B
 constexpr int CH_B16 = BM * 32 * 2;                       //  8 KB: [128 rows][32 bf16],  64-byte rows, SWIZZLE_64B
@@ -36,17 +43,21 @@ constexpr int CH_B16 = BM * 32 * 2;                       //  8 KB: [128 rows][3
 //   B ring          nB x 32 KB   (weight k-blocks: L2 hits, shallow)
 //   group g region  wide plan: F0, F1 (2 x 16 KB fp32 staging / residual) + B staging (out_planes x 8 KB)
 //                   deep plan: B staging only
-//   params          bias[2][128], ln_g[256], ln_b[256], stats[2 parities][2 groups][128] float2
+//   params          bias[2][128], ln_g[256], ln_b[256], stats[2 parities][2 groups][128] float2,
+//                   xstat[2 parities][128] float2 (the peer CTA's LayerNorm partial sums, written remotely)
 //   barriers
-constexpr int PARAM_BYTES = (2 * 128 + 256 + 256) * 4 + 2 * 2 * 128 * 8;
-constexpr int NUM_BARS = 2 * MAX_A + 2 * MAX_B + 4 + 4;
+constexpr int PARAM_BYTES = (2 * 128 + 256 + 256) * 4 + 2 * 2 * 128 * 8 + 2 * 128 * 8;
+constexpr int NUM_BARS = 2 * MAX_A + 2 * MAX_B + 4 + 4 + 2;
 struct Plan {
   int nA, nB, wide, grp_bytes;
   int serial_planes;   // deep plan with several operand planes out: the planes go through ONE 8 KB staging tile in turn
-  __host__ __device__ int ring_bytes() const { return nA * A_BYTES + nB * B_BYTES; }
+  int bn;              // tile width: 256 or 128 columns
+  int ln_pair;         // LayerNorm over a 2-CTA cluster (bn == 128): partial row statistics are exchanged through DSMEM
+  __host__ __device__ int b_bytes() const { return bn * BKE * 2; }
+  __host__ __device__ int ring_bytes() const { return nA * A_BYTES + nB * b_bytes(); }
   __host__ __device__ int total() const { return ring_bytes() + 2 * grp_bytes + PARAM_BYTES + NUM_BARS * 8 + 16; }
 };
-constexpr uint32_t TMEM_COLS = 2 * BN;
+constexpr uint32_t TMEM_COLS = 2 * BN_MAX;
 
 __constant__ int s_combo_a[6] = {0, 2, 1, 0, 1, 0};       // bf16x3 cross products, smallest first (see fs2_tc_gemm.cu)
 __constant__ int s_combo_b[6] = {2, 0, 1, 1, 0, 0};
@@ -65,6 +76,7 @@ tc_conv_gemm_staged_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t base = smem_u32(smem);
   const int nA = plan.nA, nB = plan.nB;
+  const int BN = plan.bn, B_BYTES = plan.b_bytes();
   const uint32_t ringB = base + nA * A_BYTES;      // B ring follows the A ring
   const int ring_bytes = plan.ring_bytes();
   const int grp_sz = plan.grp_bytes;
@@ -73,6 +85,7 @@ tc_conv_gemm_staged_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
   float* s_g = s_bias + 256;
   float* s_b = s_g + 256;
   float2* s_stat = reinterpret_cast<float2*>(s_b + 256);                // [2 parities][2 groups][128]
+  float2* s_xstat = s_stat + 2 * 2 * 128;                               // [2 parities][128], written by the peer CTA
   const int bar_off = param_off + PARAM_BYTES;
   const uint32_t bars = base + bar_off;
   auto fullA = [&](int s) { return bars + 8u * s; };
@@ -83,6 +96,7 @@ tc_conv_gemm_staged_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
   auto tfull_bar = [&](int s) { return bars + 8u * (TB0 + s); };
   auto tempty_bar = [&](int s) { return bars + 8u * (TB0 + 2 + s); };
   auto res_bar = [&](int g, int s) { return bars + 8u * (TB0 + 4 + 2 * g + s); };
+  auto xfull_bar = [&](int s) { return bars + 8u * (TB0 + 8 + s); };
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + bar_off + NUM_BARS * 8);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -102,6 +116,7 @@ tc_conv_gemm_staged_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
     for (int s = 0; s < MAX_B; ++s) { mbar_init(fullB(s), 1); mbar_init(emptyB(s), 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 8); }
     for (int g = 0; g < 2; ++g) for (int s = 0; s < 2; ++s) mbar_init(res_bar(g, s), 1);
+    for (int s = 0; s < 2; ++s) mbar_init(xfull_bar(s), 128);   // one remote arrive per row of the peer CTA
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -116,6 +131,7 @@ tc_conv_gemm_staged_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
   griddep_wait();   // first access to predecessor-written global memory is below
   fence_before_sync();
   __syncthreads();
+  if (plan.ln_pair) cluster_sync_all();   // the peer's barriers exist before any remote arrive can reach them
   fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
   const int R = ld_act(a.lay.off + a.lay.B);
@@ -160,7 +176,7 @@ tc_conv_gemm_staged_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
   } else if (warp == 1) {
     // ===================================================== MMA issuer
     if (lane == 0) {
-      const uint32_t idesc = make_idesc_f16kind(BM, BN, a.planes == 2 ? 0u : 1u);
+      const uint32_t idesc = make_idesc_f16kind(BM, BN, a.planes == 2 ? 0u : 1u);   // N = tile width (256 / 128)
       int sa_i = 0, sb_i = 0; uint32_t pha = 0, phb = 0;
       int as = 0; uint32_t aphase = 0;
       const int steps = iters * ncombo;
@@ -201,12 +217,14 @@ tc_conv_gemm_staged_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
     uint8_t* Bbuf = smem + grp_off + (wide ? 2 * CH_F32 : 0);
     const bool has_res = a.epi == EPI_RES_LN;
     const int out_planes = a.out_planes == 3 ? 3 : a.out_planes == 2 ? 2 : 1;
+    const int HALF = BN >> 1;                       // columns per group: 128 or 64
+    const int NCH = HALF >> 5;                      // 32-column chunks per group: 4 or 2
+    const int gc0 = g * HALF;                       // this group's first column within the tile
     float* my_bias = s_bias + g * 128;
-    const float* my_g = s_g + g * 128;
-    const float* my_b = s_b + g * 128;
     int res_cnt = 0;                                // residual chunks consumed so far by this thread (buffer / parity)
     int as = 0; uint32_t aphase = 0;
     uint32_t tile_par = 0;
+    uint32_t xphase = 0;                            // bit i = phase of peer-statistics barrier i
 
     // Stage one 32-column chunk (index c within the group's half) of this thread's row and ship it.
     //   wf: fp32 tile via tmOutF, staged in F[c & 1]; wb: bf16 plane tiles via mapB, staged in B (or, when bF, in F[c & 1]).
@@ -304,7 +322,8 @@ tc_conv_gemm_staged_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m_blk = tile / num_n_blocks, n_blk = tile - m_blk * num_n_blocks;
       const int n0 = n_blk * BN, r0 = m_blk * BM;
-      const int gc0 = g * 128;                       // this group's first column within the tile
+      const float* my_g = s_g + (n0 & 255) + gc0;    // LayerNorm parameters of this thread's columns (N == 256)
+      const float* my_b = s_b + (n0 & 255) + gc0;
       // residual prefetch: chunks 0 and 1 of this group's half (the F buffers double as output staging in pass 2 of the
       // previous tile: wait until those stores have been read out)
       if (has_res && elected) {
@@ -312,14 +331,14 @@ tc_conv_gemm_staged_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
         for (int c = 0; c < 2; ++c) {
           const int buf = (res_cnt + c) & 1;
           mbar_expect_tx(res_bar(g, buf), CH_F32);
-          tma_load_2d(base + grp_off + buf * CH_F32, &tmRes, res_bar(g, buf), gc0 + c * 32, r0);
+          tma_load_2d(base + grp_off + buf * CH_F32, &tmRes, res_bar(g, buf), n0 + gc0 + c * 32, r0);
         }
       }
       // bias slice of this group's half of the tile
       bar_grp();
       {
         const int i = threadIdx.x - EPI_T0 - g * 128;
-        my_bias[i] = (n0 + gc0 + i < a.N) ? __ldg(a.bias + n0 + gc0 + i) : 0.f;
+        if (i < HALF) my_bias[i] = (n0 + gc0 + i < a.N) ? __ldg(a.bias + n0 + gc0 + i) : 0.f;
       }
       bar_grp();
 
@@ -342,8 +361,11 @@ tc_conv_gemm_staged_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
 
       if (ln) {
         // ---- pass 1: pre-norm value, partial row statistics, park the row back in TMEM
-        float sum = 0.f, sq = 0.f;
-        for (int c = 0; c < 4; ++c) {
+        // partial sums over 64-column quarters of the row, combined below in ONE fixed association order
+        // ((q0 + q1) + (q2 + q3)) whatever the tile width, so that the statistics -- and with them every output bit -- do
+        // not depend on how the launcher tiled the GEMM (batch-size invariance, tests/test_gpu_properties.py)
+        float psum[2] = {0.f, 0.f}, psq[2] = {0.f, 0.f};
+        for (int c = 0; c < NCH; ++c) {
           __syncwarp();
           tmem_ld32(t_row + c * 32, v);
           tmem_wait_ld();
@@ -365,34 +387,54 @@ tc_conv_gemm_staged_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
           for (int j = 0; j < 32; ++j) {
             float x = fmaf(__uint_as_float(v[j]), asc, my_bias[c * 32 + j]) + rr[j];
             if (!has_res) x = fmaxf(x, 0.f);
-            sum += x;
-            sq = fmaf(x, x, sq);
+            psum[c >> 1] += x;
+            psq[c >> 1] = fmaf(x, x, psq[c >> 1]);
             v[j] = __float_as_uint(x);
           }
           tmem_st32(t_row + c * 32, v);
           if (has_res) {
             bar_grp();                               // every row of this staging buffer has been read
-            if (elected && c + 2 < 4) {
+            if (elected && c + 2 < NCH) {
               const int buf = res_cnt & 1;
               mbar_expect_tx(res_bar(g, buf), CH_F32);
-              tma_load_2d(base + grp_off + buf * CH_F32, &tmRes, res_bar(g, buf), gc0 + (c + 2) * 32, r0);
+              tma_load_2d(base + grp_off + buf * CH_F32, &tmRes, res_bar(g, buf), n0 + gc0 + (c + 2) * 32, r0);
             }
             ++res_cnt;
           }
         }
         tmem_wait_st();
+        const float sum = NCH == 4 ? psum[0] + psum[1] : psum[0];
+        const float sq = NCH == 4 ? psq[0] + psq[1] : psq[0];
         // the two threads of a row (one per group) exchange their partial sums
         s_stat[(tile_par * 2 + g) * 128 + row] = make_float2(sum, sq);
         asm volatile("bar.sync %0, 64;" ::"r"(bar_pair_id) : "memory");
         const float2 other = s_stat[(tile_par * 2 + (g ^ 1)) * 128 + row];
         // add in a fixed order (group 0 first) so that both threads of the row derive bit-identical statistics
-        const float tsum = g == 0 ? sum + other.x : other.x + sum;
-        const float tsq = g == 0 ? sq + other.y : other.y + sq;
+        float tsum = g == 0 ? sum + other.x : other.x + sum;
+        float tsq = g == 0 ? sq + other.y : other.y + sq;
+        if (plan.ln_pair) {
+          // 128-wide tiles: the other half of the row lives in the peer CTA of the cluster.  Group 0 ships this CTA's
+          // partial sums into the peer's shared memory and arrives (release.cluster) on the peer's barrier; every
+          // epilogue thread then waits (acquire.cluster) for the peer's partial.  Double-buffered by tile parity.
+          const uint32_t peer = cluster_ctarank() ^ 1u;
+          if (g == 0) {
+            const uint32_t slot = base + (uint32_t)(reinterpret_cast<uint8_t*>(s_xstat + tile_par * 128 + row) - smem);
+            st_remote_f32x2(slot, peer, tsum, tsq);
+            mbar_arrive_remote_release(xfull_bar((int)tile_par), peer);
+          }
+          mbar_wait_cluster(xfull_bar((int)tile_par), (xphase >> tile_par) & 1u);
+          xphase ^= 1u << tile_par;
+          const float2 px = s_xstat[tile_par * 128 + row];
+          // fixed order (rank 0's half first) so that both CTAs derive bit-identical statistics
+          const bool first = (cluster_ctarank() == 0);
+          tsum = first ? tsum + px.x : px.x + tsum;
+          tsq = first ? tsq + px.y : px.y + tsq;
+        }
         const float mean = tsum * (1.0f / 256.0f);
         const float var = fmaxf(tsq * (1.0f / 256.0f) - mean * mean, 0.f);
         const float rstd = rsqrtf(var + 1e-5f);
         // ---- pass 2: normalise, affine, mask, stage + store
-        for (int c = 0; c < 4; ++c) {
+        for (int c = 0; c < NCH; ++c) {
           __syncwarp();
           tmem_ld32(t_row + c * 32, v);
           tmem_wait_ld();
@@ -402,19 +444,20 @@ tc_conv_gemm_staged_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
             const float x = (__uint_as_float(v[j]) - mean) * rstd * my_g[c * 32 + j] + my_b[c * 32 + j];
             y[j] = keep ? x : 0.f;
           }
-          stage_out(y, c, gc0 + c * 32, r0, a.out != nullptr, a.out_b != nullptr, false, &tmOutB0);
+          stage_out(y, c, n0 + gc0 + c * 32, r0, a.out != nullptr, a.out_b != nullptr, false, &tmOutB0);
         }
       } else if (a.epi == EPI_QKV) {
-        // n_blk 0 -> Q, 1 -> K (bf16 [R,256] tiles); 2 -> V transposed: vt[d, flat row]
-        for (int c = 0; c < 4; ++c) {
+        // columns [0,256) -> Q, [256,512) -> K (bf16 [R,256] tiles); [512,768) -> V transposed: vt[d, flat row]
+        const int part = n0 >> 8, pc0 = (n0 & 255) + gc0;      // Q / K / V and the first column inside that part
+        for (int c = 0; c < NCH; ++c) {
           __syncwarp();
           tmem_ld32(t_row + c * 32, v);
           tmem_wait_ld();
           float y[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) y[j] = in_grid ? fmaf(__uint_as_float(v[j]), asc, my_bias[c * 32 + j]) : 0.f;
-          if (n_blk < 2) {
-            stage_out(y, c, gc0 + c * 32, r0, false, true, true, n_blk == 0 ? &tmOutB0 : &tmOutB1);
+          if (part < 2) {
+            stage_out(y, c, pc0 + c * 32, r0, false, true, true, part == 0 ? &tmOutB0 : &tmOutB1);
           } else {
             uint8_t* fb = Fbuf + (c & 1) * CH_F32;
             if (elected) tma_store_wait_read_n<1>();
@@ -436,14 +479,14 @@ tc_conv_gemm_staged_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
             bar_grp();
             if (elected) {
               for (int pl = 0; pl < out_planes; ++pl)
-                tma_store_3d(&tmVt, base + (uint32_t)(fb - smem) + pl * CH_B16, r0, gc0 + c * 32, pl);
+                tma_store_3d(&tmVt, base + (uint32_t)(fb - smem) + pl * CH_B16, r0, pc0 + c * 32, pl);
               tma_store_commit();
             }
           }
         }
       } else {
         // ---- EPI_BIAS / EPI_RELU / EPI_TANH
-        for (int c = 0; c < 4; ++c) {
+        for (int c = 0; c < NCH; ++c) {
           __syncwarp();
           tmem_ld32(t_row + c * 32, v);
           tmem_wait_ld();
@@ -470,6 +513,7 @@ tc_conv_gemm_staged_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
 
   fence_before_sync();
   __syncthreads();
+  if (plan.ln_pair) cluster_sync_all();   // no remote store / arrive may target a CTA that has already exited
   if (warp == 1) {
     fence_after_sync();
     tmem_dealloc(tmem_base, TMEM_COLS);
@@ -478,8 +522,10 @@ tc_conv_gemm_staged_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
 
 // Wide plan (fp32 staging buffers) whenever the epilogue moves fp32 tiles or V^T; deep plan for the bf16-only
 // producers (FFN conv k=9, PostNet k=5, predictor conv1).  Ring depths fill what the staging leaves of the 227 KB.
-Plan plan_for(const ConvGemmArgs& a, int out_planes) {
+Plan plan_for(const ConvGemmArgs& a, int out_planes, int bn) {
   Plan p;
+  p.bn = bn;
+  p.ln_pair = (bn == 128 && (a.epi == EPI_RES_LN || a.epi == EPI_RELU_LN)) ? 1 : 0;
   p.wide = (a.epi == EPI_RES_LN || a.epi == EPI_QKV || a.out != nullptr) ? 1 : 0;
   p.serial_planes = (!p.wide && out_planes == 2) ? 1 : 0;
   p.grp_bytes = (p.wide ? 2 * CH_F32 : 0) + (p.serial_planes ? 1 : out_planes) * CH_B16;
@@ -508,6 +554,24 @@ int tc_conv_gemm_staged_launch(const ConvGemmArgs& a, cudaStream_t st) {
   const int planes = a.planes == 3 ? 3 : a.planes == 2 ? 2 : 1;
   const int out_planes = a.out_planes == 3 ? 3 : a.out_planes == 2 ? 2 : 1;
   CUtensorMap tmA, tmB, tmRes, tmOutF, tmOutB0, tmOutB1, tmVt;
+  static int num_sms = 0;
+  if (num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (num_sms <= 0) num_sms = 148;
+  }
+  // Tile width: 128 columns when that needs fewer rounds of the persistent grid than 256 (a round of 128-wide tiles costs
+  // half a round of 256-wide ones): small launches that leave SMs idle, and row counts just past a multiple of 148 tiles.
+  const uint64_t rows = a.lay.rows_hint > 0 ? (uint64_t)a.lay.rows_hint : R;
+  const int m_tiles = (int)((rows + BM - 1) / BM);
+  // Measured (profiles/r1n): N = 128 MMAs deliver ~2/3 of the N = 256 rate, so 128-wide tiles only pay where the launch
+  // is latency-bound: the 256-wide tiles would occupy at most half of the SMs (twice as many CTAs then share the same
+  // single round) and the mainloop is short.
+  const int ksteps = a.taps * ((a.K + BKE - 1) / BKE) * (planes == 3 ? 6 : planes == 2 ? 3 : 1);
+  static const char* bn_env = getenv("FS2_TILE_N");    // experiment switch: force 128 / 256
+  int BN = (m_tiles * (a.N / 256) <= num_sms / 2 && ksteps <= 64) ? 128 : 256;
+  if (bn_env) BN = atoi(bn_env) == 128 ? 128 : 256;
   if (!make_tmap_bf16_3d(&tmA, a.Ab, (uint64_t)planes, R, (uint64_t)a.K, (uint64_t)a.K, R * a.K, BM) ||
       !make_tmap_bf16(&tmB, a.Wb, (uint64_t)planes * a.taps * a.N, (uint64_t)a.K, (uint64_t)a.K, BN))
     return fs2_fail_cuda(cudaErrorInvalidValue, "cuTensorMapEncodeTiled(A/W)");
@@ -544,22 +608,23 @@ int tc_conv_gemm_staged_launch(const ConvGemmArgs& a, cudaStream_t st) {
     if (e != cudaSuccess) return fs2_fail_cuda(e, "cudaFuncSetAttribute(tc_conv_gemm_staged)");
     configured = true;
   }
-  static int num_sms = 0;
-  if (num_sms == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-    if (num_sms <= 0) num_sms = 148;
-  }
   const int num_n_blocks = a.N / BN;
-  const int tiles = (int)((R + BM - 1) / BM) * num_n_blocks;
-  const int grid = tiles < num_sms ? tiles : num_sms;
+  const int tiles = (int)((R + BM - 1) / BM) * num_n_blocks;   // upper bound (allocated rows); the kernel reads the real count
+  int grid = tiles < num_sms ? tiles : num_sms;
   ConvGemmArgs b = a;
   if (a.epi == EPI_QKV) b.out_planes = a.planes == 2 ? 2 : 1;
-  const Plan plan = plan_for(a, a.epi == EPI_QKV ? 1 : out_planes);   // Q / K / V^T are staged in the fp32 buffers
+  const Plan plan = plan_for(a, a.epi == EPI_QKV ? 1 : out_planes, BN);   // Q / K / V^T are staged in the fp32 buffers
   if (plan.total() > 227 * 1024) return fs2_fail_cuda(cudaErrorInvalidValue, "tc_conv_gemm_staged: shared-memory plan");
-  (void)FS2_LAUNCH(tc_conv_gemm_staged_kernel, grid, NUM_THREADS, plan.total(), st, tmA, tmB, tmRes, tmOutF, tmOutB0,
-                   tmOutB1, tmVt, b, num_n_blocks, plan);
+  if (plan.ln_pair) {
+    // the two column halves of a row tile run on the two CTAs of a cluster (tile = 2 * row tile + cluster rank)
+    grid &= ~1;
+    if (grid < 2) grid = 2;
+    (void)FS2_LAUNCH_CLUSTER(2, tc_conv_gemm_staged_kernel, grid, NUM_THREADS, plan.total(), st, tmA, tmB, tmRes, tmOutF,
+                             tmOutB0, tmOutB1, tmVt, b, num_n_blocks, plan);
+  } else {
+    (void)FS2_LAUNCH(tc_conv_gemm_staged_kernel, grid, NUM_THREADS, plan.total(), st, tmA, tmB, tmRes, tmOutF, tmOutB0,
+                     tmOutB1, tmVt, b, num_n_blocks, plan);
+  }
   ++g_fs2_launches;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fs2_fail_cuda(e, "tc_conv_gemm_staged_kernel launch");
