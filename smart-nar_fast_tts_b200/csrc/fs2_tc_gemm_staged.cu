@@ -570,7 +570,8 @@ int tc_conv_gemm_staged_launch(const ConvGemmArgs& a, cudaStream_t st) {
   // single round) and the mainloop is short.
   const int ksteps = a.taps * ((a.K + BKE - 1) / BKE) * (planes == 3 ? 6 : planes == 2 ? 3 : 1);
   static const char* bn_env = getenv("FS2_TILE_N");    // experiment switch: force 128 / 256
-  int BN = (m_tiles * (a.N / 256) <= num_sms / 2 && ksteps <= 64) ? 128 : 256;
+  // (5/8 rather than 1/2 of the SMs: rows_hint / R_cap over-estimate the rows in use, by up to ~1.4x for the encoder)
+  int BN = (m_tiles * (a.N / 256) <= num_sms * 5 / 8 && ksteps <= 64) ? 128 : 256;
   if (bn_env) BN = atoi(bn_env) == 128 ? 128 : 256;
   if (!make_tmap_bf16_3d(&tmA, a.Ab, (uint64_t)planes, R, (uint64_t)a.K, (uint64_t)a.K, R * a.K, BM) ||
       !make_tmap_bf16(&tmB, a.Wb, (uint64_t)planes * a.taps * a.N, (uint64_t)a.K, (uint64_t)a.K, BN))
