@@ -13,10 +13,13 @@
 //              (profiles/r1g: with a single score buffer the softmax warps spent 22 % of their time waiting for S).
 //   warps 2-5: online softmax, one thread per query row (= TMEM lane): one tcgen05.ld pass brings the row's 64 scores
 //              into registers; running max on the raw scores, p = exp2(s * scale - m * scale) as one FFMA + one EX2 per
-//              key (the key mask only touches the utterance's last block), P written as bf16 into a 128B-swizzled
-//              K-major shared tile (A operand of the PV MMA); O is rescaled in TMEM by exp2(m_old - m_new) only when a
-//              row of the warp actually raised its maximum.  The normalised output tile leaves through a swizzled
-//              staging tile + TMA store when the whole tile lies inside the utterance.
+//              key (the key mask only touches the utterance's last block).  P never touches shared memory: the thread
+//              packs its 64 probabilities as bf16x2 into 32 columns of the score buffer it has just read (tcgen05.st) and
+//              the PV MMA takes its A operand straight from TMEM -- no staging tile, no proxy fence, and because block j
+//              writes P into score buffer j & 1 the softmax of block j+1 never waits for the PV MMA of block j.  O is
+//              rescaled in TMEM by exp2(m_old - m_new) only when a row of the warp moved its reference maximum.  The
+//              normalised output tile leaves through a swizzled staging tile + TMA store when the whole tile lies
+//              inside the utterance.
 // V is consumed K-major as V^T ([d, flat row]); the QKV GEMM epilogue (fs2_tc_gemm.cu, EPI_QKV) writes it in that layout.
 // Rows follow the ragged layout of fs2_common.cuh: utterance b owns flat rows [off[b], off[b+1]).
 // Query rows >= len_b are written as zeros (masked by the caller anyway, Layers.py:43).
@@ -34,15 +37,13 @@ constexpr int BQ = 128, BKV = 64, DK = 128;
 constexpr int Q_ATOM = BQ * 128;                 // 128 query rows x 64 elements (128-byte swizzled rows)
 constexpr int K_ATOM = BKV * 128;                // 64 key rows x 64 elements
 constexpr int V_TILE = DK * 128;                 // [128 d rows x 64 keys]
-constexpr int P_TILE = BQ * 128;                 // [128 query rows x 64 keys]
 template <int NP>
 struct AttSmem {
   static constexpr int Q_OFF = 0;                               // NP planes x 2 atoms (d 0..63, 64..127)
   static constexpr int K_OFF = Q_OFF + NP * 2 * Q_ATOM;         // 2 stages x NP planes x 2 atoms
   static constexpr int V_OFF = K_OFF + 2 * NP * 2 * K_ATOM;     // 2 stages x NP planes
-  static constexpr int P_OFF = V_OFF + 2 * NP * V_TILE;         // NP planes
-  static constexpr int BAR_OFF = P_OFF + NP * P_TILE;           // 112 KB (NP = 1) / 224 KB (NP = 2)
-  static constexpr int NUM_BARS = 12;
+  static constexpr int BAR_OFF = V_OFF + 2 * NP * V_TILE;       // 96 KB (NP = 1) / 192 KB (NP = 2)
+  static constexpr int NUM_BARS = 16;   // 14 used (see the barrier table in the kernel); the TMEM slot follows them
   static constexpr int TOTAL = BAR_OFF + NUM_BARS * 8 + 16;
 };
 constexpr float P_SCALE = 2048.0f;               // f16x2: probabilities are split as fp16 terms of p * 2^11
@@ -61,14 +62,21 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                     const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmO,
                     const RowLayout lay, bf16* out_b, float scale_log2, float out_scale) {
   using L = AttSmem<NP>;
-  constexpr int Q_OFF = L::Q_OFF, K_OFF = L::K_OFF, V_OFF = L::V_OFF, P_OFF = L::P_OFF, BAR_OFF = L::BAR_OFF,
-                NUM_BARS = L::NUM_BARS;
+  constexpr int Q_OFF = L::Q_OFF, K_OFF = L::K_OFF, V_OFF = L::V_OFF, BAR_OFF = L::BAR_OFF, NUM_BARS = L::NUM_BARS;
   constexpr int NCOMBO = NP == 2 ? 3 : 1;      // (A plane, B plane): hi*lo, lo*hi, hi*hi -- smallest first
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t base = smem_u32(smem);
   const uint32_t bars = base + BAR_OFF;
+  // barrier table (8 bytes each): 0 q_full | 1-2 k_full | 3-4 k_empty | 5-6 v_full | 7-8 v_empty | 9-10 s_full |
+  // 11-12 p_ready (one per score buffer) | 13-14 o_ready (one per block parity)
   const uint32_t q_full = bars, k_full0 = bars + 8, k_empty0 = bars + 24, v_full0 = bars + 40, v_empty0 = bars + 56,
-                 s_full0 = bars + 72, p_ready = bars + 88, o_ready = bars + 96;
+                 s_full0 = bars + 72, p_ready0 = bars + 88, o_ready0 = bars + 104;
+  static_assert(NUM_BARS * 8 > 112, "barrier table overlaps the TMEM slot");
+  // mbarrier waits are by phase PARITY: a waiter must be within one phase of the barrier or the test is answered by the
+  // wrong phase (it passes early, or blocks on a later phase).  The softmax threads only need "P(j)V(j) complete" when they
+  // rescale O and at the very end, i.e. they skip phases -- hence one o_ready barrier per block parity: the MMA warp waits
+  // for P(j)V(j) before it issues S(j+2), so when a softmax thread works on block j (it has seen S(j)) every P V up to
+  // j-2 is complete and barrier (j-1) & 1 is either in the phase of block j-1 or just past it: unambiguous.
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + BAR_OFF + NUM_BARS * 8);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -101,8 +109,14 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       mbar_init(v_full0 + 8 * s, 1); mbar_init(v_empty0 + 8 * s, 1);
       mbar_init(s_full0 + 8 * s, 1);
     }
-    mbar_init(p_ready, 128);
-    mbar_init(o_ready, 1);
+    // Two p_ready barriers, one per score buffer: a softmax warp may run ONE block ahead of the slowest warp (the scores
+    // of block j+1 exist before P(j) is complete) but never two (S(j+2) is issued after P(j)V(j)), so arrivals of
+    // consecutive blocks must land on different barriers or a fast warp's second arrival would complete the phase of a
+    // block whose P is still being written.
+    mbar_init(p_ready0, 128);
+    mbar_init(p_ready0 + 8, 128);
+    mbar_init(o_ready0, 1);
+    mbar_init(o_ready0 + 8, 1);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -166,7 +180,7 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       if (nb > 1) issue_S(1);
       for (int j = 0; j < nb; ++j) {
         const int s = j & 1;
-        mbar_wait(p_ready, j & 1);     // P(j) in smem, O rescaled, score buffer j & 1 fully consumed
+        mbar_wait(p_ready0 + 8 * s, (j >> 1) & 1);     // P(j) in TMEM (score buffer j & 1), O rescaled
         mbar_wait(v_full0 + 8 * s, (j >> 1) & 1);
         fence_after_sync();
 #pragma unroll
@@ -174,14 +188,22 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           const int pa = NP == 2 ? CA[c] : 0, pb = NP == 2 ? CB[c] : 0;
 #pragma unroll
           for (int kk = 0; kk < BKV / 16; ++kk) {
-            const uint64_t ad = make_smem_desc_sw128(base + P_OFF + pa * P_TILE) + (uint64_t)(2 * kk);
+            // A = P from TMEM: 16 keys = 8 columns of packed 16-bit pairs; plane pa at columns [32 pa, 32 pa + 32)
+            const uint32_t at = tmem_S + (uint32_t)(s * 64 + pa * 32 + kk * 8);
             const uint64_t bd = make_smem_desc_sw128(base + V_OFF + (s * NP + pb) * V_TILE) + (uint64_t)(2 * kk);
-            umma_bf16(tmem_O, ad, bd, idesc_o, (j | c | kk) ? 1u : 0u);
+            umma_bf16_ts(tmem_O, at, bd, idesc_o, (j | c | kk) ? 1u : 0u);
           }
         }
         umma_commit(v_empty0 + 8 * s);
-        umma_commit(o_ready);
-        if (j + 2 < nb) issue_S(j + 2);   // runs under the softmax of block j + 1
+        umma_commit(o_ready0 + 8 * s);
+        if (j + 2 < nb) {
+          // S(j+2) overwrites score buffer j & 1, which P(j)V(j) is still reading as its A operand: the MMA pipeline does
+          // not order a TMEM operand read against a later accumulator write (seen as run-to-run differences), so wait for
+          // P(j)V(j) to complete first.  The softmax of block j + 1 is running meanwhile; S(j+2) still lands long before
+          // it is needed.  (The softmax threads' parity waits on o_ready rely on this ordering too, see above.)
+          mbar_wait(o_ready0 + 8 * s, (j >> 1) & 1);
+          issue_S(j + 2);
+        }
       }
     }
   } else {
@@ -189,11 +211,10 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     const int q = warp & 3;
     const int row = q * 32 + lane;
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
-    uint8_t* p_row = smem + P_OFF + row * 128;
     const int sw = row & 7;
     float m = -INFINITY, l = 0.f;
     uint32_t v0[32], v1[32];
-    // m: running maximum of the RAW scores of this row; the softmax runs in the exp2 domain, p = exp2((s - m) * scale)
+    // m: reference maximum of the RAW scores of this row; the softmax runs in the exp2 domain, p = exp2((s - m) * scale)
     for (int j = 0; j < nb; ++j) {
       const uint32_t sbuf = tmem_S + lane_off + (uint32_t)((j & 1) * 64);
       mbar_wait(s_full0 + 8 * (j & 1), (j >> 1) & 1);
@@ -210,9 +231,11 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           if (kbase + 32 + i >= len) v1[i] = 0xff800000u;
         }
       }
-      float bm = -INFINITY;
+      // block maximum: four independent chains (a single 64-deep fmax / fadd chain is pure latency with 1-2 warps per SMSP)
+      float bm4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
-      for (int i = 0; i < 32; ++i) bm = fmaxf(bm, fmaxf(__uint_as_float(v0[i]), __uint_as_float(v1[i])));
+      for (int i = 0; i < 32; ++i) bm4[i & 3] = fmaxf(bm4[i & 3], fmaxf(__uint_as_float(v0[i]), __uint_as_float(v1[i])));
+      const float bm = fmaxf(fmaxf(bm4[0], bm4[1]), fmaxf(bm4[2], bm4[3]));
       // m is the REFERENCE maximum the running sum and O are expressed against.  It only moves when a block's maximum
       // exceeds it by more than SLACK in the exp2 domain: probabilities may then reach 2^SLACK (exact in fp32, harmless
       // in bf16 / scaled fp16), and the O rescale pass -- a full TMEM round trip -- practically never runs after the first
@@ -222,42 +245,35 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       const float m_new = raise ? bm : m;
       const float alpha = raise ? fast_exp2((m - m_new) * scale_log2) : 1.0f;   // 0 on the first block
       const float neg_ms = -m_new * scale_log2;
-      if (j > 0) {                               // P buffer and O are free once P(j-1)V(j-1) has completed
-        mbar_wait(o_ready, (j - 1) & 1);
-        fence_after_sync();
-      }
-      float bsum = 0.f;
+      // probabilities -> packed 16-bit pairs, written over the scores just read: P(j) = columns [0,32) (and [32,64) for the
+      // lo plane) of score buffer j & 1; key 2c sits in the low half of column c
+      float bs4[4] = {0.f, 0.f, 0.f, 0.f};
+      uint32_t ph[32], pl[NP == 2 ? 32 : 1];
 #pragma unroll
-      for (int u = 0; u < 8; ++u) {              // 8 x 16-byte chunks = 64 bf16 probabilities
-        float pv[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int k = u * 8 + i;
-          const float t = __uint_as_float(k < 32 ? v0[k] : v1[k - 32]);
-          pv[i] = fast_exp2(fmaf(t, scale_log2, neg_ms));   // exp2(-inf) = 0 for masked keys
-          bsum += pv[i];
-        }
+      for (int i = 0; i < 32; ++i) {
+        const float t0 = __uint_as_float(i < 16 ? v0[2 * i] : v1[2 * i - 32]);
+        const float t1 = __uint_as_float(i < 16 ? v0[2 * i + 1] : v1[2 * i - 31]);
+        const float p0 = fast_exp2(fmaf(t0, scale_log2, neg_ms));   // exp2(-inf) = 0 for masked keys
+        const float p1 = fast_exp2(fmaf(t1, scale_log2, neg_ms));
+        bs4[i & 3] += p0 + p1;
         if (NP == 1) {
-          *reinterpret_cast<uint4*>(p_row + ((u ^ sw) << 4)) =
-              make_uint4(pack_bf16x2(pv[0], pv[1]), pack_bf16x2(pv[2], pv[3]), pack_bf16x2(pv[4], pv[5]), pack_bf16x2(pv[6], pv[7]));
+          ph[i] = pack_bf16x2(p0, p1);
         } else {
-          uint32_t ph[4], pl[4];
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            uint16_t h0, l0, h1, l1;
-            split2h_scaled(pv[2 * i] * P_SCALE, h0, l0);
-            split2h_scaled(pv[2 * i + 1] * P_SCALE, h1, l1);
-            ph[i] = (uint32_t)h0 | ((uint32_t)h1 << 16);
-            pl[i] = (uint32_t)l0 | ((uint32_t)l1 << 16);
-          }
-          *reinterpret_cast<uint4*>(p_row + ((u ^ sw) << 4)) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
-          *reinterpret_cast<uint4*>(p_row + P_TILE + ((u ^ sw) << 4)) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+          uint16_t h0, l0, h1, l1;
+          split2h_scaled(p0 * P_SCALE, h0, l0);
+          split2h_scaled(p1 * P_SCALE, h1, l1);
+          ph[i] = (uint32_t)h0 | ((uint32_t)h1 << 16);
+          pl[i] = (uint32_t)l0 | ((uint32_t)l1 << 16);
         }
       }
-      l = l * alpha + bsum;
+      tmem_st32(sbuf, ph);
+      if (NP == 2) tmem_st32(sbuf + 32, reinterpret_cast<uint32_t(&)[32]>(pl));
+      l = l * alpha + ((bs4[0] + bs4[1]) + (bs4[2] + bs4[3]));
       m = m_new;
-      // rescale the running output only when some row of the warp raised its maximum (warp-uniform branch)
+      // rescale the running output only when some row of the warp moved its reference maximum (warp-uniform branch)
       if (j > 0 && __any_sync(0xffffffffu, alpha != 1.0f)) {
+        mbar_wait(o_ready0 + 8 * ((j - 1) & 1), ((j - 1) >> 1) & 1);   // O is stable once P(j-1)V(j-1) has completed
+        fence_after_sync();
         for (int c = 0; c < 4; ++c) {
           tmem_ld32(tmem_O + lane_off + c * 32, v0);
           tmem_wait_ld();
@@ -265,14 +281,13 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           for (int i = 0; i < 32; ++i) v0[i] = __float_as_uint(__uint_as_float(v0[i]) * alpha);
           tmem_st32(tmem_O + lane_off + c * 32, v0);
         }
-        tmem_wait_st();
       }
-      fence_proxy_async();   // P tile (generic-proxy stores) -> visible to the tensor core's async proxy
+      tmem_wait_st();        // P (and a rescaled O) are in TMEM before the MMA warp is released
       fence_before_sync();
-      mbar_arrive(p_ready);
+      mbar_arrive(p_ready0 + 8 * (j & 1));
     }
     // final: O / l -> bf16
-    mbar_wait(o_ready, (nb - 1) & 1);
+    mbar_wait(o_ready0 + 8 * ((nb - 1) & 1), ((nb - 1) >> 1) & 1);   // the last block's P V
     fence_after_sync();
     const int p = p0 + row;
     const bool valid = p < len;
