@@ -296,13 +296,15 @@ def run_b200_arm(args):
         k_flops = FLOP_FFN_W1 * frames_local                     # algorithmic: valid frames only
         achieved = k_flops / (k_ms * 1e-3) / 1e12 if k_ms > 0 else 0.0
         total_prof = sum(v["ms"] for v in prof.values()) or 1.0
-        traffic = None
+        traffic, dec_layer_bytes = None, None
         tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
         if os.path.exists(tp):
             try:
-                traffic = json.load(open(tp)).get(args.workload, {}).get("dec.ffn_w1_bytes_per_launch")
+                rec = json.load(open(tp)).get(args.workload, {})
+                traffic = rec.get("dec.ffn_w1_bytes_per_launch")
+                dec_layer_bytes = rec.get("decoder_layer_bytes")
             except Exception:
-                traffic = None
+                traffic, dec_layer_bytes = None, None
         dec_ms = sum(v["ms"] for n, v in prof.items() if n.startswith("dec.")) / steps
         dec_flops = sum(t * (FLOP_DEC_FRAME + 4096 * t) for t in mel_lens_local)
         line = {
@@ -328,8 +330,16 @@ def run_b200_arm(args):
                          "share_of_step": k["ms"] / total_prof,
                          "algorithmic_flops_per_launch": k_flops,
                          "how": "fs2_profile_* CUDA events on the launching stream, separate traced pass of the same steps"},
+            # BASELINE.json's second figure, "decoder HBM GB/s vs peak": algorithmic bytes of the 4 decoder FFT blocks
+            # (16 KB per valid frame = 4 layers x 2 sub-layers x (1 KB in + 1 KB out) fp32, + 47.2 MB of
+            # weights read once) over their measured time; "measured" = DRAM bytes of one layer's five kernels from the
+            # committed ncu captures (profiles/roofline_traffic.json) x 4 layers, when present
             "decoder": {"ms_per_step": dec_ms, "tflops": dec_flops / (dec_ms * 1e-3) / 1e12 if dec_ms > 0 else 0.0,
-                        "frac_of_bf16_peak": (dec_flops / (dec_ms * 1e-3) / 1e12 / peaks["bf16_tflops"]) if dec_ms > 0 else 0.0},
+                        "frac_of_bf16_peak": (dec_flops / (dec_ms * 1e-3) / 1e12 / peaks["bf16_tflops"]) if dec_ms > 0 else 0.0,
+                        "hbm_gbs_algorithmic": ((16384.0 * frames_local + 47.2e6) / (dec_ms * 1e-3) / 1e9) if dec_ms > 0 else 0.0,
+                        "hbm_gbs_measured": (dec_layer_bytes * 4 / (dec_ms * 1e-3) / 1e9) if (dec_ms > 0 and dec_layer_bytes) else None,
+                        "hbm_peak_gbs": peaks["hbm_gbs"],
+                        "note": "the decoder is tensor-pipe bound: low HBM utilisation is the healthy state"},
             "kernel_ms_per_step": {n: round(v["ms"] / steps, 5) for n, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])},
             "clocks": clk.result,
         }

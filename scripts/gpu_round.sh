@@ -17,9 +17,14 @@ for wl in c2 c3; do
 done
 # staged-GEMM launches per forward: 17 (encoder + duration conv1) + 2 (pitch / energy conv1) + 16 (decoder) + 4 (PostNet)
 # = 39; third forward, decoder layer 0: qkv = 78 + 19, fc_ln + 1, ffn_w1 + 2, ffn_w2_ln + 3
-bash scripts/ncu_capture.sh $TAG c2 tc_conv_gemm_staged 99 ffn_w1
-bash scripts/ncu_capture.sh $TAG c3 tc_conv_gemm_staged 99 ffn_w1
-bash scripts/ncu_capture.sh $TAG c3 tc_conv_gemm_staged 98 fc_ln
-bash scripts/ncu_capture.sh $TAG c3 tc_attention 9 attn
+for wl in c2 c3; do
+  bash scripts/ncu_capture.sh $TAG $wl tc_conv_gemm_staged 97 qkv
+  bash scripts/ncu_capture.sh $TAG $wl tc_conv_gemm_staged 98 fc_ln
+  bash scripts/ncu_capture.sh $TAG $wl tc_conv_gemm_staged 99 ffn_w1
+  bash scripts/ncu_capture.sh $TAG $wl tc_conv_gemm_staged 100 w2_ln
+  # attention launches per forward: 4 encoder (f16x2) + 4 decoder (bf16); third forward, first decoder layer
+  bash scripts/ncu_capture.sh $TAG $wl tc_attention 20 attn
+done
+bash scripts/ncu_capture.sh $TAG c3 tc_attention 16 attn_enc_f16x2
 cat gpurun_out/summary.txt
 cat gpurun_out/bench_c2_${TAG}.json

@@ -30,6 +30,7 @@ KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
 
 out = [f"# ncu summaries, tag {tag}\n"]
 traffic = {}
+layer = {}
 for path in sorted(glob.glob(os.path.join(GO, f"launches_*_{tag}.csv"))):
     rows = [r for r in csv.reader(open(path)) if len(r) > 10]
     if not rows:
@@ -71,6 +72,9 @@ for path in sorted(glob.glob(os.path.join(GO, f"prof_*_{tag}.ncu-rep"))):
                 return float(v.replace(",", "")) * m.get(u, 1)
             tr = tobytes(*d["dram__bytes_read.sum"]) + tobytes(*d["dram__bytes_write.sum"])
             out.append(f"| dram traffic (read+write) | {tr / 1e6:.1f} | MB per launch |")
+            m3 = re.match(r"prof_(qkv|attn|fc_ln|ffn_w1|w2_ln)_(c\d)_", os.path.basename(path))
+            if m3:   # one decoder layer = these five kernels
+                layer.setdefault(m3.group(2), {})[m3.group(1)] = (int(tr), float(d["gpu__time_duration.sum"][0]))
             m2 = re.match(r"prof_ffn_w1_(c\d)_", os.path.basename(path))
             if m2:   # bench.py's roofline.traffic reads this (dominant kernel: decoder FFN conv k=9 GEMM)
                 traffic[m2.group(1)] = {"dec.ffn_w1_bytes_per_launch": int(tr), "source": os.path.basename(path),
@@ -81,10 +85,21 @@ for path in sorted(glob.glob(os.path.join(GO, f"bench_*_{tag}.json"))):
     except Exception:
         continue
     out.append(f"\n## bench line {os.path.basename(path)}\n\n```json\n{json.dumps(d, indent=1)}\n```")
+for wl, parts in layer.items():
+    if len(parts) == 5:
+        traffic.setdefault(wl, {})["decoder_layer_bytes"] = sum(v[0] for v in parts.values())
+        traffic[wl]["decoder_layer_us_under_ncu"] = round(sum(v[1] for v in parts.values()), 1)
+        out.append(f"\n## decoder layer at {wl} (qkv + attention + fc_ln + ffn_w1 + ffn_w2_ln, one capture each)\n")
+        out.append("| kernel | DRAM MB | us (ncu, cold) | GB/s |\n|---|---|---|---|")
+        for k, (by, us) in parts.items():
+            out.append(f"| {k} | {by / 1e6:.1f} | {us:.1f} | {by / us / 1e3:.0f} |")
+        tb, tu = sum(v[0] for v in parts.values()), sum(v[1] for v in parts.values())
+        out.append(f"| layer | {tb / 1e6:.1f} | {tu:.1f} | {tb / tu / 1e3:.0f} |")
 if traffic:
     tp = os.path.join(PR, "roofline_traffic.json")
     old = json.load(open(tp)) if os.path.exists(tp) else {}
-    old.update(traffic)
+    for k, v in traffic.items():
+        old.setdefault(k, {}).update(v)
     json.dump(old, open(tp, "w"), indent=1)
     print("wrote", tp, traffic)
 open(os.path.join(PR, f"{tag}_summary.md"), "w").write("\n".join(out) + "\n")
