@@ -475,7 +475,7 @@ int run_predictor(fs2_handle* h, PredW& P, int prec, const float* x, const bf16*
     WS(bf16, t, "pred.h1b", (size_t)planes_of(prec) * R * C);
     p1b = t;
   }
-  HCHECK(cudaMemsetAsync(out_user, 0, sizeof(float) * (size_t)lay.B * lay.S, st));
+  HCHECK(rowops_fill_zero(out_user, sizeof(float) * (size_t)lay.B * lay.S, st));
   ConvGemmArgs a = base_args(P.c1, lay);
   a.A = x; a.Ab = xb; a.epi = EPI_RELU_LN; a.mask_mode = MASK_GRID; a.ln_g = P.ln1_g; a.ln_b = P.ln1_b;
   a.out = prec == FS2_PREC_FP32 ? p1 : nullptr; a.ldo = C; a.out_b = p1b; a.ldob = C;
@@ -635,6 +635,8 @@ int fs2_set_row_packing(fs2_handle* h, int32_t keep_rows) {
 }
 
 int fs2_load_weights(fs2_handle* h, const fs2_weight_desc* descs, int32_t n) {
+  // weight repacking interleaves cudaMemcpyAsync with small kernels: no programmatic overlap here at all
+  struct PdlOff { int saved; PdlOff() : saved(g_fs2_pdl) { g_fs2_pdl = 0; } ~PdlOff() { g_fs2_pdl = saved; } } pdl_off;
   if (!h || !descs || n <= 0) return h ? h->fail(FS2_ERR_INVALID, "null/empty weight list") : FS2_ERR_INVALID;
   HCHECK(cudaSetDevice(h->device));
   cudaStream_t st = 0;
@@ -708,6 +710,7 @@ int fs2_forward_stage1(fs2_handle* h, const int64_t* texts, const int64_t* src_l
                        float p_control, float e_control, float d_control, float* log_d, float* d_rounded,
                        int64_t* mel_lens, uint8_t* src_mask, float* pitch_ph, float* energy_ph, int32_t* T_max_out,
                        void* stream) {
+  g_fs2_plain_next = 1;   // the first launch of an entry point is fully stream-ordered (fs2_common.cuh)
   if (!h) return FS2_ERR_INVALID;
   if (!h->loaded) return h->fail(FS2_ERR_STATE, "fs2_load_weights has not succeeded on this handle");
   if (!texts || !src_lens || !log_d || !d_rounded || !mel_lens || !T_max_out || B <= 0 || L <= 0)
@@ -764,7 +767,7 @@ int fs2_forward_stage1(fs2_handle* h, const int64_t* texts, const int64_t* src_l
   {
     PROF("rows.round_scan");
     HCHECK(rowops_round_durations(log_d, (int64_t)B * L, d_control, d_rounded, st));
-    HCHECK(cudaMemsetAsync(tmax_dev, 0, 2 * sizeof(int), st));
+    HCHECK(rowops_fill_zero(tmax_dev, 2 * sizeof(int), st));
     HCHECK(rowops_duration_scan(d_rounded, B, L, cum, mel_lens, mlens32, tmax_dev, st));
   }
   HCHECK(cudaMemcpyAsync(h->host_tmax, tmax_dev, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -780,6 +783,7 @@ int fs2_forward_stage1(fs2_handle* h, const int64_t* texts, const int64_t* src_l
 
 int fs2_forward_stage2(fs2_handle* h, int32_t T, float p_control, float e_control, float* mel, float* mel_post,
                        float* pitch, float* energy, uint8_t* mel_mask, void* stream) {
+  g_fs2_plain_next = 1;   // the first launch of an entry point is fully stream-ordered (fs2_common.cuh)
   if (!h) return FS2_ERR_INVALID;
   if (!h->loaded || !h->have_stage1) return h->fail(FS2_ERR_STATE, "stage2 called before a successful stage1");
   if (T < h->st_Tmax) return h->fail(FS2_ERR_INVALID, "stage2: T smaller than the stage-1 maximum mel length");
@@ -891,6 +895,7 @@ int fs2_profile_read(fs2_handle* h, fs2_profile_entry* out, int32_t max_entries,
 // ---------------------------------------------------------------------------------------------
 // stand-alone operators
 int fs2_round_durations(const float* log_d, int64_t n, float d_control, float* out, void* stream) {
+  g_fs2_plain_next = 1;   // the first launch of an entry point is fully stream-ordered (fs2_common.cuh)
   if (!log_d || !out || n < 0) { g_last_error = "null argument"; return FS2_ERR_INVALID; }
   FS2_CUDA_CHECK(rowops_round_durations(log_d, n, d_control, out, reinterpret_cast<cudaStream_t>(stream)));
   return FS2_OK;
@@ -898,11 +903,13 @@ int fs2_round_durations(const float* log_d, int64_t n, float d_control, float* o
 
 int fs2_duration_scan(const float* dd, int32_t B, int32_t L, int32_t* cum, int64_t* mel_lens, int32_t* T_max_out,
                       void* stream) {
+  g_fs2_plain_next = 1;   // the first launch of an entry point is fully stream-ordered (fs2_common.cuh)
   if (!dd || !cum || !mel_lens || !T_max_out || B <= 0 || L <= 0) { g_last_error = "bad argument"; return FS2_ERR_INVALID; }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   int* tmax = nullptr;
   FS2_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&tmax), 2 * sizeof(int)));   // [0] max, [1] batch total
   cudaError_t e = cudaMemsetAsync(tmax, 0, 2 * sizeof(int), st);
+  g_fs2_plain_next = 1;
   if (e == cudaSuccess) e = rowops_duration_scan(dd, B, L, cum, mel_lens, nullptr, tmax, st);
   int host = 0;
   if (e == cudaSuccess) e = cudaMemcpyAsync(&host, tmax, sizeof(int), cudaMemcpyDeviceToHost, st);
@@ -915,6 +922,7 @@ int fs2_duration_scan(const float* dd, int32_t B, int32_t L, int32_t* cum, int64
 
 int fs2_length_regulate(const float* x, const int32_t* cum, int32_t B, int32_t L, int32_t D, int32_t T, float* out,
                         void* stream) {
+  g_fs2_plain_next = 1;   // the first launch of an entry point is fully stream-ordered (fs2_common.cuh)
   if (!x || !cum || !out || B <= 0 || L <= 0 || D <= 0 || D % 4 || T < 0 || B > 65535 || T > FS2_MAX_ROWS_PER_UTT) {
     g_last_error = "bad argument"; return FS2_ERR_INVALID; }
   if (T == 0) return FS2_OK;
@@ -930,6 +938,7 @@ int fs2_length_regulate(const float* x, const int32_t* cum, int32_t B, int32_t L
 
 int fs2_gaussian_upsample(const float* x, const float* dd, int32_t B, int32_t L, int32_t D, int32_t T, int32_t T_w,
                           float* out, float* s, float* w, void* stream) {
+  g_fs2_plain_next = 1;   // the first launch of an entry point is fully stream-ordered (fs2_common.cuh)
   if (!x || !dd || !out || B <= 0 || L <= 0 || D <= 0 || D % 4 || T < 0 || T_w < 0 || T_w > T) {
     g_last_error = "bad argument"; return FS2_ERR_INVALID; }
   FS2_CUDA_CHECK(rowops_gaussian_upsample(x, dd, B, L, D, T, T_w, out, s, w, reinterpret_cast<cudaStream_t>(stream)));
@@ -937,6 +946,7 @@ int fs2_gaussian_upsample(const float* x, const float* dd, int32_t B, int32_t L,
 }
 
 int fs2_mask_from_lengths(const int64_t* lens, int32_t B, int32_t max_len, uint8_t* mask, void* stream) {
+  g_fs2_plain_next = 1;   // the first launch of an entry point is fully stream-ordered (fs2_common.cuh)
   if (!lens || !mask || B <= 0 || max_len < 0) { g_last_error = "bad argument"; return FS2_ERR_INVALID; }
   FS2_CUDA_CHECK(rowops_mask(lens, nullptr, B, max_len, mask, reinterpret_cast<cudaStream_t>(stream)));
   return FS2_OK;
@@ -945,12 +955,14 @@ int fs2_mask_from_lengths(const int64_t* lens, int32_t B, int32_t max_len, uint8
 // ---------------------------------------------------------------------------------------------
 // per-operator entry points (unit parity)
 int fs2_op_sinusoid_table(fs2_handle* h, int32_t n_pos, float* out, void* stream) {
+  g_fs2_plain_next = 1;   // the first launch of an entry point is fully stream-ordered (fs2_common.cuh)
   if (!h || !out || n_pos <= 0) return FS2_ERR_INVALID;
   HCHECK(cudaSetDevice(h->device));
   return sinusoid_table_host(h, n_pos, h->dims.d_model, out, reinterpret_cast<cudaStream_t>(stream));
 }
 
 int fs2_op_embed_pe(fs2_handle* h, const int64_t* texts, int32_t B, int32_t L, float* out, void* stream) {
+  g_fs2_plain_next = 1;   // the first launch of an entry point is fully stream-ordered (fs2_common.cuh)
   if (!h || !h->loaded) return FS2_ERR_STATE;
   if (!texts || !out || B <= 0 || L <= 0) return h->fail(FS2_ERR_INVALID, "bad argument");
   HCHECK(cudaSetDevice(h->device));
@@ -966,6 +978,7 @@ int fs2_op_embed_pe(fs2_handle* h, const int64_t* texts, int32_t B, int32_t L, f
 
 int fs2_op_fft_stack(fs2_handle* h, int32_t stack, int32_t l0, int32_t l1, int32_t prec, const float* x,
                      const int64_t* lens, int32_t B, int32_t S, float* out, void* stream) {
+  g_fs2_plain_next = 1;   // the first launch of an entry point is fully stream-ordered (fs2_common.cuh)
   if (!h || !h->loaded) return FS2_ERR_STATE;
   std::vector<FftW>& Ls = stack == 0 ? h->enc : h->dec;
   if (!x || !lens || !out || B <= 0 || S <= 0 || l0 < 0 || l1 > (int)Ls.size() || l0 > l1 ||
@@ -991,6 +1004,7 @@ int fs2_op_fft_stack(fs2_handle* h, int32_t stack, int32_t l0, int32_t l1, int32
 
 int fs2_op_variance_predictor(fs2_handle* h, int32_t which, const float* x, const int64_t* lens, int32_t B, int32_t S,
                               float* out, void* stream) {
+  g_fs2_plain_next = 1;   // the first launch of an entry point is fully stream-ordered (fs2_common.cuh)
   if (!h || !h->loaded) return FS2_ERR_STATE;
   if (!x || !lens || !out || B <= 0 || S <= 0 || which < 0 || which > 2) return h->fail(FS2_ERR_INVALID, "bad argument");
   HCHECK(cudaSetDevice(h->device));
@@ -1011,6 +1025,7 @@ int fs2_op_variance_predictor(fs2_handle* h, int32_t which, const float* x, cons
 
 int fs2_op_variance_embed(fs2_handle* h, int32_t which, float* pred, float control, float* x, int32_t B, int32_t S,
                           int32_t* idx_out, void* stream) {
+  g_fs2_plain_next = 1;   // the first launch of an entry point is fully stream-ordered (fs2_common.cuh)
   if (!h || !h->loaded) return FS2_ERR_STATE;
   if (!pred || !x || B <= 0 || S <= 0 || (which != 1 && which != 2)) return h->fail(FS2_ERR_INVALID, "bad argument");
   HCHECK(cudaSetDevice(h->device));
@@ -1026,6 +1041,7 @@ int fs2_op_variance_embed(fs2_handle* h, int32_t which, float* pred, float contr
 
 int fs2_op_mel_postnet(fs2_handle* h, int32_t prec, const float* dec, int32_t B, int32_t T, float* mel, float* mel_post,
                        void* stream) {
+  g_fs2_plain_next = 1;   // the first launch of an entry point is fully stream-ordered (fs2_common.cuh)
   if (!h || !h->loaded) return FS2_ERR_STATE;
   if (!dec || !mel || !mel_post || B <= 0 || T <= 0 || prec < FS2_PREC_FP32 || prec > FS2_PREC_F16X2)
     return h->fail(FS2_ERR_INVALID, "bad argument");
@@ -1045,6 +1061,7 @@ int fs2_op_mel_postnet(fs2_handle* h, int32_t prec, const float* dec, int32_t B,
 
 int fs2_op_conv_gemm(int32_t prec, const float* A, const float* W, const float* bias, int32_t B, int32_t S, int32_t K,
                      int32_t N, int32_t taps, int32_t act, float* out, void* stream) {
+  g_fs2_plain_next = 1;   // the first launch of an entry point is fully stream-ordered (fs2_common.cuh)
   if (!A || !W || !bias || !out || B <= 0 || S <= 0 || K <= 0 || N <= 0 || taps < 1 || taps > 2 * FS2_HALO + 1 ||
       taps % 2 == 0 || K % 16 || N % 4 || act < 0 || act > 2 || prec < FS2_PREC_FP32 || prec > FS2_PREC_F16X2 ||
       B > 65535 || S > FS2_MAX_ROWS_PER_UTT) {
@@ -1086,6 +1103,7 @@ int fs2_op_conv_gemm(int32_t prec, const float* A, const float* W, const float* 
 
 int fs2_op_attention(int32_t prec, const float* q, const float* k, const float* v, const int64_t* lens, int32_t B,
                      int32_t S, int32_t H, int32_t dk, float* out, void* stream) {
+  g_fs2_plain_next = 1;   // the first launch of an entry point is fully stream-ordered (fs2_common.cuh)
   if (!q || !k || !v || !lens || !out || B <= 0 || S <= 0 || H <= 0 || (dk != 64 && dk != 128) || B > 65535 ||
       S > FS2_MAX_ROWS_PER_UTT) {
     g_last_error = "bad argument"; return FS2_ERR_INVALID; }
@@ -1105,6 +1123,7 @@ int fs2_op_attention(int32_t prec, const float* q, const float* k, const float* 
     const int Rv = (tl.lay.R_cap + 7) & ~7;
     if ((e = cudaMalloc(reinterpret_cast<void**>(&og), sizeof(float) * R * D)) != cudaSuccess) break;
     if ((e = cudaMemsetAsync(og, 0, sizeof(float) * R * D, st)) != cudaSuccess) break;
+    g_fs2_plain_next = 1;
     if (prec == FS2_PREC_FP32) {
       if ((e = cudaMalloc(reinterpret_cast<void**>(&qkv), sizeof(float) * R * 3 * D)) != cudaSuccess) break;
       if ((e = rowops_to_grid(q, tl.lay, D, qkv, 3 * D, 0, nullptr, st)) != cudaSuccess) break;
@@ -1120,6 +1139,7 @@ int fs2_op_attention(int32_t prec, const float* q, const float* k, const float* 
       if ((e = cudaMalloc(reinterpret_cast<void**>(&vtb), sizeof(bf16) * np * (size_t)D * Rv)) != cudaSuccess) break;
       if ((e = cudaMalloc(reinterpret_cast<void**>(&ob), sizeof(bf16) * np * R * D)) != cudaSuccess) break;
       if ((e = cudaMemsetAsync(ob, 0, sizeof(bf16) * np * R * D, st)) != cudaSuccess) break;
+      g_fs2_plain_next = 1;
       if (np == 1) {
         if ((e = rowops_to_grid(q, tl.lay, D, nullptr, 0, 0, qb, st)) != cudaSuccess) break;
         if ((e = rowops_to_grid(k, tl.lay, D, nullptr, 0, 0, kb, st)) != cudaSuccess) break;

@@ -260,6 +260,10 @@ __device__ __forceinline__ void griddep_launch_dependents() { asm volatile("grid
 #define FS2_PDL_PROLOGUE() do { griddep_launch_dependents(); griddep_wait(); } while (0)
 
 extern int g_fs2_pdl;  // 1: launch with the programmatic-stream-serialization attribute (default; FS2_NO_PDL=1 clears it)
+// 1: the next launch is issued WITHOUT the attribute (fully stream-ordered) and clears the flag.  Set at every C-ABI entry
+// point and after every non-kernel stream operation the library enqueues: programmatic overlap is only relied upon
+// between two kernels of this library, never against a caller's memcpy / foreign kernel / memset that precedes them.
+extern int g_fs2_plain_next;
 template <typename F>
 inline cudaError_t fs2_launch_cfg(dim3 grid, dim3 block, size_t smem, cudaStream_t st, F&& f, int cluster_x = 1) {
   cudaLaunchConfig_t cfg;
@@ -267,7 +271,8 @@ inline cudaError_t fs2_launch_cfg(dim3 grid, dim3 block, size_t smem, cudaStream
   cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
   cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = g_fs2_pdl;
+  attr[0].val.programmaticStreamSerializationAllowed = (g_fs2_pdl && !g_fs2_plain_next) ? 1 : 0;
+  g_fs2_plain_next = 0;
   cfg.attrs = attr; cfg.numAttrs = 1;
   if (cluster_x > 1) {   // thread-block cluster along x
     attr[1].id = cudaLaunchAttributeClusterDimension;

@@ -10,6 +10,7 @@
 
 long long g_fs2_launches = 0;
 int g_fs2_pdl = getenv("FS2_NO_PDL") ? 0 : 1;
+int g_fs2_plain_next = 1;
 
 namespace {
 
@@ -549,6 +550,11 @@ __global__ void unsplit2_kernel(const bf16* src, int64_t n, int64_t plane_elems,
   dst[i] = (hi + lo) * (1.0f / FS2_F16X2_ACT_SCALE);
 }
 
+__global__ void fill_zero_kernel(uint32_t* p, size_t n) {
+  FS2_PDL_PROLOGUE();
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = 0u;
+}
+
 __global__ void f32_to_bf16_kernel(const float* src, int64_t n, bf16* dst) {
   FS2_PDL_PROLOGUE();
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -765,7 +771,12 @@ cudaError_t rowops_add_pe(float* x, const float* pe, const RowLayout& lay, int D
   (void)FS2_LAUNCH(add_pe_kernel, blocks_for(n, 256), 256, 0, st, x, pe, lay, D);
   return LAUNCHED();
 }
+// zero fill as a KERNEL (not cudaMemsetAsync), so that it is an ordinary link of the programmatic-dependent-launch chain
 cudaError_t rowops_fill_zero(void* p, size_t bytes, cudaStream_t st) {
   if (bytes == 0) return cudaSuccess;
-  return cudaMemsetAsync(p, 0, bytes, st);
+  if (bytes % 4 || (reinterpret_cast<uintptr_t>(p) & 3)) { g_fs2_plain_next = 1; return cudaMemsetAsync(p, 0, bytes, st); }
+  const size_t n = bytes / 4;
+  (void)FS2_LAUNCH(fill_zero_kernel, blocks_for(n, 256) < 4096 ? blocks_for(n, 256) : 4096, 256, 0, st,
+                   reinterpret_cast<uint32_t*>(p), n);
+  return LAUNCHED();
 }
