@@ -74,9 +74,9 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   static_assert(NUM_BARS * 8 > 112, "barrier table overlaps the TMEM slot");
   // mbarrier waits are by phase PARITY: a waiter must be within one phase of the barrier or the test is answered by the
   // wrong phase (it passes early, or blocks on a later phase).  The softmax threads only need "P(j)V(j) complete" when they
-  // rescale O and at the very end, i.e. they skip phases -- hence one o_ready barrier per block parity: the MMA warp waits
-  // for P(j)V(j) before it issues S(j+2), so when a softmax thread works on block j (it has seen S(j)) every P V up to
-  // j-2 is complete and barrier (j-1) & 1 is either in the phase of block j-1 or just past it: unambiguous.
+  // rescale O and at the very end, i.e. they skip phases -- hence one o_ready barrier per block parity: S(j) is issued
+  // after P(j-2)V(j-2) and MMAs complete in issue order, so when a softmax thread works on block j (it has seen S(j)) every
+  // P V up to j-2 is complete and barrier (j-1) & 1 is either in the phase of block j-1 or just past it: unambiguous.
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + BAR_OFF + NUM_BARS * 8);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -196,14 +196,11 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         }
         umma_commit(v_empty0 + 8 * s);
         umma_commit(o_ready0 + 8 * s);
-        if (j + 2 < nb) {
-          // S(j+2) overwrites score buffer j & 1, which P(j)V(j) is still reading as its A operand: the MMA pipeline does
-          // not order a TMEM operand read against a later accumulator write (seen as run-to-run differences), so wait for
-          // P(j)V(j) to complete first.  The softmax of block j + 1 is running meanwhile; S(j+2) still lands long before
-          // it is needed.  (The softmax threads' parity waits on o_ready rely on this ordering too, see above.)
-          mbar_wait(o_ready0 + 8 * s, (j >> 1) & 1);
-          issue_S(j + 2);
-        }
+        // S(j+2) overwrites score buffer j & 1, which P(j)V(j) -- issued just above -- reads as its A operand.  MMAs of one
+        // thread execute in issue order, so the write cannot overtake the read (the same aliasing CUTLASS's sm100 FMHA
+        // relies on); tests/test_gpu_properties.py checks run-to-run bit equality at batch 256.  It runs under the softmax
+        // of block j + 1.
+        if (j + 2 < nb) issue_S(j + 2);
       }
     }
   } else {
