@@ -122,6 +122,19 @@ int fs2_forward_stage1(fs2_handle* h, const int64_t* texts, const int64_t* src_l
                        int64_t* mel_lens, uint8_t* src_mask, float* pitch_ph, float* energy_ph,
                        int32_t* T_max_out, void* stream);
 
+/* Multi-GPU variant of stage 1 (same work, same outputs, NO host synchronisation): tmax_dev[2] (device int32, caller
+ * owned) receives {max_b mel_lens[b], sum_b mel_lens[b]} on `stream`.  The caller reduces tmax_dev[0] across the ranks
+ * of its utterance shards on the same stream (all-reduce MAX: the only exchange step of the path), reads the two ints
+ * back ONCE and passes them to fs2_forward_stage1_commit before fs2_forward_stage2(h, T, ...).  One synchronisation
+ * per forward instead of two. */
+int fs2_forward_stage1_async(fs2_handle* h, const int64_t* texts, const int64_t* src_lens, int32_t B, int32_t L,
+                             float p_control, float e_control, float d_control, float* log_d, float* d_rounded,
+                             int64_t* mel_lens, uint8_t* src_mask, float* pitch_ph, float* energy_ph,
+                             int32_t* tmax_dev, void* stream);
+/* T_max: the (possibly batch-global) maximum mel length stage 2 will be called with; frames: this rank's sum of
+ * mel_lens (sizes tile-shape decisions only; 0 = unknown). */
+int fs2_forward_stage1_commit(fs2_handle* h, int32_t T_max, int32_t frames);
+
 /* replaces: LengthRegulator expand/pad (modules.py:220-226, utils/tools.py:288-306),
  * frame-level pitch/energy (modules.py:137-149), MelDecoder (Models.py:212-244),
  * mel_linear + PostNet + residual (fastspeech2_align.py:82-85).

@@ -706,14 +706,17 @@ int fs2_load_weights(fs2_handle* h, const fs2_weight_desc* descs, int32_t n) {
 }
 
 // ---------------------------------------------------------------------------------------------
-int fs2_forward_stage1(fs2_handle* h, const int64_t* texts, const int64_t* src_lens, int32_t B, int32_t L,
-                       float p_control, float e_control, float d_control, float* log_d, float* d_rounded,
-                       int64_t* mel_lens, uint8_t* src_mask, float* pitch_ph, float* energy_ph, int32_t* T_max_out,
-                       void* stream) {
+}  // extern "C"
+
+// stage 1 up to and including the duration scan; leaves {max mel_len, sum mel_lens} in the workspace int pair *tmax_out
+static int stage1_enqueue(fs2_handle* h, const int64_t* texts, const int64_t* src_lens, int32_t B, int32_t L,
+                          float p_control, float e_control, float d_control, float* log_d, float* d_rounded,
+                          int64_t* mel_lens, uint8_t* src_mask, float* pitch_ph, float* energy_ph, int** tmax_out,
+                          void* stream) {
   g_fs2_plain_next = 1;   // the first launch of an entry point is fully stream-ordered (fs2_common.cuh)
   if (!h) return FS2_ERR_INVALID;
   if (!h->loaded) return h->fail(FS2_ERR_STATE, "fs2_load_weights has not succeeded on this handle");
-  if (!texts || !src_lens || !log_d || !d_rounded || !mel_lens || !T_max_out || B <= 0 || L <= 0)
+  if (!texts || !src_lens || !log_d || !d_rounded || !mel_lens || B <= 0 || L <= 0)
     return h->fail(FS2_ERR_INVALID, "stage1: null pointer or empty batch");
   if (L > 8192) return h->fail(FS2_ERR_UNSUPPORTED, "stage1: L > 8192");
   const fs2_dims& d = h->dims;
@@ -770,14 +773,54 @@ int fs2_forward_stage1(fs2_handle* h, const int64_t* texts, const int64_t* src_l
     HCHECK(rowops_fill_zero(tmax_dev, 2 * sizeof(int), st));
     HCHECK(rowops_duration_scan(d_rounded, B, L, cum, mel_lens, mlens32, tmax_dev, st));
   }
-  HCHECK(cudaMemcpyAsync(h->host_tmax, tmax_dev, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
-  HCHECK(cudaStreamSynchronize(st));  // the one data-dependent size of the path
-  *T_max_out = *h->host_tmax;
-  h->have_stage1 = true;
-  h->st_B = B; h->st_L = L; h->st_Tmax = h->host_tmax[0];
-  h->st_frames = h->host_tmax[1];
+  h->st_B = B; h->st_L = L;
   h->st_enc_out = x;
   h->st_lay1 = lay;
+  *tmax_out = tmax_dev;
+  return FS2_OK;
+}
+
+extern "C" {
+
+int fs2_forward_stage1(fs2_handle* h, const int64_t* texts, const int64_t* src_lens, int32_t B, int32_t L,
+                       float p_control, float e_control, float d_control, float* log_d, float* d_rounded,
+                       int64_t* mel_lens, uint8_t* src_mask, float* pitch_ph, float* energy_ph, int32_t* T_max_out,
+                       void* stream) {
+  if (h && !T_max_out) return h->fail(FS2_ERR_INVALID, "stage1: null T_max_out");
+  int* tmax_dev = nullptr;
+  RCHECK(stage1_enqueue(h, texts, src_lens, B, L, p_control, e_control, d_control, log_d, d_rounded, mel_lens, src_mask,
+                        pitch_ph, energy_ph, &tmax_dev, stream));
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  HCHECK(cudaMemcpyAsync(h->host_tmax, tmax_dev, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
+  HCHECK(cudaStreamSynchronize(st));  // the one data-dependent size of the path
+  *T_max_out = h->host_tmax[0];
+  h->have_stage1 = true;
+  h->st_Tmax = h->host_tmax[0];
+  h->st_frames = h->host_tmax[1];
+  return FS2_OK;
+}
+
+int fs2_forward_stage1_async(fs2_handle* h, const int64_t* texts, const int64_t* src_lens, int32_t B, int32_t L,
+                             float p_control, float e_control, float d_control, float* log_d, float* d_rounded,
+                             int64_t* mel_lens, uint8_t* src_mask, float* pitch_ph, float* energy_ph, int32_t* tmax_user,
+                             void* stream) {
+  if (h && !tmax_user) return h->fail(FS2_ERR_INVALID, "stage1_async: null tmax_dev");
+  int* tmax_dev = nullptr;
+  RCHECK(stage1_enqueue(h, texts, src_lens, B, L, p_control, e_control, d_control, log_d, d_rounded, mel_lens, src_mask,
+                        pitch_ph, energy_ph, &tmax_dev, stream));
+  HCHECK(cudaMemcpyAsync(tmax_user, tmax_dev, 2 * sizeof(int), cudaMemcpyDeviceToDevice, reinterpret_cast<cudaStream_t>(stream)));
+  h->st_Tmax = -1;   // unknown until fs2_forward_stage1_commit
+  return FS2_OK;
+}
+
+int fs2_forward_stage1_commit(fs2_handle* h, int32_t T_max, int32_t frames) {
+  if (!h) return FS2_ERR_INVALID;
+  if (!h->loaded || h->st_B <= 0 || h->st_Tmax != -1)
+    return h->fail(FS2_ERR_STATE, "stage1_commit without a preceding fs2_forward_stage1_async");
+  if (T_max < 0 || frames < 0) return h->fail(FS2_ERR_INVALID, "stage1_commit: negative size");
+  h->st_Tmax = T_max;
+  h->st_frames = frames;
+  h->have_stage1 = true;
   return FS2_OK;
 }
 

@@ -173,8 +173,11 @@ class FastSpeech2Align(nn.Module):
         self._cached_ws = None
         self._precision = (PREC_F16X2, PREC_BF16)
         self._keep_rows = 2
-        # multi-GPU hook (sharding.py): maps the local T_max to the batch-global one between the two stages
+        # multi-GPU hooks (sharding.py): map the local T_max to the batch-global one between the two stages.
+        # t_max_hook works on the host int (one extra synchronisation); t_max_device_hook reduces the device int32[2]
+        # tensor {T_max, frames} in place on the current stream BEFORE the forward's single read-back.
         self.t_max_hook: Optional[Callable[[int, torch.device], int]] = None
+        self.t_max_device_hook: Optional[Callable[[torch.Tensor], None]] = None
 
     # ------------------------------------------------------------------ engine plumbing
     def set_precision(self, encoder: str = "f16x2", decoder: str = "bf16") -> "FastSpeech2Align":
@@ -306,14 +309,26 @@ class FastSpeech2Align(nn.Module):
         ph_e = torch.empty(B, L, **f32) if self._dims.energy_phoneme_level else None
         t_max = C.c_int32(0)
         with torch.cuda.device(dev):
-            lib.check(lib.fs2_forward_stage1(
-                h, texts.data_ptr(), src_lens_in.data_ptr(), B, L, float(p_control), float(e_control), 1.0,
-                log_d.data_ptr(), d_rounded.data_ptr(), out_mel_lens.data_ptr(), src_masks.data_ptr(),
-                ph_p.data_ptr() if ph_p is not None else None, ph_e.data_ptr() if ph_e is not None else None,
-                C.byref(t_max), stream), h)
-            T = int(t_max.value)
-            if self.t_max_hook is not None:
-                T = int(self.t_max_hook(T, dev))
+            if self.t_max_device_hook is not None:
+                # sharded forward: stage 1 without its host sync, all-reduce(MAX) of T on the device, ONE read-back
+                tm = torch.empty(2, device=dev, dtype=torch.int32)
+                lib.check(lib.fs2_forward_stage1_async(
+                    h, texts.data_ptr(), src_lens_in.data_ptr(), B, L, float(p_control), float(e_control), 1.0,
+                    log_d.data_ptr(), d_rounded.data_ptr(), out_mel_lens.data_ptr(), src_masks.data_ptr(),
+                    ph_p.data_ptr() if ph_p is not None else None, ph_e.data_ptr() if ph_e is not None else None,
+                    tm.data_ptr(), stream), h)
+                self.t_max_device_hook(tm)
+                T, frames = (int(v) for v in tm.tolist())
+                lib.check(lib.fs2_forward_stage1_commit(h, T, frames), h)
+            else:
+                lib.check(lib.fs2_forward_stage1(
+                    h, texts.data_ptr(), src_lens_in.data_ptr(), B, L, float(p_control), float(e_control), 1.0,
+                    log_d.data_ptr(), d_rounded.data_ptr(), out_mel_lens.data_ptr(), src_masks.data_ptr(),
+                    ph_p.data_ptr() if ph_p is not None else None, ph_e.data_ptr() if ph_e is not None else None,
+                    C.byref(t_max), stream), h)
+                T = int(t_max.value)
+                if self.t_max_hook is not None:
+                    T = int(self.t_max_hook(T, dev))
             n_mel = self._dims.n_mel
             mel = torch.empty(B, T, n_mel, **f32)
             mel_post = torch.empty(B, T, n_mel, **f32)

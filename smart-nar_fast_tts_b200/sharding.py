@@ -52,12 +52,19 @@ class ShardedSynthesizer:
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         if self.world > 1:
-            model.t_max_hook = self._global_tmax
+            if hasattr(model, "t_max_device_hook") and dist.get_backend(group) == "nccl":
+                model.t_max_device_hook = self._global_tmax_device   # no extra host sync (fs2_forward_stage1_async)
+            else:
+                model.t_max_hook = self._global_tmax
 
     def _global_tmax(self, t_local: int, device: torch.device) -> int:
         t = torch.tensor([t_local], dtype=torch.int32, device=device)
         dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)   # the one exchange step of the path
         return int(t.item())
+
+    def _global_tmax_device(self, tm: torch.Tensor) -> None:
+        """tm = int32[2] {T_max, frames} on the device: all-reduce MAX of T in place, stream-ordered (NCCL)."""
+        dist.all_reduce(tm[0:1], op=dist.ReduceOp.MAX, group=self.group)
 
     def bounds(self, src_lens: torch.Tensor) -> List[Tuple[int, int]]:
         lens = src_lens.tolist()

@@ -87,6 +87,24 @@ def test_c3_shard_invariance(model, c3):
         assert torch.equal(torch.cat([halves[0][i], halves[1][i]], dim=0), out[i]), f"output {i} differs under sharding"
 
 
+def test_async_stage1_path_equals_sync_path(model, c3):
+    """fs2_forward_stage1_async + commit (the sharded forward: T reduced on the device, one read-back) against the
+    synchronous stage 1 with the same forced T."""
+    (speakers, texts, src_lens, L), out = c3
+    T = out[1].shape[1]
+
+    def dev_hook(tm):
+        tm[0:1].fill_(T)
+
+    model.t_max_device_hook = dev_hook
+    try:
+        part = run(model, speakers[:64], texts[:64], src_lens[:64], L)
+    finally:
+        model.t_max_device_hook = None
+    for i in (0, 1, 2, 3, 4, 5, 6, 7, 9):
+        assert torch.equal(part[i], out[i][:64]), f"output {i} differs on the async stage-1 path"
+
+
 def test_c3_determinism(model, c3):
     inputs, out = c3
     again = run(model, *inputs)
