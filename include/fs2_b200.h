@@ -16,8 +16,9 @@
  *  - every function returns FS2_OK (0) or a negative error code, never throws, never
  *    exits.  `fs2_last_error` gives the message for the last failure on that handle.
  *  - all work is enqueued on the `stream` argument (a cudaStream_t / CUstream passed as
- *    void*; NULL = legacy default stream).  The only blocking call is the 4-byte D2H of
- *    T_max at the end of `fs2_forward_stage1`.
+ *    void*; NULL = legacy default stream).  The only blocking call is the 8-byte D2H of
+ *    {T_max, frame count} at the end of `fs2_forward_stage1` (`fs2_forward_stage1_async` leaves even
+ *    that to the caller).
  *  - a handle is bound to one device and is not thread-safe; separate handles are
  *    independent.  The library owns packed weights and workspace; the caller owns every
  *    tensor it passes in or receives results in.
