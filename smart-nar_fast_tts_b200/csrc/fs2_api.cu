@@ -465,7 +465,7 @@ int run_fft_stack(fs2_handle* h, std::vector<FftW>& Ls, int l0, int l1, int prec
 // modules.py:278-286 with the reference's padded-grid semantics (halo leak, SURVEY.md section 8(a) note 1): the layout
 // keeps the 2 padded rows that can reach a valid output.  out_user[B,S]; rows the layout does not carry are 0 (masked).
 int run_predictor(fs2_handle* h, PredW& P, int prec, const float* x, const bf16* xb, const RowLayout& lay,
-                  float* out_user, cudaStream_t st) {
+                  float* out_user, cudaStream_t st, bool out_cleared = false) {
   const int C = h->dims.vp_filter;
   const std::string tg = &P == &h->pred[0] ? "dur." : &P == &h->pred[1] ? "pitch." : "energy.";
   const size_t R = (size_t)lay.R_cap;
@@ -475,7 +475,7 @@ int run_predictor(fs2_handle* h, PredW& P, int prec, const float* x, const bf16*
     WS(bf16, t, "pred.h1b", (size_t)planes_of(prec) * R * C);
     p1b = t;
   }
-  HCHECK(rowops_fill_zero(out_user, sizeof(float) * (size_t)lay.B * lay.S, st));
+  if (!out_cleared) HCHECK(rowops_fill_zero(out_user, sizeof(float) * (size_t)lay.B * lay.S, st));
   ConvGemmArgs a = base_args(P.c1, lay);
   a.A = x; a.Ab = xb; a.epi = EPI_RELU_LN; a.mask_mode = MASK_GRID; a.ln_g = P.ln1_g; a.ln_b = P.ln1_b;
   a.out = prec == FS2_PREC_FP32 ? p1 : nullptr; a.ldo = C; a.out_b = p1b; a.ldob = C;
@@ -731,7 +731,7 @@ static int stage1_enqueue(fs2_handle* h, const int64_t* texts, const int64_t* sr
   WS(int, cum, "s1.cum", (size_t)B * L);
   WS(int, mlens32, "s1.mel_lens32", B);
   WS(int, tmax_dev, "s1.tmax", 2);   // [0] max frames of an utterance, [1] frames of the batch
-  HCHECK(rowops_lens_to_i32(src_lens, B, L, lens32, st));
+  HCHECK(rowops_lens_to_i32(src_lens, B, L, lens32, st, tmax_dev));   // also clears the {T_max, frames} accumulators
   // packed phoneme rows: valid rows + the 2 padded rows the duration predictor's convolutions can see (+ zero halo)
   RowLayout lay;
   RCHECK(make_layout(h, "s1.lay", lens32, B, L, h->halo_keep, FS2_HALO, &lay, st));
@@ -746,13 +746,13 @@ static int stage1_enqueue(fs2_handle* h, const int64_t* texts, const int64_t* sr
   RCHECK(position_table(h, 0, L, &pe, st));
   {
     PROF("rows.embed_pe");
-    if (src_mask) HCHECK(rowops_mask(src_lens, nullptr, B, L, src_mask, st));
+    if (src_mask) HCHECK(rowops_mask(src_lens, nullptr, B, L, src_mask, st, log_d));   // + log_d cleared in the same pass
     HCHECK(rowops_embed_pe(texts, raw_ptr(h, "txt_encoder.src_word_emb.weight"), pe, d.vocab, lay, D, x, xb,
                            planes_of(h->prec_enc), nullptr, st));
   }
   RCHECK(run_fft_stack(h, h->enc, 0, d.n_enc_layers, h->prec_enc, x, xb, lay, st));
   // modules.py:116 duration predictor on the encoder output
-  RCHECK(run_predictor(h, h->pred[0], h->prec_enc, x, xb, lay, log_d, st));
+  RCHECK(run_predictor(h, h->pred[0], h->prec_enc, x, xb, lay, log_d, st, src_mask != nullptr));
   // modules.py:117-126 phoneme-level variants
   if (d.pitch_phoneme_level) {
     RCHECK(run_predictor(h, h->pred[1], h->prec_enc, x, xb, lay, pitch_ph, st));
@@ -769,9 +769,7 @@ static int stage1_enqueue(fs2_handle* h, const int64_t* texts, const int64_t* sr
   // modules.py:132-135 + LengthRegulator bookkeeping
   {
     PROF("rows.round_scan");
-    HCHECK(rowops_round_durations(log_d, (int64_t)B * L, d_control, d_rounded, st));
-    HCHECK(rowops_fill_zero(tmax_dev, 2 * sizeof(int), st));
-    HCHECK(rowops_duration_scan(d_rounded, B, L, cum, mel_lens, mlens32, tmax_dev, st));
+    HCHECK(rowops_round_scan(log_d, d_control, d_rounded, B, L, cum, mel_lens, mlens32, tmax_dev, st));
   }
   h->st_B = B; h->st_L = L;
   h->st_enc_out = x;
@@ -864,7 +862,7 @@ int fs2_forward_stage2(fs2_handle* h, int32_t T, float p_control, float e_contro
   const int first_prec = (pitch_fl || energy_fl) ? h->prec_enc : FS2_PREC_FP32;
   {
     PROF("rows.length_regulate");
-    if (mel_mask) HCHECK(rowops_mask(nullptr, mlens32, B, T, mel_mask, st));
+    if (mel_mask) HCHECK(rowops_mask(nullptr, mlens32, B, T, mel_mask, st, pitch_fl ? pitch : nullptr, energy_fl ? energy : nullptr));
     // modules.py:136 length regulator (hard): gathers encoder rows (stage-1 layout) into frame rows (stage-2 layout)
     HCHECK(rowops_length_regulate(h->st_enc_out, h->st_lay1.off, 0, cum, L, D, lay, x, xb, planes_of(first_prec), st));
   }
@@ -872,14 +870,14 @@ int fs2_forward_stage2(fs2_handle* h, int32_t T, float p_control, float e_contro
   RCHECK(position_table(h, 1, T, &pe, st));
   // modules.py:139-149 frame-level pitch then energy (energy sees x + pitch embedding)
   if (pitch_fl) {
-    RCHECK(run_predictor(h, h->pred[1], h->prec_enc, x, xb, lay, pitch, st));
+    RCHECK(run_predictor(h, h->pred[1], h->prec_enc, x, xb, lay, pitch, st, mel_mask != nullptr));
     PROF("rows.variance_embed");
     HCHECK(rowops_variance_embed(pitch, p_control, raw_ptr(h, "variance_adaptor.pitch_bins"), d.n_bins,
                                  raw_ptr(h, "variance_adaptor.pitch_embedding.weight"), energy_fl ? nullptr : pe, x, xb,
                                  planes_of(energy_fl ? h->prec_enc : h->prec_dec), lay, D, nullptr, st));
   }
   if (energy_fl) {
-    RCHECK(run_predictor(h, h->pred[2], h->prec_enc, x, xb, lay, energy, st));
+    RCHECK(run_predictor(h, h->pred[2], h->prec_enc, x, xb, lay, energy, st, mel_mask != nullptr));
     // fused: + energy embedding, + decoder positional encoding (Models.py:231-233), shadow for the decoder
     PROF("rows.variance_embed");
     HCHECK(rowops_variance_embed(energy, e_control, raw_ptr(h, "variance_adaptor.energy_bins"), d.n_bins,

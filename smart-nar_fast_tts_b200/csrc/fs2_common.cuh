@@ -203,11 +203,17 @@ cudaError_t rowops_build_layout(const int* lens32, int B, int S, int halo_keep, 
                                 unsigned* rowmap, int R_cap, cudaStream_t st, int extra_ext = 0);
 cudaError_t rowops_embed_pe(const int64_t* texts, const float* emb, const float* pe, int vocab, const RowLayout& lay,
                             int D, float* out_grid, bf16* out_b, int out_planes, float* out_user, cudaStream_t st);
-cudaError_t rowops_lens_to_i32(const int64_t* lens, int B, int cap, int* out, cudaStream_t st);
-cudaError_t rowops_mask(const int64_t* lens64, const int* lens32, int B, int max_len, uint8_t* mask, cudaStream_t st);
+// zero2 (optional): two ints cleared by the same launch (the forward's {T_max, frames} accumulators)
+cudaError_t rowops_lens_to_i32(const int64_t* lens, int B, int cap, int* out, cudaStream_t st, int* zero2 = nullptr);
+// zero0 / zero1 (optional): fp32 tensors of the mask's shape cleared by the same launch
+cudaError_t rowops_mask(const int64_t* lens64, const int* lens32, int B, int max_len, uint8_t* mask, cudaStream_t st,
+                        float* zero0 = nullptr, float* zero1 = nullptr);
 cudaError_t rowops_round_durations(const float* log_d, int64_t n, float d_control, float* out, cudaStream_t st);
 cudaError_t rowops_duration_scan(const float* d, int B, int L, int* cum, int64_t* mel_lens, int* mel_lens32,
                                  int* tmax_dev, cudaStream_t st);
+// fused: d_rounded = clamp(round(exp(log_d) - 1) * d_control, 0) (modules.py:132-135), then the scan of d_rounded
+cudaError_t rowops_round_scan(const float* log_d, float d_control, float* d_rounded, int B, int L, int* cum,
+                              int64_t* mel_lens, int* mel_lens32, int* tmax_dev, cudaStream_t st);
 // x rows of utterance b start at src_off[b] (device) or b*src_stride when src_off is null; out rows follow `lay`
 cudaError_t rowops_length_regulate(const float* x, const int* src_off, int src_stride, const int* cum, int L, int D,
                                    const RowLayout& lay, float* out, bf16* out_b, int out_planes, cudaStream_t st);

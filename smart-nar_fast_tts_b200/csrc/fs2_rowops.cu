@@ -149,9 +149,10 @@ __global__ void embed_pe_kernel(const int64_t* texts, const float* emb,
   }
 }
 
-__global__ void lens_to_i32_kernel(const int64_t* lens, int B, int cap, int* out) {
+__global__ void lens_to_i32_kernel(const int64_t* lens, int B, int cap, int* out, int* zero2) {
   FS2_PDL_PROLOGUE();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 0 && zero2) { zero2[0] = 0; zero2[1] = 0; }   // the {T_max, frames} accumulators of this forward
   if (i < B) {
     long long v = lens[i];
     out[i] = (int)(v < 0 ? 0 : (v > cap ? cap : v));
@@ -159,14 +160,18 @@ __global__ void lens_to_i32_kernel(const int64_t* lens, int B, int cap, int* out
 }
 
 // utils/tools.py:89-97  mask[b,i] = i >= lens[b]
+// zero0 / zero1 (optional, same [B, max_len] shape, fp32): cleared in the same pass -- the variance predictors only write
+// the rows their packed layout carries (modules.py:285 masked_fill(mask, 0) for the rest)
 __global__ void mask_kernel(const int64_t* lens64, const int* lens32, int B, int max_len,
-                            uint8_t* mask) {
+                            uint8_t* mask, float* zero0, float* zero1) {
   FS2_PDL_PROLOGUE();
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (size_t)B * max_len) return;
   const int b = (int)(i / max_len), p = (int)(i - (size_t)b * max_len);
   const long long len = lens64 ? lens64[b] : (long long)lens32[b];
   mask[i] = (uint8_t)(p >= len);
+  if (zero0) zero0[i] = 0.f;
+  if (zero1) zero1[i] = 0.f;
 }
 
 // model/modules.py:132-135  clamp(round(exp(log_d) - 1) * d_control, min=0); torch.round = half-to-even = rintf
@@ -182,7 +187,9 @@ __global__ void round_durations_kernel(const float* log_d, int64_t n, float d_co
 
 // model/modules.py:206-222 bookkeeping: expand_size = max(int(d), 0); mel_len = sum.  One CTA per utterance,
 // block-wide inclusive scan (warp shuffles + one smem hop), chunks of 1024 phonemes.
-__global__ void __launch_bounds__(1024) duration_scan_kernel(const float* d, int L, int* cum,
+// log_d != null: the kernel first applies modules.py:132-135 (rounding) to log_d and writes d (fused forward path);
+// log_d == null: d is an input (stand-alone operator).
+__global__ void __launch_bounds__(1024) duration_scan_kernel(const float* log_d, float d_control, float* d, int L, int* cum,
                                                              int64_t* mel_lens,
                                                              int* mel_lens32, int* tmax) {
   FS2_PDL_PROLOGUE();
@@ -195,7 +202,13 @@ __global__ void __launch_bounds__(1024) duration_scan_kernel(const float* d, int
     const int i = base + tid;
     int v = 0;
     if (i < L) {
-      const float f = d[(size_t)b * L + i];
+      float f;
+      if (log_d) {
+        f = round_duration(log_d[(size_t)b * L + i], d_control);
+        d[(size_t)b * L + i] = f;
+      } else {
+        f = d[(size_t)b * L + i];
+      }
       // int() truncates toward zero; guard the conversion against inf/NaN/huge values
       v = (f > 0.f) ? (f < 1.0e6f ? (int)f : 1000000) : 0;
     }
@@ -615,14 +628,15 @@ cudaError_t rowops_embed_pe(const int64_t* texts, const float* emb, const float*
                                                                    out_planes, out_user);
   return LAUNCHED();
 }
-cudaError_t rowops_lens_to_i32(const int64_t* lens, int B, int cap, int* out, cudaStream_t st) {
+cudaError_t rowops_lens_to_i32(const int64_t* lens, int B, int cap, int* out, cudaStream_t st, int* zero2) {
   if (B <= 0) return cudaSuccess;
-  (void)FS2_LAUNCH(lens_to_i32_kernel, blocks_for(B, 256), 256, 0, st, lens, B, cap, out);
+  (void)FS2_LAUNCH(lens_to_i32_kernel, blocks_for(B, 256), 256, 0, st, lens, B, cap, out, zero2);
   return LAUNCHED();
 }
-cudaError_t rowops_mask(const int64_t* lens64, const int* lens32, int B, int max_len, uint8_t* mask, cudaStream_t st) {
+cudaError_t rowops_mask(const int64_t* lens64, const int* lens32, int B, int max_len, uint8_t* mask, cudaStream_t st,
+                        float* zero0, float* zero1) {
   if ((size_t)B * max_len == 0) return cudaSuccess;
-  (void)FS2_LAUNCH(mask_kernel, blocks_for((size_t)B * max_len, 256), 256, 0, st, lens64, lens32, B, max_len, mask);
+  (void)FS2_LAUNCH(mask_kernel, blocks_for((size_t)B * max_len, 256), 256, 0, st, lens64, lens32, B, max_len, mask, zero0, zero1);
   return LAUNCHED();
 }
 cudaError_t rowops_round_durations(const float* log_d, int64_t n, float d_control, float* out, cudaStream_t st) {
@@ -633,7 +647,14 @@ cudaError_t rowops_round_durations(const float* log_d, int64_t n, float d_contro
 cudaError_t rowops_duration_scan(const float* d, int B, int L, int* cum, int64_t* mel_lens, int* mel_lens32,
                                  int* tmax_dev, cudaStream_t st) {
   if (B <= 0) return cudaSuccess;
-  (void)FS2_LAUNCH(duration_scan_kernel, B, 1024, 0, st, d, L, cum, mel_lens, mel_lens32, tmax_dev);
+  (void)FS2_LAUNCH(duration_scan_kernel, B, 1024, 0, st, (const float*)nullptr, 1.0f, const_cast<float*>(d), L, cum, mel_lens,
+                   mel_lens32, tmax_dev);
+  return LAUNCHED();
+}
+cudaError_t rowops_round_scan(const float* log_d, float d_control, float* d_rounded, int B, int L, int* cum,
+                              int64_t* mel_lens, int* mel_lens32, int* tmax_dev, cudaStream_t st) {
+  if (B <= 0) return cudaSuccess;
+  (void)FS2_LAUNCH(duration_scan_kernel, B, 1024, 0, st, log_d, d_control, d_rounded, L, cum, mel_lens, mel_lens32, tmax_dev);
   return LAUNCHED();
 }
 cudaError_t rowops_length_regulate(const float* x, const int* src_off, int src_stride, const int* cum, int L, int D,
