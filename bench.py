@@ -115,7 +115,7 @@ def make_batch(workload: str, n_shards: int):
 
 
 # --------------------------------------------------------------------------------------------- reference arm
-def cpu_forward_timed(workload: str, budget_s: float, steps: int, warmup: int, threads: int):
+def cpu_forward_timed(workload: str, budget_s: float, steps: int, warmup: int, threads: int, fit_steps: bool = False):
     """Times the CPU oracle (oracle/fs2_oracle.py: the reference algorithm restated in torch CPU fp32) on a bounded
     sample (the first `n` utterances of the workload batch, n sized from a calibration run)."""
     import torch
@@ -137,6 +137,8 @@ def cpu_forward_timed(workload: str, budget_s: float, steps: int, warmup: int, t
     t_cal, f_cal = run(n_cal)
     per_utt = t_cal / n_cal
     n = max(1, min(B, int(budget_s / max(1e-6, per_utt * (steps + warmup)))))
+    if n == B and fit_steps:                      # the whole batch fits the budget: spend the rest on more timed steps
+        steps = max(steps, min(12, int(budget_s / max(1e-6, per_utt * B)) - warmup))
     for _ in range(warmup):
         run(n)
     times, frames = [], 0
@@ -345,7 +347,7 @@ def run_b200_arm(args):
         }
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
-            r = cpu_forward_timed(args.workload, 20.0, 2, 1, threads)
+            r = cpu_forward_timed(args.workload, 20.0, 2, 1, threads, fit_steps=True)   # ~10-20 s of CPU work
             line["cpu_baseline"] = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"]}
         else:
             line["cpu_baseline"] = None
