@@ -18,9 +18,9 @@
 // share a row swap their partial (sum, sum of squares) through shared memory (64-thread named barrier per lane quarter).
 // Row masking is by value (masked rows store zeros); rows past the end of the buffer are clipped by TMA.
 //
-// Tile width (Plan::bn): 256 columns, or 128 when that fills the 148 SMs better (the launcher compares the number of
-// rounds: at batch 32 the decoder has 151 row tiles, i.e. TWO rounds of 256-wide tiles for every N = 256 GEMM, and the
-// encoder only 22).  A LayerNorm epilogue needs the whole 256-column row: with 128-wide tiles the two CTAs that share a row
+// Tile width (Plan::bn): 256 columns, or 128 for latency-bound launches that would leave most SMs idle (at batch 32 the
+// encoder has 22 row tiles; N = 128 MMAs only reach ~2/3 of the N = 256 rate, so wide tiles stay the rule; see
+// tc_conv_gemm_staged_launch and profiles/experiments/README.md).  A LayerNorm epilogue needs the whole 256-column row: with 128-wide tiles the two CTAs that share a row
 // tile form a 2-CTA cluster and swap their partial (sum, sum of squares) through distributed shared memory
 // (st.shared::cluster + remote mbarrier arrive with release / acquire at cluster scope), one exchange per tile.
 #include "fs2_tc_common.cuh"
@@ -35,12 +35,12 @@ constexpr int BM = 128, BN_MAX = 256, BKE = 64;
 constexpr int NUM_THREADS = 352;                          // warp 0 TMA (A), warp 1 MMA, warp 2 TMA (B), warps 3-10 epilogue
 constexpr int EPI_T0 = 96;                                // first epilogue thread
 constexpr int A_BYTES = BM * BKE * 2;                     // 16 KB per k-block; the weight k-block is bn x 128 B (32 / 16 KB)
-constexpr int MAX_A = 4, MAX_B = 4;                       // ring depths: A streams from HBM (deep), W from L2 (shallow)
+constexpr int MAX_A = 4, MAX_B = 4;                       // ring depths (a k-step consumes one stage of each ring)
 constexpr int CH_F32 = BM * 32 * 4;                       // 16 KB: [128 rows][32 fp32], 128-byte rows, SWIZZLE_128B
 constexpr int CH_B16 = BM * 32 * 2;                       //  8 KB: [128 rows][32 bf16],  64-byte rows, SWIZZLE_64B
 // shared-memory plan (bytes from the 1024-aligned base), chosen per launch (struct Plan):
-//   A ring          nA x 16 KB   (activation k-blocks: HBM latency, deep)
-//   B ring          nB x 32 KB   (weight k-blocks: L2 hits, shallow)
+//   A ring          nA x 16 KB        (activation k-blocks, own producer warp)
+//   B ring          nB x 32 / 16 KB   (weight k-blocks of a 256 / 128-wide tile, own producer warp)
 //   group g region  wide plan: F0, F1 (2 x 16 KB fp32 staging / residual) + B staging (out_planes x 8 KB)
 //                   deep plan: B staging only
 //   params          bias[2][128], ln_g[256], ln_b[256], stats[2 parities][2 groups][128] float2,
