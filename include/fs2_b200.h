@@ -50,7 +50,8 @@ extern "C" {
                              accumulated in fp32 (error ~2^-23 per product); attention stays fp32 FFMA */
 #define FS2_PREC_F16X2 3  /* tcgen05, fp32-faithful: operands carried as 2 power-of-two-scaled fp16 terms (22 significant
                              bits), 3 cross products per MAC block -- half the tensor work of BF16X3 at the same error
-                             level as an fp32 FFMA GEMM; activations saturate at |x| = 4094; attention stays fp32 FFMA */
+                             level as an fp32 FFMA GEMM; activations saturate at |x| = 4094; attention runs on the tensor
+                             cores too (Q, K, V, P as scaled fp16 hi / lo planes, fp32 softmax) */
 
 typedef struct fs2_handle fs2_handle;
 
@@ -184,7 +185,7 @@ int fs2_op_mel_postnet(fs2_handle* h, int32_t prec, const float* dec, int32_t B,
                        float* mel_post, void* stream);
 /* Raw conv-as-GEMM check: out[R,N] = act(sum_t A[r+t-pad,:] . W[:, :, t]^T + bias), rows laid out as
  * B utterances of S rows (zero padded outside [0,S)).  W is torch Conv1d layout [N,K,taps].
- * act: 0 none, 1 relu, 2 tanh.  prec selects the SIMT fp32 or the tcgen05 bf16 kernel. */
+ * act: 0 none, 1 relu, 2 tanh.  prec selects the SIMT fp32 kernel or a tcgen05 mode (FS2_PREC_*). */
 int fs2_op_conv_gemm(int32_t prec, const float* A, const float* W, const float* bias, int32_t B, int32_t S,
                      int32_t K, int32_t N, int32_t taps, int32_t act, float* out, void* stream);
 /* Modules.py:14-25 on packed heads: q,k,v,out [B,S,H*dk]; keys >= lens[b] masked; rows >= lens[b] zero */
