@@ -269,7 +269,7 @@ extern int g_fs2_pdl;  // 1: launch with the programmatic-stream-serialization a
 // 1: the next launch is issued WITHOUT the attribute (fully stream-ordered) and clears the flag.  Set at every C-ABI entry
 // point and after every non-kernel stream operation the library enqueues: programmatic overlap is only relied upon
 // between two kernels of this library, never against a caller's memcpy / foreign kernel / memset that precedes them.
-extern int g_fs2_plain_next;
+extern thread_local int g_fs2_plain_next;   // per host thread: handles on different threads are independent
 template <typename F>
 inline cudaError_t fs2_launch_cfg(dim3 grid, dim3 block, size_t smem, cudaStream_t st, F&& f, int cluster_x = 1) {
   cudaLaunchConfig_t cfg;
