@@ -199,13 +199,22 @@ def run_b200_arm(args):
     # tcgen05 everywhere: f16x2 (2-term scaled fp16 split operands, fp32-faithful) for the encoder + variance predictors, whose
     # outputs are rounded to integer durations / bucket indices; plain bf16 for the decoder, mel linear and PostNet
     model.set_precision(args.enc, args.dec)
-    synth = pkg.ShardedSynthesizer(model) if world > 1 else None
+    streamed = args.streams > 1
+    # streams == 1: one forward at a time; with N > 1 GPUs ONE batch of 32 N utterances is sharded across the ranks and T is
+    #               all-reduced (ShardedSynthesizer) -- bit-identical to the unsharded reference call.
+    # streams  > 1: the job is a LIST of independent batches, as in the reference's `for batch in batchs` loop
+    #               (synthesize.py:59-76): every rank runs its own batches on `streams` CUDA streams concurrently
+    #               (StreamedSynthesizer); no collective on the data path.
+    synth = pkg.ShardedSynthesizer(model) if (world > 1 and not streamed) else None
 
     speakers, texts, src_lens, L = make_batch(args.workload, world)
     per = texts.shape[0] // world
     bounds = [(r * per, (r + 1) * per) for r in range(world)]
     lo, hi = bounds[rank]
-    # pinned host copies (e2e) and device-resident copies (value) of this rank's shard
+    if streamed and world > 1:      # this rank's utterances form a batch of their own: its own max_src_len
+        L = int(src_lens[lo:hi].max())
+        texts = texts[:, :L]
+    # pinned host copies (e2e) and device-resident copies (value) of this rank's batch / shard
     h_sp, h_tx, h_sl = (t[lo:hi].contiguous().pin_memory() for t in (speakers, texts, src_lens))
     d_sp, d_tx, d_sl = (t.to(dev) for t in (h_sp, h_tx, h_sl))
 
@@ -255,13 +264,49 @@ def run_b200_arm(args):
         step_resident()
     frames_local = int(out[9].sum().item())
     T = int(out[1].shape[1])
-    launches0 = model.launch_count
-    with ClockSampler(local_rank) as clk:
+    seq = None
+    if not streamed:
+        launches0 = model.launch_count
+        with ClockSampler(local_rank) as clk:
+            t_res = timed_loop(step_resident, steps)
+        launches = model.launch_count - launches0
+        for _ in range(3):
+            step_e2e()
+        t_e2e = timed_loop(step_e2e, steps)
+        ms_res_local, ms_e2e_local = sum(t_res) / steps, sum(t_e2e) / steps
+    else:
+        # one forward at a time first (reported as "sequential"), then the streamed job
         t_res = timed_loop(step_resident, steps)
-    launches = model.launch_count - launches0
-    for _ in range(3):
-        step_e2e()
-    t_e2e = timed_loop(step_e2e, steps)
+        for _ in range(3):
+            step_e2e()
+        t_e2e = timed_loop(step_e2e, steps)
+        seq = (sum(t_res) / steps, sum(t_e2e) / steps)
+        pipe = pkg.StreamedSynthesizer(model, n_streams=args.streams, device=dev)
+        pipe.warm_up((d_sp, d_tx, d_sl, L))
+
+        def streamed_loop(batch, n, to_host):
+            """n forwards of `batch` in flight on the worker streams; device time from the common start event to the
+            completion of the last job (every job ends with its stream synchronised)."""
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            jobs = [pipe.submit(batch, to_host=to_host, start_event=e0) for _ in range(n)]
+            for j in jobs:
+                pipe.wait(j)
+                j.result = None      # consume and drop: live results would turn every later forward into fresh cudaMallocs
+            e1.record()
+            barrier()
+            return e0.elapsed_time(e1)
+
+        for _ in range(2):           # primes the per-stream allocator pools (device and pinned host) as well
+            streamed_loop((d_sp, d_tx, d_sl, L), max(warmup, 3 * args.streams), False)
+            streamed_loop((h_sp, h_tx, h_sl, L), max(warmup, 3 * args.streams), (1, 9))
+        launches0 = model.launch_count
+        with ClockSampler(local_rank) as clk:
+            ms_res_local = streamed_loop((d_sp, d_tx, d_sl, L), steps, False) / steps
+        launches = model.launch_count - launches0
+        ms_e2e_local = streamed_loop((h_sp, h_tx, h_sl, L), steps, (1, 9)) / steps
+        pipe.close()
 
     # per-kernel-class device time (tracing on, separate pass over the same steps)
     model.profile_enable(True)
@@ -283,8 +328,10 @@ def run_b200_arm(args):
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         return float(t.item())
 
-    ms_res = reduce_max(sum(t_res)) / steps
-    ms_e2e = reduce_max(sum(t_e2e)) / steps
+    ms_res = reduce_max(ms_res_local)
+    ms_e2e = reduce_max(ms_e2e_local)
+    if seq is not None:
+        seq = (reduce_max(seq[0]), reduce_max(seq[1]))
     frames = int(reduce_sum(float(frames_local)))
     mel_lens_local = out[9].tolist()
     flops_local = algorithmic_flops(h_sl.tolist(), mel_lens_local)
@@ -317,12 +364,21 @@ def run_b200_arm(args):
             "config": {"workload": args.workload, "description": WORKLOADS[args.workload][3], "batch_per_gpu": per,
                        "global_batch": per * world, "max_src_len": L, "T_max": T, "frames_per_step": frames,
                        "weights": "random init (numpy PCG64 seed 0), duration head biased to ~7.67 frames/phoneme",
-                       "l2": "256 MiB flush buffer written between timed steps (untimed)",
-                       "parallelism": f"utterance shards x{world}" if world > 1 else "single GPU"},
+                       "streams": args.streams,
+                       "l2": ("256 MiB flush buffer written between timed steps (untimed)" if not streamed else
+                              f"no flush possible between overlapping forwards: {args.streams} concurrent forwards with private "
+                              "workspaces, aggregate working set several times the 126 MB L2 (the 'sequential' object is "
+                              "measured with the flush)"),
+                       "parallelism": (("single GPU" if world == 1 else f"utterance shards x{world}, T all-reduced") if not streamed
+                                       else f"{world} GPU(s) x {args.streams} streams, independent batches "
+                                            "(StreamedSynthesizer), no collective")},
             "e2e": {"value": frames / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
                     "h2d_bytes_per_step": int(sum(t.numel() * t.element_size() for t in (h_sp, h_tx, h_sl))),
                     "d2h_bytes_per_step": int(h_mel.numel() * h_mel.element_size() + h_lens.numel() * h_lens.element_size())},
             "gpu_launches": int(launches),
+            "sequential": (None if seq is None else
+                           {"value": frames / (seq[0] * 1e-3), "ms_per_step": seq[0], "e2e_value": frames / (seq[1] * 1e-3),
+                            "e2e_ms_per_step": seq[1], "note": "one forward at a time on one stream, L2 flushed between steps"}),
             "tflops_algorithmic": flops / (ms_res * 1e-3) / 1e12,
             "roofline": {"kernel": "tc_conv_gemm_staged_kernel as dec.ffn_w1 (Conv1d 256->1024 k=9 + ReLU, tcgen05 bf16)",
                          "bound": "tensor", "achieved": achieved, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
@@ -365,6 +421,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--streams", type=int, default=3,
+                    help="CUDA streams running independent forwards concurrently (1 = one forward at a time)")
     ap.add_argument("--enc", default="f16x2", choices=["fp32", "bf16x3", "f16x2", "bf16"], help="encoder + predictor arithmetic")
     ap.add_argument("--dec", default="bf16", choices=["fp32", "bf16x3", "f16x2", "bf16"], help="decoder + PostNet arithmetic")
     args = ap.parse_args()

@@ -15,4 +15,5 @@ run tc_stack test_gpu_tc "fft_stack or mel_postnet"
 run fwd_golden test_gpu_forward "golden"
 run fwd_other test_gpu_forward "not golden"
 run props test_gpu_properties ""
-for f in ops tc_gemm tc_attn tc_stack fwd_golden fwd_other props; do echo "=== $f"; grep -E "^(FAILED|ERROR)|Error|error|assert|max\|err\||max\|dlog" gpurun_out/$f.log | head -n 24; done
+run streamed test_gpu_streamed ""
+for f in ops tc_gemm tc_attn tc_stack fwd_golden fwd_other props streamed; do echo "=== $f"; grep -E "^(FAILED|ERROR)|Error|error|assert|max\|err\||max\|dlog" gpurun_out/$f.log | head -n 24; done

@@ -167,9 +167,11 @@ class FastSpeech2Align(nn.Module):
                                     preprocess_config["preprocessing"]["mel"]["n_mel_channels"])
         self.postnet = _PostNet()
         self._dims = dims_from_configs(preprocess_config, model_config, n_src_vocab)
-        self._handle: Optional[int] = None
+        # one engine (C handle: packed weights + workspace) per CUDA stream the module is called on: a handle is not
+        # thread-safe and its workspace is stream-ordered, so concurrent forwards on different streams (streamed.py) each
+        # get their own.  {stream pointer: {"h": handle, "stamp": weight stamp}}
+        self._engines = {}
         self._handle_device: Optional[torch.device] = None
-        self._stamp = None
         self._cached_ws = None
         self._precision = (PREC_F16X2, PREC_BF16)
         self._keep_rows = 2
@@ -186,18 +188,18 @@ class FastSpeech2Align(nn.Module):
         products, or 2 scaled fp16 terms and 3 cross products); "bf16" = tcgen05 bf16."""
         m = {"fp32": PREC_FP32, "bf16": PREC_BF16, "bf16x3": PREC_BF16X3, "f16x2": PREC_F16X2}
         self._precision = (m[encoder], m[decoder])
-        if self._handle is not None:
+        for e in self._engines.values():
             lib = load_library()
-            lib.check(lib.fs2_set_precision(self._handle, *self._precision), self._handle)
+            lib.check(lib.fs2_set_precision(e["h"], *self._precision), e["h"])
         return self
 
     def set_row_packing(self, keep_rows: int = 2) -> "FastSpeech2Align":
         """Padded rows kept per utterance in the internal layout: 2 = packed (default); a value >= the longest
         utterance = the reference's full padded grid.  Results are identical; only padded work changes."""
         self._keep_rows = int(keep_rows)
-        if self._handle is not None:
+        for e in self._engines.values():
             lib = load_library()
-            lib.check(lib.fs2_set_row_packing(self._handle, self._keep_rows), self._handle)
+            lib.check(lib.fs2_set_row_packing(e["h"], self._keep_rows), e["h"])
         return self
 
     def _weights(self):
@@ -206,32 +208,57 @@ class FastSpeech2Align(nn.Module):
                                if not k.startswith("mel_encoder.") and not k.endswith("num_batches_tracked")]
         return self._cached_ws
 
+    @property
+    def _handle(self) -> Optional[int]:
+        """The engine of the calling thread's current stream (or, failing that, any engine): tracing and counters."""
+        if not self._engines:
+            return None
+        if self._handle_device is not None:
+            key = torch.cuda.current_stream(self._handle_device).cuda_stream
+            if key in self._engines:
+                return self._engines[key]["h"]
+        return next(iter(self._engines.values()))["h"]
+
+    def _invalidate(self):
+        self._cached_ws = None
+        for e in getattr(self, "_engines", {}).values():
+            e["stamp"] = None
+
     def _apply(self, fn, *a, **k):  # .to() / .cuda() / .float(): parameter storage changes
-        self._cached_ws, self._stamp = None, None
+        self._invalidate()
         return super()._apply(fn, *a, **k)
 
     def load_state_dict(self, *a, **k):
-        self._cached_ws, self._stamp = None, None
+        self._invalidate()
         return super().load_state_dict(*a, **k)
+
+    def _destroy_engines(self):
+        lib = load_library()
+        for e in self._engines.values():
+            lib.fs2_destroy(e["h"])
+        self._engines = {}
 
     def _ensure_engine(self, device: torch.device):
         lib = load_library()
         if device.type != "cuda":
             raise RuntimeError("FastSpeech2Align (B200) runs on CUDA only; there is no CPU fallback. "
                                "Move the module and its inputs to a cuda device.")
-        if self._handle is not None and self._handle_device != device:
-            lib.fs2_destroy(self._handle)
-            self._handle, self._stamp = None, None
-        if self._handle is None:
+        if self._engines and self._handle_device != device:
+            self._destroy_engines()
+        key = torch.cuda.current_stream(device).cuda_stream
+        eng = self._engines.get(key)
+        if eng is None:
             hp = C.c_void_p()
             rc = lib.fs2_create(C.byref(hp), C.byref(self._dims), device.index if device.index is not None else torch.cuda.current_device())
             lib.check(rc, None)
-            self._handle, self._handle_device = hp.value, device
-            lib.check(lib.fs2_set_precision(self._handle, *self._precision), self._handle)
-            lib.check(lib.fs2_set_row_packing(self._handle, self._keep_rows), self._handle)
+            eng = {"h": hp.value, "stamp": None}
+            self._handle_device = device
+            lib.check(lib.fs2_set_precision(eng["h"], *self._precision), eng["h"])
+            lib.check(lib.fs2_set_row_packing(eng["h"], self._keep_rows), eng["h"])
+            self._engines[key] = eng
         ws = self._weights()
         stamp = (ws[0][1].data_ptr(), ws[-1][1].data_ptr(), sum(t._version for _, t in ws))
-        if stamp != self._stamp:
+        if stamp != eng["stamp"]:
             descs = (WeightDesc * len(ws))()
             keep = []
             for i, (k, t) in enumerate(ws):
@@ -248,15 +275,14 @@ class FastSpeech2Align(nn.Module):
                     descs[i].shape[j] = s
                 descs[i].on_device = 1
             torch.cuda.current_stream(device).synchronize()
-            lib.check(lib.fs2_load_weights(self._handle, descs, len(ws)), self._handle)
-            self._stamp = stamp
-        return lib
+            lib.check(lib.fs2_load_weights(eng["h"], descs, len(ws)), eng["h"])
+            eng["stamp"] = stamp
+        return lib, eng["h"]
 
     def __del__(self):
         try:
-            if getattr(self, "_handle", None) is not None:
-                load_library().fs2_destroy(self._handle)
-                self._handle = None
+            if getattr(self, "_engines", None):
+                self._destroy_engines()
         except Exception:
             pass
 
@@ -295,8 +321,7 @@ class FastSpeech2Align(nn.Module):
         if int(max_src_len) != L:
             raise ValueError(f"max_src_len ({int(max_src_len)}) must equal texts.shape[1] ({L})")
         dev = texts.device
-        lib = self._ensure_engine(dev)
-        h = self._handle
+        lib, h = self._ensure_engine(dev)
         texts = texts.long().contiguous()
         src_lens_in = src_lens.to(device=dev, dtype=torch.long).contiguous()
         stream = torch.cuda.current_stream(dev).cuda_stream

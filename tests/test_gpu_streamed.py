@@ -1,0 +1,39 @@
+"""StreamedSynthesizer (concurrent forwards of independent batches on several CUDA streams, one engine per stream) must
+return exactly what sequential calls return -- for device and for (pinned) host batches, and whatever the interleaving."""
+import pytest
+import torch
+
+import fs2_oracle as O
+from helpers import build_model
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def test_streamed_equals_sequential(lib):
+    from smart_nar_fast_tts_b200 import StreamedSynthesizer
+    sd = O.make_state_dict(0)
+    m = build_model(sd, O.STATS_NAN_BINS)
+    batches = [O.make_inputs(b, lo, hi, seed=s) for s, (b, lo, hi) in enumerate([(32, 40, 120), (5, 3, 40), (64, 40, 120), (1, 60, 60),
+                                                                               (16, 100, 200), (32, 40, 120), (7, 1, 9), (48, 20, 90)])]
+    seq = []
+    for sp, tx, sl, L in batches:
+        out = m(sp.to(DEV), tx.to(DEV), sl.to(DEV), L)
+        torch.cuda.synchronize()
+        seq.append([t.cpu() if t is not None else None for t in out])
+    synth = StreamedSynthesizer(m, n_streams=3)
+    try:
+        synth.warm_up(batches[0])
+        for rnd in range(3):                                  # several rounds: engines / workspaces are reused across shapes
+            order = batches if rnd % 2 == 0 else batches[::-1]
+            ref = seq if rnd % 2 == 0 else seq[::-1]
+            pinned = [tuple(t.pin_memory() if torch.is_tensor(t) else t for t in b) for b in order]
+            res = synth.run(pinned, to_host=True) if rnd == 1 else synth.run([(b[0].to(DEV), b[1].to(DEV), b[2].to(DEV), b[3]) for b in order])
+            for got, want in zip(res, ref):
+                for i in (0, 1, 2, 3, 4, 5, 6, 7, 9):
+                    assert torch.equal(got[i].cpu(), want[i]), f"round {rnd}: output {i} differs from the sequential call"
+        part = synth.run([tuple(t.pin_memory() if torch.is_tensor(t) else t for t in batches[2])], to_host=(1, 9))[0]
+        assert not part[1].is_cuda and not part[9].is_cuda and part[0].is_cuda
+        assert torch.equal(part[1], seq[2][1])
+    finally:
+        synth.close()
