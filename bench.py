@@ -4,9 +4,16 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c3|c5|c1] [--impl reference]
 
 One "step" = one forward of the hot path (FastSpeech2Align.forward, inference branch) over one synthetic
-batch.  Default workload = BASELINE.json configs[1] ("c2": batch 32, phoneme lengths 40..120, LJSpeech dims);
-with N > 1 GPUs the batch is 32*N utterances sharded contiguously across ranks (weak scaling) with the
-GLOBAL max_src_len and one all-reduce(max) of T between the two stages (the path's only exchange step).
+batch.  Default workload = BASELINE.json configs[1] ("c2": batch 32, phoneme lengths 40..120, LJSpeech dims).
+
+--streams S (default 3): the job is a list of independent batches, as in the reference's own driver loop
+(`for batch in batchs`, synthesize.py:59-76); the K steps are submitted to smart_nar_fast_tts_b200.StreamedSynthesizer,
+which keeps S forwards in flight on S CUDA streams (one engine per stream; results bit-identical to sequential calls).
+The K steps are timed as ONE bracket (CUDA events, barrier + synchronize on both sides); with N > 1 GPUs every rank
+runs its own batches (32 utterances each: 32*N per step, weak scaling, no collective on the data path).  The same
+forward issued one at a time (per-step CUDA events, L2 flushed between steps) is reported in `sequential`.
+--streams 1: one forward at a time; with N > 1 GPUs ONE batch of 32*N utterances is sharded contiguously across the
+ranks with the GLOBAL max_src_len and one all-reduce(max) of T between the two stages (ShardedSynthesizer).
 
 Printed JSON (one line, rank 0):
   value        mel-frames/s, inputs resident in HBM, CUDA events around each step, max over ranks

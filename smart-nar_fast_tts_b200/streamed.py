@@ -8,7 +8,9 @@ two stages, output allocation, the H2D / D2H copies of host batches -- overlaps 
 GPU, kernels of different forwards fill each other's tails: a persistent GEMM whose last round occupies 6 of 148 SMs
 no longer idles the rest (at batch 32 the decoder has 151 row tiles).  Results are bit-identical to sequential calls
 (tests/test_gpu_streamed.py).  Measured on B200 (bench.py): batch 32, 1 -> 3 streams: 11.0 -> 15.9 M frames/s with
-device-resident inputs, 9.4 -> 14.4 M frames/s end to end from pinned host buffers.
+device-resident inputs, 9.9 -> 15.0 M frames/s end to end from pinned host buffers.  Callers should consume and drop
+results as they arrive: every live result tuple pins ~20 MB of device (and, with to_host, page-locked host) memory that
+later forwards would otherwise reuse from the allocator caches.
 """
 from __future__ import annotations
 
