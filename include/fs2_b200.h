@@ -110,6 +110,13 @@ int fs2_set_precision(fs2_handle* h, int32_t encoder_prec, int32_t decoder_prec)
  * identical for every legal value; only the amount of padded work changes. */
 int fs2_set_row_packing(fs2_handle* h, int32_t keep_rows);
 
+/* Layout of the mel_post output of fs2_forward_stage2 / fs2_op_mel_postnet.  0 (default): [B, T, n_mel] as the reference
+ * returns it.  1: channel-major [B, n_mel, T] -- the tensor `predictions[1].transpose(1, 2)` that the reference hands to
+ * the vocoder (utils/tools.py:191, utils/model.py:70-76), written directly by the PostNet's last convolution (its
+ * epilogue holds one row per thread, so every channel is one coalesced store) instead of by a later transposing copy.
+ * `mel` (the pre-PostNet output) always stays [B, T, n_mel]. */
+int fs2_set_mel_post_layout(fs2_handle* h, int32_t channel_major);
+
 /* ---- the forward, in two stages because T = max(sum(durations)) is data dependent --- */
 /* replaces: fastspeech2_align.py:46-53 (src mask, TxtEncoder) + modules.py:116-135
  * (duration predictor, rounding) + the length bookkeeping of LengthRegulator.LR
@@ -136,6 +143,10 @@ int fs2_forward_stage1_async(fs2_handle* h, const int64_t* texts, const int64_t*
 /* T_max: the (possibly batch-global) maximum mel length stage 2 will be called with; frames: this rank's sum of
  * mel_lens (sizes tile-shape decisions only; 0 = unknown). */
 int fs2_forward_stage1_commit(fs2_handle* h, int32_t T_max, int32_t frames);
+
+/* sum_b mel_lens[b] of the last completed stage 1 on this handle (read back together with T_max; the caller sizes packed
+ * result buffers with it, fs2_pack_valid_rows); -1 before the first stage 1. */
+int64_t fs2_last_frame_count(const fs2_handle* h);
 
 /* replaces: LengthRegulator expand/pad (modules.py:220-226, utils/tools.py:288-306),
  * frame-level pitch/energy (modules.py:137-149), MelDecoder (Models.py:212-244),
@@ -164,6 +175,21 @@ int fs2_gaussian_upsample(const float* x, const float* d, int32_t B, int32_t L, 
                           float* out, float* s, float* w, void* stream);
 /* utils/tools.py:89-97: mask[b,i] = i >= lens[b] */
 int fs2_mask_from_lengths(const int64_t* lens, int32_t B, int32_t max_len, uint8_t* mask, void* stream);
+
+/* ---- hand-off of the results (no handle, no weights) ---------------------------- */
+/* replaces: the per-utterance `.item()` + slice + `.cpu()` loop of synth_samples (utils/tools.py:156-171).
+ * src [B,S,C] fp32 (channel_major = 1: [B,C,S]); lens[B] int64, clamped to [0,S].  dst receives the valid rows of
+ * utterance 0, 1, ... back to back: rows [offsets[b], offsets[b+1]) of a [sum lens, C] matrix (channel_major: utterance
+ * b's block, dst + offsets[b]*C, is a [C, lens[b]] matrix).  offsets[B+1] int64 (device, may be NULL) = exclusive prefix
+ * sum of the clamped lens.  dst must hold sum(lens)*C floats (B*S*C always suffices). */
+int fs2_pack_valid_rows(const float* src, const int64_t* lens, int32_t B, int32_t S, int32_t C, int32_t channel_major,
+                        int64_t* offsets, float* dst, void* stream);
+/* replaces: `(wavs.cpu().numpy() * max_wav_value).astype("int16")` + `wavs[i][:lengths[i]]` (utils/model.py:77-86).
+ * wav [B,N] fp32 (the vocoder's output); lens[B] int64 samples kept per row (clamped to [0,N]; NULL = all N).
+ * dst int16: the kept samples back to back, offsets[B+1] as above (may be NULL).  Conversion = numpy's on x86-64:
+ * fp32 product, truncation toward zero to int32, low 16 bits (NaN / |x| >= 2^31 -> 0). */
+int fs2_wav_to_int16(const float* wav, const int64_t* lens, int32_t B, int64_t N, float max_wav_value, int64_t* offsets,
+                     int16_t* dst, void* stream);
 
 /* ---- per-operator entry points on a loaded handle (unit parity tests) --------------- */
 /* Models.py:10-30: table[n_pos, d_model] as the reference builds it (float64 -> float32) */

@@ -16,4 +16,5 @@ run fwd_golden test_gpu_forward "golden"
 run fwd_other test_gpu_forward "not golden"
 run props test_gpu_properties ""
 run streamed test_gpu_streamed ""
-for f in ops tc_gemm tc_attn tc_stack fwd_golden fwd_other props streamed; do echo "=== $f"; grep -E "^(FAILED|ERROR)|Error|error|assert|max\|err\||max\|dlog" gpurun_out/$f.log | head -n 24; done
+run handoff test_gpu_handoff ""
+for f in ops tc_gemm tc_attn tc_stack fwd_golden fwd_other props streamed handoff; do echo "=== $f"; grep -E "^(FAILED|ERROR)|Error|error|assert|max\|err\||max\|dlog" gpurun_out/$f.log | head -n 24; done

@@ -3,7 +3,7 @@ from .capi import Fs2Error, Fs2Library, PREC_BF16, PREC_BF16X3, PREC_F16X2, PREC
 from .model import FastSpeech2Align, dims_from_configs  # noqa: F401
 from .sharding import ShardedSynthesizer, shard_bounds  # noqa: F401
 from .streamed import StreamedSynthesizer  # noqa: F401
-from . import synthetic  # noqa: F401
+from . import pipeline, synthetic  # noqa: F401
 
 __all__ = ["FastSpeech2Align", "dims_from_configs", "Fs2Error", "Fs2Library", "load_library", "PREC_FP32", "PREC_BF16", "PREC_BF16X3", "PREC_F16X2",
-           "ShardedSynthesizer", "StreamedSynthesizer", "shard_bounds", "synthetic"]
+           "ShardedSynthesizer", "StreamedSynthesizer", "shard_bounds", "synthetic", "pipeline"]

@@ -57,6 +57,7 @@ SIGNATURES = {
     "fs2_load_weights": (C.c_int, [_P, C.POINTER(WeightDesc), _I]),
     "fs2_set_precision": (C.c_int, [_P, _I, _I]),
     "fs2_set_row_packing": (C.c_int, [_P, _I]),
+    "fs2_set_mel_post_layout": (C.c_int, [_P, _I]),
     "fs2_forward_stage1": (C.c_int, [_P, _P, _P, _I, _I, _F, _F, _F, _P, _P, _P, _P, _P, _P, C.POINTER(_I), _P]),
     "fs2_forward_stage1_async": (C.c_int, [_P, _P, _P, _I, _I, _F, _F, _F, _P, _P, _P, _P, _P, _P, _P, _P]),
     "fs2_forward_stage1_commit": (C.c_int, [_P, _I, _I]),
@@ -66,6 +67,8 @@ SIGNATURES = {
     "fs2_length_regulate": (C.c_int, [_P, _P, _I, _I, _I, _I, _P, _P]),
     "fs2_gaussian_upsample": (C.c_int, [_P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P]),
     "fs2_mask_from_lengths": (C.c_int, [_P, _I, _I, _P, _P]),
+    "fs2_pack_valid_rows": (C.c_int, [_P, _P, _I, _I, _I, _I, _P, _P, _P]),
+    "fs2_wav_to_int16": (C.c_int, [_P, _P, _I, C.c_int64, _F, _P, _P, _P]),
     "fs2_op_sinusoid_table": (C.c_int, [_P, _I, _P, _P]),
     "fs2_op_embed_pe": (C.c_int, [_P, _P, _I, _I, _P, _P]),
     "fs2_op_fft_stack": (C.c_int, [_P, _I, _I, _I, _I, _P, _P, _I, _I, _P, _P]),
@@ -78,6 +81,7 @@ SIGNATURES = {
     "fs2_profile_reset": (C.c_int, [_P]),
     "fs2_profile_read": (C.c_int, [_P, C.POINTER(ProfileEntry), _I, C.POINTER(_I)]),
     "fs2_launch_count": (C.c_int64, [_P]),
+    "fs2_last_frame_count": (C.c_int64, [_P]),
 }
 
 

@@ -55,6 +55,7 @@ struct fs2_handle {
   int device = 0;
   int prec_enc = FS2_PREC_BF16X3, prec_dec = FS2_PREC_BF16;
   int halo_keep = 2;  // padded rows kept per utterance (2 = packed; >= max length = the reference's padded grid)
+  int mel_post_cm = 0;  // stage 2 / fs2_op_mel_postnet write mel_post channel-major [B, n_mel, T] (vocoder hand-off)
   bool loaded = false;
   std::string err;
   std::map<std::string, RawT> raw;
@@ -541,12 +542,13 @@ int run_mel_postnet(fs2_handle* h, int prec, const float* dec, const bf16* decb,
       in_f = of; in_b = ob;
     } else {
       a.epi = EPI_RES; a.residual = melg; a.out = postg; a.ldo = M; a.out_user = mel_post; a.ldu = M; a.out_user_B = B;
+      a.user_cm = h->mel_post_cm;
     }
     RCHECK(run_gemm(h, prec, a, st, "postnet." + std::to_string(i)));
   }
   {
     PROF("rows.postnet_far");
-    HCHECK(rowops_postnet_far_rows(postg, M, pn, B, H, mel_post, st));
+    HCHECK(rowops_postnet_far_rows(postg, M, pn, B, H, mel_post, h->mel_post_cm, st));
   }
   return FS2_OK;
 }
@@ -577,6 +579,8 @@ const char* fs2_version(void) { return "fs2_b200 0.1 (sm_100a)"; }
 const char* fs2_last_error(const fs2_handle* h) { return h ? h->err.c_str() : g_last_error.c_str(); }
 
 int64_t fs2_launch_count(const fs2_handle*) { return (int64_t)g_fs2_launches; }
+
+int64_t fs2_last_frame_count(const fs2_handle* h) { return (h && h->have_stage1) ? (int64_t)h->st_frames : -1; }
 
 int fs2_create(fs2_handle** out, const fs2_dims* d, int device) {
   if (!out || !d) { g_last_error = "null argument"; return FS2_ERR_INVALID; }
@@ -631,6 +635,13 @@ int fs2_set_row_packing(fs2_handle* h, int32_t keep_rows) {
   if (keep_rows < 2) return h->fail(FS2_ERR_INVALID, "keep_rows must be >= 2 (the variance predictors' halo)");
   h->halo_keep = keep_rows;
   h->have_stage1 = false;
+  return FS2_OK;
+}
+
+int fs2_set_mel_post_layout(fs2_handle* h, int32_t channel_major) {
+  if (!h) return FS2_ERR_INVALID;
+  if (channel_major != 0 && channel_major != 1) return h->fail(FS2_ERR_INVALID, "channel_major must be 0 or 1");
+  h->mel_post_cm = channel_major;
   return FS2_OK;
 }
 
@@ -990,6 +1001,33 @@ int fs2_mask_from_lengths(const int64_t* lens, int32_t B, int32_t max_len, uint8
   g_fs2_plain_next = 1;   // the first launch of an entry point is fully stream-ordered (fs2_common.cuh)
   if (!lens || !mask || B <= 0 || max_len < 0) { g_last_error = "bad argument"; return FS2_ERR_INVALID; }
   FS2_CUDA_CHECK(rowops_mask(lens, nullptr, B, max_len, mask, reinterpret_cast<cudaStream_t>(stream)));
+  return FS2_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// hand-off to the consumers of the result (kernels in fs2_handoff.cu)
+int fs2_pack_valid_rows(const float* src, const int64_t* lens, int32_t B, int32_t S, int32_t C, int32_t channel_major,
+                        int64_t* offsets, float* dst, void* stream) {
+  g_fs2_plain_next = 1;   // the first launch of an entry point is fully stream-ordered (fs2_common.cuh)
+  if (B == 0) return FS2_OK;
+  if (!src || !lens || !dst || B < 0 || B > 65535 || S < 0 || C <= 0 || (channel_major != 0 && channel_major != 1)) {
+    g_last_error = "fs2_pack_valid_rows: bad argument (src, lens, dst non-null; 0 <= B <= 65535; S >= 0; C > 0)";
+    return FS2_ERR_INVALID;
+  }
+  FS2_CUDA_CHECK(handoff_pack_valid_rows(src, lens, B, S, C, channel_major, offsets, dst,
+                                         reinterpret_cast<cudaStream_t>(stream)));
+  return FS2_OK;
+}
+
+int fs2_wav_to_int16(const float* wav, const int64_t* lens, int32_t B, int64_t N, float max_wav_value, int64_t* offsets,
+                     int16_t* dst, void* stream) {
+  g_fs2_plain_next = 1;   // the first launch of an entry point is fully stream-ordered (fs2_common.cuh)
+  if (B == 0) return FS2_OK;
+  if (!wav || !dst || B < 0 || B > 65535 || N < 0) {
+    g_last_error = "fs2_wav_to_int16: bad argument (wav, dst non-null; 0 <= B <= 65535; N >= 0)";
+    return FS2_ERR_INVALID;
+  }
+  FS2_CUDA_CHECK(handoff_wav_to_int16(wav, lens, B, N, max_wav_value, offsets, dst, reinterpret_cast<cudaStream_t>(stream)));
   return FS2_OK;
 }
 

@@ -110,6 +110,8 @@ struct ConvGemmArgs {
   float* out_user; // dense user layout: row (b,p), p < S, at (b*S + p)*ldu
   int ldu;
   int out_user_B;  // > 0: only utterances b < out_user_B exist in out_user (the layout carries extra pseudo utterances)
+  int user_cm;     // 1: out_user is channel-major [B, N, S] (element (b,p,c) at (b*N + c)*S + p): the layout the vocoder
+                   // takes (utils/tools.py:191 `predictions[1].transpose(1, 2)`); EPI_BIAS / RELU / TANH / RES only
   // EPI_QKV extras (tcgen05 path)
   bf16* q_b;   // [R, 256]
   bf16* k_b;   // [R, 256]
@@ -229,7 +231,7 @@ cudaError_t rowops_fill_padded_rows(const float* bias, int N, const RowLayout& s
 // PostNet rows farther than H from the last valid frame depend only on the bias row and on their distance to the end of
 // the grid: copy them from the pseudo utterance (index B of `pn`, min(S, 2H+1) all-bias rows) into out_user [B,S,N]
 cudaError_t rowops_postnet_far_rows(const float* post_grid, int N, const RowLayout& pn, int B, int H, float* out_user,
-                                    cudaStream_t st);
+                                    int user_cm, cudaStream_t st);
 cudaError_t rowops_gaussian_upsample(const float* x, const float* d, int B, int L, int D, int T, int T_w, float* out,
                                      float* s, float* w, cudaStream_t st);
 cudaError_t rowops_to_grid(const float* x_user, const RowLayout& lay, int C, float* out, int ldo, int col_off,
@@ -251,6 +253,12 @@ cudaError_t rowops_unsplit2(const bf16* src, int64_t n, int64_t plane_elems, flo
 cudaError_t rowops_transpose_v(const bf16* v, int R, int Rv, int D, bf16* vt, cudaStream_t st);
 cudaError_t rowops_add_pe(float* x, const float* pe, const RowLayout& lay, int D, cudaStream_t st);
 cudaError_t rowops_fill_zero(void* p, size_t bytes, cudaStream_t st);
+// fs2_handoff.cu: valid rows of a padded [B,S,C] (channel_major: [B,C,S]) tensor back to back + offsets[B+1];
+// int16 = numpy astype of wav * max_wav_value for the first lens[b] samples of each row, back to back
+cudaError_t handoff_pack_valid_rows(const float* src, const int64_t* lens, int B, int S, int C, int channel_major,
+                                    int64_t* offsets, float* dst, cudaStream_t st);
+cudaError_t handoff_wav_to_int16(const float* wav, const int64_t* lens, int B, int64_t N, float max_wav_value,
+                                 int64_t* offsets, int16_t* dst, cudaStream_t st);
 
 extern long long g_fs2_launches;  // kernels launched (incremented by every launcher)
 

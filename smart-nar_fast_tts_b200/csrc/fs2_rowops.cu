@@ -378,6 +378,23 @@ __global__ void __launch_bounds__(256) postnet_far_rows_kernel(const float* post
   for (int c = threadIdx.x & 31; c < (N >> 2); c += 32) st4(dst + c * 4, ld4(src + c * 4));
 }
 
+// Same rows for a channel-major user tensor [B, N, S]: one thread per row p (consecutive threads = consecutive addresses
+// in every channel), looping over the channels; the source row is the same for almost every thread (broadcast loads).
+__global__ void __launch_bounds__(256) postnet_far_rows_cm_kernel(const float* post_grid, int N, const RowLayout pn,
+                                                                  int B, int H, float* out_user) {
+  FS2_PDL_PROLOGUE();
+  const int b = blockIdx.y, S = pn.S;
+  const int e = ld_act(pn.ext + b);
+  if (e >= S) return;
+  const int p = max(e - H, 0) + blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= S) return;
+  const int Tp = ld_act(pn.ext + B);
+  const int j = S > Tp ? ((S - p <= H) ? Tp - (S - p) : H) : p;
+  const float* src = post_grid + ((size_t)ld_act(pn.off + B) + j) * N;
+  float* dst = out_user + (size_t)b * N * S + p;
+  for (int c = 0; c < N; ++c) dst[(size_t)c * S] = ld_act(src + c);
+}
+
 // model/modules.py:166-192 GaussianUpsampling.  Per utterance: e = cumsum(d), c = e - d/2 (monotone non-decreasing
 // because d >= 0 on this path; negative durations fall back to the full range), w[i,t] = exp(-0.01 (t-c_i)^2) /
 // (sum_i exp(..) + 1e-20), out[t,:] = sum_i w[i,t] x[i,:].  exp(-0.01*D^2) is exactly 0 in fp32 for |D| >= 103
@@ -682,8 +699,13 @@ cudaError_t rowops_fill_padded_rows(const float* bias, int N, const RowLayout& s
   return LAUNCHED();
 }
 cudaError_t rowops_postnet_far_rows(const float* post_grid, int N, const RowLayout& pn, int B, int H, float* out_user,
-                                    cudaStream_t st) {
+                                    int user_cm, cudaStream_t st) {
   if (B <= 0 || pn.S <= 0) return cudaSuccess;
+  if (user_cm) {
+    dim3 grid_cm((pn.S + 255) / 256, B);
+    (void)FS2_LAUNCH(postnet_far_rows_cm_kernel, grid_cm, 256, 0, st, post_grid, N, pn, B, H, out_user);
+    return LAUNCHED();
+  }
   dim3 grid((pn.S + 7) / 8, B);
   (void)FS2_LAUNCH(postnet_far_rows_kernel, grid, 256, 0, st, post_grid, N, pn, B, H, out_user);
   return LAUNCHED();

@@ -347,7 +347,13 @@ tc_conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           }
           if (a.out_b && dst_ok)
             store_bf16_chunk(a.out_b + dst_r * a.ldob + nb, dst_plane * a.ldob, a.out_planes, y, nb, a.N);
-          if (a.out_user && user_ok) {
+          if (a.out_user && user_ok && a.user_cm) {
+            // channel-major [B, N, S]: lanes hold consecutive rows p, so each column is one coalesced 128-byte store
+            float* o = a.out_user + ((size_t)ri.b * a.N + nb) * a.lay.S + ri.p;
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (nb + j < a.N) o[(size_t)j * a.lay.S] = y[j];
+          } else if (a.out_user && user_ok) {
             float* o = a.out_user + ((size_t)ri.b * a.lay.S + ri.p) * a.ldu + nb;
 #pragma unroll
             for (int j = 0; j < 32; j += 4)

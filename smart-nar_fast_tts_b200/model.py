@@ -175,6 +175,7 @@ class FastSpeech2Align(nn.Module):
         self._cached_ws = None
         self._precision = (PREC_F16X2, PREC_BF16)
         self._keep_rows = 2
+        self._mel_post_cm = False
         # multi-GPU hooks (sharding.py): map the local T_max to the batch-global one between the two stages.
         # t_max_hook works on the host int (one extra synchronisation); t_max_device_hook reduces the device int32[2]
         # tensor {T_max, frames} in place on the current stream BEFORE the forward's single read-back.
@@ -200,6 +201,18 @@ class FastSpeech2Align(nn.Module):
         for e in self._engines.values():
             lib = load_library()
             lib.check(lib.fs2_set_row_packing(e["h"], self._keep_rows), e["h"])
+        return self
+
+    def set_mel_post_layout(self, channel_major: bool = False) -> "FastSpeech2Align":
+        """channel_major=True: `postnet_output` (tuple position 1) is produced as a contiguous [B, n_mel, T] tensor by the
+        PostNet's last convolution and returned as its `.transpose(1, 2)` view -- same shape [B, T, n_mel], dtype and
+        values as the default, but `predictions[1].transpose(1, 2)`, what the reference feeds to the vocoder
+        (utils/tools.py:191), is then the contiguous tensor itself instead of a strided view the vocoder's first
+        convolution has to gather."""
+        self._mel_post_cm = bool(channel_major)
+        for e in self._engines.values():
+            lib = load_library()
+            lib.check(lib.fs2_set_mel_post_layout(e["h"], int(self._mel_post_cm)), e["h"])
         return self
 
     def _weights(self):
@@ -255,6 +268,7 @@ class FastSpeech2Align(nn.Module):
             self._handle_device = device
             lib.check(lib.fs2_set_precision(eng["h"], *self._precision), eng["h"])
             lib.check(lib.fs2_set_row_packing(eng["h"], self._keep_rows), eng["h"])
+            lib.check(lib.fs2_set_mel_post_layout(eng["h"], int(self._mel_post_cm)), eng["h"])
             self._engines[key] = eng
         ws = self._weights()
         stamp = (ws[0][1].data_ptr(), ws[-1][1].data_ptr(), sum(t._version for _, t in ws))
@@ -309,9 +323,17 @@ class FastSpeech2Align(nn.Module):
         return int(load_library().fs2_launch_count(self._handle)) if self._handle is not None else 0
 
     # ------------------------------------------------------------------ forward (fastspeech2_align.py:30-100)
-    @torch.no_grad()
     def forward(self, speakers, texts, src_lens, max_src_len, mels=None, mel_lens=None, max_mel_len=None,
                 p_targets=None, e_targets=None, p_control=1.0, e_control=1.0):
+        return self.forward_with_info(speakers, texts, src_lens, max_src_len, mels, mel_lens, max_mel_len, p_targets,
+                                      e_targets, p_control, e_control)[0]
+
+    @torch.no_grad()
+    def forward_with_info(self, speakers, texts, src_lens, max_src_len, mels=None, mel_lens=None, max_mel_len=None,
+                          p_targets=None, e_targets=None, p_control=1.0, e_control=1.0):
+        """(the reference's 12-tuple, {"T": padded frame count, "frames": sum of mel_lens or None}).  `frames` is what
+        the forward's single read-back between the two stages already brought to the host; hand-off code
+        (pipeline.collect_samples) sizes its one device-to-host copy with it instead of synchronising again."""
         if any(a is not None for a in (mels, mel_lens, max_mel_len, p_targets, e_targets)):
             raise NotImplementedError("only the inference branch (mel_lens=None) is implemented; the reference's "
                                       "training branch calls an undefined _calculate_duration")
@@ -352,11 +374,12 @@ class FastSpeech2Align(nn.Module):
                     ph_p.data_ptr() if ph_p is not None else None, ph_e.data_ptr() if ph_e is not None else None,
                     C.byref(t_max), stream), h)
                 T = int(t_max.value)
+                frames = int(lib.fs2_last_frame_count(h))
                 if self.t_max_hook is not None:
                     T = int(self.t_max_hook(T, dev))
             n_mel = self._dims.n_mel
             mel = torch.empty(B, T, n_mel, **f32)
-            mel_post = torch.empty(B, T, n_mel, **f32)
+            mel_post = torch.empty(B, n_mel, T, **f32) if self._mel_post_cm else torch.empty(B, T, n_mel, **f32)
             pitch = ph_p if ph_p is not None else torch.empty(B, T, **f32)
             energy = ph_e if ph_e is not None else torch.empty(B, T, **f32)
             mel_masks = torch.empty(B, T, device=dev, dtype=torch.bool)
@@ -364,4 +387,7 @@ class FastSpeech2Align(nn.Module):
                 h, T, float(p_control), float(e_control), mel.data_ptr(), mel_post.data_ptr(),
                 None if ph_p is not None else pitch.data_ptr(), None if ph_e is not None else energy.data_ptr(),
                 mel_masks.data_ptr(), stream), h)
-        return (mel, mel_post, pitch, energy, log_d, d_rounded, src_masks, mel_masks, src_lens, out_mel_lens, None, None)
+        if self._mel_post_cm:
+            mel_post = mel_post.transpose(1, 2)
+        return ((mel, mel_post, pitch, energy, log_d, d_rounded, src_masks, mel_masks, src_lens, out_mel_lens, None, None),
+                {"T": T, "frames": frames})

@@ -24,10 +24,10 @@ Batch = Tuple[torch.Tensor, torch.Tensor, torch.Tensor, int]   # speakers[B], te
 
 
 class _Job:
-    __slots__ = ("batch", "kw", "to_host", "result", "error", "done", "start_event")
+    __slots__ = ("batch", "kw", "to_host", "post", "result", "error", "done", "start_event")
 
-    def __init__(self, batch, kw, to_host, start_event):
-        self.batch, self.kw, self.to_host, self.start_event = batch, kw, to_host, start_event
+    def __init__(self, batch, kw, to_host, start_event, post=None):
+        self.batch, self.kw, self.to_host, self.start_event, self.post = batch, kw, to_host, start_event, post
         self.result, self.error = None, None
         self.done = threading.Event()
 
@@ -67,8 +67,10 @@ class StreamedSynthesizer:
                         stream.wait_event(job.start_event)
                     sp, tx, sl, L = job.batch
                     sp, tx, sl = (t.to(self.device, non_blocking=True) for t in (sp, tx, sl))
-                    out = self.model(sp, tx, sl, L, **job.kw)
-                    if job.to_host:
+                    out, info = self.model.forward_with_info(sp, tx, sl, L, **job.kw)
+                    if job.post is not None:      # hand-off work (pipeline.py) runs on this job's stream as well
+                        out = job.post(out, info)
+                    elif job.to_host:
                         sel = None if job.to_host is True else set(job.to_host)
                         host = []
                         for k, t in enumerate(out):
@@ -87,8 +89,10 @@ class StreamedSynthesizer:
                 job.done.set()
 
     # ------------------------------------------------------------------ API
-    def submit(self, batch: Batch, to_host=False, start_event: Optional[torch.cuda.Event] = None, **kw) -> _Job:
-        job = _Job(batch, kw, to_host, start_event)
+    def submit(self, batch: Batch, to_host=False, start_event: Optional[torch.cuda.Event] = None, post=None, **kw) -> _Job:
+        """`post(predictions, info)`: optional callable run by the worker on the job's stream right after the forward
+        (`info` = {"T", "frames"}, see FastSpeech2Align.forward_with_info); its return value becomes the job's result."""
+        job = _Job(batch, kw, to_host, start_event, post)
         self._queue.put(job)
         return job
 
