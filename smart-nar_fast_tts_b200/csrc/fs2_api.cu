@@ -68,6 +68,7 @@ struct fs2_handle {
   int pe_ext_n[2] = {0, 0};
   std::map<std::string, std::pair<void*, size_t>> ws;  // growable workspace
   int* host_tmax = nullptr;                            // pinned
+  cudaStream_t fill_stream = nullptr;                  // zero-fill of fresh workspace (see ensure)
   // tracing: per-kernel-class device time from CUDA events on the launching stream (fs2_profile_*)
   bool prof_on = false;
   struct ProfPending { int slot; cudaEvent_t a, b; };
@@ -114,8 +115,18 @@ struct fs2_handle {
     size_t cap = bytes + bytes / 4 + 256;
     void* p = nullptr;
     if (cudaMalloc(&p, cap) != cudaSuccess) return nullptr;
-    // fresh workspace is zeroed once so that no kernel can ever multiply a masked 0 with a NaN bit pattern
-    if (cudaMemset(p, 0, cap) != cudaSuccess) { cudaFree(p); return nullptr; }
+    // fresh workspace is zeroed once so that no kernel can ever multiply a masked 0 with a NaN bit pattern.  The fill
+    // must have FINISHED before this returns: the caller's kernels run on its own stream, which (torch side streams are
+    // cudaStreamNonBlocking) is not ordered against the legacy default stream a plain cudaMemset would use -- a delayed
+    // fill would wipe what the first kernels of the forward wrote (seen as T = 0 on a fresh engine of a
+    // StreamedSynthesizer while other threads kept stream 0 busy).  Allocation is rare (first use / growth).
+    // A private non-blocking stream: the fill waits for nobody else's work either.
+    if (!fill_stream && cudaStreamCreateWithFlags(&fill_stream, cudaStreamNonBlocking) != cudaSuccess) {
+      fill_stream = nullptr; cudaFree(p); return nullptr;
+    }
+    if (cudaMemsetAsync(p, 0, cap, fill_stream) != cudaSuccess || cudaStreamSynchronize(fill_stream) != cudaSuccess) {
+      cudaFree(p); return nullptr;
+    }
     ws[name] = {p, cap};
     return p;
   }
@@ -618,6 +629,7 @@ void fs2_destroy(fs2_handle* h) {
   for (auto& p : h->prof_pending) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
   for (cudaEvent_t e : h->prof_pool) cudaEventDestroy(e);
   if (h->host_tmax) cudaFreeHost(h->host_tmax);
+  if (h->fill_stream) cudaStreamDestroy(h->fill_stream);
   delete h;
 }
 
@@ -647,7 +659,7 @@ int fs2_set_mel_post_layout(fs2_handle* h, int32_t channel_major) {
 
 int fs2_load_weights(fs2_handle* h, const fs2_weight_desc* descs, int32_t n) {
   // weight repacking interleaves cudaMemcpyAsync with small kernels: no programmatic overlap here at all
-  struct PdlOff { int saved; PdlOff() : saved(g_fs2_pdl) { g_fs2_pdl = 0; } ~PdlOff() { g_fs2_pdl = saved; } } pdl_off;
+  struct PdlOff { PdlOff() { ++g_fs2_pdl_off; } ~PdlOff() { --g_fs2_pdl_off; } } pdl_off;
   if (!h || !descs || n <= 0) return h ? h->fail(FS2_ERR_INVALID, "null/empty weight list") : FS2_ERR_INVALID;
   HCHECK(cudaSetDevice(h->device));
   cudaStream_t st = 0;
@@ -1011,7 +1023,11 @@ int fs2_pack_valid_rows(const float* src, const int64_t* lens, int32_t B, int32_
   g_fs2_plain_next = 1;   // the first launch of an entry point is fully stream-ordered (fs2_common.cuh)
   if (B == 0) return FS2_OK;
   if (!src || !lens || !dst || B < 0 || B > 65535 || S < 0 || C <= 0 || (channel_major != 0 && channel_major != 1)) {
-    g_last_error = "fs2_pack_valid_rows: bad argument (src, lens, dst non-null; 0 <= B <= 65535; S >= 0; C > 0)";
+    char buf[256];
+    snprintf(buf, sizeof buf, "fs2_pack_valid_rows: bad argument (src, lens, dst non-null; 0 <= B <= 65535; S >= 0; C > 0): "
+             "src=%p lens=%p dst=%p B=%d S=%d C=%d channel_major=%d", (const void*)src, (const void*)lens, (void*)dst, B, S, C,
+             channel_major);
+    g_last_error = buf;
     return FS2_ERR_INVALID;
   }
   FS2_CUDA_CHECK(handoff_pack_valid_rows(src, lens, B, S, C, channel_major, offsets, dst,
@@ -1024,7 +1040,10 @@ int fs2_wav_to_int16(const float* wav, const int64_t* lens, int32_t B, int64_t N
   g_fs2_plain_next = 1;   // the first launch of an entry point is fully stream-ordered (fs2_common.cuh)
   if (B == 0) return FS2_OK;
   if (!wav || !dst || B < 0 || B > 65535 || N < 0) {
-    g_last_error = "fs2_wav_to_int16: bad argument (wav, dst non-null; 0 <= B <= 65535; N >= 0)";
+    char buf[256];
+    snprintf(buf, sizeof buf, "fs2_wav_to_int16: bad argument (wav, dst non-null; 0 <= B <= 65535; N >= 0): wav=%p dst=%p B=%d "
+             "N=%lld", (const void*)wav, (void*)dst, B, (long long)N);
+    g_last_error = buf;
     return FS2_ERR_INVALID;
   }
   FS2_CUDA_CHECK(handoff_wav_to_int16(wav, lens, B, N, max_wav_value, offsets, dst, reinterpret_cast<cudaStream_t>(stream)));

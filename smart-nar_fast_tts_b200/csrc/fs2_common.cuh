@@ -278,6 +278,9 @@ extern int g_fs2_pdl;  // 1: launch with the programmatic-stream-serialization a
 // point and after every non-kernel stream operation the library enqueues: programmatic overlap is only relied upon
 // between two kernels of this library, never against a caller's memcpy / foreign kernel / memset that precedes them.
 extern thread_local int g_fs2_plain_next;   // per host thread: handles on different threads are independent
+// > 0: this host thread launches everything without the attribute (weight loading).  Per thread, like the flag above:
+// toggling the process-wide g_fs2_pdl from two threads loading weights at once could leave it cleared for good.
+extern thread_local int g_fs2_pdl_off;
 template <typename F>
 inline cudaError_t fs2_launch_cfg(dim3 grid, dim3 block, size_t smem, cudaStream_t st, F&& f, int cluster_x = 1) {
   cudaLaunchConfig_t cfg;
@@ -285,7 +288,7 @@ inline cudaError_t fs2_launch_cfg(dim3 grid, dim3 block, size_t smem, cudaStream
   cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
   cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = (g_fs2_pdl && !g_fs2_plain_next) ? 1 : 0;
+  attr[0].val.programmaticStreamSerializationAllowed = (g_fs2_pdl && !g_fs2_plain_next && !g_fs2_pdl_off) ? 1 : 0;
   g_fs2_plain_next = 0;
   cfg.attrs = attr; cfg.numAttrs = 1;
   if (cluster_x > 1) {   // thread-block cluster along x

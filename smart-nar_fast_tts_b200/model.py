@@ -251,6 +251,14 @@ class FastSpeech2Align(nn.Module):
             lib.fs2_destroy(e["h"])
         self._engines = {}
 
+    def release_engine(self, stream) -> None:
+        """Destroy the engine bound to `stream` (a torch.cuda.Stream or a raw stream pointer): packed weights and
+        workspace of that stream are freed.  StreamedSynthesizer.close() calls this for its streams."""
+        key = stream.cuda_stream if hasattr(stream, "cuda_stream") else int(stream)
+        e = self._engines.pop(key, None)
+        if e is not None:
+            load_library().fs2_destroy(e["h"])
+
     def _ensure_engine(self, device: torch.device):
         lib = load_library()
         if device.type != "cuda":

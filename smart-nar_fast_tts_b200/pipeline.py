@@ -18,7 +18,6 @@ cross PCIe.  Plotting (matplotlib) and file writing stay with the caller: they a
 from __future__ import annotations
 
 import collections
-import ctypes as C
 from dataclasses import dataclass, field
 from typing import Iterable, Iterator, List, Optional, Sequence, Tuple
 
@@ -258,20 +257,23 @@ def vocoder_infer(mels, vocoder, model_config, preprocess_config, lengths=None) 
 # ------------------------------------------------------------------------------------------ the driver loop
 
 
-def synthesize(model, configs, vocoder, batchs: Iterable[tuple], n_streams: int = 3,
-               window: Optional[int] = None) -> Iterator[Tuple[tuple, SampleSet, Optional[List[np.ndarray]]]]:
+def synthesize(model, configs, vocoder, batchs: Iterable[tuple], n_streams: int = 3, window: Optional[int] = None,
+               synth: Optional[StreamedSynthesizer] = None) -> Iterator[Tuple[tuple, SampleSet, Optional[List[np.ndarray]]]]:
     """synthesize.py:59-76 as a generator: for every batch (collate's 6-tuple, numpy) yields
     (batch, SampleSet, wavs or None) in order -- everything `synth_samples` would plot and write.  The batches run
     `n_streams` at a time on separate CUDA streams (StreamedSynthesizer); staging, the forward, the packing of the
     results and the vocoder of one batch overlap the others'.  `window` bounds the batches in flight (default
-    2 * n_streams) so results are consumed while later batches run."""
+    2 * n_streams) so results are consumed while later batches run.  `synth`: a StreamedSynthesizer to reuse across calls
+    (its per-stream engines -- packed weights, workspaces -- then survive; a temporary one is created and closed otherwise)."""
     preprocess_config, model_config = configs[0], configs[1]
     pre = preprocess_config["preprocessing"]
     hop = pre["stft"]["hop_length"] if "stft" in pre else None
     p_feat, e_feat = pre["pitch"]["feature"], pre["energy"]["feature"]
     device = next(model.parameters()).device
-    synth = StreamedSynthesizer(model, n_streams=n_streams, device=device)
-    window = window or 2 * n_streams
+    own = synth is None
+    if own:
+        synth = StreamedSynthesizer(model, n_streams=n_streams, device=device)
+    window = window or 2 * synth.n_streams
 
     def stage(batch):
         _, _, speakers, texts, src_lens, max_src_len = batch
@@ -299,4 +301,7 @@ def synthesize(model, configs, vocoder, batchs: Iterable[tuple], n_streams: int 
             b, j = pending.popleft()
             yield (b, *synth.wait(j))
     finally:
-        synth.close()
+        if own:
+            for _, j in pending:          # abandoned generator: let the jobs in flight finish before the engines go
+                j.done.wait()
+            synth.close()

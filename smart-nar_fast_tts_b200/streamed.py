@@ -132,11 +132,19 @@ class StreamedSynthesizer:
             raise errs[0]
 
     def close(self) -> None:
+        """Stop the workers and free the engines (packed weights + workspaces) of this synthesizer's streams."""
+        if not self._threads:
+            return
         for _ in self._threads:
             self._queue.put(None)
         for t in self._threads:
             t.join(timeout=5)
+        alive = any(t.is_alive() for t in self._threads)
         self._threads = []
+        if not alive and hasattr(self.model, "release_engine"):
+            for st in self._streams:
+                st.synchronize()
+                self.model.release_engine(st)
 
     def __del__(self):
         try:

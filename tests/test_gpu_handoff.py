@@ -103,7 +103,8 @@ def test_wav_to_int16_matches_numpy(lib, B, N, with_lens):
     from smart_nar_fast_tts_b200 import pipeline as P
     g = np.random.Generator(np.random.PCG64(B * 31 + N))
     wav = (g.standard_normal((B, N)) * 0.6).astype(np.float32)           # |x| > 1 in ~10 %: exercises the wrap
-    wav[0, :8] = [np.nan, np.inf, -np.inf, 1e10, -1e10, 65536.0 / 32768.0, 0.99999, -1.0]
+    special = [np.nan, np.inf, -np.inf, 1e10, -1e10, 65536.0 / 32768.0, 0.99999, -1.0]
+    wav[0, : min(N, 8)] = special[: min(N, 8)]
     wav[-1, -3:] = [1.0, -1.00004, 3.5]
     lengths = None
     if with_lens:
@@ -189,11 +190,16 @@ def test_synthesize_pipeline_equals_one_batch_at_a_time(model):
         with np.errstate(invalid="ignore"):
             wavs = H.vocoder_post(voc(torch.from_numpy(np.ascontiguousarray(mels_cm)).to(DEV)).squeeze(1).cpu().numpy(), 32768.0, lengths)
         want.append((H.synth_samples_data(pn), wavs))
+    from smart_nar_fast_tts_b200 import StreamedSynthesizer
+    shared = StreamedSynthesizer(model, n_streams=2)
+    n_engines = len(model._engines)
     for layout in (False, True):
         model.set_mel_post_layout(layout)
         try:
             n = 0
-            for (b, samples, wavs), (w_s, w_w), src in zip(P.synthesize(model, (pc, mc), voc, batches), want, batches):
+            # layout False: a temporary 3-stream synthesizer; layout True: a caller-owned one, reused
+            kw = dict(synth=shared) if layout else {}
+            for (b, samples, wavs), (w_s, w_w), src in zip(P.synthesize(model, (pc, mc), voc, batches, **kw), want, batches):
                 assert b is src and len(samples) == len(w_s) == len(wavs)
                 for i, w in enumerate(w_s):
                     for k in ("mel", "pitch", "energy", "duration"):
@@ -203,6 +209,10 @@ def test_synthesize_pipeline_equals_one_batch_at_a_time(model):
             assert n == len(batches)
         finally:
             model.set_mel_post_layout(False)
+    # the temporary synthesizer released its three engines; the shared one keeps its two until closed
+    assert len(model._engines) == n_engines + 2
+    shared.close()
+    assert len(model._engines) == n_engines
     # without a vocoder: wavs is None, samples as before
     first = next(iter(P.synthesize(model, (pc, mc), None, batches[:1])))
     assert first[2] is None and np.array_equal(first[1].mel[0], want[0][0][0]["mel"])

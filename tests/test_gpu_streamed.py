@@ -37,3 +37,29 @@ def test_streamed_equals_sequential(lib):
         assert torch.equal(part[1], seq[2][1])
     finally:
         synth.close()
+
+
+def test_first_forward_on_a_side_stream_while_the_default_stream_is_busy(lib):
+    """A fresh engine allocates (and zero-fills) all of its workspace during its first forward.  The fill must be ordered
+    before the forward's kernels on the CALLER's stream: torch side streams do not synchronise with the legacy default
+    stream, so a fill issued there lands late when that stream is busy and wipes the forward's first results (the
+    regression: T == 0 from a new StreamedSynthesizer engine at batch 256)."""
+    sd = O.make_state_dict(0)
+    m = build_model(sd, O.STATS_NAN_BINS)
+    sp, tx, sl, L = O.make_inputs(64, 40, 120, seed=4)
+    args = (sp.to(DEV), tx.to(DEV), sl.to(DEV), L)
+    want = m(*args)                                           # engine of the default stream
+    a = torch.randn(8192, 8192, device=DEV)
+    torch.cuda.synchronize()
+    for trial in range(3):
+        side = torch.cuda.Stream()
+        for _ in range(12):                                   # ~100 ms of work queued on the default stream
+            a @ a
+        with torch.cuda.stream(side):
+            got = m(*args)                                    # new engine: every workspace buffer is allocated here
+        side.synchronize()
+        assert got[1].shape == want[1].shape, f"trial {trial}: T = {got[1].shape[1]}, expected {want[1].shape[1]}"
+        for i in (0, 1, 2, 3, 4, 5, 6, 7, 9):
+            assert torch.equal(got[i], want[i]), f"trial {trial}: output {i} differs on a fresh side-stream engine"
+        torch.cuda.synchronize()
+        m.release_engine(side)
