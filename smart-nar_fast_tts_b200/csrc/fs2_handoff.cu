@@ -41,7 +41,7 @@ __device__ __forceinline__ void segment_of(const int64_t* lens, int b, long long
 }
 
 // grid (chunks, B), 256 threads.  cm = 0: src [B, S, C] -> dst rows [off_b, off_b + len_b) of [sum len, C];
-// cm = 1: src [B, C, S] -> utterance b's block dst + off_b * C holds [C, len_b] (channel-major per utterance).
+// cm = 1 (grid (min(C,128), B)): src [B, C, S] -> utterance b's block dst + off_b * C holds [C, len_b].
 __global__ void __launch_bounds__(256) pack_valid_rows_kernel(const float* src, const int64_t* lens, int B, int S, int C,
                                                               int cm, int vec, int64_t* offsets, float* dst) {
   FS2_PDL_PROLOGUE();
@@ -58,15 +58,32 @@ __global__ void __launch_bounds__(256) pack_valid_rows_kernel(const float* src, 
   if (!cm) {
     const float* s = src + (size_t)b * S * C;     // the valid rows of an utterance are one contiguous block
     if (vec) {
-      for (size_t i = tid; i < (n >> 2); i += nthr) *reinterpret_cast<float4*>(d + 4 * i) = ld4(s + 4 * i);
+      const size_t n4 = n >> 2;
+      size_t i = tid;
+      for (; i + 3 * nthr < n4; i += 4 * nthr) {        // four independent 16-byte loads in flight per thread
+        const float4 v0 = ld4(s + 4 * i), v1 = ld4(s + 4 * (i + nthr)), v2 = ld4(s + 4 * (i + 2 * nthr)),
+                     v3 = ld4(s + 4 * (i + 3 * nthr));
+        *reinterpret_cast<float4*>(d + 4 * i) = v0;
+        *reinterpret_cast<float4*>(d + 4 * (i + nthr)) = v1;
+        *reinterpret_cast<float4*>(d + 4 * (i + 2 * nthr)) = v2;
+        *reinterpret_cast<float4*>(d + 4 * (i + 3 * nthr)) = v3;
+      }
+      for (; i < n4; i += nthr) *reinterpret_cast<float4*>(d + 4 * i) = ld4(s + 4 * i);
     } else {
       for (size_t i = tid; i < n; i += nthr) d[i] = ld_act(s + i);
     }
   } else {
+    // channel c of the utterance: len contiguous floats at s + c*S -> d + c*len; blocks take channels round-robin
     const float* s = src + (size_t)b * C * S;
-    for (size_t i = tid; i < n; i += nthr) {
-      const size_t c = i / (size_t)len, p = i - c * (size_t)len;
-      d[i] = ld_act(s + c * S + p);
+    for (int c = blockIdx.x; c < C; c += gridDim.x) {
+      const float* sc = s + (size_t)c * S;
+      float* dc = d + (size_t)c * len;
+      long long p = threadIdx.x;
+      for (; p + 3 * 256 < len; p += 4 * 256) {
+        const float v0 = ld_act(sc + p), v1 = ld_act(sc + p + 256), v2 = ld_act(sc + p + 512), v3 = ld_act(sc + p + 768);
+        dc[p] = v0; dc[p + 256] = v1; dc[p + 512] = v2; dc[p + 768] = v3;
+      }
+      for (; p < len; p += 256) dc[p] = ld_act(sc + p);
     }
   }
 }
@@ -94,15 +111,24 @@ __global__ void __launch_bounds__(256) wav_to_int16_kernel(const float* wav, con
   size_t done = 0;
   if (vec_ok && (off & 3) == 0) {               // 16-byte loads, 8-byte stores
     const size_t n4 = (size_t)len >> 2;
-    for (size_t i = tid; i < n4; i += nthr) {
-      const float4 v = ld4(s + 4 * i);
+    auto cvt4 = [scale](const float4 v) {
       short4 o;
       o.x = f32_to_i16_numpy(__fmul_rn(v.x, scale));
       o.y = f32_to_i16_numpy(__fmul_rn(v.y, scale));
       o.z = f32_to_i16_numpy(__fmul_rn(v.z, scale));
       o.w = f32_to_i16_numpy(__fmul_rn(v.w, scale));
-      *reinterpret_cast<short4*>(d + 4 * i) = o;
+      return o;
+    };
+    size_t i = tid;
+    for (; i + 3 * nthr < n4; i += 4 * nthr) {          // four independent 16-byte loads in flight per thread
+      const float4 v0 = ld4(s + 4 * i), v1 = ld4(s + 4 * (i + nthr)), v2 = ld4(s + 4 * (i + 2 * nthr)),
+                   v3 = ld4(s + 4 * (i + 3 * nthr));
+      *reinterpret_cast<short4*>(d + 4 * i) = cvt4(v0);
+      *reinterpret_cast<short4*>(d + 4 * (i + nthr)) = cvt4(v1);
+      *reinterpret_cast<short4*>(d + 4 * (i + 2 * nthr)) = cvt4(v2);
+      *reinterpret_cast<short4*>(d + 4 * (i + 3 * nthr)) = cvt4(v3);
     }
+    for (; i < n4; i += nthr) *reinterpret_cast<short4*>(d + 4 * i) = cvt4(ld4(s + 4 * i));
     done = n4 << 2;
   }
   for (size_t i = done + tid; i < (size_t)len; i += nthr) d[i] = f32_to_i16_numpy(__fmul_rn(ld_act(s + i), scale));
@@ -120,7 +146,7 @@ cudaError_t handoff_pack_valid_rows(const float* src, const int64_t* lens, int B
   if (B <= 0) return cudaSuccess;
   const bool aligned = ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15u) == 0;
   const int vec = (!channel_major && (C % 4 == 0) && aligned) ? 1 : 0;
-  dim3 grid(chunks_for((size_t)S * C, vec ? 16 : 8), B);
+  dim3 grid(channel_major ? (unsigned)(C < 128 ? C : 128) : chunks_for((size_t)S * C, vec ? 16 : 8), B);
   (void)FS2_LAUNCH(pack_valid_rows_kernel, grid, 256, 0, st, src, lens, B, S, C, channel_major, vec, offsets, dst);
   ++g_fs2_launches;
   return cudaGetLastError();
