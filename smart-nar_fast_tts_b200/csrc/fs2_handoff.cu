@@ -41,7 +41,7 @@ __device__ __forceinline__ void segment_of(const int64_t* lens, int b, long long
 }
 
 // grid (chunks, B), 256 threads.  cm = 0: src [B, S, C] -> dst rows [off_b, off_b + len_b) of [sum len, C];
-// cm = 1 (grid (min(C,128), B)): src [B, C, S] -> utterance b's block dst + off_b * C holds [C, len_b].
+// cm = 1: src [B, C, S] -> utterance b's block dst + off_b * C holds [C, len_b] (channel-major per utterance).
 __global__ void __launch_bounds__(256) pack_valid_rows_kernel(const float* src, const int64_t* lens, int B, int S, int C,
                                                               int cm, int vec, int64_t* offsets, float* dst) {
   FS2_PDL_PROLOGUE();
@@ -73,17 +73,23 @@ __global__ void __launch_bounds__(256) pack_valid_rows_kernel(const float* src, 
       for (size_t i = tid; i < n; i += nthr) d[i] = ld_act(s + i);
     }
   } else {
-    // channel c of the utterance: len contiguous floats at s + c*S -> d + c*len; blocks take channels round-robin
+    // utterance block [C, len]: element i = c * len + p comes from s + c*S + p.  32-bit index arithmetic (the division by
+    // len is the only non-trivial instruction); four independent loads in flight per thread
     const float* s = src + (size_t)b * C * S;
-    for (int c = blockIdx.x; c < C; c += gridDim.x) {
-      const float* sc = s + (size_t)c * S;
-      float* dc = d + (size_t)c * len;
-      long long p = threadIdx.x;
-      for (; p + 3 * 256 < len; p += 4 * 256) {
-        const float v0 = ld_act(sc + p), v1 = ld_act(sc + p + 256), v2 = ld_act(sc + p + 512), v3 = ld_act(sc + p + 768);
-        dc[p] = v0; dc[p + 256] = v1; dc[p + 512] = v2; dc[p + 768] = v3;
+    const unsigned n32 = (unsigned)n, l32 = (unsigned)len, t32 = (unsigned)tid, nt32 = (unsigned)nthr;
+    auto at = [=](unsigned i) { const unsigned c = i / l32; return s + (size_t)c * S + (i - c * l32); };
+    unsigned i = t32;
+    if (n < 0x40000000ull) {
+      for (; i + 3 * nt32 < n32; i += 4 * nt32) {
+        const float v0 = ld_act(at(i)), v1 = ld_act(at(i + nt32)), v2 = ld_act(at(i + 2 * nt32)), v3 = ld_act(at(i + 3 * nt32));
+        d[i] = v0; d[i + nt32] = v1; d[i + 2 * nt32] = v2; d[i + 3 * nt32] = v3;
       }
-      for (; p < len; p += 256) dc[p] = ld_act(sc + p);
+      for (; i < n32; i += nt32) d[i] = ld_act(at(i));
+    } else {
+      for (size_t j = tid; j < n; j += nthr) {
+        const size_t c = j / (size_t)len;
+        d[j] = ld_act(s + c * S + (j - c * (size_t)len));
+      }
     }
   }
 }
@@ -134,9 +140,20 @@ __global__ void __launch_bounds__(256) wav_to_int16_kernel(const float* wav, con
   for (size_t i = done + tid; i < (size_t)len; i += nthr) d[i] = f32_to_i16_numpy(__fmul_rn(ld_act(s + i), scale));
 }
 
-inline unsigned chunks_for(size_t elems_per_utt, size_t per_thread) {
-  const size_t c = (elems_per_utt + 256 * per_thread - 1) / (256 * per_thread);
-  return (unsigned)(c < 1 ? 1 : (c > 64 ? 64 : c));
+// Blocks per utterance.  Every block pays a fixed prologue (it re-derives its utterance's offset from the lengths), so
+// blocks should be few and fat: aim at ~8 blocks per SM over the whole grid, but keep >= min_per_thread work items per
+// thread (small batches: parallelism first), at least 1 and at most 1024 chunks.
+inline unsigned chunks_for(int B, size_t items_per_utt, size_t min_per_thread) {
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0)
+      sms = 148;
+  }
+  size_t want = ((size_t)8 * sms + B - 1) / B;
+  const size_t most = items_per_utt / (256 * min_per_thread);
+  if (want > most) want = most;
+  return (unsigned)(want < 1 ? 1 : (want > 1024 ? 1024 : want));
 }
 
 }  // namespace
@@ -146,7 +163,7 @@ cudaError_t handoff_pack_valid_rows(const float* src, const int64_t* lens, int B
   if (B <= 0) return cudaSuccess;
   const bool aligned = ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15u) == 0;
   const int vec = (!channel_major && (C % 4 == 0) && aligned) ? 1 : 0;
-  dim3 grid(channel_major ? (unsigned)(C < 128 ? C : 128) : chunks_for((size_t)S * C, vec ? 16 : 8), B);
+  dim3 grid(chunks_for(B, (size_t)S * C / (vec ? 4 : 1), 4), B);
   (void)FS2_LAUNCH(pack_valid_rows_kernel, grid, 256, 0, st, src, lens, B, S, C, channel_major, vec, offsets, dst);
   ++g_fs2_launches;
   return cudaGetLastError();
@@ -157,7 +174,7 @@ cudaError_t handoff_wav_to_int16(const float* wav, const int64_t* lens, int B, i
   if (B <= 0) return cudaSuccess;
   const bool aligned = (reinterpret_cast<uintptr_t>(wav) & 15u) == 0 && (reinterpret_cast<uintptr_t>(dst) & 7u) == 0;
   const int vec_ok = (aligned && N % 4 == 0) ? 1 : 0;
-  dim3 grid(chunks_for((size_t)N, 16), B);
+  dim3 grid(chunks_for(B, (size_t)N / 4, 4), B);
   (void)FS2_LAUNCH(wav_to_int16_kernel, grid, 256, 0, st, wav, lens, B, (long long)N, max_wav_value, vec_ok, offsets,
                    reinterpret_cast<short*>(dst));
   ++g_fs2_launches;
