@@ -589,7 +589,7 @@ const char* fs2_version(void) { return "fs2_b200 0.1 (sm_100a)"; }
 
 const char* fs2_last_error(const fs2_handle* h) { return h ? h->err.c_str() : g_last_error.c_str(); }
 
-int64_t fs2_launch_count(const fs2_handle*) { return (int64_t)g_fs2_launches; }
+int64_t fs2_launch_count(const fs2_handle*) { return (int64_t)g_fs2_launches.load(); }
 
 int64_t fs2_last_frame_count(const fs2_handle* h) { return (h && h->have_stage1) ? (int64_t)h->st_frames : -1; }
 

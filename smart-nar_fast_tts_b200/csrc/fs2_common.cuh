@@ -22,6 +22,7 @@
 //     (S_max - len) rows.
 // The layout lives in device memory (lens are device data; nothing is copied back to size it).
 #pragma once
+#include <atomic>
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
@@ -260,7 +261,8 @@ cudaError_t handoff_pack_valid_rows(const float* src, const int64_t* lens, int B
 cudaError_t handoff_wav_to_int16(const float* wav, const int64_t* lens, int B, int64_t N, float max_wav_value,
                                  int64_t* offsets, int16_t* dst, cudaStream_t st);
 
-extern long long g_fs2_launches;  // kernels launched (incremented by every launcher)
+extern std::atomic<long long> g_fs2_launches;  // kernels launched by the process (every launcher increments it; handles on
+                                                // several host threads launch concurrently)
 
 // ---------------------------------------------------------------------------------------------
 // Programmatic dependent launch.  Every kernel of the library is launched with the programmatic-stream-serialization

@@ -8,7 +8,7 @@
 #include <stdlib.h>
 #include <string.h>
 
-long long g_fs2_launches = 0;
+std::atomic<long long> g_fs2_launches{0};
 int g_fs2_pdl = getenv("FS2_NO_PDL") ? 0 : 1;
 thread_local int g_fs2_plain_next = 1;
 thread_local int g_fs2_pdl_off = 0;

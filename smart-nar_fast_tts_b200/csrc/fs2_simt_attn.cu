@@ -174,7 +174,7 @@ template <int DK>
 cudaError_t launch(const float* qkv, int ldqkv, int q_off, int k_off, int v_off, const RowLayout& lay, int H, float* out,
                    int ldo, cudaStream_t st) {
   const size_t smem = sizeof(float) * (BQ * (DK + 4) + BKV * (DK + 4) + BKV * DK + BQ * (BKV + 4));
-  static bool configured = false;
+  static std::atomic<bool> configured{false};   // handles on several host threads may race here: benign, but formally atomic
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(simt_attention_kernel<DK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;

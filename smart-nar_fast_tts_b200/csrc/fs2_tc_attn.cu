@@ -373,7 +373,7 @@ int launch_attention(const bf16* q, const bf16* k, const bf16* vt, const RowLayo
       !tc::make_tmap_bf16_3d(&tmV, vt, NP, 256, (uint64_t)Rv, (uint64_t)Rv, (uint64_t)256 * Rv, DK) ||
       !tc::make_tmap_bf16_3d(&tmO, out_b, NP, R, 256, 256, R * 256, BQ))
     return fs2_fail_cuda(cudaErrorInvalidValue, "cuTensorMapEncodeTiled(attention)");
-  static bool configured = false;
+  static std::atomic<bool> configured{false};   // handles on several host threads may race here: benign, but formally atomic
   const int smem = AttSmem<NP>::TOTAL;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(tc_attention_kernel<NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);

@@ -225,14 +225,14 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_
                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 inline PFN_encodeTiled get_encode_fn() {
-  static PFN_encodeTiled fn = nullptr;
-  if (!fn) {
+  static const PFN_encodeTiled fn = [] {        // initialised once, thread-safe (C++11 magic static)
     void* p = nullptr;
     cudaDriverEntryPointQueryResult qres;
     if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
         qres == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<PFN_encodeTiled>(p);
-  }
+      return reinterpret_cast<PFN_encodeTiled>(p);
+    return static_cast<PFN_encodeTiled>(nullptr);
+  }();
   return fn;
 }
 

@@ -392,7 +392,7 @@ int launch(const ConvGemmArgs& a, cudaStream_t st) {
     return fs2_fail_cuda(cudaErrorInvalidValue, "cuTensorMapEncodeTiled(A)");
   if (!make_tmap_bf16(&tmB, a.Wb, (uint64_t)planes * a.taps * a.N, (uint64_t)a.K, (uint64_t)a.K, BN))
     return fs2_fail_cuda(cudaErrorInvalidValue, "cuTensorMapEncodeTiled(W)");
-  static bool configured = false;
+  static std::atomic<bool> configured{false};   // handles on several host threads may race here: benign, but formally atomic
   const int smem = L::TOTAL + 1024;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(tc_conv_gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
