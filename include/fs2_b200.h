@@ -181,7 +181,8 @@ int fs2_mask_from_lengths(const int64_t* lens, int32_t B, int32_t max_len, uint8
  * src [B,S,C] fp32 (channel_major = 1: [B,C,S]); lens[B] int64, clamped to [0,S].  dst receives the valid rows of
  * utterance 0, 1, ... back to back: rows [offsets[b], offsets[b+1]) of a [sum lens, C] matrix (channel_major: utterance
  * b's block, dst + offsets[b]*C, is a [C, lens[b]] matrix).  offsets[B+1] int64 (device, may be NULL) = exclusive prefix
- * sum of the clamped lens.  dst must hold sum(lens)*C floats (B*S*C always suffices). */
+ * sum of the clamped lens.  dst must hold sum(lens)*C floats (B*S*C always suffices).  S == 0 (the degenerate T == 0
+ * batch): nothing is copied, offsets are all 0, src / dst may be NULL. */
 int fs2_pack_valid_rows(const float* src, const int64_t* lens, int32_t B, int32_t S, int32_t C, int32_t channel_major,
                         int64_t* offsets, float* dst, void* stream);
 /* replaces: `(wavs.cpu().numpy() * max_wav_value).astype("int16")` + `wavs[i][:lengths[i]]` (utils/model.py:77-86).

@@ -1022,6 +1022,10 @@ int fs2_pack_valid_rows(const float* src, const int64_t* lens, int32_t B, int32_
                         int64_t* offsets, float* dst, void* stream) {
   g_fs2_plain_next = 1;   // the first launch of an entry point is fully stream-ordered (fs2_common.cuh)
   if (B == 0) return FS2_OK;
+  if (S == 0 && B > 0) {   // no rows at all (degenerate T == 0 batch): every offset is 0; src / dst may be empty tensors (NULL)
+    if (offsets) FS2_CUDA_CHECK(cudaMemsetAsync(offsets, 0, sizeof(int64_t) * ((size_t)B + 1), reinterpret_cast<cudaStream_t>(stream)));
+    return FS2_OK;
+  }
   if (!src || !lens || !dst || B < 0 || B > 65535 || S < 0 || C <= 0 || (channel_major != 0 && channel_major != 1)) {
     char buf[256];
     snprintf(buf, sizeof buf, "fs2_pack_valid_rows: bad argument (src, lens, dst non-null; 0 <= B <= 65535; S >= 0; C > 0): "
@@ -1039,6 +1043,10 @@ int fs2_wav_to_int16(const float* wav, const int64_t* lens, int32_t B, int64_t N
                      int16_t* dst, void* stream) {
   g_fs2_plain_next = 1;   // the first launch of an entry point is fully stream-ordered (fs2_common.cuh)
   if (B == 0) return FS2_OK;
+  if (N == 0 && B > 0) {   // empty waveforms: every offset is 0
+    if (offsets) FS2_CUDA_CHECK(cudaMemsetAsync(offsets, 0, sizeof(int64_t) * ((size_t)B + 1), reinterpret_cast<cudaStream_t>(stream)));
+    return FS2_OK;
+  }
   if (!wav || !dst || B < 0 || B > 65535 || N < 0) {
     char buf[256];
     snprintf(buf, sizeof buf, "fs2_wav_to_int16: bad argument (wav, dst non-null; 0 <= B <= 65535; N >= 0): wav=%p dst=%p B=%d "

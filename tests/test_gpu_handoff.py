@@ -218,3 +218,24 @@ def test_synthesize_pipeline_equals_one_batch_at_a_time(model):
     assert first[2] is None and np.array_equal(first[1].mel[0], want[0][0][0]["mel"])
     with pytest.raises(ValueError):
         P.vocoder_infer(torch.zeros(1, 80, 4, device=DEV), voc, {"vocoder": {"model": "WaveGlow"}}, pc)
+
+
+def test_handoff_of_a_degenerate_batch(lib):
+    """All durations zero -> T == 0 (SURVEY.md section 8(a) note 6): empty per-utterance arrays, durations still reported."""
+    from smart_nar_fast_tts_b200 import pipeline as P
+    sd0 = dict(O.make_state_dict(0))
+    sd0["variance_adaptor.duration_predictor.linear_layer.bias"] = torch.full((1,), -20.0)
+    sd0["variance_adaptor.duration_predictor.linear_layer.weight"] = torch.zeros(1, 256)
+    m = build_model(sd0, O.STATS_NAN_BINS)
+    sp, tx, sl, L = O.make_inputs(3, 5, 9, seed=2)
+    for cm in (False, True):
+        m.set_mel_post_layout(cm)
+        pred, info = m.forward_with_info(sp.to(DEV), tx.to(DEV), sl.to(DEV), L)
+        assert pred[1].shape == (3, 0, 80) and info == {"T": 0, "frames": 0}
+        s = P.collect_samples(pred, info, sl.numpy())
+        want = H.synth_samples_data(to_np(pred))
+        for i, w in enumerate(want):
+            assert s.mel[i].shape == (80, 0) and s.pitch[i].shape == (0,) and np.array_equal(s.duration[i], w["duration"])
+        assert np.array_equal(s.mel_lens, np.zeros(3, np.int64)) and np.array_equal(s.src_lens, sl.numpy())
+    wavs = P.wavs_to_int16(torch.zeros(3, 0, device=DEV), 32768.0, np.zeros(3, np.int64))
+    assert [w.shape for w in wavs] == [(0,)] * 3
