@@ -37,7 +37,12 @@ class StreamedSynthesizer:
 
     Batches may hold host tensors (ideally pinned: the H2D copies are then asynchronous) or device tensors.  With
     `to_host=True` (every tensor) or `to_host=(1, 9)` (those positions of the 12-tuple; the rest stay on the device) the
-    worker copies results into pinned host memory: the D2H is part of the job and overlaps other streams' compute."""
+    worker copies results into pinned host memory: the D2H is part of the job and overlaps other streams' compute.
+
+    Device results are complete when `wait` returns (the worker synchronises its stream), but their memory belongs to
+    that stream's allocator pool: a caller that consumes them asynchronously on ANOTHER stream and drops them before that
+    work has run should call `tensor.record_stream(consumer_stream)` first (the usual torch multi-stream rule).
+    `close()` frees the per-stream engines (packed weights + workspaces) this synthesizer created inside the module."""
 
     def __init__(self, model, n_streams: int = 3, device: Optional[torch.device] = None):
         if n_streams < 1:
