@@ -17,4 +17,5 @@ run fwd_other test_gpu_forward "not golden"
 run props test_gpu_properties ""
 run streamed test_gpu_streamed ""
 run handoff test_gpu_handoff ""
-for f in ops tc_gemm tc_attn tc_stack fwd_golden fwd_other props streamed handoff; do echo "=== $f"; grep -E "^(FAILED|ERROR)|Error|error|assert|max\|err\||max\|dlog" gpurun_out/$f.log | head -n 24; done
+run operators test_gpu_operators ""
+for f in ops tc_gemm tc_attn tc_stack fwd_golden fwd_other props streamed handoff operators; do echo "=== $f"; grep -E "^(FAILED|ERROR)|Error|error|assert|max\|err\||max\|dlog" gpurun_out/$f.log | head -n 24; done
