@@ -42,12 +42,10 @@ def pad_1D(inputs: Sequence[np.ndarray], PAD: int = 0) -> np.ndarray:
 def collate(data: Sequence[tuple]):
     """dataset.py:182-191 (`TextDataset.collate_fn`): data = [(basename, speaker_id, phone ids, raw_text), ...] ->
     (ids, raw_texts, speakers, texts[B, Lmax], text_lens[B], max(text_lens))."""
-    ids = [d[0] for d in data]
-    speakers = np.array([d[1] for d in data])
-    texts = [np.asarray(d[2]) for d in data]
-    raw_texts = [d[3] for d in data]
-    text_lens = np.array([t.shape[0] for t in texts])
-    return ids, raw_texts, speakers, pad_1D(texts), text_lens, max(text_lens)
+    ids, speaker_ids, phones, raw_texts = (list(col) for col in zip(*data))
+    phones = [np.asarray(p) for p in phones]
+    text_lens = np.fromiter((p.shape[0] for p in phones), dtype=np.int64, count=len(phones))
+    return ids, raw_texts, np.array(speaker_ids), pad_1D(phones), text_lens, text_lens.max()
 
 
 def make_batches(items: Sequence[tuple], batch_size: int, sort_by_length: bool = True) -> Tuple[List[tuple], List[List[int]]]:
@@ -105,11 +103,11 @@ class SampleSet:
 
 
 def expand(values, durations):
-    """utils/tools.py:100-104."""
-    out = list()
-    for value, d in zip(values, durations):
-        out += [value] * max(0, int(d))
-    return np.array(out)
+    """utils/tools.py:100-104: values[i] repeated max(0, int(durations[i])) times."""
+    reps = np.maximum(np.trunc(np.asarray(durations, dtype=np.float64)).astype(np.int64), 0)
+    if reps.sum() == 0:
+        return np.array([])
+    return np.repeat(np.asarray(values), reps)
 
 
 def _host_lens(x, cap: int) -> Optional[np.ndarray]:
