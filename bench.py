@@ -1,35 +1,43 @@
 #!/usr/bin/env python
 """bench.py -- mel-frames/s of the FastSpeech2-align inference forward on B200 (BASELINE.json's metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c3|c5|c1] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c1|c2|c3|c4|c5] [--impl reference]
 
-One "step" = one forward of the hot path (FastSpeech2Align.forward, inference branch) over one synthetic
-batch.  Default workload = BASELINE.json configs[1] ("c2": batch 32, phoneme lengths 40..120, LJSpeech dims).
+One "step" = one forward of the hot path (FastSpeech2Align.forward, inference branch) over one synthetic batch.
 
---streams S (default 3): the job is a list of independent batches, as in the reference's own driver loop
-(`for batch in batchs`, synthesize.py:59-76); the K steps are submitted to smart_nar_fast_tts_b200.StreamedSynthesizer,
-which keeps S forwards in flight on S CUDA streams (one engine per stream; results bit-identical to sequential calls).
-The K steps are timed as ONE bracket (CUDA events, barrier + synchronize on both sides); with N > 1 GPUs every rank
-runs its own batches (32 utterances each: 32*N per step, weak scaling, no collective on the data path).  The same
-forward issued one at a time (per-step CUDA events, L2 flushed between steps) is reported in `sequential`.
---streams 1: one forward at a time; with N > 1 GPUs ONE batch of 32*N utterances is sharded contiguously across the
-ranks with the GLOBAL max_src_len and one all-reduce(max) of T between the two stages (ShardedSynthesizer).
+Workloads (BASELINE.json `configs`):  N = 1 defaults to c3 (batch 256, the roofline configuration: the largest one
+quoted for a single GPU); N > 1 defaults to c4 (ONE batch of 1024 utterances sharded over the N ranks: strong scaling).
 
-Printed JSON (one line, rank 0):
-  value        mel-frames/s, inputs resident in HBM, CUDA events around each step, max over ranks
-  e2e          same metric through the public module call with HOST (pinned) inputs: H2D of ids/lengths and D2H of
-               postnet mel + mel_lens inside the timed region
-  roofline     dominant kernel (decoder FFN conv k=9 GEMM, tcgen05): algorithmic FLOPs of the valid frames /
-               CUDA-event time of that kernel class measured live by the library's tracing (fs2_profile_*)
+N = 1
+  value      K steps submitted to StreamedSynthesizer (the reference's `for batch in batchs` loop, synthesize.py:59-76,
+             with `--streams` forwards in flight; inputs resident in HBM), timed as ONE bracket of exactly K steps
+             (CUDA events on the launching stream, synchronize on both sides).  The bracket is repeated until >= 0.6 s
+             of timed work has run; the MEDIAN bracket is reported (`config.timing` lists all of them).
+  sequential the same forward one call at a time on one stream, L2 flushed between steps.
+  e2e        the public pipeline: pinned HOST batches -> H2D -> forward -> `pipeline.collect_samples` (valid rows of
+             postnet mel / pitch / energy / durations packed on the device, ONE D2H into pinned memory: everything
+             the reference's `synth_samples` reads, utils/tools.py:156-171) -> host arrays, inside the timed bracket.
+  faithful   the same workload with the decoder / PostNet in the fp32-faithful f16x2 arithmetic (`--dec f16x2`).
+N > 1  (torchrun, one rank per GPU, NCCL)
+  value      every step = ShardedSynthesizer over this rank's shard of the c4 batch: stage 1, all-reduce(MAX) of T on
+             the device (inside the timed region), ONE read-back, stage 2; outputs stay resident on their rank.
+  gathered   the same plus the result gather to rank 0: `nccl` = one grouped NCCL send/recv of every tensor;
+             `peer` = mel / postnet mel written straight into rank 0's memory by the producing kernels' epilogues
+             (peer-mapped output pointers over NVLink), the small tensors by the grouped NCCL operation.
+  e2e        host shards in, packed host results out on every rank (as for N = 1, one forward at a time).
+
+Printed JSON (one line, rank 0): metric / value / unit / ... as the driver's contract asks, plus
+  roofline     dominant kernel (decoder FFN conv k=9 GEMM, tcgen05) AND the decoder FFT blocks as a whole: algorithmic
+               FLOPs of the valid frames / CUDA-event time measured live by the library's tracing (fs2_profile_*)
   cpu_baseline the CPU oracle (port of the reference algorithm, torch CPU fp32) timed on this box's host cores on a
                bounded sample of the same workload (rank 0, N = 1 only)
-  --impl reference : the reference's CPU implementation (oracle port; the Python reference itself cannot travel to the
-               GPU box) timed with all host threads; same metric / unit / config.
+  --impl reference : the reference's CPU implementation (oracle port) timed with all host threads; same metric / config.
 """
 from __future__ import annotations
 
 import argparse
 import json
+import math
 import os
 import statistics
 import subprocess
@@ -42,12 +50,14 @@ if ROOT not in sys.path:
 
 METRIC = "mel-frames/sec (batched synth)"
 UNIT = "mel-frames/s"
-WORKLOADS = {  # name: (batch per GPU, len_lo, len_hi, description)
+WORKLOADS = {  # name: (global batch, len_lo, len_hi, description)
     "c1": (1, 60, 60, "BASELINE configs[0]: 1 utterance, 60 phonemes"),
     "c2": (32, 40, 120, "BASELINE configs[1]: batch=32 synthetic phoneme seqs (len 40-120), LJSpeech model dims"),
-    "c3": (256, 40, 120, "BASELINE configs[2]: batch=256 synthetic, roofline capture"),
-    "c5": (64, 300, 300, "BASELINE configs[4]: long-form batch=64, 300-phoneme inputs"),
+    "c3": (256, 40, 120, "BASELINE configs[2]: batch=256 synthetic, 80-bin mel, 4-layer/2-head/256-dim FFT blocks, roofline capture"),
+    "c4": (1024, 40, 120, "BASELINE configs[3]: batch=1024 synthetic sharded across the GPUs via NCCL batch split"),
+    "c5": (64, 300, 300, "BASELINE configs[4]: long-form batch=64, 300-phoneme inputs (~2000 mel frames)"),
 }
+MIN_TIMED_S = 0.6
 # algorithmic FLOPs per VALID unit; 2 FLOP per MAC
 FLOP_FFN_W1 = 2 * 9 * 256 * 1024          # Conv1d(256->1024, k=9) per frame
 FLOP_DEC_FRAME = 23_068_672                # + 4096*T attention, per valid frame of the 4 decoder FFT blocks
@@ -67,20 +77,21 @@ class ClockSampler:
 
     def __init__(self, index: int):
         self.index, self.proc = index, None
+        self.result = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
 
     def __enter__(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms",
                                           "20", "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            time.sleep(0.1)     # first sample out before the timed region starts
         except OSError:
             self.proc = None
         return self
 
     def __exit__(self, *a):
-        self.result = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
         if self.proc is None:
             return
-        time.sleep(0.15)
+        time.sleep(0.05)
         self.proc.terminate()
         try:
             out, _ = self.proc.communicate(timeout=5)
@@ -115,10 +126,10 @@ def measured_peaks():
             "source": "fallback (B200_PROFILING.md)"}
 
 
-def make_batch(workload: str, n_shards: int):
+def make_batch(workload: str):
     from smart_nar_fast_tts_b200 import synthetic
     b, lo, hi, _ = WORKLOADS[workload]
-    return synthetic.make_inputs(b * n_shards, lo, hi, seed=1)
+    return synthetic.make_inputs(b, lo, hi, seed=1)
 
 
 # --------------------------------------------------------------------------------------------- reference arm
@@ -130,7 +141,7 @@ def cpu_forward_timed(workload: str, budget_s: float, steps: int, warmup: int, t
     import fs2_oracle as O
     torch.set_num_threads(threads)
     sd = O.make_state_dict(0)
-    speakers, texts, src_lens, L = make_batch(workload, 1)
+    speakers, texts, src_lens, L = make_batch(workload)
     B = texts.shape[0]
 
     def run(n):
@@ -167,7 +178,8 @@ def run_reference_arm(args):
     r = cpu_forward_timed(args.workload, 150.0, steps, warmup, threads)
     line = {
         "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
-        "warmup": warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+        "warmup": warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+        "scaling": "strong" if args.workload == "c4" else "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": args.workload, "description": WORKLOADS[args.workload][3],
                    "frames_per_step": r["frames_per_step"], "note": "reference algorithm on host CPU cores (torch CPU fp32 port: "
@@ -184,7 +196,7 @@ def run_b200_arm(args):
     import torch
     import torch.distributed as dist
     import smart_nar_fast_tts_b200 as pkg
-    from smart_nar_fast_tts_b200 import synthetic
+    from smart_nar_fast_tts_b200 import pipeline, synthetic
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -206,27 +218,22 @@ def run_b200_arm(args):
     # tcgen05 everywhere: f16x2 (2-term scaled fp16 split operands, fp32-faithful) for the encoder + variance predictors, whose
     # outputs are rounded to integer durations / bucket indices; plain bf16 for the decoder, mel linear and PostNet
     model.set_precision(args.enc, args.dec)
-    streamed = args.streams > 1
-    # streams == 1: one forward at a time; with N > 1 GPUs ONE batch of 32 N utterances is sharded across the ranks and T is
-    #               all-reduced (ShardedSynthesizer) -- bit-identical to the unsharded reference call.
-    # streams  > 1: the job is a LIST of independent batches, as in the reference's `for batch in batchs` loop
-    #               (synthesize.py:59-76): every rank runs its own batches on `streams` CUDA streams concurrently
-    #               (StreamedSynthesizer); no collective on the data path.
-    synth = pkg.ShardedSynthesizer(model) if (world > 1 and not streamed) else None
+    sharded = world > 1
+    streamed = args.streams > 1 and not sharded
+    synth = pkg.ShardedSynthesizer(model) if sharded else None
 
-    speakers, texts, src_lens, L = make_batch(args.workload, world)
-    per = texts.shape[0] // world
-    bounds = [(r * per, (r + 1) * per) for r in range(world)]
+    speakers, texts, src_lens, L = make_batch(args.workload)
+    B_global = texts.shape[0]
+    bounds = synth.bounds(src_lens) if sharded else [(0, B_global)]
     lo, hi = bounds[rank]
-    if streamed and world > 1:      # this rank's utterances form a batch of their own: its own max_src_len
-        L = int(src_lens[lo:hi].max())
-        texts = texts[:, :L]
-    # pinned host copies (e2e) and device-resident copies (value) of this rank's batch / shard
+    per = hi - lo
+    # pinned host copies (e2e) and device-resident copies (value) of this rank's shard; the GLOBAL max_src_len everywhere
     h_sp, h_tx, h_sl = (t[lo:hi].contiguous().pin_memory() for t in (speakers, texts, src_lens))
     d_sp, d_tx, d_sl = (t.to(dev) for t in (h_sp, h_tx, h_sl))
+    h2d_bytes = int(sum(t.numel() * t.element_size() for t in (h_sp, h_tx, h_sl)))
 
     def forward(sp, tx, sl):
-        return model(sp, tx, sl, L)       # with world > 1 model.t_max_hook all-reduces T (ShardedSynthesizer)
+        return model.forward_with_info(sp, tx, sl, L)       # world > 1: t_max_device_hook all-reduces T (ShardedSynthesizer)
 
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
 
@@ -236,7 +243,20 @@ def run_b200_arm(args):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    def timed_loop(fn, n):
+    def reduce(x, op):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=op)
+        return float(t.item())
+
+    def rmax(x):
+        return reduce(x, dist.ReduceOp.MAX if world > 1 else None)
+
+    def rsum(x):
+        return reduce(x, dist.ReduceOp.SUM if world > 1 else None)
+
+    def per_step_loop(fn, n):
         """n steps, CUDA events around each step on the launching stream, L2 flushed between steps (untimed)."""
         ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n)]
         barrier()
@@ -246,103 +266,159 @@ def run_b200_arm(args):
             fn()
             b.record()
         barrier()
-        return [a.elapsed_time(b) for a, b in ev]
+        return sum(a.elapsed_time(b) for a, b in ev) / n
 
-    out = None
+    def bracket(fn, n):
+        """EXACTLY n steps back to back inside one CUDA-event bracket; barrier + synchronize on both sides.  The working
+        set of a step (c3: 1.5 GB of activations) is far larger than the 126 MB L2, so no flush is needed in between."""
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        barrier()
+        return e0.elapsed_time(e1) / n
+
+    def rounds_of(measure, first_ms):
+        """Repeat a K-step bracket until MIN_TIMED_S of timed work has run; every rank runs the same number of rounds."""
+        n_rounds = max(1, min(40, math.ceil(MIN_TIMED_S * 1e3 / max(1e-3, rmax(first_ms) * steps)) - 1))
+        return [first_ms] + [measure() for _ in range(n_rounds)]
+
+    out = info = None
 
     def step_resident():
-        nonlocal out
-        out = forward(d_sp, d_tx, d_sl)
+        nonlocal out, info
+        out, info = forward(d_sp, d_tx, d_sl)
 
-    h_mel = h_lens = None
+    samples = None
 
     def step_e2e():
-        nonlocal out, h_mel, h_lens
+        """The public API with host buffers: H2D of the batch, the forward, the packed result hand-off to host arrays."""
+        nonlocal out, info, samples
         sp, tx, sl = (t.to(dev, non_blocking=True) for t in (h_sp, h_tx, h_sl))
-        out = forward(sp, tx, sl)
-        if h_mel is None or h_mel.shape != out[1].shape:
-            h_mel = torch.empty(out[1].shape, dtype=out[1].dtype).pin_memory()
-            h_lens = torch.empty(out[9].shape, dtype=out[9].dtype).pin_memory()
-        h_mel.copy_(out[1], non_blocking=True)
-        h_lens.copy_(out[9], non_blocking=True)
-        torch.cuda.current_stream(dev).synchronize()   # the caller owns the result only after the D2H completes
+        out, info = forward(sp, tx, sl)
+        samples = pipeline.collect_samples(out, info, src_lens_host=h_sl)   # ends with its one stream synchronisation
 
     for _ in range(warmup):
         step_resident()
+    torch.cuda.synchronize(dev)
     frames_local = int(out[9].sum().item())
     T = int(out[1].shape[1])
-    seq = None
-    if not streamed:
-        launches0 = model.launch_count
-        with ClockSampler(local_rank) as clk:
-            t_res = timed_loop(step_resident, steps)
-        launches = model.launch_count - launches0
-        for _ in range(3):
-            step_e2e()
-        t_e2e = timed_loop(step_e2e, steps)
-        ms_res_local, ms_e2e_local = sum(t_res) / steps, sum(t_e2e) / steps
-    else:
-        # one forward at a time first (reported as "sequential"), then the streamed job
-        t_res = timed_loop(step_resident, steps)
-        for _ in range(3):
-            step_e2e()
-        t_e2e = timed_loop(step_e2e, steps)
-        seq = (sum(t_res) / steps, sum(t_e2e) / steps)
+    mel_lens_local = out[9].tolist()
+    frames = int(rsum(float(frames_local)))
+    launches_fwd0 = model.launch_count
+    step_resident()
+    torch.cuda.synchronize(dev)
+    launches_per_forward = model.launch_count - launches_fwd0
+
+    seq_ms = per_step_loop(step_resident, steps)
+    for _ in range(3):
+        step_e2e()
+    d2h_bytes = int(samples.d2h_bytes)
+    seq_e2e_ms = per_step_loop(step_e2e, steps)
+    extra = {}
+
+    if streamed:
         pipe = pkg.StreamedSynthesizer(model, n_streams=args.streams, device=dev)
         pipe.warm_up((d_sp, d_tx, d_sl, L))
 
-        def streamed_loop(batch, n, to_host):
+        def post(o, i):
+            return pipeline.collect_samples(o, i, src_lens_host=h_sl).d2h_bytes
+
+        def streamed_bracket(batch, n, e2e):
             """n forwards of `batch` in flight on the worker streams; device time from the common start event to the
             completion of the last job (every job ends with its stream synchronised)."""
             barrier()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            jobs = [pipe.submit(batch, to_host=to_host, start_event=e0) for _ in range(n)]
+            jobs = [pipe.submit(batch, start_event=e0, post=post if e2e else None) for _ in range(n)]
             for j in jobs:
                 pipe.wait(j)
                 j.result = None      # consume and drop: live results would turn every later forward into fresh cudaMallocs
             e1.record()
             barrier()
-            return e0.elapsed_time(e1)
+            return e0.elapsed_time(e1) / n
 
         for _ in range(2):           # primes the per-stream allocator pools (device and pinned host) as well
-            streamed_loop((d_sp, d_tx, d_sl, L), max(warmup, 3 * args.streams), False)
-            streamed_loop((h_sp, h_tx, h_sl, L), max(warmup, 3 * args.streams), (1, 9))
+            streamed_bracket((d_sp, d_tx, d_sl, L), max(warmup, 3 * args.streams), False)
+            streamed_bracket((h_sp, h_tx, h_sl, L), max(warmup, 3 * args.streams), True)
         launches0 = model.launch_count
         with ClockSampler(local_rank) as clk:
-            ms_res_local = streamed_loop((d_sp, d_tx, d_sl, L), steps, False) / steps
-        launches = model.launch_count - launches0
-        ms_e2e_local = streamed_loop((h_sp, h_tx, h_sl, L), steps, (1, 9)) / steps
+            res_rounds = rounds_of(lambda: streamed_bracket((d_sp, d_tx, d_sl, L), steps, False),
+                                   streamed_bracket((d_sp, d_tx, d_sl, L), steps, False))
+        launches = (model.launch_count - launches0) / len(res_rounds)
+        e2e_rounds = rounds_of(lambda: streamed_bracket((h_sp, h_tx, h_sl, L), steps, True),
+                               streamed_bracket((h_sp, h_tx, h_sl, L), steps, True))
         pipe.close()
+        launches_e2e_extra = 4     # fs2_pack_valid_rows x 4 per batch
+    else:
+        launches0 = model.launch_count
+        with ClockSampler(local_rank) as clk:
+            res_rounds = rounds_of(lambda: bracket(step_resident, steps), bracket(step_resident, steps))
+        launches = (model.launch_count - launches0) / len(res_rounds)
+        e2e_rounds = rounds_of(lambda: bracket(step_e2e, steps), bracket(step_e2e, steps))
+        launches_e2e_extra = 4
+
+    if sharded:
+        # ---- where the results end up: resident (value), gathered to rank 0 by NCCL, or written there by the kernels
+        B_tot, T_cap = B_global, T + 8
+
+        def step_gather_nccl():
+            nonlocal out
+            out = synth(d_sp_full, d_tx_full, d_sl_full, L, gather="root", bounds=bounds)
+
+        d_sp_full, d_tx_full, d_sl_full = (t.to(dev) for t in (speakers, texts, src_lens))
+        for _ in range(3):
+            step_gather_nccl()
+        g_nccl = rounds_of(lambda: bracket(step_gather_nccl, steps), bracket(step_gather_nccl, steps))
+        extra["gathered"] = {"nccl": {"ms_per_step": rmax(statistics.median(g_nccl)),
+                                      "how": "stage 2 into local tensors, then ONE grouped NCCL send/recv of all result tensors to rank 0"}}
+        try:
+            synth.enable_peer_gather(B_tot, T_cap, 80, dst=0)
+
+            def step_gather_peer():
+                nonlocal out
+                out = synth(d_sp_full, d_tx_full, d_sl_full, L, gather="peer", bounds=bounds)
+
+            for _ in range(3):
+                step_gather_peer()
+            g_peer = rounds_of(lambda: bracket(step_gather_peer, steps), bracket(step_gather_peer, steps))
+            extra["gathered"]["peer"] = {"ms_per_step": rmax(statistics.median(g_peer)),
+                                         "how": "mel / postnet mel stored into rank 0's memory by the mel_linear / last PostNet "
+                                                "convolution epilogues (peer-mapped pointers, NVLink), small tensors by NCCL"}
+        except Exception as e:   # symmetric memory unavailable: report, keep the line
+            extra["gathered"]["peer"] = {"unavailable": f"{type(e).__name__}: {e}"[:300]}
+        for k, v in extra["gathered"].items():
+            if "ms_per_step" in v:
+                v["value"] = frames / (v["ms_per_step"] * 1e-3)
+        extra["gathered"]["bytes_to_rank0"] = int(2 * (B_tot - per if rank == 0 else 0) * T * 80 * 4)
 
     # per-kernel-class device time (tracing on, separate pass over the same steps)
     model.profile_enable(True)
-    timed_loop(step_resident, steps)
+    per_step_loop(step_resident, steps)
     prof = model.profile_read()
     model.profile_enable(False)
 
-    def reduce_max(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+    # fp32-faithful decoder arithmetic on the same workload (one forward at a time)
+    faithful = None
+    if not args.no_faithful and args.dec != "f16x2":
+        model.set_precision(args.enc, "f16x2")
+        for _ in range(3):
+            step_resident()
+        f_ms = per_step_loop(step_resident, steps)
+        model.profile_enable(True)
+        per_step_loop(step_resident, max(3, steps // 4))
+        fprof = model.profile_read()
+        model.profile_enable(False)
+        f_dec_ms = sum(v["ms"] for n, v in fprof.items() if n.startswith("dec.")) / max(3, steps // 4)
+        model.set_precision(args.enc, args.dec)
+        faithful = (rmax(f_ms), f_dec_ms)
 
-    def reduce_sum(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        return float(t.item())
-
-    ms_res = reduce_max(ms_res_local)
-    ms_e2e = reduce_max(ms_e2e_local)
-    if seq is not None:
-        seq = (reduce_max(seq[0]), reduce_max(seq[1]))
-    frames = int(reduce_sum(float(frames_local)))
-    mel_lens_local = out[9].tolist()
-    flops_local = algorithmic_flops(h_sl.tolist(), mel_lens_local)
-    flops = reduce_sum(float(flops_local))
+    ms_res = rmax(statistics.median(res_rounds))
+    ms_e2e = rmax(statistics.median(e2e_rounds))
+    seq_ms, seq_e2e_ms = rmax(seq_ms), rmax(seq_e2e_ms)
+    flops = rsum(float(algorithmic_flops(h_sl.tolist(), mel_lens_local)))
 
     if rank == 0:
         peaks = measured_peaks()
@@ -352,55 +428,72 @@ def run_b200_arm(args):
         k_flops = FLOP_FFN_W1 * frames_local                     # algorithmic: valid frames only
         achieved = k_flops / (k_ms * 1e-3) / 1e12 if k_ms > 0 else 0.0
         total_prof = sum(v["ms"] for v in prof.values()) or 1.0
-        traffic, dec_layer_bytes = None, None
+        traffic, dec_layer_bytes, traffic_src = None, None, None
         tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
         if os.path.exists(tp):
             try:
-                rec = json.load(open(tp)).get(args.workload, {})
+                j = json.load(open(tp))
+                rec = j.get(args.workload, {})
                 traffic = rec.get("dec.ffn_w1_bytes_per_launch")
                 dec_layer_bytes = rec.get("decoder_layer_bytes")
+                traffic_src = j.get("source")
             except Exception:
                 traffic, dec_layer_bytes = None, None
         dec_ms = sum(v["ms"] for n, v in prof.items() if n.startswith("dec.")) / steps
         dec_flops = sum(t * (FLOP_DEC_FRAME + 4096 * t) for t in mel_lens_local)
+        dec_tflops = dec_flops / (dec_ms * 1e-3) / 1e12 if dec_ms > 0 else 0.0
+        wl = WORKLOADS[args.workload]
         line = {
             "metric": METRIC, "value": frames / (ms_res * 1e-3), "unit": UNIT, "n_gpus": world, "steps": steps,
-            "warmup": warmup, "ms_per_step": ms_res, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "warmup": warmup, "ms_per_step": ms_res, "higher_is_better": True,
+            "scaling": "strong" if args.workload == "c4" else "weak", "vs_baseline": None,
             "dtype": f"{args.dec} (decoder, mel linear, PostNet) + {args.enc} (encoder, variance predictors); tcgen05, "
                      "fp32 accumulation in TMEM", "data": "synthetic",
-            "config": {"workload": args.workload, "description": WORKLOADS[args.workload][3], "batch_per_gpu": per,
-                       "global_batch": per * world, "max_src_len": L, "T_max": T, "frames_per_step": frames,
+            "config": {"workload": args.workload, "description": wl[3], "batch_per_gpu": per,
+                       "global_batch": B_global, "max_src_len": L, "T_max": T, "frames_per_step": frames,
                        "weights": "random init (numpy PCG64 seed 0), duration head biased to ~7.67 frames/phoneme",
-                       "streams": args.streams,
-                       "l2": ("256 MiB flush buffer written between timed steps (untimed)" if not streamed else
-                              f"no flush possible between overlapping forwards: {args.streams} concurrent forwards with private "
-                              "workspaces, aggregate working set several times the 126 MB L2 (the 'sequential' object is "
-                              "measured with the flush)"),
-                       "parallelism": (("single GPU" if world == 1 else f"utterance shards x{world}, T all-reduced") if not streamed
-                                       else f"{world} GPU(s) x {args.streams} streams, independent batches "
-                                            "(StreamedSynthesizer), no collective")},
+                       "streams": args.streams if streamed else 1,
+                       "timing": {"rounds_ms_per_step": [round(x, 5) for x in res_rounds], "steps_per_round": steps,
+                                  "timed_s_total": round(sum(res_rounds) * steps * 1e-3, 3),
+                                  "reported": "median round (every round times exactly K steps in one CUDA-event bracket)"},
+                       "l2": "every step streams > 1 GB of activations through the 126 MB L2 (inputs larger than L2); the "
+                             "'sequential' object is measured with a 256 MiB flush buffer written between steps",
+                       "parallelism": (f"{world} ranks x NCCL: contiguous utterance shards of ONE batch, all-reduce(MAX) of T "
+                                       "on the device inside every step; outputs resident per rank" if sharded else
+                                       (f"1 GPU x {args.streams} streams, independent batches (StreamedSynthesizer)" if streamed
+                                        else "1 GPU, one forward at a time"))},
             "e2e": {"value": frames / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
-                    "h2d_bytes_per_step": int(sum(t.numel() * t.element_size() for t in (h_sp, h_tx, h_sl))),
-                    "d2h_bytes_per_step": int(h_mel.numel() * h_mel.element_size() + h_lens.numel() * h_lens.element_size())},
-            "gpu_launches": int(launches),
-            "sequential": (None if seq is None else
-                           {"value": frames / (seq[0] * 1e-3), "ms_per_step": seq[0], "e2e_value": frames / (seq[1] * 1e-3),
-                            "e2e_ms_per_step": seq[1], "note": "one forward at a time on one stream, L2 flushed between steps"}),
+                    "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
+                    "what": "pinned host batch -> H2D -> forward -> collect_samples (valid rows of postnet mel, pitch, energy, "
+                            "durations packed on the device, one D2H into pinned memory) -> per-utterance host arrays",
+                    "rounds_ms_per_step": [round(x, 5) for x in e2e_rounds]},
+            "gpu_launches": int(round(launches)),
+            "launches_per_forward": int(launches_per_forward),
+            "sequential": {"value": frames / (seq_ms * 1e-3), "ms_per_step": seq_ms, "e2e_value": frames / (seq_e2e_ms * 1e-3),
+                           "e2e_ms_per_step": seq_e2e_ms, "note": "one forward at a time on one stream, L2 flushed between steps"},
             "tflops_algorithmic": flops / (ms_res * 1e-3) / 1e12,
             "roofline": {"kernel": "tc_conv_gemm_staged_kernel as dec.ffn_w1 (Conv1d 256->1024 k=9 + ReLU, tcgen05 bf16)",
                          "bound": "tensor", "achieved": achieved, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
                          "frac": achieved / peaks["bf16_tflops"], "peak_source": peaks["source"] + ", burst",
-                         "peak_sustained": peaks["bf16_tflops_sustained"], "traffic": traffic,
+                         "peak_sustained": peaks["bf16_tflops_sustained"],
+                         "frac_of_sustained": (achieved / peaks["bf16_tflops_sustained"]) if peaks["bf16_tflops_sustained"] else None,
+                         "traffic": traffic, "traffic_source": traffic_src,
                          "ms_per_launch": k_ms, "launches_per_step": k["launches"] / steps,
                          "share_of_step": k["ms"] / total_prof,
                          "algorithmic_flops_per_launch": k_flops,
+                         # the north-star figure: all four decoder FFT blocks (QKV, attention, fc + LN, FFN conv k=9, conv k=1 + LN)
+                         "decoder_fft_blocks": {"achieved": dec_tflops, "frac": dec_tflops / peaks["bf16_tflops"],
+                                                "frac_of_sustained": (dec_tflops / peaks["bf16_tflops_sustained"])
+                                                if peaks["bf16_tflops_sustained"] else None,
+                                                "ms_per_step": dec_ms, "algorithmic_flops_per_step": dec_flops,
+                                                "share_of_step": dec_ms * steps / total_prof},
                          "how": "fs2_profile_* CUDA events on the launching stream, separate traced pass of the same steps"},
             # BASELINE.json's second figure, "decoder HBM GB/s vs peak": algorithmic bytes of the 4 decoder FFT blocks
             # (16 KB per valid frame = 4 layers x 2 sub-layers x (1 KB in + 1 KB out) fp32, + 47.2 MB of
             # weights read once) over their measured time; "measured" = DRAM bytes of one layer's five kernels from the
             # committed ncu captures (profiles/roofline_traffic.json) x 4 layers, when present
-            "decoder": {"ms_per_step": dec_ms, "tflops": dec_flops / (dec_ms * 1e-3) / 1e12 if dec_ms > 0 else 0.0,
-                        "frac_of_bf16_peak": (dec_flops / (dec_ms * 1e-3) / 1e12 / peaks["bf16_tflops"]) if dec_ms > 0 else 0.0,
+            "decoder": {"ms_per_step": dec_ms, "tflops": dec_tflops,
+                        "frac_of_bf16_peak": dec_tflops / peaks["bf16_tflops"],
                         "hbm_gbs_algorithmic": ((16384.0 * frames_local + 47.2e6) / (dec_ms * 1e-3) / 1e9) if dec_ms > 0 else 0.0,
                         "hbm_gbs_measured": (dec_layer_bytes * 4 / (dec_ms * 1e-3) / 1e9) if (dec_ms > 0 and dec_layer_bytes) else None,
                         "hbm_peak_gbs": peaks["hbm_gbs"],
@@ -408,6 +501,17 @@ def run_b200_arm(args):
             "kernel_ms_per_step": {n: round(v["ms"] / steps, 5) for n, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])},
             "clocks": clk.result,
         }
+        if faithful is not None:
+            f_ms, f_dec_ms = faithful
+            f_dec_tflops = dec_flops / (f_dec_ms * 1e-3) / 1e12 if f_dec_ms > 0 else 0.0
+            line["faithful"] = {"dtype": f"f16x2 decoder / PostNet (2 scaled fp16 terms, 3 tcgen05 products per MAC: fp32-faithful, "
+                                         f"mel within 2e-3 abs of the fp32 reference) + {args.enc} encoder",
+                                "value": frames / (f_ms * 1e-3), "ms_per_step": f_ms, "decoder_ms_per_step": f_dec_ms,
+                                "decoder_tflops_algorithmic": f_dec_tflops,
+                                "decoder_frac_of_bf16_peak": f_dec_tflops / peaks["bf16_tflops"],
+                                "note": "one forward at a time, L2 flushed between steps; 3 MMAs per algorithmic MAC, so the "
+                                        "tensor pipe does 3x the counted FLOPs"}
+        line.update(extra)
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
             r = cpu_forward_timed(args.workload, 20.0, 2, 1, threads, fit_steps=True)   # ~10-20 s of CPU work
@@ -426,13 +530,17 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default=None, choices=sorted(WORKLOADS),
+                    help="default: c3 on one GPU, c4 (one batch of 1024 sharded over the ranks) on several")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-faithful", action="store_true")
     ap.add_argument("--streams", type=int, default=3,
-                    help="CUDA streams running independent forwards concurrently (1 = one forward at a time)")
+                    help="N = 1: CUDA streams running independent forwards concurrently (1 = one forward at a time)")
     ap.add_argument("--enc", default="f16x2", choices=["fp32", "bf16x3", "f16x2", "bf16"], help="encoder + predictor arithmetic")
     ap.add_argument("--dec", default="bf16", choices=["fp32", "bf16x3", "f16x2", "bf16"], help="decoder + PostNet arithmetic")
     args = ap.parse_args()
+    if args.workload is None:
+        args.workload = "c3" if args.gpus == 1 else "c4"
     if args.impl == "reference":
         run_reference_arm(args)
     else:

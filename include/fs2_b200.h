@@ -99,6 +99,13 @@ const char* fs2_version(void);
  * `*.num_batches_tracked` are accepted and ignored.  Missing inference keys -> error. */
 int fs2_load_weights(fs2_handle* h, const fs2_weight_desc* descs, int32_t n);
 
+/* Lets `h` run on the packed weights `src` already loaded instead of its own copy (same device, same dims).  The
+ * weights are read-only after fs2_load_weights, so the handles of several CUDA streams -- the reference's
+ * `for batch in batchs` loop (synthesize.py:59-76) run concurrently -- share ONE copy (~300 MB with every operand
+ * format) instead of one per stream.  The block is reference-counted: it is freed when the last handle that uses it
+ * is destroyed or loads / shares other weights.  Workspaces stay private to each handle. */
+int fs2_share_weights(fs2_handle* h, const fs2_handle* src);
+
 /* encoder_prec covers txt_encoder + all three variance predictors (the discrete
  * decisions: durations, pitch/energy buckets); decoder_prec covers mel_decoder,
  * mel_linear and PostNet.  Defaults: F16X2 / BF16. */

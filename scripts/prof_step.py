@@ -20,7 +20,7 @@ ap.add_argument("--dec", default="bf16")
 a = ap.parse_args()
 dev = torch.device("cuda", 0)
 m = synthetic.build_module(synthetic.make_state_dict(0), synthetic.STATS_NAN_BINS, device=dev).set_precision(a.enc, a.dec)
-sp, tx, sl, L = bench.make_batch(a.workload, 1)
+sp, tx, sl, L = bench.make_batch(a.workload)
 sp, tx, sl = sp.to(dev), tx.to(dev), sl.to(dev)
 for _ in range(a.warmup + a.steps - 1):
     out = m(sp, tx, sl, L)

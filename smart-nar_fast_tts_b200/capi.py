@@ -55,6 +55,7 @@ SIGNATURES = {
     "fs2_last_error": (C.c_char_p, [_P]),
     "fs2_version": (C.c_char_p, []),
     "fs2_load_weights": (C.c_int, [_P, C.POINTER(WeightDesc), _I]),
+    "fs2_share_weights": (C.c_int, [_P, _P]),
     "fs2_set_precision": (C.c_int, [_P, _I, _I]),
     "fs2_set_row_packing": (C.c_int, [_P, _I]),
     "fs2_set_mel_post_layout": (C.c_int, [_P, _I]),

@@ -10,6 +10,7 @@
 #include <string.h>
 #include <stdlib.h>
 #include <map>
+#include <memory>
 #include <string>
 #include <vector>
 
@@ -50,6 +51,28 @@ struct PredW {
 
 }  // namespace
 
+// Raw + packed weights of one model: read-only once fs2_load_weights has returned, so any number of handles on the
+// same device (one per CUDA stream: StreamedSynthesizer) can run on ONE copy (fs2_share_weights).  Freed with the last
+// handle that references it.
+struct fs2_weights {
+  int device = 0;
+  std::map<std::string, RawT> raw;
+  std::vector<void*> owned;  // packed weight allocations
+  std::vector<FftW> enc, dec;
+  PredW pred[3];
+  GemmW mel_linear;
+  std::vector<GemmW> postnet;
+  ~fs2_weights() {
+    int cur = -1;
+    cudaGetDevice(&cur);
+    cudaSetDevice(device);
+    cudaDeviceSynchronize();   // kernels of another handle that still read these buffers
+    for (auto& kv : raw) cudaFree(kv.second.d);
+    for (void* p : owned) cudaFree(p);
+    if (cur >= 0) cudaSetDevice(cur);
+  }
+};
+
 struct fs2_handle {
   fs2_dims dims{};
   int device = 0;
@@ -58,12 +81,7 @@ struct fs2_handle {
   int mel_post_cm = 0;  // stage 2 / fs2_op_mel_postnet write mel_post channel-major [B, n_mel, T] (vocoder hand-off)
   bool loaded = false;
   std::string err;
-  std::map<std::string, RawT> raw;
-  std::vector<void*> owned;  // packed weight allocations
-  std::vector<FftW> enc, dec;
-  PredW pred[3];
-  GemmW mel_linear;
-  std::vector<GemmW> postnet;
+  std::shared_ptr<fs2_weights> w;   // possibly shared with other handles (fs2_share_weights)
   float* pe_ext[2] = {nullptr, nullptr};  // on-the-fly tables for S > max_seq_len (encoder / decoder)
   int pe_ext_n[2] = {0, 0};
   std::map<std::string, std::pair<void*, size_t>> ws;  // growable workspace
@@ -169,13 +187,13 @@ struct ProfScope {
 #define PROF(name) ProfScope _prof_scope(h, name, st)
 
 const float* raw_ptr(fs2_handle* h, const std::string& k) {
-  auto it = h->raw.find(k);
-  return it == h->raw.end() ? nullptr : it->second.d;
+  auto it = h->w->raw.find(k);
+  return it == h->w->raw.end() ? nullptr : it->second.d;
 }
 
 int need(fs2_handle* h, const std::string& k, std::initializer_list<int64_t> shape, const float** out) {
-  auto it = h->raw.find(k);
-  if (it == h->raw.end()) return h->fail(FS2_ERR_MISSING_WEIGHT, "missing state_dict key: " + k);
+  auto it = h->w->raw.find(k);
+  if (it == h->w->raw.end()) return h->fail(FS2_ERR_MISSING_WEIGHT, "missing state_dict key: " + k);
   std::vector<int64_t> want(shape);
   if (it->second.shape != want) {
     std::string m = "bad shape for " + k + ": got [";
@@ -193,7 +211,7 @@ int dev_alloc(fs2_handle* h, T** p, size_t count) {
   void* q = nullptr;
   cudaError_t e = cudaMalloc(&q, sizeof(T) * (count ? count : 1));
   if (e != cudaSuccess) return h->cuda_fail(e, "cudaMalloc(packed weight)");
-  h->owned.push_back(q);
+  h->w->owned.push_back(q);
   *p = reinterpret_cast<T*>(q);
   return FS2_OK;
 }
@@ -210,7 +228,7 @@ int build_gemm(fs2_handle* h, GemmW& g, const std::vector<std::string>& wkeys, c
   RCHECK(dev_alloc(h, &g.bias, (size_t)g.N));
   for (int i = 0; i < parts; ++i) {
     const float* w = nullptr;
-    if (taps == 1 && h->raw.count(wkeys[i]) && h->raw[wkeys[i]].shape.size() == 2)
+    if (taps == 1 && h->w->raw.count(wkeys[i]) && h->w->raw[wkeys[i]].shape.size() == 2)
       RCHECK(need(h, wkeys[i], {N_each, K}, &w));
     else
       RCHECK(need(h, wkeys[i], {N_each, K, taps}, &w));
@@ -379,7 +397,7 @@ int run_fft_stack(fs2_handle* h, std::vector<FftW>& Ls, int l0, int l1, int prec
                   cudaStream_t st) {
   const int D = h->dims.d_model, F = h->dims.d_ffn, H = h->dims.n_heads, dk = D / H;
   const size_t R = (size_t)lay.R_cap;
-  const std::string tg = (&Ls == &h->enc) ? "enc." : "dec.";
+  const std::string tg = (&Ls == &h->w->enc) ? "enc." : "dec.";
   WS(float, y, "fft.y", R * D);
   if (prec == FS2_PREC_FP32) {
     WS(float, qkv, "fft.qkv", R * 3 * D);
@@ -479,7 +497,7 @@ int run_fft_stack(fs2_handle* h, std::vector<FftW>& Ls, int l0, int l1, int prec
 int run_predictor(fs2_handle* h, PredW& P, int prec, const float* x, const bf16* xb, const RowLayout& lay,
                   float* out_user, cudaStream_t st, bool out_cleared = false) {
   const int C = h->dims.vp_filter;
-  const std::string tg = &P == &h->pred[0] ? "dur." : &P == &h->pred[1] ? "pitch." : "energy.";
+  const std::string tg = &P == &h->w->pred[0] ? "dur." : &P == &h->w->pred[1] ? "pitch." : "energy.";
   const size_t R = (size_t)lay.R_cap;
   WS(float, p1, "pred.h1", R * C);
   bf16* p1b = nullptr;
@@ -533,18 +551,18 @@ int run_mel_postnet(fs2_handle* h, int prec, const float* dec, const bf16* decb,
     WS(float, t1, "pn.a", R * P); pa = t1;
     WS(float, t2, "pn.b", R * P); pb = t2;
   }
-  ConvGemmArgs a = base_args(h->mel_linear, lay);
+  ConvGemmArgs a = base_args(h->w->mel_linear, lay);
   a.A = dec; a.Ab = decb; a.epi = EPI_BIAS; a.mask_mode = MASK_GRID; a.dst_off = pn.off; a.dst_R_cap = pn.R_cap;
   a.out = melg; a.ldo = M; a.out_b = melb; a.ldob = M; a.out_user = mel; a.ldu = M;
   RCHECK(run_gemm(h, prec, a, st, "mel_linear"));
   {
     PROF("rows.fill_padded");
-    HCHECK(rowops_fill_padded_rows(h->mel_linear.bias, M, lay, pn, melg, melb, (int)np, mel, st));
+    HCHECK(rowops_fill_padded_rows(h->w->mel_linear.bias, M, lay, pn, melg, melb, (int)np, mel, st));
   }
 
   const float* in_f = melg; const bf16* in_b = melb;
   for (int i = 0; i < NL; ++i) {
-    a = base_args(h->postnet[i], pn);
+    a = base_args(h->w->postnet[i], pn);
     a.A = in_f; a.Ab = in_b; a.mask_mode = MASK_GRID;
     if (i < NL - 1) {
       a.epi = EPI_TANH;
@@ -622,8 +640,7 @@ void fs2_destroy(fs2_handle* h) {
   if (!h) return;
   cudaSetDevice(h->device);
   cudaDeviceSynchronize();
-  for (auto& kv : h->raw) cudaFree(kv.second.d);
-  for (void* p : h->owned) cudaFree(p);
+  h->w.reset();   // frees the weights when this was the last handle using them
   for (auto& kv : h->ws) cudaFree(kv.second.first);
   for (int i = 0; i < 2; ++i) if (h->pe_ext[i]) cudaFree(h->pe_ext[i]);
   for (auto& p : h->prof_pending) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
@@ -663,12 +680,10 @@ int fs2_load_weights(fs2_handle* h, const fs2_weight_desc* descs, int32_t n) {
   if (!h || !descs || n <= 0) return h ? h->fail(FS2_ERR_INVALID, "null/empty weight list") : FS2_ERR_INVALID;
   HCHECK(cudaSetDevice(h->device));
   cudaStream_t st = 0;
-  // drop anything loaded before
-  for (auto& kv : h->raw) cudaFree(kv.second.d);
-  h->raw.clear();
-  for (void* p : h->owned) cudaFree(p);
-  h->owned.clear();
+  // a fresh weight block: handles that share the previous one keep running on it until they load or share again
   h->loaded = false;
+  h->w = std::make_shared<fs2_weights>();
+  h->w->device = h->device;
   h->have_stage1 = false;
 
   for (int i = 0; i < n; ++i) {
@@ -685,8 +700,8 @@ int fs2_load_weights(fs2_handle* h, const fs2_weight_desc* descs, int32_t n) {
     cudaError_t e = cudaMemcpyAsync(t.d, w.data, sizeof(float) * (size_t)t.numel,
                                     w.on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st);
     if (e != cudaSuccess) { cudaFree(t.d); return h->cuda_fail(e, "cudaMemcpyAsync(weight)"); }
-    if (h->raw.count(name)) cudaFree(h->raw[name].d);
-    h->raw[name] = t;
+    if (h->w->raw.count(name)) cudaFree(h->w->raw[name].d);
+    h->w->raw[name] = t;
   }
   HCHECK(cudaStreamSynchronize(st));
 
@@ -700,14 +715,14 @@ int fs2_load_weights(fs2_handle* h, const fs2_weight_desc* descs, int32_t n) {
   RCHECK(need(h, "variance_adaptor.energy_bins", {d.n_bins - 1}, &t));
   RCHECK(need(h, "variance_adaptor.pitch_embedding.weight", {d.n_bins, D}, &t));
   RCHECK(need(h, "variance_adaptor.energy_embedding.weight", {d.n_bins, D}, &t));
-  h->enc.assign(d.n_enc_layers, FftW());
-  h->dec.assign(d.n_dec_layers, FftW());
-  for (int l = 0; l < d.n_enc_layers; ++l) RCHECK(build_fft(h, h->enc[l], "txt_encoder.layer_stack." + std::to_string(l), st));
-  for (int l = 0; l < d.n_dec_layers; ++l) RCHECK(build_fft(h, h->dec[l], "mel_decoder.layer_stack." + std::to_string(l), st));
+  h->w->enc.assign(d.n_enc_layers, FftW());
+  h->w->dec.assign(d.n_dec_layers, FftW());
+  for (int l = 0; l < d.n_enc_layers; ++l) RCHECK(build_fft(h, h->w->enc[l], "txt_encoder.layer_stack." + std::to_string(l), st));
+  for (int l = 0; l < d.n_dec_layers; ++l) RCHECK(build_fft(h, h->w->dec[l], "mel_decoder.layer_stack." + std::to_string(l), st));
   const char* which[3] = {"duration", "pitch", "energy"};
-  for (int i = 0; i < 3; ++i) RCHECK(build_pred(h, h->pred[i], std::string("variance_adaptor.") + which[i] + "_predictor", st));
-  RCHECK(build_gemm(h, h->mel_linear, {"mel_linear.weight"}, {"mel_linear.bias"}, d.n_mel, D, 1, nullptr, nullptr, st));
-  h->postnet.assign(d.pn_layers, GemmW());
+  for (int i = 0; i < 3; ++i) RCHECK(build_pred(h, h->w->pred[i], std::string("variance_adaptor.") + which[i] + "_predictor", st));
+  RCHECK(build_gemm(h, h->w->mel_linear, {"mel_linear.weight"}, {"mel_linear.bias"}, d.n_mel, D, 1, nullptr, nullptr, st));
+  h->w->postnet.assign(d.pn_layers, GemmW());
   for (int i = 0; i < d.pn_layers; ++i) {
     const int cin = i == 0 ? d.n_mel : d.pn_dim, cout = i == d.pn_layers - 1 ? d.n_mel : d.pn_dim;
     const std::string p = "postnet.convolutions." + std::to_string(i);
@@ -721,10 +736,22 @@ int fs2_load_weights(fs2_handle* h, const fs2_weight_desc* descs, int32_t n) {
     RCHECK(dev_alloc(h, &scale, (size_t)cout));
     RCHECK(dev_alloc(h, &fb, (size_t)cout));
     HCHECK(rowops_bn_fold(cb, g, b, mean, var, cout, 1e-5f, scale, fb, st));
-    RCHECK(build_gemm(h, h->postnet[i], {p + ".0.conv.weight"}, {}, cout, cin, d.pn_kernel, scale, fb, st));
+    RCHECK(build_gemm(h, h->w->postnet[i], {p + ".0.conv.weight"}, {}, cout, cin, d.pn_kernel, scale, fb, st));
   }
   HCHECK(cudaStreamSynchronize(st));
   h->loaded = true;
+  return FS2_OK;
+}
+
+int fs2_share_weights(fs2_handle* h, const fs2_handle* src) {
+  if (!h || !src) return h ? h->fail(FS2_ERR_INVALID, "share_weights: null handle") : FS2_ERR_INVALID;
+  if (h == src) return FS2_OK;
+  if (!src->loaded || !src->w) return h->fail(FS2_ERR_STATE, "share_weights: the source handle has no weights loaded");
+  if (h->device != src->device) return h->fail(FS2_ERR_INVALID, "share_weights: handles live on different devices");
+  if (memcmp(&h->dims, &src->dims, sizeof(fs2_dims)) != 0) return h->fail(FS2_ERR_INVALID, "share_weights: dims differ");
+  h->w = src->w;
+  h->loaded = true;
+  h->have_stage1 = false;
   return FS2_OK;
 }
 
@@ -773,18 +800,18 @@ static int stage1_enqueue(fs2_handle* h, const int64_t* texts, const int64_t* sr
     HCHECK(rowops_embed_pe(texts, raw_ptr(h, "txt_encoder.src_word_emb.weight"), pe, d.vocab, lay, D, x, xb,
                            planes_of(h->prec_enc), nullptr, st));
   }
-  RCHECK(run_fft_stack(h, h->enc, 0, d.n_enc_layers, h->prec_enc, x, xb, lay, st));
+  RCHECK(run_fft_stack(h, h->w->enc, 0, d.n_enc_layers, h->prec_enc, x, xb, lay, st));
   // modules.py:116 duration predictor on the encoder output
-  RCHECK(run_predictor(h, h->pred[0], h->prec_enc, x, xb, lay, log_d, st, src_mask != nullptr));
+  RCHECK(run_predictor(h, h->w->pred[0], h->prec_enc, x, xb, lay, log_d, st, src_mask != nullptr));
   // modules.py:117-126 phoneme-level variants
   if (d.pitch_phoneme_level) {
-    RCHECK(run_predictor(h, h->pred[1], h->prec_enc, x, xb, lay, pitch_ph, st));
+    RCHECK(run_predictor(h, h->w->pred[1], h->prec_enc, x, xb, lay, pitch_ph, st));
     HCHECK(rowops_variance_embed(pitch_ph, p_control, raw_ptr(h, "variance_adaptor.pitch_bins"), d.n_bins,
                                  raw_ptr(h, "variance_adaptor.pitch_embedding.weight"), nullptr, x, xb,
                                  planes_of(h->prec_enc), lay, D, nullptr, st));
   }
   if (d.energy_phoneme_level) {
-    RCHECK(run_predictor(h, h->pred[2], h->prec_enc, x, xb, lay, energy_ph, st));
+    RCHECK(run_predictor(h, h->w->pred[2], h->prec_enc, x, xb, lay, energy_ph, st));
     HCHECK(rowops_variance_embed(energy_ph, e_control, raw_ptr(h, "variance_adaptor.energy_bins"), d.n_bins,
                                  raw_ptr(h, "variance_adaptor.energy_embedding.weight"), nullptr, x, xb,
                                  planes_of(h->prec_enc), lay, D, nullptr, st));
@@ -893,14 +920,14 @@ int fs2_forward_stage2(fs2_handle* h, int32_t T, float p_control, float e_contro
   RCHECK(position_table(h, 1, T, &pe, st));
   // modules.py:139-149 frame-level pitch then energy (energy sees x + pitch embedding)
   if (pitch_fl) {
-    RCHECK(run_predictor(h, h->pred[1], h->prec_enc, x, xb, lay, pitch, st, mel_mask != nullptr));
+    RCHECK(run_predictor(h, h->w->pred[1], h->prec_enc, x, xb, lay, pitch, st, mel_mask != nullptr));
     PROF("rows.variance_embed");
     HCHECK(rowops_variance_embed(pitch, p_control, raw_ptr(h, "variance_adaptor.pitch_bins"), d.n_bins,
                                  raw_ptr(h, "variance_adaptor.pitch_embedding.weight"), energy_fl ? nullptr : pe, x, xb,
                                  planes_of(energy_fl ? h->prec_enc : h->prec_dec), lay, D, nullptr, st));
   }
   if (energy_fl) {
-    RCHECK(run_predictor(h, h->pred[2], h->prec_enc, x, xb, lay, energy, st, mel_mask != nullptr));
+    RCHECK(run_predictor(h, h->w->pred[2], h->prec_enc, x, xb, lay, energy, st, mel_mask != nullptr));
     // fused: + energy embedding, + decoder positional encoding (Models.py:231-233), shadow for the decoder
     PROF("rows.variance_embed");
     HCHECK(rowops_variance_embed(energy, e_control, raw_ptr(h, "variance_adaptor.energy_bins"), d.n_bins,
@@ -911,7 +938,7 @@ int fs2_forward_stage2(fs2_handle* h, int32_t T, float p_control, float e_contro
     HCHECK(rowops_add_pe(x, pe, lay, D, st));
     HCHECK(make_shadow(x, R * D, h->prec_dec, xb, st));
   }
-  RCHECK(run_fft_stack(h, h->dec, 0, d.n_dec_layers, h->prec_dec, x, xb, lay, st));
+  RCHECK(run_fft_stack(h, h->w->dec, 0, d.n_dec_layers, h->prec_dec, x, xb, lay, st));
   RCHECK(run_mel_postnet(h, h->prec_dec, x, xb, lay, mel, mel_post, st));
   return FS2_OK;
 }
@@ -1086,7 +1113,7 @@ int fs2_op_fft_stack(fs2_handle* h, int32_t stack, int32_t l0, int32_t l1, int32
                      const int64_t* lens, int32_t B, int32_t S, float* out, void* stream) {
   g_fs2_plain_next = 1;   // the first launch of an entry point is fully stream-ordered (fs2_common.cuh)
   if (!h || !h->loaded) return FS2_ERR_STATE;
-  std::vector<FftW>& Ls = stack == 0 ? h->enc : h->dec;
+  std::vector<FftW>& Ls = stack == 0 ? h->w->enc : h->w->dec;
   if (!x || !lens || !out || B <= 0 || S <= 0 || l0 < 0 || l1 > (int)Ls.size() || l0 > l1 ||
       prec < FS2_PREC_FP32 || prec > FS2_PREC_F16X2)
     return h->fail(FS2_ERR_INVALID, "bad argument");
@@ -1126,7 +1153,7 @@ int fs2_op_variance_predictor(fs2_handle* h, int32_t which, const float* x, cons
   if (h->prec_enc != FS2_PREC_FP32) { WS(bf16, t, "op.xb", (size_t)planes_of(h->prec_enc) * R * D); xb = t; }
   HCHECK(rowops_to_grid(x, lay, D, xg, D, 0, nullptr, st));
   HCHECK(make_shadow(xg, R * D, h->prec_enc, xb, st));
-  return run_predictor(h, h->pred[which], h->prec_enc, xg, xb, lay, out, st);
+  return run_predictor(h, h->w->pred[which], h->prec_enc, xg, xb, lay, out, st);
 }
 
 int fs2_op_variance_embed(fs2_handle* h, int32_t which, float* pred, float control, float* x, int32_t B, int32_t S,

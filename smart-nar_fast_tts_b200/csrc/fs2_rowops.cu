@@ -213,11 +213,15 @@ __global__ void __launch_bounds__(1024) duration_scan_kernel(const float* log_d,
       // int() truncates toward zero; guard the conversion against inf/NaN/huge values
       v = (f > 0.f) ? (f < 1.0e6f ? (int)f : 1000000) : 0;
     }
+    // the running sums saturate at SAT (far above the 65535 frames an utterance may have, far below INT_MAX): garbage
+    // log-durations (inf, untrained weights) must end in a loud "too many frames" error of stage 2, never in a wrapped,
+    // plausible-looking length.  Every partial sum is clamped, so no int32 addition below can overflow (2 * SAT < 2^31).
+    constexpr int SAT = 1 << 30;
     int x = v;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
       const int y = __shfl_up_sync(0xffffffffu, x, o);
-      if (lane >= o) x += y;
+      if (lane >= o) x = min(x + y, SAT);
     }
     if (lane == 31) warp_tot[w] = x;
     __syncthreads();
@@ -226,13 +230,13 @@ __global__ void __launch_bounds__(1024) duration_scan_kernel(const float* log_d,
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) {
         const int y = __shfl_up_sync(0xffffffffu, t, o);
-        if (lane >= o) t += y;
+        if (lane >= o) t = min(t + y, SAT);
       }
       warp_tot[lane] = t;  // inclusive totals
     }
     __syncthreads();
     const int carry = carry_s;
-    const int incl = carry + x + (w > 0 ? warp_tot[w - 1] : 0);
+    const int incl = min(min(carry + x, SAT) + (w > 0 ? warp_tot[w - 1] : 0), SAT);
     if (i < L) cum[(size_t)b * L + i] = incl;
     __syncthreads();
     if (tid == 1023) carry_s = incl;
@@ -244,7 +248,12 @@ __global__ void __launch_bounds__(1024) duration_scan_kernel(const float* log_d,
     if (mel_lens32) mel_lens32[b] = total;
     if (tmax) {               // tmax[0] = longest utterance (frames), tmax[1] = frames of the whole batch (saturating)
       atomicMax(tmax, total);
-      atomicAdd(tmax + 1, total);
+      int old = *(volatile int*)(tmax + 1), assumed;
+      do {
+        assumed = old;
+        const long long sum = (long long)assumed + total;
+        old = atomicCAS(tmax + 1, assumed, sum > 0x7fffffffll ? 0x7fffffff : (int)sum);
+      } while (old != assumed);
     }
   }
 }

@@ -12,6 +12,7 @@ from __future__ import annotations
 import ctypes as C
 import json
 import os
+import threading
 from collections import OrderedDict
 from typing import Callable, Optional
 
@@ -171,6 +172,7 @@ class FastSpeech2Align(nn.Module):
         # thread-safe and its workspace is stream-ordered, so concurrent forwards on different streams (streamed.py) each
         # get their own.  {stream pointer: {"h": handle, "stamp": weight stamp}}
         self._engines = {}
+        self._load_lock = threading.Lock()   # one thread packs the weights; the engines of other streams then share them
         self._handle_device: Optional[torch.device] = None
         self._cached_ws = None
         self._precision = (PREC_F16X2, PREC_BF16)
@@ -181,6 +183,10 @@ class FastSpeech2Align(nn.Module):
         # tensor {T_max, frames} in place on the current stream BEFORE the forward's single read-back.
         self.t_max_hook: Optional[Callable[[int, torch.device], int]] = None
         self.t_max_device_hook: Optional[Callable[[torch.Tensor], None]] = None
+        # output_allocator(name, shape, dtype, device) -> contiguous tensor or None (None = torch.empty): where stage 2
+        # writes "mel" / "mel_post" / "pitch" / "energy" / "mel_masks".  sharding.PeerGather returns views of ANOTHER
+        # GPU's memory here, so the last PostNet convolution's epilogue stores its tiles straight over NVLink.
+        self.output_allocator: Optional[Callable[[str, tuple, torch.dtype, torch.device], Optional[torch.Tensor]]] = None
 
     # ------------------------------------------------------------------ engine plumbing
     def set_precision(self, encoder: str = "f16x2", decoder: str = "bf16") -> "FastSpeech2Align":
@@ -237,6 +243,17 @@ class FastSpeech2Align(nn.Module):
         for e in getattr(self, "_engines", {}).values():
             e["stamp"] = None
 
+    def refresh_weights(self) -> "FastSpeech2Align":
+        """Re-copy and re-pack the parameters into every engine at its next forward.
+
+        The engines run on PRIVATE packed copies of the weights (bf16 / split planes, BatchNorm folded).  Changes made
+        through the tracked tensor API (`load_state_dict`, `.to()`, in-place ops on the parameters, replacing a
+        parameter's storage) are detected automatically from every tensor's (data_ptr, _version).  Writes that bypass
+        version counting -- `p.data.copy_()`, `p.data.add_()` (EMA swaps, weight surgery), raw pointer writes -- are
+        NOT visible: call this afterwards."""
+        self._invalidate()
+        return self
+
     def _apply(self, fn, *a, **k):  # .to() / .cuda() / .float(): parameter storage changes
         self._invalidate()
         return super()._apply(fn, *a, **k)
@@ -279,26 +296,41 @@ class FastSpeech2Align(nn.Module):
             lib.check(lib.fs2_set_mel_post_layout(eng["h"], int(self._mel_post_cm)), eng["h"])
             self._engines[key] = eng
         ws = self._weights()
-        stamp = (ws[0][1].data_ptr(), ws[-1][1].data_ptr(), sum(t._version for _, t in ws))
+        # every tensor's storage address and version counter: catches a replaced middle tensor and any tracked in-place
+        # update; `.data` writes bypass the counter by design -> refresh_weights()
+        stamp = tuple((t.data_ptr(), t._version) for _, t in ws)
         if stamp != eng["stamp"]:
-            descs = (WeightDesc * len(ws))()
-            keep = []
-            for i, (k, t) in enumerate(ws):
-                if t.device != device:
-                    raise RuntimeError(f"parameter {k} lives on {t.device}, inputs on {device}")
-                tt = t.detach()
-                if tt.dtype != torch.float32 or not tt.is_contiguous():
-                    tt = tt.float().contiguous()
-                keep.append(tt)
-                descs[i].name = k.encode()
-                descs[i].data = tt.data_ptr()
-                descs[i].ndim = tt.dim()
-                for j, s in enumerate(tt.shape):
-                    descs[i].shape[j] = s
-                descs[i].on_device = 1
-            torch.cuda.current_stream(device).synchronize()
-            lib.check(lib.fs2_load_weights(eng["h"], descs, len(ws)), eng["h"])
-            eng["stamp"] = stamp
+            # another stream's engine already holds these weights packed: run on ITS copy (read-only, ref-counted in the
+            # library) instead of packing a second one -- a 3-stream StreamedSynthesizer keeps one ~300 MB block, not three
+            donor = next((e for e in list(self._engines.values()) if e is not eng and e["stamp"] == stamp), None)
+            if donor is not None:
+                lib.check(lib.fs2_share_weights(eng["h"], donor["h"]), eng["h"])
+                eng["stamp"] = stamp
+                return lib, eng["h"]
+            with self._load_lock:
+                donor = next((e for e in list(self._engines.values()) if e is not eng and e["stamp"] == stamp), None)
+                if donor is not None:     # another thread packed them while this one waited
+                    lib.check(lib.fs2_share_weights(eng["h"], donor["h"]), eng["h"])
+                    eng["stamp"] = stamp
+                    return lib, eng["h"]
+                descs = (WeightDesc * len(ws))()
+                keep = []
+                for i, (k, t) in enumerate(ws):
+                    if t.device != device:
+                        raise RuntimeError(f"parameter {k} lives on {t.device}, inputs on {device}")
+                    tt = t.detach()
+                    if tt.dtype != torch.float32 or not tt.is_contiguous():
+                        tt = tt.float().contiguous()
+                    keep.append(tt)
+                    descs[i].name = k.encode()
+                    descs[i].data = tt.data_ptr()
+                    descs[i].ndim = tt.dim()
+                    for j, s_ in enumerate(tt.shape):
+                        descs[i].shape[j] = s_
+                    descs[i].on_device = 1
+                torch.cuda.current_stream(device).synchronize()
+                lib.check(lib.fs2_load_weights(eng["h"], descs, len(ws)), eng["h"])
+                eng["stamp"] = stamp
         return lib, eng["h"]
 
     def __del__(self):
@@ -386,11 +418,20 @@ class FastSpeech2Align(nn.Module):
                 if self.t_max_hook is not None:
                     T = int(self.t_max_hook(T, dev))
             n_mel = self._dims.n_mel
-            mel = torch.empty(B, T, n_mel, **f32)
-            mel_post = torch.empty(B, n_mel, T, **f32) if self._mel_post_cm else torch.empty(B, T, n_mel, **f32)
-            pitch = ph_p if ph_p is not None else torch.empty(B, T, **f32)
-            energy = ph_e if ph_e is not None else torch.empty(B, T, **f32)
-            mel_masks = torch.empty(B, T, device=dev, dtype=torch.bool)
+
+            def alloc(name, shape, dtype=torch.float32):
+                t = self.output_allocator(name, shape, dtype, dev) if self.output_allocator is not None else None
+                if t is None:
+                    return torch.empty(shape, device=dev, dtype=dtype)
+                if tuple(t.shape) != tuple(shape) or t.dtype != dtype or not t.is_contiguous() or not t.is_cuda:
+                    raise ValueError(f"output_allocator returned an unusable tensor for {name!r}")
+                return t
+
+            mel = alloc("mel", (B, T, n_mel))
+            mel_post = alloc("mel_post", (B, n_mel, T) if self._mel_post_cm else (B, T, n_mel))
+            pitch = ph_p if ph_p is not None else alloc("pitch", (B, T))
+            energy = ph_e if ph_e is not None else alloc("energy", (B, T))
+            mel_masks = alloc("mel_masks", (B, T), torch.bool)
             lib.check(lib.fs2_forward_stage2(
                 h, T, float(p_control), float(e_control), mel.data_ptr(), mel_post.data_ptr(),
                 None if ph_p is not None else pitch.data_ptr(), None if ph_e is not None else energy.data_ptr(),

@@ -54,16 +54,25 @@ class StreamedSynthesizer:
         self.n_streams = n_streams
         self._streams = [torch.cuda.Stream(self.device) for _ in range(n_streams)]
         self._queue: "queue.Queue[Optional[_Job]]" = queue.Queue()
-        self._threads = [threading.Thread(target=self._worker, args=(i,), daemon=True) for i in range(n_streams)]
+        # the workers hold the queue, their stream and the model -- NOT this object: a synthesizer that is dropped without
+        # close() is still collected, and its __del__ stops the threads and releases the engines
+        self._threads = [threading.Thread(target=self._worker, args=(self._queue, self._streams[i], model, self.device),
+                                          daemon=True) for i in range(n_streams)]
         for t in self._threads:
             t.start()
 
+    def __enter__(self) -> "StreamedSynthesizer":
+        return self
+
+    def __exit__(self, *exc) -> None:
+        self.close()
+
     # ------------------------------------------------------------------ worker
-    def _worker(self, i: int) -> None:
-        stream = self._streams[i]
-        torch.cuda.set_device(self.device)
+    @staticmethod
+    def _worker(jobs: "queue.Queue[Optional[_Job]]", stream: torch.cuda.Stream, model, device: torch.device) -> None:
+        torch.cuda.set_device(device)
         while True:
-            job = self._queue.get()
+            job = jobs.get()
             if job is None:
                 return
             try:
@@ -71,8 +80,8 @@ class StreamedSynthesizer:
                     if job.start_event is not None:
                         stream.wait_event(job.start_event)
                     sp, tx, sl, L = job.batch
-                    sp, tx, sl = (t.to(self.device, non_blocking=True) for t in (sp, tx, sl))
-                    out, info = self.model.forward_with_info(sp, tx, sl, L, **job.kw)
+                    sp, tx, sl = (t.to(device, non_blocking=True) for t in (sp, tx, sl))
+                    out, info = model.forward_with_info(sp, tx, sl, L, **job.kw)
                     if job.post is not None:      # hand-off work (pipeline.py) runs on this job's stream as well
                         out = job.post(out, info)
                     elif job.to_host:
@@ -137,16 +146,17 @@ class StreamedSynthesizer:
             raise errs[0]
 
     def close(self) -> None:
-        """Stop the workers and free the engines (packed weights + workspaces) of this synthesizer's streams."""
+        """Stop the workers (after the jobs already queued) and free the engines (workspaces; the packed weights are
+        shared with the module's other engines) of this synthesizer's streams.  Blocks until every worker has exited: an
+        engine must not be released under a forward that is still running.  Idempotent."""
         if not self._threads:
             return
         for _ in self._threads:
             self._queue.put(None)
         for t in self._threads:
-            t.join(timeout=5)
-        alive = any(t.is_alive() for t in self._threads)
+            t.join()
         self._threads = []
-        if not alive and hasattr(self.model, "release_engine"):
+        if hasattr(self.model, "release_engine"):
             for st in self._streams:
                 st.synchronize()
                 self.model.release_engine(st)

@@ -63,3 +63,56 @@ def test_first_forward_on_a_side_stream_while_the_default_stream_is_busy(lib):
             assert torch.equal(got[i], want[i]), f"trial {trial}: output {i} differs on a fresh side-stream engine"
         torch.cuda.synchronize()
         m.release_engine(side)
+
+
+def test_engines_of_several_streams_share_one_weight_copy(lib):
+    """fs2_share_weights: the engine of every further stream runs on the packed weights the first one loaded.  A second
+    engine must cost (far) less device memory than the ~300 MB weight block, and results must not change -- also after
+    the module's parameters changed (version-counted update -> one engine re-packs, the others re-share) and after the
+    engine that packed them is gone (the block is reference-counted)."""
+    sd = O.make_state_dict(0)
+    m = build_model(sd, O.STATS_NAN_BINS)
+    sp, tx, sl, L = O.make_inputs(4, 10, 30, seed=8)
+    args = (sp.to(DEV), tx.to(DEV), sl.to(DEV), L)
+    torch.cuda.synchronize()
+    free0 = torch.cuda.mem_get_info()[0]
+    want = m(*args)
+    torch.cuda.synchronize()
+    free1 = torch.cuda.mem_get_info()[0]
+    first_cost = free0 - free1
+    assert first_cost > 200 << 20                               # raw fp32 + every packed operand format
+    sides = [torch.cuda.Stream() for _ in range(2)]
+    outs = []
+    for s in sides:
+        with torch.cuda.stream(s):
+            outs.append(m(*args))
+        s.synchronize()
+    free2 = torch.cuda.mem_get_info()[0]
+    assert free1 - free2 < 64 << 20, f"two more engines cost {(free1 - free2) >> 20} MiB: weights were copied, not shared"
+    for o in outs:
+        for i in (0, 1, 2, 3, 4, 5, 9):
+            assert torch.equal(o[i], want[i])
+    # tracked in-place update: every engine must see the new weights (one re-pack, then sharing again)
+    with torch.no_grad():
+        m.mel_linear.bias.add_(0.25)
+    want2 = m(*args)
+    assert not torch.equal(want2[0], want[0])
+    with torch.cuda.stream(sides[0]):
+        got2 = m(*args)
+    sides[0].synchronize()
+    assert torch.equal(got2[0], want2[0]) and torch.equal(got2[1], want2[1])
+    # an untracked `.data` write is invisible until refresh_weights()
+    m.mel_linear.bias.data.add_(0.25)
+    stale = m(*args)
+    assert torch.equal(stale[0], want2[0])
+    m.refresh_weights()
+    fresh = m(*args)
+    assert torch.allclose(fresh[0], want2[0] + 0.25, atol=1e-5)
+    # the block outlives the engine that packed it
+    m.release_engine(torch.cuda.current_stream())
+    with torch.cuda.stream(sides[1]):
+        again = m(*args)
+    sides[1].synchronize()
+    assert again[1].shape == fresh[1].shape
+    for s in sides:
+        m.release_engine(s)
