@@ -16,6 +16,7 @@ import torch  # noqa: E402
 
 import fs2_oracle as O  # noqa: E402
 from helpers import build_model, max_abs, rel_rms  # noqa: E402
+from test_gpu_forward import check_against  # noqa: E402
 
 CONFIGS = {"c1": (1, 60, 60), "c2": (32, 40, 120), "c3": (256, 40, 120), "c5": (64, 300, 300)}
 
@@ -38,7 +39,14 @@ def main():
             torch.cuda.synchronize()
             out = [o.cpu() if o is not None else None for o in out]
             valid = ~ref[7]
-            rec = {"config": name, "enc": enc, "dec": dec, "frames": int(ref[9].sum()), "T": int(ref[0].shape[1]),
+            try:      # gate check + errors over the utterances without a pitch / energy bucket flip
+                st = check_against(list(ref[:10]), out[:10], sd, dec)
+                kept = {"gates": "pass", "flips": st["flips"], "kept_utterances": st["kept_utterances"],
+                        "mel_rel_rms_kept": st["mel"][0], "mel_max_kept": st["mel"][1],
+                        "post_rel_rms_kept": st["postnet_mel"][0], "post_max_kept": st["postnet_mel"][1]}
+            except AssertionError as e:
+                kept = {"gates": f"FAIL: {e}"[:200]}
+            rec = {**kept, "config": name, "enc": enc, "dec": dec, "frames": int(ref[9].sum()), "T": int(ref[0].shape[1]),
                    "oracle_s": round(t_cpu, 2),
                    "d_rounded_equal": bool(torch.equal(out[5] + 0, ref[5] + 0)), "mel_lens_equal": bool(torch.equal(out[9], ref[9])),
                    "log_d_max": max_abs(out[4], ref[4]), "pitch_max": max_abs(out[2], ref[2]), "energy_max": max_abs(out[3], ref[3]),

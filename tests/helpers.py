@@ -12,6 +12,13 @@ import torch
 
 import fs2_oracle as O
 
+# Parity gates of the mel outputs on every row of every utterance without a pitch / energy bucket flip (mels are O(1);
+# profiles/parity_r2*.jsonl holds the measured errors of every BASELINE config the gates are derived from):
+#   fp32-faithful decoder arithmetic (fp32 FFMA, bf16x3, f16x2): max abs 2e-3  (measured <= 1e-5: the gate is the
+#     tolerance SURVEY.md 8(d) allows an fp32 re-implementation with a different summation order, not a fit)
+#   bf16 decoder (the benchmarked default): relative RMS and max abs <= 2x the worst measured value
+GATES = {"faithful_max_abs": 2e-3, "bf16_rel_rms": 8e-3, "bf16_max_abs": 2.5e-2}
+
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 

@@ -14,7 +14,7 @@ import pytest
 import torch
 
 import fs2_oracle as O
-from helpers import build_model, max_abs, rel_rms
+from helpers import build_model, max_abs
 from test_gpu_forward import check_against, run_model
 
 pytestmark = pytest.mark.gpu
@@ -41,12 +41,9 @@ def test_config_against_oracle(lib, sd, case, dec_prec):
     name, inputs, ref = case
     m = build_model(sd, O.STATS_NAN_BINS).set_precision("f16x2", dec_prec)
     out = run_model(m, *inputs)
-    flips = check_against(ref, out[:10], sd, dec_prec)
-    valid = ~ref[7]
-    print(f"\n{name} dec={dec_prec}: frames {int(ref[9].sum())} T {ref[0].shape[1]} bucket flips {flips} "
-          f"max|dlog_d| {max_abs(out[4], ref[4]):.2e} "
-          f"mel relRMS {rel_rms(out[0], ref[0]):.2e} max {max_abs(out[0], ref[0]):.2e} "
-          f"postnet relRMS {rel_rms(out[1], ref[1]):.2e} max {max_abs(out[1], ref[1]):.2e} "
-          f"(valid rows: postnet max {max_abs(out[1][valid], ref[1][valid]):.2e})")
+    st = check_against(ref, out[:10], sd, dec_prec)
+    print(f"\n{name} dec={dec_prec}: frames {int(ref[9].sum())} T {ref[0].shape[1]} bucket flips {st['flips']} "
+          f"(utterances compared: {st['kept_utterances']} of {ref[0].shape[0]}) max|dlog_d| {max_abs(out[4], ref[4]):.2e} "
+          f"mel relRMS {st['mel'][0]:.2e} max {st['mel'][1]:.2e} postnet relRMS {st['postnet_mel'][0]:.2e} max {st['postnet_mel'][1]:.2e}")
     if name == "c5":
         assert ref[0].shape[1] > 1000      # the T > max_seq_len branch (Models.py:218-225) is really exercised
