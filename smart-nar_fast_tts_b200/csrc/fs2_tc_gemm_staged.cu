@@ -23,16 +23,6 @@
 // tc_conv_gemm_staged_launch and profiles/experiments/README.md).  A LayerNorm epilogue needs the whole 256-column row: with 128-wide tiles the two CTAs that share a row
 // tile form a 2-CTA cluster and swap their partial (sum, sum of squares) through distributed shared memory
 // (st.shared::cluster + remote mbarrier arrive with release / acquire at cluster scope), one exchange per tile.
-// Epilogue v3 (round 2; profiles/r1r: the k = 1 GEMMs ran at 38-66 % of HBM peak with the tensor pipe 7-29 % busy: their
-// epilogues were chains of exposed latencies, not bandwidth):
-//   * residual + LayerNorm tiles: the fp32 residual arrives through a DEDICATED 2-deep ring per column group, fed by
-//     its own producer warp (warp 11) that runs ahead across tile boundaries -- the first residual chunks of tile i+1 land
-//     while tile i is still being normalised and stored; the ring is released per warp through mbarriers (no named
-//     barrier in pass 1); output staging has its own buffers, so loads and stores no longer take turns on shared memory;
-//   * QKV tiles: the whole [128 x 128] half tile of a group is staged at once (32 KB, two 128B-swizzled atoms, or the
-//     transposed V^T block) and leaves as 2 TMA stores: 2 named barriers per tile instead of 8;
-//   * bias / LayerNorm parameters are read as float4; the per-row length (row mask) is loaded where it is first needed
-//     instead of at the top of the tile, and not at all for MASK_GRID epilogues.
 #include "fs2_tc_common.cuh"
 #include "../../include/fs2_b200.h"
 #include <stdlib.h>
@@ -42,9 +32,7 @@ namespace {
 using namespace tc;
 
 constexpr int BM = 128, BN_MAX = 256, BKE = 64;
-constexpr int NUM_THREADS = 384;                          // warp 0 TMA (A), warp 1 MMA, warp 2 TMA (B), warps 3-10 epilogue,
-                                                          // warp 11 TMA (fp32 residual ring of the LayerNorm epilogues)
-constexpr int RES_WARP = 11;
+constexpr int NUM_THREADS = 352;                          // warp 0 TMA (A), warp 1 MMA, warp 2 TMA (B), warps 3-10 epilogue
 constexpr int EPI_T0 = 96;                                // first epilogue thread
 constexpr int A_BYTES = BM * BKE * 2;                     // 16 KB per k-block; the weight k-block is bn x 128 B (32 / 16 KB)
 constexpr int MAX_A = 4, MAX_B = 4;                       // ring depths (a k-step consumes one stage of each ring)
@@ -55,17 +43,13 @@ constexpr int CH_B16 = BM * 32 * 2;                       //  8 KB: [128 rows][3
 //   B ring          nB x 32 / 16 KB   (weight k-blocks of a 256 / 128-wide tile, own producer warp)
 //   group g region  wide plan: F0, F1 (2 x 16 KB fp32 staging / residual) + B staging (out_planes x 8 KB)
 //                   deep plan: B staging only
-//                   res_ring plan (v3 LayerNorm + residual): R0, R1 (residual ring) + F (fp32 staging) + B (8 KB)
-//                   qkv_full plan (v3 QKV): 32 KB half-tile staging
 //   params          bias[2][128], ln_g[256], ln_b[256], stats[2 parities][2 groups][128] float2,
 //                   xstat[2 parities][128] float2 (the peer CTA's LayerNorm partial sums, written remotely)
 //   barriers
 constexpr int PARAM_BYTES = (2 * 128 + 256 + 256) * 4 + 2 * 2 * 128 * 8 + 2 * 128 * 8;
-constexpr int NUM_BARS = 2 * MAX_A + 2 * MAX_B + 4 + 8 + 2;
+constexpr int NUM_BARS = 2 * MAX_A + 2 * MAX_B + 4 + 4 + 2;
 struct Plan {
   int nA, nB, wide, grp_bytes;
-  int res_ring;        // EPI_RES_LN v3: group region = R0 | R1 (residual ring, warp 11) | F (fp32 out staging) | B (8 KB plane staging)
-  int qkv_full;        // EPI_QKV v3: group region = one [128 x 128] 16-bit half tile (32 KB), staged once per tile and plane
   int serial_planes;   // deep plan with several operand planes out: the planes go through ONE 8 KB staging tile in turn
   int bn;              // tile width: 256 or 128 columns
   int ln_pair;         // LayerNorm over a 2-CTA cluster (bn == 128): partial row statistics are exchanged through DSMEM
@@ -79,35 +63,6 @@ __constant__ int s_combo_a[6] = {0, 2, 1, 0, 1, 0};       // bf16x3 cross produc
 __constant__ int s_combo_b[6] = {2, 0, 1, 1, 0, 0};
 __constant__ int s_combo2_a[3] = {0, 1, 0};               // f16x2 cross products (hi*lo, lo*hi, hi*hi)
 __constant__ int s_combo2_b[3] = {1, 0, 0};
-
-// 32 consecutive floats of shared memory (16-byte aligned) as eight float4 loads
-__device__ __forceinline__ void lds32(const float* p, float (&o)[32]) {
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const float4 t = reinterpret_cast<const float4*>(p)[j];
-    o[4 * j] = t.x; o[4 * j + 1] = t.y; o[4 * j + 2] = t.z; o[4 * j + 3] = t.w;
-  }
-}
-// operand plane `pl` of `np` (1: bf16; 2: f16x2 hi / lo of the scaled value; 3: bf16x3 hi / mid / lo) of two neighbouring
-// values, packed into one 32-bit word (first value in the low half)
-__device__ __forceinline__ uint32_t plane_pack2(float a, float b, int pl, int np) {
-  if (np == 1) return pack_bf16x2(a, b);
-  if (np == 2) {
-    uint32_t h, l;
-    split2h_pair(a, b, h, l);
-    return pl == 0 ? h : l;
-  }
-  float h0, m0, l0, h1, m1, l1;
-  split3(a, h0, m0, l0);
-  split3(b, h1, m1, l1);
-  return pl == 0 ? pack_bf16x2(h0, h1) : pl == 1 ? pack_bf16x2(m0, m1) : pack_bf16x2(l0, l1);
-}
-__device__ __forceinline__ uint16_t plane_half(float a, int pl, int np) {
-  if (np == 1) return __bfloat16_as_ushort(__float2bfloat16_rn(a));
-  uint16_t hi, lo;
-  split2h_scaled(a * FS2_F16X2_ACT_SCALE, hi, lo);
-  return pl == 0 ? hi : lo;
-}
 
 template <int N>
 __device__ __forceinline__ void tma_store_wait_read_n() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
@@ -140,9 +95,8 @@ tc_conv_gemm_staged_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
   constexpr int TB0 = 2 * MAX_A + 2 * MAX_B;
   auto tfull_bar = [&](int s) { return bars + 8u * (TB0 + s); };
   auto tempty_bar = [&](int s) { return bars + 8u * (TB0 + 2 + s); };
-  auto res_bar = [&](int g, int s) { return bars + 8u * (TB0 + 4 + 2 * g + s); };        // residual chunk landed (tx)
-  auto res_empty = [&](int g, int s) { return bars + 8u * (TB0 + 8 + 2 * g + s); };      // v3 ring: 4 warps have read it
-  auto xfull_bar = [&](int s) { return bars + 8u * (TB0 + 12 + s); };
+  auto res_bar = [&](int g, int s) { return bars + 8u * (TB0 + 4 + 2 * g + s); };
+  auto xfull_bar = [&](int s) { return bars + 8u * (TB0 + 8 + s); };
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + bar_off + NUM_BARS * 8);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -161,7 +115,7 @@ tc_conv_gemm_staged_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
     for (int s = 0; s < MAX_A; ++s) { mbar_init(fullA(s), 1); mbar_init(emptyA(s), 1); }
     for (int s = 0; s < MAX_B; ++s) { mbar_init(fullB(s), 1); mbar_init(emptyB(s), 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 8); }
-    for (int g = 0; g < 2; ++g) for (int s = 0; s < 2; ++s) { mbar_init(res_bar(g, s), 1); mbar_init(res_empty(g, s), 4); }
+    for (int g = 0; g < 2; ++g) for (int s = 0; s < 2; ++s) mbar_init(res_bar(g, s), 1);
     for (int s = 0; s < 2; ++s) mbar_init(xfull_bar(s), 128);   // one remote arrive per row of the peer CTA
     fence_barrier_init();
   }
@@ -169,7 +123,7 @@ tc_conv_gemm_staged_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
     tmem_alloc(smem_u32(tmem_slot), TMEM_COLS);
     tmem_relinquish();
   }
-  if (warp >= 3 && warp < RES_WARP) {
+  if (warp >= 3) {
     const int i = threadIdx.x - EPI_T0;   // 0..255
     s_g[i] = ln ? __ldg(a.ln_g + i) : 1.f;
     s_b[i] = ln ? __ldg(a.ln_b + i) : 0.f;
@@ -248,25 +202,6 @@ tc_conv_gemm_staged_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
         if (++as == 2) { as = 0; aphase ^= 1u; }
       }
     }
-  } else if (warp == RES_WARP) {
-    // ===================================================== TMA producer, fp32 residual ring (v3 LayerNorm epilogue)
-    // Runs ahead of the epilogue warps by the depth of the ring (2 chunks per group), across tile boundaries.
-    if (lane == 0 && plan.res_ring) {
-      const int HALF = BN >> 1, NCH = HALF >> 5;
-      int cnt = 0;                                   // chunks issued so far (per group; both groups advance together)
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m_blk = tile / num_n_blocks, n0 = (tile - m_blk * num_n_blocks) * BN, r0 = m_blk * BM;
-        for (int c = 0; c < NCH; ++c, ++cnt) {
-          const int buf = cnt & 1;
-          const uint32_t par = (uint32_t)((cnt >> 1) & 1);
-          for (int g = 0; g < 2; ++g) {
-            mbar_wait(res_empty(g, buf), par ^ 1u);
-            mbar_expect_tx(res_bar(g, buf), CH_F32);
-            tma_load_2d(base + ring_bytes + g * grp_sz + buf * CH_F32, &tmRes, res_bar(g, buf), n0 + g * HALF + c * 32, r0);
-          }
-        }
-      }
-    }
   } else {
     // ===================================================== epilogue: 2 groups x 4 warps, thread = (output row, column half)
     const int g = (warp - 3) >> 2;                  // group = column half
@@ -278,9 +213,8 @@ tc_conv_gemm_staged_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
     const int sw128 = row & 7, sw64 = (row >> 1) & 3;
     const int grp_off = ring_bytes + g * grp_sz;
     const bool wide = plan.wide != 0;               // F buffers exist
-    const bool ring = plan.res_ring != 0;           // v3: R0 | R1 | F | B
-    uint8_t* Fbuf = smem + grp_off + (ring ? 2 * CH_F32 : 0);   // F0 | F1 (wide plan), or the single F of the ring plan
-    uint8_t* Bbuf = smem + grp_off + (ring ? 3 * CH_F32 : wide ? 2 * CH_F32 : 0);
+    uint8_t* Fbuf = smem + grp_off;                 // F0 | F1 (wide plan only)
+    uint8_t* Bbuf = smem + grp_off + (wide ? 2 * CH_F32 : 0);
     const bool has_res = a.epi == EPI_RES_LN;
     const int out_planes = a.out_planes == 3 ? 3 : a.out_planes == 2 ? 2 : 1;
     const int HALF = BN >> 1;                       // columns per group: 128 or 64
@@ -380,37 +314,6 @@ tc_conv_gemm_staged_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
       }
     };
 
-    // v3 ring plan: ONE fp32 staging tile (F) and ONE 8 KB plane tile (B) per group; operand planes leave one after the
-    // other.  The previous chunk's stores have had a whole TMEM load + the chunk's arithmetic to read their tiles out.
-    auto stage_single = [&](const float (&y)[32], int gcol, int r0, bool wf, bool wb) {
-      const int np = wb ? out_planes : 1;
-      for (int pl = 0; pl < np; ++pl) {
-        if (elected) tma_store_wait_read_n<0>();
-        bar_grp();
-        if (wf && pl == 0) {
-          uint8_t* o = Fbuf + row * 128;
-#pragma unroll
-          for (int j = 0; j < 8; ++j)
-            *reinterpret_cast<float4*>(o + ((j ^ sw128) << 4)) = make_float4(y[4 * j], y[4 * j + 1], y[4 * j + 2], y[4 * j + 3]);
-        }
-        if (wb) {
-          uint8_t* orow = Bbuf + row * 64;
-#pragma unroll
-          for (int j = 0; j < 4; ++j)
-            *reinterpret_cast<uint4*>(orow + ((j ^ sw64) << 4)) =
-                make_uint4(plane_pack2(y[8 * j], y[8 * j + 1], pl, out_planes), plane_pack2(y[8 * j + 2], y[8 * j + 3], pl, out_planes),
-                           plane_pack2(y[8 * j + 4], y[8 * j + 5], pl, out_planes), plane_pack2(y[8 * j + 6], y[8 * j + 7], pl, out_planes));
-        }
-        fence_proxy_async();
-        bar_grp();
-        if (elected) {
-          if (wb) tma_store_3d(&tmOutB0, base + (uint32_t)(Bbuf - smem), gcol, r0, pl);
-          if (wf && pl == 0) tma_store_2d(&tmOutF, base + (uint32_t)(Fbuf - smem), gcol, r0);
-          tma_store_commit();
-        }
-      }
-    };
-
     unsigned next_code = FS2_ROW_NONE;
     {
       const int r_first = ((int)blockIdx.x / num_n_blocks) * BM + row;
@@ -423,7 +326,7 @@ tc_conv_gemm_staged_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
       const float* my_b = s_b + (n0 & 255) + gc0;
       // residual prefetch: chunks 0 and 1 of this group's half (the F buffers double as output staging in pass 2 of the
       // previous tile: wait until those stores have been read out)
-      if (has_res && !ring && elected) {
+      if (has_res && elected) {
         tma_store_wait_read_n<0>();
         for (int c = 0; c < 2; ++c) {
           const int buf = (res_cnt + c) & 1;
@@ -448,10 +351,8 @@ tc_conv_gemm_staged_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
       }
       const bool in_grid = code != FS2_ROW_NONE;
       const int rb = in_grid ? (int)(code >> 16) : 0, rpp = in_grid ? (int)(code & 0xFFFFu) : 0;
-      // the utterance's length is only needed by the row mask at store time: issue the load here (MASK_LEN epilogues only)
-      // and compare where `keep` is first used, so that its latency hides behind the accumulator wait and pass 1
-      int len_b = 0x7fffffff;
-      if (a.mask_mode == MASK_LEN && in_grid && a.lay.lens != nullptr) len_b = ld_act(a.lay.lens + rb);
+      const bool keep_len = in_grid && (a.lay.lens == nullptr || rpp < ld_act(a.lay.lens + rb));
+      const bool keep = (a.mask_mode == MASK_LEN) ? keep_len : in_grid;
 
       mbar_wait(tfull_bar(as), aphase);
       fence_after_sync();
@@ -464,39 +365,6 @@ tc_conv_gemm_staged_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
         // ((q0 + q1) + (q2 + q3)) whatever the tile width, so that the statistics -- and with them every output bit -- do
         // not depend on how the launcher tiled the GEMM (batch-size invariance, tests/test_gpu_properties.py)
         float psum[2] = {0.f, 0.f}, psq[2] = {0.f, 0.f};
-        if (ring) {
-          // v3: residual chunks come from the ring warp 11 keeps full; a chunk is handed back per warp as soon as its 32
-          // rows are in registers (no named barrier), and the TMEM load is in flight while the residual is fetched
-          for (int c = 0; c < NCH; ++c) {
-            __syncwarp();
-            tmem_ld32(t_row + c * 32, v);
-            const int buf = res_cnt & 1;
-            mbar_wait(res_bar(g, buf), (uint32_t)((res_cnt >> 1) & 1));
-            float rr[32];
-            {
-              const uint8_t* rrow = smem + grp_off + buf * CH_F32 + row * 128;
-#pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                const float4 t4 = *reinterpret_cast<const float4*>(rrow + ((j ^ sw128) << 4));
-                rr[4 * j] = t4.x; rr[4 * j + 1] = t4.y; rr[4 * j + 2] = t4.z; rr[4 * j + 3] = t4.w;
-              }
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(res_empty(g, buf));
-            ++res_cnt;
-            float bs[32];
-            lds32(my_bias + c * 32, bs);
-            tmem_wait_ld();
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const float x = fmaf(__uint_as_float(v[j]), asc, bs[j]) + rr[j];
-              psum[c >> 1] += x;
-              psq[c >> 1] = fmaf(x, x, psq[c >> 1]);
-              v[j] = __float_as_uint(x);
-            }
-            tmem_st32(t_row + c * 32, v);
-          }
-        } else
         for (int c = 0; c < NCH; ++c) {
           __syncwarp();
           tmem_ld32(t_row + c * 32, v);
@@ -566,64 +434,17 @@ tc_conv_gemm_staged_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
         const float var = fmaxf(tsq * (1.0f / 256.0f) - mean * mean, 0.f);
         const float rstd = rsqrtf(var + 1e-5f);
         // ---- pass 2: normalise, affine, mask, stage + store
-        const bool keep = (a.mask_mode == MASK_LEN) ? (in_grid && rpp < len_b) : in_grid;
         for (int c = 0; c < NCH; ++c) {
           __syncwarp();
           tmem_ld32(t_row + c * 32, v);
-          float gg[32], bb2[32];
-          lds32(my_g + c * 32, gg);
-          lds32(my_b + c * 32, bb2);
           tmem_wait_ld();
           float y[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
-            const float x = (__uint_as_float(v[j]) - mean) * rstd * gg[j] + bb2[j];
+            const float x = (__uint_as_float(v[j]) - mean) * rstd * my_g[c * 32 + j] + my_b[c * 32 + j];
             y[j] = keep ? x : 0.f;
           }
-          if (ring) stage_single(y, n0 + gc0 + c * 32, r0, a.out != nullptr, a.out_b != nullptr);
-          else stage_out(y, c, n0 + gc0 + c * 32, r0, a.out != nullptr, a.out_b != nullptr, false, &tmOutB0);
-        }
-      } else if (a.epi == EPI_QKV && plan.qkv_full) {
-        // v3: the group's whole half tile ([128 rows x HALF columns], or the [HALF d x 128 rows] block of V^T) is staged at
-        // once -- HALF / 64 atoms of 16 KB -- and leaves as HALF / 64 TMA stores; with two operand planes (f16x2) the tile is
-        // read from TMEM twice and the planes leave one after the other.  Two named barriers per tile and plane.
-        const int part = n0 >> 8, pc0 = (n0 & 255) + gc0;      // Q / K / V and the first column inside that part
-        uint8_t* S = smem + grp_off;
-        for (int pl = 0; pl < out_planes; ++pl) {
-          if (elected) tma_store_wait_read_n<0>();
-          bar_grp();
-          for (int c = 0; c < NCH; ++c) {
-            __syncwarp();
-            tmem_ld32(t_row + c * 32, v);
-            float bs[32];
-            lds32(my_bias + c * 32, bs);
-            tmem_wait_ld();
-            float y[32];
-#pragma unroll
-            for (int j = 0; j < 32; ++j) y[j] = in_grid ? fmaf(__uint_as_float(v[j]), asc, bs[j]) : 0.f;
-            if (part < 2) {
-              uint8_t* orow = S + (c >> 1) * (BM * 128) + row * 128;           // 128-byte rows, SWIZZLE_128B atoms of 64 columns
-#pragma unroll
-              for (int j = 0; j < 4; ++j)
-                *reinterpret_cast<uint4*>(orow + ((((c & 1) * 4 + j) ^ sw128) << 4)) =
-                    make_uint4(plane_pack2(y[8 * j], y[8 * j + 1], pl, out_planes), plane_pack2(y[8 * j + 2], y[8 * j + 3], pl, out_planes),
-                               plane_pack2(y[8 * j + 4], y[8 * j + 5], pl, out_planes), plane_pack2(y[8 * j + 6], y[8 * j + 7], pl, out_planes));
-            } else {
-              uint16_t* vt_s = reinterpret_cast<uint16_t*>(S);                 // [HALF d][128 rows], no swizzle
-#pragma unroll
-              for (int j = 0; j < 32; ++j) vt_s[(c * 32 + j) * BM + row] = plane_half(y[j], pl, out_planes);
-            }
-          }
-          fence_proxy_async();
-          bar_grp();
-          if (elected) {
-            const uint32_t ssm = base + (uint32_t)(S - smem);
-            for (int at = 0; at < (HALF >> 6); ++at) {
-              if (part < 2) tma_store_3d(part == 0 ? &tmOutB0 : &tmOutB1, ssm + at * (BM * 128), pc0 + at * 64, r0, pl);
-              else tma_store_3d(&tmVt, ssm + at * (BM * 128), r0, pc0 + at * 64, pl);
-            }
-            tma_store_commit();
-          }
+          stage_out(y, c, n0 + gc0 + c * 32, r0, a.out != nullptr, a.out_b != nullptr, false, &tmOutB0);
         }
       } else if (a.epi == EPI_QKV) {
         // columns [0,256) -> Q, [256,512) -> K (bf16 [R,256] tiles); [512,768) -> V transposed: vt[d, flat row]
@@ -665,17 +486,14 @@ tc_conv_gemm_staged_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
         }
       } else {
         // ---- EPI_BIAS / EPI_RELU / EPI_TANH
-        const bool keep = (a.mask_mode == MASK_LEN) ? (in_grid && rpp < len_b) : in_grid;
         for (int c = 0; c < NCH; ++c) {
           __syncwarp();
           tmem_ld32(t_row + c * 32, v);
-          float bs[32];
-          lds32(my_bias + c * 32, bs);
           tmem_wait_ld();
           float y[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
-            float x = fmaf(__uint_as_float(v[j]), asc, bs[j]);
+            float x = fmaf(__uint_as_float(v[j]), asc, my_bias[c * 32 + j]);
             if (a.epi == EPI_RELU) x = fmaxf(x, 0.f);
             if (a.epi == EPI_TANH) x = tanhf(x);
             y[j] = keep ? x : 0.f;
@@ -704,22 +522,13 @@ tc_conv_gemm_staged_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
 
 // Wide plan (fp32 staging buffers) whenever the epilogue moves fp32 tiles or V^T; deep plan for the bf16-only
 // producers (FFN conv k=9, PostNet k=5, predictor conv1).  Ring depths fill what the staging leaves of the 227 KB.
-bool epilogue_v3() {   // FS2_EPI_V3=0 selects the round-1 epilogue plans (A/B measurements)
-  static const bool on = [] { const char* e = getenv("FS2_EPI_V3"); return !(e && atoi(e) == 0); }();
-  return on;
-}
-
 Plan plan_for(const ConvGemmArgs& a, int out_planes, int bn) {
   Plan p;
   p.bn = bn;
   p.ln_pair = (bn == 128 && (a.epi == EPI_RES_LN || a.epi == EPI_RELU_LN)) ? 1 : 0;
   p.wide = (a.epi == EPI_RES_LN || a.epi == EPI_QKV || a.out != nullptr) ? 1 : 0;
-  p.res_ring = (epilogue_v3() && a.epi == EPI_RES_LN) ? 1 : 0;
-  p.qkv_full = (epilogue_v3() && a.epi == EPI_QKV) ? 1 : 0;
   p.serial_planes = (!p.wide && out_planes == 2) ? 1 : 0;
-  if (p.res_ring) p.grp_bytes = 3 * CH_F32 + CH_B16;                       // R0 | R1 | F | one 8 KB plane tile
-  else if (p.qkv_full) p.grp_bytes = BM * (bn / 2) * 2;                    // [128 rows x bn/2 columns] 16-bit
-  else p.grp_bytes = (p.wide ? 2 * CH_F32 : 0) + (p.serial_planes ? 1 : out_planes) * CH_B16;
+  p.grp_bytes = (p.wide ? 2 * CH_F32 : 0) + (p.serial_planes ? 1 : out_planes) * CH_B16;
   // a k-step consumes one A and one B stage: the pipeline is as deep as the shallower ring.  Deepest B ring that
   // fits next to a full A ring, then shrink the A ring if even two B stages do not fit.
   p.nA = MAX_A;
@@ -783,22 +592,10 @@ int tc_conv_gemm_staged_launch(const ConvGemmArgs& a, cudaStream_t st) {
   ok = ok && f32_map(&tmOutF, a.out ? a.out : reinterpret_cast<const float*>(a.Ab), a.out ? a.ldo : 256);
   if (a.epi == EPI_QKV) {
     const int qp = a.planes == 2 ? 2 : 1;           // Q, K, V^T operand planes for the attention kernel
+    ok = ok && b16_map(&tmOutB0, a.q_b, 256, qp) && b16_map(&tmOutB1, a.k_b, 256, qp);
     const uint64_t dims[3] = {(uint64_t)a.Rv, 256, (uint64_t)qp}, strides[2] = {(uint64_t)a.Rv * 2, (uint64_t)a.Rv * 512};
-    if (epilogue_v3()) {
-      // whole half tiles: Q / K leave as [128 rows x 64 columns] 128B-swizzled atoms, V^T as [64 d x 128 rows] blocks
-      auto b16_map64 = [&](CUtensorMap* m, const bf16* p) {
-        const uint64_t d3[3] = {256, R, (uint64_t)qp}, st3[2] = {512, R * 512};
-        const uint32_t bx[3] = {64, (uint32_t)BM, 1};
-        return make_tmap_generic(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, p, d3, st3, bx, CU_TENSOR_MAP_SWIZZLE_128B);
-      };
-      const uint32_t box[3] = {(uint32_t)BM, 64, 1};
-      ok = ok && b16_map64(&tmOutB0, a.q_b) && b16_map64(&tmOutB1, a.k_b) &&
-           make_tmap_generic(&tmVt, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, a.vt_b, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE);
-    } else {
-      ok = ok && b16_map(&tmOutB0, a.q_b, 256, qp) && b16_map(&tmOutB1, a.k_b, 256, qp);
-      const uint32_t box[3] = {(uint32_t)BM, 32, 1};
-      ok = ok && make_tmap_generic(&tmVt, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, a.vt_b, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE);
-    }
+    const uint32_t box[3] = {(uint32_t)BM, 32, 1};
+    ok = ok && make_tmap_generic(&tmVt, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, a.vt_b, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE);
   } else {
     const bf16* ob = a.out_b ? a.out_b : a.Ab;
     ok = ok && b16_map(&tmOutB0, ob, a.out_b ? a.ldob : a.K, a.out_b ? out_planes : 1);
