@@ -132,6 +132,47 @@ def make_batch(workload: str):
     return synthetic.make_inputs(b, lo, hi, seed=1)
 
 
+def measure_gaussian_upsampler(dev, flush, peaks, iters=20):
+    """GaussianUpsampling (modules.py:162-192) as a stand-alone operator at the BASELINE configs[4] shape: batch 64, 300
+    phonemes, LJSpeech-like integer durations (~6.7 frames per phoneme -> T ~ 2300), D = 256.  HBM roofline: algorithmic
+    bytes = 1 KB per output frame row written + 1 KB per phoneme row read (+ 4 L bytes per frame when `w`, the [B, L, T]
+    weight tensor the reference returns, is materialised); CUDA events around each call, L2 flushed in between."""
+    import numpy as np
+    import torch
+    import smart_nar_fast_tts_b200 as pkg
+    rng = np.random.Generator(np.random.PCG64(5))
+    B, L, D = 64, 300, 256
+    x = torch.from_numpy(rng.standard_normal((B, L, D)).astype(np.float32)).to(dev)
+    d = torch.from_numpy(np.clip(np.round(rng.normal(6.7, 3.0, size=(B, L))), 0, 30).astype(np.float32)).to(dev)
+    lib = pkg.load_library()
+    T = int(d.sum(1).max().item())
+    out = torch.empty(B, T, D, device=dev)
+    s_ = torch.empty(B, device=dev)
+    w_full = torch.empty(B, L, T, device=dev)
+    st = torch.cuda.current_stream(dev).cuda_stream
+    res = {"shape": {"B": B, "L": L, "D": D, "T": T}, "hbm_peak_gbs": peaks["hbm_gbs"]}
+    for key, w in (("without_w", None), ("with_w", w_full)):
+        def call():
+            lib.check(lib.fs2_gaussian_upsample(x.data_ptr(), d.data_ptr(), B, L, D, T, T, out.data_ptr(), s_.data_ptr(),
+                                                w.data_ptr() if w is not None else None, st), None)
+        for _ in range(3):
+            call()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(iters)]
+        for a, b in ev:
+            flush.zero_()
+            a.record()
+            call()
+            b.record()
+        torch.cuda.synchronize(dev)
+        ms = statistics.median(a.elapsed_time(b) for a, b in ev)
+        nbytes = B * T * D * 4 + B * L * D * 4 + (B * L * T * 4 if w is not None else 0)
+        res[key] = {"ms": ms, "algorithmic_bytes": nbytes, "gbs": nbytes / (ms * 1e-3) / 1e9,
+                    "frac_of_hbm_peak": nbytes / (ms * 1e-3) / 1e9 / peaks["hbm_gbs"], "frames_per_s": B * T / (ms * 1e-3)}
+    res["note"] = ("one fs2_gaussian_upsample C-ABI call per sample (centres kernel + upsampling kernel, T known to the caller); "
+                   "padded frames t >= s_b are computed like valid ones (no masking in the reference class)")
+    return res
+
+
 # --------------------------------------------------------------------------------------------- reference arm
 def cpu_forward_timed(workload: str, budget_s: float, steps: int, warmup: int, threads: int, fit_steps: bool = False):
     """Times the CPU oracle (oracle/fs2_oracle.py: the reference algorithm restated in torch CPU fp32) on a bounded
@@ -512,6 +553,8 @@ def run_b200_arm(args):
                                 "note": "one forward at a time, L2 flushed between steps; 3 MMAs per algorithmic MAC, so the "
                                         "tensor pipe does 3x the counted FLOPs"}
         line.update(extra)
+        if world == 1:
+            line["gaussian_upsampler"] = measure_gaussian_upsampler(dev, flush, peaks)
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
             r = cpu_forward_timed(args.workload, 20.0, 2, 1, threads, fit_steps=True)   # ~10-20 s of CPU work

@@ -124,6 +124,16 @@ int fs2_set_row_packing(fs2_handle* h, int32_t keep_rows);
  * `mel` (the pre-PostNet output) always stays [B, T, n_mel]. */
 int fs2_set_mel_post_layout(fs2_handle* h, int32_t channel_major);
 
+/* Which operator expands phoneme rows to frame rows in fs2_forward_stage2.  HARD (default): LengthRegulator
+ * (modules.py:195-230), what the reference's VarianceAdaptor instantiates (modules.py:22,129,136).  GAUSSIAN:
+ * GaussianUpsampling (modules.py:162-192; the operator the reference's README.md:10 announces but never wires in) applied
+ * to the same rounded durations: frame t = sum_i w[i,t] x[i], w = softmax-like Gaussian weights around the phoneme centres,
+ * over ALL L phoneme slots of the padded batch (no masking, as in the reference class); mel_lens, masks and T are those of
+ * the hard regulator (s_b = sum d_b, integer durations).  Everything downstream is unchanged. */
+#define FS2_UPSAMPLER_HARD 0
+#define FS2_UPSAMPLER_GAUSSIAN 1
+int fs2_set_upsampler(fs2_handle* h, int32_t upsampler);
+
 /* ---- the forward, in two stages because T = max(sum(durations)) is data dependent --- */
 /* replaces: fastspeech2_align.py:46-53 (src mask, TxtEncoder) + modules.py:116-135
  * (duration predictor, rounding) + the length bookkeeping of LengthRegulator.LR

@@ -274,7 +274,10 @@ class Trace:
 # model/modules.py:102-159  VarianceAdaptor.forward (inference: all targets None)
 def variance_adaptor(sd, d: Dims, x, src_mask, p_control=1.0, e_control=1.0, d_control=1.0,
                      trace: Optional[Trace] = None, force_durations: Optional[torch.Tensor] = None,
-                     t_pad: Optional[int] = None):
+                     t_pad: Optional[int] = None, upsampler: str = "hard"):
+    """`upsampler="gaussian"`: the reference's GaussianUpsampling (modules.py:162-192, dead code there) in the place of
+    `self.length_regulator` -- pinned by oracle/gen_golden.py, which swaps the reference's own class into the reference
+    module through a three-line adapter ((out, s, w) -> (out, s.long()))."""
     log_d = variance_predictor(sd, "variance_adaptor.duration_predictor", x, src_mask)
     if d.pitch_feature == "phoneme_level":
         p_pred, p_emb, p_idx = variance_embedding(sd, "pitch", x, src_mask, p_control)
@@ -283,7 +286,11 @@ def variance_adaptor(sd, d: Dims, x, src_mask, p_control=1.0, e_control=1.0, d_c
         e_pred, e_emb, e_idx = variance_embedding(sd, "energy", x, src_mask, e_control)
         x = x + e_emb
     d_rounded = round_durations(log_d, d_control) if force_durations is None else force_durations
-    x, mel_len = length_regulate(x, d_rounded, t_pad)
+    if upsampler == "gaussian":
+        x, s, _ = gaussian_upsample(x, d_rounded, t_pad)
+        mel_len = s.squeeze(-1).long()
+    else:
+        x, mel_len = length_regulate(x, d_rounded, t_pad)
     mel_mask = get_mask_from_lengths(mel_len, t_pad)
     if trace is not None:
         trace.lr_out = x
@@ -302,7 +309,7 @@ def variance_adaptor(sd, d: Dims, x, src_mask, p_control=1.0, e_control=1.0, d_c
 @torch.no_grad()
 def forward(sd, d: Dims, speakers, texts, src_lens, max_src_len, p_control=1.0, e_control=1.0,
             trace: Optional[Trace] = None, force_durations: Optional[torch.Tensor] = None,
-            t_pad: Optional[int] = None):
+            t_pad: Optional[int] = None, upsampler: str = "hard"):
     """Returns the reference's 12-tuple.  `speakers` is ignored (no speaker
     embedding exists in the reference).  `force_durations` (test hook, not in the
     reference) replaces d_rounded so downstream stages can be compared on
@@ -314,7 +321,7 @@ def forward(sd, d: Dims, speakers, texts, src_lens, max_src_len, p_control=1.0, 
     if trace is not None:
         trace.enc_out = enc
     (x, p_pred, e_pred, log_d, d_rounded, mel_lens, mel_masks) = variance_adaptor(
-        sd, d, enc, src_masks, p_control, e_control, 1.0, trace, force_durations, t_pad)
+        sd, d, enc, src_masks, p_control, e_control, 1.0, trace, force_durations, t_pad, upsampler)
     dec, mel_masks = mel_decoder(sd, d, x, mel_masks)
     if trace is not None:
         trace.dec_out = dec

@@ -128,6 +128,33 @@ def main():
     import model.modules as ref_modules  # type: ignore
     ref_modules.device = torch.device("cpu")
     gu = ref_modules.GaussianUpsampling()
+
+    # ... and wired into the reference module in the LengthRegulator's place (the opt-in `upsampler="gaussian"` switch):
+    # the reference's own class behind a three-line adapter to the (x, duration, max_len) -> (out, mel_len) interface
+    class _GaussianAsRegulator(torch.nn.Module):
+        def forward(self, x, duration, max_len):
+            out, s_, _w = gu(x, duration, torch.ones_like(duration), max_len)   # range_outputs is overwritten by 10.0 (:175)
+            return out, s_.squeeze(-1).long()
+
+    for name, (seed, stats, pq, B, lo, hi, iseed, fpp) in {"gaussian_forward": (9, O.STATS_NAN_BINS, "log", 4, 5, 21, 6, 6.0)}.items():
+        d = O.Dims(pitch_quantization=pq)
+        sd = O.make_state_dict(seed, d, stats, frames_per_phoneme=fpp)
+        ref = build_reference(FastSpeech2Align, sd, stats, pq)
+        ref.variance_adaptor.length_regulator = _GaussianAsRegulator()
+        speakers, texts, src_lens, L = O.make_inputs(B, lo, hi, iseed)
+        with torch.no_grad():
+            r = ref(speakers, texts, src_lens, L)
+        o = O.forward(sd, d, speakers, texts, src_lens, L, upsampler="gaussian")
+        for i, (a, b) in enumerate(zip(r, o)):
+            assert bit_equal(a, b), f"{name}: oracle != reference on output {i}"
+        print(f"{name}: B={B} L={L} T={int(r[9].max())} mel_lens={r[9].tolist()} -> oracle bit-identical to reference")
+        np.savez_compressed(
+            os.path.join(out_dir, f"{name}.npz"),
+            seed=seed, stats=json.dumps(stats), pitch_quantization=pq, frames_per_phoneme=fpp,
+            speakers=speakers.numpy(), texts=texts.numpy(), src_lens=src_lens.numpy(), max_src_len=L,
+            mel=r[0].numpy(), postnet_mel=r[1].numpy(), pitch=r[2].numpy(), energy=r[3].numpy(),
+            log_d=r[4].numpy(), d_rounded=r[5].numpy(), src_masks=r[6].numpy(), mel_masks=r[7].numpy(),
+            mel_lens=r[9].numpy())
     rng = np.random.Generator(np.random.PCG64(11))
     x = torch.from_numpy(rng.standard_normal((3, 9, 256)).astype(np.float32))
     dur = torch.tensor([[3, 0, 5, 2, 7, 1, 4, 0, 0], [2, 2, 2, 2, 2, 2, 2, 2, 2], [9, 0, 0, 30, 1, 0, 0, 0, 0]],

@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libfs2_b200.so")
 STAMP = os.path.join(HERE, "build", "stamp.txt")
-SOURCES = ["fs2_api.cu", "fs2_rowops.cu", "fs2_simt_gemm.cu", "fs2_simt_attn.cu", "fs2_tc_gemm.cu", "fs2_tc_gemm_staged.cu", "fs2_tc_attn.cu", "fs2_handoff.cu"]
+SOURCES = ["fs2_api.cu", "fs2_rowops.cu", "fs2_simt_gemm.cu", "fs2_simt_attn.cu", "fs2_tc_gemm.cu", "fs2_tc_gemm_staged.cu", "fs2_tc_attn.cu", "fs2_handoff.cu", "fs2_gaussian.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr",

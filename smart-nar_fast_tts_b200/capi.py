@@ -59,6 +59,7 @@ SIGNATURES = {
     "fs2_set_precision": (C.c_int, [_P, _I, _I]),
     "fs2_set_row_packing": (C.c_int, [_P, _I]),
     "fs2_set_mel_post_layout": (C.c_int, [_P, _I]),
+    "fs2_set_upsampler": (C.c_int, [_P, _I]),
     "fs2_forward_stage1": (C.c_int, [_P, _P, _P, _I, _I, _F, _F, _F, _P, _P, _P, _P, _P, _P, C.POINTER(_I), _P]),
     "fs2_forward_stage1_async": (C.c_int, [_P, _P, _P, _I, _I, _F, _F, _F, _P, _P, _P, _P, _P, _P, _P, _P]),
     "fs2_forward_stage1_commit": (C.c_int, [_P, _I, _I]),

@@ -79,6 +79,7 @@ struct fs2_handle {
   int prec_enc = FS2_PREC_BF16X3, prec_dec = FS2_PREC_BF16;
   int halo_keep = 2;  // padded rows kept per utterance (2 = packed; >= max length = the reference's padded grid)
   int mel_post_cm = 0;  // stage 2 / fs2_op_mel_postnet write mel_post channel-major [B, n_mel, T] (vocoder hand-off)
+  int upsampler = 0;    // FS2_UPSAMPLER_HARD (LengthRegulator, the reference's wiring) / FS2_UPSAMPLER_GAUSSIAN
   bool loaded = false;
   std::string err;
   std::shared_ptr<fs2_weights> w;   // possibly shared with other handles (fs2_share_weights)
@@ -674,6 +675,14 @@ int fs2_set_mel_post_layout(fs2_handle* h, int32_t channel_major) {
   return FS2_OK;
 }
 
+int fs2_set_upsampler(fs2_handle* h, int32_t upsampler) {
+  if (!h) return FS2_ERR_INVALID;
+  if (upsampler != FS2_UPSAMPLER_HARD && upsampler != FS2_UPSAMPLER_GAUSSIAN)
+    return h->fail(FS2_ERR_INVALID, "upsampler must be FS2_UPSAMPLER_HARD or FS2_UPSAMPLER_GAUSSIAN");
+  h->upsampler = upsampler;
+  return FS2_OK;
+}
+
 int fs2_load_weights(fs2_handle* h, const fs2_weight_desc* descs, int32_t n) {
   // weight repacking interleaves cudaMemcpyAsync with small kernels: no programmatic overlap here at all
   struct PdlOff { PdlOff() { ++g_fs2_pdl_off; } ~PdlOff() { --g_fs2_pdl_off; } } pdl_off;
@@ -880,6 +889,9 @@ int fs2_forward_stage2(fs2_handle* h, int32_t T, float p_control, float e_contro
   if (T < h->st_Tmax) return h->fail(FS2_ERR_INVALID, "stage2: T smaller than the stage-1 maximum mel length");
   const fs2_dims& d = h->dims;
   if (T == 0) return FS2_OK;  // degenerate batch (all durations zero): nothing to write
+  if (h->upsampler == FS2_UPSAMPLER_GAUSSIAN && (d.pitch_phoneme_level || d.energy_phoneme_level))
+    return h->fail(FS2_ERR_UNSUPPORTED, "stage2: the Gaussian upsampler is built for frame-level pitch / energy (with "
+                   "phoneme-level features the padded phoneme rows are not zero and would need their embedding rows)");
   if (T > FS2_MAX_ROWS_PER_UTT) return h->fail(FS2_ERR_UNSUPPORTED, "stage2: more than 65535 mel frames per utterance");
   if (!mel || !mel_post || (!d.pitch_phoneme_level && !pitch) || (!d.energy_phoneme_level && !energy))
     return h->fail(FS2_ERR_INVALID, "stage2: null output pointer");
@@ -914,7 +926,11 @@ int fs2_forward_stage2(fs2_handle* h, int32_t T, float p_control, float e_contro
     PROF("rows.length_regulate");
     if (mel_mask) HCHECK(rowops_mask(nullptr, mlens32, B, T, mel_mask, st, pitch_fl ? pitch : nullptr, energy_fl ? energy : nullptr));
     // modules.py:136 length regulator (hard): gathers encoder rows (stage-1 layout) into frame rows (stage-2 layout)
-    HCHECK(rowops_length_regulate(h->st_enc_out, h->st_lay1.off, 0, cum, L, D, lay, x, xb, planes_of(first_prec), st));
+    if (h->upsampler == FS2_UPSAMPLER_GAUSSIAN)   // modules.py:162-192 in the LengthRegulator's place (README.md:10 of the reference)
+      HCHECK(rowops_gaussian_regulate(h->st_enc_out, h->st_lay1.off, h->st_lay1.lens, cum, L, D, lay, x, xb,
+                                      planes_of(first_prec), st));
+    else
+      HCHECK(rowops_length_regulate(h->st_enc_out, h->st_lay1.off, 0, cum, L, D, lay, x, xb, planes_of(first_prec), st));
   }
   const float* pe = nullptr;
   RCHECK(position_table(h, 1, T, &pe, st));

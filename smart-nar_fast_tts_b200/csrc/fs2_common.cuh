@@ -178,6 +178,40 @@ __device__ __forceinline__ void split2h_pair(float a, float b, uint32_t& hi2, ui
   lo2 = (uint32_t)la | ((uint32_t)lb << 16);
 }
 
+// operand-plane stores shared by the row operators (fs2_rowops.cu, fs2_gaussian.cu)
+__device__ __forceinline__ uint32_t pack2(float a, float b) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+// y -> (hi, mid, lo) bf16 terms, residuals exact in fp32
+__device__ __forceinline__ void split3f(float y, float& hi, float& mid, float& lo) {
+  hi = __bfloat162float(__float2bfloat16_rn(y));
+  const float r1 = y - hi;
+  mid = __bfloat162float(__float2bfloat16_rn(r1));
+  lo = r1 - mid;
+}
+// write 4 consecutive values into `planes` operand planes (1: bf16 rounded; 3: bf16 hi/mid/lo split; 2: scaled fp16 hi/lo)
+__device__ __forceinline__ void store_planes4(bf16* dst, size_t plane_elems, int planes, float4 a) {
+  if (planes == 1) {
+    *reinterpret_cast<uint2*>(dst) = make_uint2(pack2(a.x, a.y), pack2(a.z, a.w));
+    return;
+  }
+  if (planes == 2) {
+    uint32_t h0, l0, h1, l1;
+    split2h_pair(a.x, a.y, h0, l0);
+    split2h_pair(a.z, a.w, h1, l1);
+    *reinterpret_cast<uint2*>(dst) = make_uint2(h0, h1);
+    *reinterpret_cast<uint2*>(dst + plane_elems) = make_uint2(l0, l1);
+    return;
+  }
+  float h[4], m[4], l[4];
+  split3f(a.x, h[0], m[0], l[0]); split3f(a.y, h[1], m[1], l[1]);
+  split3f(a.z, h[2], m[2], l[2]); split3f(a.w, h[3], m[3], l[3]);
+  *reinterpret_cast<uint2*>(dst) = make_uint2(pack2(h[0], h[1]), pack2(h[2], h[3]));
+  *reinterpret_cast<uint2*>(dst + plane_elems) = make_uint2(pack2(m[0], m[1]), pack2(m[2], m[3]));
+  *reinterpret_cast<uint2*>(dst + 2 * plane_elems) = make_uint2(pack2(l[0], l[1]), pack2(l[2], l[3]));
+}
+
 #define FS2_CUDA_CHECK(expr)                                  \
   do {                                                        \
     cudaError_t _e = (expr);                                  \
@@ -234,7 +268,11 @@ cudaError_t rowops_fill_padded_rows(const float* bias, int N, const RowLayout& s
 cudaError_t rowops_postnet_far_rows(const float* post_grid, int N, const RowLayout& pn, int B, int H, float* out_user,
                                     int user_cm, cudaStream_t st);
 cudaError_t rowops_gaussian_upsample(const float* x, const float* d, int B, int L, int D, int T, int T_w, float* out,
-                                     float* s, float* w, cudaStream_t st);
+                                     float* s, float* w, cudaStream_t st);   // fs2_gaussian.cu
+// the forward's soft length regulator: rowops_length_regulate's arguments + src_rows[b] = rows of utterance b that exist
+// in x (the phonemes beyond them are the masked, all-zero ones); integer durations given by their scan `cum`
+cudaError_t rowops_gaussian_regulate(const float* x, const int* src_off, const int* src_rows, const int* cum, int L, int D,
+                                     const RowLayout& lay, float* out, bf16* out_b, int out_planes, cudaStream_t st);
 cudaError_t rowops_to_grid(const float* x_user, const RowLayout& lay, int C, float* out, int ldo, int col_off,
                            bf16* out_b, cudaStream_t st);
 cudaError_t rowops_from_grid(const float* x_grid, const RowLayout& lay, int C, float* out_user, cudaStream_t st);

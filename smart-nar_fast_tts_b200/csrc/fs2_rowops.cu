@@ -17,38 +17,6 @@ namespace {
 
 __device__ __forceinline__ float4 ld4(const float* p) { return ld_act(reinterpret_cast<const float4*>(p)); }
 __device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
-__device__ __forceinline__ uint32_t pack2(float a, float b) {
-  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
-  return *reinterpret_cast<uint32_t*>(&v);
-}
-// y -> (hi, mid, lo) bf16 terms, residuals exact in fp32
-__device__ __forceinline__ void split3f(float y, float& hi, float& mid, float& lo) {
-  hi = __bfloat162float(__float2bfloat16_rn(y));
-  const float r1 = y - hi;
-  mid = __bfloat162float(__float2bfloat16_rn(r1));
-  lo = r1 - mid;
-}
-// write 4 consecutive values into `planes` operand planes (1: bf16 rounded; 3: bf16 hi/mid/lo split; 2: scaled fp16 hi/lo)
-__device__ __forceinline__ void store_planes4(bf16* dst, size_t plane_elems, int planes, float4 a) {
-  if (planes == 1) {
-    *reinterpret_cast<uint2*>(dst) = make_uint2(pack2(a.x, a.y), pack2(a.z, a.w));
-    return;
-  }
-  if (planes == 2) {
-    uint32_t h0, l0, h1, l1;
-    split2h_pair(a.x, a.y, h0, l0);
-    split2h_pair(a.z, a.w, h1, l1);
-    *reinterpret_cast<uint2*>(dst) = make_uint2(h0, h1);
-    *reinterpret_cast<uint2*>(dst + plane_elems) = make_uint2(l0, l1);
-    return;
-  }
-  float h[4], m[4], l[4];
-  split3f(a.x, h[0], m[0], l[0]); split3f(a.y, h[1], m[1], l[1]);
-  split3f(a.z, h[2], m[2], l[2]); split3f(a.w, h[3], m[3], l[3]);
-  *reinterpret_cast<uint2*>(dst) = make_uint2(pack2(h[0], h[1]), pack2(h[2], h[3]));
-  *reinterpret_cast<uint2*>(dst + plane_elems) = make_uint2(pack2(m[0], m[1]), pack2(m[2], m[3]));
-  *reinterpret_cast<uint2*>(dst + 2 * plane_elems) = make_uint2(pack2(l[0], l[1]), pack2(l[2], l[3]));
-}
 
 
 // ---------------------------------------------------------------------------------------------
@@ -403,82 +371,6 @@ __global__ void __launch_bounds__(256) postnet_far_rows_cm_kernel(const float* p
   for (int c = 0; c < N; ++c) dst[(size_t)c * S] = ld_act(src + c);
 }
 
-// model/modules.py:166-192 GaussianUpsampling.  Per utterance: e = cumsum(d), c = e - d/2 (monotone non-decreasing
-// because d >= 0 on this path; negative durations fall back to the full range), w[i,t] = exp(-0.01 (t-c_i)^2) /
-// (sum_i exp(..) + 1e-20), out[t,:] = sum_i w[i,t] x[i,:].  exp(-0.01*D^2) is exactly 0 in fp32 for |D| >= 103
-// (denormal limit: 0.01*D^2 > 103.97), so each frame only visits the phonemes with |t - c_i| < 104 found by binary
-// search: O(band) instead of O(L) work per frame, identical sums.  One warp per frame; lanes split the band for the
-// weights (warp-shuffle normalisation), then split the D channels for the accumulation.
-__global__ void __launch_bounds__(256) gaussian_upsample_kernel(const float* x, const float* d,
-                                                                int L, int D, int T, int T_w, float* out,
-                                                                float* s_out, float* w_out) {
-  FS2_PDL_PROLOGUE();
-  extern __shared__ float c_s[];  // [L] centres
-  __shared__ int mono_s;
-  const int b = blockIdx.y;
-  if (threadIdx.x == 0) {  // sequential fp32 cumsum: same association order as torch.cumsum on CPU
-    float e = 0.f;
-    int mono = 1;
-    float prev = -INFINITY;
-    for (int i = 0; i < L; ++i) {
-      const float di = d[(size_t)b * L + i];
-      e += di;
-      const float c = e - 0.5f * di;
-      c_s[i] = c;
-      if (!(c >= prev)) mono = 0;
-      prev = c;
-    }
-    mono_s = mono;
-    if (s_out && blockIdx.x == 0) s_out[b] = e;
-  }
-  __syncthreads();
-  const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-  const int nv = D >> 2;
-  for (int t = blockIdx.x * nwarps + wp; t < T; t += gridDim.x * nwarps) {
-    float* dst = out + ((size_t)b * T + t) * D;
-    if (t >= T_w) {  // `pad(output, max_len)` rows
-      for (int c = lane; c < nv; c += 32) st4(dst + c * 4, make_float4(0.f, 0.f, 0.f, 0.f));
-      continue;
-    }
-    const float tf = (float)t;
-    int i_lo = 0, i_hi = L;
-    if (mono_s) {
-      int lo = 0, hi = L;  // first i with c_i > t - 104
-      while (lo < hi) { const int mid = (lo + hi) >> 1; if (c_s[mid] > tf - 104.f) hi = mid; else lo = mid + 1; }
-      i_lo = lo;
-      hi = L;              // first i with c_i >= t + 104
-      while (lo < hi) { const int mid = (lo + hi) >> 1; if (c_s[mid] >= tf + 104.f) hi = mid; else lo = mid + 1; }
-      i_hi = lo;
-    }
-    float part = 0.f;
-    for (int i = i_lo + lane; i < i_hi; i += 32) {
-      const float dl = tf - c_s[i];
-      part += expf(-0.01f * (dl * dl));
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
-    const float denom = part + 1e-20f;
-    if (w_out) {
-      for (int i = lane; i < L; i += 32) {
-        float wv = 0.f;
-        if (i >= i_lo && i < i_hi) { const float dl = tf - c_s[i]; wv = expf(-0.01f * (dl * dl)) / denom; }
-        w_out[((size_t)b * L + i) * T_w + t] = wv;
-      }
-    }
-    for (int c = lane; c < nv; c += 32) {
-      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-      for (int i = i_lo; i < i_hi; ++i) {
-        const float dl = tf - c_s[i];
-        const float wv = expf(-0.01f * (dl * dl)) / denom;
-        const float4 xv = ld4(x + ((size_t)b * L + i) * D + c * 4);
-        acc.x = fmaf(wv, xv.x, acc.x); acc.y = fmaf(wv, xv.y, acc.y);
-        acc.z = fmaf(wv, xv.z, acc.z); acc.w = fmaf(wv, xv.w, acc.w);
-      }
-      st4(dst + c * 4, acc);
-    }
-  }
-}
-
 // dense user layout [B,S,C] <-> ragged grid layout (test / per-operator entry points)
 __global__ void to_grid_kernel(const float* xu, const RowLayout lay, int C, float* out,
                                int ldo, int col_off, bf16* out_b) {
@@ -755,18 +647,6 @@ cudaError_t rowops_split(const float* src, int64_t n, int planes, bf16* dst, int
   if (n <= 0) return cudaSuccess;
   if (n % 4) return cudaErrorInvalidValue;
   (void)FS2_LAUNCH(split_kernel, blocks_for((size_t)(n / 4), 256), 256, 0, st, src, n / 4, planes, dst, plane_elems);
-  return LAUNCHED();
-}
-cudaError_t rowops_gaussian_upsample(const float* x, const float* d, int B, int L, int D, int T, int T_w, float* out,
-                                     float* s, float* w, cudaStream_t st) {
-  if (B <= 0) return cudaSuccess;
-  const size_t smem = sizeof(float) * (size_t)(L > 0 ? L : 1);
-  if (smem > 48 * 1024) return cudaErrorInvalidValue;
-  int gx = (T + 7) / 8;
-  if (gx < 1) gx = 1;
-  if (gx > 1024) gx = 1024;
-  dim3 grid(gx, B);
-  (void)FS2_LAUNCH(gaussian_upsample_kernel, grid, 256, smem, st, x, d, L, D, T, T_w, out, s, w);
   return LAUNCHED();
 }
 cudaError_t rowops_to_grid(const float* x_user, const RowLayout& lay, int C, float* out, int ldo, int col_off,

@@ -172,7 +172,9 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             umma_bf16(tmem_S + (uint32_t)(s * 64), ad, bd, idesc_s, (c | kk) ? 1u : 0u);
           }
         }
-        umma_commit(k_empty0 + 8 * s);   // the K stage is reusable as soon as these MMAs have read it
+        // the K stage is reusable as soon as these MMAs have read it; the producer only waits for that when block j + 2
+        // exists (an arrival nobody waits for is flagged by compute-sanitizer's synccheck)
+        if (j + 2 < nb) umma_commit(k_empty0 + 8 * s);
         umma_commit(s_full0 + 8 * s);
       };
       mbar_wait(q_full, 0);
@@ -194,7 +196,7 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             umma_bf16_ts(tmem_O, at, bd, idesc_o, (j | c | kk) ? 1u : 0u);
           }
         }
-        umma_commit(v_empty0 + 8 * s);
+        if (j + 2 < nb) umma_commit(v_empty0 + 8 * s);
         umma_commit(o_ready0 + 8 * s);
         // S(j+2) overwrites score buffer j & 1, which P(j)V(j) -- issued just above -- reads as its A operand.  MMAs of one
         // thread execute in issue order, so the write cannot overtake the read (the same aliasing CUTLASS's sm100 FMHA
@@ -267,9 +269,12 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       if (NP == 2) tmem_st32(sbuf + 32, reinterpret_cast<uint32_t(&)[32]>(pl));
       l = l * alpha + ((bs4[0] + bs4[1]) + (bs4[2] + bs4[3]));
       m = m_new;
+      // O is stable once P(j-1)V(j-1) has completed.  Every phase of o_ready is waited for (not only the ones a rescale
+      // needs): P(j-1)V(j-1) was issued before this block's exponentials started, so the wait is already satisfied, and no
+      // phase of the barrier ever completes unobserved (what compute-sanitizer's synccheck reports as "missing wait").
+      if (j > 0) mbar_wait(o_ready0 + 8 * ((j - 1) & 1), ((j - 1) >> 1) & 1);
       // rescale the running output only when some row of the warp moved its reference maximum (warp-uniform branch)
       if (j > 0 && __any_sync(0xffffffffu, alpha != 1.0f)) {
-        mbar_wait(o_ready0 + 8 * ((j - 1) & 1), ((j - 1) >> 1) & 1);   // O is stable once P(j-1)V(j-1) has completed
         fence_after_sync();
         for (int c = 0; c < 4; ++c) {
           tmem_ld32(tmem_O + lane_off + c * 32, v0);

@@ -155,9 +155,12 @@ def dims_from_configs(preprocess_config, model_config, n_src_vocab: int = N_SRC_
 class FastSpeech2Align(nn.Module):
     """Drop-in for the reference class of the same name; inference (`mel_lens is None`) only."""
 
-    def __init__(self, preprocess_config, model_config, n_src_vocab: int = N_SRC_VOCAB_LJSPEECH):
+    def __init__(self, preprocess_config, model_config, n_src_vocab: int = N_SRC_VOCAB_LJSPEECH, upsampler: str = "hard"):
         super().__init__()
         self.model_config = model_config
+        if upsampler not in ("hard", "gaussian"):
+            raise ValueError('upsampler must be "hard" (LengthRegulator, the reference\'s wiring) or "gaussian"')
+        self._upsampler = upsampler
         # construction order mirrors fastspeech2_align.py:20-28 so that default initialisation consumes the
         # torch RNG in the same order as the reference
         self.txt_encoder = _Stack(model_config, "txt_encoder", n_src_vocab)
@@ -219,6 +222,20 @@ class FastSpeech2Align(nn.Module):
         for e in self._engines.values():
             lib = load_library()
             lib.check(lib.fs2_set_mel_post_layout(e["h"], int(self._mel_post_cm)), e["h"])
+        return self
+
+    def set_upsampler(self, upsampler: str = "hard") -> "FastSpeech2Align":
+        """"hard": model/modules.py:195-230 LengthRegulator (the reference's wiring, the default).  "gaussian":
+        model/modules.py:162-192 GaussianUpsampling in its place (what the reference's README.md:10 announces): frame rows
+        are Gaussian-weighted sums of the phoneme rows around them, over all L phoneme slots of the padded batch exactly
+        like the reference class (no masking); lengths, masks and everything downstream are unchanged.  Frame-level
+        pitch / energy only."""
+        if upsampler not in ("hard", "gaussian"):
+            raise ValueError('upsampler must be "hard" or "gaussian"')
+        self._upsampler = upsampler
+        for e in self._engines.values():
+            lib = load_library()
+            lib.check(lib.fs2_set_upsampler(e["h"], int(upsampler == "gaussian")), e["h"])
         return self
 
     def _weights(self):
@@ -294,6 +311,7 @@ class FastSpeech2Align(nn.Module):
             lib.check(lib.fs2_set_precision(eng["h"], *self._precision), eng["h"])
             lib.check(lib.fs2_set_row_packing(eng["h"], self._keep_rows), eng["h"])
             lib.check(lib.fs2_set_mel_post_layout(eng["h"], int(self._mel_post_cm)), eng["h"])
+            lib.check(lib.fs2_set_upsampler(eng["h"], int(self._upsampler == "gaussian")), eng["h"])
             self._engines[key] = eng
         ws = self._weights()
         # every tensor's storage address and version counter: catches a replaced middle tensor and any tracked in-place

@@ -40,11 +40,12 @@ def ljspeech_configs(stats: dict, pitch_q: str = "log", energy_q: str = "linear"
     return pc, mc
 
 
-def build_model(sd, stats, pitch_q="log", device="cuda", pitch_feature="frame_level", energy_feature="frame_level"):
+def build_model(sd, stats, pitch_q="log", device="cuda", pitch_feature="frame_level", energy_feature="frame_level",
+                upsampler="hard"):
     from smart_nar_fast_tts_b200 import FastSpeech2Align
     pc, mc = ljspeech_configs(stats, pitch_q, pitch_feature=pitch_feature, energy_feature=energy_feature)
     with np.errstate(invalid="ignore"):
-        m = FastSpeech2Align(pc, mc)
+        m = FastSpeech2Align(pc, mc, upsampler=upsampler)
     full = m.state_dict()
     merged = {k: (sd[k] if k in sd else v) for k, v in full.items()}
     m.load_state_dict(merged, strict=True)

@@ -159,3 +159,37 @@ def test_forward_phoneme_level(lib):
         ebins = sd["variance_adaptor.energy_bins"]
         if torch.equal(torch.bucketize(o["energy"], ebins), torch.bucketize(r["energy"], ebins)):
             assert max_abs(o["postnet_mel"], r["postnet_mel"]) < 2e-3
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# upsampler="gaussian": GaussianUpsampling (modules.py:162-192) in the LengthRegulator's place
+@pytest.mark.parametrize("enc_prec,dec_prec", [("fp32", "fp32"), ("f16x2", "f16x2"), ("f16x2", "bf16")])
+def test_forward_gaussian_golden(lib, enc_prec, dec_prec):
+    """golden = the reference module run with its own GaussianUpsampling class swapped in (oracle/gen_golden.py)."""
+    g = load_golden("gaussian_forward")
+    sd, d, stats, pq = golden_state_dict(g)
+    m = build_model(sd, stats, pq, upsampler="gaussian").set_precision(enc_prec, dec_prec)
+    ref = [torch.from_numpy(g[k]) for k in NAMES[:8]] + [torch.from_numpy(g["src_lens"]), torch.from_numpy(g["mel_lens"])]
+    out = run_model(m, torch.from_numpy(g["speakers"]), torch.from_numpy(g["texts"]), torch.from_numpy(g["src_lens"]),
+                    int(g["max_src_len"]))
+    check_against(ref, out[:10], sd, dec_prec)
+    # the switch really changes the result: the hard regulator gives different mels on the same inputs
+    hard = run_model(m.set_upsampler("hard"), torch.from_numpy(g["speakers"]), torch.from_numpy(g["texts"]),
+                     torch.from_numpy(g["src_lens"]), int(g["max_src_len"]))
+    assert torch.equal(hard[5], out[5]) and max_abs(hard[0], out[0]) > 1e-2
+
+
+@pytest.mark.parametrize("dec_prec", ["f16x2", "bf16"])
+def test_forward_gaussian_oracle_batch(lib, dec_prec):
+    """Ragged batch 16, lengths 20..120 (T ~ 900, several 64-frame tiles and phoneme chunks per utterance, padded phoneme
+    slots that keep their weight), packed rows == padded grid, and a shard of the batch == the same rows of the whole."""
+    sd = O.make_state_dict(0)
+    speakers, texts, src_lens, L = O.make_inputs(16, 20, 120, seed=21)
+    ref = list(O.forward(sd, O.Dims(), speakers, texts, src_lens, L, upsampler="gaussian")[:10])
+    m = build_model(sd, O.STATS_NAN_BINS, upsampler="gaussian").set_precision("f16x2", dec_prec)
+    out = run_model(m, speakers, texts, src_lens, L)
+    st = check_against(ref, out[:10], sd, dec_prec)
+    print(f"gaussian batch16 dec={dec_prec}: T {ref[0].shape[1]} flips {st['flips']} mel relRMS {st['mel'][0]:.2e} max {st['mel'][1]:.2e}")
+    padded = run_model(m.set_row_packing(1 << 20), speakers, texts, src_lens, L)
+    for i, (a, b) in enumerate(zip(out[:10], padded[:10])):
+        assert torch.equal(a, b), f"output {i} differs between packed and padded layouts"

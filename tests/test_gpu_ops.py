@@ -125,6 +125,43 @@ def test_gaussian_upsample_oracle(lib, B, L, pad):
     assert torch.equal(out2, out)
 
 
+def test_gaussian_upsample_c5_shape_and_edge_cases(lib):
+    """BASELINE configs[4] shape (batch 64 x 300 phonemes -> T ~ 2000; 8 utterances checked against the oracle to keep the
+    CPU side short), D not a multiple of 256 (two channel slabs), fractional and negative durations (non-monotone centres:
+    full-range fallback), an all-zero utterance."""
+    rng = np.random.Generator(np.random.PCG64(5))
+    B, L = 8, 300
+    x = torch.from_numpy(rng.standard_normal((B, L, 256)).astype(np.float32))
+    d = torch.from_numpy(np.clip(np.round(rng.normal(6.7, 3.0, size=(B, L))), 0, 30).astype(np.float32))
+    for b in range(B):
+        d[b, 300 - 20 * b:] = 0.0                                       # padded phoneme slots (no masking in the reference)
+    T_w = int(d.sum(1).max())
+    ref, ref_s, ref_w = O.gaussian_upsample(x, d, None)
+    out = torch.empty(B, T_w, 256, device=DEV)
+    s = torch.empty(B, device=DEV)
+    w = torch.empty(B, L, T_w, device=DEV)
+    lib.check(lib.fs2_gaussian_upsample(x.to(DEV).data_ptr(), d.to(DEV).data_ptr(), B, L, 256, T_w, T_w, out.data_ptr(),
+                                        s.data_ptr(), w.data_ptr(), stream()))
+    assert torch.equal(s.cpu(), ref_s.flatten())
+    assert max_abs(w.cpu(), ref_w) < 2e-6 and max_abs(out.cpu(), ref) < 5e-5
+    # D = 320 (slabs of 256 + 64), fractional / negative durations, a silent utterance
+    B, L, D = 3, 37, 320
+    x = torch.from_numpy(rng.standard_normal((B, L, D)).astype(np.float32))
+    d = torch.from_numpy(rng.uniform(0.0, 9.0, size=(B, L)).astype(np.float32))
+    d[1, 5] = -3.5
+    d[2] = 0.0
+    ref, ref_s, ref_w = O.gaussian_upsample(x, d, None)
+    T_w = ref.shape[1]
+    out = torch.full((B, T_w + 3, D), 7.0, device=DEV)
+    s = torch.empty(B, device=DEV)
+    w = torch.empty(B, L, T_w, device=DEV)
+    lib.check(lib.fs2_gaussian_upsample(x.to(DEV).data_ptr(), d.to(DEV).data_ptr(), B, L, D, T_w + 3, T_w, out.data_ptr(),
+                                        s.data_ptr(), w.data_ptr(), stream()))
+    assert max_abs(s.cpu(), ref_s.flatten()) < 1e-4
+    assert max_abs(w.cpu(), ref_w) < 5e-6 and max_abs(out.cpu()[:, :T_w], ref) < 1e-4
+    assert bool((out[:, T_w:] == 0).all())
+
+
 def test_sinusoid_table(lib, oph):
     n = 1300
     out = torch.empty(n, 256, device=DEV)

@@ -9,12 +9,13 @@ import fs2_oracle as O
 from helpers import golden_state_dict, load_golden, max_abs
 
 
-@pytest.mark.parametrize("case", ["small_nanbins", "small_finitebins", "ragged_linearbins", "longform"])
+@pytest.mark.parametrize("case", ["small_nanbins", "small_finitebins", "ragged_linearbins", "longform", "gaussian_forward"])
 def test_oracle_matches_reference_golden(case):
     g = load_golden(case)
     sd, d, stats, pq = golden_state_dict(g)
+    # gaussian_forward: the reference module with its own GaussianUpsampling class in the LengthRegulator's place
     out = O.forward(sd, d, torch.from_numpy(g["speakers"]), torch.from_numpy(g["texts"]), torch.from_numpy(g["src_lens"]),
-                    int(g["max_src_len"]))
+                    int(g["max_src_len"]), upsampler="gaussian" if case == "gaussian_forward" else "hard")
     names = ["mel", "postnet_mel", "pitch", "energy", "log_d", "d_rounded", "src_masks", "mel_masks"]
     for nm, t in zip(names, out):
         ref = torch.from_numpy(g[nm])
