@@ -175,6 +175,30 @@ int64_t fs2_last_frame_count(const fs2_handle* h);
 int fs2_forward_stage2(fs2_handle* h, int32_t T, float p_control, float e_control, float* mel, float* mel_post,
                        float* pitch, float* energy, uint8_t* mel_mask, void* stream);
 
+/* ---- the same two stages through the handle's CUDA-graph cache ------------------------------------------------------
+ * replaces: the per-batch launch sequence of the reference's driver loop (synthesize.py:59-76) -- ~30 + ~38 kernel
+ * launches per forward -- by two cudaGraphLaunch calls.  Graphs are keyed on
+ * (B, L bucket) for stage 1 and (B, L bucket, T bucket) for stage 2 plus every pointer and control value baked into the
+ * launches, so the caller passes L_cap / T_cap = the upper bound of the bucket the true L / T falls in (any policy: the
+ * library only needs L <= L_cap, T <= T_cap) and REUSES its output buffers from call to call.  The true L / T travel
+ * through device memory and every kernel reads them from there, so the results are bit-identical to
+ * fs2_forward_stage1 / fs2_forward_stage2 on the exact shapes: a bucket only bounds grid and workspace sizes.
+ *   - outputs: caller-owned buffers with room for the bucket ([B, L_cap] / [B, T_cap, n_mel] / ... elements); they are
+ *     written DENSELY with the true shape ([B, L] / [B, T, n_mel]: the first B*L / B*T*n_mel elements).
+ *   - texts [B, L] / src_lens [B] may change from call to call (they are copied to staging buffers first).
+ *   - first call with a key: plain launches (sizes the workspace); second: stream capture + instantiate; then replays.
+ *     Growth of the workspace, new weights or a changed setting invalidate the cached graphs (re-captured on demand).
+ *   - a bucket never straddles max_seq_len (the positional table differs on either side): L_cap / T_cap are clamped.
+ * The only blocking call is still the 8-byte read-back of {T_max, frames} at the end of stage 1. */
+int fs2_forward_stage1_graph(fs2_handle* h, const int64_t* texts, const int64_t* src_lens, int32_t B, int32_t L,
+                             int32_t L_cap, float p_control, float e_control, float d_control, float* log_d,
+                             float* d_rounded, int64_t* mel_lens, uint8_t* src_mask, float* pitch_ph, float* energy_ph,
+                             int32_t* T_max_out, void* stream);
+int fs2_forward_stage2_graph(fs2_handle* h, int32_t T, int32_t T_cap, float p_control, float e_control, float* mel,
+                             float* mel_post, float* pitch, float* energy, uint8_t* mel_mask, void* stream);
+/* graphs currently instantiated on this handle, graph launches and captures since creation (any pointer may be NULL) */
+int fs2_graph_stats(const fs2_handle* h, int64_t* n_graphs, int64_t* replays, int64_t* captures);
+
 /* ---- stand-alone operators (no weights) -------------------------------------------- */
 /* modules.py:132-135: out = clamp(round(exp(log_d) - 1) * d_control, min=0); n elements */
 int fs2_round_durations(const float* log_d, int64_t n, float d_control, float* out, void* stream);

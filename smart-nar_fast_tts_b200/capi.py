@@ -64,6 +64,9 @@ SIGNATURES = {
     "fs2_forward_stage1_async": (C.c_int, [_P, _P, _P, _I, _I, _F, _F, _F, _P, _P, _P, _P, _P, _P, _P, _P]),
     "fs2_forward_stage1_commit": (C.c_int, [_P, _I, _I]),
     "fs2_forward_stage2": (C.c_int, [_P, _I, _F, _F, _P, _P, _P, _P, _P, _P]),
+    "fs2_forward_stage1_graph": (C.c_int, [_P, _P, _P, _I, _I, _I, _F, _F, _F, _P, _P, _P, _P, _P, _P, C.POINTER(_I), _P]),
+    "fs2_forward_stage2_graph": (C.c_int, [_P, _I, _I, _F, _F, _P, _P, _P, _P, _P, _P]),
+    "fs2_graph_stats": (C.c_int, [_P, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "fs2_round_durations": (C.c_int, [_P, C.c_int64, _F, _P, _P]),
     "fs2_duration_scan": (C.c_int, [_P, _I, _I, _P, _P, C.POINTER(_I), _P]),
     "fs2_length_regulate": (C.c_int, [_P, _P, _I, _I, _I, _I, _P, _P]),

@@ -107,6 +107,31 @@ struct fs2_handle {
     cudaEventCreate(&e);
     return e;
   }
+  // CUDA-graph cache (fs2_forward_stage*_graph): one instantiated graph per (stage, B, bucket, pointers, controls).  A graph
+  // bakes in every workspace / weight / table pointer and every setting its launches read, so `gen` is bumped whenever one
+  // of those may have changed (workspace growth, position-table growth, weights, precision, packing, layouts): an entry
+  // captured under an older generation is re-captured at its next use.
+  struct GraphEntry {
+    cudaGraphExec_t exec = nullptr;
+    unsigned long long gen = 0;
+    int seen = 0;            // 0 = never run, 1 = ran eagerly once (workspace sized), -1 = capture failed: always eager
+    long long kernels = 0;   // kernel nodes (for fs2_launch_count)
+    // host-side state stage 1 leaves for stage 2: a replay launches no host code, so it is restored from here
+    int st_B = 0, st_L = 0; float* st_enc_out = nullptr; RowLayout st_lay1{}; const int* st_Ldev = nullptr;
+  };
+  std::map<std::string, GraphEntry> graphs;
+  unsigned long long gen = 1;
+  long long graph_replays = 0, graph_captures = 0;
+  int* shape_host = nullptr;   // pinned int[4]: {L, T} of the forward in flight (copied to shape_dev before a graph launch)
+  int* shape_dev = nullptr;    // device int[4] the replayed kernels read the true L / T from
+  const int* cur_Ldev = nullptr;  // non-null while a *_graph entry point enqueues: true L / T live in shape_dev
+  const int* cur_Tdev = nullptr;
+  const int* st_Ldev = nullptr;   // stage 1 ran with L as an upper bound: [B, L] tensors (cum, ...) have the TRUE row stride
+  void drop_graphs() {
+    for (auto& kv : graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+    graphs.clear();
+    ++gen;
+  }
   // stage-1 -> stage-2 state
   bool have_stage1 = false;
   int st_B = 0, st_L = 0, st_Tmax = 0;
@@ -131,6 +156,7 @@ struct fs2_handle {
       cudaFree(it->second.first);
       ws.erase(it);
     }
+    ++gen;   // a buffer moved (or appeared): graphs captured before this do not know it
     size_t cap = bytes + bytes / 4 + 256;
     void* p = nullptr;
     if (cudaMalloc(&p, cap) != cudaSuccess) return nullptr;
@@ -305,6 +331,7 @@ int position_table(fs2_handle* h, int stack, int S, const float** out, cudaStrea
   if (h->pe_ext_n[stack] < S) {
     if (h->pe_ext[stack]) cudaFree(h->pe_ext[stack]);
     h->pe_ext[stack] = nullptr;
+    ++h->gen;
     const int n = S + S / 4;
     HCHECK(cudaMalloc(reinterpret_cast<void**>(&h->pe_ext[stack]), sizeof(float) * (size_t)n * D));
     RCHECK(sinusoid_table_host(h, n, D, h->pe_ext[stack], st));
@@ -331,7 +358,7 @@ cudaError_t make_shadow(const float* x, size_t n, int prec, bf16* xb, cudaStream
 // extra_ext > 0: one pseudo utterance with extra_ext grid rows is appended (index B; the layout then has B + 1
 // utterances and carries no lens pointer: it is used with MASK_GRID only).
 int make_layout(fs2_handle* h, const std::string& name, const int* lens32, int B, int S, int halo_keep, int halo_rows,
-                RowLayout* out, cudaStream_t st, int extra_ext = 0) {
+                RowLayout* out, cudaStream_t st, int extra_ext = 0, const int* S_dev = nullptr) {
   const int Bt = B + (extra_ext > 0 ? 1 : 0);
   if (Bt > 65535) return h->fail(FS2_ERR_UNSUPPORTED, "more than 65535 utterances in one call");
   if (S > FS2_MAX_ROWS_PER_UTT) return h->fail(FS2_ERR_UNSUPPORTED, "more than 65535 rows per utterance");
@@ -340,10 +367,11 @@ int make_layout(fs2_handle* h, const std::string& name, const int* lens32, int B
   WS(int, off, name + ".off", (size_t)Bt + 1);
   WS(int, ext, name + ".ext", (size_t)Bt);
   WS(unsigned, rowmap, name + ".map", (size_t)R_cap);
-  HCHECK(rowops_build_layout(lens32, B, S, halo_keep, halo_rows, off, ext, rowmap, R_cap, st, extra_ext));
+  HCHECK(rowops_build_layout(lens32, B, S, halo_keep, halo_rows, off, ext, rowmap, R_cap, st, extra_ext, S_dev));
   out->B = Bt; out->S = S; out->R_cap = R_cap; out->off = off; out->ext = ext; out->lens = extra_ext > 0 ? nullptr : lens32;
   out->rowmap = rowmap;
   out->rows_hint = 0;
+  out->S_dev = S_dev;
   return FS2_OK;
 }
 
@@ -358,7 +386,7 @@ struct TmpLayout {
     if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&ext), sizeof(int) * (size_t)B);
     if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&map), sizeof(unsigned) * (size_t)(R_cap > 0 ? R_cap : 1));
     if (e == cudaSuccess) e = rowops_build_layout(lens32, B, S, halo_keep, halo_rows, off, ext, map, R_cap, st);
-    lay = RowLayout{B, S, R_cap, off, ext, lens32, map};
+    lay = RowLayout{B, S, R_cap, off, ext, lens32, map, 0, nullptr};
     return e;
   }
   ~TmpLayout() { cudaFree(off); cudaFree(ext); cudaFree(map); }
@@ -534,7 +562,8 @@ int run_mel_postnet(fs2_handle* h, int prec, const float* dec, const bf16* decb,
   RowLayout pn;
   // never fewer rows than the source layout carries (mel_linear scatters every source grid row into this grid)
   const int keep = !lay.lens ? T : (h->halo_keep > 2 * H ? h->halo_keep : 2 * H);
-  RCHECK(make_layout(h, "pn.lay", lay.lens, B, T, keep, FS2_HALO, &pn, st, T < 2 * H + 1 ? T : 2 * H + 1));
+  // the pseudo utterance has min(T, 2H + 1) rows: the layout kernel clamps to the true T itself when T is a device value
+  RCHECK(make_layout(h, "pn.lay", lay.lens, B, T, keep, FS2_HALO, &pn, st, T < 2 * H + 1 ? T : 2 * H + 1, lay.S_dev));
   if (lay.rows_hint > 0 && keep < T) {
     const long long est = (long long)lay.rows_hint + (long long)B * (keep - h->halo_keep) + 4 * H;
     pn.rows_hint = (int)(est < pn.R_cap ? est : pn.R_cap);
@@ -641,6 +670,9 @@ void fs2_destroy(fs2_handle* h) {
   if (!h) return;
   cudaSetDevice(h->device);
   cudaDeviceSynchronize();
+  h->drop_graphs();
+  if (h->shape_host) cudaFreeHost(h->shape_host);
+  if (h->shape_dev) cudaFree(h->shape_dev);
   h->w.reset();   // frees the weights when this was the last handle using them
   for (auto& kv : h->ws) cudaFree(kv.second.first);
   for (int i = 0; i < 2; ++i) if (h->pe_ext[i]) cudaFree(h->pe_ext[i]);
@@ -657,6 +689,7 @@ int fs2_set_precision(fs2_handle* h, int32_t enc, int32_t dec) {
     return h->fail(FS2_ERR_INVALID, "precision must be FS2_PREC_FP32, FS2_PREC_BF16, FS2_PREC_BF16X3 or FS2_PREC_F16X2");
   h->prec_enc = enc;
   h->prec_dec = dec;
+  h->drop_graphs();
   return FS2_OK;
 }
 
@@ -665,6 +698,7 @@ int fs2_set_row_packing(fs2_handle* h, int32_t keep_rows) {
   if (keep_rows < 2) return h->fail(FS2_ERR_INVALID, "keep_rows must be >= 2 (the variance predictors' halo)");
   h->halo_keep = keep_rows;
   h->have_stage1 = false;
+  h->drop_graphs();
   return FS2_OK;
 }
 
@@ -672,6 +706,7 @@ int fs2_set_mel_post_layout(fs2_handle* h, int32_t channel_major) {
   if (!h) return FS2_ERR_INVALID;
   if (channel_major != 0 && channel_major != 1) return h->fail(FS2_ERR_INVALID, "channel_major must be 0 or 1");
   h->mel_post_cm = channel_major;
+  h->drop_graphs();
   return FS2_OK;
 }
 
@@ -680,6 +715,7 @@ int fs2_set_upsampler(fs2_handle* h, int32_t upsampler) {
   if (upsampler != FS2_UPSAMPLER_HARD && upsampler != FS2_UPSAMPLER_GAUSSIAN)
     return h->fail(FS2_ERR_INVALID, "upsampler must be FS2_UPSAMPLER_HARD or FS2_UPSAMPLER_GAUSSIAN");
   h->upsampler = upsampler;
+  h->drop_graphs();
   return FS2_OK;
 }
 
@@ -691,6 +727,7 @@ int fs2_load_weights(fs2_handle* h, const fs2_weight_desc* descs, int32_t n) {
   cudaStream_t st = 0;
   // a fresh weight block: handles that share the previous one keep running on it until they load or share again
   h->loaded = false;
+  h->drop_graphs();
   h->w = std::make_shared<fs2_weights>();
   h->w->device = h->device;
   h->have_stage1 = false;
@@ -758,6 +795,7 @@ int fs2_share_weights(fs2_handle* h, const fs2_handle* src) {
   if (!src->loaded || !src->w) return h->fail(FS2_ERR_STATE, "share_weights: the source handle has no weights loaded");
   if (h->device != src->device) return h->fail(FS2_ERR_INVALID, "share_weights: handles live on different devices");
   if (memcmp(&h->dims, &src->dims, sizeof(fs2_dims)) != 0) return h->fail(FS2_ERR_INVALID, "share_weights: dims differ");
+  h->drop_graphs();
   h->w = src->w;
   h->loaded = true;
   h->have_stage1 = false;
@@ -790,10 +828,11 @@ static int stage1_enqueue(fs2_handle* h, const int64_t* texts, const int64_t* sr
   WS(int, cum, "s1.cum", (size_t)B * L);
   WS(int, mlens32, "s1.mel_lens32", B);
   WS(int, tmax_dev, "s1.tmax", 2);   // [0] max frames of an utterance, [1] frames of the batch
-  HCHECK(rowops_lens_to_i32(src_lens, B, L, lens32, st, tmax_dev));   // also clears the {T_max, frames} accumulators
+  const int* Ldev = h->cur_Ldev;   // graph entry point: L is the bucket's bound, the true L is read from device memory
+  HCHECK(rowops_lens_to_i32(src_lens, B, L, lens32, st, tmax_dev, Ldev));   // also clears the {T_max, frames} accumulators
   // packed phoneme rows: valid rows + the 2 padded rows the duration predictor's convolutions can see (+ zero halo)
   RowLayout lay;
-  RCHECK(make_layout(h, "s1.lay", lens32, B, L, h->halo_keep, FS2_HALO, &lay, st));
+  RCHECK(make_layout(h, "s1.lay", lens32, B, L, h->halo_keep, FS2_HALO, &lay, st, 0, Ldev));
   const size_t R = (size_t)lay.R_cap;
   WS(float, x, "s1.x", R * D);
   bf16* xb = nullptr;
@@ -805,7 +844,7 @@ static int stage1_enqueue(fs2_handle* h, const int64_t* texts, const int64_t* sr
   RCHECK(position_table(h, 0, L, &pe, st));
   {
     PROF("rows.embed_pe");
-    if (src_mask) HCHECK(rowops_mask(src_lens, nullptr, B, L, src_mask, st, log_d));   // + log_d cleared in the same pass
+    if (src_mask) HCHECK(rowops_mask(src_lens, nullptr, B, L, src_mask, st, log_d, nullptr, Ldev));   // + log_d cleared in the same pass
     HCHECK(rowops_embed_pe(texts, raw_ptr(h, "txt_encoder.src_word_emb.weight"), pe, d.vocab, lay, D, x, xb,
                            planes_of(h->prec_enc), nullptr, st));
   }
@@ -828,9 +867,10 @@ static int stage1_enqueue(fs2_handle* h, const int64_t* texts, const int64_t* sr
   // modules.py:132-135 + LengthRegulator bookkeeping
   {
     PROF("rows.round_scan");
-    HCHECK(rowops_round_scan(log_d, d_control, d_rounded, B, L, cum, mel_lens, mlens32, tmax_dev, st));
+    HCHECK(rowops_round_scan(log_d, d_control, d_rounded, B, L, cum, mel_lens, mlens32, tmax_dev, st, Ldev));
   }
   h->st_B = B; h->st_L = L;
+  h->st_Ldev = Ldev;
   h->st_enc_out = x;
   h->st_lay1 = lay;
   *tmax_out = tmax_dev;
@@ -881,32 +921,42 @@ int fs2_forward_stage1_commit(fs2_handle* h, int32_t T_max, int32_t frames) {
   return FS2_OK;
 }
 
-int fs2_forward_stage2(fs2_handle* h, int32_t T, float p_control, float e_control, float* mel, float* mel_post,
-                       float* pitch, float* energy, uint8_t* mel_mask, void* stream) {
-  g_fs2_plain_next = 1;   // the first launch of an entry point is fully stream-ordered (fs2_common.cuh)
-  if (!h) return FS2_ERR_INVALID;
+}  // extern "C"
+
+static int stage2_check(fs2_handle* h, int32_t T, float* mel, float* mel_post, float* pitch, float* energy) {
   if (!h->loaded || !h->have_stage1) return h->fail(FS2_ERR_STATE, "stage2 called before a successful stage1");
   if (T < h->st_Tmax) return h->fail(FS2_ERR_INVALID, "stage2: T smaller than the stage-1 maximum mel length");
   const fs2_dims& d = h->dims;
-  if (T == 0) return FS2_OK;  // degenerate batch (all durations zero): nothing to write
-  if (h->upsampler == FS2_UPSAMPLER_GAUSSIAN && (d.pitch_phoneme_level || d.energy_phoneme_level))
-    return h->fail(FS2_ERR_UNSUPPORTED, "stage2: the Gaussian upsampler is built for frame-level pitch / energy (with "
-                   "phoneme-level features the padded phoneme rows are not zero and would need their embedding rows)");
+  if (T == 0) return FS2_OK;
   if (T > FS2_MAX_ROWS_PER_UTT) return h->fail(FS2_ERR_UNSUPPORTED, "stage2: more than 65535 mel frames per utterance");
   if (!mel || !mel_post || (!d.pitch_phoneme_level && !pitch) || (!d.energy_phoneme_level && !energy))
     return h->fail(FS2_ERR_INVALID, "stage2: null output pointer");
+  if (h->upsampler == FS2_UPSAMPLER_GAUSSIAN && (d.pitch_phoneme_level || d.energy_phoneme_level))
+    return h->fail(FS2_ERR_UNSUPPORTED, "stage2: the Gaussian upsampler is built for frame-level pitch / energy (with "
+                   "phoneme-level features the padded phoneme rows are not zero and would need their embedding rows)");
+  return FS2_OK;
+}
+
+// everything stage 2 enqueues.  T = rows per utterance of the outputs: the exact value, or (h->cur_Tdev set) the bucket's
+// upper bound while the true value is read from device memory by the kernels.
+static int stage2_enqueue(fs2_handle* h, int32_t T, float p_control, float e_control, float* mel, float* mel_post,
+                          float* pitch, float* energy, uint8_t* mel_mask, void* stream) {
+  g_fs2_plain_next = 1;   // the first launch of an entry point is fully stream-ordered (fs2_common.cuh)
+  const fs2_dims& d = h->dims;
   HCHECK(cudaSetDevice(h->device));
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int B = h->st_B, L = h->st_L, D = d.d_model;
+  const int* Tdev = h->cur_Tdev;
   const int* cum = reinterpret_cast<int*>(h->ws["s1.cum"].first);
   const int* mlens32 = reinterpret_cast<int*>(h->ws["s1.mel_lens32"].first);
   const bool pitch_fl = !d.pitch_phoneme_level, energy_fl = !d.energy_phoneme_level;
 
   // packed frame rows: valid frames + the 2 padded rows the pitch / energy predictors can see (+ zero halo)
   RowLayout lay;
-  RCHECK(make_layout(h, "s2.lay", mlens32, B, T, h->halo_keep, FS2_HALO, &lay, st));
-  // rows in use, estimated on the host from the batch's frame count (exact up to the 8-row alignment of each utterance)
-  if (h->halo_keep < T) {
+  RCHECK(make_layout(h, "s2.lay", mlens32, B, T, h->halo_keep, FS2_HALO, &lay, st, 0, Tdev));
+  // rows in use, estimated on the host from the batch's frame count (exact up to the 8-row alignment of each utterance);
+  // a graph is replayed for other batches of its bucket, so it keeps the allocation's bound
+  if (h->halo_keep < T && !Tdev) {
     const long long est = (long long)h->st_frames + (long long)B * (h->halo_keep + FS2_HALO + FS2_ROW_ALIGN / 2);
     lay.rows_hint = (int)(est < lay.R_cap ? est : lay.R_cap);
   }
@@ -924,13 +974,14 @@ int fs2_forward_stage2(fs2_handle* h, int32_t T, float p_control, float e_contro
   const int first_prec = (pitch_fl || energy_fl) ? h->prec_enc : FS2_PREC_FP32;
   {
     PROF("rows.length_regulate");
-    if (mel_mask) HCHECK(rowops_mask(nullptr, mlens32, B, T, mel_mask, st, pitch_fl ? pitch : nullptr, energy_fl ? energy : nullptr));
+    if (mel_mask) HCHECK(rowops_mask(nullptr, mlens32, B, T, mel_mask, st, pitch_fl ? pitch : nullptr, energy_fl ? energy : nullptr, Tdev));
     // modules.py:136 length regulator (hard): gathers encoder rows (stage-1 layout) into frame rows (stage-2 layout)
     if (h->upsampler == FS2_UPSAMPLER_GAUSSIAN)   // modules.py:162-192 in the LengthRegulator's place (README.md:10 of the reference)
       HCHECK(rowops_gaussian_regulate(h->st_enc_out, h->st_lay1.off, h->st_lay1.lens, cum, L, D, lay, x, xb,
-                                      planes_of(first_prec), st));
+                                      planes_of(first_prec), st, h->st_Ldev));
     else
-      HCHECK(rowops_length_regulate(h->st_enc_out, h->st_lay1.off, 0, cum, L, D, lay, x, xb, planes_of(first_prec), st));
+      HCHECK(rowops_length_regulate(h->st_enc_out, h->st_lay1.off, 0, cum, L, D, lay, x, xb, planes_of(first_prec), st,
+                                    h->st_Ldev));
   }
   const float* pe = nullptr;
   RCHECK(position_table(h, 1, T, &pe, st));
@@ -956,6 +1007,162 @@ int fs2_forward_stage2(fs2_handle* h, int32_t T, float p_control, float e_contro
   }
   RCHECK(run_fft_stack(h, h->w->dec, 0, d.n_dec_layers, h->prec_dec, x, xb, lay, st));
   RCHECK(run_mel_postnet(h, h->prec_dec, x, xb, lay, mel, mel_post, st));
+  return FS2_OK;
+}
+
+extern "C" {
+
+int fs2_forward_stage2(fs2_handle* h, int32_t T, float p_control, float e_control, float* mel, float* mel_post,
+                       float* pitch, float* energy, uint8_t* mel_mask, void* stream) {
+  if (!h) return FS2_ERR_INVALID;
+  RCHECK(stage2_check(h, T, mel, mel_post, pitch, energy));
+  if (T == 0) return FS2_OK;  // degenerate batch (all durations zero): nothing to write
+  return stage2_enqueue(h, T, p_control, e_control, mel, mel_post, pitch, energy, mel_mask, stream);
+}
+
+}  // extern "C"
+
+// Runs `enqueue` (a lambda that launches one stage on `st`) through the handle's graph cache: first sighting of a key =
+// plain launches (sizes the workspace), second = stream capture + instantiate + launch, afterwards = one cudaGraphLaunch.
+// Returns FS2_OK with *replayed = true when the work went out as a graph launch (no host-side stage code ran).
+template <typename F>
+static int run_graphed(fs2_handle* h, const std::string& key, cudaStream_t st, bool* replayed, F&& enqueue) {
+  fs2_handle::GraphEntry& e = h->graphs[key];
+  *replayed = false;
+  if (e.exec && e.gen == h->gen) {
+    HCHECK(cudaGraphLaunch(e.exec, st));
+    g_fs2_launches += e.kernels;
+    g_fs2_plain_next = 1;
+    ++h->graph_replays;
+    *replayed = true;
+    return FS2_OK;
+  }
+  if (e.exec) { cudaGraphExecDestroy(e.exec); e.exec = nullptr; }   // captured under an older generation
+  if (e.seen <= 0 || h->prof_on) {       // first sighting (or tracing on, or capture known to fail): plain launches
+    if (e.seen == 0) e.seen = 1;
+    return enqueue();
+  }
+  const unsigned long long gen0 = h->gen;
+  const long long l0 = g_fs2_launches.load();
+  // relaxed mode: the stage code may still call cudaMalloc / cudaFuncSetAttribute; it must not synchronise `st`
+  HCHECK(cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed));
+  const int rc = enqueue();
+  cudaGraph_t g = nullptr;
+  cudaError_t ce = cudaStreamEndCapture(st, &g);
+  cudaGraphExec_t ex = nullptr;
+  if (rc == FS2_OK && ce == cudaSuccess && g && h->gen == gen0) ce = cudaGraphInstantiate(&ex, g, 0);
+  if (g) cudaGraphDestroy(g);
+  if (rc != FS2_OK) { (void)cudaGetLastError(); return rc; }
+  if (ce != cudaSuccess || !ex || h->gen != gen0) {
+    // nothing has run yet (the launches were only recorded).  A buffer moved during the capture: try again next time;
+    // capture / instantiation itself failed: this key stays on plain launches.
+    (void)cudaGetLastError();
+    if (ex) cudaGraphExecDestroy(ex);
+    if (h->gen == gen0) e.seen = -1;
+    g_fs2_launches -= g_fs2_launches.load() - l0;
+    return enqueue();
+  }
+  e.exec = ex;
+  e.gen = gen0;
+  e.kernels = g_fs2_launches.load() - l0;
+  ++h->graph_captures;
+  HCHECK(cudaGraphLaunch(ex, st));
+  g_fs2_plain_next = 1;
+  return FS2_OK;
+}
+
+static int graph_shape_buffers(fs2_handle* h) {
+  if (!h->shape_host) HCHECK(cudaMallocHost(reinterpret_cast<void**>(&h->shape_host), 4 * sizeof(int)));
+  if (!h->shape_dev) {
+    HCHECK(cudaMalloc(reinterpret_cast<void**>(&h->shape_dev), 4 * sizeof(int)));
+    ++h->gen;
+  }
+  return FS2_OK;
+}
+
+extern "C" {
+
+int fs2_forward_stage1_graph(fs2_handle* h, const int64_t* texts, const int64_t* src_lens, int32_t B, int32_t L,
+                             int32_t L_cap, float p_control, float e_control, float d_control, float* log_d,
+                             float* d_rounded, int64_t* mel_lens, uint8_t* src_mask, float* pitch_ph, float* energy_ph,
+                             int32_t* T_max_out, void* stream) {
+  if (!h) return FS2_ERR_INVALID;
+  if (!T_max_out) return h->fail(FS2_ERR_INVALID, "stage1_graph: null T_max_out");
+  if (!h->loaded) return h->fail(FS2_ERR_STATE, "fs2_load_weights has not succeeded on this handle");
+  if (!texts || !src_lens || B <= 0 || L <= 0 || L_cap < L) return h->fail(FS2_ERR_INVALID, "stage1_graph: bad argument (need 0 < L <= L_cap)");
+  // one bucket never straddles max_seq_len: below it the positional table is the checkpoint's, above it the computed one
+  if (L <= h->dims.max_seq_len && L_cap > h->dims.max_seq_len) L_cap = h->dims.max_seq_len;
+  HCHECK(cudaSetDevice(h->device));
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  RCHECK(graph_shape_buffers(h));
+  // the caller's input tensors change from call to call, the graph reads fixed staging copies ([B, L] with the TRUE L)
+  WS(int64_t, g_texts, "g1.texts", (size_t)B * L_cap);
+  WS(int64_t, g_lens, "g1.lens", (size_t)B);
+  h->shape_host[0] = L;
+  HCHECK(cudaMemcpyAsync(g_texts, texts, sizeof(int64_t) * (size_t)B * L, cudaMemcpyDeviceToDevice, st));
+  HCHECK(cudaMemcpyAsync(g_lens, src_lens, sizeof(int64_t) * (size_t)B, cudaMemcpyDeviceToDevice, st));
+  HCHECK(cudaMemcpyAsync(h->shape_dev, h->shape_host, sizeof(int), cudaMemcpyHostToDevice, st));
+  char key[512];
+  snprintf(key, sizeof key, "s1|%d|%d|%p|%p|%p|%p|%p|%p|%a|%a|%a", B, L_cap, (void*)log_d, (void*)d_rounded, (void*)mel_lens,
+           (void*)src_mask, (void*)pitch_ph, (void*)energy_ph, p_control, e_control, d_control);
+  bool replayed = false;
+  h->cur_Ldev = h->shape_dev;
+  const int rc = run_graphed(h, key, st, &replayed, [&]() -> int {
+    int* tm = nullptr;
+    RCHECK(stage1_enqueue(h, g_texts, g_lens, B, L_cap, p_control, e_control, d_control, log_d, d_rounded, mel_lens,
+                          src_mask, pitch_ph, energy_ph, &tm, stream));
+    HCHECK(cudaMemcpyAsync(h->host_tmax, tm, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
+    return FS2_OK;
+  });
+  h->cur_Ldev = nullptr;
+  RCHECK(rc);
+  fs2_handle::GraphEntry& e = h->graphs[key];
+  if (replayed) {
+    h->st_B = e.st_B; h->st_L = e.st_L; h->st_enc_out = e.st_enc_out; h->st_lay1 = e.st_lay1; h->st_Ldev = e.st_Ldev;
+  } else {
+    e.st_B = h->st_B; e.st_L = h->st_L; e.st_enc_out = h->st_enc_out; e.st_lay1 = h->st_lay1; e.st_Ldev = h->st_Ldev;
+  }
+  HCHECK(cudaStreamSynchronize(st));  // the one data-dependent size of the path
+  *T_max_out = h->host_tmax[0];
+  h->have_stage1 = true;
+  h->st_Tmax = h->host_tmax[0];
+  h->st_frames = h->host_tmax[1];
+  return FS2_OK;
+}
+
+int fs2_forward_stage2_graph(fs2_handle* h, int32_t T, int32_t T_cap, float p_control, float e_control, float* mel,
+                             float* mel_post, float* pitch, float* energy, uint8_t* mel_mask, void* stream) {
+  if (!h) return FS2_ERR_INVALID;
+  RCHECK(stage2_check(h, T, mel, mel_post, pitch, energy));
+  if (T == 0) return FS2_OK;
+  if (T_cap < T) return h->fail(FS2_ERR_INVALID, "stage2_graph: T_cap smaller than T");
+  if (T <= h->dims.max_seq_len && T_cap > h->dims.max_seq_len) T_cap = h->dims.max_seq_len;
+  if (T_cap > FS2_MAX_ROWS_PER_UTT) T_cap = FS2_MAX_ROWS_PER_UTT;
+  HCHECK(cudaSetDevice(h->device));
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  RCHECK(graph_shape_buffers(h));
+  h->shape_host[1] = T;
+  HCHECK(cudaMemcpyAsync(h->shape_dev + 1, h->shape_host + 1, sizeof(int), cudaMemcpyHostToDevice, st));
+  char key[512];
+  snprintf(key, sizeof key, "s2|%d|%d|%d|%d|%p|%p|%p|%p|%p|%a|%a", h->st_B, h->st_L, h->st_Ldev ? 1 : 0, T_cap, (void*)mel,
+           (void*)mel_post, (void*)pitch, (void*)energy, (void*)mel_mask, p_control, e_control);
+  bool replayed = false;
+  h->cur_Tdev = h->shape_dev + 1;
+  const int rc = run_graphed(h, key, st, &replayed, [&]() -> int {
+    return stage2_enqueue(h, T_cap, p_control, e_control, mel, mel_post, pitch, energy, mel_mask, stream);
+  });
+  h->cur_Tdev = nullptr;
+  return rc;
+}
+
+/* {graphs held, replays, captures} of this handle */
+int fs2_graph_stats(const fs2_handle* h, int64_t* n_graphs, int64_t* replays, int64_t* captures) {
+  if (!h) return FS2_ERR_INVALID;
+  int64_t n = 0;
+  for (const auto& kv : h->graphs) n += kv.second.exec != nullptr;
+  if (n_graphs) *n_graphs = n;
+  if (replays) *replays = h->graph_replays;
+  if (captures) *captures = h->graph_captures;
   return FS2_OK;
 }
 

@@ -70,6 +70,9 @@ struct RowLayout {
   const int* lens;         // [B] device: valid rows (p < lens[b]); may be null where no length mask applies
   const unsigned* rowmap;  // [R_cap] device: (b << 16) | p for grid rows, FS2_ROW_NONE for halo / unused rows
   int rows_hint;           // host-side estimate of off[B] (rows in use) for tile-shape decisions; 0 = unknown (use R_cap)
+  const int* S_dev;        // non-null (CUDA-graph replays, fs2_forward_stage*_graph): the TRUE S of this forward lives in
+                           // device memory and `S` above is only its bucket's upper bound, used by the host for grid and
+                           // buffer sizes.  Device code must read the row count through lay_S(), never through `S`.
 };
 #define FS2_ROW_NONE 0xFFFFFFFFu
 #define FS2_MAX_ROWS_PER_UTT 65535
@@ -144,6 +147,11 @@ __device__ __forceinline__ float4 ld_act(const float4* p) {
   asm volatile("ld.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
   return v;
 }
+
+// rows per utterance of the user tensors, as device code must see it (see RowLayout::S_dev)
+__device__ __forceinline__ int lay_S(const RowLayout& lay) { return lay.S_dev ? ld_act(lay.S_dev) : lay.S; }
+// a scalar shape parameter (L, max_len, ...) that a graph replay reads from device memory instead of its baked-in bound
+__device__ __forceinline__ int shape_or(const int* dev, int host_value) { return dev ? ld_act(dev) : host_value; }
 
 // (b, p) of a flat row
 struct RowPos {
@@ -236,24 +244,27 @@ int tc_attention_launch(const bf16* q, const bf16* k, const bf16* vt, const RowL
 // off/ext/rowmap of `lay` from lens32 (device; null = every utterance has S rows): ext = min(lens + halo_keep, S),
 // each utterance followed by halo_rows zero rows (FS2_HALO for GEMM operands, 0 for dense user tensors).
 // extra_ext > 0 appends one pseudo utterance (index B) with extra_ext grid rows: off has B + 2 entries, ext B + 1.
+// S_dev (optional, device): the true S when `S` is only an upper bound (graph replays)
 cudaError_t rowops_build_layout(const int* lens32, int B, int S, int halo_keep, int halo_rows, int* off, int* ext,
-                                unsigned* rowmap, int R_cap, cudaStream_t st, int extra_ext = 0);
+                                unsigned* rowmap, int R_cap, cudaStream_t st, int extra_ext = 0, const int* S_dev = nullptr);
 cudaError_t rowops_embed_pe(const int64_t* texts, const float* emb, const float* pe, int vocab, const RowLayout& lay,
                             int D, float* out_grid, bf16* out_b, int out_planes, float* out_user, cudaStream_t st);
 // zero2 (optional): two ints cleared by the same launch (the forward's {T_max, frames} accumulators)
-cudaError_t rowops_lens_to_i32(const int64_t* lens, int B, int cap, int* out, cudaStream_t st, int* zero2 = nullptr);
+cudaError_t rowops_lens_to_i32(const int64_t* lens, int B, int cap, int* out, cudaStream_t st, int* zero2 = nullptr,
+                               const int* cap_dev = nullptr);
 // zero0 / zero1 (optional): fp32 tensors of the mask's shape cleared by the same launch
 cudaError_t rowops_mask(const int64_t* lens64, const int* lens32, int B, int max_len, uint8_t* mask, cudaStream_t st,
-                        float* zero0 = nullptr, float* zero1 = nullptr);
+                        float* zero0 = nullptr, float* zero1 = nullptr, const int* max_len_dev = nullptr);
 cudaError_t rowops_round_durations(const float* log_d, int64_t n, float d_control, float* out, cudaStream_t st);
 cudaError_t rowops_duration_scan(const float* d, int B, int L, int* cum, int64_t* mel_lens, int* mel_lens32,
                                  int* tmax_dev, cudaStream_t st);
 // fused: d_rounded = clamp(round(exp(log_d) - 1) * d_control, 0) (modules.py:132-135), then the scan of d_rounded
 cudaError_t rowops_round_scan(const float* log_d, float d_control, float* d_rounded, int B, int L, int* cum,
-                              int64_t* mel_lens, int* mel_lens32, int* tmax_dev, cudaStream_t st);
+                              int64_t* mel_lens, int* mel_lens32, int* tmax_dev, cudaStream_t st, const int* L_dev = nullptr);
 // x rows of utterance b start at src_off[b] (device) or b*src_stride when src_off is null; out rows follow `lay`
 cudaError_t rowops_length_regulate(const float* x, const int* src_off, int src_stride, const int* cum, int L, int D,
-                                   const RowLayout& lay, float* out, bf16* out_b, int out_planes, cudaStream_t st);
+                                   const RowLayout& lay, float* out, bf16* out_b, int out_planes, cudaStream_t st,
+                                   const int* L_dev = nullptr);
 cudaError_t rowops_variance_embed(float* pred, float control, const float* bins, int n_bins, const float* emb,
                                   const float* pe, float* x, bf16* xb, int xb_planes, const RowLayout& lay, int D,
                                   int* idx_out, cudaStream_t st);
@@ -272,7 +283,8 @@ cudaError_t rowops_gaussian_upsample(const float* x, const float* d, int B, int 
 // the forward's soft length regulator: rowops_length_regulate's arguments + src_rows[b] = rows of utterance b that exist
 // in x (the phonemes beyond them are the masked, all-zero ones); integer durations given by their scan `cum`
 cudaError_t rowops_gaussian_regulate(const float* x, const int* src_off, const int* src_rows, const int* cum, int L, int D,
-                                     const RowLayout& lay, float* out, bf16* out_b, int out_planes, cudaStream_t st);
+                                     const RowLayout& lay, float* out, bf16* out_b, int out_planes, cudaStream_t st,
+                                     const int* L_dev = nullptr);
 cudaError_t rowops_to_grid(const float* x_user, const RowLayout& lay, int C, float* out, int ldo, int col_off,
                            bf16* out_b, cudaStream_t st);
 cudaError_t rowops_from_grid(const float* x_grid, const RowLayout& lay, int C, float* out_user, cudaStream_t st);

@@ -85,6 +85,8 @@ struct GuArgs {
   const int* cum;          // [B, L] inclusive integer duration scan (used when centres == null)
   const int* mono;         // [B] or null (= monotone)
   int L, Dp, T, T_w;
+  const int* L_dev;        // graph replays: the true L / T_w live in device memory (L, T_w above are upper bounds)
+  const int* Tw_dev;
   float* out; int ldo;
   const int* dst_off;      // null: dense rows b * T + t
   const int* dst_ext;      // grid rows per utterance (ragged destination)
@@ -102,7 +104,7 @@ __global__ void __launch_bounds__(GU_THREADS, 2) gaussian_upsample_kernel(const 
   __shared__ unsigned act_s[GU_NG];
   __shared__ float dmin_s[GU_THREADS / 32];
 
-  const int b = blockIdx.y, t0 = blockIdx.x * GU_TF, L = a.L, T_w = a.T_w;
+  const int b = blockIdx.y, t0 = blockIdx.x * GU_TF, L = shape_or(a.L_dev, a.L), T_w = shape_or(a.Tw_dev, a.T_w);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int cq = tid & 63, fg = tid >> 6;      // channel quad, frame group (a warp lies inside one frame group)
   const int nq = a.Dp >> 2;
@@ -326,7 +328,8 @@ cudaError_t rowops_gaussian_upsample(const float* x, const float* d, int B, int 
 // The forward's soft length regulator (fs2_set_upsampler(h, 1)): same arguments as rowops_length_regulate.  T_w = the
 // frame count of the batch's longest utterance (`torch.arange(0, max(s))`, modules.py:174), i.e. the layout's S.
 cudaError_t rowops_gaussian_regulate(const float* x, const int* src_off, const int* src_rows, const int* cum, int L, int D,
-                                     const RowLayout& lay, float* out, bf16* out_b, int out_planes, cudaStream_t st) {
+                                     const RowLayout& lay, float* out, bf16* out_b, int out_planes, cudaStream_t st,
+                                     const int* L_dev) {
   if (lay.B <= 0 || lay.R_cap <= 0) return cudaSuccess;
   if (L <= 0 || D != 256 || gu_smem_bytes(L) > GU_SMEM_MAX) return cudaErrorInvalidValue;
   cudaError_t e = gu_configure();
@@ -336,6 +339,7 @@ cudaError_t rowops_gaussian_regulate(const float* x, const int* src_off, const i
   a.x = x; a.ldx = D; a.src_off = src_off; a.src_rows = src_rows; a.cum = cum; a.L = L; a.Dp = D;
   a.T = lay.S; a.T_w = lay.S; a.out = out; a.ldo = D; a.dst_off = lay.off; a.dst_ext = lay.ext;
   a.out_b = out_b; a.out_planes = out_planes; a.plane_elems = (size_t)lay.R_cap * D;
+  a.L_dev = L_dev; a.Tw_dev = lay.S_dev;
   dim3 grid((FS2_ROWS_PER_UTT(lay.S, FS2_HALO) + GU_TF - 1) / GU_TF, lay.B);   // covers ext + halo rows of the longest utterance
   (void)FS2_LAUNCH(gaussian_upsample_kernel, grid, GU_THREADS, gu_smem_bytes(L), st, a);
   return LAUNCHED_ERR();

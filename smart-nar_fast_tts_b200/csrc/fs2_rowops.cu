@@ -23,11 +23,12 @@ __device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<floa
 // Ragged-grid layout (fs2_common.cuh): ext[b] = min(lens[b] + halo_keep, S); off = exclusive scan of ext + halo_rows
 // rounded up to FS2_ROW_ALIGN rows (utterances start on 16-byte boundaries of the transposed-V operand).
 // One CTA, chunks of 1024 utterances, block-wide scan by warp shuffles.
-__global__ void __launch_bounds__(1024) build_layout_kernel(const int* lens, int Breal, int S, int halo_keep,
+__global__ void __launch_bounds__(1024) build_layout_kernel(const int* lens, int Breal, int S_host, int halo_keep,
                                                             int halo_rows, int* off, int* ext,
-                                                            int extra_ext) {
+                                                            int extra_ext, const int* S_dev) {
   FS2_PDL_PROLOGUE();
-  const int B = Breal + (extra_ext > 0 ? 1 : 0);   // the pseudo utterance (index Breal) has extra_ext grid rows
+  const int S = shape_or(S_dev, S_host);
+  const int B = Breal + (extra_ext > 0 ? 1 : 0);   // the pseudo utterance (index Breal) has min(extra_ext, S) grid rows
   __shared__ int warp_tot[32];
   __shared__ int carry_s;
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
@@ -107,19 +108,21 @@ __global__ void embed_pe_kernel(const int64_t* texts, const float* emb,
     }
     return;
   }
-  long long id = texts[(size_t)rp.b * lay.S + rp.p];
+  const int S = lay_S(lay);
+  long long id = texts[(size_t)rp.b * S + rp.p];
   id = id < 0 ? 0 : (id >= vocab ? vocab - 1 : id);  // the reference would raise; clamp instead of faulting
   for (int c = lane; c < nv; c += 32) {
     const float4 e = ld4(emb + (size_t)id * D + c * 4), q = ld4(pe + (size_t)rp.p * D + c * 4);
     const float4 v = make_float4(e.x + q.x, e.y + q.y, e.z + q.z, e.w + q.w);
     if (out_grid) st4(out_grid + (size_t)r * D + c * 4, v);
     if (out_b && out_planes > 0) store_planes4(out_b + (size_t)r * D + c * 4, plane, out_planes, v);
-    if (out_user) st4(out_user + ((size_t)rp.b * lay.S + rp.p) * D + c * 4, v);
+    if (out_user) st4(out_user + ((size_t)rp.b * S + rp.p) * D + c * 4, v);
   }
 }
 
-__global__ void lens_to_i32_kernel(const int64_t* lens, int B, int cap, int* out, int* zero2) {
+__global__ void lens_to_i32_kernel(const int64_t* lens, int B, int cap_host, int* out, int* zero2, const int* cap_dev) {
   FS2_PDL_PROLOGUE();
+  const int cap = shape_or(cap_dev, cap_host);
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i == 0 && zero2) { zero2[0] = 0; zero2[1] = 0; }   // the {T_max, frames} accumulators of this forward
   if (i < B) {
@@ -131,9 +134,10 @@ __global__ void lens_to_i32_kernel(const int64_t* lens, int B, int cap, int* out
 // utils/tools.py:89-97  mask[b,i] = i >= lens[b]
 // zero0 / zero1 (optional, same [B, max_len] shape, fp32): cleared in the same pass -- the variance predictors only write
 // the rows their packed layout carries (modules.py:285 masked_fill(mask, 0) for the rest)
-__global__ void mask_kernel(const int64_t* lens64, const int* lens32, int B, int max_len,
-                            uint8_t* mask, float* zero0, float* zero1) {
+__global__ void mask_kernel(const int64_t* lens64, const int* lens32, int B, int max_len_host,
+                            uint8_t* mask, float* zero0, float* zero1, const int* max_len_dev) {
   FS2_PDL_PROLOGUE();
+  const int max_len = shape_or(max_len_dev, max_len_host);
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (size_t)B * max_len) return;
   const int b = (int)(i / max_len), p = (int)(i - (size_t)b * max_len);
@@ -158,10 +162,11 @@ __global__ void round_durations_kernel(const float* log_d, int64_t n, float d_co
 // block-wide inclusive scan (warp shuffles + one smem hop), chunks of 1024 phonemes.
 // log_d != null: the kernel first applies modules.py:132-135 (rounding) to log_d and writes d (fused forward path);
 // log_d == null: d is an input (stand-alone operator).
-__global__ void __launch_bounds__(1024) duration_scan_kernel(const float* log_d, float d_control, float* d, int L, int* cum,
+__global__ void __launch_bounds__(1024) duration_scan_kernel(const float* log_d, float d_control, float* d, int L_host, int* cum,
                                                              int64_t* mel_lens,
-                                                             int* mel_lens32, int* tmax) {
+                                                             int* mel_lens32, int* tmax, const int* L_dev) {
   FS2_PDL_PROLOGUE();
+  const int L = shape_or(L_dev, L_host);
   __shared__ int warp_tot[32];
   __shared__ int carry_s;
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
@@ -228,10 +233,11 @@ __global__ void __launch_bounds__(1024) duration_scan_kernel(const float* log_d,
 // cum[i-1] <= t < cum[i]; frames >= mel_len (kept padded rows and halo) are zero.  One warp per output row, the
 // utterance's cumulative table staged in shared memory, binary search per row, 16-byte row copy (+ bf16 shadow).
 __global__ void __launch_bounds__(256) length_regulate_kernel(const float* x, const int* src_off,
-                                                              int src_stride, const int* cum, int L, int D,
+                                                              int src_stride, const int* cum, int L_host, int D,
                                                               const RowLayout lay, float* out,
-                                                              bf16* out_b, int out_planes) {
+                                                              bf16* out_b, int out_planes, const int* L_dev) {
   FS2_PDL_PROLOGUE();
+  const int L = shape_or(L_dev, L_host);
   extern __shared__ int cum_s[];
   const int b = blockIdx.y;
   const int rows_b = ld_act(lay.off + b + 1) - ld_act(lay.off + b);   // ext + halo
@@ -251,7 +257,7 @@ __global__ void __launch_bounds__(256) length_regulate_kernel(const float* x, co
     float* dst = out + (row0 + t) * D;
     bf16* dstb = out_b ? out_b + (row0 + t) * D : nullptr;
     const float* src = nullptr;
-    if (t < total && t < lay.S) {
+    if (t < total && t < lay_S(lay)) {
       int lo = 0, hi = L - 1;  // first i with cum[i] > t
       while (lo < hi) {
         const int mid = (lo + hi) >> 1;
@@ -280,7 +286,7 @@ __global__ void variance_embed_kernel(float* pred, float control, const float* b
   if (r >= R) return;
   const RowPos rp = row_pos(lay, r, R);
   if (!rp.in_grid) return;   // halo rows stay zero
-  const size_t u = (size_t)rp.b * lay.S + rp.p;
+  const size_t u = (size_t)rp.b * lay_S(lay) + rp.p;
   const float v = pred[u] * control;
   int start = 0, end = n_bins - 1;  // boundaries array has n_bins-1 entries
   while (start < end) {
@@ -321,7 +327,8 @@ __global__ void __launch_bounds__(256) fill_padded_rows_kernel(const float* bias
   const int o0 = ld_act(dst.off + b);
   const int rows_dst = ld_act(dst.off + b + 1) - o0;               // grid rows + zero rows of utterance b
   const int e_dst = ld_act(dst.ext + b);
-  const bool in_dst = p < rows_dst, in_user = b < src.B && p < src.S;
+  const int S_user = lay_S(src);
+  const bool in_dst = p < rows_dst, in_user = b < src.B && p < S_user;
   if (!in_dst && !in_user) return;
   const int lane = threadIdx.x & 31, nv = N >> 2;
   const size_t g = (size_t)o0 + p;
@@ -333,7 +340,7 @@ __global__ void __launch_bounds__(256) fill_padded_rows_kernel(const float* bias
       if (out_grid) st4(out_grid + g * N + c * 4, v);
       if (out_b && out_planes > 0) store_planes4(out_b + g * N + c * 4, plane, out_planes, v);
     }
-    if (out_user && in_user) st4(out_user + ((size_t)b * src.S + p) * N + c * 4, bv);
+    if (out_user && in_user) st4(out_user + ((size_t)b * S_user + p) * N + c * 4, bv);
   }
 }
 
@@ -342,7 +349,7 @@ __global__ void __launch_bounds__(256) fill_padded_rows_kernel(const float* bias
 __global__ void __launch_bounds__(256) postnet_far_rows_kernel(const float* post_grid, int N, const RowLayout pn,
                                                                int B, int H, float* out_user) {
   FS2_PDL_PROLOGUE();
-  const int b = blockIdx.y, S = pn.S;
+  const int b = blockIdx.y, S = lay_S(pn);
   const int e = ld_act(pn.ext + b);
   if (e >= S) return;                                   // the utterance reaches the end of the grid: every row is exact
   const int p = max(e - H, 0) + blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -359,7 +366,7 @@ __global__ void __launch_bounds__(256) postnet_far_rows_kernel(const float* post
 __global__ void __launch_bounds__(256) postnet_far_rows_cm_kernel(const float* post_grid, int N, const RowLayout pn,
                                                                   int B, int H, float* out_user) {
   FS2_PDL_PROLOGUE();
-  const int b = blockIdx.y, S = pn.S;
+  const int b = blockIdx.y, S = lay_S(pn);
   const int e = ld_act(pn.ext + b);
   if (e >= S) return;
   const int p = max(e - H, 0) + blockIdx.x * blockDim.x + threadIdx.x;
@@ -382,7 +389,7 @@ __global__ void to_grid_kernel(const float* xu, const RowLayout lay, int C, floa
   const int c = (int)(i - row * nv);
   const RowPos rp = row_pos(lay, (int)row, ld_act(lay.off + lay.B));
   float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (rp.in_grid) v = ld4(xu + ((size_t)rp.b * lay.S + rp.p) * C + c * 4);
+  if (rp.in_grid) v = ld4(xu + ((size_t)rp.b * lay_S(lay) + rp.p) * C + c * 4);
   if (out) st4(out + row * ldo + col_off + c * 4, v);
   if (out_b) *reinterpret_cast<uint2*>(out_b + row * C + c * 4) = make_uint2(pack2(v.x, v.y), pack2(v.z, v.w));
 }
@@ -529,11 +536,11 @@ inline unsigned blocks_for(size_t n, int per) { return (unsigned)((n + per - 1) 
 #define LAUNCHED() (++g_fs2_launches, cudaGetLastError())
 
 cudaError_t rowops_build_layout(const int* lens32, int B, int S, int halo_keep, int halo_rows, int* off, int* ext,
-                                unsigned* rowmap, int R_cap, cudaStream_t st, int extra_ext) {
+                                unsigned* rowmap, int R_cap, cudaStream_t st, int extra_ext, const int* S_dev) {
   if (B <= 0 || R_cap <= 0) return cudaSuccess;
   const int Bt = B + (extra_ext > 0 ? 1 : 0);
   if (Bt > 65535 || S > FS2_MAX_ROWS_PER_UTT) return cudaErrorInvalidValue;
-  (void)FS2_LAUNCH(build_layout_kernel, 1, 1024, 0, st, lens32, B, S, halo_keep, halo_rows, off, ext, extra_ext);
+  (void)FS2_LAUNCH(build_layout_kernel, 1, 1024, 0, st, lens32, B, S, halo_keep, halo_rows, off, ext, extra_ext, S_dev);
   ++g_fs2_launches;
   (void)FS2_LAUNCH(fill_rowmap_kernel, blocks_for((size_t)R_cap, 256), 256, 0, st, off, ext, Bt, R_cap, rowmap);
   return LAUNCHED();
@@ -545,15 +552,15 @@ cudaError_t rowops_embed_pe(const int64_t* texts, const float* emb, const float*
                                                                    out_planes, out_user);
   return LAUNCHED();
 }
-cudaError_t rowops_lens_to_i32(const int64_t* lens, int B, int cap, int* out, cudaStream_t st, int* zero2) {
+cudaError_t rowops_lens_to_i32(const int64_t* lens, int B, int cap, int* out, cudaStream_t st, int* zero2, const int* cap_dev) {
   if (B <= 0) return cudaSuccess;
-  (void)FS2_LAUNCH(lens_to_i32_kernel, blocks_for(B, 256), 256, 0, st, lens, B, cap, out, zero2);
+  (void)FS2_LAUNCH(lens_to_i32_kernel, blocks_for(B, 256), 256, 0, st, lens, B, cap, out, zero2, cap_dev);
   return LAUNCHED();
 }
 cudaError_t rowops_mask(const int64_t* lens64, const int* lens32, int B, int max_len, uint8_t* mask, cudaStream_t st,
-                        float* zero0, float* zero1) {
+                        float* zero0, float* zero1, const int* max_len_dev) {
   if ((size_t)B * max_len == 0) return cudaSuccess;
-  (void)FS2_LAUNCH(mask_kernel, blocks_for((size_t)B * max_len, 256), 256, 0, st, lens64, lens32, B, max_len, mask, zero0, zero1);
+  (void)FS2_LAUNCH(mask_kernel, blocks_for((size_t)B * max_len, 256), 256, 0, st, lens64, lens32, B, max_len, mask, zero0, zero1, max_len_dev);
   return LAUNCHED();
 }
 cudaError_t rowops_round_durations(const float* log_d, int64_t n, float d_control, float* out, cudaStream_t st) {
@@ -565,22 +572,23 @@ cudaError_t rowops_duration_scan(const float* d, int B, int L, int* cum, int64_t
                                  int* tmax_dev, cudaStream_t st) {
   if (B <= 0) return cudaSuccess;
   (void)FS2_LAUNCH(duration_scan_kernel, B, 1024, 0, st, (const float*)nullptr, 1.0f, const_cast<float*>(d), L, cum, mel_lens,
-                   mel_lens32, tmax_dev);
+                   mel_lens32, tmax_dev, (const int*)nullptr);
   return LAUNCHED();
 }
 cudaError_t rowops_round_scan(const float* log_d, float d_control, float* d_rounded, int B, int L, int* cum,
-                              int64_t* mel_lens, int* mel_lens32, int* tmax_dev, cudaStream_t st) {
+                              int64_t* mel_lens, int* mel_lens32, int* tmax_dev, cudaStream_t st, const int* L_dev) {
   if (B <= 0) return cudaSuccess;
-  (void)FS2_LAUNCH(duration_scan_kernel, B, 1024, 0, st, log_d, d_control, d_rounded, L, cum, mel_lens, mel_lens32, tmax_dev);
+  (void)FS2_LAUNCH(duration_scan_kernel, B, 1024, 0, st, log_d, d_control, d_rounded, L, cum, mel_lens, mel_lens32, tmax_dev, L_dev);
   return LAUNCHED();
 }
 cudaError_t rowops_length_regulate(const float* x, const int* src_off, int src_stride, const int* cum, int L, int D,
-                                   const RowLayout& lay, float* out, bf16* out_b, int out_planes, cudaStream_t st) {
+                                   const RowLayout& lay, float* out, bf16* out_b, int out_planes, cudaStream_t st,
+                                   const int* L_dev) {
   if (lay.B <= 0 || lay.R_cap <= 0) return cudaSuccess;
   const size_t smem = sizeof(int) * (size_t)(L > 0 ? L : 1);
   if (smem > 48 * 1024) return cudaErrorInvalidValue;
   dim3 grid((FS2_ROWS_PER_UTT(lay.S, FS2_HALO) + 63) / 64, lay.B);   // covers ext + halo rows of the longest utterance
-  (void)FS2_LAUNCH(length_regulate_kernel, grid, 256, smem, st, x, src_off, src_stride, cum, L, D, lay, out, out_b, out_planes);
+  (void)FS2_LAUNCH(length_regulate_kernel, grid, 256, smem, st, x, src_off, src_stride, cum, L, D, lay, out, out_b, out_planes, L_dev);
   return LAUNCHED();
 }
 cudaError_t rowops_variance_embed(float* pred, float control, const float* bins, int n_bins, const float* emb,

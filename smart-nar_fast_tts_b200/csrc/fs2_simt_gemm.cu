@@ -202,7 +202,7 @@ __global__ void __launch_bounds__(256) simt_conv_gemm_kernel(const ConvGemmArgs 
 #pragma unroll
         for (int j = 0; j < 8; ++j) d = fmaf(v[j], dw[j], d);
         d = warp_sum(d) + a.dot_b;
-        if (tx == 0 && in_grid && a.out_user) a.out_user[(size_t)b * a.lay.S + p] = keep_len ? d : 0.0f;
+        if (tx == 0 && in_grid && a.out_user) a.out_user[(size_t)b * lay_S(a.lay) + p] = keep_len ? d : 0.0f;
         continue;
       }
     }
@@ -215,14 +215,15 @@ __global__ void __launch_bounds__(256) simt_conv_gemm_kernel(const ConvGemmArgs 
       if (nB < a.N) *reinterpret_cast<float4*>(a.out + dst_r * a.ldo + nB) = make_float4(v[4], v[5], v[6], v[7]);
     }
     if (a.out_user && a.user_cm && in_grid && (a.out_user_B <= 0 || b < a.out_user_B)) {
-      float* o = a.out_user + (size_t)b * a.N * a.lay.S + p;   // channel-major [B, N, S]
+      const int Su = lay_S(a.lay);
+      float* o = a.out_user + (size_t)b * a.N * Su + p;   // channel-major [B, N, S]
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        if (nA < a.N) o[(size_t)(nA + j) * a.lay.S] = v[j];
-        if (nB < a.N) o[(size_t)(nB + j) * a.lay.S] = v[4 + j];
+        if (nA < a.N) o[(size_t)(nA + j) * Su] = v[j];
+        if (nB < a.N) o[(size_t)(nB + j) * Su] = v[4 + j];
       }
     } else if (a.out_user && in_grid && (a.out_user_B <= 0 || b < a.out_user_B)) {
-      float* o = a.out_user + ((size_t)b * a.lay.S + p) * a.ldu;
+      float* o = a.out_user + ((size_t)b * lay_S(a.lay) + p) * a.ldu;
       if (nA < a.N) *reinterpret_cast<float4*>(o + nA) = make_float4(v[0], v[1], v[2], v[3]);
       if (nB < a.N) *reinterpret_cast<float4*>(o + nB) = make_float4(v[4], v[5], v[6], v[7]);
     }

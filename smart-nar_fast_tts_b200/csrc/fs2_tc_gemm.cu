@@ -229,6 +229,7 @@ tc_conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const size_t dst_r = a.dst_off ? (size_t)(ld_act(a.dst_off + ri.b) + ri.p) : (size_t)ri.r;
       const size_t dst_plane = a.dst_off ? (size_t)a.dst_R_cap : (size_t)a.lay.R_cap;
       const bool user_ok = ri.in_grid && (a.out_user_B <= 0 || ri.b < a.out_user_B);
+      const int S_user = a.out_user ? lay_S(a.lay) : 0;   // rows per utterance of the user tensor (device value in graph replays)
 
       mbar_wait(tfull_bar(as), aphase);
       fence_after_sync();
@@ -289,7 +290,7 @@ tc_conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           }
         }
         if (a.epi == EPI_RELU_LN_DOT && ri.in_grid && a.out_user)
-          a.out_user[(size_t)ri.b * a.lay.S + ri.p] = ri.keep_len ? dot + a.dot_b : 0.f;
+          a.out_user[(size_t)ri.b * S_user + ri.p] = ri.keep_len ? dot + a.dot_b : 0.f;
       } else if (a.epi == EPI_QKV) {
         // n_blk 0 -> Q, 1 -> K (bf16 row-major [R,256]); 2 -> V transposed: vt[c, r] (column = flat row)
         for (int c = 0; c < BN / 32; ++c) {
@@ -349,12 +350,12 @@ tc_conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             store_bf16_chunk(a.out_b + dst_r * a.ldob + nb, dst_plane * a.ldob, a.out_planes, y, nb, a.N);
           if (a.out_user && user_ok && a.user_cm) {
             // channel-major [B, N, S]: lanes hold consecutive rows p, so each column is one coalesced 128-byte store
-            float* o = a.out_user + ((size_t)ri.b * a.N + nb) * a.lay.S + ri.p;
+            float* o = a.out_user + ((size_t)ri.b * a.N + nb) * S_user + ri.p;
 #pragma unroll
             for (int j = 0; j < 32; ++j)
-              if (nb + j < a.N) o[(size_t)j * a.lay.S] = y[j];
+              if (nb + j < a.N) o[(size_t)j * S_user] = y[j];
           } else if (a.out_user && user_ok) {
-            float* o = a.out_user + ((size_t)ri.b * a.lay.S + ri.p) * a.ldu + nb;
+            float* o = a.out_user + ((size_t)ri.b * S_user + ri.p) * a.ldu + nb;
 #pragma unroll
             for (int j = 0; j < 32; j += 4)
               if (nb + j < a.N) *reinterpret_cast<float4*>(o + j) = make_float4(y[j], y[j + 1], y[j + 2], y[j + 3]);

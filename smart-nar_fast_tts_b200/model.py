@@ -161,6 +161,10 @@ class FastSpeech2Align(nn.Module):
         if upsampler not in ("hard", "gaussian"):
             raise ValueError('upsampler must be "hard" (LengthRegulator, the reference\'s wiring) or "gaussian"')
         self._upsampler = upsampler
+        # CUDA-graph mode (enable_graphs): bucket policies and, per (stream, B, bucket), the static output buffers whose
+        # addresses the captured graphs bake in
+        self._graphs = False
+        self._graph_bufs = {}
         # construction order mirrors fastspeech2_align.py:20-28 so that default initialisation consumes the
         # torch RNG in the same order as the reference
         self.txt_encoder = _Stack(model_config, "txt_encoder", n_src_vocab)
@@ -237,6 +241,95 @@ class FastSpeech2Align(nn.Module):
             lib = load_library()
             lib.check(lib.fs2_set_upsampler(e["h"], int(upsampler == "gaussian")), e["h"])
         return self
+
+    # ------------------------------------------------------------------ CUDA-graph mode
+    @staticmethod
+    def l_bucket(L: int) -> int:
+        """Phoneme-count bucket: multiples of 16 up to 128, of 32 up to 512, of 128 beyond."""
+        step = 16 if L <= 128 else 32 if L <= 512 else 128
+        return -(-L // step) * step
+
+    @staticmethod
+    def t_bucket(T: int) -> int:
+        """Frame-count bucket: multiples of 64 up to 512, of 128 up to 2048, of 512 beyond (the library clamps a bucket
+        that would straddle max_seq_len)."""
+        step = 64 if T <= 512 else 128 if T <= 2048 else 512
+        return -(-T // step) * step
+
+    def enable_graphs(self, on: bool = True) -> "FastSpeech2Align":
+        """Run the forward as two CUDA-graph launches (stage 1 keyed on (B, L bucket), stage 2 on (B, L bucket, T bucket))
+        instead of ~70 kernel launches: what the reference's per-batch loop (synthesize.py:59-76) costs at small batch is
+        launch latency.  Results are bit-identical to the plain path (the true L / T reach the kernels through device
+        memory; a bucket only bounds grid and workspace sizes).
+
+        The price of baking addresses into graphs: the returned tensors are VIEWS OF STATIC BUFFERS owned by the module,
+        one set per (stream, batch size, bucket).  They stay valid until the next forward on the same stream that falls
+        into the same bucket; consume (or `.clone()`) them before that -- `pipeline.synthesize` and
+        `StreamedSynthesizer` jobs with a `post` hook do.  Not used by the sharded path (t_max hooks) or with an
+        output_allocator.  The first forward of a new key runs plain launches, the second captures, later ones replay."""
+        self._graphs = bool(on)
+        if not on:
+            self._graph_bufs = {}
+        return self
+
+    def graph_stats(self) -> dict:
+        """{"graphs", "replays", "captures"} summed over the engines (fs2_graph_stats)."""
+        lib = load_library()
+        tot = {"graphs": 0, "replays": 0, "captures": 0}
+        for e in self._engines.values():
+            a, b, c = C.c_int64(0), C.c_int64(0), C.c_int64(0)
+            lib.check(lib.fs2_graph_stats(e["h"], C.byref(a), C.byref(b), C.byref(c)), e["h"])
+            tot["graphs"] += a.value; tot["replays"] += b.value; tot["captures"] += c.value
+        return tot
+
+    def _static(self, key, name, numel, dtype, dev):
+        bufs = self._graph_bufs.setdefault(key, {})
+        t = bufs.get(name)
+        if t is None or t.numel() < numel or t.device != dev:
+            t = bufs[name] = torch.empty(numel, device=dev, dtype=dtype)
+        return t
+
+    def _forward_graphed(self, lib, h, texts, src_lens_in, src_lens, B, L, p_control, e_control, dev, stream):
+        f32, n_mel = torch.float32, self._dims.n_mel
+        Lc = min(self.l_bucket(L), self._dims.max_seq_len) if L <= self._dims.max_seq_len else self.l_bucket(L)
+        k1 = (stream, B, "L", Lc)
+        log_d = self._static(k1, "log_d", B * Lc, f32, dev)
+        d_rounded = self._static(k1, "d_rounded", B * Lc, f32, dev)
+        src_masks = self._static(k1, "src_masks", B * Lc, torch.bool, dev)
+        out_mel_lens = self._static(k1, "mel_lens", B, torch.long, dev)
+        ph_p = self._static(k1, "pitch_ph", B * Lc, f32, dev) if self._dims.pitch_phoneme_level else None
+        ph_e = self._static(k1, "energy_ph", B * Lc, f32, dev) if self._dims.energy_phoneme_level else None
+        t_max = C.c_int32(0)
+        lib.check(lib.fs2_forward_stage1_graph(
+            h, texts.data_ptr(), src_lens_in.data_ptr(), B, L, Lc, float(p_control), float(e_control), 1.0,
+            log_d.data_ptr(), d_rounded.data_ptr(), out_mel_lens.data_ptr(), src_masks.data_ptr(),
+            ph_p.data_ptr() if ph_p is not None else None, ph_e.data_ptr() if ph_e is not None else None,
+            C.byref(t_max), stream), h)
+        T = int(t_max.value)
+        frames = int(lib.fs2_last_frame_count(h))
+        Tc = min(self.t_bucket(T), self._dims.max_seq_len) if T <= self._dims.max_seq_len else self.t_bucket(T)
+        k2 = (stream, B, "T", Lc, Tc)
+        mel = self._static(k2, "mel", B * Tc * n_mel, f32, dev)
+        mel_post = self._static(k2, "mel_post", B * Tc * n_mel, f32, dev)
+        pitch = ph_p if ph_p is not None else self._static(k2, "pitch", B * Tc, f32, dev)
+        energy = ph_e if ph_e is not None else self._static(k2, "energy", B * Tc, f32, dev)
+        mel_masks = self._static(k2, "mel_masks", B * Tc, torch.bool, dev)
+        lib.check(lib.fs2_forward_stage2_graph(
+            h, T, Tc, float(p_control), float(e_control), mel.data_ptr(), mel_post.data_ptr(),
+            None if ph_p is not None else pitch.data_ptr(), None if ph_e is not None else energy.data_ptr(),
+            mel_masks.data_ptr(), stream), h)
+
+        def v(t, *shape):       # dense true-shape view of the front of a static buffer
+            n = 1
+            for s_ in shape:
+                n *= s_
+            return t[:n].view(*shape)
+
+        mel_post_v = v(mel_post, B, n_mel, T).transpose(1, 2) if self._mel_post_cm else v(mel_post, B, T, n_mel)
+        return ((v(mel, B, T, n_mel), mel_post_v, v(pitch, B, L) if ph_p is not None else v(pitch, B, T),
+                 v(energy, B, L) if ph_e is not None else v(energy, B, T), v(log_d, B, L), v(d_rounded, B, L),
+                 v(src_masks, B, L), v(mel_masks, B, T), src_lens, v(out_mel_lens, B), None, None),
+                {"T": T, "frames": frames})
 
     def _weights(self):
         if self._cached_ws is None:
@@ -405,6 +498,9 @@ class FastSpeech2Align(nn.Module):
         texts = texts.long().contiguous()
         src_lens_in = src_lens.to(device=dev, dtype=torch.long).contiguous()
         stream = torch.cuda.current_stream(dev).cuda_stream
+        if self._graphs and self.t_max_device_hook is None and self.t_max_hook is None and self.output_allocator is None:
+            with torch.cuda.device(dev):
+                return self._forward_graphed(lib, h, texts, src_lens_in, src_lens, B, L, p_control, e_control, dev, stream)
         f32 = dict(device=dev, dtype=torch.float32)
         log_d = torch.empty(B, L, **f32)
         d_rounded = torch.empty(B, L, **f32)
