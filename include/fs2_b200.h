@@ -95,8 +95,9 @@ const char* fs2_last_error(const fs2_handle* h); /* h may be NULL: last creation
 const char* fs2_version(void);
 
 /* replaces: load_state_dict in utils/model.py:16-22.  Copies + repacks (QKV concat,
- * BatchNorm fold, conv weight -> per-tap K-major bf16 tiles).  `mel_encoder.*`,
- * `*.num_batches_tracked` are accepted and ignored.  Missing inference keys -> error. */
+ * BatchNorm fold, conv weight -> per-tap K-major bf16 tiles).  `mel_encoder.*` is optional (kept for
+ * fs2_op_mel_encoder, packed on its first call); `*.num_batches_tracked` is accepted and ignored.  Missing inference
+ * keys -> error. */
 int fs2_load_weights(fs2_handle* h, const fs2_weight_desc* descs, int32_t n);
 
 /* Lets `h` run on the packed weights `src` already loaded instead of its own copy (same device, same dims).  The
@@ -251,6 +252,18 @@ int fs2_op_variance_embed(fs2_handle* h, int32_t which, float* pred, float contr
 /* fastspeech2_align.py:83-85: mel = mel_linear(dec); mel_post = PostNet(mel) + mel. dec[B,T,D] */
 int fs2_op_mel_postnet(fs2_handle* h, int32_t prec, const float* dec, int32_t B, int32_t T, float* mel,
                        float* mel_post, void* stream);
+/* Training-side aligner: transformer/Models.py:140-173 MelEncoder.forward in eval mode --
+ * Prenet (Layers.py:15-28) on the mels with frame 0 replaced by zeros, + positional table, n_dec_layers x FFTBlock2
+ * (Layers.py:51-70: cross-attention with queries = mel frames and keys = values = src_seq, then the conv FFN).  This is the
+ * forward only (what `fastspeech2_align.py:56` calls; the reference's own training branch stops right after it on an
+ * undefined `_calculate_duration`).
+ *   src_seq [B,L,d_model] (TxtEncoder output), mels [B,T,n_mel], src_lens / mel_lens [B] int64 (valid rows; the masks).
+ *   out [B,T,d_model] (rows >= mel_lens[b] are zero); attn (may be NULL): [n_dec_layers, B, n_heads, T, L] softmax
+ *   probabilities, the `dec_crs_attn_list` the reference returns (per layer a [B, H, T, L] tensor, SubLayers.py:47-48).
+ *   prec selects the GEMM arithmetic (FS2_PREC_*); the attention itself runs in fp32.
+ * Needs the `mel_encoder.*` keys in the loaded state_dict (FS2_ERR_MISSING_WEIGHT otherwise). */
+int fs2_op_mel_encoder(fs2_handle* h, int32_t prec, const float* src_seq, const float* mels, const int64_t* src_lens,
+                       const int64_t* mel_lens, int32_t B, int32_t L, int32_t T, float* out, float* attn, void* stream);
 /* Raw conv-as-GEMM check: out[R,N] = act(sum_t A[r+t-pad,:] . W[:, :, t]^T + bias), rows laid out as
  * B utterances of S rows (zero padded outside [0,S)).  W is torch Conv1d layout [N,K,taps].
  * act: 0 none, 1 relu, 2 tanh.  prec selects the SIMT fp32 kernel or a tcgen05 mode (FS2_PREC_*). */

@@ -157,6 +157,55 @@ def fft_block(sd, p: str, x: torch.Tensor, pad_mask: torch.Tensor, n_head: int) 
     return x.masked_fill(pad_mask.unsqueeze(-1), 0)
 
 
+# ----------------------------------------------------------------------------
+# Training-side aligner: transformer/Models.py:103-173 MelEncoder,
+# Layers.py:15-28 Prenet, :51-70 FFTBlock2 (cross-attention: queries = mel frames, keys / values = phonemes)
+# ----------------------------------------------------------------------------
+def cross_attention(sd, p: str, q_in: torch.Tensor, kv_in: torch.Tensor, key_pad: torch.Tensor, n_head: int
+                    ) -> Tuple[torch.Tensor, torch.Tensor]:
+    """SubLayers.py:29-59 with q != k = v.  Returns (LayerNorm(fc(attention) + q_in), attn[B, H, len_q, len_k])."""
+    B, Tq, D = q_in.shape
+    Lk = kv_in.shape[1]
+    dk = D // n_head
+    q = F.linear(q_in, sd[f"{p}.w_qs.weight"], sd[f"{p}.w_qs.bias"]).view(B, Tq, n_head, dk)
+    k = F.linear(kv_in, sd[f"{p}.w_ks.weight"], sd[f"{p}.w_ks.bias"]).view(B, Lk, n_head, dk)
+    v = F.linear(kv_in, sd[f"{p}.w_vs.weight"], sd[f"{p}.w_vs.bias"]).view(B, Lk, n_head, dk)
+    q = q.permute(2, 0, 1, 3).contiguous().view(-1, Tq, dk)
+    k = k.permute(2, 0, 1, 3).contiguous().view(-1, Lk, dk)
+    v = v.permute(2, 0, 1, 3).contiguous().view(-1, Lk, dk)
+    mask = key_pad.unsqueeze(1).expand(-1, Tq, -1).repeat(n_head, 1, 1)
+    attn = torch.bmm(q, k.transpose(1, 2)) / np.power(dk, 0.5)
+    attn = torch.softmax(attn.masked_fill(mask, -np.inf), dim=2)
+    out = torch.bmm(attn, v)
+    out = out.view(n_head, B, Tq, dk).permute(1, 2, 0, 3).contiguous().view(B, Tq, -1)
+    out = F.linear(out, sd[f"{p}.fc.weight"], sd[f"{p}.fc.bias"])
+    out = F.layer_norm(out + q_in, (D,), sd[f"{p}.layer_norm.weight"], sd[f"{p}.layer_norm.bias"], 1e-5)
+    return out, attn.view(n_head, B, Tq, Lk).transpose(0, 1)
+
+
+def mel_encoder(sd, d: Dims, src_seq: torch.Tensor, tgt_seq: torch.Tensor, src_mask: torch.Tensor, tgt_mask: torch.Tensor
+                ) -> Tuple[torch.Tensor, list]:
+    """MelEncoder.forward in eval mode.  src_seq [B, L, 256] (TxtEncoder output), tgt_seq [B, T, 80] (mels); masks True =
+    padded.  Returns (dec_output [B, T, 256], [attn [B, H, T, L]] * n_layers)."""
+    B, T = tgt_seq.shape[0], tgt_seq.shape[1]
+    tgt_seq = torch.cat([torch.zeros(B, 1, tgt_seq.shape[2]), tgt_seq[:, 1:, :]], dim=1)      # frame 0 replaced by zeros (:144-145)
+    pre = F.relu(F.linear(F.relu(F.linear(tgt_seq, sd["mel_encoder.prenet.w_1.weight"], sd["mel_encoder.prenet.w_1.bias"])),
+                          sd["mel_encoder.prenet.w_2.weight"], sd["mel_encoder.prenet.w_2.bias"]))
+    if T > d.max_seq_len:
+        x = pre + sinusoid_table(T, d.d_model)[:T, :].unsqueeze(0).expand(B, -1, -1)
+    else:
+        x = pre + sd["mel_encoder.position_enc"][:, :T, :].expand(B, -1, -1)
+    attns = []
+    for i in range(d.n_dec_layers):
+        p = f"mel_encoder.layer_stack.{i}"
+        x, a = cross_attention(sd, f"{p}.crs_attn", x, src_seq, src_mask, d.n_heads)
+        x = x.masked_fill(tgt_mask.unsqueeze(-1), 0)
+        x = positionwise_ffn(sd, f"{p}.pos_ffn", x)
+        x = x.masked_fill(tgt_mask.unsqueeze(-1), 0)
+        attns.append(a)
+    return x, attns
+
+
 # transformer/Models.py:73-100  TxtEncoder.forward (eval)
 def txt_encoder(sd, d: Dims, texts: torch.Tensor, pad_mask: torch.Tensor) -> torch.Tensor:
     B, L = texts.shape

@@ -167,6 +167,26 @@ def main():
                         out=ro.numpy(), s=rs.numpy(), w=rw.numpy())
     print(f"gaussian_upsample: T={ro.shape[1]} -> oracle bit-identical to reference")
 
+    # Training-side aligner: the reference's MelEncoder (eval mode) on ragged text / mel lengths
+    sd = O.make_state_dict(13, include_mel_encoder=True)
+    ref = build_reference(FastSpeech2Align, sd, O.STATS_NAN_BINS)
+    rng = np.random.Generator(np.random.PCG64(21))
+    Bm, Lm, Tm = 3, 19, 75
+    src_lens_m, mel_lens_m = torch.tensor([19, 7, 12]), torch.tensor([75, 31, 50])
+    src_mask_m, tgt_mask_m = O.get_mask_from_lengths(src_lens_m, Lm), O.get_mask_from_lengths(mel_lens_m, Tm)
+    src_seq = torch.from_numpy(rng.standard_normal((Bm, Lm, 256)).astype(np.float32)).masked_fill(src_mask_m.unsqueeze(-1), 0)
+    mels = torch.from_numpy(rng.standard_normal((Bm, Tm, 80)).astype(np.float32)).masked_fill(tgt_mask_m.unsqueeze(-1), 0)
+    with torch.no_grad():
+        r_out, r_attn = ref.mel_encoder(src_seq, mels, src_mask_m, tgt_mask_m)
+    o_out, o_attn = O.mel_encoder(sd, O.Dims(), src_seq, mels, src_mask_m, tgt_mask_m)
+    assert bit_equal(r_out, o_out) and len(r_attn) == len(o_attn) == 4
+    for a, b in zip(r_attn, o_attn):
+        assert a.shape == (Bm, 2, Tm, Lm) and bit_equal(a.contiguous(), b.contiguous())
+    np.savez_compressed(os.path.join(out_dir, "mel_encoder.npz"), seed=13, src_seq=src_seq.numpy(), mels=mels.numpy(),
+                        src_lens=src_lens_m.numpy(), mel_lens=mel_lens_m.numpy(), out=r_out.numpy(),
+                        attn=np.stack([a.contiguous().numpy() for a in r_attn]))
+    print(f"mel_encoder: B={Bm} L={Lm} T={Tm} -> oracle bit-identical to reference (output + 4 attention maps)")
+
     # Length regulator (reference class) incl. zero / negative / fractional durations
     lr = ref_modules.LengthRegulator()
     dur2 = torch.tensor([[2.0, 0.0, -1.0, 3.7, 1.0, 0.0, 0.0, 0.0, 0.0], [0.0] * 9, [1.0] * 9])

@@ -74,6 +74,7 @@ SIGNATURES = {
     "fs2_mask_from_lengths": (C.c_int, [_P, _I, _I, _P, _P]),
     "fs2_pack_valid_rows": (C.c_int, [_P, _P, _I, _I, _I, _I, _P, _P, _P]),
     "fs2_wav_to_int16": (C.c_int, [_P, _P, _I, C.c_int64, _F, _P, _P, _P]),
+    "fs2_op_mel_encoder": (C.c_int, [_P, _I, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P]),
     "fs2_op_sinusoid_table": (C.c_int, [_P, _I, _P, _P]),
     "fs2_op_embed_pe": (C.c_int, [_P, _P, _I, _I, _P, _P]),
     "fs2_op_fft_stack": (C.c_int, [_P, _I, _I, _I, _I, _P, _P, _I, _I, _P, _P]),

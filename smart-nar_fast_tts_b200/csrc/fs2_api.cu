@@ -11,6 +11,7 @@
 #include <stdlib.h>
 #include <map>
 #include <memory>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -43,6 +44,10 @@ struct FftW {
   GemmW qkv, fc, w1, w2;
   float *ln1_g = nullptr, *ln1_b = nullptr, *ln2_g = nullptr, *ln2_b = nullptr;
 };
+struct CrossW {   // FFTBlock2 (Layers.py:51-70): cross-attention (queries from one sequence, keys / values from another) + FFN
+  GemmW q, kv, fc, w1, w2;
+  float *ln1_g = nullptr, *ln1_b = nullptr, *ln2_g = nullptr, *ln2_b = nullptr;
+};
 struct PredW {
   GemmW c1, c2;
   float *ln1_g = nullptr, *ln1_b = nullptr, *ln2_g = nullptr, *ln2_b = nullptr, *lin_w = nullptr;
@@ -62,6 +67,11 @@ struct fs2_weights {
   PredW pred[3];
   GemmW mel_linear;
   std::vector<GemmW> postnet;
+  // training-side aligner (mel_encoder.*): raw tensors are kept at load time, packed on the first fs2_op_mel_encoder call
+  std::mutex menc_mu;
+  bool menc_built = false;
+  GemmW menc_pre1, menc_pre2;
+  std::vector<CrossW> menc;
   ~fs2_weights() {
     int cur = -1;
     cudaGetDevice(&cur);
@@ -122,6 +132,8 @@ struct fs2_handle {
   std::map<std::string, GraphEntry> graphs;
   unsigned long long gen = 1;
   long long graph_replays = 0, graph_captures = 0;
+  cudaStream_t capture_stream = nullptr;   // private stream the stages are captured on (the caller's may be the legacy
+                                           // default stream, which cannot capture); graphs are LAUNCHED on the caller's
   int* shape_host = nullptr;   // pinned int[4]: {L, T} of the forward in flight (copied to shape_dev before a graph launch)
   int* shape_dev = nullptr;    // device int[4] the replayed kernels read the true L / T from
   const int* cur_Ldev = nullptr;  // non-null while a *_graph entry point enqueues: true L / T live in shape_dev
@@ -612,6 +624,128 @@ int run_mel_postnet(fs2_handle* h, int prec, const float* dec, const bf16* decb,
   return FS2_OK;
 }
 
+// packs mel_encoder.* (prenet, 4 x FFTBlock2) on first use; the weight block may be shared by several handles
+int build_mel_encoder(fs2_handle* h, cudaStream_t st) {
+  fs2_weights& W = *h->w;
+  std::lock_guard<std::mutex> lock(W.menc_mu);
+  if (W.menc_built) return FS2_OK;
+  struct PdlOff { PdlOff() { ++g_fs2_pdl_off; } ~PdlOff() { --g_fs2_pdl_off; } } pdl_off;   // memcpys between small kernels
+  const fs2_dims& d = h->dims;
+  const int D = d.d_model, F = d.d_ffn;
+  const float* t = nullptr;
+  RCHECK(need(h, "mel_encoder.position_enc", {1, d.max_seq_len + 1, D}, &t));
+  RCHECK(build_gemm(h, W.menc_pre1, {"mel_encoder.prenet.w_1.weight"}, {"mel_encoder.prenet.w_1.bias"}, D, d.n_mel, 1, nullptr, nullptr, st));
+  RCHECK(build_gemm(h, W.menc_pre2, {"mel_encoder.prenet.w_2.weight"}, {"mel_encoder.prenet.w_2.bias"}, D, D, 1, nullptr, nullptr, st));
+  W.menc.assign(d.n_dec_layers, CrossW());
+  for (int l = 0; l < d.n_dec_layers; ++l) {
+    CrossW& L = W.menc[l];
+    const std::string p = "mel_encoder.layer_stack." + std::to_string(l), a = p + ".crs_attn.", f = p + ".pos_ffn.";
+    RCHECK(build_gemm(h, L.q, {a + "w_qs.weight"}, {a + "w_qs.bias"}, D, D, 1, nullptr, nullptr, st));
+    RCHECK(build_gemm(h, L.kv, {a + "w_ks.weight", a + "w_vs.weight"}, {a + "w_ks.bias", a + "w_vs.bias"}, D, D, 1, nullptr, nullptr, st));
+    RCHECK(build_gemm(h, L.fc, {a + "fc.weight"}, {a + "fc.bias"}, D, D, 1, nullptr, nullptr, st));
+    RCHECK(build_gemm(h, L.w1, {f + "w_1.weight"}, {f + "w_1.bias"}, F, D, d.ffn_k1, nullptr, nullptr, st));
+    RCHECK(build_gemm(h, L.w2, {f + "w_2.weight"}, {f + "w_2.bias"}, D, F, d.ffn_k2, nullptr, nullptr, st));
+    RCHECK(need(h, a + "layer_norm.weight", {D}, &t)); L.ln1_g = const_cast<float*>(t);
+    RCHECK(need(h, a + "layer_norm.bias", {D}, &t));   L.ln1_b = const_cast<float*>(t);
+    RCHECK(need(h, f + "layer_norm.weight", {D}, &t)); L.ln2_g = const_cast<float*>(t);
+    RCHECK(need(h, f + "layer_norm.bias", {D}, &t));   L.ln2_b = const_cast<float*>(t);
+  }
+  HCHECK(cudaStreamSynchronize(st));
+  W.menc_built = true;
+  return FS2_OK;
+}
+
+// transformer/Models.py:140-173 MelEncoder.forward (eval): Prenet on the mels with frame 0 zeroed, + positional table, then
+// n_dec_layers x FFTBlock2 (cross-attention over the phoneme sequence, FFN).  Both sequences live on their PADDED grids
+// (ext = S: the reference computes -- and returns attention rows for -- padded query positions too).  GEMMs run in `prec`
+// (fp32 FFMA or tcgen05 with bf16 / split operands); the cross-attention itself is the fp32 kernel of fs2_simt_attn.cu,
+// which materialises the alignment.
+int run_mel_encoder(fs2_handle* h, int prec, const float* src_seq, const float* mels, const int64_t* src_lens,
+                    const int64_t* mel_lens, int B, int L, int T, float* out, float* attn, cudaStream_t st) {
+  const fs2_dims& d = h->dims;
+  const int D = d.d_model, F = d.d_ffn, H = d.n_heads, dk = D / H, M = d.n_mel;
+  fs2_weights& W = *h->w;
+  const bool tc = prec != FS2_PREC_FP32;
+  const size_t np = (size_t)planes_of(prec);
+  WS(int, sl32, "me.sl32", B);
+  WS(int, ml32, "me.ml32", B);
+  HCHECK(rowops_lens_to_i32(src_lens, B, L, sl32, st));
+  HCHECK(rowops_lens_to_i32(mel_lens, B, T, ml32, st));
+  RowLayout ls, lt;
+  RCHECK(make_layout(h, "me.slay", sl32, B, L, L, FS2_HALO, &ls, st));
+  RCHECK(make_layout(h, "me.tlay", ml32, B, T, T, FS2_HALO, &lt, st));
+  const size_t Rs = (size_t)ls.R_cap, Rt = (size_t)lt.R_cap;
+  WS(float, src_g, "me.src", Rs * D);
+  WS(float, mel_g, "me.mel", Rt * M);
+  WS(float, x, "me.x", Rt * D);
+  WS(float, y, "me.y", Rt * D);
+  WS(float, p1, "me.p1", Rt * D);
+  WS(float, qbuf, "me.q", Rt * D);
+  WS(float, kvbuf, "me.kv", Rs * 2 * D);
+  WS(float, att, "me.att", Rt * D);
+  float* hid = nullptr;
+  bf16 *src_b = nullptr, *mel_b = nullptr, *xb = nullptr, *yb = nullptr, *p1b = nullptr, *attb = nullptr, *hidb = nullptr;
+  if (tc) {
+    WS(bf16, t0, "me.src_b", np * Rs * D); src_b = t0;
+    WS(bf16, t1, "me.mel_b", np * Rt * M); mel_b = t1;
+    WS(bf16, t2, "me.xb", np * Rt * D);    xb = t2;
+    WS(bf16, t3, "me.yb", np * Rt * D);    yb = t3;
+    WS(bf16, t4, "me.p1b", np * Rt * D);   p1b = t4;
+    WS(bf16, t5, "me.attb", np * Rt * D);  attb = t5;
+    WS(bf16, t6, "me.hidb", np * Rt * F);  hidb = t6;
+  } else {
+    WS(float, t7, "me.hid", Rt * F); hid = t7;
+  }
+  HCHECK(rowops_to_grid(src_seq, ls, D, src_g, D, 0, nullptr, st));
+  HCHECK(make_shadow(src_g, Rs * D, prec, src_b, st));
+  HCHECK(rowops_to_grid(mels, lt, M, mel_g, M, 0, nullptr, st));
+  HCHECK(rowops_zero_first_rows(lt, M, mel_g, st));                     // Models.py:144-145
+  HCHECK(make_shadow(mel_g, Rt * M, prec, mel_b, st));
+  // Layers.py:24-28 Prenet: relu(w_2(relu(w_1(x)))) on every grid row (dropout is the identity in eval mode)
+  ConvGemmArgs a = base_args(W.menc_pre1, lt);
+  a.A = mel_g; a.Ab = mel_b; a.epi = EPI_RELU; a.mask_mode = MASK_GRID; a.out = tc ? nullptr : p1; a.ldo = D; a.out_b = p1b; a.ldob = D;
+  RCHECK(run_gemm(h, prec, a, st, "menc.prenet1"));
+  a = base_args(W.menc_pre2, lt);
+  a.A = p1; a.Ab = p1b; a.epi = EPI_RELU; a.mask_mode = MASK_GRID; a.out = x; a.ldo = D;
+  if (tc) a.out_planes = 1;
+  RCHECK(run_gemm(h, prec, a, st, "menc.prenet2"));
+  const float* pe = nullptr;
+  if (T <= d.max_seq_len) pe = raw_ptr(h, "mel_encoder.position_enc");
+  else RCHECK(position_table(h, 1, T, &pe, st));                        // same closed form as the decoder's (Models.py:148-153)
+  HCHECK(rowops_add_pe(x, pe, lt, D, st));
+  HCHECK(make_shadow(x, Rt * D, prec, xb, st));
+  for (int l = 0; l < d.n_dec_layers; ++l) {
+    CrossW& Lw = W.menc[l];
+    a = base_args(Lw.q, lt);
+    a.A = x; a.Ab = xb; a.epi = EPI_BIAS; a.mask_mode = MASK_GRID; a.out = qbuf; a.ldo = D;
+    if (tc) a.out_planes = 1;
+    RCHECK(run_gemm(h, prec, a, st, "menc.q"));
+    a = base_args(Lw.kv, ls);
+    a.A = src_g; a.Ab = src_b; a.epi = EPI_BIAS; a.mask_mode = MASK_GRID; a.out = kvbuf; a.ldo = 2 * D;
+    if (tc) a.out_planes = 1;
+    RCHECK(run_gemm(h, prec, a, st, "menc.kv"));
+    {
+      PROF("menc.cross_attn");
+      HCHECK(simt_cross_attention_launch(qbuf, D, kvbuf, 2 * D, 0, D, lt, ls, H, dk, att, D,
+                                         attn ? attn + (size_t)l * B * H * T * L : nullptr, st));
+      HCHECK(make_shadow(att, Rt * D, prec, attb, st));
+    }
+    a = base_args(Lw.fc, lt);
+    a.A = att; a.Ab = attb; a.epi = EPI_RES_LN; a.mask_mode = MASK_LEN; a.residual = x; a.ln_g = Lw.ln1_g; a.ln_b = Lw.ln1_b;
+    a.out = y; a.ldo = D; a.out_b = yb; a.ldob = D;
+    RCHECK(run_gemm(h, prec, a, st, "menc.fc_ln"));
+    a = base_args(Lw.w1, lt);
+    a.A = y; a.Ab = yb; a.epi = EPI_RELU; a.mask_mode = MASK_GRID; a.out = hid; a.ldo = F; a.out_b = hidb; a.ldob = F;
+    RCHECK(run_gemm(h, prec, a, st, "menc.ffn_w1"));
+    a = base_args(Lw.w2, lt);
+    a.A = hid; a.Ab = hidb; a.epi = EPI_RES_LN; a.mask_mode = MASK_LEN; a.residual = y; a.ln_g = Lw.ln2_g; a.ln_b = Lw.ln2_b;
+    a.out = x; a.ldo = D; a.out_b = xb; a.ldob = D;
+    RCHECK(run_gemm(h, prec, a, st, "menc.ffn_w2_ln"));
+  }
+  HCHECK(rowops_from_grid(x, lt, D, out, st));
+  return FS2_OK;
+}
+
 int check_device(int device) {
   int n = 0;
   cudaError_t e = cudaGetDeviceCount(&n);
@@ -671,6 +805,7 @@ void fs2_destroy(fs2_handle* h) {
   cudaSetDevice(h->device);
   cudaDeviceSynchronize();
   h->drop_graphs();
+  if (h->capture_stream) cudaStreamDestroy(h->capture_stream);
   if (h->shape_host) cudaFreeHost(h->shape_host);
   if (h->shape_dev) cudaFree(h->shape_dev);
   h->w.reset();   // frees the weights when this was the last handle using them
@@ -736,7 +871,6 @@ int fs2_load_weights(fs2_handle* h, const fs2_weight_desc* descs, int32_t n) {
     const fs2_weight_desc& w = descs[i];
     if (!w.name || !w.data || w.ndim < 0 || w.ndim > 4) return h->fail(FS2_ERR_INVALID, "malformed weight descriptor");
     const std::string name(w.name);
-    if (name.rfind("mel_encoder.", 0) == 0) continue;  // training-only aligner (Models.py:103-173)
     if (name.size() > 19 && name.compare(name.size() - 19, 19, "num_batches_tracked") == 0) continue;
     RawT t;
     t.numel = 1;
@@ -1022,7 +1156,7 @@ int fs2_forward_stage2(fs2_handle* h, int32_t T, float p_control, float e_contro
 
 }  // extern "C"
 
-// Runs `enqueue` (a lambda that launches one stage on `st`) through the handle's graph cache: first sighting of a key =
+// Runs `enqueue(stream)` (a lambda that launches one stage on the stream it is given) through the handle's graph cache: first sighting of a key =
 // plain launches (sizes the workspace), second = stream capture + instantiate + launch, afterwards = one cudaGraphLaunch.
 // Returns FS2_OK with *replayed = true when the work went out as a graph launch (no host-side stage code ran).
 template <typename F>
@@ -1040,15 +1174,17 @@ static int run_graphed(fs2_handle* h, const std::string& key, cudaStream_t st, b
   if (e.exec) { cudaGraphExecDestroy(e.exec); e.exec = nullptr; }   // captured under an older generation
   if (e.seen <= 0 || h->prof_on) {       // first sighting (or tracing on, or capture known to fail): plain launches
     if (e.seen == 0) e.seen = 1;
-    return enqueue();
+    return enqueue(st);
   }
+  if (!h->capture_stream) HCHECK(cudaStreamCreateWithFlags(&h->capture_stream, cudaStreamNonBlocking));
+  cudaStream_t cs = h->capture_stream;
   const unsigned long long gen0 = h->gen;
   const long long l0 = g_fs2_launches.load();
   // relaxed mode: the stage code may still call cudaMalloc / cudaFuncSetAttribute; it must not synchronise `st`
-  HCHECK(cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed));
-  const int rc = enqueue();
+  HCHECK(cudaStreamBeginCapture(cs, cudaStreamCaptureModeRelaxed));
+  const int rc = enqueue(cs);
   cudaGraph_t g = nullptr;
-  cudaError_t ce = cudaStreamEndCapture(st, &g);
+  cudaError_t ce = cudaStreamEndCapture(cs, &g);
   cudaGraphExec_t ex = nullptr;
   if (rc == FS2_OK && ce == cudaSuccess && g && h->gen == gen0) ce = cudaGraphInstantiate(&ex, g, 0);
   if (g) cudaGraphDestroy(g);
@@ -1060,7 +1196,7 @@ static int run_graphed(fs2_handle* h, const std::string& key, cudaStream_t st, b
     if (ex) cudaGraphExecDestroy(ex);
     if (h->gen == gen0) e.seen = -1;
     g_fs2_launches -= g_fs2_launches.load() - l0;
-    return enqueue();
+    return enqueue(st);
   }
   e.exec = ex;
   e.gen = gen0;
@@ -1107,11 +1243,11 @@ int fs2_forward_stage1_graph(fs2_handle* h, const int64_t* texts, const int64_t*
            (void*)src_mask, (void*)pitch_ph, (void*)energy_ph, p_control, e_control, d_control);
   bool replayed = false;
   h->cur_Ldev = h->shape_dev;
-  const int rc = run_graphed(h, key, st, &replayed, [&]() -> int {
+  const int rc = run_graphed(h, key, st, &replayed, [&](cudaStream_t s_) -> int {
     int* tm = nullptr;
     RCHECK(stage1_enqueue(h, g_texts, g_lens, B, L_cap, p_control, e_control, d_control, log_d, d_rounded, mel_lens,
-                          src_mask, pitch_ph, energy_ph, &tm, stream));
-    HCHECK(cudaMemcpyAsync(h->host_tmax, tm, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
+                          src_mask, pitch_ph, energy_ph, &tm, s_));
+    HCHECK(cudaMemcpyAsync(h->host_tmax, tm, 2 * sizeof(int), cudaMemcpyDeviceToHost, s_));
     return FS2_OK;
   });
   h->cur_Ldev = nullptr;
@@ -1148,8 +1284,8 @@ int fs2_forward_stage2_graph(fs2_handle* h, int32_t T, int32_t T_cap, float p_co
            (void*)mel_post, (void*)pitch, (void*)energy, (void*)mel_mask, p_control, e_control);
   bool replayed = false;
   h->cur_Tdev = h->shape_dev + 1;
-  const int rc = run_graphed(h, key, st, &replayed, [&]() -> int {
-    return stage2_enqueue(h, T_cap, p_control, e_control, mel, mel_post, pitch, energy, mel_mask, stream);
+  const int rc = run_graphed(h, key, st, &replayed, [&](cudaStream_t s_) -> int {
+    return stage2_enqueue(h, T_cap, p_control, e_control, mel, mel_post, pitch, energy, mel_mask, s_);
   });
   h->cur_Tdev = nullptr;
   return rc;
@@ -1413,6 +1549,24 @@ int fs2_op_mel_postnet(fs2_handle* h, int32_t prec, const float* dec, int32_t B,
   HCHECK(rowops_to_grid(dec, lay, D, xg, D, 0, nullptr, st));
   HCHECK(make_shadow(xg, R * D, prec, xb, st));
   return run_mel_postnet(h, prec, xg, xb, lay, mel, mel_post, st);
+}
+
+int fs2_op_mel_encoder(fs2_handle* h, int32_t prec, const float* src_seq, const float* mels, const int64_t* src_lens,
+                       const int64_t* mel_lens, int32_t B, int32_t L, int32_t T, float* out, float* attn, void* stream) {
+  g_fs2_plain_next = 1;   // the first launch of an entry point is fully stream-ordered (fs2_common.cuh)
+  if (!h || !h->loaded) return FS2_ERR_STATE;
+  if (!src_seq || !mels || !src_lens || !mel_lens || !out || B <= 0 || L <= 0 || T <= 0 || prec < FS2_PREC_FP32 ||
+      prec > FS2_PREC_F16X2)
+    return h->fail(FS2_ERR_INVALID, "mel_encoder: bad argument");
+  if (L > 2048) return h->fail(FS2_ERR_UNSUPPORTED, "mel_encoder: more than 2048 phonemes (the scores of a query tile live in shared memory)");
+  if (T > FS2_MAX_ROWS_PER_UTT) return h->fail(FS2_ERR_UNSUPPORTED, "mel_encoder: more than 65535 mel frames per utterance");
+  if (!h->w->raw.count("mel_encoder.prenet.w_1.weight"))
+    return h->fail(FS2_ERR_MISSING_WEIGHT, "mel_encoder.* was not part of the loaded state_dict");
+  HCHECK(cudaSetDevice(h->device));
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  RCHECK(build_mel_encoder(h, st));
+  g_fs2_plain_next = 1;
+  return run_mel_encoder(h, prec, src_seq, mels, src_lens, mel_lens, B, L, T, out, attn, st);
 }
 
 int fs2_op_conv_gemm(int32_t prec, const float* A, const float* W, const float* bias, int32_t B, int32_t S, int32_t K,

@@ -233,6 +233,12 @@ cudaError_t simt_conv_gemm_launch(const ConvGemmArgs& a, cudaStream_t st);
 cudaError_t simt_attention_launch(const float* qkv, int ldqkv, int q_off, int k_off, int v_off, const RowLayout& lay,
                                   int H, int dk, float* out, int ldo, cudaStream_t st);
 
+// cross-attention of the training-side aligner (queries in layq, keys / values in layk; K at column k_off, V at v_off of kv);
+// attn (optional): [B, H, layq.S, layk.S] probabilities, the alignment MelEncoder returns (Models.py:167-171)
+cudaError_t simt_cross_attention_launch(const float* q, int ldq, const float* kv, int ldkv, int k_off, int v_off,
+                                        const RowLayout& layq, const RowLayout& layk, int H, int dk, float* out, int ldo,
+                                        float* attn, cudaStream_t st);
+
 // tcgen05 path
 int tc_conv_gemm_launch(const ConvGemmArgs& a, cudaStream_t st);  // returns FS2_* code
 bool tc_conv_gemm_staged_supported(const ConvGemmArgs& a);        // fs2_tc_gemm_staged.cu: TMA-staged epilogue variant
@@ -287,6 +293,7 @@ cudaError_t rowops_gaussian_regulate(const float* x, const int* src_off, const i
                                      const int* L_dev = nullptr);
 cudaError_t rowops_to_grid(const float* x_user, const RowLayout& lay, int C, float* out, int ldo, int col_off,
                            bf16* out_b, cudaStream_t st);
+cudaError_t rowops_zero_first_rows(const RowLayout& lay, int C, float* x, cudaStream_t st);
 cudaError_t rowops_from_grid(const float* x_grid, const RowLayout& lay, int C, float* out_user, cudaStream_t st);
 // dst_b: [3][taps][n_total][K] -- plane 0 doubles as the plain bf16 weight, planes 1..2 are the split residuals
 cudaError_t rowops_pack_weight(const float* src, int N, int K, int taps, const float* scale, float* dst_f,

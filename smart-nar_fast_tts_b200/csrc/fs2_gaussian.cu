@@ -18,7 +18,9 @@
 //     those phonemes (~25, one chunk of 32) have their x rows fetched (cp.async, 16 bytes per lane) and their normalised
 //     weights staged in shared memory; a warp additionally skips the phonemes whose weight stays below 1e-12 over its own 8
 //     frames.  What is skipped changes a sum by < 1e-12 |x| per phoneme, four orders of magnitude below an fp32 ulp of the
-//     result.  Each thread accumulates an 8-frame x 4-channel register tile (3 shared-memory vector loads per 32 FMAs); the
+//     result.  Each thread accumulates an 8-frame x 4-channel register tile with packed fp32 FMAs (fma.rn.f32x2: a plain
+//     3-register FFMA issues every other cycle on this part, FFMA2 retires two per issue; 3 shared-memory vector loads per
+//     16 FFMA2); the
 //     weight tensor `w`, when requested, is written exactly (every weight of the fp32 support, zeros elsewhere),
 //     coalesced along t.  Output rows leave as 512-byte warp stores (+ operand planes inside the forward).
 #include "fs2_common.cuh"
@@ -43,32 +45,48 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
-// centres[b, :], s[b], mono[b] (1: centres non-decreasing, the banded search is valid)
+// centres[b, :], s[b], mono[b] (1: centres non-decreasing, the banded search is valid).  torch.cumsum on the CPU
+// accumulates fp32 inputs in DOUBLE (at::acc_type<float, false>) and rounds every prefix to fp32; double sums of fp32
+// values are exact while their exponents span < 29 bits (any realistic durations), so a block-parallel double scan gives
+// the very same prefixes as the sequential loop: thread t scans its chunk of ceil(L / 256) durations, the chunk totals
+// are combined by warp shuffles.
 __global__ void __launch_bounds__(256) gaussian_centres_kernel(const float* d, int L, float* centres, float* s_out,
                                                                int* mono_out) {
   FS2_PDL_PROLOGUE();
   extern __shared__ float d_s[];  // [L]: durations in, centres out
-  const int b = blockIdx.x;
-  for (int i = threadIdx.x; i < L; i += blockDim.x) d_s[i] = ld_act(d + (size_t)b * L + i);
+  __shared__ double wtot[8];
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  for (int i = tid; i < L; i += blockDim.x) d_s[i] = ld_act(d + (size_t)b * L + i);
   __syncthreads();
-  if (threadIdx.x == 0) {
-    // torch.cumsum on the CPU accumulates fp32 inputs in double (at::acc_type<float, false>) and rounds every prefix to fp32
-    double e = 0.0;
-    float prev = -INFINITY;
-    int mono = 1;
-    for (int i = 0; i < L; ++i) {
-      const float di = d_s[i];
-      e += (double)di;
-      const float c = (float)e - 0.5f * di;
-      d_s[i] = c;
-      if (!(c >= prev)) mono = 0;
-      prev = c;
-    }
-    if (s_out) s_out[b] = (float)e;
-    mono_out[b] = mono;
+  const int per = (L + 255) / 256, i0 = tid * per, i1 = min(L, i0 + per);
+  double tot = 0.0;
+  for (int i = i0; i < i1; ++i) tot += (double)d_s[i];
+  double incl = tot;                                   // inclusive scan of the chunk totals
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const double y = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += y;
   }
+  if (lane == 31) wtot[w] = incl;
   __syncthreads();
-  for (int i = threadIdx.x; i < L; i += blockDim.x) centres[(size_t)b * L + i] = d_s[i];
+  double base = incl - tot;
+  for (int k = 0; k < w; ++k) base += wtot[k];
+  double e = base;
+  for (int i = i0; i < i1; ++i) {
+    const float di = d_s[i];
+    e += (double)di;
+    d_s[i] = (float)e - 0.5f * di;
+  }
+  if (tid == 255 && s_out) s_out[b] = (float)e;        // the last chunk ends at L (empty chunks carry the total along)
+  __syncthreads();
+  int ok = 1;
+  for (int i = tid; i < L; i += blockDim.x) {
+    const float c = d_s[i];
+    if (!(c >= (i > 0 ? d_s[i - 1] : -INFINITY))) ok = 0;
+    centres[(size_t)b * L + i] = c;
+  }
+  ok = __syncthreads_and(ok);
+  if (tid == 0) mono_out[b] = ok;
 }
 
 // One argument block for both uses of the kernel:
@@ -99,10 +117,11 @@ __global__ void __launch_bounds__(GU_THREADS, 2) gaussian_upsample_kernel(const 
   extern __shared__ __align__(16) float gu_smem[];
   float* x_s = gu_smem;                        // [GU_CH][256]
   float* w_s = x_s + GU_CH * 256;              // [GU_CH][GU_TF]
-  float* den_s = w_s + GU_CH * GU_TF;          // [GU_TF]
-  float* c_s = den_s + GU_TF;                  // [L]
+  float* inv_s = w_s + GU_CH * GU_TF;          // [GU_TF]  1 / denominator of the frame
+  float* c_s = inv_s + GU_TF;                  // [L]
   __shared__ unsigned act_s[GU_NG];
   __shared__ float dmin_s[GU_THREADS / 32];
+  __shared__ int band_s[4];                    // i_lo, i_hi (fp32 support of the tile), a_lo, a_hi (accumulated phonemes)
 
   const int b = blockIdx.y, t0 = blockIdx.x * GU_TF, L = shape_or(a.L_dev, a.L), T_w = shape_or(a.Tw_dev, a.T_w);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -147,17 +166,24 @@ __global__ void __launch_bounds__(GU_THREADS, 2) gaussian_upsample_kernel(const 
   const size_t src0 = a.src_off ? (size_t)ld_act(a.src_off + b) : (size_t)b * L;
   __syncthreads();
 
-  // phonemes that can reach the tile: c_i in (t0 - 104, t_last + 104)
-  int i_lo = 0, i_hi = L;
-  if (is_mono) {
-    const float lo_v = (float)t0 - GU_CUT, hi_v = (float)(t0 + n_w - 1) + GU_CUT;
-    int lo = 0, hi = L;
-    while (lo < hi) { const int mid = (lo + hi) >> 1; if (c_s[mid] > lo_v) hi = mid; else lo = mid + 1; }
-    i_lo = lo;
-    hi = L;
-    while (lo < hi) { const int mid = (lo + hi) >> 1; if (c_s[mid] >= hi_v) hi = mid; else lo = mid + 1; }
-    i_hi = lo;
+  // first phoneme with c > v (strict) or c >= v, by binary search on the monotone centres; lanes 0 / 1 of warp 0 find the
+  // two ends of a band at the same time and publish them (512 threads repeating the searches cost a third of the kernel)
+  auto lower = [&](int lo, int hi, float v, bool strict) {
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      const float c = c_s[mid];
+      if (strict ? c > v : c >= v) hi = mid; else lo = mid + 1;
+    }
+    return lo;
+  };
+  // phonemes that can reach the tile at all: c_i in (t0 - 104, t_last + 104), the fp32 support of the Gaussian
+  if (tid < 2) {
+    int v = tid == 0 ? 0 : L;
+    if (is_mono) v = tid == 0 ? lower(0, L, (float)t0 - GU_CUT, true) : lower(0, L, (float)(t0 + n_w - 1) + GU_CUT, false);
+    band_s[tid] = v;
   }
+  __syncthreads();
+  const int i_lo = band_s[0], i_hi = band_s[1];
 
   // denominators: 8 lanes per frame, lane q takes phonemes i_lo + q, + 8, ...
   float den_mine = INFINITY;
@@ -170,66 +196,69 @@ __global__ void __launch_bounds__(GU_THREADS, 2) gaussian_upsample_kernel(const 
     part += __shfl_xor_sync(0xffffffffu, part, 1);
     part += __shfl_xor_sync(0xffffffffu, part, 2);
     part += __shfl_xor_sync(0xffffffffu, part, 4);
-    if (f < n_w) den_mine = part + 1e-20f;
-    if (q == 0) den_s[f] = part + 1e-20f;
+    const float den = part + 1e-20f;
+    if (f < n_w) den_mine = den;
+    if (q == 0) inv_s[f] = 1.0f / den;
   }
-  // smallest denominator of the tile -> how far a phoneme can sit and still reach a normalised weight of GU_SKIP somewhere
-  // in the tile: exp(-0.01 D^2) / den_min >= GU_SKIP  <=>  D <= sqrt(-100 ln(GU_SKIP den_min)).  ~53 frames at den ~ 1; the
-  // full 104 when a frame of the tile is far from every centre (tiny denominators make far phonemes matter).
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) den_mine = fminf(den_mine, __shfl_xor_sync(0xffffffffu, den_mine, o));
   if (lane == 0) dmin_s[warp] = den_mine;
   __syncthreads();
-  float den_min = dmin_s[0];
+  // smallest denominator of the tile -> how far a phoneme can sit and still reach a normalised weight of GU_SKIP somewhere
+  // in the tile: exp(-0.01 D^2) / den_min >= GU_SKIP  <=>  D <= sqrt(-100 ln(GU_SKIP den_min)).  ~53 frames at den ~ 1; the
+  // full 104 when a frame of the tile is far from every centre (tiny denominators make far phonemes matter).
+  if (tid < 2) {
+    int v = tid == 0 ? i_lo : i_hi;
+    if (is_mono) {
+      float den_min = dmin_s[0];
 #pragma unroll
-  for (int k = 1; k < GU_THREADS / 32; ++k) den_min = fminf(den_min, dmin_s[k]);
-  int a_lo = i_lo, a_hi = i_hi;     // phonemes whose x rows are fetched and accumulated
-  if (is_mono) {
-    const float arg = GU_SKIP * den_min;                       // > 0: den_min >= 1e-20
-    const float d_cut = fminf(GU_CUT, sqrtf(-100.f * logf(arg)) + 1.f);   // + 1 frame of slack on the analytic bound
-    const float lo_v = (float)t0 - d_cut, hi_v = (float)(t0 + n_w - 1) + d_cut;
-    int lo = i_lo, hi = i_hi;
-    while (lo < hi) { const int mid = (lo + hi) >> 1; if (c_s[mid] > lo_v) hi = mid; else lo = mid + 1; }
-    a_lo = lo;
-    hi = i_hi;
-    while (lo < hi) { const int mid = (lo + hi) >> 1; if (c_s[mid] >= hi_v) hi = mid; else lo = mid + 1; }
-    a_hi = lo;
+      for (int k = 1; k < GU_THREADS / 32; ++k) den_min = fminf(den_min, dmin_s[k]);
+      const float d_cut = fminf(GU_CUT, sqrtf(-100.f * logf(GU_SKIP * den_min)) + 1.f);   // + 1 frame of slack on the bound
+      v = tid == 0 ? lower(i_lo, i_hi, (float)t0 - d_cut, true) : lower(i_lo, i_hi, (float)(t0 + n_w - 1) + d_cut, false);
+    }
+    band_s[2 + tid] = v;
   }
+  __syncthreads();
+  const int a_lo = band_s[2], a_hi = max(band_s[2], band_s[3]);     // phonemes whose x rows are fetched and accumulated
+
   // w rows of the phonemes that are not accumulated: exact weights inside the fp32 support, zeros outside it
   if (a.w_out) {
     const int f = tid & 63;
     if (f < n_w) {
-      const float tf = (float)(t0 + f), den = den_s[f];
+      const float tf = (float)(t0 + f), inv = inv_s[f];
       for (int i = tid >> 6; i < L; i += GU_NG) {
         if (i >= a_lo && i < a_hi) continue;
         float wv = 0.f;
-        if (i >= i_lo && i < i_hi) { const float dl = tf - c_s[i]; wv = expf(-0.01f * (dl * dl)) / den; }
+        if (i >= i_lo && i < i_hi) { const float dl = tf - c_s[i]; wv = expf(-0.01f * (dl * dl)) * inv; }
         a.w_out[((size_t)b * L + i) * T_w + t0 + f] = wv;
       }
     }
   }
 
-  float4 acc[GU_FG];
+  // register tile: 4 channels x 8 frames held as frame PAIRS so that one FFMA2 (fma.rn.f32x2) updates two frames of a channel:
+  // acc[c][p] = (frame 2p, frame 2p + 1) of channel c.  The weights of a phoneme arrive as aligned pairs straight from
+  // shared memory; only the 4 channel values are duplicated (4 moves per 16 FFMA2).
+  float2 acc[4][GU_FG / 2];
 #pragma unroll
-  for (int j = 0; j < GU_FG; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int c = 0; c < 4; ++c)
+#pragma unroll
+    for (int p2 = 0; p2 < GU_FG / 2; ++p2) acc[c][p2] = make_float2(0.f, 0.f);
 
   for (int i0 = a_lo; i0 < a_hi; i0 += GU_CH) {
     const int n = min(GU_CH, a_hi - i0);
     const int n_x = max(0, min(n, n_src - i0));   // rows of the chunk that exist in x
     // x rows of the chunk -> shared memory (16 bytes per lane, coalesced 1 KB rows)
-    for (int v = tid; v < n_x * nq; v += GU_THREADS) {
-      const int ii = v / nq, c4 = v - ii * nq;
-      cp_async16(x_s + ii * 256 + c4 * 4, a.x + (src0 + i0 + ii) * a.ldx + c4 * 4);
-    }
+    for (int ii = tid >> 6; ii < n_x; ii += GU_NG)
+      if (has_ch) cp_async16(x_s + ii * 256 + cq * 4, a.x + (src0 + i0 + ii) * a.ldx + cq * 4);
     cp_async_commit();
     // normalised weights of the chunk, once per (frame, phoneme)
     {
       const int f = tid & 63;
       const float tf = (float)(t0 + f);
-      const float den = den_s[f];
+      const float inv = f < n_w ? inv_s[f] : 0.f;   // pad rows (t >= T_w) stay zero
       for (int ii = tid >> 6; ii < n; ii += GU_NG) {
         const float dl = tf - c_s[i0 + ii];
-        const float wv = f < n_w ? expf(-0.01f * (dl * dl)) / den : 0.f;   // pad rows (t >= T_w) stay zero
+        const float wv = expf(-0.01f * (dl * dl)) * inv;
         w_s[ii * GU_TF + f] = wv;
         if (a.w_out && f < n_w) a.w_out[((size_t)b * L + i0 + ii) * T_w + t0 + f] = wv;
       }
@@ -255,15 +284,15 @@ __global__ void __launch_bounds__(GU_THREADS, 2) gaussian_upsample_kernel(const 
         mask &= mask - 1;
         const float4 xv = *reinterpret_cast<const float4*>(x_s + ii * 256 + cq * 4);
         const float4* wr = reinterpret_cast<const float4*>(w_s + ii * GU_TF + fg * GU_FG);
+        const float2 xd[4] = {make_float2(xv.x, xv.x), make_float2(xv.y, xv.y), make_float2(xv.z, xv.z), make_float2(xv.w, xv.w)};
 #pragma unroll
         for (int j4 = 0; j4 < GU_FG / 4; ++j4) {
           const float4 wv = wr[j4];
-          const float ws[4] = {wv.x, wv.y, wv.z, wv.w};
+          const float2 w01 = make_float2(wv.x, wv.y), w23 = make_float2(wv.z, wv.w);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            float4& c = acc[j4 * 4 + k];
-            c.x = fmaf(ws[k], xv.x, c.x); c.y = fmaf(ws[k], xv.y, c.y);
-            c.z = fmaf(ws[k], xv.z, c.z); c.w = fmaf(ws[k], xv.w, c.w);
+          for (int c = 0; c < 4; ++c) {
+            acc[c][2 * j4] = __ffma2_rn(w01, xd[c], acc[c][2 * j4]);
+            acc[c][2 * j4 + 1] = __ffma2_rn(w23, xd[c], acc[c][2 * j4 + 1]);
           }
         }
       }
@@ -275,8 +304,10 @@ __global__ void __launch_bounds__(GU_THREADS, 2) gaussian_upsample_kernel(const 
     for (int j = 0; j < GU_FG; ++j) {
       const int f = fg * GU_FG + j;
       if (f < n_t) {
-        *reinterpret_cast<float4*>(out_t + (size_t)f * a.ldo) = acc[j];
-        if (outb_t && a.out_planes > 0) store_planes4(outb_t + (size_t)f * a.ldo, a.plane_elems, a.out_planes, acc[j]);
+        const float4 v = (j & 1) ? make_float4(acc[0][j >> 1].y, acc[1][j >> 1].y, acc[2][j >> 1].y, acc[3][j >> 1].y)
+                                 : make_float4(acc[0][j >> 1].x, acc[1][j >> 1].x, acc[2][j >> 1].x, acc[3][j >> 1].x);
+        *reinterpret_cast<float4*>(out_t + (size_t)f * a.ldo) = v;
+        if (outb_t && a.out_planes > 0) store_planes4(outb_t + (size_t)f * a.ldo, a.plane_elems, a.out_planes, v);
       }
     }
   }

@@ -378,6 +378,15 @@ __global__ void __launch_bounds__(256) postnet_far_rows_cm_kernel(const float* p
   for (int c = 0; c < N; ++c) dst[(size_t)c * S] = ld_act(src + c);
 }
 
+// row p = 0 of every utterance <- 0 (MelEncoder replaces the first mel frame by zeros, Models.py:144-145); one warp per utterance
+__global__ void zero_first_rows_kernel(const RowLayout lay, int C, float* x) {
+  FS2_PDL_PROLOGUE();
+  const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (b >= lay.B || ld_act(lay.ext + b) <= 0) return;
+  float* row = x + (size_t)ld_act(lay.off + b) * C;
+  for (int c = lane; c < (C >> 2); c += 32) st4(row + c * 4, make_float4(0.f, 0.f, 0.f, 0.f));
+}
+
 // dense user layout [B,S,C] <-> ragged grid layout (test / per-operator entry points)
 __global__ void to_grid_kernel(const float* xu, const RowLayout lay, int C, float* out,
                                int ldo, int col_off, bf16* out_b) {
@@ -655,6 +664,11 @@ cudaError_t rowops_split(const float* src, int64_t n, int planes, bf16* dst, int
   if (n <= 0) return cudaSuccess;
   if (n % 4) return cudaErrorInvalidValue;
   (void)FS2_LAUNCH(split_kernel, blocks_for((size_t)(n / 4), 256), 256, 0, st, src, n / 4, planes, dst, plane_elems);
+  return LAUNCHED();
+}
+cudaError_t rowops_zero_first_rows(const RowLayout& lay, int C, float* x, cudaStream_t st) {
+  if (lay.B <= 0) return cudaSuccess;
+  (void)FS2_LAUNCH(zero_first_rows_kernel, blocks_for((size_t)lay.B, 8), 256, 0, st, lay, C, x);
   return LAUNCHED();
 }
 cudaError_t rowops_to_grid(const float* x_user, const RowLayout& lay, int C, float* out, int ldo, int col_off,

@@ -76,6 +76,22 @@ class _Stack(nn.Module):  # Models.py:36-71 / 179-210 / 106-138
             [_FFTBlock(d_model, n_head, t["conv_filter_size"], t["conv_kernel_size"], attn) for _ in range(n_layers)])
 
 
+class _MelEncoder(_Stack):
+    """transformer/Models.py:103-173 MelEncoder: the training-side aligner.  Parameter container like the other stacks;
+    `forward` mirrors the reference's signature and return value and runs on the owning module's engine
+    (fs2_op_mel_encoder)."""
+
+    def __init__(self, cfg):
+        super().__init__(cfg, "mel_encoder")
+        self._owner = None      # weak reference to the FastSpeech2Align that holds the engine (set by the owner)
+
+    def forward(self, src_seq, tgt_seq, src_mask, tgt_mask, return_attns=True):
+        owner = self._owner() if self._owner is not None else None
+        if owner is None:
+            raise RuntimeError("mel_encoder is not attached to a FastSpeech2Align module")
+        return owner.mel_encoder_forward(src_seq, tgt_seq, src_mask, tgt_mask, return_attns)
+
+
 class _Prenet(nn.Module):  # Layers.py:15-21 (training-only; kept so checkpoints load strictly)
     def __init__(self):
         super().__init__()
@@ -169,7 +185,9 @@ class FastSpeech2Align(nn.Module):
         # torch RNG in the same order as the reference
         self.txt_encoder = _Stack(model_config, "txt_encoder", n_src_vocab)
         self.variance_adaptor = _VarianceAdaptor(preprocess_config, model_config)
-        self.mel_encoder = _Stack(model_config, "mel_encoder")  # training-only aligner: parameters kept, never used
+        self.mel_encoder = _MelEncoder(model_config)   # training-side aligner (forward only: mel_encoder_forward)
+        import weakref
+        self.mel_encoder._owner = weakref.ref(self)
         self.mel_decoder = _Stack(model_config, "mel_decoder")
         self.mel_linear = nn.Linear(model_config["transformer"]["decoder_hidden"],
                                     preprocess_config["preprocessing"]["mel"]["n_mel_channels"])
@@ -334,7 +352,7 @@ class FastSpeech2Align(nn.Module):
     def _weights(self):
         if self._cached_ws is None:
             self._cached_ws = [(k, v) for k, v in self.state_dict(keep_vars=True).items()
-                               if not k.startswith("mel_encoder.") and not k.endswith("num_batches_tracked")]
+                               if not k.endswith("num_batches_tracked")]
         return self._cached_ws
 
     @property
@@ -472,6 +490,38 @@ class FastSpeech2Align(nn.Module):
     @property
     def launch_count(self) -> int:
         return int(load_library().fs2_launch_count(self._handle)) if self._handle is not None else 0
+
+    # ------------------------------------------------------------------ training-side aligner (Models.py:140-173)
+    @torch.no_grad()
+    def mel_encoder_forward(self, src_seq, tgt_seq, src_mask, tgt_mask, return_attns=True, precision: Optional[str] = None):
+        """`self.mel_encoder(src_output, mels, src_masks, mel_masks)` of fastspeech2_align.py:56 in eval mode:
+        src_seq [B, L, 256] (TxtEncoder output), tgt_seq [B, T, 80] (mels), masks [B, L] / [B, T] bool (True = padded, as
+        get_mask_from_lengths builds them: a prefix of valid positions).  Returns (dec_output [B, T, 256],
+        [attn [B, H, T, L]] * n_layers) -- the reference's `dec_crs_attn_list` -- or (dec_output, []) with
+        return_attns=False.  Forward only: there is no backward pass (the reference's training loop cannot run, its
+        model calls an undefined `_calculate_duration`).  `precision`: GEMM arithmetic ("fp32", "bf16", "bf16x3", "f16x2";
+        default = the encoder precision of set_precision); the attention runs in fp32."""
+        dev = src_seq.device
+        lib, h = self._ensure_engine(dev)
+        B, L, D = src_seq.shape
+        T = tgt_seq.shape[1]
+        if tgt_seq.shape[0] != B or src_mask.shape != (B, L) or tgt_mask.shape != (B, T):
+            raise ValueError("mel_encoder_forward: inconsistent shapes")
+        m = {"fp32": PREC_FP32, "bf16": PREC_BF16, "bf16x3": PREC_BF16X3, "f16x2": PREC_F16X2}
+        prec = m[precision] if precision is not None else self._precision[0]
+        src_lens = (~src_mask).sum(dim=1).to(torch.long).contiguous()
+        mel_lens = (~tgt_mask).sum(dim=1).to(torch.long).contiguous()
+        src_seq = src_seq.float().contiguous()
+        tgt_seq = tgt_seq.float().contiguous()
+        n_layers, H = self._dims.n_dec_layers, self._dims.n_heads
+        out = torch.empty(B, T, D, device=dev, dtype=torch.float32)
+        attn = torch.empty(n_layers, B, H, T, L, device=dev, dtype=torch.float32) if return_attns else None
+        with torch.cuda.device(dev):
+            lib.check(lib.fs2_op_mel_encoder(h, prec, src_seq.data_ptr(), tgt_seq.data_ptr(), src_lens.data_ptr(),
+                                             mel_lens.data_ptr(), B, L, T, out.data_ptr(),
+                                             attn.data_ptr() if attn is not None else None,
+                                             torch.cuda.current_stream(dev).cuda_stream), h)
+        return out, ([attn[i] for i in range(n_layers)] if attn is not None else [])
 
     # ------------------------------------------------------------------ forward (fastspeech2_align.py:30-100)
     def forward(self, speakers, texts, src_lens, max_src_len, mels=None, mel_lens=None, max_mel_len=None,

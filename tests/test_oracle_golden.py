@@ -40,6 +40,19 @@ def test_oracle_gaussian_and_length_regulator_golden():
     assert torch.equal(out, torch.from_numpy(g["out"])) and torch.equal(ml, torch.from_numpy(g["mel_len"]))
 
 
+def test_oracle_mel_encoder_golden():
+    """training-side aligner: the oracle against the reference's own MelEncoder outputs (dec_output + 4 alignments)"""
+    g = load_golden("mel_encoder")
+    sd = O.make_state_dict(int(g["seed"]), include_mel_encoder=True)
+    src_lens, mel_lens = torch.from_numpy(g["src_lens"]), torch.from_numpy(g["mel_lens"])
+    L, T = g["src_seq"].shape[1], g["mels"].shape[1]
+    out, attns = O.mel_encoder(sd, O.Dims(), torch.from_numpy(g["src_seq"]), torch.from_numpy(g["mels"]),
+                               O.get_mask_from_lengths(src_lens, L), O.get_mask_from_lengths(mel_lens, T))
+    assert max_abs(out, torch.from_numpy(g["out"])) < 2e-5
+    for i, a in enumerate(attns):
+        assert max_abs(a.contiguous(), torch.from_numpy(g["attn"][i])) < 2e-6
+
+
 def test_oracle_properties():
     # NaN boundaries (shipped LJSpeech config: log bins of a negative minimum) -> every bucket is n_bins-1
     bins = O.make_bins(-2.9, 11.4, 256, "log")
