@@ -9,20 +9,22 @@
 //     fp32: a parallel fp32 scan would move the centres of non-integer durations by an ulp of e ~ 1e-4, visible in w),
 //     the centres go to a scratch buffer once per utterance
 //     instead of once per CTA of the main kernel.
-//   * gaussian_upsample_kernel, one CTA of 512 threads per (utterance, tile of 64 frames): exp(-0.01 D^2) is exactly 0 in
-//     fp32 for |D| >= 104 (0.01 D^2 > 103.97, below the smallest denormal), so only the phonemes whose centre lies within
-//     104 frames of the tile enter the denominators (binary search on the monotone centres; negative durations fall back
-//     to the full range; 8 lanes per frame + warp shuffles).  The smallest denominator of the tile then bounds how far a
-//     phoneme can sit and still reach a NORMALISED weight of 1e-12 anywhere in the tile (~53 frames when the tile lies
-//     inside the utterance, the full 104 where every centre is far and the tiny denominators blow the weights up): only
-//     those phonemes (~25, one chunk of 32) have their x rows fetched (cp.async, 16 bytes per lane) and their normalised
-//     weights staged in shared memory; a warp additionally skips the phonemes whose weight stays below 1e-12 over its own 8
-//     frames.  What is skipped changes a sum by < 1e-12 |x| per phoneme, four orders of magnitude below an fp32 ulp of the
-//     result.  Each thread accumulates an 8-frame x 4-channel register tile with packed fp32 FMAs (fma.rn.f32x2: a plain
-//     3-register FFMA issues every other cycle on this part, FFMA2 retires two per issue; 3 shared-memory vector loads per
-//     16 FFMA2); the
-//     weight tensor `w`, when requested, is written exactly (every weight of the fp32 support, zeros elsewhere),
-//     coalesced along t.  Output rows leave as 512-byte warp stores (+ operand planes inside the forward).
+//   * gaussian_upsample_kernel, one CTA of 8 warps per (utterance, tile of 32 frames), each warp owning 4 frames x all 256
+//     channels (lane = 8 channels).  exp(-0.01 D^2) is exactly 0 in fp32 for |D| >= 104 (0.01 D^2 > 103.97, below the
+//     smallest denormal), so only the phonemes whose centre lies within 104 frames of the tile can matter (binary search
+//     on the monotone centres; negative durations fall back to the full range): the CTA stages their x rows in shared
+//     memory once (cp.async, 16 bytes per lane).  Everything else is warp-local, so the main loop has no CTA barrier:
+//       - denominators of the warp's 4 frames, 8 lanes per frame + shuffles, over the phonemes within 64 frames (what is
+//         farther adds < 1.6e-18 each); only a frame far from every centre (sum < 1e-6) makes the warp sum the full support;
+//       - the smallest of them bounds how far a phoneme can sit and still reach a NORMALISED weight of 1e-12 on one of the
+//         warp's frames (~53 frames; up to 104 where the denominators are tiny): ~16 phonemes survive at LJSpeech
+//         durations.  What is skipped changes a sum by < 1e-12 |x| per phoneme, four orders below an fp32 ulp of the result;
+//       - their normalised weights, evaluated once per (frame, phoneme), go to the warp's slice of shared memory as
+//         (w, w) pairs, so that the accumulation is 2 + 2 shared-memory vector loads and 16 packed FMAs (fma.rn.f32x2: a
+//         3-register FFMA issues every other cycle on this part, FFMA2 retires two per issue) per phoneme and lane.
+//     Output rows leave as 512-byte warp stores (+ operand planes inside the forward).  The weight tensor `w`, when
+//     requested, is written by a separate pass of the CTA, coalesced along t: exact weights inside the fp32 support,
+//     zeros elsewhere.
 #include "fs2_common.cuh"
 #include <math.h>
 
@@ -30,12 +32,14 @@
 
 namespace {
 
-constexpr int GU_TF = 64;        // frames per CTA tile
-constexpr int GU_FG = 8;         // frames per thread (register tile rows)
-constexpr int GU_NG = GU_TF / GU_FG;   // frame groups per tile
-constexpr int GU_CH = 32;        // phonemes per shared-memory chunk
-constexpr int GU_THREADS = 64 * GU_NG;  // 64 channel quads x 8 frame groups = 512
+constexpr int GU_TF = 32;        // frames per CTA tile
+constexpr int GU_FW = 4;         // frames per warp (register tile: 4 frames x 8 channels per lane)
+constexpr int GU_WARPS = GU_TF / GU_FW;
+constexpr int GU_THREADS = 32 * GU_WARPS;   // 256
+constexpr int GU_XR = 48;        // phoneme rows of x staged per chunk (48 KB at D = 256)
 constexpr float GU_CUT = 104.f;  // exp(-0.01 * 104^2) == 0 in fp32
+constexpr float GU_NEAR = 64.f;  // exp(-0.01 * 64^2) = 1.6e-18: invisible next to a denominator >= GU_DEN_OK
+constexpr float GU_DEN_OK = 1e-6f;
 constexpr float GU_SKIP = 1e-12f;
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
@@ -112,22 +116,19 @@ struct GuArgs {
   float* w_out;
 };
 
-__global__ void __launch_bounds__(GU_THREADS, 2) gaussian_upsample_kernel(const GuArgs a) {   // <= 64 registers: 2 CTAs = 32 warps per SM
+__global__ void __launch_bounds__(GU_THREADS, 3) gaussian_upsample_kernel(const GuArgs a) {
   FS2_PDL_PROLOGUE();
   extern __shared__ __align__(16) float gu_smem[];
-  float* x_s = gu_smem;                        // [GU_CH][256]
-  float* w_s = x_s + GU_CH * 256;              // [GU_CH][GU_TF]
-  float* inv_s = w_s + GU_CH * GU_TF;          // [GU_TF]  1 / denominator of the frame
+  float* x_s = gu_smem;                        // [GU_XR][256]   phoneme rows of the current chunk
+  float* w_s = x_s + GU_XR * 256;              // [GU_WARPS][GU_XR][2 * GU_FW]  per warp: weights as (w, w) pairs per frame
+  float* inv_s = w_s + GU_WARPS * GU_XR * 2 * GU_FW;   // [GU_TF]  1 / denominator (only read by the `w` pass)
   float* c_s = inv_s + GU_TF;                  // [L]
-  __shared__ unsigned act_s[GU_NG];
-  __shared__ float dmin_s[GU_THREADS / 32];
-  __shared__ int band_s[4];                    // i_lo, i_hi (fp32 support of the tile), a_lo, a_hi (accumulated phonemes)
+  __shared__ int band_s[2];                    // i_lo, i_hi: phonemes inside the fp32 support of the tile
 
   const int b = blockIdx.y, t0 = blockIdx.x * GU_TF, L = shape_or(a.L_dev, a.L), T_w = shape_or(a.Tw_dev, a.T_w);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int cq = tid & 63, fg = tid >> 6;      // channel quad, frame group (a warp lies inside one frame group)
-  const int nq = a.Dp >> 2;
-  const bool has_ch = cq < nq;
+  const int nq = a.Dp >> 2;                    // channel quads of the slab; lane owns quads `lane` and `32 + lane`
+  const bool has0 = lane < nq, has1 = 32 + lane < nq;
   size_t row0;                                 // destination row of frame 0
   int rows_b, ext_b;                           // rows to write / rows that carry weights
   if (a.dst_off) {
@@ -141,16 +142,24 @@ __global__ void __launch_bounds__(GU_THREADS, 2) gaussian_upsample_kernel(const 
   const int n_t = min(GU_TF, rows_b - t0);     // rows of the tile that exist in `out`
   if (n_t <= 0) return;
   const int n_w = max(0, min(GU_TF, ext_b - t0));   // frames with weights; the rest (`pad` rows / halo rows) are zero
-  float* out_t = a.out + (row0 + t0) * a.ldo + cq * 4;
-  bf16* outb_t = a.out_b ? a.out_b + (row0 + t0) * a.ldo + cq * 4 : nullptr;
-
+  const int f0 = warp * GU_FW;                 // first frame of this warp inside the tile
+  float* out_w = a.out + (row0 + t0 + f0) * a.ldo + lane * 4;
+  bf16* outb_w = a.out_b ? a.out_b + (row0 + t0 + f0) * a.ldo + lane * 4 : nullptr;
+  auto store_row = [&](int j, float4 v0, float4 v1) {     // frame f0 + j: two 512-byte warp stores (+ operand planes)
+    if (f0 + j >= n_t) return;
+    float* o = out_w + (size_t)j * a.ldo;
+    if (has0) *reinterpret_cast<float4*>(o) = v0;
+    if (has1) *reinterpret_cast<float4*>(o + 128) = v1;
+    if (outb_w && a.out_planes > 0) {
+      bf16* ob = outb_w + (size_t)j * a.ldo;
+      if (has0) store_planes4(ob, a.plane_elems, a.out_planes, v0);
+      if (has1) store_planes4(ob + 128, a.plane_elems, a.out_planes, v1);
+    }
+  };
   if (n_w == 0) {                              // pure padding tile
-    if (has_ch)
-      for (int f = fg; f < n_t; f += GU_NG) {
-        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-        *reinterpret_cast<float4*>(out_t + (size_t)f * a.ldo) = z;
-        if (outb_t && a.out_planes > 0) store_planes4(outb_t + (size_t)f * a.ldo, a.plane_elems, a.out_planes, z);
-      }
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int j = 0; j < GU_FW; ++j) store_row(j, z, z);
     return;
   }
   if (a.centres) {
@@ -166,8 +175,7 @@ __global__ void __launch_bounds__(GU_THREADS, 2) gaussian_upsample_kernel(const 
   const size_t src0 = a.src_off ? (size_t)ld_act(a.src_off + b) : (size_t)b * L;
   __syncthreads();
 
-  // first phoneme with c > v (strict) or c >= v, by binary search on the monotone centres; lanes 0 / 1 of warp 0 find the
-  // two ends of a band at the same time and publish them (512 threads repeating the searches cost a third of the kernel)
+  // first phoneme in [lo, hi) with c > v (strict) or c >= v: binary search on the monotone centres
   auto lower = [&](int lo, int hi, float v, bool strict) {
     while (lo < hi) {
       const int mid = (lo + hi) >> 1;
@@ -176,145 +184,129 @@ __global__ void __launch_bounds__(GU_THREADS, 2) gaussian_upsample_kernel(const 
     }
     return lo;
   };
-  // phonemes that can reach the tile at all: c_i in (t0 - 104, t_last + 104), the fp32 support of the Gaussian
-  if (tid < 2) {
-    int v = tid == 0 ? 0 : L;
-    if (is_mono) v = tid == 0 ? lower(0, L, (float)t0 - GU_CUT, true) : lower(0, L, (float)(t0 + n_w - 1) + GU_CUT, false);
-    band_s[tid] = v;
+  // lanes 0 / 1 find the two ends of the band (v_lo - reach, v_hi + reach); every lane of the warp gets both
+  auto warp_band = [&](int lo, int hi, float v_lo, float v_hi, float reach, int& b_lo, int& b_hi) {
+    int v = lane == 0 ? lo : hi;
+    if (is_mono && lane < 2) v = lane == 0 ? lower(lo, hi, v_lo - reach, true) : lower(lo, hi, v_hi + reach, false);
+    b_lo = __shfl_sync(0xffffffffu, v, 0);
+    b_hi = max(b_lo, __shfl_sync(0xffffffffu, v, 1));
+  };
+  // phonemes inside the fp32 support of the whole tile: their x rows are what the CTA stages
+  if (warp == 0) {
+    int lo, hi;
+    warp_band(0, L, (float)t0, (float)(t0 + n_w - 1), GU_CUT, lo, hi);
+    if (lane == 0) { band_s[0] = lo; band_s[1] = hi; }
   }
   __syncthreads();
   const int i_lo = band_s[0], i_hi = band_s[1];
-
-  // denominators: 8 lanes per frame, lane q takes phonemes i_lo + q, + 8, ...
-  float den_mine = INFINITY;
-  {
-    const int f = tid >> 3, q = tid & 7;
-    const float tf = (float)(t0 + f);
-    float part = 0.f;
-    if (f < n_w)
-      for (int i = i_lo + q; i < i_hi; i += 8) { const float dl = tf - c_s[i]; part += expf(-0.01f * (dl * dl)); }
-    part += __shfl_xor_sync(0xffffffffu, part, 1);
-    part += __shfl_xor_sync(0xffffffffu, part, 2);
-    part += __shfl_xor_sync(0xffffffffu, part, 4);
-    const float den = part + 1e-20f;
-    if (f < n_w) den_mine = den;
-    if (q == 0) inv_s[f] = 1.0f / den;
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) den_mine = fminf(den_mine, __shfl_xor_sync(0xffffffffu, den_mine, o));
-  if (lane == 0) dmin_s[warp] = den_mine;
-  __syncthreads();
-  // smallest denominator of the tile -> how far a phoneme can sit and still reach a normalised weight of GU_SKIP somewhere
-  // in the tile: exp(-0.01 D^2) / den_min >= GU_SKIP  <=>  D <= sqrt(-100 ln(GU_SKIP den_min)).  ~53 frames at den ~ 1; the
-  // full 104 when a frame of the tile is far from every centre (tiny denominators make far phonemes matter).
-  if (tid < 2) {
-    int v = tid == 0 ? i_lo : i_hi;
-    if (is_mono) {
-      float den_min = dmin_s[0];
-#pragma unroll
-      for (int k = 1; k < GU_THREADS / 32; ++k) den_min = fminf(den_min, dmin_s[k]);
-      const float d_cut = fminf(GU_CUT, sqrtf(-100.f * logf(GU_SKIP * den_min)) + 1.f);   // + 1 frame of slack on the bound
-      v = tid == 0 ? lower(i_lo, i_hi, (float)t0 - d_cut, true) : lower(i_lo, i_hi, (float)(t0 + n_w - 1) + d_cut, false);
+  auto stage_x = [&](int c0) {                 // rows [c0, c0 + GU_XR) of the band -> x_s (cp.async, 16 bytes per lane)
+    const int n_x = max(0, min(min(GU_XR, i_hi - c0), n_src - c0));
+    for (int r = warp; r < n_x; r += GU_WARPS) {
+      const float* src = a.x + (src0 + c0 + r) * a.ldx + lane * 4;
+      if (has0) cp_async16(x_s + r * 256 + lane * 4, src);
+      if (has1) cp_async16(x_s + r * 256 + 128 + lane * 4, src + 128);
     }
-    band_s[2 + tid] = v;
-  }
-  __syncthreads();
-  const int a_lo = band_s[2], a_hi = max(band_s[2], band_s[3]);     // phonemes whose x rows are fetched and accumulated
-
-  // w rows of the phonemes that are not accumulated: exact weights inside the fp32 support, zeros outside it
-  if (a.w_out) {
-    const int f = tid & 63;
-    if (f < n_w) {
-      const float tf = (float)(t0 + f), inv = inv_s[f];
-      for (int i = tid >> 6; i < L; i += GU_NG) {
-        if (i >= a_lo && i < a_hi) continue;
-        float wv = 0.f;
-        if (i >= i_lo && i < i_hi) { const float dl = tf - c_s[i]; wv = expf(-0.01f * (dl * dl)) * inv; }
-        a.w_out[((size_t)b * L + i) * T_w + t0 + f] = wv;
-      }
-    }
-  }
-
-  // register tile: 4 channels x 8 frames held as frame PAIRS so that one FFMA2 (fma.rn.f32x2) updates two frames of a channel:
-  // acc[c][p] = (frame 2p, frame 2p + 1) of channel c.  The weights of a phoneme arrive as aligned pairs straight from
-  // shared memory; only the 4 channel values are duplicated (4 moves per 16 FFMA2).
-  float2 acc[4][GU_FG / 2];
-#pragma unroll
-  for (int c = 0; c < 4; ++c)
-#pragma unroll
-    for (int p2 = 0; p2 < GU_FG / 2; ++p2) acc[c][p2] = make_float2(0.f, 0.f);
-
-  for (int i0 = a_lo; i0 < a_hi; i0 += GU_CH) {
-    const int n = min(GU_CH, a_hi - i0);
-    const int n_x = max(0, min(n, n_src - i0));   // rows of the chunk that exist in x
-    // x rows of the chunk -> shared memory (16 bytes per lane, coalesced 1 KB rows)
-    for (int ii = tid >> 6; ii < n_x; ii += GU_NG)
-      if (has_ch) cp_async16(x_s + ii * 256 + cq * 4, a.x + (src0 + i0 + ii) * a.ldx + cq * 4);
     cp_async_commit();
-    // normalised weights of the chunk, once per (frame, phoneme)
-    {
-      const int f = tid & 63;
-      const float tf = (float)(t0 + f);
-      const float inv = f < n_w ? inv_s[f] : 0.f;   // pad rows (t >= T_w) stay zero
-      for (int ii = tid >> 6; ii < n; ii += GU_NG) {
-        const float dl = tf - c_s[i0 + ii];
-        const float wv = expf(-0.01f * (dl * dl)) * inv;
-        w_s[ii * GU_TF + f] = wv;
-        if (a.w_out && f < n_w) a.w_out[((size_t)b * L + i0 + ii) * T_w + t0 + f] = wv;
-      }
+  };
+  stage_x(i_lo);
+
+  // ---- this warp's frames: denominators.  Lane = (phoneme slot q, frame fr): 8 lanes per frame.  First over the
+  // phonemes within GU_NEAR frames (what is farther adds < 1.6e-18 each); a frame whose sum stays below GU_DEN_OK is far
+  // from every centre, the warp then sums the whole fp32 support (tiny denominators make far phonemes matter).
+  const int fr = lane & 3, q = lane >> 2;
+  const int fw = f0 + fr;                      // this lane's frame inside the tile
+  const bool f_ok = fw < n_w;
+  const float tf = (float)(t0 + fw);
+  const float tw_lo = (float)(t0 + f0), tw_hi = (float)(t0 + min(f0 + GU_FW, max(n_w, f0 + 1)) - 1);   // frames of the warp with weights
+  int d_lo, d_hi;
+  warp_band(i_lo, i_hi, tw_lo, tw_hi, GU_NEAR, d_lo, d_hi);
+  auto den_over = [&](int lo, int hi) {
+    float part = 0.f;
+    if (f_ok)
+      for (int i = lo + q; i < hi; i += 8) { const float dl = tf - c_s[i]; part += expf(-0.01f * (dl * dl)); }
+    part += __shfl_xor_sync(0xffffffffu, part, 4);
+    part += __shfl_xor_sync(0xffffffffu, part, 8);
+    part += __shfl_xor_sync(0xffffffffu, part, 16);
+    return part;
+  };
+  float den = den_over(d_lo, d_hi);
+  if (__any_sync(0xffffffffu, f_ok && den < GU_DEN_OK)) den = den_over(i_lo, i_hi);
+  den += 1e-20f;
+  const float inv = f_ok ? 1.0f / den : 0.f;   // pad rows (t >= T_w) keep zero weights
+  // smallest denominator of the warp's frames -> how far a phoneme can sit and still reach a normalised weight of GU_SKIP
+  // on one of them: exp(-0.01 D^2) / den_min >= GU_SKIP  <=>  D <= sqrt(-100 ln(GU_SKIP den_min))  (~53 frames at den ~ 1)
+  float den_min = f_ok ? den : INFINITY;
+  den_min = fminf(den_min, __shfl_xor_sync(0xffffffffu, den_min, 1));
+  den_min = fminf(den_min, __shfl_xor_sync(0xffffffffu, den_min, 2));
+  int a_lo = i_lo, a_hi = i_lo;                // phonemes this warp accumulates (none when it has no frame with weights)
+  if (f0 < n_w) {
+    const float d_cut = fminf(GU_CUT, sqrtf(-100.f * logf(GU_SKIP * den_min)) + 1.f);   // + 1 frame of slack on the bound
+    warp_band(i_lo, i_hi, tw_lo, tw_hi, d_cut, a_lo, a_hi);
+  }
+  if (a.w_out && q == 0) inv_s[fw] = inv;
+
+  // register tile: 4 frames x 8 channels as channel PAIRS, so that one FFMA2 (fma.rn.f32x2) updates two channels of a
+  // frame: acc[j][p] = channels (pair p) of frame f0 + j.  x arrives from shared memory as natural pairs, the weights are
+  // stored as (w, w) pairs by the lanes that evaluate them: no register shuffling around the 16 FFMA2 of a phoneme.
+  float2 acc[GU_FW][4];
+#pragma unroll
+  for (int j = 0; j < GU_FW; ++j)
+#pragma unroll
+    for (int p2 = 0; p2 < 4; ++p2) acc[j][p2] = make_float2(0.f, 0.f);
+  float* w_w = w_s + warp * (GU_XR * 2 * GU_FW);
+
+  for (int c0 = i_lo; c0 < i_hi; c0 += GU_XR) {
+    if (c0 != i_lo) {
+      __syncthreads();                          // every warp is done with the previous chunk's rows
+      stage_x(c0);
+    }
+    const int lo = max(a_lo, c0), hi = min(min(a_hi, c0 + GU_XR), n_src);   // rows beyond n_src are zeros: nothing to add
+    // normalised weights of this warp's frames, once per (frame, phoneme)
+    for (int i = lo + q; i < hi; i += 8) {
+      const float dl = tf - c_s[i];
+      const float wv = expf(-0.01f * (dl * dl)) * inv;
+      *reinterpret_cast<float2*>(w_w + (i - c0) * (2 * GU_FW) + 2 * fr) = make_float2(wv, wv);
     }
     cp_async_wait_all();
-    __syncthreads();
-    // which phonemes of the chunk matter to which frame group (one warp per group, one lane per phoneme)
-    if (warp < GU_NG) {
-      float m = 0.f;
-      if (lane < n_x) {
-        const float4* wr = reinterpret_cast<const float4*>(w_s + lane * GU_TF + warp * GU_FG);
+    __syncthreads();                            // x rows (all warps' copies) and, warp-locally, the weights are visible
+    for (int i = lo; i < hi; ++i) {
+      const int r = i - c0;
+      const float4 w01 = *reinterpret_cast<const float4*>(w_w + r * (2 * GU_FW));
+      const float4 w23 = *reinterpret_cast<const float4*>(w_w + r * (2 * GU_FW) + 4);
+      if (fmaxf(fmaxf(w01.x, w01.z), fmaxf(w23.x, w23.z)) < GU_SKIP) continue;   // warp-uniform
+      const float4 xa = *reinterpret_cast<const float4*>(x_s + r * 256 + lane * 4);
+      const float4 xb = *reinterpret_cast<const float4*>(x_s + r * 256 + 128 + lane * 4);
+      const float2 xp[4] = {make_float2(xa.x, xa.y), make_float2(xa.z, xa.w), make_float2(xb.x, xb.y), make_float2(xb.z, xb.w)};
+      const float2 wp[GU_FW] = {make_float2(w01.x, w01.y), make_float2(w01.z, w01.w), make_float2(w23.x, w23.y), make_float2(w23.z, w23.w)};
 #pragma unroll
-        for (int j = 0; j < GU_FG / 4; ++j) { const float4 v = wr[j]; m = fmaxf(m, fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w))); }
-      }
-      const unsigned mask = __ballot_sync(0xffffffffu, m >= GU_SKIP);
-      if (lane == 0) act_s[warp] = mask;
+      for (int j = 0; j < GU_FW; ++j)
+#pragma unroll
+        for (int p2 = 0; p2 < 4; ++p2) acc[j][p2] = __ffma2_rn(wp[j], xp[p2], acc[j][p2]);
     }
-    __syncthreads();
-    unsigned mask = act_s[fg];
-    if (has_ch) {
-      while (mask) {
-        const int ii = __ffs(mask) - 1;
-        mask &= mask - 1;
-        const float4 xv = *reinterpret_cast<const float4*>(x_s + ii * 256 + cq * 4);
-        const float4* wr = reinterpret_cast<const float4*>(w_s + ii * GU_TF + fg * GU_FG);
-        const float2 xd[4] = {make_float2(xv.x, xv.x), make_float2(xv.y, xv.y), make_float2(xv.z, xv.z), make_float2(xv.w, xv.w)};
-#pragma unroll
-        for (int j4 = 0; j4 < GU_FG / 4; ++j4) {
-          const float4 wv = wr[j4];
-          const float2 w01 = make_float2(wv.x, wv.y), w23 = make_float2(wv.z, wv.w);
-#pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            acc[c][2 * j4] = __ffma2_rn(w01, xd[c], acc[c][2 * j4]);
-            acc[c][2 * j4 + 1] = __ffma2_rn(w23, xd[c], acc[c][2 * j4 + 1]);
-          }
-        }
-      }
-    }
-    __syncthreads();   // x_s / w_s are rewritten by the next chunk
   }
-  if (has_ch) {
 #pragma unroll
-    for (int j = 0; j < GU_FG; ++j) {
-      const int f = fg * GU_FG + j;
-      if (f < n_t) {
-        const float4 v = (j & 1) ? make_float4(acc[0][j >> 1].y, acc[1][j >> 1].y, acc[2][j >> 1].y, acc[3][j >> 1].y)
-                                 : make_float4(acc[0][j >> 1].x, acc[1][j >> 1].x, acc[2][j >> 1].x, acc[3][j >> 1].x);
-        *reinterpret_cast<float4*>(out_t + (size_t)f * a.ldo) = v;
-        if (outb_t && a.out_planes > 0) store_planes4(outb_t + (size_t)f * a.ldo, a.plane_elems, a.out_planes, v);
+  for (int j = 0; j < GU_FW; ++j)
+    store_row(j, make_float4(acc[j][0].x, acc[j][0].y, acc[j][1].x, acc[j][1].y),
+              make_float4(acc[j][2].x, acc[j][2].y, acc[j][3].x, acc[j][3].y));
+
+  // ---- the weight tensor, when requested: w[b, i, t0 .. t0 + n_w) for every phoneme slot, coalesced along t (exact
+  // weights inside the fp32 support, zeros outside it)
+  if (a.w_out) {
+    __syncthreads();                            // inv_s of every warp
+    const int f = lane;                         // GU_TF == 32: lane = frame
+    if (f < n_w) {
+      const float tfw = (float)(t0 + f), invf = inv_s[f];
+      for (int i = warp; i < L; i += GU_WARPS) {
+        float wv = 0.f;
+        if (i >= i_lo && i < i_hi) { const float dl = tfw - c_s[i]; wv = expf(-0.01f * (dl * dl)) * invf; }
+        a.w_out[((size_t)b * L + i) * T_w + t0 + f] = wv;
       }
     }
   }
 }
 
 constexpr size_t GU_SMEM_MAX = 200 * 1024;
-inline size_t gu_smem_bytes(int L) { return sizeof(float) * ((size_t)GU_CH * 256 + GU_CH * GU_TF + GU_TF + (size_t)L); }
+inline size_t gu_smem_bytes(int L) { return sizeof(float) * ((size_t)GU_XR * 256 + GU_WARPS * GU_XR * 2 * GU_FW + GU_TF + (size_t)L); }
 inline cudaError_t gu_configure() {   // opt in to > 48 KB of dynamic shared memory (per device, idempotent)
   cudaError_t e = cudaFuncSetAttribute(gaussian_upsample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GU_SMEM_MAX);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(gaussian_centres_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GU_SMEM_MAX);

@@ -126,3 +126,28 @@ def test_graphs_with_gaussian_upsampler_and_streams(lib):
         res = [syn.wait(j) for j in jobs]
     for k, got in enumerate(res):
         assert_same(got, plain[k % len(cases)], f"streamed job {k}")
+
+
+def test_synthesize_pipeline_with_graphs(lib):
+    """pipeline.synthesize (length-bucketed batches, several in flight, packed hand-off) with the graph cache on: the same
+    host arrays as with plain launches; repeated passes over the batch list replay the cached graphs."""
+    from smart_nar_fast_tts_b200 import StreamedSynthesizer, pipeline as P
+    sd = O.make_state_dict(0)
+    m = build_model(sd, O.STATS_NAN_BINS)
+    g = np.random.Generator(np.random.PCG64(9))
+    items = [(f"utt{i}", 0, g.integers(1, 361, int(n)), f"text {i}") for i, n in enumerate(g.integers(3, 70, 29))]
+    batches, _ = P.make_batches(items, batch_size=8)
+    pc = {"preprocessing": {"pitch": {"feature": "frame_level"}, "energy": {"feature": "frame_level"},
+                            "audio": {"max_wav_value": 32768.0}}}
+    mc = {"vocoder": {"model": "HiFi-GAN"}}
+    want = [s for _, s, _ in P.synthesize(m, (pc, mc), None, batches, n_streams=2)]
+    m.enable_graphs(True)
+    with StreamedSynthesizer(m, n_streams=2) as syn:
+        for rnd in range(3):
+            got = [s for _, s, _ in P.synthesize(m, (pc, mc), None, batches, synth=syn)]
+            for k, (a, b) in enumerate(zip(got, want)):
+                for i in range(len(b)):
+                    for name in ("mel", "pitch", "energy", "duration"):
+                        assert np.array_equal(getattr(a, name)[i], getattr(b, name)[i]), (rnd, k, i, name)
+        st = m.graph_stats()
+    assert st["replays"] > 0 and st["captures"] > 0, st
