@@ -9,22 +9,27 @@
 //     fp32: a parallel fp32 scan would move the centres of non-integer durations by an ulp of e ~ 1e-4, visible in w),
 //     the centres go to a scratch buffer once per utterance
 //     instead of once per CTA of the main kernel.
-//   * gaussian_upsample_kernel, one CTA of 8 warps per (utterance, tile of 32 frames), each warp owning 4 frames x all 256
-//     channels (lane = 8 channels).  exp(-0.01 D^2) is exactly 0 in fp32 for |D| >= 104 (0.01 D^2 > 103.97, below the
-//     smallest denormal), so only the phonemes whose centre lies within 104 frames of the tile can matter (binary search
-//     on the monotone centres; negative durations fall back to the full range): the CTA stages their x rows in shared
-//     memory once (cp.async, 16 bytes per lane).  Everything else is warp-local, so the main loop has no CTA barrier:
-//       - denominators of the warp's 4 frames, 8 lanes per frame + shuffles, over the phonemes within 64 frames (what is
+//   * gaussian_upsample_kernel, one CTA of 4 warps per (utterance, tile of 32 frames), each warp owning 8 frames x all 256
+//     channels (lane = 8 channels; 4 CTAs per SM).  exp(-0.01 D^2) is exactly 0 in fp32 for |D| >= 104 (0.01 D^2 > 103.97,
+//     below the smallest denormal), so only the phonemes whose centre lies within 104 frames of the tile can matter (a
+//     32-ary search of the monotone centres by warp ballots; negative durations fall back to the full range): the CTA
+//     stages their x rows in shared memory once (cp.async, 16 bytes per lane).  Everything else is warp-local, so the
+//     main loop has no CTA barrier:
+//       - denominators of the warp's 8 frames, 4 lanes per frame + shuffles, over the phonemes within 64 frames (what is
 //         farther adds < 1.6e-18 each); only a frame far from every centre (sum < 1e-6) makes the warp sum the full support;
 //       - the smallest of them bounds how far a phoneme can sit and still reach a NORMALISED weight of 1e-12 on one of the
-//         warp's frames (~53 frames; up to 104 where the denominators are tiny): ~16 phonemes survive at LJSpeech
+//         warp's frames (~53 frames; up to 104 where the denominators are tiny): ~17 phonemes survive at LJSpeech
 //         durations.  What is skipped changes a sum by < 1e-12 |x| per phoneme, four orders below an fp32 ulp of the result;
 //       - their normalised weights, evaluated once per (frame, phoneme), go to the warp's slice of shared memory as
-//         (w, w) pairs, so that the accumulation is 2 + 2 shared-memory vector loads and 16 packed FMAs (fma.rn.f32x2: a
+//         (w, w) pairs, so that the accumulation is 2 + 4 shared-memory vector loads and 32 packed FMAs (fma.rn.f32x2: a
 //         3-register FFMA issues every other cycle on this part, FFMA2 retires two per issue) per phoneme and lane.
 //     Output rows leave as 512-byte warp stores (+ operand planes inside the forward).  The weight tensor `w`, when
 //     requested, is written by a separate pass of the CTA, coalesced along t: exact weights inside the fp32 support,
 //     zeros elsewhere.
+//     Measured at the BASELINE configs[4] shape (batch 64 x 300 phonemes, T = 2160; profiles/r2_gaussian.md): 62 us per
+//     call without `w` = 2.6 TB/s of algorithmic bytes (40 % of the measured HBM peak), 96 us with `w` (3.4 TB/s, 52 %).
+//     The limiter is FP32 issue, not HBM: 17 phonemes x 256 channels per frame is 0.6 GFMA per call, the FMA pipe is 44 %
+//     busy and half of the issued instructions are the per-warp bookkeeping around it.
 #include "fs2_common.cuh"
 #include <math.h>
 
@@ -32,11 +37,16 @@
 
 namespace {
 
-constexpr int GU_TF = 32;        // frames per CTA tile
-constexpr int GU_FW = 4;         // frames per warp (register tile: 4 frames x 8 channels per lane)
-constexpr int GU_WARPS = GU_TF / GU_FW;
+#ifndef FS2_GU_FW
+#define FS2_GU_FW 8
+#endif
+constexpr int GU_FW = FS2_GU_FW; // frames per warp (register tile: GU_FW frames x 8 channels per lane); 4 or 8
+constexpr int GU_WARPS = 4;
+constexpr int GU_TF = GU_WARPS * GU_FW;   // frames per CTA tile
+constexpr int GU_QN = 32 / GU_FW;         // lanes per frame while denominators / weights are evaluated
+static_assert(GU_FW == 4 || GU_FW == 8, "frames per warp");
 constexpr int GU_THREADS = 32 * GU_WARPS;   // 256
-constexpr int GU_XR = 48;        // phoneme rows of x staged per chunk (48 KB at D = 256)
+constexpr int GU_XR = 40;        // phoneme rows of x staged per chunk (40 KB at D = 256)
 constexpr float GU_CUT = 104.f;  // exp(-0.01 * 104^2) == 0 in fp32
 constexpr float GU_NEAR = 64.f;  // exp(-0.01 * 64^2) = 1.6e-18: invisible next to a denominator >= GU_DEN_OK
 constexpr float GU_DEN_OK = 1e-6f;
@@ -116,14 +126,13 @@ struct GuArgs {
   float* w_out;
 };
 
-__global__ void __launch_bounds__(GU_THREADS, 3) gaussian_upsample_kernel(const GuArgs a) {
+__global__ void __launch_bounds__(GU_THREADS, 4) gaussian_upsample_kernel(const GuArgs a) {
   FS2_PDL_PROLOGUE();
   extern __shared__ __align__(16) float gu_smem[];
   float* x_s = gu_smem;                        // [GU_XR][256]   phoneme rows of the current chunk
   float* w_s = x_s + GU_XR * 256;              // [GU_WARPS][GU_XR][2 * GU_FW]  per warp: weights as (w, w) pairs per frame
   float* inv_s = w_s + GU_WARPS * GU_XR * 2 * GU_FW;   // [GU_TF]  1 / denominator (only read by the `w` pass)
   float* c_s = inv_s + GU_TF;                  // [L]
-  __shared__ int band_s[2];                    // i_lo, i_hi: phonemes inside the fp32 support of the tile
 
   const int b = blockIdx.y, t0 = blockIdx.x * GU_TF, L = shape_or(a.L_dev, a.L), T_w = shape_or(a.Tw_dev, a.T_w);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -175,30 +184,48 @@ __global__ void __launch_bounds__(GU_THREADS, 3) gaussian_upsample_kernel(const 
   const size_t src0 = a.src_off ? (size_t)ld_act(a.src_off + b) : (size_t)b * L;
   __syncthreads();
 
-  // first phoneme in [lo, hi) with c > v (strict) or c >= v: binary search on the monotone centres
-  auto lower = [&](int lo, int hi, float v, bool strict) {
-    while (lo < hi) {
-      const int mid = (lo + hi) >> 1;
-      const float c = c_s[mid];
-      if (strict ? c > v : c >= v) hi = mid; else lo = mid + 1;
+  // Bands on the monotone centres.  first(v, strict) = number of phonemes with c <= v (strict) or c < v: the index of the
+  // first phoneme beyond v.  For the whole tile it is counted by the CTA (one predicate per thread and 256 phonemes,
+  // __syncthreads_count); inside a warp, over the <= 64 phonemes of a window, by two ballots -- no serial search anywhere.
+  // count(v, strict) over the whole utterance: a 32-ary search, the lanes probe 32 evenly spaced centres per level (two
+  // levels up to 1024 phonemes).  Every warp of the CTA computes the same band: no exchange, no barrier.
+  auto first_beyond = [&](float v, bool incl) {            // incl: count c <= v, else c < v
+    int lo = 0, n = L;
+    while (n > 32) {
+      const int stride = (n + 31) >> 5, idx = lo + lane * stride;
+      const float c = idx < lo + n ? c_s[idx] : INFINITY;
+      const int k = __popc(__ballot_sync(0xffffffffu, incl ? c <= v : c < v));
+      if (k == 0) return lo;
+      const int nlo = lo + (k - 1) * stride + 1;           // probe k - 1 is before v, probe k (if any) is not
+      n = min(lo + n, lo + k * stride) - nlo;
+      lo = nlo;
     }
-    return lo;
+    const float c = lane < n ? c_s[lo + lane] : INFINITY;
+    return lo + __popc(__ballot_sync(0xffffffffu, incl ? c <= v : c < v));
   };
-  // lanes 0 / 1 find the two ends of the band (v_lo - reach, v_hi + reach); every lane of the warp gets both
-  auto warp_band = [&](int lo, int hi, float v_lo, float v_hi, float reach, int& b_lo, int& b_hi) {
-    int v = lane == 0 ? lo : hi;
-    if (is_mono && lane < 2) v = lane == 0 ? lower(lo, hi, v_lo - reach, true) : lower(lo, hi, v_hi + reach, false);
-    b_lo = __shfl_sync(0xffffffffu, v, 0);
-    b_hi = max(b_lo, __shfl_sync(0xffffffffu, v, 1));
-  };
-  // phonemes inside the fp32 support of the whole tile: their x rows are what the CTA stages
-  if (warp == 0) {
-    int lo, hi;
-    warp_band(0, L, (float)t0, (float)(t0 + n_w - 1), GU_CUT, lo, hi);
-    if (lane == 0) { band_s[0] = lo; band_s[1] = hi; }
+  int i_lo = 0, i_hi = L;                      // phonemes inside the fp32 support of the tile: (t0 - 104, t_last + 104)
+  if (is_mono) {
+    i_lo = first_beyond((float)t0 - GU_CUT, true);
+    i_hi = max(i_lo, first_beyond((float)(t0 + n_w - 1) + GU_CUT, false));
   }
-  __syncthreads();
-  const int i_lo = band_s[0], i_hi = band_s[1];
+  // [b_lo, b_hi) = phonemes of [lo, hi) with c in (v_lo - reach, v_hi + reach); all lanes get the same answer
+  auto warp_band = [&](int lo, int hi, float v_lo, float v_hi, float reach, int& b_lo, int& b_hi) {
+    b_lo = lo; b_hi = hi;
+    if (!is_mono) return;
+    const float a_ = v_lo - reach, z_ = v_hi + reach;
+    if (hi - lo <= 64) {
+      const float c0 = lo + lane < hi ? c_s[lo + lane] : INFINITY, c1 = lo + 32 + lane < hi ? c_s[lo + 32 + lane] : INFINITY;
+      b_lo = lo + __popc(__ballot_sync(0xffffffffu, c0 <= a_)) + __popc(__ballot_sync(0xffffffffu, c1 <= a_));
+      b_hi = lo + __popc(__ballot_sync(0xffffffffu, c0 < z_)) + __popc(__ballot_sync(0xffffffffu, c1 < z_));
+    } else {                                   // many (zero-duration) phonemes in the window: binary searches
+      int l0 = lo, h0 = hi;
+      while (l0 < h0) { const int mid = (l0 + h0) >> 1; if (c_s[mid] > a_) h0 = mid; else l0 = mid + 1; }
+      b_lo = l0; h0 = hi;
+      while (l0 < h0) { const int mid = (l0 + h0) >> 1; if (c_s[mid] >= z_) h0 = mid; else l0 = mid + 1; }
+      b_hi = l0;
+    }
+    b_hi = max(b_hi, b_lo);
+  };
   auto stage_x = [&](int c0) {                 // rows [c0, c0 + GU_XR) of the band -> x_s (cp.async, 16 bytes per lane)
     const int n_x = max(0, min(min(GU_XR, i_hi - c0), n_src - c0));
     for (int r = warp; r < n_x; r += GU_WARPS) {
@@ -213,7 +240,7 @@ __global__ void __launch_bounds__(GU_THREADS, 3) gaussian_upsample_kernel(const 
   // ---- this warp's frames: denominators.  Lane = (phoneme slot q, frame fr): 8 lanes per frame.  First over the
   // phonemes within GU_NEAR frames (what is farther adds < 1.6e-18 each); a frame whose sum stays below GU_DEN_OK is far
   // from every centre, the warp then sums the whole fp32 support (tiny denominators make far phonemes matter).
-  const int fr = lane & 3, q = lane >> 2;
+  const int fr = lane & (GU_FW - 1), q = lane / GU_FW;
   const int fw = f0 + fr;                      // this lane's frame inside the tile
   const bool f_ok = fw < n_w;
   const float tf = (float)(t0 + fw);
@@ -223,10 +250,9 @@ __global__ void __launch_bounds__(GU_THREADS, 3) gaussian_upsample_kernel(const 
   auto den_over = [&](int lo, int hi) {
     float part = 0.f;
     if (f_ok)
-      for (int i = lo + q; i < hi; i += 8) { const float dl = tf - c_s[i]; part += expf(-0.01f * (dl * dl)); }
-    part += __shfl_xor_sync(0xffffffffu, part, 4);
-    part += __shfl_xor_sync(0xffffffffu, part, 8);
-    part += __shfl_xor_sync(0xffffffffu, part, 16);
+      for (int i = lo + q; i < hi; i += GU_QN) { const float dl = tf - c_s[i]; part += expf(-0.01f * (dl * dl)); }
+#pragma unroll
+    for (int o = GU_FW; o < 32; o <<= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
     return part;
   };
   float den = den_over(d_lo, d_hi);
@@ -236,8 +262,8 @@ __global__ void __launch_bounds__(GU_THREADS, 3) gaussian_upsample_kernel(const 
   // smallest denominator of the warp's frames -> how far a phoneme can sit and still reach a normalised weight of GU_SKIP
   // on one of them: exp(-0.01 D^2) / den_min >= GU_SKIP  <=>  D <= sqrt(-100 ln(GU_SKIP den_min))  (~53 frames at den ~ 1)
   float den_min = f_ok ? den : INFINITY;
-  den_min = fminf(den_min, __shfl_xor_sync(0xffffffffu, den_min, 1));
-  den_min = fminf(den_min, __shfl_xor_sync(0xffffffffu, den_min, 2));
+#pragma unroll
+  for (int o = 1; o < GU_FW; o <<= 1) den_min = fminf(den_min, __shfl_xor_sync(0xffffffffu, den_min, o));
   int a_lo = i_lo, a_hi = i_lo;                // phonemes this warp accumulates (none when it has no frame with weights)
   if (f0 < n_w) {
     const float d_cut = fminf(GU_CUT, sqrtf(-100.f * logf(GU_SKIP * den_min)) + 1.f);   // + 1 frame of slack on the bound
@@ -262,26 +288,30 @@ __global__ void __launch_bounds__(GU_THREADS, 3) gaussian_upsample_kernel(const 
     }
     const int lo = max(a_lo, c0), hi = min(min(a_hi, c0 + GU_XR), n_src);   // rows beyond n_src are zeros: nothing to add
     // normalised weights of this warp's frames, once per (frame, phoneme)
-    for (int i = lo + q; i < hi; i += 8) {
+    for (int i = lo + q; i < hi; i += GU_QN) {
       const float dl = tf - c_s[i];
       const float wv = expf(-0.01f * (dl * dl)) * inv;
       *reinterpret_cast<float2*>(w_w + (i - c0) * (2 * GU_FW) + 2 * fr) = make_float2(wv, wv);
     }
     cp_async_wait_all();
     __syncthreads();                            // x rows (all warps' copies) and, warp-locally, the weights are visible
-    for (int i = lo; i < hi; ++i) {
-      const int r = i - c0;
-      const float4 w01 = *reinterpret_cast<const float4*>(w_w + r * (2 * GU_FW));
-      const float4 w23 = *reinterpret_cast<const float4*>(w_w + r * (2 * GU_FW) + 4);
-      if (fmaxf(fmaxf(w01.x, w01.z), fmaxf(w23.x, w23.z)) < GU_SKIP) continue;   // warp-uniform
-      const float4 xa = *reinterpret_cast<const float4*>(x_s + r * 256 + lane * 4);
-      const float4 xb = *reinterpret_cast<const float4*>(x_s + r * 256 + 128 + lane * 4);
+    const float* wr = w_w + (lo - c0) * (2 * GU_FW);
+    const float* xr = x_s + (lo - c0) * 256 + lane * 4;
+#pragma unroll 2
+    for (int i = lo; i < hi; ++i, wr += 2 * GU_FW, xr += 256) {
+      const float4 xa = *reinterpret_cast<const float4*>(xr);
+      const float4 xb = *reinterpret_cast<const float4*>(xr + 128);
       const float2 xp[4] = {make_float2(xa.x, xa.y), make_float2(xa.z, xa.w), make_float2(xb.x, xb.y), make_float2(xb.z, xb.w)};
-      const float2 wp[GU_FW] = {make_float2(w01.x, w01.y), make_float2(w01.z, w01.w), make_float2(w23.x, w23.y), make_float2(w23.z, w23.w)};
 #pragma unroll
-      for (int j = 0; j < GU_FW; ++j)
+      for (int j2 = 0; j2 < GU_FW / 2; ++j2) {
+        const float4 wq = *reinterpret_cast<const float4*>(wr + 4 * j2);     // (w, w) of frames 2 j2 and 2 j2 + 1
+        const float2 wa = make_float2(wq.x, wq.y), wb = make_float2(wq.z, wq.w);
 #pragma unroll
-        for (int p2 = 0; p2 < 4; ++p2) acc[j][p2] = __ffma2_rn(wp[j], xp[p2], acc[j][p2]);
+        for (int p2 = 0; p2 < 4; ++p2) {
+          acc[2 * j2][p2] = __ffma2_rn(wa, xp[p2], acc[2 * j2][p2]);
+          acc[2 * j2 + 1][p2] = __ffma2_rn(wb, xp[p2], acc[2 * j2 + 1][p2]);
+        }
+      }
     }
   }
 #pragma unroll
@@ -293,8 +323,7 @@ __global__ void __launch_bounds__(GU_THREADS, 3) gaussian_upsample_kernel(const 
   // weights inside the fp32 support, zeros outside it)
   if (a.w_out) {
     __syncthreads();                            // inv_s of every warp
-    const int f = lane;                         // GU_TF == 32: lane = frame
-    if (f < n_w) {
+    for (int f = lane; f < n_w; f += 32) {      // lane = frame: 128-byte rows of w
       const float tfw = (float)(t0 + f), invf = inv_s[f];
       for (int i = warp; i < L; i += GU_WARPS) {
         float wv = 0.f;
