@@ -447,6 +447,29 @@ def run_b200_arm(args):
                 v["value"] = frames / (v["ms_per_step"] * 1e-3)
         extra["gathered"]["bytes_to_rank0"] = int(2 * (B_tot - per if rank == 0 else 0) * T * 80 * 4)
 
+    # N = 1 only: the multi-GPU workload (c4: ONE batch of 1024 utterances) on this single GPU, one forward at a time exactly
+    # like a rank of the sharded run -- the denominator of strong-scaling efficiency for the N > 1 lines of this bench
+    scaling_ref = None
+    if world == 1 and args.workload != "c4" and not args.no_scaling_ref:
+        sp4, tx4, sl4, L4 = make_batch("c4")
+        d4 = tuple(t.to(dev) for t in (sp4, tx4, sl4))
+        o4 = None
+
+        def step_c4():
+            nonlocal o4
+            o4 = model.forward_with_info(*d4, L4)[0]
+
+        for _ in range(3):
+            step_c4()
+        torch.cuda.synchronize(dev)
+        frames4 = int(o4[9].sum().item())
+        ms4 = statistics.median([bracket(step_c4, max(5, steps // 2)) for _ in range(3)])
+        scaling_ref = {"workload": "c4", "global_batch": int(tx4.shape[0]), "frames_per_step": frames4, "ms_per_step": ms4,
+                       "value": frames4 / (ms4 * 1e-3), "unit": UNIT,
+                       "note": "the N > 1 default workload (one batch of 1024 utterances) on ONE GPU, one forward at a time: "
+                               "strong-scaling efficiency at N GPUs = value(N) / (N x this value)"}
+        del o4, d4
+
     # per-kernel-class device time (tracing on, separate pass over the same steps)
     model.profile_enable(True)
     per_step_loop(step_resident, steps)
@@ -567,6 +590,8 @@ def run_b200_arm(args):
         line.update(extra)
         if graphs is not None:
             line["graphs"] = graphs
+        if scaling_ref is not None:
+            line["scaling_reference"] = scaling_ref
         if world == 1:
             line["gaussian_upsampler"] = measure_gaussian_upsampler(dev, flush, peaks)
         if world == 1 and not args.no_cpu_baseline:
@@ -591,6 +616,7 @@ def main():
                     help="default: c3 on one GPU, c4 (one batch of 1024 sharded over the ranks) on several")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-faithful", action="store_true")
+    ap.add_argument("--no-scaling-ref", action="store_true", help="skip the single-GPU c4 measurement of the N = 1 line")
     ap.add_argument("--streams", type=int, default=3,
                     help="N = 1: CUDA streams running independent forwards concurrently (1 = one forward at a time)")
     ap.add_argument("--enc", default="f16x2", choices=["fp32", "bf16x3", "f16x2", "bf16"], help="encoder + predictor arithmetic")
