@@ -357,7 +357,7 @@ def run_b200_arm(args):
     graphs = None
     if not sharded:
         # the same forward through the CUDA-graph cache (two graph launches instead of ~70 kernel launches per forward)
-        model.enable_graphs(True)
+        model.enable_graphs(True, max_rows=1 << 30)     # measured at every batch size (the module's default skips big batches)
         for _ in range(4):
             step_resident()
         torch.cuda.synchronize(dev)
@@ -475,6 +475,12 @@ def run_b200_arm(args):
     per_step_loop(step_resident, steps)
     prof = model.profile_read()
     model.profile_enable(False)
+    # segment-level tracing: ONE pair of events around the whole decoder FFT stack (the per-kernel events above break the
+    # programmatic overlap of consecutive launches and inflate the sum of the kernels by several percent)
+    model.profile_enable(2)
+    per_step_loop(step_resident, steps)
+    seg = model.profile_read()
+    model.profile_enable(False)
 
     # fp32-faithful decoder arithmetic on the same workload (one forward at a time)
     faithful = None
@@ -512,10 +518,11 @@ def run_b200_arm(args):
                 rec = j.get(args.workload, {})
                 traffic = rec.get("dec.ffn_w1_bytes_per_launch")
                 dec_layer_bytes = rec.get("decoder_layer_bytes")
-                traffic_src = j.get("source")
+                traffic_src = f"profiles/roofline_traffic.json <- {rec.get('source')} (one ncu --set full capture of this kernel at this workload)"
             except Exception:
                 traffic, dec_layer_bytes = None, None
-        dec_ms = sum(v["ms"] for n, v in prof.items() if n.startswith("dec.")) / steps
+        dec_ms_kernels = sum(v["ms"] for n, v in prof.items() if n.startswith("dec.")) / steps
+        dec_ms = seg.get("dec.fft_stack", {"ms": dec_ms_kernels * steps})["ms"] / steps     # un-perturbed: one event pair
         dec_flops = sum(t * (FLOP_DEC_FRAME + 4096 * t) for t in mel_lens_local)
         dec_tflops = dec_flops / (dec_ms * 1e-3) / 1e12 if dec_ms > 0 else 0.0
         wl = WORKLOADS[args.workload]
@@ -562,7 +569,10 @@ def run_b200_arm(args):
                                                 "frac_of_sustained": (dec_tflops / peaks["bf16_tflops_sustained"])
                                                 if peaks["bf16_tflops_sustained"] else None,
                                                 "ms_per_step": dec_ms, "algorithmic_flops_per_step": dec_flops,
-                                                "share_of_step": dec_ms * steps / total_prof},
+                                                "ms_per_step_sum_of_traced_kernels": dec_ms_kernels,
+                                                "share_of_step": dec_ms / seq_ms,
+                                                "how": "one CUDA-event pair around all 4 decoder FFT blocks (fs2_profile_enable(h, 2)), "
+                                                       "one forward at a time, L2 flushed between steps"},
                          "how": "fs2_profile_* CUDA events on the launching stream, separate traced pass of the same steps"},
             # BASELINE.json's second figure, "decoder HBM GB/s vs peak": algorithmic bytes of the 4 decoder FFT blocks
             # (16 KB per valid frame = 4 layers x 2 sub-layers x (1 KB in + 1 KB out) fp32, + 47.2 MB of

@@ -22,11 +22,14 @@ timeout 300 python scripts/sanitize_target.py > $OUT/plain.log 2>&1; echo "plain
 run memcheck ops -- ops
 run memcheck forward -- forward
 run memcheck wide_streamed -- wide streamed
+run memcheck graphs_aligner -- graphs aligner
 run synccheck ops_forward -- ops forward
 run synccheck wide -- wide
+run synccheck graphs_aligner -- graphs aligner
 run racecheck ops -- ops
 run racecheck forward --racecheck-report all -- forward
 run racecheck wide --racecheck-report all -- wide
+run racecheck aligner --racecheck-report all -- aligner
 run initcheck ops_forward -- ops forward
 for f in $OUT/*.log; do echo "=== $f"; grep -E "=========" $f | grep -vE "COMPUTE-SANITIZER|ERROR SUMMARY: 0|RACECHECK SUMMARY: 0" | head -n 30; done > $OUT/findings.txt
 head -c 6000 $OUT/findings.txt

@@ -8,6 +8,8 @@ One process = one sanitizer tool.  Each section is sized so that the instrumente
   wide     one forward at B = 24 so the 256-wide tiles, several tiles per persistent CTA and the multi-block
            attention path run as well (default precision only)
   streamed two forwards on two side streams (shared packed weights, private workspaces)
+  graphs   the CUDA-graph cache: plain launches, capture, replay of a small forward (+ the Gaussian upsampler switch)
+  aligner  the training-side aligner forward (Prenet, cross-attention kernel, FFN) in fp32 and f16x2 GEMM arithmetic
 Outputs are compared with the CPU oracle, so a sanitizer-clean run that computes garbage still fails."""
 import os
 import sys
@@ -23,7 +25,7 @@ import smart_nar_fast_tts_b200 as pkg  # noqa: E402
 from helpers import build_model  # noqa: E402
 
 dev = torch.device("cuda", 0)
-which = set(sys.argv[1:]) or {"ops", "forward", "wide", "streamed"}
+which = set(sys.argv[1:]) or {"ops", "forward", "wide", "streamed", "graphs", "aligner"}
 lib = pkg.load_library()
 st = lambda: torch.cuda.current_stream().cuda_stream  # noqa: E731
 
@@ -75,7 +77,7 @@ def main():
     sd = O.make_state_dict(0)
     if "ops" in which:
         section_ops()
-    if which & {"forward", "wide", "streamed"}:
+    if which & {"forward", "wide", "streamed", "graphs"}:
         with np.errstate(invalid="ignore"):
             m = build_model(sd, O.STATS_NAN_BINS)
     if "forward" in which:
@@ -98,6 +100,48 @@ def main():
             ref = O.forward(sd, O.Dims(), sp.cpu(), tx.cpu(), sl.cpu(), L)
             assert torch.equal(got[5].cpu() + 0, ref[5] + 0)
         print("streamed ok")
+    if "graphs" in which:
+        section_graphs(m, sd)
+    if "aligner" in which:
+        section_aligner()
+
+
+def section_graphs(m, sd):
+    m.set_precision("f16x2", "bf16")
+    cases = [O.make_inputs(3, 6, 24, seed=20 + i) for i in range(2)]
+    for ups in ("hard", "gaussian"):
+        m.set_upsampler(ups).enable_graphs(False)
+        want = []
+        for sp, tx, sl, L in cases:
+            want.append([t.clone() if t is not None else None for t in m(sp.to(dev), tx.to(dev), sl.to(dev), L)])
+        m.enable_graphs(True)
+        for rnd in range(3):
+            for (sp, tx, sl, L), w in zip(cases, want):
+                got = m(sp.to(dev), tx.to(dev), sl.to(dev), L)
+                torch.cuda.synchronize()
+                assert all(a is None or torch.equal(a, b) for a, b in zip(w[:10], got[:10])), (ups, rnd)
+        assert m.graph_stats()["replays"] > 0
+    m.set_upsampler("hard").enable_graphs(False)
+    print("graphs ok")
+
+
+def section_aligner():
+    sd = O.make_state_dict(4, include_mel_encoder=True)
+    with np.errstate(invalid="ignore"):
+        m = build_model(sd, O.STATS_NAN_BINS)
+    g = torch.Generator().manual_seed(2)
+    B, L, T = 2, 70, 90
+    src_lens, mel_lens = torch.tensor([70, 33]), torch.tensor([61, 90])
+    sm, tm = O.get_mask_from_lengths(src_lens, L), O.get_mask_from_lengths(mel_lens, T)
+    src = torch.randn(B, L, 256, generator=g).masked_fill(sm.unsqueeze(-1), 0)
+    mels = torch.randn(B, T, 80, generator=g).masked_fill(tm.unsqueeze(-1), 0)
+    ref_out, ref_attn = O.mel_encoder(sd, O.Dims(), src, mels, sm, tm)
+    for prec, tol in (("fp32", 2e-4), ("f16x2", 2e-4)):
+        out, attns = m.mel_encoder_forward(src.to(dev), mels.to(dev), sm.to(dev), tm.to(dev), True, precision=prec)
+        torch.cuda.synchronize()
+        assert float((out.cpu() - ref_out).abs().max()) < tol, prec
+        assert float((attns[-1].cpu() - ref_attn[-1]).abs().max()) < 2e-5, prec
+    print("aligner ok")
 
 
 main()

@@ -99,7 +99,7 @@ struct fs2_handle {
   int* host_tmax = nullptr;                            // pinned
   cudaStream_t fill_stream = nullptr;                  // zero-fill of fresh workspace (see ensure)
   // tracing: per-kernel-class device time from CUDA events on the launching stream (fs2_profile_*)
-  bool prof_on = false;
+  int prof_on = 0;   // 0 off, 1 every kernel class bracketed by events, 2 only whole segments (encoder / decoder stack, ...)
   struct ProfPending { int slot; cudaEvent_t a, b; };
   std::vector<ProfPending> prof_pending;
   std::vector<cudaEvent_t> prof_pool;
@@ -208,8 +208,8 @@ namespace {
 // Times everything enqueued on `st` during its lifetime under `name` when tracing is enabled (otherwise free).
 struct ProfScope {
   fs2_handle* h; cudaStream_t st; int slot = -1; cudaEvent_t a = nullptr; long long l0 = 0;
-  ProfScope(fs2_handle* h_, const std::string& name, cudaStream_t st_) : h(h_), st(st_) {
-    if (!h || !h->prof_on) return;
+  ProfScope(fs2_handle* h_, const std::string& name, cudaStream_t st_, int mode = 1) : h(h_), st(st_) {
+    if (!h || h->prof_on != mode) return;
     slot = h->prof_slot(name);
     a = h->prof_event();
     l0 = g_fs2_launches;
@@ -224,6 +224,7 @@ struct ProfScope {
   }
 };
 #define PROF(name) ProfScope _prof_scope(h, name, st)
+#define PROF_SEG(name) ProfScope _prof_seg(h, name, st, 2)   /* segment-level tracing (mode 2): no events between the kernels inside */
 
 const float* raw_ptr(fs2_handle* h, const std::string& k) {
   auto it = h->w->raw.find(k);
@@ -439,6 +440,7 @@ int run_fft_stack(fs2_handle* h, std::vector<FftW>& Ls, int l0, int l1, int prec
   const int D = h->dims.d_model, F = h->dims.d_ffn, H = h->dims.n_heads, dk = D / H;
   const size_t R = (size_t)lay.R_cap;
   const std::string tg = (&Ls == &h->w->enc) ? "enc." : "dec.";
+  PROF_SEG(tg + "fft_stack");
   WS(float, y, "fft.y", R * D);
   if (prec == FS2_PREC_FP32) {
     WS(float, qkv, "fft.qkv", R * 3 * D);
@@ -571,6 +573,7 @@ int run_mel_postnet(fs2_handle* h, int prec, const float* dec, const bf16* decb,
   const int H = NL * ((h->dims.pn_kernel - 1) / 2);
   const bool tc = prec != FS2_PREC_FP32;
   const size_t np = (size_t)planes_of(prec);
+  PROF_SEG("mel_postnet");
   RowLayout pn;
   // never fewer rows than the source layout carries (mel_linear scatters every source grid row into this grid)
   const int keep = !lay.lens ? T : (h->halo_keep > 2 * H ? h->halo_keep : 2 * H);
@@ -1306,7 +1309,8 @@ int fs2_graph_stats(const fs2_handle* h, int64_t* n_graphs, int64_t* replays, in
 // tracing
 int fs2_profile_enable(fs2_handle* h, int32_t on) {
   if (!h) return FS2_ERR_INVALID;
-  h->prof_on = on != 0;
+  if (on < 0 || on > 2) return h->fail(FS2_ERR_INVALID, "profile_enable: 0 = off, 1 = per kernel class, 2 = per segment");
+  h->prof_on = on;
   return FS2_OK;
 }
 

@@ -180,6 +180,7 @@ class FastSpeech2Align(nn.Module):
         # CUDA-graph mode (enable_graphs): bucket policies and, per (stream, B, bucket), the static output buffers whose
         # addresses the captured graphs bake in
         self._graphs = False
+        self._graph_max_rows = 8192
         self._graph_bufs = {}
         # construction order mirrors fastspeech2_align.py:20-28 so that default initialisation consumes the
         # torch RNG in the same order as the reference
@@ -274,7 +275,7 @@ class FastSpeech2Align(nn.Module):
         step = 64 if T <= 512 else 128 if T <= 2048 else 512
         return -(-T // step) * step
 
-    def enable_graphs(self, on: bool = True) -> "FastSpeech2Align":
+    def enable_graphs(self, on: bool = True, max_rows: int = 8192) -> "FastSpeech2Align":
         """Run the forward as two CUDA-graph launches (stage 1 keyed on (B, L bucket), stage 2 on (B, L bucket, T bucket))
         instead of ~70 kernel launches: what the reference's per-batch loop (synthesize.py:59-76) costs at small batch is
         launch latency.  Results are bit-identical to the plain path (the true L / T reach the kernels through device
@@ -284,8 +285,12 @@ class FastSpeech2Align(nn.Module):
         one set per (stream, batch size, bucket).  They stay valid until the next forward on the same stream that falls
         into the same bucket; consume (or `.clone()`) them before that -- `pipeline.synthesize` and
         `StreamedSynthesizer` jobs with a `post` hook do.  Not used by the sharded path (t_max hooks) or with an
-        output_allocator.  The first forward of a new key runs plain launches, the second captures, later ones replay."""
+        output_allocator.  The first forward of a new key runs plain launches, the second captures, later ones replay.
+        Batches with more than `max_rows` phoneme rows (B * L) keep the plain path: there the launches are hidden behind
+        the kernels anyway and a replayed graph, whose tile shapes were chosen for its bucket's upper bound instead of the
+        batch at hand, measured 4 % SLOWER at batch 256 (batch 1: 1.01 -> 0.97 ms, batch 32: 1.72 -> 1.69 ms)."""
         self._graphs = bool(on)
+        self._graph_max_rows = int(max_rows)
         if not on:
             self._graph_bufs = {}
         return self
@@ -470,7 +475,8 @@ class FastSpeech2Align(nn.Module):
             pass
 
     # tracing (fs2_profile_*): per-kernel-class device time, CUDA events on the launching stream
-    def profile_enable(self, on: bool = True, reset: bool = True) -> None:
+    def profile_enable(self, on=True, reset: bool = True) -> None:
+        """on: False / True (every kernel class) / 2 (whole segments only: "enc.fft_stack", "dec.fft_stack", "mel_postnet")."""
         if self._handle is None:
             raise RuntimeError("profile_enable needs an engine: run one forward first")
         lib = load_library()
@@ -548,7 +554,8 @@ class FastSpeech2Align(nn.Module):
         texts = texts.long().contiguous()
         src_lens_in = src_lens.to(device=dev, dtype=torch.long).contiguous()
         stream = torch.cuda.current_stream(dev).cuda_stream
-        if self._graphs and self.t_max_device_hook is None and self.t_max_hook is None and self.output_allocator is None:
+        if (self._graphs and B * L <= self._graph_max_rows and self.t_max_device_hook is None and self.t_max_hook is None
+                and self.output_allocator is None):
             with torch.cuda.device(dev):
                 return self._forward_graphed(lib, h, texts, src_lens_in, src_lens, B, L, p_control, e_control, dev, stream)
         f32 = dict(device=dev, dtype=torch.float32)
