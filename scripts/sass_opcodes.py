@@ -15,7 +15,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "smart-nar_fast_tts_b200", "libfs2_b200.so")
 OPS = ["UTCHMMA", "UTCQMMA", "LDTM", "STTM", "UTMALDG", "UTMASTG", "UTCBAR", "SYNCS", "ACQBULK", "PREEXIT", "LDGSTS", "UBLKCP",
-       "HMMA", "FFMA", "MUFU"]
+       "HMMA", "FFMA2", "FFMA", "MUFU"]
 
 
 def kernel_name(demangled: str) -> str:

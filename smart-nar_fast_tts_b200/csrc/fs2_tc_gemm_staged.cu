@@ -104,7 +104,10 @@ tc_conv_gemm_staged_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
   const int KB = (a.K + BKE - 1) / BKE;
   const int ncombo = a.planes == 3 ? 6 : a.planes == 2 ? 3 : 1;
   const int iters = a.taps * KB;
-  const float asc = a.acc_scale;
+  // pinned in a register: as a plain read of the parameter block the compiler re-loads it from the constant bank next to
+  // every use inside the (issue-bound) epilogue loops -- 31 LDC per 32-column chunk in the r2l capture of dec.qkv
+  float asc;
+  asm volatile("mov.f32 %0, %1;" : "=f"(asc) : "f"(a.acc_scale));
   const bool ln = (a.epi == EPI_RES_LN || a.epi == EPI_RELU_LN);
 
   griddep_launch_dependents();   // PDL (fs2_common.cuh)
@@ -225,6 +228,16 @@ tc_conv_gemm_staged_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
     int as = 0; uint32_t aphase = 0;
     uint32_t tile_par = 0;
     uint32_t xphase = 0;                            // bit i = phase of peer-statistics barrier i
+
+    // 32 per-column parameters (bias / gamma / beta slice of a chunk) from shared memory as 8 vector loads (they were 32
+    // scalar broadcast loads per chunk and parameter)
+    auto ld_cols = [&](const float* p, float (&o)[32]) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4 t4 = *reinterpret_cast<const float4*>(p + 4 * j);
+        o[4 * j] = t4.x; o[4 * j + 1] = t4.y; o[4 * j + 2] = t4.z; o[4 * j + 3] = t4.w;
+      }
+    };
 
     // Stage one 32-column chunk (index c within the group's half) of this thread's row and ship it.
     //   wf: fp32 tile via tmOutF, staged in F[c & 1]; wb: bf16 plane tiles via mapB, staged in B (or, when bF, in F[c & 1]).
@@ -383,9 +396,11 @@ tc_conv_gemm_staged_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
 #pragma unroll
             for (int j = 0; j < 32; ++j) rr[j] = 0.f;
           }
+          float bb[32];
+          ld_cols(my_bias + c * 32, bb);
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
-            float x = fmaf(__uint_as_float(v[j]), asc, my_bias[c * 32 + j]) + rr[j];
+            float x = fmaf(__uint_as_float(v[j]), asc, bb[j]) + rr[j];
             if (!has_res) x = fmaxf(x, 0.f);
             psum[c >> 1] += x;
             psq[c >> 1] = fmaf(x, x, psq[c >> 1]);
@@ -438,10 +453,12 @@ tc_conv_gemm_staged_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
           __syncwarp();
           tmem_ld32(t_row + c * 32, v);
           tmem_wait_ld();
-          float y[32];
+          float y[32], gg[32], be[32];
+          ld_cols(my_g + c * 32, gg);
+          ld_cols(my_b + c * 32, be);
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
-            const float x = (__uint_as_float(v[j]) - mean) * rstd * my_g[c * 32 + j] + my_b[c * 32 + j];
+            const float x = (__uint_as_float(v[j]) - mean) * rstd * gg[j] + be[j];
             y[j] = keep ? x : 0.f;
           }
           stage_out(y, c, n0 + gc0 + c * 32, r0, a.out != nullptr, a.out_b != nullptr, false, &tmOutB0);
@@ -453,9 +470,13 @@ tc_conv_gemm_staged_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
           __syncwarp();
           tmem_ld32(t_row + c * 32, v);
           tmem_wait_ld();
-          float y[32];
+          float y[32], bb[32];
+          ld_cols(my_bias + c * 32, bb);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) y[j] = in_grid ? fmaf(__uint_as_float(v[j]), asc, my_bias[c * 32 + j]) : 0.f;
+          for (int j = 0; j < 32; ++j) {
+            const float x = fmaf(__uint_as_float(v[j]), asc, bb[j]);
+            y[j] = in_grid ? x : 0.f;
+          }
           if (part < 2) {
             stage_out(y, c, pc0 + c * 32, r0, false, true, true, part == 0 ? &tmOutB0 : &tmOutB1);
           } else {
@@ -490,10 +511,11 @@ tc_conv_gemm_staged_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
           __syncwarp();
           tmem_ld32(t_row + c * 32, v);
           tmem_wait_ld();
-          float y[32];
+          float y[32], bb[32];
+          ld_cols(my_bias + c * 32, bb);
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
-            float x = fmaf(__uint_as_float(v[j]), asc, my_bias[c * 32 + j]);
+            float x = fmaf(__uint_as_float(v[j]), asc, bb[j]);
             if (a.epi == EPI_RELU) x = fmaxf(x, 0.f);
             if (a.epi == EPI_TANH) x = tanhf(x);
             y[j] = keep ? x : 0.f;
