@@ -121,7 +121,8 @@ tc_conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const int KB = (a.K + BKE - 1) / BKE;
   const int ncombo = a.planes == 3 ? 6 : a.planes == 2 ? 3 : 1;
   const int iters = a.taps * KB;
-  const float asc = a.acc_scale;
+  float asc;   // pinned in a register (see fs2_tc_gemm_staged.cu: the compiler otherwise re-loads it from the constant bank per use)
+  asm volatile("mov.f32 %0, %1;" : "=f"(asc) : "f"(a.acc_scale));
   constexpr uint32_t TMEM_COLS = 2 * BN;  // 512 or 256: power of two
 
   griddep_launch_dependents();   // PDL: the next kernel may start its own prologue while this one runs
@@ -251,9 +252,11 @@ tc_conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             float4 rv = make_float4(0.f, 0.f, 0.f, 0.f);
             if (res) rv = ld_act(reinterpret_cast<const float4*>(res + j));
             const float rr[4] = {rv.x, rv.y, rv.z, rv.w};
+            const float4 b4 = *reinterpret_cast<const float4*>(s_bias + c * 32 + j);
+            const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-              float x = fmaf(__uint_as_float(v[j + u]), asc, s_bias[c * 32 + j + u]) + rr[u];
+              float x = fmaf(__uint_as_float(v[j + u]), asc, bb[u]) + rr[u];
               if (a.epi != EPI_RES_LN) x = fmaxf(x, 0.f);
               sum += x;
               sq = fmaf(x, x, sq);
@@ -299,7 +302,15 @@ tc_conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           tmem_wait_ld();
           float y[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) y[j] = ri.in_grid ? fmaf(__uint_as_float(v[j]), asc, s_bias[c * 32 + j]) : 0.f;
+          for (int j = 0; j < 32; j += 4) {
+            const float4 b4 = *reinterpret_cast<const float4*>(s_bias + c * 32 + j);
+            const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const float x = fmaf(__uint_as_float(v[j + u]), asc, bb[u]);
+              y[j + u] = ri.in_grid ? x : 0.f;
+            }
+          }
           if (ri.in_buf && n_blk < 2) {
             bf16* o = (n_blk == 0 ? a.q_b : a.k_b) + (size_t)ri.r * 256 + c * 32;
 #pragma unroll
@@ -321,11 +332,16 @@ tc_conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           const int nb = n0 + c * 32;
           float y[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            float x = fmaf(__uint_as_float(v[j]), asc, s_bias[c * 32 + j]);
-            if (a.epi == EPI_RELU) x = fmaxf(x, 0.f);
-            if (a.epi == EPI_TANH) x = tanhf(x);
-            y[j] = x;
+          for (int j = 0; j < 32; j += 4) {
+            const float4 b4 = *reinterpret_cast<const float4*>(s_bias + c * 32 + j);
+            const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              float x = fmaf(__uint_as_float(v[j + u]), asc, bb[u]);
+              if (a.epi == EPI_RELU) x = fmaxf(x, 0.f);
+              if (a.epi == EPI_TANH) x = tanhf(x);
+              y[j + u] = x;
+            }
           }
           if (a.epi == EPI_RES && ri.in_buf) {
 #pragma unroll
