@@ -151,3 +151,20 @@ def test_synthesize_pipeline_with_graphs(lib):
                         assert np.array_equal(getattr(a, name)[i], getattr(b, name)[i]), (rnd, k, i, name)
         st = m.graph_stats()
     assert st["replays"] > 0 and st["captures"] > 0, st
+
+
+def test_graph_path_phoneme_level_features(lib):
+    """pitch / energy predicted per phoneme (preprocess.yaml feature: phoneme_level): their outputs are [B, L] tensors
+    written by stage 1 and the stage-2 graph gets no pitch / energy pointers."""
+    d = O.Dims(pitch_feature="phoneme_level", energy_feature="phoneme_level", pitch_quantization="linear")
+    sd = O.make_state_dict(2, d)
+    m = build_model(sd, O.STATS_NAN_BINS, "linear", pitch_feature="phoneme_level", energy_feature="phoneme_level")
+    m.set_precision("fp32", "fp32")
+    cases = [O.make_inputs(4, 6, 25, seed=9 + i) for i in range(3)]
+    plain = [run(m, c) for c in cases]
+    assert plain[0][2].shape == (4, cases[0][3])
+    m.enable_graphs(True)
+    for rnd in range(3):
+        for i, c in enumerate(cases):
+            assert_same(run(m, c), plain[i], f"phoneme-level round {rnd} case {i}")
+    assert m.graph_stats()["replays"] > 0

@@ -162,6 +162,25 @@ def test_gaussian_upsample_c5_shape_and_edge_cases(lib):
     assert bool((out[:, T_w:] == 0).all())
 
 
+def test_gaussian_upsample_long_utterance(lib):
+    """1500 phonemes in one utterance: three levels of the 32-ary band search, more staged-row chunks than one per tile
+    where runs of zero-duration phonemes pile up on one centre."""
+    rng = np.random.Generator(np.random.PCG64(8))
+    B, L = 2, 1500
+    x = torch.from_numpy(rng.standard_normal((B, L, 256)).astype(np.float32))
+    d = torch.from_numpy(rng.integers(0, 4, size=(B, L)).astype(np.float32))
+    d[1, 400:520] = 0.0                                                  # 120 phonemes on one centre
+    ref, ref_s, ref_w = O.gaussian_upsample(x, d, None)
+    T_w = ref.shape[1]
+    out = torch.empty(B, T_w, 256, device=DEV)
+    s = torch.empty(B, device=DEV)
+    w = torch.empty(B, L, T_w, device=DEV)
+    lib.check(lib.fs2_gaussian_upsample(x.to(DEV).data_ptr(), d.to(DEV).data_ptr(), B, L, 256, T_w, T_w, out.data_ptr(),
+                                        s.data_ptr(), w.data_ptr(), stream()))
+    assert torch.equal(s.cpu(), ref_s.flatten())
+    assert max_abs(w.cpu(), ref_w) < 2e-6 and max_abs(out.cpu(), ref) < 1e-4
+
+
 def test_sinusoid_table(lib, oph):
     n = 1300
     out = torch.empty(n, 256, device=DEV)
