@@ -1164,6 +1164,8 @@ int fs2_forward_stage2(fs2_handle* h, int32_t T, float p_control, float e_contro
 // Returns FS2_OK with *replayed = true when the work went out as a graph launch (no host-side stage code ran).
 template <typename F>
 static int run_graphed(fs2_handle* h, const std::string& key, cudaStream_t st, bool* replayed, F&& enqueue) {
+  // bounded cache: a long-running service with many (B, bucket) combinations starts over instead of growing for ever
+  if (h->graphs.size() >= 512 && !h->graphs.count(key)) h->drop_graphs();
   fs2_handle::GraphEntry& e = h->graphs[key];
   *replayed = false;
   if (e.exec && e.gen == h->gen) {
